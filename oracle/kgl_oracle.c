@@ -1,0 +1,343 @@
+/* kgl_oracle.c -- TEST INFRASTRUCTURE (see kgl_oracle.h). Plain-C restatement of the reference algorithms on the
+ * flattened population. Compiled with -ffp-contract=off so every double operation rounds exactly like the
+ * reference's (g++ -O3 on x86-64 does not contract either). OpenMP over genomes mirrors the reference's only
+ * parallelism: one task per genome (kga_analysis_inbreed_diploid.cpp:117-150).
+ *
+ * Every function cites the reference file:line it follows; all paths are relative to /root/reference. */
+#include "kgl_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int kgl_oracle_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static inline unsigned cell_code(const uint8_t* packed, size_t row_bytes, size_t locus, size_t genome) {
+  const uint8_t* unit = packed + locus * row_bytes + (genome / 64) * 16;
+  uint64_t lo, hi;
+  memcpy(&lo, unit, 8);
+  memcpy(&hi, unit + 8, 8);
+  const unsigned bit = (unsigned)(genome % 64);
+  return (unsigned)((lo >> bit) & 1u) | ((unsigned)((hi >> bit) & 1u) << 1);
+}
+
+static inline double clamp01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }
+
+/* AlleleFreqVector ctor + checkValidAlleleVector for ONE alternate allele
+ * (kga_analysis_inbreed_freq.cpp:18-57,61-75): the frequency is the INFO float widened to double and clamped to
+ * [0,1] (:47); the vector is valid iff it is non-empty (AF present) and sum - 1 <= 1e-5 (always true after clamp). */
+static inline int allele_valid(float af, double* p) {
+  if (isnan(af)) return 0;
+  *p = clamp01((double)af);
+  return 1;
+}
+
+/* majorAlleleFrequency(): clamp(1 - clamp(sum,0,1), 0, 1)  (kga_analysis_inbreed_freq.cpp:113-123). */
+static inline double major_freq(double p) { return clamp01(1.0 - clamp01(p)); }
+
+size_t kgl_oracle_select_loci(const uint32_t* offsets, const float* af, size_t n_loci,
+                              uint64_t lower, uint64_t upper, uint64_t spacing, uint64_t count,
+                              double min_af, double max_af, int mode, uint8_t* selected, size_t* last_index) {
+  /* kga_analysis_inbreed_locus.cpp:21-72 (FromTo) and :105-156 (Count). */
+  size_t n_selected = 0;
+  uint64_t previous_offset = 0;
+  memset(selected, 0, n_loci);
+  size_t l = 0;
+  while (l < n_loci && offsets[l] < lower) ++l;             /* getMap().lower_bound(lowerOffset)  (:26,:110) */
+  for (; l < n_loci; ++l) {
+    const uint64_t offset = offsets[l];
+    if (mode == 0) { if (offset > upper) break; }             /* :33 */
+    else { if (n_selected >= count) break; }                  /* :117 */
+    if (offset >= previous_offset + spacing || previous_offset == 0) {   /* :38,:122 */
+      double p;
+      if (!allele_valid(af[l], &p)) continue;                /* :44,:128 */
+      const double sum_frequencies = clamp01(p);             /* minorAlleleFrequencies()  :51 */
+      if (sum_frequencies == 0.0 || sum_frequencies < min_af || sum_frequencies > max_af) continue;   /* :53-54 */
+      previous_offset = offset;                              /* :61 */
+      selected[l] = 1;
+      if (last_index) *last_index = l;
+      ++n_selected;
+    }
+  }
+  return n_selected;
+}
+
+/* One classified locus of one genome: the information AlleleFreqInfo carries for the estimators. */
+typedef struct { uint8_t cls; double first, second; } locus_term;
+enum { CLS_MAJOR_HOM = 0, CLS_MAJOR_HET = 1, CLS_MINOR_HET = 2, CLS_MINOR_HOM = 3 };
+
+/* generateFrequencies (kga_analysis_inbreed_freq.cpp:425-583) for one genome; returns the number of classified loci. */
+static size_t generate_frequencies(const uint8_t* packed, size_t row_bytes, size_t n_loci, size_t genome,
+                                   const float* af_pop, const uint8_t* sel_pop, int unphased,
+                                   locus_term* terms, kgl_oracle_locus_results* r) {
+  size_t n = 0;
+  memset(r, 0, sizeof *r);
+  for (size_t l = 0; l < n_loci; ++l) {
+    if (!sel_pop[l]) continue;                               /* locus_list holds only the selected loci (:439) */
+    double p;
+    if (!allele_valid(af_pop[l], &p)) continue;              /* :445-449 */
+    const double q = major_freq(p);
+    const unsigned code = cell_code(packed, row_bytes, l, genome);
+    locus_term t;
+    if (code == 0) {                                         /* no variant at the offset (:521-541) */
+      if (!(q > 0.01)) continue;                             /* minimum_major_frequency (:532-533) */
+      t.cls = CLS_MAJOR_HOM; t.first = q; t.second = q;
+    } else if (code == 1) {                                  /* one copy: MAJOR_HETEROZYGOUS (:464-472) */
+      t.cls = CLS_MAJOR_HET; t.first = p; t.second = q;
+    } else if (code == 2) {
+      if (unphased) { t.cls = CLS_MINOR_HET; t.first = p; t.second = p; }   /* Q6: homozygous() needs differing phase (:476,:482-511) */
+      else { t.cls = CLS_MINOR_HOM; t.first = p; t.second = p; }            /* :476-479 */
+    } else {
+      continue;                                              /* allele not in the AF list etc.: dropped (:462 never matches) */
+    }
+    terms[n++] = t;
+
+    /* Statistics block (:549-579): alleleClassFrequencies(0.0) = unadjusted (:127-205) then normalize() (freq.h:54-63). */
+    const double inbreeding = 0.0;
+    const double sum_minor_freq = p;
+    const double major_frequency = fmax(0.0, 1.0 - sum_minor_freq);        /* :140 */
+    const double minor_frequency = (sum_minor_freq > 1.0) ? p / sum_minor_freq : p;   /* :143-151 */
+    double minor_homozygous = 0.0;
+    minor_homozygous += (inbreeding * minor_frequency) + ((1.0 - inbreeding) * minor_frequency * minor_frequency);   /* :158 */
+    double minor_heterozygous = 0.0;                          /* one allele: no pairs (:166-174) */
+    double major_homozygous = (inbreeding * major_frequency) + ((1.0 - inbreeding) * major_frequency * major_frequency); /* :176 */
+    double major_heterozygous = 0.0;
+    major_heterozygous += (1.0 - inbreeding) * 2.0 * major_frequency * minor_frequency;   /* :181 */
+    major_homozygous = fmax(0.0, major_homozygous);           /* nonNegative() */
+    major_heterozygous = fmax(0.0, major_heterozygous);
+    minor_homozygous = fmax(0.0, minor_homozygous);
+    minor_heterozygous = fmax(0.0, minor_heterozygous);
+    const double sum_freqs = major_homozygous + major_heterozygous + minor_homozygous + minor_heterozygous;
+    r->major_homo_freq += major_homozygous / sum_freqs;       /* :553-556 */
+    r->minor_homo_freq += minor_homozygous / sum_freqs;
+    r->major_hetero_freq += major_heterozygous / sum_freqs;
+    r->minor_hetero_freq += minor_heterozygous / sum_freqs;
+    switch (t.cls) {                                          /* :559-577 */
+      case CLS_MINOR_HOM: ++r->minor_homo_count; break;
+      case CLS_MAJOR_HET: ++r->major_hetero_count; break;
+      case CLS_MINOR_HET: ++r->minor_hetero_count; break;
+      default: ++r->major_homo_count; break;
+    }
+  }
+  r->total_allele_count = n;                                  /* :548 */
+  return n;
+}
+
+/* InbreedingCalculation::logLikelihood (kga_analysis_inbreed_calc.cpp:94-129). */
+static double log_likelihood(double f, const locus_term* terms, size_t n) {
+  double log_prob_sum = 0.0;
+  const double small_prob = 1e-10;
+  for (size_t i = 0; i < n; ++i) {
+    double prob;
+    if (terms[i].cls == CLS_MAJOR_HOM || terms[i].cls == CLS_MINOR_HOM) {
+      const double freq_sqd = terms[i].first * terms[i].first;
+      prob = (f * terms[i].first) + ((1.0 - f) * freq_sqd);
+    } else {
+      prob = 2 * (1.0 - f) * terms[i].first * terms[i].second;
+    }
+    prob = prob < small_prob ? small_prob : (prob > 1.0 ? 1.0 : prob);
+    log_prob_sum += log(prob);
+  }
+  return log_prob_sum;
+}
+
+/* The converged argmax of logLikelihood over the optimiser's box [-1,1] (kga_analysis_inbreed_calc.cpp:131-143).
+ * The reference reaches it with nlopt Nelder-Mead to xtol 1e-6 from a random start (Q1,Q2); parity is defined
+ * against the optimum itself: global scan to bracket, then golden-section refinement to 1e-13. */
+static double log_likelihood_argmax(const locus_term* terms, size_t n) {
+  if (n == 0) return 0.0;
+  const int grid = 400;
+  int best = 0;
+  double best_val = -INFINITY;
+  for (int i = 0; i <= grid; ++i) {
+    const double f = -1.0 + 2.0 * i / grid;
+    const double v = log_likelihood(f, terms, n);
+    if (v > best_val) { best_val = v; best = i; }
+  }
+  double a = -1.0 + 2.0 * (best > 0 ? best - 1 : 0) / grid;
+  double b = -1.0 + 2.0 * (best < grid ? best + 1 : grid) / grid;
+  const double gr = 0.6180339887498949;
+  double c = b - gr * (b - a), d = a + gr * (b - a);
+  double fc = log_likelihood(c, terms, n), fd = log_likelihood(d, terms, n);
+  for (int it = 0; it < 200 && (b - a) > 1e-13; ++it) {
+    if (fc > fd) { b = d; d = c; fd = fc; c = b - gr * (b - a); fc = log_likelihood(c, terms, n); }
+    else { a = c; c = d; fc = fd; d = a + gr * (b - a); fd = log_likelihood(d, terms, n); }
+  }
+  return 0.5 * (a + b);
+}
+
+/* One EM sweep of processHallME (kga_analysis_inbreed_calc.cpp:257-285). */
+static double hall_sweep(double inbreed_coefficient, const locus_term* terms, size_t n) {
+  double expectation_sum = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    if (terms[i].cls == CLS_MAJOR_HOM || terms[i].cls == CLS_MINOR_HOM) {
+      const double denominator = (inbreed_coefficient + ((1.0 - inbreed_coefficient) * terms[i].first));
+      if (denominator != 0) expectation_sum += inbreed_coefficient / denominator;
+    }
+  }
+  return expectation_sum / (double)n;
+}
+
+void kgl_oracle_inbreed(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                        const float* af, size_t n_pop, const uint8_t* selected, const uint8_t* superpop,
+                        int unphased, int algorithm, const double* start, int sweeps,
+                        kgl_oracle_locus_results* out) {
+  (void)n_pop;
+#pragma omp parallel
+  {
+    locus_term* terms = (locus_term*)malloc(sizeof(locus_term) * (n_loci ? n_loci : 1));
+#pragma omp for schedule(dynamic, 1)
+    for (long gi = 0; gi < (long)n_genomes; ++gi) {
+      const size_t g = (size_t)gi;
+      const size_t k = superpop[g];
+      kgl_oracle_locus_results r;
+      const size_t n = generate_frequencies(packed, row_bytes, n_loci, g, af + k * n_loci, selected + k * n_loci,
+                                            unphased, terms, &r);
+      switch (algorithm) {
+        case KGL_ORACLE_SIMPLE: {                              /* processSimple (calc.cpp:319-365) */
+          double homozygous_inbreeding = 0.0;
+          if (r.total_allele_count > 0) {
+            const double observed_homozygous = (double)(r.minor_homo_count + r.major_homo_count);
+            const double expected_homozygous = r.minor_homo_freq + r.major_homo_freq;
+            homozygous_inbreeding = (observed_homozygous - expected_homozygous) / ((double)r.total_allele_count - expected_homozygous);
+          }
+          r.inbred_allele_sum = homozygous_inbreeding;
+        } break;
+        case KGL_ORACLE_RITLAND: {                             /* processRitlandLocus (calc.cpp:375-431) */
+          const double minimum_frequency = 0.001;
+          size_t sum_allele = 0;
+          double locus_allele_sum = 0.0;
+          for (size_t i = 0; i < n; ++i) {
+            if (terms[i].cls == CLS_MAJOR_HOM || terms[i].cls == CLS_MINOR_HOM) {
+              if (terms[i].first > minimum_frequency) {
+                const double ratio = (1.0 / terms[i].first);
+                locus_allele_sum += ratio;
+                locus_allele_sum -= 1.0;
+                ++sum_allele;
+              }
+            } else {
+              locus_allele_sum -= 1.0;
+              ++sum_allele;
+            }
+          }
+          r.inbred_allele_sum = (sum_allele > 0 ? locus_allele_sum / (double)sum_allele : 0.0);
+        } break;
+        case KGL_ORACLE_HALLME: {                              /* processHallME (calc.cpp:226-307); Q1: 50 sweeps */
+          double f = start ? start[g] : 0.25;
+          if (n == 0) { r.inbred_allele_sum = 0.0 / 0.0; break; }   /* 0/0 in :285, as the reference */
+          if (sweeps >= 0) {
+            for (int s = 0; s < sweeps; ++s) f = hall_sweep(f, terms, n);
+          } else {
+            for (int s = 0; s < 100000; ++s) { const double nf = hall_sweep(f, terms, n); const int done = fabs(nf - f) < 1e-15; f = nf; if (done) break; }
+          }
+          r.inbred_allele_sum = f;
+        } break;
+        default:                                               /* processLogLikelihood (calc.cpp:154-216) */
+          r.inbred_allele_sum = log_likelihood_argmax(terms, n);
+          break;
+      }
+      out[g] = r;
+    }
+    free(terms);
+  }
+}
+
+void kgl_oracle_loglik_grid(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                            const float* af, size_t n_pop, const uint8_t* selected, const uint8_t* superpop,
+                            int unphased, const double* grid, size_t n_grid, double* out) {
+  (void)n_pop;
+#pragma omp parallel
+  {
+    locus_term* terms = (locus_term*)malloc(sizeof(locus_term) * (n_loci ? n_loci : 1));
+#pragma omp for schedule(dynamic, 1)
+    for (long gi = 0; gi < (long)n_genomes; ++gi) {
+      const size_t g = (size_t)gi, k = superpop[g];
+      kgl_oracle_locus_results r;
+      const size_t n = generate_frequencies(packed, row_bytes, n_loci, g, af + k * n_loci, selected + k * n_loci, unphased, terms, &r);
+      for (size_t i = 0; i < n_grid; ++i) out[g * n_grid + i] = log_likelihood(grid[i], terms, n);
+    }
+    free(terms);
+  }
+}
+
+void kgl_oracle_allele_count(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                             uint32_t* locus_counts, uint64_t* genome_counts) {
+  /* The byte-at-a-time switch of kgl_variant_db_variant.cpp:142-163 / :196-217, on 2-bit cells. */
+  memset(locus_counts, 0, n_loci * 4 * sizeof(uint32_t));
+  memset(genome_counts, 0, n_genomes * 4 * sizeof(uint64_t));
+  for (size_t l = 0; l < n_loci; ++l)
+    for (size_t g = 0; g < n_genomes; ++g) {
+      const unsigned c = cell_code(packed, row_bytes, l, g);
+      ++locus_counts[l * 4 + c];
+      ++genome_counts[g * 4 + c];
+    }
+}
+
+void kgl_oracle_ibs(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci, uint32_t* out) {
+  uint8_t* codes = (uint8_t*)malloc(n_genomes * n_loci + 1);
+  for (size_t l = 0; l < n_loci; ++l)
+    for (size_t g = 0; g < n_genomes; ++g) codes[g * n_loci + l] = (uint8_t)cell_code(packed, row_bytes, l, g);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long ai = 0; ai < (long)n_genomes; ++ai) {
+    const size_t a = (size_t)ai;
+    for (size_t b = 0; b < n_genomes; ++b) {
+      uint32_t c[4] = {0, 0, 0, 0};
+      const uint8_t* ga = codes + a * n_loci;
+      const uint8_t* gb = codes + b * n_loci;
+      for (size_t l = 0; l < n_loci; ++l) {
+        if (ga[l] == 3 || gb[l] == 3) continue;
+        const int d = abs((int)ga[l] - (int)gb[l]);
+        ++c[2 - d];                                           /* |d|=0 -> IBS2, 1 -> IBS1, 2 -> IBS0 */
+        ++c[3];
+      }
+      memcpy(out + (a * n_genomes + b) * 4, c, sizeof c);
+    }
+  }
+  free(codes);
+}
+
+static inline uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+void kgl_oracle_synth_genotypes(uint64_t seed, size_t n_genomes, size_t n_loci, size_t locus_base,
+                                const float* af, size_t n_pop, const uint8_t* superpop,
+                                const double* inbreeding, double missing_rate, uint8_t* packed, size_t row_bytes) {
+  (void)n_pop;
+  const uint64_t miss_threshold = (uint64_t)(missing_rate * 16777216.0);
+  memset(packed, 0, n_loci * row_bytes);
+#pragma omp parallel for schedule(static)
+  for (long li = 0; li < (long)n_loci; ++li) {
+    const size_t l = (size_t)li;
+    uint8_t* row = packed + l * row_bytes;
+    for (size_t g = 0; g < n_genomes; ++g) {
+      const float a = af[(size_t)superpop[g] * n_loci + l];
+      const double p = isnan(a) ? 0.0 : clamp01((double)a);
+      const double q = 1.0 - p, F = inbreeding[g];
+      const double pq = p * q;
+      const double t0 = q * q + F * pq;
+      const double t1 = t0 + (2.0 * pq) * (1.0 - F);
+      const uint64_t h1 = mix64(seed ^ ((uint64_t)(locus_base + l) << 32) ^ (uint64_t)g);
+      const uint64_t h2 = mix64(h1 ^ 0xD6E8FEB86659FD93ULL);
+      const double u = (double)(h1 >> 11) * (1.0 / 9007199254740992.0);
+      unsigned code = (unsigned)(u >= t0) + (unsigned)(u >= t1);
+      if ((h2 >> 40) < miss_threshold) code = 3;
+      uint8_t* unit = row + (g / 64) * 16;
+      const unsigned bit = (unsigned)(g % 64);
+      if (code & 1u) unit[bit / 8] |= (uint8_t)(1u << (bit % 8));
+      if (code & 2u) unit[8 + bit / 8] |= (uint8_t)(1u << (bit % 8));
+    }
+  }
+}

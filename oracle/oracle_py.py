@@ -1,0 +1,147 @@
+"""ctypes wrapper over oracle/_build/libkgl_oracle.so and the reference harness. TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never from the
+product package (kgl_gene_b200/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libkgl_oracle.so")
+HARNESS_PATH = os.path.join(HERE, "_ref", "kgl_ref_harness")
+
+ALGORITHMS = {"Simple": 0, "RitlandLocus": 1, "HallME": 2, "Loglikelihood": 3}
+
+RESULT_DTYPE = np.dtype([  # kga::LocusResults field order (kga_analysis_inbreed_output.h:21-35)
+    ("major_hetero_count", "<u8"), ("major_hetero_freq", "<f8"),
+    ("minor_hetero_count", "<u8"), ("minor_hetero_freq", "<f8"),
+    ("minor_homo_count", "<u8"), ("minor_homo_freq", "<f8"),
+    ("major_homo_count", "<u8"), ("major_homo_freq", "<f8"),
+    ("total_allele_count", "<u8"), ("inbred_allele_sum", "<f8"),
+])
+
+_lib = None
+
+
+def build() -> None:
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.kgl_oracle_select_loci.restype = C.c_size_t
+        _lib.kgl_oracle_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def select_loci(offsets, af_pop, lower=0, upper=10**9, spacing=0, count=10**9, min_af=0.0, max_af=1.0, mode=0):
+    """RetrieveLociiVector restatement; returns (selected uint8 [L], last_index)."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    af_pop = np.ascontiguousarray(af_pop, dtype=np.float32)
+    sel = np.zeros(offsets.shape[0], dtype=np.uint8)
+    last = C.c_size_t(0)
+    lib().kgl_oracle_select_loci(_p(offsets), _p(af_pop), C.c_size_t(offsets.shape[0]), C.c_uint64(lower), C.c_uint64(upper),
+                                 C.c_uint64(spacing), C.c_uint64(count), C.c_double(min_af), C.c_double(max_af), C.c_int(mode),
+                                 _p(sel), C.byref(last))
+    return sel, int(last.value)
+
+
+def select_all_pops(pop, **kw):
+    """uint8 [6, L] selection masks, one per super-population."""
+    return np.stack([select_loci(pop.offsets, pop.af[k], **kw)[0] for k in range(pop.af.shape[0])])
+
+
+def inbreed(pop, selected, algorithm: str, start=None, sweeps: int = 50) -> np.ndarray:
+    out = np.zeros(pop.n_genomes, dtype=RESULT_DTYPE)
+    packed = np.ascontiguousarray(pop.packed)
+    af = np.ascontiguousarray(pop.af, dtype=np.float32)
+    selected = np.ascontiguousarray(selected, dtype=np.uint8)
+    sp = np.ascontiguousarray(pop.superpop, dtype=np.uint8)
+    st = None if start is None else np.ascontiguousarray(start, dtype=np.float64)
+    lib().kgl_oracle_inbreed(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci),
+                             _p(af), C.c_size_t(af.shape[0]), _p(selected), _p(sp), C.c_int(int(pop.unphased)),
+                             C.c_int(ALGORITHMS[algorithm]), None if st is None else _p(st), C.c_int(sweeps), _p(out))
+    return out
+
+
+def loglik_grid(pop, selected, grid) -> np.ndarray:
+    grid = np.ascontiguousarray(grid, dtype=np.float64)
+    out = np.zeros((pop.n_genomes, grid.shape[0]), dtype=np.float64)
+    packed = np.ascontiguousarray(pop.packed)
+    af = np.ascontiguousarray(pop.af, dtype=np.float32)
+    selected = np.ascontiguousarray(selected, dtype=np.uint8)
+    sp = np.ascontiguousarray(pop.superpop, dtype=np.uint8)
+    lib().kgl_oracle_loglik_grid(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci),
+                                 _p(af), C.c_size_t(af.shape[0]), _p(selected), _p(sp), C.c_int(int(pop.unphased)),
+                                 _p(grid), C.c_size_t(grid.shape[0]), _p(out))
+    return out
+
+
+def allele_count(pop):
+    lc = np.zeros((pop.n_loci, 4), dtype=np.uint32)
+    gc = np.zeros((pop.n_genomes, 4), dtype=np.uint64)
+    packed = np.ascontiguousarray(pop.packed)
+    lib().kgl_oracle_allele_count(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci), _p(lc), _p(gc))
+    return lc, gc
+
+
+def ibs(pop) -> np.ndarray:
+    out = np.zeros((pop.n_genomes, pop.n_genomes, 4), dtype=np.uint32)
+    packed = np.ascontiguousarray(pop.packed)
+    lib().kgl_oracle_ibs(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci), _p(out))
+    return out
+
+
+def synth_genotypes(seed, n_genomes, n_loci, af, superpop, inbreeding, missing_rate=0.001, locus_base=0) -> np.ndarray:
+    rb = 16 * ((n_genomes + 63) // 64)
+    packed = np.zeros((n_loci, rb), dtype=np.uint8)
+    af = np.ascontiguousarray(af, dtype=np.float32)
+    sp = np.ascontiguousarray(superpop, dtype=np.uint8)
+    fi = np.ascontiguousarray(inbreeding, dtype=np.float64)
+    lib().kgl_oracle_synth_genotypes(C.c_uint64(seed), C.c_size_t(n_genomes), C.c_size_t(n_loci), C.c_size_t(locus_base), _p(af),
+                                     C.c_size_t(af.shape[0]), _p(sp), _p(fi), C.c_double(missing_rate), _p(packed), C.c_size_t(rb))
+    return packed
+
+
+def threads() -> int:
+    return int(lib().kgl_oracle_threads())
+
+
+def have_reference_harness() -> bool:
+    return os.path.exists(HARNESS_PATH) and os.access(HARNESS_PATH, os.X_OK)
+
+
+def run_reference(pop, algos=("Simple", "RitlandLocus", "HallME", "Loglikelihood"), spacing=0, min_af=0.0, max_af=1.0,
+                  lower=0, upper=10**9, grid=0, threads=0, variantdb=True, seed=None, timeout=3600):
+    """Runs the reference's own code (oracle/_ref/kgl_ref_harness) on `pop`; returns the dumped arrays."""
+    from kgl_gene_b200.flatfile import read_tensors
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.flat"), os.path.join(d, "out.tens")
+        pop.write(fin)
+        cmd = [HARNESS_PATH, fin, fout, "--algos", ",".join(algos), "--spacing", str(spacing), "--min-af", repr(float(min_af)),
+               "--max-af", repr(float(max_af)), "--lower", str(lower), "--upper", str(upper), "--grid", str(grid), "--threads", str(threads)]
+        if not variantdb:
+            cmd.append("--no-variantdb")
+        if seed is not None:
+            cmd += ["--seed", str(int(seed))]
+        env = dict(os.environ, KGL_REF_LOG=os.path.join(d, "ref.log"))
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if proc.returncode != 0:
+            raise RuntimeError(f"reference harness failed ({proc.returncode}): {proc.stderr[-2000:]}")
+        out = read_tensors(fout)
+        out["_stderr"] = proc.stderr
+        return out

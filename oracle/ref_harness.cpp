@@ -1,0 +1,349 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE (oracle/_ref build only). Not part of the product.
+//
+// Drives the UNMODIFIED reference implementation of the population-genotype hot path on a flattened
+// population (oracle/flat_io.h, KGLFLAT1) and dumps what it computes (KGLTENS1):
+//
+//   * locus selection per super-population   InbreedSampling::getPopulationLocusMap
+//                                            (kga_analytic/kga_inbreed/kga_analysis_inbreed_locus.cpp:192)
+//   * the four inbreeding estimators         InbreedingCalculation::namedAlgorithm -> process{Simple,RitlandLocus,
+//                                            HallME,LogLikelihood} (kga_analysis_inbreed_calc.cpp:71,319,375,226,154),
+//                                            fanned out over the reference's own WorkflowThreads pool exactly as
+//                                            InbreedingAnalysis::processResults does (kga_analysis_inbreed_diploid.cpp:117-160)
+//   * logLikelihood(f) on a fixed grid       (kga_analysis_inbreed_calc.cpp:94, captured inside the Optimize shim)
+//   * allele summaries                       VariantDBVariant::{summaryByVariant,summaryByGenome,populationSummary}
+//                                            (kgl_genomics/kgl_variant_db/kgl_variant_db_variant.cpp:126,180,234)
+//
+// The population is rebuilt through the reference's own containers (EvidenceFactory -> VariantEvidence ->
+// Variant -> PopulationDB::addVariant), so everything downstream is reference code. It is used to
+// (a) pin the C restatement (oracle/kgl_oracle.c) and generate tests/golden/*, (b) time the reference CPU
+// path for bench.py's cpu_baseline / --impl reference.
+#include "kel_exec_env_app.h"
+#include "kel_workflow_threads.h"
+#include "kgl_variant_db_population.h"
+#include "kgl_variant_db_variant.h"
+#include "kgl_variant_db_freq.h"
+#include "kgl_variant_factory_vcf_evidence.h"
+#include "kga_analysis_inbreed_calc.h"
+#include "kga_analysis_inbreed_locus.h"
+
+#include "flat_io.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+#include <map>
+#include <random>
+#include <sstream>
+
+namespace kel = kellerberrin;
+namespace kgl = kellerberrin::genome;
+namespace kga = kellerberrin::genome::analysis;
+
+namespace kglref {
+extern thread_local std::vector<double> tl_start_points;
+extern thread_local std::vector<double> tl_end_points;
+extern thread_local std::vector<double> tl_grid_values;
+extern thread_local std::vector<size_t> tl_evals;
+extern std::vector<double> g_grid;
+extern std::atomic<bool> g_fixed_seed_enabled;
+extern unsigned g_fixed_seed;
+}  // namespace kglref
+
+namespace {
+
+struct Options {
+  std::string in_path, out_path;
+  std::vector<std::string> algos{"Simple", "RitlandLocus", "HallME", "Loglikelihood"};
+  double min_af{0.0}, max_af{1.0};
+  size_t spacing{0}, count{1000000000}, lower{0}, upper{1000000000};
+  size_t threads{0};  // 0 = reference default (hardware_concurrency - 1)
+  size_t grid{0};
+  long seed{-1};      // >= 0: std::random_device is pinned to this value (see ref_stubs.cpp)
+  bool variantdb{true};
+  bool quiet{true};
+};
+Options g_opt;
+
+const char* const kSuperPops[6] = {"AFR", "AMR", "EAS", "EUR", "SAS", "ALL"};
+// INFO field names the reference resolves for DataSourceEnum::Genome1000 (kgl_variant_db_freq.h:87-92).
+const char* const kAfFields[6] = {"AFR_AF", "AMR_AF", "EAS_AF", "EUR_AF", "SAS_AF", "AF"};
+const std::string kContig = "chrFlat";
+
+std::string genomeName(uint32_t g) {
+  char buf[32];
+  std::snprintf(buf, sizeof buf, "G%07u", g);  // zero padded: lexicographic == numeric (std::map order)
+  return buf;
+}
+
+struct GenomeOut {
+  kga::LocusResults results;
+  std::vector<double> starts, ends, grid;
+  std::vector<size_t> evals;
+};
+
+void run() {
+  using Clock = std::chrono::steady_clock;
+  const kglflat::Flat flat = kglflat::readFlat(g_opt.in_path);
+  const uint32_t N = flat.N(), L = flat.L();
+  const bool unphased = (flat.hdr.flags & kglflat::FLAG_UNPHASED) != 0;
+  kglflat::TensorWriter out;
+
+  // ---- INFO evidence: six Float AF fields, Number=A ----------------------------------------------
+  kgl::EvidenceInfoSet info_set;
+  kgl::VCFInfoRecordMap info_map;
+  for (auto* field : kAfFields) {
+    info_set.insert(field);
+    info_map[field] = kgl::VCFInfoRecord{field, "", "Float", "A", "", ""};
+  }
+  kgl::EvidenceFactory evidence_factory(info_set);
+  evidence_factory.availableInfoFields(info_map);
+
+  // ---- AF "genome": 1 genome, 1 contig (kga_analysis_inbreed_diploid.cpp:26,36) --------------------
+  auto af_population = std::make_shared<kgl::PopulationDB>("AF_POPULATION", kgl::DataSourceEnum::Genome1000);
+  const std::vector<kgl::GenomeId_t> af_genome{"AF_GENOME"};
+  for (uint32_t l = 0; l < L; ++l) {
+    std::string info;
+    for (int k = 0; k < 6; ++k) {
+      const float af = flat.afAt(k, l);
+      if (std::isnan(af)) continue;  // field absent for this variant -> superPopFrequency() == nullopt
+      char buf[64];
+      std::snprintf(buf, sizeof buf, "%s%s=%.9g", info.empty() ? "" : ";", kAfFields[k], double(af));
+      info += buf;
+    }
+    auto block = evidence_factory.createVariantEvidence(std::move(info));
+    kgl::VariantEvidence evidence(l, kgl::DataSourceEnum::Genome1000, true, block, nullptr, 0, 1);
+    auto variant = std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], kgl::VariantPhase::UNPHASED, "",
+                                                        kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
+                                                        kgl::DNA5SequenceLinear(kgl::StringDNA5("G")), evidence);
+    if (!af_population->addVariant(variant, af_genome)) kel::ExecEnv::log().error("harness: AF addVariant failed at locus {}", l);
+  }
+
+  // ---- diploid population: only non-reference alleles are stored ---------------------
+  auto diploid = std::make_shared<kgl::PopulationDB>("DIPLOID", kgl::DataSourceEnum::Genome1000);
+  std::vector<kgl::GenomeId_t> genome_ids(N);
+  for (uint32_t g = 0; g < N; ++g) genome_ids[g] = genomeName(g);
+  std::vector<std::shared_ptr<const kgl::Variant>> locus_variant(L);  // phase-A copy, used for summaryByVariant
+  {
+    const kgl::VariantEvidence no_evidence(0, kgl::DataSourceEnum::Genome1000, true, nullptr, nullptr, 0, 1);
+    auto make = [&](uint32_t l, kgl::VariantPhase phase, const char* alt) {
+      return std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], phase, "",
+                                                  kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
+                                                  kgl::DNA5SequenceLinear(kgl::StringDNA5(alt)), no_evidence);
+    };
+    std::vector<kgl::GenomeId_t> first, second, other;
+    for (uint32_t l = 0; l < L; ++l) {
+      first.clear(); second.clear(); other.clear();
+      for (uint32_t g = 0; g < N; ++g) {
+        switch (flat.code(l, g)) {
+          case 1: first.push_back(genome_ids[g]); break;
+          case 2: first.push_back(genome_ids[g]); second.push_back(genome_ids[g]); break;
+          case 3: other.push_back(genome_ids[g]); break;  // an allele that is not in the AF list -> dropped (freq.cpp:462)
+          default: break;
+        }
+      }
+      const auto phase_a = unphased ? kgl::VariantPhase::UNPHASED : kgl::VariantPhase::DIPLOID_PHASE_A;
+      const auto phase_b = unphased ? kgl::VariantPhase::UNPHASED : kgl::VariantPhase::DIPLOID_PHASE_B;
+      auto va = make(l, phase_a, "G");
+      locus_variant[l] = va;
+      if (!first.empty() && !diploid->addVariant(va, first)) kel::ExecEnv::log().error("harness: addVariant A failed");
+      if (!second.empty() && !diploid->addVariant(make(l, phase_b, "G"), second)) kel::ExecEnv::log().error("harness: addVariant B failed");
+      if (!other.empty() && !diploid->addVariant(make(l, phase_a, "T"), other)) kel::ExecEnv::log().error("harness: addVariant X failed");
+    }
+  }
+  std::vector<uint32_t> present(N, 0);
+  for (uint32_t g = 0; g < N; ++g) present[g] = diploid->getMap().contains(genome_ids[g]) ? 1 : 0;
+  out.addU32("genome_present", {N}, present);
+
+  // ---- locus selection, reference code ---------------------------------------------------------------
+  kga::LociiVectorArguments args;
+  args.lowerOffset(g_opt.lower);
+  args.upperOffset(g_opt.upper);
+  args.lociiSpacing(g_opt.spacing);
+  args.lociiCount(g_opt.count);
+  args.minAlleleFrequency(g_opt.min_af);
+  args.maxAlleleFrequency(g_opt.max_af);
+  args.frequencySource(kgl::DataSourceEnum::Genome1000);
+  auto t0 = Clock::now();
+  kga::ContigLocusMap contig_locus_map = kga::InbreedSampling::getPopulationLocusMap(af_population, args);
+  const double locus_seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+  const kga::LocusMap& locus_map = contig_locus_map.at(kContig);
+  for (int k = 0; k < 6; ++k) {
+    std::vector<uint32_t> selected;
+    for (auto const& [offset, offset_ptr] : locus_map.at(kSuperPops[k])->getMap()) selected.push_back(uint32_t(offset));
+    out.addU32(std::string("selected_offsets_") + kSuperPops[k], {selected.size()}, selected);
+  }
+
+  // ---- estimators: one task per genome on the reference thread pool -----------------------------------
+  if (g_opt.grid > 1) {
+    for (size_t i = 0; i < g_opt.grid; ++i) kglref::g_grid.push_back(-0.5 + double(i) / double(g_opt.grid - 1));
+    out.addF64("ll_grid", {kglref::g_grid.size()}, kglref::g_grid);
+  }
+  if (g_opt.seed >= 0) {
+    kglref::g_fixed_seed = unsigned(g_opt.seed);
+    kglref::g_fixed_seed_enabled = true;
+    // The start values every genome will draw: the same library calls the reference makes
+    // (kga_analysis_inbreed_calc.cpp:165,181 and :237,251), on a generator seeded the same way.
+    std::vector<double> hall, ll;
+    { std::mt19937_64 gen(kglref::g_fixed_seed); std::uniform_real_distribution<> d(0.5, 0); for (int i = 0; i < 5; ++i) hall.push_back(d(gen)); }
+    { std::mt19937_64 gen(kglref::g_fixed_seed); std::uniform_real_distribution<> d(0.5, -0.5); for (int i = 0; i < 5; ++i) ll.push_back(d(gen)); }
+    out.addF64("hall_start_sequence", {5}, hall);
+    out.addF64("ll_start_sequence", {5}, ll);
+  }
+  const size_t threads = g_opt.threads ? g_opt.threads : kel::WorkflowThreads::defaultThreads();
+  std::vector<double> timing;
+  for (auto const& algo_name : g_opt.algos) {
+    auto algorithm_opt = kga::InbreedingCalculation::namedAlgorithm(algo_name);
+    if (!algorithm_opt) { std::fprintf(stderr, "unknown algorithm %s\n", algo_name.c_str()); std::exit(2); }
+    const kga::InbreedingAlgorithm algorithm = algorithm_opt.value();
+    std::vector<GenomeOut> results(N);
+    t0 = Clock::now();
+    {
+      kel::WorkflowThreads pool(threads);
+      std::vector<std::pair<uint32_t, std::future<GenomeOut>>> futures;
+      for (uint32_t g = 0; g < N; ++g) {
+        auto genome_opt = diploid->getGenome(genome_ids[g]);
+        if (!genome_opt) continue;
+        auto contig_opt = genome_opt.value()->getContig(kContig);
+        if (!contig_opt) continue;
+        std::shared_ptr<const kgl::ContigDB> contig_ptr = contig_opt.value();
+        const std::string super_pop = kSuperPops[flat.superpop[g]];
+        std::shared_ptr<const kgl::ContigDB> locus_list = locus_map.at(super_pop);
+        auto task = [algorithm](kgl::GenomeId_t genome_id, std::shared_ptr<const kgl::ContigDB> contig,
+                                std::string pop, std::shared_ptr<const kgl::ContigDB> list) {
+          kglref::tl_start_points.clear(); kglref::tl_end_points.clear();
+          kglref::tl_grid_values.clear(); kglref::tl_evals.clear();
+          GenomeOut go;
+          go.results = algorithm(genome_id, contig, pop, list);
+          go.starts = kglref::tl_start_points; go.ends = kglref::tl_end_points;
+          go.grid = kglref::tl_grid_values; go.evals = kglref::tl_evals;
+          return go;
+        };
+        futures.emplace_back(g, pool.enqueueFuture(task, genome_ids[g], contig_ptr, super_pop, locus_list));
+      }
+      for (auto& [g, future] : futures) results[g] = future.get();
+    }
+    const double seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+    timing.push_back(seconds);
+    std::fprintf(stderr, "[ref] %-14s %u genomes x %u loci  %.3f s  (%zu threads)  %.3e genotype-loci/s\n",
+                 algo_name.c_str(), N, L, seconds, threads, double(N) * double(L) / seconds);
+
+    std::vector<uint64_t> counts(size_t(N) * 5);
+    std::vector<double> freqs(size_t(N) * 4), coeff(N);
+    for (uint32_t g = 0; g < N; ++g) {
+      const auto& r = results[g].results;
+      counts[g * 5 + 0] = r.major_homo_count;  counts[g * 5 + 1] = r.major_hetero_count;
+      counts[g * 5 + 2] = r.minor_homo_count;  counts[g * 5 + 3] = r.minor_hetero_count;
+      counts[g * 5 + 4] = r.total_allele_count;
+      freqs[g * 4 + 0] = r.major_homo_freq;  freqs[g * 4 + 1] = r.major_hetero_freq;
+      freqs[g * 4 + 2] = r.minor_homo_freq;  freqs[g * 4 + 3] = r.minor_hetero_freq;
+      coeff[g] = r.inbred_allele_sum;
+    }
+    out.addU64(algo_name + "_counts", {N, 5}, counts);   // majHom, majHet, minHom, minHet, total
+    out.addF64(algo_name + "_freqs", {N, 4}, freqs);     // same order
+    out.addF64(algo_name + "_coeff", {N}, coeff);
+    if (algo_name == "Loglikelihood") {
+      size_t runs = 0;
+      for (auto const& r : results) runs = std::max(runs, r.starts.size());
+      std::vector<double> starts(size_t(N) * runs, std::nan("")), ends(size_t(N) * runs, std::nan("")), evals(size_t(N) * runs, 0.0);
+      for (uint32_t g = 0; g < N; ++g) for (size_t i = 0; i < results[g].starts.size(); ++i) {
+        starts[g * runs + i] = results[g].starts[i];
+        ends[g * runs + i] = results[g].ends[i];
+        evals[g * runs + i] = double(results[g].evals[i]);
+      }
+      out.addF64("ll_starts", {N, runs}, starts);
+      out.addF64("ll_ends", {N, runs}, ends);
+      out.addF64("ll_evals", {N, runs}, evals);
+      if (!kglref::g_grid.empty()) {
+        const size_t G = kglref::g_grid.size();
+        std::vector<double> grid(size_t(N) * G, std::nan(""));
+        for (uint32_t g = 0; g < N; ++g) for (size_t i = 0; i < results[g].grid.size() && i < G; ++i) grid[g * G + i] = results[g].grid[i];
+        out.addF64("ll_grid_values", {N, G}, grid);
+      }
+    }
+  }
+  out.addF64("seconds_per_algo", {timing.size()}, timing);
+  out.addF64("meta", {4}, std::vector<double>{double(threads), double(std::thread::hardware_concurrency()), locus_seconds, 0.0});
+
+  // ---- allele summaries (VariantDBVariant) ------------------------------------------------------------
+  if (g_opt.variantdb) {
+    t0 = Clock::now();
+    kgl::VariantDBVariant variant_db(diploid);
+    std::vector<uint64_t> by_variant(size_t(L) * 3, 0), by_genome(size_t(N) * 3, 0), pop(3, 0);
+    std::vector<uint32_t> variant_present(L, 0);
+    for (uint32_t l = 0; l < L; ++l) {
+      // Only variants that exist in the population have a column (kgl_variant_db_variant.cpp:14-30).
+      if (!variant_db.variantMap().contains(locus_variant[l]->HGVS())) continue;
+      variant_present[l] = 1;
+      auto s = variant_db.summaryByVariant(locus_variant[l]);
+      by_variant[l * 3 + 0] = s.referenceHomozygous_; by_variant[l * 3 + 1] = s.minorHeterozygous_; by_variant[l * 3 + 2] = s.minorHomozygous_;
+    }
+    for (uint32_t g = 0; g < N; ++g) {
+      if (!present[g]) continue;
+      auto s = variant_db.summaryByGenome(genome_ids[g]);
+      by_genome[g * 3 + 0] = s.referenceHomozygous_; by_genome[g * 3 + 1] = s.minorHeterozygous_; by_genome[g * 3 + 2] = s.minorHomozygous_;
+    }
+    auto s = variant_db.populationSummary();
+    pop[0] = s.referenceHomozygous_; pop[1] = s.minorHeterozygous_; pop[2] = s.minorHomozygous_;
+    const double seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+    std::fprintf(stderr, "[ref] VariantDBVariant   %zu variants x %zu genomes  %.3f s\n", variant_db.variantMap().size(), variant_db.genomeMap().size(), seconds);
+    out.addU64("summary_by_variant", {L, 3}, by_variant);     // refHom, het, minorHom for the locus' "A>G" column
+    out.addU32("variant_present", {L}, variant_present);
+    out.addU64("summary_by_genome", {N, 3}, by_genome);
+    out.addU64("summary_population", {3}, pop);
+    out.addF64("variantdb_meta", {3}, std::vector<double>{double(variant_db.variantMap().size()), double(variant_db.genomeMap().size()), seconds});
+  }
+  out.write(g_opt.out_path);
+}
+
+std::vector<std::string> split(const std::string& s, char d) {
+  std::vector<std::string> r; std::stringstream ss(s); std::string t;
+  while (std::getline(ss, t, d)) if (!t.empty()) r.push_back(t);
+  return r;
+}
+
+}  // namespace
+
+class HarnessEnv {
+ public:
+  HarnessEnv() = delete;
+  inline static constexpr const char* VERSION = "1";
+  inline static constexpr const char* MODULE_NAME = "kglRefHarness";
+  inline static constexpr size_t MAX_ERROR_MESSAGES = 100000;
+  inline static constexpr size_t MAX_WARNING_MESSAGES = 1000;
+
+  static void executeApp() { run(); }
+
+  [[nodiscard]] static bool parseCommandLine(int argc, char const** argv) {
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; ++i) {
+      std::string a = argv[i];
+      auto next = [&]() -> std::string { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", a.c_str()); std::exit(2); } return argv[++i]; };
+      if (a == "--algos") g_opt.algos = split(next(), ',');
+      else if (a == "--min-af") g_opt.min_af = std::stod(next());
+      else if (a == "--max-af") g_opt.max_af = std::stod(next());
+      else if (a == "--spacing") g_opt.spacing = std::stoull(next());
+      else if (a == "--count") g_opt.count = std::stoull(next());
+      else if (a == "--lower") g_opt.lower = std::stoull(next());
+      else if (a == "--upper") g_opt.upper = std::stoull(next());
+      else if (a == "--threads") g_opt.threads = std::stoull(next());
+      else if (a == "--grid") g_opt.grid = std::stoull(next());
+      else if (a == "--seed") g_opt.seed = std::stol(next());
+      else if (a == "--no-variantdb") g_opt.variantdb = false;
+      else if (a == "--verbose") g_opt.quiet = false;
+      else pos.push_back(a);
+    }
+    if (pos.size() != 2) { std::fprintf(stderr, "usage: kgl_ref_harness IN.flat OUT.tens [options]\n"); return false; }
+    g_opt.in_path = pos[0]; g_opt.out_path = pos[1];
+    // The reference logs one line per genome to stdout (kga_analysis_inbreed_calc.cpp:209,301,346,425).
+    if (g_opt.quiet) { if (!std::freopen("/dev/null", "w", stdout)) return false; }
+    return true;
+  }
+
+  [[nodiscard]] static std::unique_ptr<kel::ExecEnvLogger> createLogger() {
+    const char* log_file = std::getenv("KGL_REF_LOG");
+    return kel::ExecEnv::createLogger(MODULE_NAME, log_file ? log_file : "/tmp/kgl_ref_harness.log", MAX_ERROR_MESSAGES, MAX_WARNING_MESSAGES);
+  }
+};
+
+int main(int argc, const char* argv[]) { return kel::ExecEnv::runApplication<HarnessEnv>(argc, argv); }

@@ -1,0 +1,117 @@
+"""Pins the CPU oracle (oracle/kgl_oracle.c) against outputs of the reference's own code.
+
+tests/golden/*.npz were produced by tests/golden/make_golden.py from oracle/_ref/kgl_ref_harness, i.e. the reference's
+translation units compiled where they lie. Integer results must be bit-exact; here the double results are bit-exact
+too, because the oracle performs the same IEEE operations in the same order.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from conftest import results_matrix
+
+SUPER_POPS = ["AFR", "AMR", "EAS", "EUR", "SAS", "ALL"]
+
+
+def test_locus_selection_matches_reference(golden):
+    name, pop, ref, sel_kw = golden
+    sel = O.select_all_pops(pop, **sel_kw)
+    for k, sp in enumerate(SUPER_POPS):
+        assert np.array_equal(pop.offsets[sel[k] == 1], ref["selected_offsets_" + sp]), (name, sp)
+
+
+@pytest.mark.parametrize("algo", ["Simple", "RitlandLocus"])
+def test_closed_form_estimators_bit_exact(golden, algo):
+    name, pop, ref, sel_kw = golden
+    sel = O.select_all_pops(pop, **sel_kw)
+    counts, freqs = results_matrix(O.inbreed(pop, sel, algo))
+    present = ref["genome_present"] == 1
+    assert np.array_equal(counts[present], ref[algo + "_counts"][present])
+    assert np.array_equal(freqs[present], ref[algo + "_freqs"][present])          # same ops, same order: bit-exact
+    mine = O.inbreed(pop, sel, algo)["inbred_allele_sum"]
+    assert np.array_equal(mine[present], ref[algo + "_coeff"][present])
+
+
+def test_loglikelihood_grid_bit_exact(golden):
+    name, pop, ref, sel_kw = golden
+    sel = O.select_all_pops(pop, **sel_kw)
+    ll = O.loglik_grid(pop, sel, ref["ll_grid"])
+    present = ref["genome_present"] == 1
+    assert np.array_equal(ll[present], ref["ll_grid_values"][present])
+
+
+def test_loglikelihood_optimum_within_optimiser_tolerance(golden):
+    """The reference stops Nelder-Mead at xtol_abs 1e-6 (calc.cpp:138); every one of its 5 restarts must land within
+    that distance (plus slack for a flat objective) of the oracle's converged optimum."""
+    name, pop, ref, sel_kw = golden
+    sel = O.select_all_pops(pop, **sel_kw)
+    opt = O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"]
+    present = ref["genome_present"] == 1
+    assert np.all(np.abs(ref["Loglikelihood_coeff"][present] - opt[present]) < 5e-6)
+    # and the oracle optimum is at least as good as anything the reference found
+    grid_at = np.stack([opt, ref["Loglikelihood_coeff"]], axis=1)
+    for g in np.flatnonzero(present)[:8]:
+        vals = O.loglik_grid(pop, sel, grid_at[g])[g]
+        assert vals[0] >= vals[1] - 1e-9
+
+
+def test_hallme_fifty_sweeps_bit_exact(golden):
+    """Q1: the reference runs exactly 50 EM sweeps from its 5th random start; with std::random_device pinned in the
+    harness the start is known, and the oracle's 50 sweeps reproduce the result bit for bit."""
+    name, pop, ref, sel_kw = golden
+    sel = O.select_all_pops(pop, **sel_kw)
+    start = np.full(pop.n_genomes, ref["hall_start_sequence"][4])
+    mine = O.inbreed(pop, sel, "HallME", start=start, sweeps=50)["inbred_allele_sum"]
+    present = ref["genome_present"] == 1
+    assert np.array_equal(mine[present], ref["HallME_coeff"][present])
+
+
+def test_allele_summaries_match_variantdb(golden):
+    """VariantDBVariant (kgl_variant_db_variant.cpp): het = cells == 1, minorHom = cells == 2 of the locus' A>G column.
+    Dropped cells (code 3) carry a different allele in the harness, so they land in the column's refHom count."""
+    name, pop, ref, sel_kw = golden
+    lc, gc = O.allele_count(pop)
+    m = ref["variant_present"] == 1
+    sv = ref["summary_by_variant"]
+    assert np.array_equal(sv[m, 1], lc[m, 1]) and np.array_equal(sv[m, 2], lc[m, 2])
+    assert np.array_equal(sv[m, 0], (lc[m, 0] + lc[m, 3]).astype(np.uint64))
+    assert np.array_equal(lc.sum(axis=1), np.full(pop.n_loci, pop.n_genomes))
+    assert np.array_equal(gc.sum(axis=1), np.full(pop.n_genomes, pop.n_loci))
+    # summaryByGenome runs over every distinct variant column, including the harness' "A>T" stand-in for a dropped cell
+    # (one copy -> counted as heterozygous): het = n1 + n3, minorHom = n2, refHom = columns - het - minorHom.
+    sg = ref["summary_by_genome"]
+    present = ref["genome_present"] == 1
+    n_columns = int(ref["variantdb_meta"][0])
+    assert np.array_equal(sg[present, 1], gc[present, 1] + gc[present, 3]) and np.array_equal(sg[present, 2], gc[present, 2])
+    assert np.array_equal(sg[present, 0], n_columns - sg[present, 1] - sg[present, 2])
+    assert np.array_equal(ref["summary_population"], sg[present].sum(axis=0))
+
+
+def test_synthetic_generator_matches_numpy():
+    from kgl_gene_b200.synth import make_population
+    pop, f = make_population(77, 300, seed=5)
+    packed = O.synth_genotypes(5, 77, 300, pop.af, pop.superpop, f)
+    assert np.array_equal(packed, pop.packed)
+
+
+def test_ibs_oracle_basic_properties():
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(19, 257, seed=9, missing_rate=0.05)
+    ibs = O.ibs(pop)
+    assert np.array_equal(ibs, ibs.transpose(1, 0, 2))
+    assert np.array_equal(ibs[..., :3].sum(-1), ibs[..., 3])
+    codes = pop.codes()
+    valid = (codes != 3).sum(axis=0)
+    d = np.arange(19)
+    assert np.array_equal(ibs[d, d, 2], valid) and np.all(ibs[d, d, 0] == 0)
+
+
+@pytest.mark.skipif(not O.have_reference_harness(), reason="oracle/_ref not built (needs /root/reference)")
+def test_live_reference_run_matches_oracle():
+    """Fresh (non-golden) population through the live reference harness, when it exists."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(16, 400, seed=777, spectrum="dense")
+    ref = O.run_reference(pop, algos=("Simple", "RitlandLocus"), spacing=15, variantdb=False)
+    sel = O.select_all_pops(pop, spacing=15)
+    for algo in ("Simple", "RitlandLocus"):
+        assert np.array_equal(O.inbreed(pop, sel, algo)["inbred_allele_sum"], ref[algo + "_coeff"])
