@@ -1,0 +1,161 @@
+/* kgl_b200.h -- C ABI of the B200-native population-genotype hot path for KGL_Gene.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no exceptions. A KGL_Gene maintainer binds
+ * it from a VirtualAnalysis subclass (kgl_app/kgl_package_analysis_virtual.h:20-55) -- see INTEGRATION.md and
+ * kgl_gene_b200/host/ for the C++ host layer (flattener, locus selection, window loop, CSV writer) that sits on top.
+ * Every entry point names the reference routine it replaces (paths relative to the KGL_Gene tree).
+ *
+ * Threading: a context is used from one host thread at a time (the reference calls its analysis stages sequentially
+ * from the main thread, kgl_app/kgl_package.cpp:17-77). Several contexts (one per GPU / per rank) may coexist.
+ * There is NO CPU fallback: every compute entry point fails with KGL_B200_ERR_NO_DEVICE / _CUDA when no sm_100 device
+ * is usable.
+ *
+ * ---- data layout (what the host flattener emits) ------------------------------------------------------------------
+ *  genotype matrix  loci-major, 2 bits per genome, rows aligned to 128 bits:
+ *                   row_bytes = 16 * ceil(n_genomes / 64); row l = units u = 0..row_bytes/16-1;
+ *                   unit u = { uint64 lo, uint64 hi } (little endian) for genomes 64u .. 64u+63,
+ *                   code(g) = bit(lo, g%64) + 2*bit(hi, g%64):
+ *                     0 = no variant at the offset (hom-ref)           kga_analysis_inbreed_freq.cpp:521-541
+ *                     1 = one copy of the locus' alt allele (het)       :464-472
+ *                     2 = two copies (hom-alt)                          :476-479
+ *                     3 = dropped / unclassifiable / missing           (first variant not in the AF list, >2 variants, ...)
+ *                   padding genomes (>= n_genomes) must be 0.
+ *  allele frequency float[n_pop][n_loci], the INFO float exactly as the reference stores it
+ *                   (kgl_variant_factory_vcf_parse_info.cpp:232); NaN = no value for that super-population.
+ *                   Populations are indexed AFR, AMR, EAS, EUR, SAS, ALL (kgl_variant_db_freq.h:55-71).
+ *  super-population uint8[n_genomes], index of each genome's PED super-population (kgl_hsgenealogy_parser.h:68).
+ *  locus selection  uint8[n_loci], bit k set = locus is in super-population k's locus list for the current window
+ *                   (InbreedSampling::getLocusList, kga_analysis_inbreed_locus.cpp:263).
+ */
+#ifndef KGL_B200_H
+#define KGL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGL_B200_OK             0
+#define KGL_B200_ERR_INVALID    1   /* bad argument */
+#define KGL_B200_ERR_STATE      2   /* call order: something required has not been uploaded yet */
+#define KGL_B200_ERR_CUDA       3   /* a CUDA call failed; see kgl_b200_last_error */
+#define KGL_B200_ERR_NO_DEVICE  4   /* no usable sm_100 GPU */
+#define KGL_B200_ERR_NOMEM      5
+
+#define KGL_B200_MAX_POP 6
+
+/* InbreedingCalculation::inbreeding_algo_map_ (kga_analysis_inbreed_calc.h:103-118). */
+#define KGL_B200_ALGO_SIMPLE        0   /* "Simple"        processSimple         calc.cpp:319 */
+#define KGL_B200_ALGO_RITLAND       1   /* "RitlandLocus"  processRitlandLocus   calc.cpp:375 */
+#define KGL_B200_ALGO_HALLME        2   /* "HallME"        processHallME         calc.cpp:226 */
+#define KGL_B200_ALGO_LOGLIKELIHOOD 3   /* "Loglikelihood" processLogLikelihood  calc.cpp:154 */
+
+typedef struct kgl_b200_ctx kgl_b200_ctx;
+
+/* Same fields, same order as kga::LocusResults (kga_analysis_inbreed_output.h:21-35) without the genome id string. */
+typedef struct kgl_b200_locus_results {
+  uint64_t major_hetero_count; double major_hetero_freq;
+  uint64_t minor_hetero_count; double minor_hetero_freq;
+  uint64_t minor_homo_count;   double minor_homo_freq;
+  uint64_t major_homo_count;   double major_homo_freq;
+  uint64_t total_allele_count; double inbred_allele_sum;
+} kgl_b200_locus_results;
+
+/* Options of the iterative estimators. Zero-initialise for the defaults. */
+typedef struct kgl_b200_inbreed_options {
+  /* HallME: EM start value per genome (NULL = 0.25 for all) and number of sweeps. The reference runs exactly 50 sweeps
+   * from a random start in (0,0.5]; sweeps == 0 means 50; sweeps < 0 iterates to the EM fixed point. */
+  const double* hall_start;
+  int32_t hall_sweeps;
+  /* Loglikelihood: safeguarded Newton on the reference objective, stops when |step| < ll_tolerance (0 = 1e-12) or
+   * after ll_max_iterations (0 = 64). */
+  double ll_tolerance;
+  int32_t ll_max_iterations;
+  int32_t reserved;
+} kgl_b200_inbreed_options;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------- */
+const char* kgl_b200_version(void);
+int  kgl_b200_device_count(void);
+int  kgl_b200_create(int device, kgl_b200_ctx** ctx);
+void kgl_b200_destroy(kgl_b200_ctx* ctx);
+/* Message of the last failure on this context (ctx == NULL: of the last failed kgl_b200_create on this thread). */
+const char* kgl_b200_last_error(const kgl_b200_ctx* ctx);
+/* All kernels of this context are enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). */
+int  kgl_b200_set_stream(kgl_b200_ctx* ctx, void* cuda_stream);
+int  kgl_b200_synchronize(kgl_b200_ctx* ctx);
+
+/* ---- population upload (host buffers; replaces walking PopulationDB per genome, kga_analysis_inbreed_freq.cpp:436-452) */
+int kgl_b200_upload_genotypes(kgl_b200_ctx* ctx, uint64_t n_genomes, uint64_t n_loci, uint64_t row_bytes, const void* packed);
+int kgl_b200_upload_loci(kgl_b200_ctx* ctx, uint64_t n_loci, uint32_t n_pop, const float* af, const uint32_t* offsets);
+int kgl_b200_set_genome_superpop(kgl_b200_ctx* ctx, uint64_t n_genomes, const uint8_t* superpop);
+/* Pf7-style population: all variants UNPHASED, so a hom-alt pair is classified MINOR_HETEROZYGOUS. */
+int kgl_b200_set_unphased(kgl_b200_ctx* ctx, int unphased);
+
+/* Locus selection for the current window. kgl_b200_select_loci applies RetrieveLociiVector::getLociiFromTo
+ * (kga_analysis_inbreed_locus.cpp:21-72,76) to every super-population: loci with lower <= offset <= upper, at least
+ * `spacing` apart, valid AF with 0 < AF and min_af <= AF <= max_af. n_selected (nullable) receives n_pop counts.
+ * kgl_b200_set_locus_selection uploads a mask computed elsewhere. Default after kgl_b200_upload_loci: nothing selected. */
+int kgl_b200_select_loci(kgl_b200_ctx* ctx, uint64_t lower, uint64_t upper, uint64_t spacing,
+                         double min_af, double max_af, uint64_t* n_selected);
+int kgl_b200_set_locus_selection(kgl_b200_ctx* ctx, uint64_t n_loci, const uint8_t* selected);
+int kgl_b200_get_locus_selection(kgl_b200_ctx* ctx, uint64_t n_loci, uint8_t* selected);
+
+/* Synthetic population generated on the device (configs too large to stage through a PopulationDB; the law is
+ * InbreedSynthetic's, kga_analysis_inbreed_syngen.cpp:20-196). Needs upload_loci + set_genome_superpop first.
+ * Cells are a pure function of (seed, locus_base + locus, genome), so shards of one population can be generated
+ * independently on different GPUs. */
+int kgl_b200_synth_genotypes(kgl_b200_ctx* ctx, uint64_t seed, uint64_t n_genomes, uint64_t n_loci, uint64_t locus_base,
+                             const double* inbreeding, double missing_rate);
+int kgl_b200_download_genotypes(kgl_b200_ctx* ctx, uint64_t n_bytes, void* packed);
+
+/* ---- hot path, host-buffer results (synchronous) ------------------------------------------------------------------ */
+/* VariantDBVariant::summaryByVariant / summaryByGenome / populationSummary (kgl_variant_db_variant.cpp:126,180,234):
+ * locus_counts uint32[n_loci][4] and genome_counts uint64[n_genomes][4] = number of cells with code 0,1,2,3
+ * (AlleleSummmary = {referenceHomozygous_, minorHeterozygous_, minorHomozygous_} = columns 0,1,2). Either may be NULL. */
+int kgl_b200_run_allele_count(kgl_b200_ctx* ctx, uint32_t* locus_counts, uint64_t* genome_counts);
+
+/* InbreedingCalculation::process{Simple,RitlandLocus,HallME,LogLikelihood} for every genome over the selected loci
+ * (kga_analysis_inbreed_calc.cpp:319,375,226,154 on top of generateFrequencies, kga_analysis_inbreed_freq.cpp:425-583).
+ * out[n_genomes]. options may be NULL. */
+int kgl_b200_run_inbreed(kgl_b200_ctx* ctx, int algorithm, const kgl_b200_inbreed_options* options,
+                         kgl_b200_locus_results* out);
+
+/* The fused streaming pass the benchmark times: one read of the genotype matrix yields the per-locus allele counts
+ * AND the per-genome Simple moments (class counts, expected class-frequency sums, F). Either output may be NULL. */
+int kgl_b200_run_count_and_inbreed(kgl_b200_ctx* ctx, uint32_t* locus_counts, kgl_b200_locus_results* out);
+
+/* InbreedingCalculation::logLikelihood (kga_analysis_inbreed_calc.cpp:94-129) on a grid of f values: out[n_genomes][n_grid]. */
+int kgl_b200_run_loglik_grid(kgl_b200_ctx* ctx, const double* grid, uint64_t n_grid, double* out);
+
+/* Pairwise identity-by-state between genomes [row_begin,row_end) and all genomes, over all loci:
+ * out uint32[row_end-row_begin][n_genomes][4] = {IBS0, IBS1, IBS2, loci valid in both}. (No reference routine exists;
+ * the matrix is the one VariantDBVariant::genomeData() describes, kgl_variant_db_variant.h:49-51) */
+int kgl_b200_run_ibs(kgl_b200_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint32_t* out);
+
+/* ---- resident / asynchronous building blocks (bench.py, multi-GPU drivers) ------------------------------------------ */
+/* Enqueue the fused pass on the context stream and return immediately; results stay in device buffers. */
+int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* ctx);
+/* Number of kernels this context has launched so far. */
+uint64_t kgl_b200_launch_count(const kgl_b200_ctx* ctx);
+/* Milliseconds the dominant streaming kernel (k_count_moments) took in the most recent enqueue/run, measured with
+ * CUDA events around that launch on the context stream. Returns < 0 if none has run. Synchronises. */
+float kgl_b200_last_stream_kernel_ms(kgl_b200_ctx* ctx);
+
+/* Locus-sharded multi-GPU inbreeding: each rank holds a shard of the loci. begin() prepares `algorithm`;
+ * accumulate() fills the context's per-genome partial-sum buffer (device, doubles) for the current iterate;
+ * the caller all-reduces (SUM) that buffer across ranks (partials_buffer() exposes it); update() consumes the reduced
+ * partials and reports whether the iteration has finished; fetch() copies the LocusResults to the host.
+ * On one GPU run_inbreed() is exactly begin + (accumulate + update)* + fetch. */
+int kgl_b200_inbreed_begin(kgl_b200_ctx* ctx, int algorithm, const kgl_b200_inbreed_options* options);
+int kgl_b200_inbreed_accumulate(kgl_b200_ctx* ctx);
+int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* ctx, void** device_ptr, uint64_t* n_doubles);
+int kgl_b200_inbreed_update(kgl_b200_ctx* ctx, int* finished);
+int kgl_b200_inbreed_fetch(kgl_b200_ctx* ctx, kgl_b200_locus_results* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGL_B200_H */

@@ -1,0 +1,771 @@
+// kgl_b200_api.cu -- the C ABI (include/kgl_b200.h) over the sm_100a kernels. No CPU fallback anywhere in this file.
+#include "../../include/kgl_b200.h"
+
+#include "common.cuh"
+#include "locus_kernels.cuh"
+#include "count_moments.cuh"
+#include "sample_major.cuh"
+#include "misc_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace kgl;
+
+namespace {
+
+thread_local std::string tl_create_error;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct kgl_b200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  // population
+  uint64_t N = 0, L = 0, row_bytes = 0, units = 0, Npad = 0;
+  uint32_t n_pop = 0;
+  bool have_geno = false, have_loci = false, have_superpop = false, unphased = false;
+  DevBuf<uint8_t> d_packed;
+  DevBuf<float> d_af;
+  DevBuf<uint8_t> d_superpop, d_sel, d_unit_pop;
+  DevBuf<uint64_t> d_popmask;
+  std::vector<float> h_af;
+  std::vector<uint32_t> h_offsets;
+  std::vector<uint8_t> h_superpop, h_sel;
+  bool any_mixed = false;
+  bool units_valid = false;
+
+  // per-locus preparation
+  DevBuf<uint16_t> d_flags16;
+  DevBuf<uint32_t> d_selw;
+  DevBuf<double> d_block_totals, d_totals;
+  bool prep_valid = false;
+
+  // sample-major copy
+  DevBuf<uint32_t> d_sm_lo, d_sm_hi;
+  uint64_t n_gblocks = 0, n_words = 0;
+  bool sm_valid = false;
+
+  // fused pass outputs
+  DevBuf<uint32_t> d_locus_counts, d_planes, d_gcounts, d_nz_rare;
+  DevBuf<double> d_ecorr, d_partials, d_iter, d_f, d_bracket, d_chunk_out, d_inbreeding, d_grid;
+  DevBuf<uint32_t> d_done;
+  DevBuf<unsigned long long> d_flag;
+  DevBuf<uint64_t> d_genome_counts;
+  DevBuf<kgl_b200_locus_results> d_results;
+  DevBuf<uint32_t> d_ibs;
+
+  // iterative estimator state
+  int algo = -1, phase = 0, iteration = 0;
+  kgl_b200_inbreed_options opt{};
+  std::vector<double> hall_start;
+};
+
+namespace {
+
+int fail(kgl_b200_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else tl_create_error = msg;
+  return code;
+}
+
+#define KGL_CUDA(c, call)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t e_ = (call);                                                                                \
+    if (e_ != cudaSuccess)                                                                                  \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? KGL_B200_ERR_NOMEM : KGL_B200_ERR_CUDA,            \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                      \
+  } while (0)
+
+#define KGL_LAUNCH_CHECK(c)                                                                                 \
+  do {                                                                                                      \
+    ++(c)->launches;                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                                    \
+    if (e_ != cudaSuccess) return fail((c), KGL_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+int use_device(kgl_b200_ctx* c) {
+  KGL_CUDA(c, cudaSetDevice(c->device));
+  return KGL_B200_OK;
+}
+
+// Super-population of every 128-bit unit (0xFF = mixed) and the per-population genome masks.
+int build_unit_tables(kgl_b200_ctx* c) {
+  if (c->units_valid) return KGL_B200_OK;
+  const uint64_t units = c->units;
+  std::vector<uint8_t> unit_pop(units, 0);
+  std::vector<uint64_t> popmask((size_t)KGL_B200_MAX_POP * units, 0);
+  c->any_mixed = false;
+  for (uint64_t u = 0; u < units; ++u) {
+    int first = -1;
+    bool mixed = false;
+    for (int b = 0; b < 64; ++b) {
+      const uint64_t g = u * 64 + b;
+      if (g >= c->N) break;
+      const int k = c->h_superpop[g];
+      popmask[(size_t)k * units + u] |= 1ull << b;
+      if (first < 0) first = k; else if (k != first) mixed = true;
+    }
+    unit_pop[u] = mixed ? 0xFF : (uint8_t)std::max(first, 0);
+    c->any_mixed |= mixed;
+  }
+  KGL_CUDA(c, c->d_unit_pop.ensure(units));
+  KGL_CUDA(c, c->d_popmask.ensure(popmask.size()));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_unit_pop.p, unit_pop.data(), units, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_popmask.p, popmask.data(), popmask.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->units_valid = true;
+  return KGL_B200_OK;
+}
+
+int require_population(kgl_b200_ctx* c, bool need_loci) {
+  if (!c->have_geno) return fail(c, KGL_B200_ERR_STATE, "no genotype matrix uploaded");
+  if (need_loci) {
+    if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "no allele frequencies uploaded (kgl_b200_upload_loci)");
+    if (!c->have_superpop) return fail(c, KGL_B200_ERR_STATE, "no genome super-populations set (kgl_b200_set_genome_superpop)");
+    if (c->h_sel.size() != c->L) return fail(c, KGL_B200_ERR_STATE, "locus selection does not match the genotype matrix");
+    for (uint64_t g = 0; g < c->N; ++g)
+      if (c->h_superpop[g] >= c->n_pop) return fail(c, KGL_B200_ERR_INVALID, "genome super-population index out of range");
+  }
+  return KGL_B200_OK;
+}
+
+// Selection flags, packed selection words and dense totals (once per selection).
+int ensure_prepared(kgl_b200_ctx* c) {
+  if (c->prep_valid) return KGL_B200_OK;
+  const uint64_t L = c->L;
+  c->n_words = (L + 31) / 32;
+  c->n_words = (c->n_words + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
+  const unsigned nb = std::max(1u, blocks_for(L, kPrepThreads));
+  KGL_CUDA(c, c->d_flags16.ensure(L));
+  KGL_CUDA(c, c->d_selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
+  KGL_CUDA(c, c->d_block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
+  KGL_CUDA(c, c->d_totals.ensure(kMaxPop * TOT_COUNT));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_selw.p, 0, (size_t)KGL_B200_MAX_POP * c->n_words * 4, c->stream));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_block_totals.p, 0, (size_t)nb * kMaxPop * TOT_COUNT * 8, c->stream));
+  k_locus_prepare<<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, (int)c->n_pop, 0, c->d_flags16.p,
+                                                      c->d_selw.p, c->n_words, c->d_block_totals.p);
+  KGL_LAUNCH_CHECK(c);
+  k_reduce_totals<<<1, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p);
+  KGL_LAUNCH_CHECK(c);
+  c->prep_valid = true;
+  return KGL_B200_OK;
+}
+
+int ensure_sample_major(kgl_b200_ctx* c) {
+  if (c->sm_valid) return KGL_B200_OK;
+  c->n_gblocks = c->units * 2;
+  uint64_t nw = (c->L + 31) / 32;
+  nw = (nw + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
+  c->n_words = nw;
+  const size_t n = (size_t)c->n_gblocks * nw * 32;
+  KGL_CUDA(c, c->d_sm_lo.ensure(n));
+  KGL_CUDA(c, c->d_sm_hi.ensure(n));
+  dim3 grid((unsigned)nw, (unsigned)((c->n_gblocks + 7) / 8));
+  k_to_sample_major<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->d_packed.p), c->row_bytes / 4, c->L,
+                                                  c->n_gblocks, nw, c->d_sm_lo.p, c->d_sm_hi.p);
+  KGL_LAUNCH_CHECK(c);
+  c->sm_valid = true;
+  return KGL_B200_OK;
+}
+
+struct CountLaunch { int sw, ty; unsigned slices, n_chunks; uint32_t rows_per_cta; };
+
+CountLaunch plan_count(const kgl_b200_ctx* c) {
+  CountLaunch p;
+  p.sw = (int)std::min<uint64_t>(c->units, kCountThreads);
+  p.ty = std::max(1, std::min(kCountMaxTY, kCountThreads / p.sw));
+  p.slices = (unsigned)((c->units + p.sw - 1) / p.sw);
+  const uint64_t group = (uint64_t)kCountUnroll * p.ty;
+  uint64_t target = std::max<uint64_t>(1, (uint64_t)c->sm_count * 2 / p.slices);
+  uint64_t rows = (c->L + target - 1) / target;
+  rows = std::max<uint64_t>(group, (rows + group - 1) / group * group);
+  const uint64_t max_rows = (uint64_t)kMaxRowsPerThread / kCountUnroll * kCountUnroll * p.ty;
+  rows = std::min(rows, max_rows);
+  p.rows_per_cta = (uint32_t)rows;
+  p.n_chunks = (unsigned)std::max<uint64_t>(1, (c->L + rows - 1) / rows);
+  return p;
+}
+
+// The fused streaming pass. raw: allele_count over all loci; otherwise over the selected loci with corrections.
+int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome) {
+  int rc = build_unit_tables(c);
+  if (rc) return rc;
+  const CountLaunch pl = plan_count(c);
+  const uint64_t vchunks = (uint64_t)pl.n_chunks * pl.ty;
+  if (want_locus_counts) {
+    KGL_CUDA(c, c->d_locus_counts.ensure((size_t)c->L * 4));
+    if (pl.slices > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_locus_counts.p, 0, (size_t)c->L * 16, c->stream));
+  }
+  if (want_genome) {
+    KGL_CUDA(c, c->d_planes.ensure((size_t)vchunks * c->units * 3 * 2 * kLevels));
+    KGL_CUDA(c, c->d_gcounts.ensure((size_t)c->Npad * 4));
+    KGL_CUDA(c, c->d_ecorr.ensure((size_t)c->Npad * 2));
+    KGL_CUDA(c, c->d_nz_rare.ensure(c->Npad));
+    KGL_CUDA(c, cudaMemsetAsync(c->d_gcounts.p, 0, (size_t)c->Npad * 16, c->stream));
+    KGL_CUDA(c, cudaMemsetAsync(c->d_ecorr.p, 0, (size_t)c->Npad * 16, c->stream));
+    KGL_CUDA(c, cudaMemsetAsync(c->d_nz_rare.p, 0, (size_t)c->Npad * 4, c->stream));
+  }
+  CountParams P{};
+  P.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
+  P.units = c->units; P.n_loci = c->L; P.n_genomes = c->N;
+  P.rows_per_cta = pl.rows_per_cta; P.sw = pl.sw; P.ty = pl.ty;
+  P.flags16 = c->d_flags16.p; P.unit_pop = c->d_unit_pop.p; P.popmask = c->d_popmask.p;
+  P.superpop = c->d_superpop.p; P.af = c->d_af.p; P.n_pop = (int)c->n_pop;
+  P.raw = raw ? 1 : 0; P.multi_slice = pl.slices > 1 ? 1 : 0;
+  P.locus_counts = want_locus_counts ? c->d_locus_counts.p : nullptr;
+  P.planes = want_genome ? c->d_planes.p : nullptr;
+  P.ecorr = c->d_ecorr.p; P.nz_rare = c->d_nz_rare.p;
+  dim3 grid(pl.n_chunks, pl.slices);
+  KGL_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  if (c->any_mixed && !raw) k_count_moments<true><<<grid, kCountThreads, 0, c->stream>>>(P);
+  else k_count_moments<false><<<grid, kCountThreads, 0, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  c->ev_valid = true;
+  if (want_locus_counts && pl.slices > 1) {
+    k_fix_locus_n0<<<blocks_for(c->L, 256), 256, 0, c->stream>>>(c->d_locus_counts.p, c->L, (uint32_t)c->N);
+    KGL_LAUNCH_CHECK(c);
+  }
+  if (want_genome) {
+    dim3 eg(blocks_for(c->Npad, 256), (unsigned)((vchunks + kExpandChunkGroup - 1) / kExpandChunkGroup));
+    k_expand_counts<<<eg, 256, 0, c->stream>>>(c->d_planes.p, vchunks, c->units, c->Npad, c->d_gcounts.p);
+    KGL_LAUNCH_CHECK(c);
+  }
+  return KGL_B200_OK;
+}
+
+// Moments of all genomes over the selected loci into d_partials (phase 0 of every estimator).
+int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts) {
+  int rc = ensure_prepared(c);
+  if (rc) return rc;
+  rc = launch_count(c, false, want_locus_counts, true);
+  if (rc) return rc;
+  KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
+  k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts.p, c->d_totals.p, c->d_ecorr.p, c->d_nz_rare.p,
+                                                                  c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+struct TermLaunch { dim3 grid; uint32_t words_per_chunk; uint64_t n_chunks; };
+
+TermLaunch plan_terms(const kgl_b200_ctx* c) {
+  TermLaunch t;
+  const uint64_t gx = (c->n_gblocks + kTermWarps - 1) / kTermWarps;
+  // aim for ~4 waves of CTAs; chunks are multiples of the shared-memory tile
+  uint64_t want_chunks = std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8 + gx - 1) / gx);
+  uint64_t wpc = (c->n_words + want_chunks - 1) / want_chunks;
+  wpc = std::max<uint64_t>(kTermTileWords, (wpc + kTermTileWords - 1) / kTermTileWords * kTermTileWords);
+  t.words_per_chunk = (uint32_t)wpc;
+  t.n_chunks = (c->n_words + wpc - 1) / wpc;
+  t.grid = dim3((unsigned)gx, (unsigned)t.n_chunks);
+  return t;
+}
+
+template <int MODE>
+int launch_terms(kgl_b200_ctx* c, int n_out, const double* d_grid, int n_grid, TermLaunch& tl) {
+  int rc = ensure_sample_major(c);
+  if (rc) return rc;
+  tl = plan_terms(c);
+  KGL_CUDA(c, c->d_chunk_out.ensure((size_t)tl.n_chunks * c->Npad * n_out));
+  TermParams P{};
+  P.sm_lo = c->d_sm_lo.p; P.sm_hi = c->d_sm_hi.p;
+  P.n_gblocks = c->n_gblocks; P.n_words = c->n_words; P.n_loci = c->L; P.n_genomes = c->N;
+  P.selw = c->d_selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
+  P.unphased = c->unphased ? 1 : 0; P.words_per_chunk = tl.words_per_chunk;
+  P.f = c->d_f.p; P.grid = d_grid; P.n_grid = n_grid;
+  P.out = c->d_chunk_out.p; P.n_out = n_out; P.n_genomes_padded = c->Npad;
+  k_genome_terms<MODE><<<tl.grid, kTermWarps * 32, 0, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* kgl_b200_version(void) { return "kgl_b200 0.1 (sm_100a)"; }
+
+int kgl_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int kgl_b200_create(int device, kgl_b200_ctx** out) {
+  if (!out) return fail(nullptr, KGL_B200_ERR_INVALID, "ctx out pointer is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, KGL_B200_ERR_NO_DEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                                 " (kgl_b200 has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, KGL_B200_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, KGL_B200_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU; this library ships sm_100a code only",
+                  device, prop.name, prop.major, prop.minor);
+    return fail(nullptr, KGL_B200_ERR_NO_DEVICE, buf);
+  }
+  auto* c = new kgl_b200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    std::string m = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete c;
+    return fail(nullptr, KGL_B200_ERR_CUDA, m);
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return KGL_B200_OK;
+}
+
+void kgl_b200_destroy(kgl_b200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_unit_pop.release();
+  c->d_popmask.release(); c->d_flags16.release(); c->d_selw.release(); c->d_block_totals.release(); c->d_totals.release();
+  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_planes.release(); c->d_gcounts.release();
+  c->d_nz_rare.release(); c->d_ecorr.release(); c->d_partials.release(); c->d_iter.release(); c->d_f.release();
+  c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
+  c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* kgl_b200_last_error(const kgl_b200_ctx* c) { return c ? c->err.c_str() : tl_create_error.c_str(); }
+
+int kgl_b200_set_stream(kgl_b200_ctx* c, void* s) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_synchronize(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+uint64_t kgl_b200_launch_count(const kgl_b200_ctx* c) { return c ? c->launches : 0; }
+
+float kgl_b200_last_stream_kernel_ms(kgl_b200_ctx* c) {
+  if (!c || !c->ev_valid) return -1.0f;
+  if (cudaSetDevice(c->device) != cudaSuccess) return -1.0f;
+  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint64_t row_bytes) {
+  if (n_genomes == 0 || n_loci == 0) return fail(c, KGL_B200_ERR_INVALID, "empty genotype matrix");
+  if (row_bytes != 16 * ((n_genomes + 63) / 64)) return fail(c, KGL_B200_ERR_INVALID, "row_bytes must be 16*ceil(n_genomes/64)");
+  if (n_genomes >= (1ull << 32) || n_loci >= (1ull << 32)) return fail(c, KGL_B200_ERR_INVALID, "dimension too large");
+  if (c->have_loci && c->h_af.size() != (size_t)c->n_pop * n_loci)
+    return fail(c, KGL_B200_ERR_INVALID, "genotype matrix and allele-frequency vectors disagree on n_loci");
+  if (c->have_superpop && c->h_superpop.size() != n_genomes)
+    return fail(c, KGL_B200_ERR_INVALID, "genotype matrix and super-population vector disagree on n_genomes");
+  c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->units = row_bytes / 16; c->Npad = c->units * 64;
+  c->sm_valid = false; c->units_valid = false;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_upload_genotypes(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint64_t row_bytes, const void* packed) {
+  if (!c || !packed) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  rc = set_shape(c, n_genomes, n_loci, row_bytes); if (rc) return rc;
+  KGL_CUDA(c, c->d_packed.ensure((size_t)n_loci * row_bytes));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_packed.p, packed, (size_t)n_loci * row_bytes, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_geno = true;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const float* af, const uint32_t* offsets) {
+  if (!c || !af) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (n_pop == 0 || n_pop > KGL_B200_MAX_POP) return fail(c, KGL_B200_ERR_INVALID, "n_pop must be 1..6");
+  if (n_loci == 0) return fail(c, KGL_B200_ERR_INVALID, "n_loci is 0");
+  if (c->have_geno && c->L != n_loci) return fail(c, KGL_B200_ERR_INVALID, "allele-frequency vectors and genotype matrix disagree on n_loci");
+  int rc = use_device(c); if (rc) return rc;
+  c->h_af.assign(af, af + (size_t)n_pop * n_loci);
+  if (offsets) c->h_offsets.assign(offsets, offsets + n_loci); else c->h_offsets.clear();
+  c->n_pop = n_pop;
+  if (!c->have_geno) c->L = n_loci;
+  KGL_CUDA(c, c->d_af.ensure((size_t)n_pop * n_loci));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_af.p, af, (size_t)n_pop * n_loci * 4, cudaMemcpyHostToDevice, c->stream));
+  c->h_sel.assign(n_loci, 0);
+  KGL_CUDA(c, c->d_sel.ensure(n_loci));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, n_loci, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_loci = true; c->prep_valid = false;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_set_genome_superpop(kgl_b200_ctx* c, uint64_t n_genomes, const uint8_t* superpop) {
+  if (!c || !superpop) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (c->have_geno && c->N != n_genomes) return fail(c, KGL_B200_ERR_INVALID, "super-population vector and genotype matrix disagree on n_genomes");
+  for (uint64_t g = 0; g < n_genomes; ++g)
+    if (superpop[g] >= KGL_B200_MAX_POP) return fail(c, KGL_B200_ERR_INVALID, "super-population index must be 0..5");
+  int rc = use_device(c); if (rc) return rc;
+  c->h_superpop.assign(superpop, superpop + n_genomes);
+  KGL_CUDA(c, c->d_superpop.ensure(n_genomes));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_superpop.p, superpop, n_genomes, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_superpop = true; c->units_valid = false;
+  if (!c->have_geno) c->N = n_genomes;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_set_unphased(kgl_b200_ctx* c, int unphased) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  c->unphased = unphased != 0;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_set_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, const uint8_t* selected) {
+  if (!c || !selected) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "upload_loci first");
+  if (n_loci != c->L) return fail(c, KGL_B200_ERR_INVALID, "selection length differs from n_loci");
+  int rc = use_device(c); if (rc) return rc;
+  c->h_sel.assign(selected, selected + n_loci);
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_sel.p, selected, n_loci, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->prep_valid = false;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_get_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, uint8_t* selected) {
+  if (!c || !selected) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (n_loci != c->h_sel.size()) return fail(c, KGL_B200_ERR_INVALID, "selection length differs from n_loci");
+  std::memcpy(selected, c->h_sel.data(), n_loci);
+  return KGL_B200_OK;
+}
+
+// RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) per super-population. The spacing rule makes
+// the scan sequential in locus order; it runs once per window on the host copy of the AF vectors (not on the hot path).
+int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64_t spacing, double min_af, double max_af,
+                         uint64_t* n_selected) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "upload_loci first");
+  if (c->h_offsets.size() != c->L) return fail(c, KGL_B200_ERR_STATE, "select_loci needs the locus offsets (upload_loci with offsets)");
+  min_af = std::min(std::max(min_af, 0.0), 1.0);     // LociiVectorArguments clamps (kga_analysis_inbreed_args.h:85-86)
+  max_af = std::min(std::max(max_af, 0.0), 1.0);
+  std::vector<uint8_t> sel(c->L, 0);
+  for (uint32_t k = 0; k < c->n_pop; ++k) {
+    const float* af = c->h_af.data() + (size_t)k * c->L;
+    uint64_t previous_offset = 0, count = 0;
+    uint64_t l = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
+                                  [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
+    for (; l < c->L; ++l) {
+      const uint64_t offset = c->h_offsets[l];
+      if (offset > upper) break;
+      if (offset >= previous_offset + spacing || previous_offset == 0) {
+        const float a = af[l];
+        if (a != a) continue;                                    // empty AlleleFreqVector: invalid
+        const double p = std::min(std::max((double)a, 0.0), 1.0);
+        if (p == 0.0 || p < min_af || p > max_af) continue;
+        previous_offset = offset;
+        sel[l] |= (uint8_t)(1u << k);
+        ++count;
+      }
+    }
+    if (n_selected) n_selected[k] = count;
+  }
+  return kgl_b200_set_locus_selection(c, c->L, sel.data());
+}
+
+int kgl_b200_synth_genotypes(kgl_b200_ctx* c, uint64_t seed, uint64_t n_genomes, uint64_t n_loci, uint64_t locus_base,
+                             const double* inbreeding, double missing_rate) {
+  if (!c || !inbreeding) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->have_loci || !c->have_superpop) return fail(c, KGL_B200_ERR_STATE, "upload_loci and set_genome_superpop first");
+  if (c->h_superpop.size() != n_genomes || c->h_af.size() != (size_t)c->n_pop * n_loci)
+    return fail(c, KGL_B200_ERR_INVALID, "shape differs from the uploaded loci / super-populations");
+  int rc = use_device(c); if (rc) return rc;
+  const uint64_t row_bytes = 16 * ((n_genomes + 63) / 64);
+  rc = set_shape(c, n_genomes, n_loci, row_bytes);
+  if (rc) return rc;
+  KGL_CUDA(c, c->d_packed.ensure((size_t)n_loci * row_bytes));
+  KGL_CUDA(c, c->d_inbreeding.ensure(n_genomes));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_inbreeding.p, inbreeding, n_genomes * 8, cudaMemcpyHostToDevice, c->stream));
+  const uint64_t total = n_loci * c->units;
+  k_synth<<<blocks_for(total, 256), 256, 0, c->stream>>>(seed, n_genomes, n_loci, locus_base, c->units, c->d_af.p, c->d_superpop.p,
+                                                        c->d_inbreeding.p, (uint64_t)(missing_rate * 16777216.0),
+                                                        reinterpret_cast<uint4*>(c->d_packed.p));
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_geno = true;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_download_genotypes(kgl_b200_ctx* c, uint64_t n_bytes, void* packed) {
+  if (!c || !packed) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->have_geno) return fail(c, KGL_B200_ERR_STATE, "no genotype matrix on the device");
+  if (n_bytes != c->L * c->row_bytes) return fail(c, KGL_B200_ERR_INVALID, "n_bytes must be n_loci*row_bytes");
+  int rc = use_device(c); if (rc) return rc;
+  KGL_CUDA(c, cudaMemcpyAsync(packed, c->d_packed.p, n_bytes, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t* genome_counts) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  if (!c->have_superpop) {   // raw counting needs no super-populations: treat everyone as population 0
+    std::vector<uint8_t> zeros(c->N, 0);
+    rc = kgl_b200_set_genome_superpop(c, c->N, zeros.data()); if (rc) return rc;
+    c->have_superpop = false;
+  }
+  rc = launch_count(c, true, locus_counts != nullptr, genome_counts != nullptr); if (rc) return rc;
+  if (locus_counts)
+    KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
+  if (genome_counts) {
+    KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 4));
+    k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts.p, c->N, c->L, c->d_genome_counts.p);
+    KGL_LAUNCH_CHECK(c);
+    KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_genome_counts.p, (size_t)c->N * 32, cudaMemcpyDeviceToHost, c->stream));
+  }
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, true); if (rc) return rc;
+  c->prep_valid = false;   // the AF vectors are an input of the pass: the per-locus preparation is part of every step
+  rc = enqueue_moments(c, true); if (rc) return rc;
+  KGL_CUDA(c, c->d_results.ensure(c->Npad));
+  k_finalize_closed_form<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_partials.p, c->N, KGL_B200_ALGO_SIMPLE, c->d_results.p, nullptr);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_count_and_inbreed(kgl_b200_ctx* c, uint32_t* locus_counts, kgl_b200_locus_results* out) {
+  int rc = kgl_b200_enqueue_count_and_inbreed(c); if (rc) return rc;
+  if (locus_counts)
+    KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
+  if (out)
+    KGL_CUDA(c, cudaMemcpyAsync(out, c->d_results.p, (size_t)c->N * sizeof(kgl_b200_locus_results), cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+// ---- estimator state machine ----------------------------------------------------------------------------------------
+int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbreed_options* options) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  if (algorithm < KGL_B200_ALGO_SIMPLE || algorithm > KGL_B200_ALGO_LOGLIKELIHOOD) return fail(c, KGL_B200_ERR_INVALID, "unknown algorithm");
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, true); if (rc) return rc;
+  c->algo = algorithm; c->phase = 0; c->iteration = 0;
+  c->opt = options ? *options : kgl_b200_inbreed_options{};
+  c->hall_start.clear();
+  if (c->opt.hall_start) c->hall_start.assign(c->opt.hall_start, c->opt.hall_start + c->N);
+  c->opt.hall_start = nullptr;
+  if (c->opt.hall_sweeps == 0) c->opt.hall_sweeps = 50;        // MINIMUM_ITERATIONS_ (calc.h:124), SURVEY Q1
+  if (c->opt.ll_tolerance <= 0.0) c->opt.ll_tolerance = 1e-12;
+  if (c->opt.ll_max_iterations <= 0) c->opt.ll_max_iterations = 64;
+  KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
+  KGL_CUDA(c, c->d_iter.ensure((size_t)c->Npad * PART_COUNT));
+  KGL_CUDA(c, c->d_f.ensure(c->Npad));
+  KGL_CUDA(c, c->d_bracket.ensure((size_t)c->Npad * 2));
+  KGL_CUDA(c, c->d_done.ensure(c->Npad));
+  KGL_CUDA(c, c->d_flag.ensure(1));
+  KGL_CUDA(c, c->d_results.ensure(c->Npad));
+  return KGL_B200_OK;
+}
+
+int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
+  if (!c || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
+  int rc = use_device(c); if (rc) return rc;
+  TermLaunch tl;
+  if (c->phase == 0) {
+    rc = enqueue_moments(c, false); if (rc) return rc;
+    if (c->algo == KGL_B200_ALGO_RITLAND) {
+      rc = launch_terms<TERM_RITLAND>(c, 3, nullptr, 0, tl); if (rc) return rc;
+      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 3, c->d_totals.p,
+                                                                       c->d_superpop.p, c->N, c->d_partials.p);
+      KGL_LAUNCH_CHECK(c);
+    }
+    return KGL_B200_OK;
+  }
+  if (c->algo == KGL_B200_ALGO_HALLME) rc = launch_terms<TERM_HALL>(c, 1, nullptr, 0, tl);
+  else rc = launch_terms<TERM_NEWTON>(c, 3, nullptr, 0, tl);
+  if (rc) return rc;
+  // iteration terms live in d_iter (the all-reduce payload of this phase); the reduced moments stay in d_partials
+  k_iter_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad,
+                                                                c->algo == KGL_B200_ALGO_HALLME ? 1 : 3, c->N, c->d_iter.p);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_doubles) {
+  if (!c || !device_ptr || !n_doubles || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
+  *device_ptr = (c->phase == 0) ? (void*)c->d_partials.p : (void*)c->d_iter.p;
+  *n_doubles = c->N * PART_COUNT;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
+  if (!c || !finished || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
+  int rc = use_device(c); if (rc) return rc;
+  const unsigned nb = blocks_for(c->N, 256);
+  *finished = 0;
+  if (c->phase == 0) {
+    if (c->algo == KGL_B200_ALGO_SIMPLE || c->algo == KGL_B200_ALGO_RITLAND) {
+      k_finalize_closed_form<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->N, c->algo, c->d_results.p, nullptr);
+      KGL_LAUNCH_CHECK(c);
+      *finished = 1;
+      return KGL_B200_OK;
+    }
+    if (c->algo == KGL_B200_ALGO_HALLME) {
+      if (!c->hall_start.empty()) {
+        KGL_CUDA(c, cudaMemcpyAsync(c->d_f.p, c->hall_start.data(), c->N * 8, cudaMemcpyHostToDevice, c->stream));
+        KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+      } else {
+        k_fill_double<<<nb, 256, 0, c->stream>>>(c->d_f.p, c->N, 0.25);
+        KGL_LAUNCH_CHECK(c);
+      }
+    } else {
+      // Newton start: the Simple estimate, kept away from the box edges
+      k_finalize_closed_form<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->N, KGL_B200_ALGO_SIMPLE, nullptr, c->d_f.p);
+      KGL_LAUNCH_CHECK(c);
+      k_init_bracket<<<nb, 256, 0, c->stream>>>(c->d_bracket.p, c->d_done.p, c->N);
+      KGL_LAUNCH_CHECK(c);
+    }
+    c->phase = 1; c->iteration = 0;
+    return KGL_B200_OK;
+  }
+  // the update kernels read the (all-reduced) moments from d_partials and the (all-reduced) iteration terms from d_iter
+  KGL_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, 8, c->stream));
+  unsigned long long flag = 0;
+  ++c->iteration;
+  if (c->algo == KGL_B200_ALGO_HALLME) {
+    k_hall_update<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->d_iter.p, c->N, c->d_f.p, c->d_flag.p);
+    KGL_LAUNCH_CHECK(c);
+    if (c->opt.hall_sweeps > 0) { *finished = (c->iteration >= c->opt.hall_sweeps) ? 1 : 0; return KGL_B200_OK; }
+    KGL_CUDA(c, cudaMemcpyAsync(&flag, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    double max_delta; std::memcpy(&max_delta, &flag, 8);
+    *finished = (max_delta < 1e-15 || c->iteration >= 100000) ? 1 : 0;
+    return KGL_B200_OK;
+  }
+  k_newton_update<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->d_iter.p, c->N, c->opt.ll_tolerance, c->d_f.p, c->d_bracket.p, c->d_done.p, c->d_flag.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemcpyAsync(&flag, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  *finished = (flag == 0 || c->iteration >= c->opt.ll_max_iterations) ? 1 : 0;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_inbreed_fetch(kgl_b200_ctx* c, kgl_b200_locus_results* out) {
+  if (!c || !out || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
+  int rc = use_device(c); if (rc) return rc;
+  if (c->algo == KGL_B200_ALGO_HALLME || c->algo == KGL_B200_ALGO_LOGLIKELIHOOD) {
+    k_store_coeff<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_partials.p, c->d_f.p, c->N, c->d_results.p);
+    KGL_LAUNCH_CHECK(c);
+  }
+  KGL_CUDA(c, cudaMemcpyAsync(out, c->d_results.p, (size_t)c->N * sizeof(kgl_b200_locus_results), cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_inbreed(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbreed_options* options, kgl_b200_locus_results* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = kgl_b200_inbreed_begin(c, algorithm, options); if (rc) return rc;
+  int finished = 0;
+  while (!finished) {
+    rc = kgl_b200_inbreed_accumulate(c); if (rc) return rc;
+    rc = kgl_b200_inbreed_update(c, &finished); if (rc) return rc;
+  }
+  return kgl_b200_inbreed_fetch(c, out);
+}
+
+int kgl_b200_run_loglik_grid(kgl_b200_ctx* c, const double* grid, uint64_t n_grid, double* out) {
+  if (!c || !grid || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, true); if (rc) return rc;
+  rc = ensure_prepared(c); if (rc) return rc;
+  KGL_CUDA(c, c->d_grid.ensure(kGridMax));
+  KGL_CUDA(c, c->d_iter.ensure((size_t)c->Npad * PART_COUNT));
+  std::vector<double> host((size_t)c->N * PART_COUNT);
+  for (uint64_t g0 = 0; g0 < n_grid; g0 += kGridMax) {
+    const int ng = (int)std::min<uint64_t>(kGridMax, n_grid - g0);
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_grid.p, grid + g0, ng * 8, cudaMemcpyHostToDevice, c->stream));
+    TermLaunch tl;
+    rc = launch_terms<TERM_GRID>(c, kGridMax, c->d_grid.p, ng, tl); if (rc) return rc;
+    // reduce over chunks on the host side of the stream: reuse k_iter_partials three slots at a time is not enough for 8
+    // values, so sum the chunk outputs with a strided 2D copy + the generic reduction below
+    std::vector<double> chunks((size_t)tl.n_chunks * c->Npad * kGridMax);
+    KGL_CUDA(c, cudaMemcpyAsync(chunks.data(), c->d_chunk_out.p, chunks.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (uint64_t g = 0; g < c->N; ++g)
+      for (int j = 0; j < ng; ++j) {
+        double s = 0.0;
+        for (uint64_t ch = 0; ch < tl.n_chunks; ++ch) s += chunks[(ch * c->Npad + g) * kGridMax + j];
+        out[g * n_grid + g0 + j] = s;
+      }
+  }
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_ibs(kgl_b200_ctx* c, uint64_t row_begin, uint64_t row_end, uint32_t* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  if (row_begin >= row_end || row_end > c->N) return fail(c, KGL_B200_ERR_INVALID, "bad genome row range");
+  rc = ensure_sample_major(c); if (rc) return rc;
+  // slabs of rows keep the device result under ~1 GiB
+  const uint64_t slab_rows = std::max<uint64_t>(kIbsTile, ((1ull << 30) / (c->N * 16)) / kIbsTile * kIbsTile);
+  for (uint64_t r0 = row_begin; r0 < row_end; r0 += slab_rows) {
+    const uint64_t r1 = std::min(row_end, r0 + slab_rows);
+    const size_t n = (size_t)(r1 - r0) * c->N * 4;
+    KGL_CUDA(c, c->d_ibs.ensure(n));
+    dim3 grid((unsigned)((c->N + kIbsTile - 1) / kIbsTile), (unsigned)((r1 - r0 + kIbsTile - 1) / kIbsTile));
+    k_ibs_tile<<<grid, 256, 0, c->stream>>>(c->d_sm_lo.p, c->d_sm_hi.p, c->n_gblocks, c->n_words, c->N, r0, r1, c->d_ibs.p);
+    KGL_LAUNCH_CHECK(c);
+    KGL_CUDA(c, cudaMemcpyAsync(out + (size_t)(r0 - row_begin) * c->N * 4, c->d_ibs.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return KGL_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+// misc_kernels.cuh -- estimator finalisation, iterative updates, pairwise IBS tiles and the synthetic generator.
+#pragma once
+#include "common.cuh"
+#include "locus_kernels.cuh"
+#include "../../include/kgl_b200.h"
+
+namespace kgl {
+
+// Per-genome partial sums that are additive over locus shards (multi-GPU all-reduce payload), doubles.
+enum { PART_NMAJHOM = 0, PART_NMAJHET, PART_NMINHOM, PART_NMINHET,
+       PART_EMAJHOM, PART_EMAJHET, PART_EMINHOM, PART_EMINHET,
+       PART_RSUM, PART_RCOUNT,            // Ritland numerator / denominator
+       PART_IT0, PART_IT1, PART_IT2,      // iterative estimators: reduced per-iteration terms
+       PART_COUNT = 16 };
+
+// Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
+__global__ void __launch_bounds__(256)
+k_moment_partials(const uint32_t* __restrict__ gcounts, const double* __restrict__ totals, const double* __restrict__ ecorr,
+                  const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
+                  int unphased, double* __restrict__ partials) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const int k = superpop[g];
+  const double* T = totals + k * TOT_COUNT;
+  const double n1 = gcounts[g * 4 + 0], n2 = gcounts[g * 4 + 1], n3 = gcounts[g * 4 + 2];
+  // hom-ref cells in q > 0.01 rows: all such rows minus the non-reference cells that sit in them
+  const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - (double)nz_rare[g]);
+  double* P = partials + g * PART_COUNT;
+  P[PART_NMAJHOM] = n_majhom;
+  P[PART_NMAJHET] = n1;
+  P[PART_NMINHOM] = unphased ? 0.0 : n2;
+  P[PART_NMINHET] = unphased ? n2 : 0.0;
+  const double d_majhom = ecorr[g * 2 + 0], d_minhom = ecorr[g * 2 + 1];
+  // dropped cells: code 3 in selected rows (n3) and hom-ref cells of rare-q rows; their class frequencies leave the sums.
+  const double n_dropped = (T[TOT_T] - T[TOT_TQ]) - (double)nz_rare[g] + n3;   // rare-q rows that are hom-ref + code-3 cells
+  P[PART_EMAJHOM] = T[TOT_EMAJHOM] - d_majhom;
+  P[PART_EMINHOM] = T[TOT_EMINHOM] - d_minhom;
+  // the three normalised class frequencies of a locus sum to 1, so the dropped majHet mass is n_dropped - majHom - minHom
+  P[PART_EMAJHET] = T[TOT_EMAJHET] - (n_dropped - d_majhom - d_minhom);
+  P[PART_EMINHET] = 0.0;
+  for (int j = PART_RSUM; j < PART_COUNT; ++j) P[j] = 0.0;
+}
+
+// Adds the Ritland terms (reduced over locus chunks) to the partials.
+__global__ void __launch_bounds__(256)
+k_ritland_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_genomes_padded, int n_out,
+                   const double* __restrict__ totals, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
+                   double* __restrict__ partials) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  double s0 = 0.0, s2 = 0.0, c2x = 0.0;
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const double* o = chunk_out + (c * n_genomes_padded + g) * n_out;
+    s0 += o[0]; s2 += o[1]; c2x += o[2];
+  }
+  const int k = superpop[g];
+  double* P = partials + g * PART_COUNT;
+  const double n_het = P[PART_NMAJHET] + P[PART_NMINHET];
+  P[PART_RSUM] = (totals[k * TOT_COUNT + TOT_W0] - s0) + s2 - n_het;
+  P[PART_RCOUNT] = P[PART_NMAJHOM] + (P[PART_NMINHOM] - c2x) + n_het;
+}
+
+// Reduce the per-chunk outputs of an iterative pass into PART_IT0..2.
+__global__ void __launch_bounds__(256)
+k_iter_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_genomes_padded, int n_out,
+                uint64_t n_genomes, double* __restrict__ partials) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  double s[3] = {0.0, 0.0, 0.0};
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const double* o = chunk_out + (c * n_genomes_padded + g) * n_out;
+    for (int j = 0; j < n_out && j < 3; ++j) s[j] += o[j];
+  }
+  double* P = partials + g * PART_COUNT;
+  P[PART_IT0] = s[0]; P[PART_IT1] = s[1]; P[PART_IT2] = s[2];
+}
+
+__device__ __forceinline__ void fill_results(const double* P, kgl_b200_locus_results& r) {
+  r.major_homo_count = (uint64_t)llrint(P[PART_NMAJHOM]);   r.major_homo_freq = P[PART_EMAJHOM];
+  r.major_hetero_count = (uint64_t)llrint(P[PART_NMAJHET]); r.major_hetero_freq = P[PART_EMAJHET];
+  r.minor_homo_count = (uint64_t)llrint(P[PART_NMINHOM]);   r.minor_homo_freq = P[PART_EMINHOM];
+  r.minor_hetero_count = (uint64_t)llrint(P[PART_NMINHET]); r.minor_hetero_freq = P[PART_EMINHET];
+  r.total_allele_count = r.major_homo_count + r.major_hetero_count + r.minor_homo_count + r.minor_hetero_count;
+}
+
+// processSimple (calc.cpp:333-359) / processRitlandLocus (calc.cpp:423) closed forms from the (all-reduced) partials.
+__global__ void __launch_bounds__(256)
+k_finalize_closed_form(const double* __restrict__ partials, uint64_t n_genomes, int algorithm,
+                       kgl_b200_locus_results* __restrict__ out, double* __restrict__ f_out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const double* P = partials + g * PART_COUNT;
+  kgl_b200_locus_results r;
+  fill_results(P, r);
+  double coeff = 0.0;
+  if (algorithm == KGL_B200_ALGO_RITLAND) {
+    coeff = (P[PART_RCOUNT] > 0.0) ? P[PART_RSUM] / P[PART_RCOUNT] : 0.0;
+  } else {
+    if (r.total_allele_count > 0) {
+      const double observed_homozygous = (double)(r.minor_homo_count + r.major_homo_count);
+      const double expected_homozygous = r.minor_homo_freq + r.major_homo_freq;
+      coeff = (observed_homozygous - expected_homozygous) / ((double)r.total_allele_count - expected_homozygous);
+    }
+  }
+  r.inbred_allele_sum = coeff;
+  if (out) out[g] = r;
+  if (f_out) f_out[g] = coeff;
+}
+
+// processHallME: f <- (1/n) * sum_hom f/(f+(1-f)a)   (calc.cpp:285). flag[0] = max |delta| bits (atomicMax on the ordered int).
+__global__ void __launch_bounds__(256)
+k_hall_update(const double* __restrict__ partials, const double* __restrict__ iter, uint64_t n_genomes, double* __restrict__ f,
+              unsigned long long* __restrict__ flag) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const double* P = partials + g * PART_COUNT;
+  const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
+  const double nf = __ddiv_rn(iter[g * PART_COUNT + PART_IT0], n);
+  const double delta = fabs(nf - f[g]);
+  f[g] = nf;
+  if (delta == delta) atomicMax(flag, (unsigned long long)__double_as_longlong(delta));   // non-negative doubles order like ints
+}
+
+// Safeguarded Newton on dLL/df: bracket [a,b]; a clamped homozygous term means f is left of the
+// concave region, so the bracket moves right; otherwise the sign of the derivative updates the bracket and the Newton
+// step is accepted only inside it. state = {a, b, done}.
+__global__ void __launch_bounds__(256)
+k_newton_update(const double* __restrict__ partials, const double* __restrict__ iter, uint64_t n_genomes, double tol, double* __restrict__ f,
+                double* __restrict__ bracket /* [n][2] */, uint32_t* __restrict__ done, unsigned long long* __restrict__ flag) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  if (done[g]) return;
+  const double* P = partials + g * PART_COUNT;
+  const double* I = iter + g * PART_COUNT;
+  const double g1 = I[PART_IT0], g2 = I[PART_IT1], clamped = I[PART_IT2];
+  const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
+  double a = bracket[g * 2], b = bracket[g * 2 + 1];
+  const double x = f[g];
+  double nx;
+  if (n <= 0.0) { f[g] = 0.0; done[g] = 1; return; }
+  if (clamped > 0.0 || g1 > 0.0) a = x; else b = x;
+  bool newton_ok = false;
+  if (clamped == 0.0 && g2 < 0.0) {
+    nx = x - g1 / g2;
+    newton_ok = (nx > a) && (nx < b) && (nx == nx);
+  }
+  if (!newton_ok) nx = 0.5 * (a + b);
+  bracket[g * 2] = a; bracket[g * 2 + 1] = b;
+  const double step = fabs(nx - x);
+  f[g] = nx;
+  if (step < tol || (b - a) < tol) done[g] = 1;
+  else atomicAdd(flag, 1ull);
+}
+
+__global__ void __launch_bounds__(256)
+k_store_coeff(const double* __restrict__ partials, const double* __restrict__ f, uint64_t n_genomes,
+              kgl_b200_locus_results* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  kgl_b200_locus_results r;
+  fill_results(partials + g * PART_COUNT, r);
+  r.inbred_allele_sum = f[g];
+  out[g] = r;
+}
+
+__global__ void k_fill_double(double* p, uint64_t n, double v) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void k_init_bracket(double* bracket, uint32_t* done, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { bracket[i * 2] = -1.0; bracket[i * 2 + 1] = 1.0; done[i] = 0; }
+}
+
+__global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, uint64_t n_genomes, uint64_t n_loci, uint64_t* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const uint64_t n1 = gcounts[g * 4], n2 = gcounts[g * 4 + 1], n3 = gcounts[g * 4 + 2];
+  out[g * 4 + 0] = n_loci - n1 - n2 - n3; out[g * 4 + 1] = n1; out[g * 4 + 2] = n2; out[g * 4 + 3] = n3;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4: pairwise IBS tile kernel. CTA = 64x64 genome pairs, thread = 4x4 pairs, 32-locus words staged in shared memory as
+// thermometer planes X = (g>=1), Y = (g==2), V = valid. Per pair and word: 2 XOR + 3 LOP3 + 3 POPC + 3 IADD.
+constexpr int kIbsTile = 64;
+constexpr int kIbsWords = 16;   // words per shared-memory stage
+
+__global__ void __launch_bounds__(256)
+k_ibs_tile(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi, uint64_t n_gblocks, uint64_t n_words,
+           uint64_t n_genomes, uint64_t row_begin, uint64_t row_end, uint32_t* __restrict__ out /* [rows][n_genomes][4] */) {
+  __shared__ __align__(16) uint32_t sA[3][kIbsWords][kIbsTile];
+  __shared__ __align__(16) uint32_t sB[3][kIbsWords][kIbsTile];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const uint64_t a0 = row_begin + (uint64_t)blockIdx.y * kIbsTile;   // rows of this tile
+  const uint64_t b0 = (uint64_t)blockIdx.x * kIbsTile;               // columns of this tile
+  uint32_t c0[4][4], c1[4][4], cv[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c0[i][j] = 0; c1[i][j] = 0; cv[i][j] = 0; }
+
+  for (uint64_t w0 = 0; w0 < n_words; w0 += kIbsWords) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kIbsWords * kIbsTile; i += 256) {
+      const int w = i / kIbsTile, gi = i % kIbsTile;
+      uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
+      const uint64_t ga = a0 + gi;
+      if (ga < n_genomes && w0 + w < n_words) {
+        const uint64_t o = ((ga >> 5) * n_words + w0 + w) * 32 + (ga & 31);
+        lo = sm_lo[o]; hi = sm_hi[o];
+      }
+      sA[0][w][gi] = lo ^ hi; sA[1][w][gi] = hi & ~lo; sA[2][w][gi] = ~(lo & hi);
+      lo = 0xFFFFFFFFu; hi = 0xFFFFFFFFu;
+      const uint64_t gbb = b0 + gi;
+      if (gbb < n_genomes && w0 + w < n_words) {
+        const uint64_t o = ((gbb >> 5) * n_words + w0 + w) * 32 + (gbb & 31);
+        lo = sm_lo[o]; hi = sm_hi[o];
+      }
+      sB[0][w][gi] = lo ^ hi; sB[1][w][gi] = hi & ~lo; sB[2][w][gi] = ~(lo & hi);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int w = 0; w < kIbsWords; ++w) {
+      const uint4 ax = *reinterpret_cast<const uint4*>(&sA[0][w][ty * 4]);
+      const uint4 ay = *reinterpret_cast<const uint4*>(&sA[1][w][ty * 4]);
+      const uint4 av = *reinterpret_cast<const uint4*>(&sA[2][w][ty * 4]);
+      const uint4 bx = *reinterpret_cast<const uint4*>(&sB[0][w][tx * 4]);
+      const uint4 by = *reinterpret_cast<const uint4*>(&sB[1][w][tx * 4]);
+      const uint4 bv = *reinterpret_cast<const uint4*>(&sB[2][w][tx * 4]);
+      const uint32_t AX[4] = {ax.x, ax.y, ax.z, ax.w}, AY[4] = {ay.x, ay.y, ay.z, ay.w}, AV[4] = {av.x, av.y, av.z, av.w};
+      const uint32_t BX[4] = {bx.x, bx.y, bx.z, bx.w}, BY[4] = {by.x, by.y, by.z, by.w}, BV[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t dx = AX[i] ^ BX[j], dy = AY[i] ^ BY[j], v = AV[i] & BV[j];
+          c0[i][j] += __popc(dx & dy & v);          // |ga-gb| == 2
+          c1[i][j] += __popc((dx ^ dy) & v);        // |ga-gb| == 1
+          cv[i][j] += __popc(v);
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t ga = a0 + ty * 4 + i;
+    if (ga >= row_end || ga >= n_genomes) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t gbb = b0 + tx * 4 + j;
+      if (gbb >= n_genomes) continue;
+      *reinterpret_cast<uint4*>(out + ((ga - row_begin) * n_genomes + gbb) * 4) =
+          make_uint4(c0[i][j], c1[i][j], cv[i][j] - c0[i][j] - c1[i][j], cv[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Synthetic genotypes, bit-identical to kgl_gene_b200/synth.py (numpy) -- the tests compare the two cell by cell.
+// One thread = one 128-bit unit (64 genomes) of one locus row.
+__global__ void __launch_bounds__(256)
+k_synth(uint64_t seed, uint64_t n_genomes, uint64_t n_loci, uint64_t locus_base, uint64_t units,
+        const float* __restrict__ af, const uint8_t* __restrict__ superpop, const double* __restrict__ inbreeding,
+        uint64_t miss_threshold, uint4* __restrict__ packed) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_loci * units) return;
+  const uint64_t l = idx / units, unit = idx % units;
+  uint64_t lo = 0, hi = 0;
+  for (int b = 0; b < 64; ++b) {
+    const uint64_t g = unit * 64 + b;
+    if (g >= n_genomes) break;
+    const float a = af[(uint64_t)superpop[g] * n_loci + l];
+    double p = (double)a;
+    p = (a != a) ? 0.0 : (p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p));
+    const double q = __dsub_rn(1.0, p), F = inbreeding[g];
+    const double pq = __dmul_rn(p, q);
+    const double t0 = __dadd_rn(__dmul_rn(q, q), __dmul_rn(F, pq));
+    const double t1 = __dadd_rn(t0, __dmul_rn(__dmul_rn(2.0, pq), __dsub_rn(1.0, F)));
+    const uint64_t h1 = mix64(seed ^ ((locus_base + l) << 32) ^ g);
+    const uint64_t h2 = mix64(h1 ^ 0xD6E8FEB86659FD93ULL);
+    const double u = __dmul_rn((double)(h1 >> 11), 1.0 / 9007199254740992.0);
+    unsigned code = (unsigned)(u >= t0) + (unsigned)(u >= t1);
+    if ((h2 >> 40) < miss_threshold) code = 3;
+    lo |= (uint64_t)(code & 1u) << b;
+    hi |= (uint64_t)(code >> 1) << b;
+  }
+  packed[idx] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
+}  // namespace kgl

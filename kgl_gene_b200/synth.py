@@ -53,7 +53,7 @@ def make_genomes(n_genomes: int, seed: int, grouped: bool = True):
 
 def synth_codes(seed: int, af: np.ndarray, superpop: np.ndarray, inbreeding: np.ndarray,
                 missing_rate: float = 0.001, locus_base: int = 0) -> np.ndarray:
-    """uint8 [L, N] genotype codes; bit-identical to kgl_oracle_synth_genotypes / kgl_b200_synth_genotypes."""
+    """uint8 [L, N] genotype codes; bit-identical to the device generator kgl_b200_synth_genotypes (and to the CPU checker used by the tests)."""
     n_loci = af.shape[1]
     n = superpop.shape[0]
     a = af[superpop.astype(np.int64), :].T.astype(np.float64)           # [L, N]

@@ -1,0 +1,231 @@
+"""GPU parity tests: every call goes through the C ABI (kgl_gene_b200/libkgl_b200.so) and is compared with
+(a) the committed golden vectors produced by the reference's own code and (b) the CPU oracle on seeded inputs.
+Integer results (allele counts, class counts, locus selection, IBS) must be bit-exact; floating-point results must
+agree within 1e-6 relative (BASELINE.json north_star) -- the assertions below use far tighter bounds where the
+arithmetic allows it."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+from conftest import results_matrix
+
+pytestmark = pytest.mark.gpu
+
+SUPER_POPS = ["AFR", "AMR", "EAS", "EUR", "SAS", "ALL"]
+REL = 1e-6          # the contract
+TIGHT = 1e-11       # what double arithmetic in a different summation order actually gives
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from kgl_gene_b200.capi import KglB200
+    ctx = KglB200(0)
+    yield ctx
+    ctx.close()
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if a.size else 0.0
+
+
+def sel_bits(sel):   # uint8 [6, L] -> bit mask per locus
+    return np.bitwise_or.reduce(sel.astype(np.uint8) << np.arange(sel.shape[0], dtype=np.uint8)[:, None], axis=0).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------- golden (reference) ----
+def test_golden_locus_selection(gpu, golden):
+    name, pop, ref, sel_kw = golden
+    gpu.upload_population(pop)
+    counts = gpu.select_loci(**sel_kw)
+    bits = gpu.get_locus_selection()
+    for k, sp in enumerate(SUPER_POPS):
+        chosen = pop.offsets[(bits >> k) & 1 == 1]
+        assert np.array_equal(chosen, ref["selected_offsets_" + sp]), (name, sp)
+        assert counts[k] == len(ref["selected_offsets_" + sp])
+
+
+def test_golden_simple_and_counts(gpu, golden):
+    name, pop, ref, sel_kw = golden
+    gpu.upload_population(pop)
+    gpu.select_loci(**sel_kw)
+    lc, res = gpu.count_and_inbreed()
+    counts, freqs = results_matrix(res)
+    present = ref["genome_present"] == 1
+    assert np.array_equal(counts[present], ref["Simple_counts"][present])                 # bit-exact
+    assert rel_err(freqs[present][:, :3], ref["Simple_freqs"][present][:, :3]) < TIGHT
+    assert np.all(freqs[:, 3] == 0.0)
+    assert rel_err(res["inbred_allele_sum"][present], ref["Simple_coeff"][present]) < 1e-9
+    # per-locus allele counts vs VariantDBVariant::summaryByVariant
+    m = ref["variant_present"] == 1
+    sv = ref["summary_by_variant"]
+    assert np.array_equal(lc[m, 1], sv[m, 1]) and np.array_equal(lc[m, 2], sv[m, 2])
+    assert np.array_equal((lc[m, 0] + lc[m, 3]).astype(np.uint64), sv[m, 0])
+
+
+def test_golden_allele_count(gpu, golden):
+    name, pop, ref, _ = golden
+    gpu.upload_population(pop)
+    lc, gc = gpu.allele_count()
+    olc, ogc = O.allele_count(pop)
+    assert np.array_equal(lc, olc) and np.array_equal(gc, ogc)
+    sg = ref["summary_by_genome"]
+    present = ref["genome_present"] == 1
+    assert np.array_equal(sg[present, 1], gc[present, 1] + gc[present, 3]) and np.array_equal(sg[present, 2], gc[present, 2])
+
+
+def test_golden_ritland(gpu, golden):
+    name, pop, ref, sel_kw = golden
+    gpu.upload_population(pop)
+    gpu.select_loci(**sel_kw)
+    res = gpu.inbreed("RitlandLocus")
+    counts, freqs = results_matrix(res)
+    present = ref["genome_present"] == 1
+    assert np.array_equal(counts[present], ref["RitlandLocus_counts"][present])
+    assert rel_err(res["inbred_allele_sum"][present], ref["RitlandLocus_coeff"][present]) < 1e-9
+
+
+def test_golden_hallme_fifty_sweeps(gpu, golden):
+    name, pop, ref, sel_kw = golden
+    gpu.upload_population(pop)
+    gpu.select_loci(**sel_kw)
+    start = np.full(pop.n_genomes, ref["hall_start_sequence"][4])
+    res = gpu.inbreed("HallME", hall_start=start, hall_sweeps=50)
+    present = ref["genome_present"] == 1
+    assert rel_err(res["inbred_allele_sum"][present], ref["HallME_coeff"][present]) < 1e-9
+
+
+def test_golden_loglikelihood(gpu, golden):
+    name, pop, ref, sel_kw = golden
+    gpu.upload_population(pop)
+    gpu.select_loci(**sel_kw)
+    present = ref["genome_present"] == 1
+    ll = gpu.loglik_grid(ref["ll_grid"])
+    assert rel_err(ll[present], ref["ll_grid_values"][present]) < 1e-12
+    res = gpu.inbreed("Loglikelihood")
+    sel = O.select_all_pops(pop, **sel_kw)
+    opt = O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"]
+    # converged optimum of the same objective: <= 1e-9; the reference's own Nelder-Mead stops at xtol 1e-6
+    assert np.max(np.abs(res["inbred_allele_sum"][present] - opt[present])) < 1e-9
+    assert np.max(np.abs(res["inbred_allele_sum"][present] - ref["Loglikelihood_coeff"][present])) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ oracle, seeded ----
+CASES = [
+    dict(n_genomes=300, n_loci=20000, seed=1, spectrum="sfs", grouped=True),
+    dict(n_genomes=257, n_loci=9000, seed=2, spectrum="dense", grouped=False),             # mixed-population units
+    dict(n_genomes=64, n_loci=4097, seed=3, spectrum="sfs", unphased=True),
+    dict(n_genomes=1, n_loci=100, seed=4, spectrum="dense"),                                # single genome
+    dict(n_genomes=2504, n_loci=3000, seed=5, spectrum="sfs", missing_rate=0.02, missing_af_rate=0.02),
+    dict(n_genomes=130, n_loci=31, seed=6, spectrum="dense"),                               # fewer loci than one word
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"N{c['n_genomes']}xL{c['n_loci']}")
+def test_all_estimators_match_oracle(gpu, case):
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(**case)
+    if case["seed"] == 1:   # exercise q <= 0.01 rows and p <= 0.001 on a big case
+        pop.af[:, ::97] = np.float32(0.996)
+        pop.af[:, 5::89] = np.float32(0.0004)
+    sel_kw = dict(spacing=20 if case["seed"] % 2 else 0, min_af=0.0, max_af=1.0)
+    sel = O.select_all_pops(pop, **sel_kw)
+    gpu.upload_population(pop)
+    gpu.select_loci(**sel_kw)
+    assert np.array_equal(gpu.get_locus_selection(), sel_bits(sel))
+
+    lc, gc = gpu.allele_count()
+    olc, ogc = O.allele_count(pop)
+    assert np.array_equal(lc, olc) and np.array_equal(gc, ogc)
+
+    lc2, res = gpu.count_and_inbreed()
+    assert np.array_equal(lc2, olc)
+    for algo, got in (("Simple", res), ("RitlandLocus", gpu.inbreed("RitlandLocus"))):
+        want = O.inbreed(pop, sel, algo)
+        c_got, f_got = results_matrix(got)
+        c_want, f_want = results_matrix(want)
+        assert np.array_equal(c_got, c_want), algo
+        assert rel_err(f_got[:, :3], f_want[:, :3]) < TIGHT, algo
+        ok = c_want[:, 4] > 0
+        assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])
+                      / np.maximum(np.abs(want["inbred_allele_sum"][ok]), 1e-3)) < 1e-8, algo
+
+    start = np.linspace(0.05, 0.5, pop.n_genomes)
+    got = gpu.inbreed("HallME", hall_start=start, hall_sweeps=50)
+    want = O.inbreed(pop, sel, "HallME", start=start, sweeps=50)
+    ok = results_matrix(want)[0][:, 4] > 0
+    assert rel_err(got["inbred_allele_sum"][ok], want["inbred_allele_sum"][ok]) < 1e-9
+
+    grid = np.array([-0.4, -0.05, 0.0, 0.07, 0.3, 0.9])
+    assert rel_err(gpu.loglik_grid(grid)[ok], O.loglik_grid(pop, sel, grid)[ok]) < 1e-12
+    got = gpu.inbreed("Loglikelihood")
+    want = O.inbreed(pop, sel, "Loglikelihood")
+    # the optimum is only defined up to the flatness of the objective: compare objective values, then locations
+    if pop.n_loci >= 1000:
+        assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-7
+
+
+def test_hallme_fixed_point(gpu):
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(96, 6000, seed=11)
+    sel = O.select_all_pops(pop)
+    gpu.upload_population(pop)
+    gpu.select_loci()
+    got = gpu.inbreed("HallME", hall_sweeps=-1)
+    want = O.inbreed(pop, sel, "HallME", sweeps=-1)
+    assert np.max(np.abs(got["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-9
+
+
+def test_ibs_matches_oracle(gpu):
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(150, 3001, seed=21, missing_rate=0.03)
+    gpu.upload_population(pop)
+    assert np.array_equal(gpu.ibs(), O.ibs(pop))
+    assert np.array_equal(gpu.ibs(64, 130), O.ibs(pop)[64:130])
+
+
+def test_device_generator_matches_numpy(gpu):
+    from kgl_gene_b200.synth import make_genomes, make_loci, synth_codes
+    from kgl_gene_b200.flatfile import pack_codes
+    offsets, af = make_loci(700, 9)
+    superpop, f = make_genomes(333, 9)
+    gpu.upload_loci(af, offsets)
+    gpu.set_genome_superpop(superpop)
+    gpu.synth_genotypes(1234, 333, 700, f, missing_rate=0.01, locus_base=5)
+    assert np.array_equal(gpu.download_genotypes(), pack_codes(synth_codes(1234, af, superpop, f, 0.01, locus_base=5)))
+
+
+def test_wide_population_multi_slice(gpu):
+    """More than 16384 genomes: a locus row spans several CTA slices (global-atomic locus counts)."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(16384 + 777, 160, seed=31)
+    sel = O.select_all_pops(pop)
+    gpu.upload_population(pop)
+    gpu.select_loci()
+    lc, res = gpu.count_and_inbreed()
+    olc, _ = O.allele_count(pop)
+    assert np.array_equal(lc, olc)
+    want = O.inbreed(pop, sel, "Simple")
+    assert np.array_equal(results_matrix(res)[0], results_matrix(want)[0])
+
+
+def test_full_width_properties_on_device_generated_population(gpu):
+    """chr22-shaped width (2,504 genomes), generated on the device: size-independent invariants."""
+    from kgl_gene_b200.synth import make_genomes, make_loci
+    n, l = 2504, 200_000
+    offsets, af = make_loci(l, 77)
+    superpop, f = make_genomes(n, 77)
+    gpu.upload_loci(af, offsets)
+    gpu.set_genome_superpop(superpop)
+    gpu.synth_genotypes(77, n, l, f)
+    gpu.select_loci()
+    lc, gc = gpu.allele_count()
+    assert np.all(lc.sum(axis=1) == n) and np.all(gc.sum(axis=1) == l)
+    assert np.array_equal(lc.sum(axis=0).astype(np.uint64), gc.sum(axis=0))               # checksum of checksums
+    lc2, res = gpu.count_and_inbreed()
+    assert np.array_equal(lc, lc2)
+    counts, freqs = results_matrix(res)
+    # every locus is selected for every population here, so classified + dropped = all loci
+    assert np.all(counts[:, 4] <= l) and np.all(counts[:, 1] == gc[:, 1]) and np.all(counts[:, 2] == gc[:, 2])
+    assert np.allclose(freqs.sum(axis=1), counts[:, 4], rtol=1e-12)                       # Q8: class frequencies sum to n
+    assert np.corrcoef(res["inbred_allele_sum"], f)[0, 1] > 0.99                          # recovers the planted F
