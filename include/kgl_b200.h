@@ -69,8 +69,9 @@ typedef struct kgl_b200_inbreed_options {
    * from a random start in (0,0.5]; sweeps == 0 means 50; sweeps < 0 iterates to the EM fixed point. */
   const double* hall_start;
   int32_t hall_sweeps;
-  /* Loglikelihood: safeguarded Newton on the reference objective, stops when |step| < ll_tolerance (0 = 1e-12) or
-   * after ll_max_iterations (0 = 64). */
+  /* Loglikelihood: bracketed Newton on d/df of the reference objective over the feasible region (no homozygous
+   * probability clamped), from the Simple estimate; stops when |step| < ll_tolerance (0 = 1e-12) or after
+   * ll_max_iterations (0 = 200). */
   double ll_tolerance;
   int32_t ll_max_iterations;
   int32_t reserved;

@@ -399,10 +399,10 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   if (n_genomes == 0 || n_loci == 0) return fail(c, KGL_B200_ERR_INVALID, "empty genotype matrix");
   if (row_bytes != 16 * ((n_genomes + 63) / 64)) return fail(c, KGL_B200_ERR_INVALID, "row_bytes must be 16*ceil(n_genomes/64)");
   if (n_genomes >= (1ull << 32) || n_loci >= (1ull << 32)) return fail(c, KGL_B200_ERR_INVALID, "dimension too large");
-  if (c->have_loci && c->h_af.size() != (size_t)c->n_pop * n_loci)
-    return fail(c, KGL_B200_ERR_INVALID, "genotype matrix and allele-frequency vectors disagree on n_loci");
-  if (c->have_superpop && c->h_superpop.size() != n_genomes)
-    return fail(c, KGL_B200_ERR_INVALID, "genotype matrix and super-population vector disagree on n_genomes");
+  // A matrix of a different shape starts a new population: stale loci / super-populations must be uploaded again
+  // (require_population reports what is missing at run time).
+  if (c->have_loci && c->h_af.size() != (size_t)c->n_pop * n_loci) { c->have_loci = false; c->prep_valid = false; }
+  if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->units = row_bytes / 16; c->Npad = c->units * 64;
   c->sm_valid = false; c->units_valid = false;
   return KGL_B200_OK;
@@ -423,7 +423,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   if (!c || !af) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   if (n_pop == 0 || n_pop > KGL_B200_MAX_POP) return fail(c, KGL_B200_ERR_INVALID, "n_pop must be 1..6");
   if (n_loci == 0) return fail(c, KGL_B200_ERR_INVALID, "n_loci is 0");
-  if (c->have_geno && c->L != n_loci) return fail(c, KGL_B200_ERR_INVALID, "allele-frequency vectors and genotype matrix disagree on n_loci");
+  if (c->have_geno && c->L != n_loci) c->have_geno = false;   // new population: the old matrix no longer applies
   int rc = use_device(c); if (rc) return rc;
   c->h_af.assign(af, af + (size_t)n_pop * n_loci);
   if (offsets) c->h_offsets.assign(offsets, offsets + n_loci); else c->h_offsets.clear();
@@ -441,7 +441,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
 
 int kgl_b200_set_genome_superpop(kgl_b200_ctx* c, uint64_t n_genomes, const uint8_t* superpop) {
   if (!c || !superpop) return fail(c, KGL_B200_ERR_INVALID, "null argument");
-  if (c->have_geno && c->N != n_genomes) return fail(c, KGL_B200_ERR_INVALID, "super-population vector and genotype matrix disagree on n_genomes");
+  if (c->have_geno && c->N != n_genomes) c->have_geno = false;   // new population
   for (uint64_t g = 0; g < n_genomes; ++g)
     if (superpop[g] >= KGL_B200_MAX_POP) return fail(c, KGL_B200_ERR_INVALID, "super-population index must be 0..5");
   int rc = use_device(c); if (rc) return rc;
@@ -602,11 +602,13 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   c->opt.hall_start = nullptr;
   if (c->opt.hall_sweeps == 0) c->opt.hall_sweeps = 50;        // MINIMUM_ITERATIONS_ (calc.h:124), SURVEY Q1
   if (c->opt.ll_tolerance <= 0.0) c->opt.ll_tolerance = 1e-12;
-  if (c->opt.ll_max_iterations <= 0) c->opt.ll_max_iterations = 64;
+  if (c->opt.ll_max_iterations <= 0) c->opt.ll_max_iterations = 200;
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
-  KGL_CUDA(c, c->d_iter.ensure((size_t)c->Npad * PART_COUNT));
+  KGL_CUDA(c, c->d_iter.ensure((size_t)c->Npad * ITER_COUNT));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_iter.p, 0, (size_t)c->Npad * ITER_COUNT * 8, c->stream));
   KGL_CUDA(c, c->d_f.ensure(c->Npad));
-  KGL_CUDA(c, c->d_bracket.ensure((size_t)c->Npad * 2));
+  KGL_CUDA(c, c->d_bracket.ensure((size_t)c->Npad * 4));
+  KGL_CUDA(c, c->d_grid.ensure(kGridMax));
   KGL_CUDA(c, c->d_done.ensure(c->Npad));
   KGL_CUDA(c, c->d_flag.ensure(1));
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
@@ -627,12 +629,15 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
     }
     return KGL_B200_OK;
   }
-  if (c->algo == KGL_B200_ALGO_HALLME) rc = launch_terms<TERM_HALL>(c, 1, nullptr, 0, tl);
-  else rc = launch_terms<TERM_NEWTON>(c, 3, nullptr, 0, tl);
-  if (rc) return rc;
-  // iteration terms live in d_iter (the all-reduce payload of this phase); the reduced moments stay in d_partials
-  k_iter_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad,
-                                                                c->algo == KGL_B200_ALGO_HALLME ? 1 : 3, c->N, c->d_iter.p);
+  const unsigned nb = blocks_for(c->N, 256);
+  if (c->algo == KGL_B200_ALGO_HALLME) {
+    rc = launch_terms<TERM_HALL>(c, 1, nullptr, 0, tl); if (rc) return rc;
+    k_iter_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 1, c->N, 0, 1, c->d_iter.p);
+    KGL_LAUNCH_CHECK(c);
+    return KGL_B200_OK;
+  }
+  rc = launch_terms<TERM_NEWTON>(c, 4, nullptr, 0, tl); if (rc) return rc;
+  k_iter_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 4, c->N, 0, 4, c->d_iter.p);
   KGL_LAUNCH_CHECK(c);
   return KGL_B200_OK;
 }
@@ -640,7 +645,7 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
 int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_doubles) {
   if (!c || !device_ptr || !n_doubles || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
   *device_ptr = (c->phase == 0) ? (void*)c->d_partials.p : (void*)c->d_iter.p;
-  *n_doubles = c->N * PART_COUNT;
+  *n_doubles = c->N * (uint64_t)((c->phase == 0) ? PART_COUNT : ITER_COUNT);
   return KGL_B200_OK;
 }
 
@@ -665,10 +670,7 @@ int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
         KGL_LAUNCH_CHECK(c);
       }
     } else {
-      // Newton start: the Simple estimate, kept away from the box edges
-      k_finalize_closed_form<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->N, KGL_B200_ALGO_SIMPLE, nullptr, c->d_f.p);
-      KGL_LAUNCH_CHECK(c);
-      k_init_bracket<<<nb, 256, 0, c->stream>>>(c->d_bracket.p, c->d_done.p, c->N);
+      k_ll_init<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->N, c->d_f.p, c->d_bracket.p, c->d_done.p);
       KGL_LAUNCH_CHECK(c);
     }
     c->phase = 1; c->iteration = 0;
@@ -677,8 +679,8 @@ int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
   // the update kernels read the (all-reduced) moments from d_partials and the (all-reduced) iteration terms from d_iter
   KGL_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, 8, c->stream));
   unsigned long long flag = 0;
-  ++c->iteration;
   if (c->algo == KGL_B200_ALGO_HALLME) {
+    ++c->iteration;
     k_hall_update<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->d_iter.p, c->N, c->d_f.p, c->d_flag.p);
     KGL_LAUNCH_CHECK(c);
     if (c->opt.hall_sweeps > 0) { *finished = (c->iteration >= c->opt.hall_sweeps) ? 1 : 0; return KGL_B200_OK; }
@@ -688,7 +690,8 @@ int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
     *finished = (max_delta < 1e-15 || c->iteration >= 100000) ? 1 : 0;
     return KGL_B200_OK;
   }
-  k_newton_update<<<nb, 256, 0, c->stream>>>(c->d_partials.p, c->d_iter.p, c->N, c->opt.ll_tolerance, c->d_f.p, c->d_bracket.p, c->d_done.p, c->d_flag.p);
+  ++c->iteration;
+  k_ll_step<<<nb, 256, 0, c->stream>>>(c->d_iter.p, c->N, c->opt.ll_tolerance, c->d_f.p, c->d_bracket.p, c->d_done.p, c->d_flag.p);
   KGL_LAUNCH_CHECK(c);
   KGL_CUDA(c, cudaMemcpyAsync(&flag, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -725,8 +728,6 @@ int kgl_b200_run_loglik_grid(kgl_b200_ctx* c, const double* grid, uint64_t n_gri
   rc = require_population(c, true); if (rc) return rc;
   rc = ensure_prepared(c); if (rc) return rc;
   KGL_CUDA(c, c->d_grid.ensure(kGridMax));
-  KGL_CUDA(c, c->d_iter.ensure((size_t)c->Npad * PART_COUNT));
-  std::vector<double> host((size_t)c->N * PART_COUNT);
   for (uint64_t g0 = 0; g0 < n_grid; g0 += kGridMax) {
     const int ng = (int)std::min<uint64_t>(kGridMax, n_grid - g0);
     KGL_CUDA(c, cudaMemcpyAsync(c->d_grid.p, grid + g0, ng * 8, cudaMemcpyHostToDevice, c->stream));

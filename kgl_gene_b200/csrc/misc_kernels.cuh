@@ -10,8 +10,10 @@ namespace kgl {
 enum { PART_NMAJHOM = 0, PART_NMAJHET, PART_NMINHOM, PART_NMINHET,
        PART_EMAJHOM, PART_EMAJHET, PART_EMINHOM, PART_EMINHET,
        PART_RSUM, PART_RCOUNT,            // Ritland numerator / denominator
-       PART_IT0, PART_IT1, PART_IT2,      // iterative estimators: reduced per-iteration terms
        PART_COUNT = 16 };
+// Per-iteration payload of the iterative estimators (second all-reduce buffer): HallME uses slot 0, the likelihood
+// root search slots 0..3 = {dLL, d2LL, clamped hom terms, clamped het terms}.
+constexpr int ITER_COUNT = 4;
 
 // Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
 __global__ void __launch_bounds__(256)
@@ -60,19 +62,17 @@ k_ritland_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint
   P[PART_RCOUNT] = P[PART_NMAJHOM] + (P[PART_NMINHOM] - c2x) + n_het;
 }
 
-// Reduce the per-chunk outputs of an iterative pass into PART_IT0..2.
+// Reduce the per-chunk outputs of an iterative pass into iter[g][slot0 .. slot0+n_take).
 __global__ void __launch_bounds__(256)
-k_iter_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_genomes_padded, int n_out,
-                uint64_t n_genomes, double* __restrict__ partials) {
+k_iter_reduce(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_genomes_padded, int n_out,
+              uint64_t n_genomes, int slot0, int n_take, double* __restrict__ iter) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
-  double s[3] = {0.0, 0.0, 0.0};
-  for (uint64_t c = 0; c < n_chunks; ++c) {
-    const double* o = chunk_out + (c * n_genomes_padded + g) * n_out;
-    for (int j = 0; j < n_out && j < 3; ++j) s[j] += o[j];
+  for (int j = 0; j < n_take; ++j) {
+    double s = 0.0;
+    for (uint64_t c = 0; c < n_chunks; ++c) s += chunk_out[(c * n_genomes_padded + g) * n_out + j];
+    iter[g * ITER_COUNT + slot0 + j] = s;
   }
-  double* P = partials + g * PART_COUNT;
-  P[PART_IT0] = s[0]; P[PART_IT1] = s[1]; P[PART_IT2] = s[2];
 }
 
 __device__ __forceinline__ void fill_results(const double* P, kgl_b200_locus_results& r) {
@@ -115,40 +115,58 @@ k_hall_update(const double* __restrict__ partials, const double* __restrict__ it
   if (g >= n_genomes) return;
   const double* P = partials + g * PART_COUNT;
   const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
-  const double nf = __ddiv_rn(iter[g * PART_COUNT + PART_IT0], n);
+  const double nf = __ddiv_rn(iter[g * ITER_COUNT], n);
   const double delta = fabs(nf - f[g]);
   f[g] = nf;
   if (delta == delta) atomicMax(flag, (unsigned long long)__double_as_longlong(delta));   // non-negative doubles order like ints
 }
 
-// Safeguarded Newton on dLL/df: bracket [a,b]; a clamped homozygous term means f is left of the
-// concave region, so the bracket moves right; otherwise the sign of the derivative updates the bracket and the Newton
-// step is accepted only inside it. state = {a, b, done}.
+// ---- log-likelihood maximiser (processLogLikelihood, calc.cpp:154-216) --------------------------------------------
+// The reference maximises the clamped objective over [-1,1] with Nelder-Mead from random starts. The clamp at 1e-10 is a
+// numerical guard: left of the largest pole of a homozygous term the objective has convex kinks and extra local maxima,
+// and which one Nelder-Mead returns depends on its random start. The product returns the maximiser over the FEASIBLE
+// region (no homozygous probability clamped), where the objective is smooth and concave -- this is what the reference
+// returns for every genome of the golden fixtures (tests/test_oracle_vs_reference.py). Bracketed Newton on dLL/df:
+// a clamped homozygous term means "left of the feasible region" (move right); otherwise the sign of dLL/df updates the
+// bracket and the Newton step is taken when it stays inside it (else bisection). state: bracket a,b ; done flag.
 __global__ void __launch_bounds__(256)
-k_newton_update(const double* __restrict__ partials, const double* __restrict__ iter, uint64_t n_genomes, double tol, double* __restrict__ f,
-                double* __restrict__ bracket /* [n][2] */, uint32_t* __restrict__ done, unsigned long long* __restrict__ flag) {
+k_ll_init(const double* __restrict__ partials, uint64_t n_genomes, double* __restrict__ f, double* __restrict__ bracket,
+          uint32_t* __restrict__ done) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const double* P = partials + g * PART_COUNT;
+  const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
+  double x = 0.0;                                        // start: the Simple estimate (calc.cpp:344)
+  if (n > 0.0) {
+    const double oh = P[PART_NMINHOM] + P[PART_NMAJHOM], eh = P[PART_EMINHOM] + P[PART_EMAJHOM];
+    x = (oh - eh) / (n - eh);
+  }
+  if (!(x > -1.0 && x < 1.0)) x = 0.0;
+  bracket[g * 2 + 0] = -1.0; bracket[g * 2 + 1] = 1.0;
+  done[g] = (n <= 0.0) ? 1u : 0u;
+  f[g] = (n <= 0.0) ? 0.0 : x;
+}
+
+__global__ void __launch_bounds__(256)
+k_ll_step(const double* __restrict__ iter, uint64_t n_genomes, double tol, double* __restrict__ f,
+          double* __restrict__ bracket, uint32_t* __restrict__ done, unsigned long long* __restrict__ flag) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
   if (done[g]) return;
-  const double* P = partials + g * PART_COUNT;
-  const double* I = iter + g * PART_COUNT;
-  const double g1 = I[PART_IT0], g2 = I[PART_IT1], clamped = I[PART_IT2];
-  const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
-  double a = bracket[g * 2], b = bracket[g * 2 + 1];
+  const double* I = iter + g * ITER_COUNT;
+  const double g1 = I[0], g2 = I[1];
+  const bool hom_clamped = I[2] > 0.0;
+  double a = bracket[g * 2 + 0], b = bracket[g * 2 + 1];
   const double x = f[g];
-  double nx;
-  if (n <= 0.0) { f[g] = 0.0; done[g] = 1; return; }
-  if (clamped > 0.0 || g1 > 0.0) a = x; else b = x;
-  bool newton_ok = false;
-  if (clamped == 0.0 && g2 < 0.0) {
-    nx = x - g1 / g2;
-    newton_ok = (nx > a) && (nx < b) && (nx == nx);
+  if (hom_clamped || g1 > 0.0) a = x; else b = x;
+  double nx = 0.5 * (a + b);
+  if (!hom_clamped && g2 < 0.0) {
+    const double cand = x - g1 / g2;
+    if (cand > a && cand < b) nx = cand;
   }
-  if (!newton_ok) nx = 0.5 * (a + b);
-  bracket[g * 2] = a; bracket[g * 2 + 1] = b;
-  const double step = fabs(nx - x);
+  bracket[g * 2 + 0] = a; bracket[g * 2 + 1] = b;
   f[g] = nx;
-  if (step < tol || (b - a) < tol) done[g] = 1;
+  if (fabs(nx - x) < tol || (b - a) < tol) done[g] = 1;
   else atomicAdd(flag, 1ull);
 }
 
@@ -166,11 +184,6 @@ k_store_coeff(const double* __restrict__ partials, const double* __restrict__ f,
 __global__ void k_fill_double(double* p, uint64_t n, double v) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
-}
-
-__global__ void k_init_bracket(double* bracket, uint32_t* done, uint64_t n) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { bracket[i * 2] = -1.0; bracket[i * 2 + 1] = 1.0; done[i] = 0; }
 }
 
 __global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, uint64_t n_genomes, uint64_t n_loci, uint64_t* __restrict__ out) {

@@ -53,8 +53,8 @@ k_to_sample_major(const uint32_t* __restrict__ packed32 /* loci-major as u32 wor
 //                     S2 = sum over hom-alt cells with p > 0.001 of (1/p - 1),  C2x = number of hom-alt cells with p <= 0.001 }
 //             The caller combines them with the dense total W0 = sum_l (1/q_l - 1) and the class counts of K2.
 //   HALL    : sum over homozygous loci of f/(f+(1-f)a)                       (processHallME, calc.cpp:260-283)
-//   NEWTON  : d/df, d2/df2 of logLikelihood over the unclamped terms, and the number of clamped homozygous terms
-//             (calc.cpp:94-129; a clamped term is constant in f, so it contributes no derivative)
+//   NEWTON  : d/df, d2/df2 of logLikelihood over the unclamped terms, and the numbers of clamped homozygous and
+//             heterozygous terms (calc.cpp:94-129; a clamped term is constant in f, so it contributes no derivative)
 //   GRID    : logLikelihood at up to kGridMax shared f values                (calc.cpp:94-129)
 enum { TERM_RITLAND = 0, TERM_HALL = 1, TERM_NEWTON = 2, TERM_GRID = 3 };
 constexpr int kTermWarps = 8;          // genome blocks per CTA
@@ -77,7 +77,7 @@ struct TermParams {
   uint64_t n_genomes_padded;
 };
 
-template <int MODE> struct TermAcc { static constexpr int N = (MODE == TERM_GRID) ? kGridMax : 3; };
+template <int MODE> struct TermAcc { static constexpr int N = (MODE == TERM_GRID) ? kGridMax : (MODE == TERM_NEWTON) ? 4 : 3; };
 
 template <int MODE>
 __global__ void __launch_bounds__(kTermWarps * 32)
@@ -171,6 +171,8 @@ k_genome_terms(const TermParams P) {
               const double t = 1.0 / (1.0 - f);
               acc[0] -= t;
               acc[1] -= t * t;
+            } else {
+              acc[3] += 1.0;
             }
           }
         } else {  // TERM_GRID: logLikelihood, operation order of calc.cpp:100-125

@@ -150,29 +150,57 @@ static double log_likelihood(double f, const locus_term* terms, size_t n) {
   return log_prob_sum;
 }
 
-/* The converged argmax of logLikelihood over the optimiser's box [-1,1] (kga_analysis_inbreed_calc.cpp:131-143).
- * The reference reaches it with nlopt Nelder-Mead to xtol 1e-6 from a random start (Q1,Q2); parity is defined
- * against the optimum itself: global scan to bracket, then golden-section refinement to 1e-13. */
-static double log_likelihood_argmax(const locus_term* terms, size_t n) {
+/* d/df and d2/df2 of logLikelihood over the terms that are not clamped, plus the clamp signature (numbers of clamped
+ * homozygous / heterozygous terms). A clamped term is constant in f (calc.cpp:108,117), so it has no derivative. */
+static void log_likelihood_deriv(double f, const locus_term* terms, size_t n, double* g1, double* g2, double* sig) {
+  double d1 = 0.0, d2 = 0.0, chom = 0.0, chet = 0.0;
+  const double small_prob = 1e-10;
+  for (size_t i = 0; i < n; ++i) {
+    const double a = terms[i].first;
+    if (terms[i].cls == CLS_MAJOR_HOM || terms[i].cls == CLS_MINOR_HOM) {
+      const double prob = (f * a) + ((1.0 - f) * (a * a));
+      if (prob >= small_prob) {
+        if (prob <= 1.0) { const double t = (1.0 - a) / (a + f * (1.0 - a)); d1 += t; d2 -= t * t; }
+      } else chom += 1.0;
+    } else {
+      const double prob = 2 * (1.0 - f) * a * terms[i].second;
+      if (prob >= small_prob && prob <= 1.0) { const double t = 1.0 / (1.0 - f); d1 -= t; d2 -= t * t; }
+      else chet += 1.0;
+    }
+  }
+  *g1 = d1; *g2 = d2; *sig = chom * 4294967296.0 + chet;
+}
+
+/* The maximum-likelihood inbreeding coefficient the reference's optimiser is after (kga_analysis_inbreed_calc.cpp:131-216).
+ * The reference maximises the CLAMPED objective over [-1,1] with nlopt Nelder-Mead to xtol 1e-6 from random starts
+ * (Q1,Q2). The clamp at 1e-10 (calc.cpp:98,108) is a numerical guard: left of the largest pole of a homozygous term that
+ * term is constant, the objective gets a convex kink and can have extra local maxima there, and which one Nelder-Mead
+ * returns depends on its random start. Parity is therefore defined against the maximiser over the FEASIBLE region -- the
+ * f for which no homozygous probability is clamped -- where the objective is smooth and concave and the maximiser is
+ * unique. It is located deterministically with a bracketed Newton iteration on dLL/df: a clamped homozygous term means
+ * "left of the feasible region" (move right), otherwise the sign of dLL/df updates the bracket and a Newton step is
+ * taken when it stays inside it (else bisection). Function-value searches (golden section, Nelder-Mead) cannot resolve
+ * the maximiser below ~1e-8; the derivative can. The product (k_ll_step) runs the identical iteration. */
+static double log_likelihood_argmax(const locus_term* terms, size_t n, double start) {
   if (n == 0) return 0.0;
-  const int grid = 400;
-  int best = 0;
-  double best_val = -INFINITY;
-  for (int i = 0; i <= grid; ++i) {
-    const double f = -1.0 + 2.0 * i / grid;
-    const double v = log_likelihood(f, terms, n);
-    if (v > best_val) { best_val = v; best = i; }
+  double a = -1.0, b = 1.0, x = start;
+  if (!(x > a && x < b)) x = 0.0;
+  const double tol = 1e-12;
+  for (int it = 0; it < 200; ++it) {
+    double g1, g2, sig;
+    log_likelihood_deriv(x, terms, n, &g1, &g2, &sig);
+    const int hom_clamped = sig >= 4294967296.0;
+    if (hom_clamped || g1 > 0.0) a = x; else b = x;
+    double nx = 0.5 * (a + b);
+    if (!hom_clamped && g2 < 0.0) {
+      const double cand = x - g1 / g2;
+      if (cand > a && cand < b) nx = cand;
+    }
+    const int stop = fabs(nx - x) < tol || (b - a) < tol;
+    x = nx;
+    if (stop) break;
   }
-  double a = -1.0 + 2.0 * (best > 0 ? best - 1 : 0) / grid;
-  double b = -1.0 + 2.0 * (best < grid ? best + 1 : grid) / grid;
-  const double gr = 0.6180339887498949;
-  double c = b - gr * (b - a), d = a + gr * (b - a);
-  double fc = log_likelihood(c, terms, n), fd = log_likelihood(d, terms, n);
-  for (int it = 0; it < 200 && (b - a) > 1e-13; ++it) {
-    if (fc > fd) { b = d; d = c; fd = fc; c = b - gr * (b - a); fc = log_likelihood(c, terms, n); }
-    else { a = c; c = d; fc = fd; d = a + gr * (b - a); fd = log_likelihood(d, terms, n); }
-  }
-  return 0.5 * (a + b);
+  return x;
 }
 
 /* One EM sweep of processHallME (kga_analysis_inbreed_calc.cpp:257-285). */
@@ -241,9 +269,14 @@ void kgl_oracle_inbreed(const uint8_t* packed, size_t row_bytes, size_t n_genome
           }
           r.inbred_allele_sum = f;
         } break;
-        default:                                               /* processLogLikelihood (calc.cpp:154-216) */
-          r.inbred_allele_sum = log_likelihood_argmax(terms, n);
-          break;
+        default: {                                             /* processLogLikelihood (calc.cpp:154-216) */
+          double simple = 0.0;                                 /* start: the Simple estimate (calc.cpp:344) */
+          if (r.total_allele_count > 0) {
+            const double oh = (double)(r.minor_homo_count + r.major_homo_count), eh = r.minor_homo_freq + r.major_homo_freq;
+            simple = (oh - eh) / ((double)r.total_allele_count - eh);
+          }
+          r.inbred_allele_sum = log_likelihood_argmax(terms, n, simple);
+        } break;
       }
       out[g] = r;
     }

@@ -107,7 +107,7 @@ def test_golden_loglikelihood(gpu, golden):
     opt = O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"]
     # converged optimum of the same objective: <= 1e-9; the reference's own Nelder-Mead stops at xtol 1e-6
     assert np.max(np.abs(res["inbred_allele_sum"][present] - opt[present])) < 1e-9
-    assert np.max(np.abs(res["inbred_allele_sum"][present] - ref["Loglikelihood_coeff"][present])) < 5e-6
+    assert np.max(np.abs(res["inbred_allele_sum"][present] - ref["Loglikelihood_coeff"][present])) < 2e-6
 
 
 # ------------------------------------------------------------------------------------------------ oracle, seeded ----
@@ -160,9 +160,7 @@ def test_all_estimators_match_oracle(gpu, case):
     assert rel_err(gpu.loglik_grid(grid)[ok], O.loglik_grid(pop, sel, grid)[ok]) < 1e-12
     got = gpu.inbreed("Loglikelihood")
     want = O.inbreed(pop, sel, "Loglikelihood")
-    # the optimum is only defined up to the flatness of the objective: compare objective values, then locations
-    if pop.n_loci >= 1000:
-        assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-7
+    assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-9
 
 
 def test_hallme_fixed_point(gpu):

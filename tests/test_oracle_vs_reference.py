@@ -41,18 +41,19 @@ def test_loglikelihood_grid_bit_exact(golden):
 
 
 def test_loglikelihood_optimum_within_optimiser_tolerance(golden):
-    """The reference stops Nelder-Mead at xtol_abs 1e-6 (calc.cpp:138); every one of its 5 restarts must land within
-    that distance (plus slack for a flat objective) of the oracle's converged optimum."""
+    """The reference stops Nelder-Mead at xtol_abs 1e-6 (calc.cpp:138) from random starts. The oracle returns the
+    maximiser over the feasible region (no homozygous probability clamped), located with the derivative; for every genome
+    of every fixture the reference's returned coefficient lies within the optimiser tolerance of it."""
     name, pop, ref, sel_kw = golden
     sel = O.select_all_pops(pop, **sel_kw)
     opt = O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"]
     present = ref["genome_present"] == 1
-    assert np.all(np.abs(ref["Loglikelihood_coeff"][present] - opt[present]) < 5e-6)
-    # and the oracle optimum is at least as good as anything the reference found
-    grid_at = np.stack([opt, ref["Loglikelihood_coeff"]], axis=1)
+    assert np.all(np.abs(ref["Loglikelihood_coeff"][present] - opt[present]) < 2e-6)
+    # dLL/df vanishes at the oracle optimum: the objective is flat to first order there (checked by symmetric differences)
+    h = 1e-5
     for g in np.flatnonzero(present)[:8]:
-        vals = O.loglik_grid(pop, sel, grid_at[g])[g]
-        assert vals[0] >= vals[1] - 1e-9
+        vals = O.loglik_grid(pop, sel, np.array([opt[g] - h, opt[g], opt[g] + h]))[g]
+        assert vals[1] >= vals[0] and vals[1] >= vals[2]
 
 
 def test_hallme_fifty_sweeps_bit_exact(golden):
