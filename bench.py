@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json on N B200s of one node.
+
+Metric: inbreeding genotype-loci/s (BASELINE.json `metric`) on config 2, the chr22 shape: 2,504 genomes x 1.1 M biallelic
+SNPs, per-locus allele counts + per-genome inbreeding (Simple estimator: class counts, expected class-frequency sums, F)
+with a gnomAD-style float AF vector per super-population. One "step" = one fused pass over one batch of synthetic input:
+per-locus preparation from the AF vectors, the streaming kernel k_count_moments over the 2-bit matrix, counter expansion,
+moment assembly and the closed-form estimator.
+
+  value : whole-job genotype-loci/s with the inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e   : the same pass through the C ABI with HOST buffers: H2D of the packed matrix, AF vectors, super-populations and
+          locus selection, and D2H of the per-locus counts and LocusResults inside the timed region
+  N > 1 : weak scaling, every rank owns a locus shard of the same size; per-genome partial sums are all-reduced (NCCL)
+          between the streaming pass and the estimator.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/kgl_ref_harness, the reference TUs
+compiled where they lie; else the oracle port) on a bounded sample of the same workload, on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GENOMES = 2504
+N_LOCI = 1_100_000
+SEED = 20261018
+METRIC = "inbreeding genotype-loci/s"
+UNIT = "genotype-loci/s"
+CPU_SAMPLE = (512, 20_000)      # genomes x loci of the bounded CPU sample (same generator, same law)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=N_GENOMES)
+    ap.add_argument("--loci", type=int, default=N_LOCI)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n, l, world):
+    base = f"1000G chr22 shape: {n} genomes x {l} biallelic SNPs, per-locus allele counts + Simple inbreeding, 6 float AF vectors"
+    return base if world == 1 else base + f" per GPU (locus-sharded, {world} shards, partial sums all-reduced)"
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline ---------
+def cpu_reference_run(repeat: int):
+    """Times the reference CPU path on the bounded sample. Returns dict(value, cores, kind, sample, seconds list)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    from kgl_gene_b200.synth import make_population
+    n, l = CPU_SAMPLE
+    pop, _ = make_population(n, l, seed=SEED, spectrum="sfs")
+    cells = float(n) * float(l)
+    if O.have_reference_harness():
+        out = O.run_reference(pop, algos=("Simple",), variantdb=False, repeat=repeat, timeout=3000)
+        secs = [float(s) for s in out["Simple_repeat_seconds"]]
+        cores = int(out["meta"][0])
+        kind = "reference"
+        what = (f"reference TUs (kga_inbreed processSimple + generateFrequencies) via WorkflowThreads({cores}) on {n} genomes x {l} loci "
+                f"drawn from the bench generator; fan-out/future.get() loop timed, PopulationDB construction excluded")
+    else:
+        sel = O.select_all_pops(pop)
+        secs = []
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            O.inbreed(pop, sel, "Simple")
+            secs.append(time.perf_counter() - t0)
+        cores = O.threads()
+        kind = "port"
+        what = f"oracle C port (OpenMP, {cores} threads) on {n} genomes x {l} loci drawn from the bench generator"
+    return dict(cells=cells, seconds=secs, cores=cores, kind=kind, sample=what)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps + args.warmup)
+    secs = r["seconds"][args.warmup:] if len(r["seconds"]) > args.warmup else r["seconds"]
+    mean = float(np.mean(secs))
+    value = r["cells"] / mean
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
+        "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.genomes, args.loci, 1),
+                   "note": "reference CPU path timed on a bounded sample of this workload; value is per-unit throughput"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------- clocks ---------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class RawCudaArray:
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+# ----------------------------------------------------------------------------------------------------- ours ---------
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from kgl_gene_b200.capi import KglB200, RESULT_DTYPE
+    from kgl_gene_b200.flatfile import row_bytes_for
+    from kgl_gene_b200.synth import make_genomes, make_loci
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, l = args.genomes, args.loci
+    rb = row_bytes_for(n)
+    ctx = KglB200(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- synthetic shard, generated on the device: same genomes on every rank, rank-specific loci ----
+    offsets, af = make_loci(l, SEED + 1000 * rank)
+    superpop, inbreeding = make_genomes(n, SEED)
+    ctx.upload_loci(af, offsets)
+    ctx.set_genome_superpop(superpop)
+    ctx.synth_genotypes(SEED, n, l, inbreeding, missing_rate=0.001, locus_base=rank * l)
+    ctx.select_loci()                      # one window = all loci (LociiCount = inf, SamplingDistance = 0, AF in [0,1])
+
+    def allreduce_partials():
+        ptr, cnt = ctx.inbreed_partials_buffer()
+        t = torch.as_tensor(RawCudaArray(ptr, cnt, "<f8"), device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def step_resident():
+        if world == 1:
+            ctx.enqueue_count_and_inbreed()
+        else:
+            ctx.inbreed_begin("Simple", count_loci=True)
+            ctx.inbreed_accumulate()
+            allreduce_partials()
+            ctx.inbreed_update()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- resident timing ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    ctx.kernel_timer_reset()
+    launches0 = ctx.launch_count()
+    total_ms = timed(step_resident, args.steps, 0)
+    launches = ctx.launch_count() - launches0
+    kernel_ms = ctx.kernel_timer_read()
+    clocks = sampler.stop() if rank == 0 else None
+    cells = float(n) * float(l) * world
+    value = cells * args.steps / (total_ms * 1e-3)
+
+    # ---- parity spot check of the resident result (size-independent invariants; full parity lives in tests/) ----
+    res = ctx.inbreed_fetch() if world > 1 else None
+    lc = ctx.fetch_locus_counts()
+    assert int(lc.sum()) == n * l and np.all(lc.sum(axis=1) == n), "per-locus counts do not add up to the genome count"
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        h_packed = torch.empty((l, rb), dtype=torch.uint8, pin_memory=True)
+        ctx._check(ctx.lib.kgl_b200_download_genotypes(ctx.h, C.c_uint64(l * rb), C.c_void_p(h_packed.data_ptr())), "download_genotypes")
+        h_af = torch.from_numpy(af).pin_memory()
+        h_lc = torch.empty((l, 4), dtype=torch.int32, pin_memory=True)
+        h_res = torch.empty((n * RESULT_DTYPE.itemsize,), dtype=torch.uint8, pin_memory=True)
+        af_np, off_np = h_af.numpy(), offsets
+
+        def step_e2e():
+            ctx.upload_genotypes_ptr(h_packed.data_ptr(), n, l, rb)
+            ctx.upload_loci(af_np, off_np)
+            ctx.set_genome_superpop(superpop)
+            ctx.select_loci()
+            if world == 1:
+                ctx.count_and_inbreed_into(h_lc.data_ptr(), h_res.data_ptr())
+            else:
+                ctx.inbreed_begin("Simple", count_loci=True)
+                ctx.inbreed_accumulate()
+                allreduce_partials()
+                ctx.inbreed_update()
+                ctx._check(ctx.lib.kgl_b200_inbreed_fetch(ctx.h, C.c_void_p(h_res.data_ptr())), "inbreed_fetch")
+                ctx._check(ctx.lib.kgl_b200_fetch_locus_counts(ctx.h, C.c_void_p(h_lc.data_ptr())), "fetch_locus_counts")
+
+        e2e_steps = max(3, min(args.steps, 10))
+        e2e_ms = timed(step_e2e, e2e_steps, 2)
+        h2d = l * rb + af.nbytes + n + l
+        d2h = 16 * l + RESULT_DTYPE.itemsize * n
+        e2e = {"value": cells * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps}
+        lc2 = h_lc.numpy().view(np.uint32)
+        assert np.array_equal(lc2, lc), "e2e per-locus counts differ from the resident run"
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        k_ms = float(np.mean(kernel_ms)) if len(kernel_ms) else None
+        # algorithmic bytes of one k_count_moments launch: 2 bits per genotype + 2 B selection flags and 16 B of counts per locus
+        alg_bytes = n * l / 4.0 + 2.0 * l + 16.0 * l
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "k_count_moments_traffic.json")))
+            if prof.get("n_genomes") == n and prof.get("n_loci") == l:
+                traffic = prof.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 bit-planes + f64 sums", "data": "synthetic",
+            "config": {"workload": workload_name(n, l, world), "n_genomes": n, "n_loci_per_gpu": l, "af_vectors": int(af.shape[0]),
+                       "selection": "one window, all loci", "missing_rate": 0.001,
+                       "l2": f"inputs ({l * rb / 1e6:.0f} MB matrix per GPU) are larger than the 126 MB L2; no flush needed",
+                       "step": "k_locus_prepare + k_reduce_totals + k_count_moments + k_expand_counts + k_moment_partials (+ NCCL all-reduce) + k_finalize_closed_form"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_count_moments", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * len(kernel_ms) / total_ms) if k_ms else None,
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                r = cpu_reference_run(2)
+                secs = r["seconds"][1:] or r["seconds"]
+                line["cpu_baseline"] = {"value": r["cells"] / float(np.mean(secs)), "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                        "sample": r["sample"]}
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

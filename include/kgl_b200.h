@@ -74,7 +74,9 @@ typedef struct kgl_b200_inbreed_options {
    * ll_max_iterations (0 = 200). */
   double ll_tolerance;
   int32_t ll_max_iterations;
-  int32_t reserved;
+  /* != 0: the moments pass of kgl_b200_inbreed_accumulate also produces the per-locus allele counts of this rank's
+   * locus shard (the fused pass of kgl_b200_run_count_and_inbreed, split around the all-reduce). */
+  int32_t count_loci;
 } kgl_b200_inbreed_options;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -144,6 +146,12 @@ uint64_t kgl_b200_launch_count(const kgl_b200_ctx* ctx);
 /* Milliseconds the dominant streaming kernel (k_count_moments) took in the most recent enqueue/run, measured with
  * CUDA events around that launch on the context stream. Returns < 0 if none has run. Synchronises. */
 float kgl_b200_last_stream_kernel_ms(kgl_b200_ctx* ctx);
+/* The same measurement for every launch of that kernel since the last reset (up to 256), read after the fact so that
+ * no host synchronisation lands inside a timed region. */
+int kgl_b200_kernel_timer_reset(kgl_b200_ctx* ctx);
+int kgl_b200_kernel_timer_read(kgl_b200_ctx* ctx, float* ms, uint32_t capacity, uint32_t* n);
+/* Copy the per-locus allele counts of the last fused pass to the host: uint32[n_loci][4]. */
+int kgl_b200_fetch_locus_counts(kgl_b200_ctx* ctx, uint32_t* locus_counts);
 
 /* Locus-sharded multi-GPU inbreeding: each rank holds a shard of the loci. begin() prepares `algorithm`;
  * accumulate() fills the context's per-genome partial-sum buffer (device, doubles) for the current iterate;

@@ -28,13 +28,13 @@ EXPORTS = [
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
-    "kgl_b200_inbreed_fetch",
+    "kgl_b200_inbreed_fetch", "kgl_b200_kernel_timer_reset", "kgl_b200_kernel_timer_read", "kgl_b200_fetch_locus_counts",
 ]
 
 
 class InbreedOptions(C.Structure):
     _fields_ = [("hall_start", C.POINTER(C.c_double)), ("hall_sweeps", C.c_int32), ("ll_tolerance", C.c_double),
-                ("ll_max_iterations", C.c_int32), ("reserved", C.c_int32)]
+                ("ll_max_iterations", C.c_int32), ("count_loci", C.c_int32)]
 
 
 class KglError(RuntimeError):
@@ -216,8 +216,23 @@ class KglB200:
     def last_stream_kernel_ms(self) -> float:
         return float(self.lib.kgl_b200_last_stream_kernel_ms(self.h))
 
-    def inbreed_begin(self, algorithm: str, hall_start=None, hall_sweeps=0, ll_tolerance=0.0, ll_max_iterations=0):
+    def kernel_timer_reset(self):
+        self._check(self.lib.kgl_b200_kernel_timer_reset(self.h), "kernel_timer_reset")
+
+    def kernel_timer_read(self) -> np.ndarray:
+        ms = np.zeros(256, dtype=np.float32)
+        n = C.c_uint32(0)
+        self._check(self.lib.kgl_b200_kernel_timer_read(self.h, _ptr(ms), C.c_uint32(256), C.byref(n)), "kernel_timer_read")
+        return ms[: n.value].copy()
+
+    def fetch_locus_counts(self) -> np.ndarray:
+        lc = np.zeros((self.n_loci, 4), dtype=np.uint32)
+        self._check(self.lib.kgl_b200_fetch_locus_counts(self.h, _ptr(lc)), "fetch_locus_counts")
+        return lc
+
+    def inbreed_begin(self, algorithm: str, hall_start=None, hall_sweeps=0, ll_tolerance=0.0, ll_max_iterations=0, count_loci=False):
         opt = InbreedOptions()
+        opt.count_loci = int(bool(count_loci))
         self._hall_keep = None
         if hall_start is not None:
             self._hall_keep = np.ascontiguousarray(hall_start, dtype=np.float64)

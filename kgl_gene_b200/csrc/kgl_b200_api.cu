@@ -43,6 +43,12 @@ struct kgl_b200_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  // ring of event pairs around every k_count_moments launch since the last reset (bench.py's live roofline timing)
+  static constexpr int kTimerSlots = 256;
+  std::vector<cudaEvent_t> timer_ev;
+  int timer_used = 0;
+  bool count_loci_in_accumulate = false;
+  cudaEvent_t last_e0 = nullptr, last_e1 = nullptr;
   std::string err;
   uint64_t launches = 0;
 
@@ -243,12 +249,24 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   P.planes = want_genome ? c->d_planes.p : nullptr;
   P.ecorr = c->d_ecorr.p; P.nz_rare = c->d_nz_rare.p;
   dim3 grid(pl.n_chunks, pl.slices);
-  KGL_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  cudaEvent_t e0 = c->ev0, e1 = c->ev1;
+  if (c->timer_used < kgl_b200_ctx::kTimerSlots) {
+    if ((int)c->timer_ev.size() < 2 * (c->timer_used + 1)) {
+      cudaEvent_t a0 = nullptr, a1 = nullptr;
+      KGL_CUDA(c, cudaEventCreate(&a0));
+      KGL_CUDA(c, cudaEventCreate(&a1));
+      c->timer_ev.push_back(a0); c->timer_ev.push_back(a1);
+    }
+    e0 = c->timer_ev[2 * c->timer_used]; e1 = c->timer_ev[2 * c->timer_used + 1];
+    ++c->timer_used;
+  }
+  KGL_CUDA(c, cudaEventRecord(e0, c->stream));
   if (c->any_mixed && !raw) k_count_moments<true><<<grid, kCountThreads, 0, c->stream>>>(P);
   else k_count_moments<false><<<grid, kCountThreads, 0, c->stream>>>(P);
   KGL_LAUNCH_CHECK(c);
-  KGL_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  KGL_CUDA(c, cudaEventRecord(e1, c->stream));
   c->ev_valid = true;
+  c->last_e0 = e0; c->last_e1 = e1;
   if (want_locus_counts && pl.slices > 1) {
     k_fix_locus_n0<<<blocks_for(c->L, 256), 256, 0, c->stream>>>(c->d_locus_counts.p, c->L, (uint32_t)c->N);
     KGL_LAUNCH_CHECK(c);
@@ -363,6 +381,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_nz_rare.release(); c->d_ecorr.release(); c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
+  for (cudaEvent_t e : c->timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -389,10 +408,27 @@ uint64_t kgl_b200_launch_count(const kgl_b200_ctx* c) { return c ? c->launches :
 float kgl_b200_last_stream_kernel_ms(kgl_b200_ctx* c) {
   if (!c || !c->ev_valid) return -1.0f;
   if (cudaSetDevice(c->device) != cudaSuccess) return -1.0f;
-  if (cudaEventSynchronize(c->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventSynchronize(c->last_e1) != cudaSuccess) return -1.0f;
   float ms = -1.0f;
-  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, c->last_e0, c->last_e1) != cudaSuccess) return -1.0f;
   return ms;
+}
+
+int kgl_b200_kernel_timer_reset(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  c->timer_used = 0;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_kernel_timer_read(kgl_b200_ctx* c, float* ms, uint32_t capacity, uint32_t* n) {
+  if (!c || !ms || !n) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint32_t k = 0;
+  for (int i = 0; i < c->timer_used && k < capacity; ++i, ++k)
+    KGL_CUDA(c, cudaEventElapsedTime(&ms[k], c->timer_ev[2 * i], c->timer_ev[2 * i + 1]));
+  *n = k;
+  return KGL_B200_OK;
 }
 
 static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint64_t row_bytes) {
@@ -579,6 +615,15 @@ int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   return KGL_B200_OK;
 }
 
+int kgl_b200_fetch_locus_counts(kgl_b200_ctx* c, uint32_t* locus_counts) {
+  if (!c || !locus_counts) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (c->d_locus_counts.cap < (size_t)c->L * 4) return fail(c, KGL_B200_ERR_STATE, "no per-locus counts have been computed");
+  int rc = use_device(c); if (rc) return rc;
+  KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
 int kgl_b200_run_count_and_inbreed(kgl_b200_ctx* c, uint32_t* locus_counts, kgl_b200_locus_results* out) {
   int rc = kgl_b200_enqueue_count_and_inbreed(c); if (rc) return rc;
   if (locus_counts)
@@ -600,6 +645,7 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   c->hall_start.clear();
   if (c->opt.hall_start) c->hall_start.assign(c->opt.hall_start, c->opt.hall_start + c->N);
   c->opt.hall_start = nullptr;
+  if (c->opt.count_loci) c->prep_valid = false;               // fused step: the AF vectors are re-read every pass
   if (c->opt.hall_sweeps == 0) c->opt.hall_sweeps = 50;        // MINIMUM_ITERATIONS_ (calc.h:124), SURVEY Q1
   if (c->opt.ll_tolerance <= 0.0) c->opt.ll_tolerance = 1e-12;
   if (c->opt.ll_max_iterations <= 0) c->opt.ll_max_iterations = 200;
@@ -620,7 +666,7 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   int rc = use_device(c); if (rc) return rc;
   TermLaunch tl;
   if (c->phase == 0) {
-    rc = enqueue_moments(c, false); if (rc) return rc;
+    rc = enqueue_moments(c, c->opt.count_loci != 0); if (rc) return rc;
     if (c->algo == KGL_B200_ALGO_RITLAND) {
       rc = launch_terms<TERM_RITLAND>(c, 3, nullptr, 0, tl); if (rc) return rc;
       k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 3, c->d_totals.p,

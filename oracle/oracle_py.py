@@ -126,7 +126,7 @@ def have_reference_harness() -> bool:
 
 
 def run_reference(pop, algos=("Simple", "RitlandLocus", "HallME", "Loglikelihood"), spacing=0, min_af=0.0, max_af=1.0,
-                  lower=0, upper=10**9, grid=0, threads=0, variantdb=True, seed=None, timeout=3600):
+                  lower=0, upper=10**9, grid=0, threads=0, variantdb=True, seed=None, repeat=1, timeout=3600):
     """Runs the reference's own code (oracle/_ref/kgl_ref_harness) on `pop`; returns the dumped arrays."""
     from kgl_gene_b200.flatfile import read_tensors
     with tempfile.TemporaryDirectory() as d:
@@ -138,6 +138,8 @@ def run_reference(pop, algos=("Simple", "RitlandLocus", "HallME", "Loglikelihood
             cmd.append("--no-variantdb")
         if seed is not None:
             cmd += ["--seed", str(int(seed))]
+        if repeat > 1:
+            cmd += ["--repeat", str(int(repeat))]
         env = dict(os.environ, KGL_REF_LOG=os.path.join(d, "ref.log"))
         proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         if proc.returncode != 0:

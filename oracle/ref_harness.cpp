@@ -60,6 +60,7 @@ struct Options {
   size_t threads{0};  // 0 = reference default (hardware_concurrency - 1)
   size_t grid{0};
   long seed{-1};      // >= 0: std::random_device is pinned to this value (see ref_stubs.cpp)
+  size_t repeat{1};   // time the per-genome fan-out this many times (bench.py --impl reference)
   bool variantdb{true};
   bool quiet{true};
 };
@@ -197,6 +198,8 @@ void run() {
     if (!algorithm_opt) { std::fprintf(stderr, "unknown algorithm %s\n", algo_name.c_str()); std::exit(2); }
     const kga::InbreedingAlgorithm algorithm = algorithm_opt.value();
     std::vector<GenomeOut> results(N);
+    std::vector<double> repeat_seconds;
+    for (size_t rep = 0; rep < g_opt.repeat; ++rep) {
     t0 = Clock::now();
     {
       kel::WorkflowThreads pool(threads);
@@ -223,7 +226,10 @@ void run() {
       }
       for (auto& [g, future] : futures) results[g] = future.get();
     }
-    const double seconds = std::chrono::duration<double>(Clock::now() - t0).count();
+    repeat_seconds.push_back(std::chrono::duration<double>(Clock::now() - t0).count());
+    }
+    out.addF64(algo_name + "_repeat_seconds", {repeat_seconds.size()}, repeat_seconds);
+    const double seconds = repeat_seconds.back();
     timing.push_back(seconds);
     std::fprintf(stderr, "[ref] %-14s %u genomes x %u loci  %.3f s  (%zu threads)  %.3e genotype-loci/s\n",
                  algo_name.c_str(), N, L, seconds, threads, double(N) * double(L) / seconds);
@@ -329,6 +335,7 @@ class HarnessEnv {
       else if (a == "--threads") g_opt.threads = std::stoull(next());
       else if (a == "--grid") g_opt.grid = std::stoull(next());
       else if (a == "--seed") g_opt.seed = std::stol(next());
+      else if (a == "--repeat") g_opt.repeat = std::max<size_t>(1, std::stoull(next()));
       else if (a == "--no-variantdb") g_opt.variantdb = false;
       else if (a == "--verbose") g_opt.quiet = false;
       else pos.push_back(a);
