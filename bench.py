@@ -183,7 +183,11 @@ def run_ours(args):
     n, l = args.genomes, args.loci
     rb = row_bytes_for(n)
     ctx = KglB200(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the C ABI treats a NULL handle as "use the context's own stream", and CUDA events must
+    # be recorded on the stream the kernels run on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     # ---- synthetic shard, generated on the device: same genomes on every rank, rank-specific loci ----

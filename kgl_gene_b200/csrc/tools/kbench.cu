@@ -1,0 +1,292 @@
+// kbench.cu -- standalone micro-benchmarks for the kgl_b200 kernels (development tool; not part of the library).
+//   1. issue rates of the integer pipes the kernels lean on (POPC, LOP3, IADD3, REDUX, SHFL) -> the INT-pipe roofline
+//      denominators of DESIGN.md
+//   2. the streaming pass k_stream_count in its configurations, timed with CUDA events and checked against naive kernels
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o kbench kbench.cu
+#include "../stream_count.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace kgl;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); std::exit(2); } } while (0)
+
+// ------------------------------------------------------------------------------------------------ pipe rates --------
+template <int OP>
+__global__ void __launch_bounds__(256) k_pipe(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x9E3779B9u;
+  uint32_t b = seed ^ 0x5bd1e995u, c = seed * 7u + 1u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) a[i] = __popc(a[i]) + b;                                   // POPC + IADD
+      else if (OP == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c));
+      else if (OP == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+      else if (OP == 3) a[i] = __reduce_add_sync(0xffffffffu, a[i]) + b;     // REDUX + IADD
+      else if (OP == 4) a[i] = __shfl_xor_sync(0xffffffffu, a[i], 1) + b;    // SHFL + IADD
+      else if (OP == 5) { a[i] = __popc(a[i]); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); }  // POPC + LOP3
+      else if (OP == 6) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); a[i] = a[i] * 3u + b; }  // LOP3 + IMAD
+      else if (OP == 7) a[i] = __popc(a[i]);                                  // POPC alone (dependent chain per register)
+      else if (OP == 8) a[i] = __reduce_add_sync(0xffffffffu, __popc(a[i]) + b);   // POPC + IADD + REDUX
+      else if (OP == 9) { a[i] += b; asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)); }  // IADD + LOP3
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r ^= a[i];
+  if (r == 0x12345678u) out[0] = r;
+}
+
+template <int OP>
+static void pipe_rate(const char* name, int ops_per_inner, uint32_t* d_out, int sms, double clk_ghz) {
+  const int iters = 4096, blocks = sms * 8;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_pipe<OP><<<blocks, 256>>>(d_out, 64, 1u);
+  CK(cudaEventRecord(e0));
+  k_pipe<OP><<<blocks, 256>>>(d_out, iters, 1u);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double inner = (double)blocks * 256 * iters * 8;
+  const double per_s = inner / (ms * 1e-3);
+  std::printf("pipe %-12s %8.3f ms  %.3e inner-ops/s  = %.2f inner/clk/SM at %.3f GHz (%d instr per inner)\n", name, ms, per_s,
+              per_s / sms / (clk_ghz * 1e9), clk_ghz, ops_per_inner);
+}
+
+// ------------------------------------------------------------------------------------------------ data --------------
+__global__ void k_fill(uint4* packed, uint64_t n_loci, uint64_t units, uint32_t n_genomes, uint32_t p_het_1024, uint32_t p_hom_1024,
+                       uint32_t p_miss_65536, uint64_t seed) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_loci * units) return;
+  const uint64_t unit = idx % units;
+  uint64_t lo = 0, hi = 0;
+  for (int b = 0; b < 64; ++b) {
+    if (unit * 64 + b >= n_genomes) break;
+    const uint64_t h = mix64(seed ^ (idx * 64 + b));
+    const uint32_t u = (uint32_t)(h & 1023), m = (uint32_t)((h >> 20) & 65535);
+    unsigned code = u < p_het_1024 ? 1u : (u < p_het_1024 + p_hom_1024 ? 2u : 0u);
+    if (m < p_miss_65536) code = 3;
+    lo |= (uint64_t)(code & 1) << b;
+    hi |= (uint64_t)(code >> 1) << b;
+  }
+  packed[idx] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
+__global__ void k_fill_flags(uint16_t* flags, uint64_t n, int mode, uint64_t seed) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint16_t f = 0x3f;
+  if (mode == 1) { const uint64_t h = mix64(seed ^ i); if ((h & 63) == 0) f = (uint16_t)((h >> 8) & 0x3f); }   // ~1.6% partial rows
+  flags[i] = f;
+}
+
+// naive references ------------------------------------------------------------------------------------------------------
+__global__ void k_ref_locus(const uint4* packed, uint64_t n_loci, uint64_t units, uint32_t* out) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_loci * units) return;
+  const uint4 v = packed[idx];
+  const uint64_t row = idx / units;
+  atomicAdd(out + row * 4 + 1, __popc(v.x & ~v.z) + __popc(v.y & ~v.w));
+  atomicAdd(out + row * 4 + 2, __popc(v.z & ~v.x) + __popc(v.w & ~v.y));
+  atomicAdd(out + row * 4 + 3, __popc(v.x & v.z) + __popc(v.y & v.w));
+}
+__global__ void k_ref_genome(const uint4* packed, uint64_t n_loci, uint64_t units, const uint16_t* flags, const uint8_t* superpop,
+                             uint32_t n_genomes, uint32_t* out /* [N][2] */) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const uint64_t unit = g >> 6;
+  const int b = g & 63;
+  const int k = superpop ? superpop[g] : 0;
+  uint32_t nlo = 0, nhi = 0;
+  for (uint64_t l = blockIdx.y; l < n_loci; l += gridDim.y) {
+    if (flags && !((flags[l] >> k) & 1)) continue;
+    const uint4 v = packed[l * units + unit];
+    const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+    nlo += (lo >> b) & 1; nhi += (hi >> b) & 1;
+  }
+  atomicAdd(out + g * 2, nlo); atomicAdd(out + g * 2 + 1, nhi);
+}
+
+__global__ void __launch_bounds__(256) k_read_only(const uint4* packed, uint64_t n, uint32_t* out) {
+  uint32_t acc = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const uint4 a = ld_stream_u4(packed + i), b = ld_stream_u4(packed + i + stride), c = ld_stream_u4(packed + i + 2 * stride),
+                d = ld_stream_u4(packed + i + 3 * stride);
+    acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+  }
+  for (; i < n; i += stride) { const uint4 a = ld_stream_u4(packed + i); acc ^= a.x ^ a.y ^ a.z ^ a.w; }
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
+template <bool WL, bool WG>
+static void launch_stream(const StreamParams& P, const StreamPlan& pl, cudaStream_t st) {
+  dim3 grid(pl.n_ctas, pl.slices);
+  if (pl.threads <= 384) {
+    CK(cudaFuncSetAttribute(k_stream_count<WL, WG, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k_stream_count<WL, WG, 384><<<grid, pl.threads, pl.smem, st>>>(P);
+  } else {
+    CK(cudaFuncSetAttribute(k_stream_count<WL, WG, 704>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k_stream_count<WL, WG, 704><<<grid, pl.threads, pl.smem, st>>>(P);
+  }
+  CK(cudaGetLastError());
+}
+
+int main(int argc, char** argv) {
+  uint64_t n_loci = 1100000; uint32_t n_genomes = 2504; int reps = 10; int do_pipes = 1; uint64_t verify_loci = 65536; int only_cfg = -1; int do_verify = 1;
+  for (int i = 1; i < argc; ++i) {
+    if (!std::strcmp(argv[i], "--loci")) n_loci = std::strtoull(argv[++i], nullptr, 10);
+    else if (!std::strcmp(argv[i], "--genomes")) n_genomes = (uint32_t)std::strtoul(argv[++i], nullptr, 10);
+    else if (!std::strcmp(argv[i], "--reps")) reps = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--no-pipes")) do_pipes = 0;
+    else if (!std::strcmp(argv[i], "--verify-loci")) verify_loci = std::strtoull(argv[++i], nullptr, 10);
+    else if (!std::strcmp(argv[i], "--cfg")) only_cfg = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--no-verify")) do_verify = 0;
+  }
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  const double clk = prop.clockRate * 1e-6;
+  std::printf("device %s, %d SMs, %.3f GHz max, L2 %d MB\n", prop.name, sms, clk, prop.l2CacheSize >> 20);
+  uint32_t* d_out; CK(cudaMalloc(&d_out, 64));
+
+  if (do_pipes) {
+    pipe_rate<7>("POPC", 1, d_out, sms, clk);
+    pipe_rate<0>("POPC+IADD", 2, d_out, sms, clk);
+    pipe_rate<1>("LOP3", 1, d_out, sms, clk);
+    pipe_rate<2>("IADD", 1, d_out, sms, clk);
+    pipe_rate<3>("REDUX+IADD", 2, d_out, sms, clk);
+    pipe_rate<4>("SHFL+IADD", 2, d_out, sms, clk);
+    pipe_rate<5>("POPC+LOP3", 2, d_out, sms, clk);
+    pipe_rate<6>("LOP3+IMAD", 2, d_out, sms, clk);
+    pipe_rate<8>("POPC+IADD+REDUX", 3, d_out, sms, clk);
+    pipe_rate<9>("IADD+LOP3", 2, d_out, sms, clk);
+  }
+
+  const uint64_t units = (n_genomes + 63) / 64;
+  std::vector<uint8_t> h_superpop(n_genomes), h_need(units, 0);
+  std::vector<uint64_t> h_popmask(6 * units, 0);
+  for (uint32_t g = 0; g < n_genomes; ++g) {
+    const int k = (int)((uint64_t)g * 5 / n_genomes);
+    h_superpop[g] = (uint8_t)k;
+    h_need[g >> 6] |= (uint8_t)(1u << k);
+    h_popmask[(size_t)k * units + (g >> 6)] |= 1ull << (g & 63);
+  }
+  uint8_t *d_superpop, *d_need; uint64_t* d_popmask;
+  CK(cudaMalloc(&d_superpop, n_genomes)); CK(cudaMalloc(&d_need, units)); CK(cudaMalloc(&d_popmask, 6 * units * 8));
+  CK(cudaMemcpy(d_superpop, h_superpop.data(), n_genomes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_need, h_need.data(), units, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_popmask, h_popmask.data(), 6 * units * 8, cudaMemcpyHostToDevice));
+
+  const uint64_t pad_rows = n_loci + 4096;
+  uint4* d_packed; CK(cudaMalloc(&d_packed, pad_rows * units * 16));
+  CK(cudaMemset(d_packed, 0, pad_rows * units * 16));
+  k_fill<<<(unsigned)((n_loci * units + 255) / 256), 256>>>(d_packed, n_loci, units, n_genomes, 140, 25, 66, 20261018ull);
+  uint16_t* d_flags[2];
+  for (int m = 0; m < 2; ++m) {
+    CK(cudaMalloc(&d_flags[m], pad_rows * 2)); CK(cudaMemset(d_flags[m], 0, pad_rows * 2));
+    k_fill_flags<<<(unsigned)((n_loci + 255) / 256), 256>>>(d_flags[m], n_loci, m, 99);
+  }
+  uint32_t *d_lc, *d_lc_ref, *d_gc, *d_gc_ref, *d_planes;
+  CK(cudaMalloc(&d_lc, n_loci * 16)); CK(cudaMalloc(&d_lc_ref, n_loci * 16));
+  CK(cudaMalloc(&d_gc, units * 64 * 8)); CK(cudaMalloc(&d_gc_ref, units * 64 * 8));
+  CK(cudaDeviceSynchronize());
+
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const double matrix_bytes = (double)n_loci * units * 16;
+  {
+    for (int w = 0; w < 2; ++w) k_read_only<<<sms * 8, 256>>>(d_packed, n_loci * units, d_out);
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) k_read_only<<<sms * 8, 256>>>(d_packed, n_loci * units, d_out);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::printf("read-only LDG.128 x4        %8.4f ms  %7.1f GB/s\n", ms / reps, matrix_bytes / (ms / reps * 1e-3) / 1e9);
+  }
+
+  struct Cfg { const char* name; bool wl, wg; int flags_mode; int ty, stages; };
+  const Cfg cfgs[] = {
+      {"locus+genome full  ty8  s4", true, true, 0, 8, 4},   {"locus+genome full  ty8  s2", true, true, 0, 8, 2},
+      {"locus+genome full  ty16 s2", true, true, 0, 16, 2},  {"locus+genome full  ty4  s8", true, true, 0, 4, 8},
+      {"locus+genome full  ty8  s3", true, true, 0, 8, 3},
+      {"locus only         ty8  s4", true, false, 0, 8, 4},  {"genome only full   ty8  s4", false, true, 0, 8, 4},
+      {"neither (stream)   ty8  s4", false, false, 0, 8, 4}, {"locus+genome part. ty8  s4", true, true, 1, 8, 4},
+      {"locus+genome raw   ty8  s4", true, true, -1, 8, 4},
+  };
+  int cfg_index = -1;
+  for (const Cfg& c : cfgs) {
+    ++cfg_index;
+    if (only_cfg >= 0 && cfg_index != only_cfg) continue;
+    StreamPlan pl = plan_stream(units, n_loci, sms, c.ty, c.stages);
+    if (pl.smem > 227 * 1024) { std::printf("%-28s skipped (smem %zu)\n", c.name, pl.smem); continue; }
+    CK(cudaMalloc(&d_planes, pl.n_vchunks * units * kStreamPlaneWords * 4));
+    StreamParams P{};
+    fill_stream_params(P, pl);
+    P.packed = d_packed; P.units = units; P.n_loci = n_loci; P.n_genomes = n_genomes;
+    P.flags16 = c.flags_mode < 0 ? nullptr : d_flags[c.flags_mode];
+    P.unit_need = d_need; P.popmask = d_popmask; P.n_pop = 6; P.locus_counts = c.wl ? d_lc : nullptr;
+    P.planes = c.wg ? d_planes : nullptr;
+    auto go = [&]() {
+      if (c.wl && c.wg) launch_stream<true, true>(P, pl, 0);
+      else if (c.wl) launch_stream<true, false>(P, pl, 0);
+      else if (c.wg) launch_stream<false, true>(P, pl, 0);
+      else launch_stream<false, false>(P, pl, 0);
+    };
+    for (int w = 0; w < 3; ++w) go();
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) go();
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::printf("%-28s %8.4f ms  %7.1f GB/s  (grid %ux%u, %d thr, ty %d, %d stages, smem %zu KB)\n", c.name, ms / reps,
+                matrix_bytes / (ms / reps * 1e-3) / 1e9, pl.n_ctas, pl.slices, pl.threads, pl.tyw, pl.n_stages, pl.smem >> 10);
+    CK(cudaFree(d_planes));
+  }
+
+  // ---- correctness on a prefix of the matrix ----
+  if (do_verify) {
+    const uint64_t vl = verify_loci < n_loci ? verify_loci : n_loci;
+    int bad = 0;
+    for (int mode = -1; mode <= 1; ++mode) {
+      for (int ty : {8, 16, 4}) {
+        StreamPlan pl = plan_stream(units, vl, sms, ty, 3);
+        CK(cudaMalloc(&d_planes, pl.n_vchunks * units * kStreamPlaneWords * 4));
+        CK(cudaMemset(d_planes, 0xAB, pl.n_vchunks * units * kStreamPlaneWords * 4));
+        StreamParams P{};
+        fill_stream_params(P, pl);
+        P.packed = d_packed; P.units = units; P.n_loci = vl; P.n_genomes = n_genomes;
+        P.flags16 = mode < 0 ? nullptr : d_flags[mode];
+        P.unit_need = d_need; P.popmask = d_popmask; P.n_pop = 6; P.locus_counts = d_lc; P.planes = d_planes;
+        CK(cudaMemset(d_lc, 0, vl * 16)); CK(cudaMemset(d_lc_ref, 0, vl * 16));
+        CK(cudaMemset(d_gc, 0, units * 64 * 8)); CK(cudaMemset(d_gc_ref, 0, units * 64 * 8));
+        launch_stream<true, true>(P, pl, 0);
+        if (pl.slices > 1) k_fix_locus_n0<<<(unsigned)((vl + 255) / 256), 256>>>(d_lc, vl, n_genomes);
+        dim3 eg((unsigned)((units * 64 + 255) / 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
+        k_expand_planes<<<eg, 256>>>(d_planes, pl.n_vchunks, units, units * 64, d_gc);
+        k_ref_locus<<<(unsigned)((vl * units + 255) / 256), 256>>>(d_packed, vl, units, d_lc_ref);
+        k_fix_locus_n0<<<(unsigned)((vl + 255) / 256), 256>>>(d_lc_ref, vl, n_genomes);
+        dim3 rg((n_genomes + 127) / 128, 64);
+        k_ref_genome<<<rg, 128>>>(d_packed, vl, units, mode < 0 ? nullptr : d_flags[mode], d_superpop, n_genomes, d_gc_ref);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> a(vl * 4), b(vl * 4), ga(units * 128), gb(units * 128);
+        CK(cudaMemcpy(a.data(), d_lc, vl * 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), d_lc_ref, vl * 16, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ga.data(), d_gc, units * 512, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(gb.data(), d_gc_ref, units * 512, cudaMemcpyDeviceToHost));
+        uint64_t dl = 0, dg = 0;
+        for (size_t i = 0; i < a.size(); ++i) dl += a[i] != b[i];
+        for (size_t i = 0; i < (size_t)n_genomes * 2; ++i) dg += ga[i] != gb[i];
+        std::printf("verify mode %2d ty %2d (grid %u, chunks %u): locus mismatches %llu, genome mismatches %llu  [g0 lo %u hi %u]\n", mode, pl.tyw,
+                    pl.n_ctas, pl.chunks_per_cta, (unsigned long long)dl, (unsigned long long)dg, ga[0], ga[1]);
+        bad += (dl != 0) + (dg != 0);
+        CK(cudaFree(d_planes));
+      }
+    }
+    std::printf(bad ? "VERIFY FAILED\n" : "VERIFY OK\n");
+    if (bad) return 1;
+  }
+  return 0;
+}
