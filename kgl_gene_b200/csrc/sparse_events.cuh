@@ -1,0 +1,161 @@
+// sparse_events.cuh -- the sparse side of the fused pass: code-3 ("dropped") cells and rare-major rows.
+//
+// The streaming kernel (stream_count.cuh) only counts set lo / hi bits. Two kinds of cells need more than a count, and
+// both are sparse in real data:
+//   * code-3 cells (first variant not in the AF list, >2 variants, missing ...; SURVEY flattener contract): they are not
+//     classified, so the locus' class frequencies leave the genome's expected sums (kga_analysis_inbreed_freq.cpp:462-543)
+//   * rows whose major allele is rare for a population (q <= 0.01): a hom-ref genome is dropped there (freq.cpp:532-539)
+// Dropped cells are indexed ONCE per uploaded matrix (k_dropped_count / k_dropped_index, part of the upload: the index is
+// the "side list" of the flattener contract in device form); every pass then visits only the indexed cells. Populations
+// with too many code-3 cells for an index fall back to k_dropped_scan, which re-reads the matrix.
+#pragma once
+#include "common.cuh"
+
+namespace kgl {
+
+struct DroppedCell { uint32_t row, genome; };
+
+// ---- index construction (upload time) ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_dropped_count(const uint4* __restrict__ packed, uint64_t n_cells128, unsigned long long* __restrict__ total) {
+  uint32_t c = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells128; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = ld_stream_u4(packed + i);
+    c += __popc(v.x & v.z) + __popc(v.y & v.w);
+  }
+  c = __reduce_add_sync(kFull, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
+}
+
+// Appends one DroppedCell per code-3 cell (any order). cursor starts at 0; capacity is the count from k_dropped_count.
+__global__ void __launch_bounds__(256)
+k_dropped_index(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t units, unsigned long long* __restrict__ cursor,
+                DroppedCell* __restrict__ cells, uint64_t capacity) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t base = i0 - lane; base < n_cells128; base += stride) {   // whole warps iterate together
+    const uint64_t i = base + lane;
+    uint64_t both = 0;
+    if (i < n_cells128) {
+      const uint4 v = ld_stream_u4(packed + i);
+      both = (uint64_t)(v.x & v.z) | ((uint64_t)(v.y & v.w) << 32);
+    }
+    const uint32_t n = (uint32_t)__popcll(both);
+    if (__any_sync(kFull, n != 0)) {
+      // warp-level exclusive scan of n, one atomic per warp
+      uint32_t incl = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      const uint32_t warp_total = __shfl_sync(kFull, incl, 31);
+      unsigned long long start = 0;
+      if (lane == 0) start = atomicAdd(cursor, (unsigned long long)warp_total);
+      start = __shfl_sync(kFull, start, 0);
+      uint64_t o = start + (incl - n);
+      const uint32_t row = (uint32_t)(i / units), unit = (uint32_t)(i % units);
+      while (both) {
+        const int b = __ffsll((long long)both) - 1;
+        both &= both - 1;
+        if (o < capacity) cells[o] = DroppedCell{row, unit * 64 + (uint32_t)b};
+        ++o;
+      }
+    }
+  }
+}
+
+// ---- per pass ---------------------------------------------------------------------------------------------------------------
+// Accumulators per genome: n3[g] (code-3 cells in rows selected for the genome), nz_rare[g] (non-reference cells in
+// rare-major rows), ecorr[g][2] (sum over the genome's dropped loci of e_majHom, e_minHom).
+struct SparseOut {
+  uint32_t* n3;
+  uint32_t* nz_rare;
+  double* ecorr;
+};
+
+// flags16 == null: raw mode (allele_count) -- every code-3 cell counts, no frequency corrections.
+__global__ void __launch_bounds__(256)
+k_dropped_apply(const DroppedCell* __restrict__ cells, uint64_t n_cells, const uint16_t* __restrict__ flags16,
+                const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  const DroppedCell c = cells[i];
+  if (flags16 == nullptr) { atomicAdd(&out.n3[c.genome], 1u); return; }
+  const int k = superpop[c.genome];
+  if (!((flags16[c.row] >> k) & 1u)) return;
+  atomicAdd(&out.n3[c.genome], 1u);
+  double a, h, m;
+  class_freqs(locus_freq(af[(uint64_t)k * n_loci + c.row]).p, a, h, m);
+  atomicAdd(&out.ecorr[(uint64_t)c.genome * 2 + 0], a);
+  atomicAdd(&out.ecorr[(uint64_t)c.genome * 2 + 1], m);
+}
+
+// Fallback without an index: one thread per 128-bit unit-row.
+__global__ void __launch_bounds__(256)
+k_dropped_scan(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t units, const uint16_t* __restrict__ flags16,
+               const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells128; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = ld_stream_u4(packed + i);
+    uint64_t both = (uint64_t)(v.x & v.z) | ((uint64_t)(v.y & v.w) << 32);
+    if (both == 0) continue;
+    const uint32_t row = (uint32_t)(i / units), unit = (uint32_t)(i % units);
+    const uint32_t fl = flags16 ? flags16[row] : 0u;
+    while (both) {
+      const int b = __ffsll((long long)both) - 1;
+      both &= both - 1;
+      const uint32_t g = unit * 64 + (uint32_t)b;
+      if (flags16 == nullptr) { atomicAdd(&out.n3[g], 1u); continue; }
+      const int k = superpop[g];
+      if (!((fl >> k) & 1u)) continue;
+      atomicAdd(&out.n3[g], 1u);
+      double a, h, m;
+      class_freqs(locus_freq(af[(uint64_t)k * n_loci + row]).p, a, h, m);
+      atomicAdd(&out.ecorr[(uint64_t)g * 2 + 0], a);
+      atomicAdd(&out.ecorr[(uint64_t)g * 2 + 1], m);
+    }
+  }
+}
+
+// Rare-major rows (flags16 high byte != 0; listed by k_locus_prepare). One warp per listed row, lane = unit (looping):
+// for every genome whose population has q <= 0.01 at this row: hom-ref -> the locus is dropped for it; else nz_rare++.
+__global__ void __launch_bounds__(256)
+k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare, const uint4* __restrict__ packed,
+            uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16, const uint64_t* __restrict__ popmask,
+            const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n = *n_rare;
+  for (uint32_t r = warp; r < n; r += n_warps) {
+    const uint32_t row = rare_rows[r];
+    const uint32_t rq = (uint32_t)flags16[row] >> 8;
+    for (int k = 0; k < n_pop; ++k) {
+      if (!((rq >> k) & 1u)) continue;
+      double a, h, m;
+      class_freqs(locus_freq(af[(uint64_t)k * n_loci + row]).p, a, h, m);
+      for (uint32_t u = lane; u < units; u += 32) {
+        const uint64_t mask = popmask[(uint64_t)k * units + u];
+        if (mask == 0) continue;
+        const uint4 v = packed[(uint64_t)row * units + u];
+        const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        uint64_t homref = ~(lo | hi) & mask;
+        uint64_t nonref = (lo | hi) & mask;
+        while (homref) {
+          const int b = __ffsll((long long)homref) - 1;
+          homref &= homref - 1;
+          const uint64_t g = (uint64_t)u * 64 + b;
+          atomicAdd(&out.ecorr[g * 2 + 0], a);
+          atomicAdd(&out.ecorr[g * 2 + 1], m);
+        }
+        while (nonref) {
+          const int b = __ffsll((long long)nonref) - 1;
+          nonref &= nonref - 1;
+          atomicAdd(&out.nz_rare[(uint64_t)u * 64 + b], 1u);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace kgl

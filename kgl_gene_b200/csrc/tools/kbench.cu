@@ -3,7 +3,7 @@
 //      denominators of DESIGN.md
 //   2. the streaming pass k_stream_count in its configurations, timed with CUDA events and checked against naive kernels
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o kbench kbench.cu
-#include "../stream_count.cuh"
+#include "../stream_launch.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -83,7 +83,15 @@ __global__ void k_fill_flags(uint16_t* flags, uint64_t n, int mode, uint64_t see
   if (i >= n) return;
   uint16_t f = 0x3f;
   if (mode == 1) { const uint64_t h = mix64(seed ^ i); if ((h & 63) == 0) f = (uint16_t)((h >> 8) & 0x3f); }   // ~1.6% partial rows
+  if (mode == 2) { const uint64_t h = mix64(seed ^ (i >> 9)); f = (h & 1) ? 0x3f : 0; }                        // windows of 512 rows on/off
   flags[i] = f;
+}
+__global__ void k_fill_sum64(const uint16_t* flags, uint64_t n_groups, uint16_t* sum64) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  uint32_t a = 0xFF, o = 0;
+  for (int i = 0; i < 64; ++i) { const uint32_t f = flags[g * 64 + i] & 0xFF; a &= f; o |= f; }
+  sum64[g] = (uint16_t)(a | (o << 8));
 }
 
 // naive references ------------------------------------------------------------------------------------------------------
@@ -126,19 +134,6 @@ __global__ void __launch_bounds__(256) k_read_only(const uint4* packed, uint64_t
   if (acc == 0x12345678u) out[0] = acc;
 }
 
-template <bool WL, bool WG>
-static void launch_stream(const StreamParams& P, const StreamPlan& pl, cudaStream_t st) {
-  dim3 grid(pl.n_ctas, pl.slices);
-  if (pl.threads <= 384) {
-    CK(cudaFuncSetAttribute(k_stream_count<WL, WG, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k_stream_count<WL, WG, 384><<<grid, pl.threads, pl.smem, st>>>(P);
-  } else {
-    CK(cudaFuncSetAttribute(k_stream_count<WL, WG, 704>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k_stream_count<WL, WG, 704><<<grid, pl.threads, pl.smem, st>>>(P);
-  }
-  CK(cudaGetLastError());
-}
-
 int main(int argc, char** argv) {
   uint64_t n_loci = 1100000; uint32_t n_genomes = 2504; int reps = 10; int do_pipes = 1; uint64_t verify_loci = 65536; int only_cfg = -1; int do_verify = 1;
   for (int i = 1; i < argc; ++i) {
@@ -169,29 +164,31 @@ int main(int argc, char** argv) {
     pipe_rate<9>("IADD+LOP3", 2, d_out, sms, clk);
   }
 
-  const uint64_t units = (n_genomes + 63) / 64;
-  std::vector<uint8_t> h_superpop(n_genomes), h_need(units, 0);
-  std::vector<uint64_t> h_popmask(6 * units, 0);
+  const uint64_t units = stream_units_padded((n_genomes + 63) / 64);
+  std::vector<uint8_t> h_superpop(n_genomes), h_need(units * 2, 0);
+  std::vector<uint32_t> h_popmask(6 * units * 2, 0);
   for (uint32_t g = 0; g < n_genomes; ++g) {
     const int k = (int)((uint64_t)g * 5 / n_genomes);
     h_superpop[g] = (uint8_t)k;
-    h_need[g >> 6] |= (uint8_t)(1u << k);
-    h_popmask[(size_t)k * units + (g >> 6)] |= 1ull << (g & 63);
+    h_need[g >> 5] |= (uint8_t)(1u << k);
+    h_popmask[(size_t)k * units * 2 + (g >> 5)] |= 1u << (g & 31);
   }
-  uint8_t *d_superpop, *d_need; uint64_t* d_popmask;
-  CK(cudaMalloc(&d_superpop, n_genomes)); CK(cudaMalloc(&d_need, units)); CK(cudaMalloc(&d_popmask, 6 * units * 8));
+  uint8_t *d_superpop, *d_need; uint32_t* d_popmask;
+  CK(cudaMalloc(&d_superpop, n_genomes)); CK(cudaMalloc(&d_need, units * 2)); CK(cudaMalloc(&d_popmask, 6 * units * 8));
   CK(cudaMemcpy(d_superpop, h_superpop.data(), n_genomes, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_need, h_need.data(), units, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_need, h_need.data(), units * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_popmask, h_popmask.data(), 6 * units * 8, cudaMemcpyHostToDevice));
 
-  const uint64_t pad_rows = n_loci + 4096;
+  const uint64_t pad_rows = (n_loci + 255) / 256 * 256;
   uint4* d_packed; CK(cudaMalloc(&d_packed, pad_rows * units * 16));
   CK(cudaMemset(d_packed, 0, pad_rows * units * 16));
   k_fill<<<(unsigned)((n_loci * units + 255) / 256), 256>>>(d_packed, n_loci, units, n_genomes, 140, 25, 66, 20261018ull);
-  uint16_t* d_flags[2];
-  for (int m = 0; m < 2; ++m) {
+  uint16_t* d_flags[3]; uint16_t* d_sum64[3];
+  for (int m = 0; m < 3; ++m) {
     CK(cudaMalloc(&d_flags[m], pad_rows * 2)); CK(cudaMemset(d_flags[m], 0, pad_rows * 2));
+    CK(cudaMalloc(&d_sum64[m], pad_rows / 64 * 2));
     k_fill_flags<<<(unsigned)((n_loci + 255) / 256), 256>>>(d_flags[m], n_loci, m, 99);
+    k_fill_sum64<<<(unsigned)((pad_rows / 64 + 255) / 256), 256>>>(d_flags[m], pad_rows / 64, d_sum64[m]);
   }
   uint32_t *d_lc, *d_lc_ref, *d_gc, *d_gc_ref, *d_planes;
   CK(cudaMalloc(&d_lc, n_loci * 16)); CK(cudaMalloc(&d_lc_ref, n_loci * 16));
@@ -209,42 +206,43 @@ int main(int argc, char** argv) {
     std::printf("read-only LDG.128 x4        %8.4f ms  %7.1f GB/s\n", ms / reps, matrix_bytes / (ms / reps * 1e-3) / 1e9);
   }
 
-  struct Cfg { const char* name; bool wl, wg; int flags_mode; int ty, stages; };
+  auto make_params = [&](const StreamPlan& pl, uint64_t loci, int flags_mode, bool wl, bool wg, uint32_t* planes) {
+    StreamParams P{};
+    fill_stream_params(P, pl);
+    P.packed = d_packed; P.units = (uint32_t)units; P.n_loci = (uint32_t)loci; P.n_genomes = n_genomes;
+    P.flags16 = flags_mode < 0 ? nullptr : d_flags[flags_mode];
+    P.sum64 = flags_mode < 0 ? nullptr : d_sum64[flags_mode];
+    P.need32 = d_need; P.popmask32 = d_popmask; P.n_pop = 6; P.locus_counts = wl ? d_lc : nullptr;
+    P.planes = wg ? planes : nullptr;
+    return P;
+  };
+
+  struct Cfg { const char* name; bool wl, wg; int flags_mode; int rows, stages; bool generic; };
   const Cfg cfgs[] = {
-      {"locus+genome full  ty8  s4", true, true, 0, 8, 4},   {"locus+genome full  ty8  s2", true, true, 0, 8, 2},
-      {"locus+genome full  ty16 s2", true, true, 0, 16, 2},  {"locus+genome full  ty4  s8", true, true, 0, 4, 8},
-      {"locus+genome full  ty8  s3", true, true, 0, 8, 3},
-      {"locus only         ty8  s4", true, false, 0, 8, 4},  {"genome only full   ty8  s4", false, true, 0, 8, 4},
-      {"neither (stream)   ty8  s4", false, false, 0, 8, 4}, {"locus+genome part. ty8  s4", true, true, 1, 8, 4},
-      {"locus+genome raw   ty8  s4", true, true, -1, 8, 4},
+      {"locus+genome full  auto   ", true, true, 0, 0, 0},    {"locus+genome full  s3     ", true, true, 0, 0, 3},
+      {"locus+genome full  s2     ", true, true, 0, 0, 2},    {"locus+genome full  generic", true, true, 0, 0, 0, true},
+      {"locus only         auto   ", true, false, 0, 0, 0},   {"genome only full   auto   ", false, true, 0, 0, 0},
+      {"neither (stream)   auto   ", false, false, 0, 0, 0},  {"locus+genome part. auto   ", true, true, 1, 0, 0},
+      {"locus+genome windows auto ", true, true, 2, 0, 0},    {"locus+genome raw   auto   ", true, true, -1, 0, 0},
   };
   int cfg_index = -1;
   for (const Cfg& c : cfgs) {
     ++cfg_index;
     if (only_cfg >= 0 && cfg_index != only_cfg) continue;
-    StreamPlan pl = plan_stream(units, n_loci, sms, c.ty, c.stages);
-    if (pl.smem > 227 * 1024) { std::printf("%-28s skipped (smem %zu)\n", c.name, pl.smem); continue; }
-    CK(cudaMalloc(&d_planes, pl.n_vchunks * units * kStreamPlaneWords * 4));
-    StreamParams P{};
-    fill_stream_params(P, pl);
-    P.packed = d_packed; P.units = units; P.n_loci = n_loci; P.n_genomes = n_genomes;
-    P.flags16 = c.flags_mode < 0 ? nullptr : d_flags[c.flags_mode];
-    P.unit_need = d_need; P.popmask = d_popmask; P.n_pop = 6; P.locus_counts = c.wl ? d_lc : nullptr;
-    P.planes = c.wg ? d_planes : nullptr;
-    auto go = [&]() {
-      if (c.wl && c.wg) launch_stream<true, true>(P, pl, 0);
-      else if (c.wl) launch_stream<true, false>(P, pl, 0);
-      else if (c.wg) launch_stream<false, true>(P, pl, 0);
-      else launch_stream<false, false>(P, pl, 0);
-    };
+    StreamPlan pl = plan_stream(units, n_loci, sms, c.rows, c.stages, !c.generic);
+    if (pl.smem > 227 * 1024 || pl.rows_per_stage * pl.h_parts != (uint32_t)kScHThreads) { std::printf("%-28s skipped (smem %zu)\n", c.name, pl.smem); continue; }
+    CK(cudaMalloc(&d_planes, pl.n_vchunks * units * 4 * kScLevels * 4));
+    StreamParams P = make_params(pl, n_loci, c.flags_mode, c.wl, c.wg, d_planes);
+    auto go = [&]() { CK(launch_stream(P, pl, c.wl, c.wg, 0)); };
     for (int w = 0; w < 3; ++w) go();
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
     for (int r = 0; r < reps; ++r) go();
     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-    std::printf("%-28s %8.4f ms  %7.1f GB/s  (grid %ux%u, %d thr, ty %d, %d stages, smem %zu KB)\n", c.name, ms / reps,
-                matrix_bytes / (ms / reps * 1e-3) / 1e9, pl.n_ctas, pl.slices, pl.threads, pl.tyw, pl.n_stages, pl.smem >> 10);
+    std::printf("%-28s %8.4f ms  %7.1f GB/s  (shape %d grid %ux%u, R %u, SU %u, parts %u, RL %u, %u stages, smem %zu KB)\n", c.name, ms / reps,
+                matrix_bytes / (ms / reps * 1e-3) / 1e9, pl.shape, pl.n_ctas, pl.slices, pl.rows_per_stage, pl.slice_units, pl.h_parts, pl.v_row_lanes,
+                pl.n_stages, pl.smem >> 10);
     CK(cudaFree(d_planes));
   }
 
@@ -252,19 +250,16 @@ int main(int argc, char** argv) {
   if (do_verify) {
     const uint64_t vl = verify_loci < n_loci ? verify_loci : n_loci;
     int bad = 0;
-    for (int mode = -1; mode <= 1; ++mode) {
-      for (int ty : {8, 16, 4}) {
-        StreamPlan pl = plan_stream(units, vl, sms, ty, 3);
-        CK(cudaMalloc(&d_planes, pl.n_vchunks * units * kStreamPlaneWords * 4));
-        CK(cudaMemset(d_planes, 0xAB, pl.n_vchunks * units * kStreamPlaneWords * 4));
-        StreamParams P{};
-        fill_stream_params(P, pl);
-        P.packed = d_packed; P.units = units; P.n_loci = vl; P.n_genomes = n_genomes;
-        P.flags16 = mode < 0 ? nullptr : d_flags[mode];
-        P.unit_need = d_need; P.popmask = d_popmask; P.n_pop = 6; P.locus_counts = d_lc; P.planes = d_planes;
+    for (int mode = -1; mode <= 2; ++mode) {
+      for (int rows : {0, 1, 64, 128, 256}) {
+        StreamPlan pl = plan_stream(units, vl, sms, rows == 1 ? 0 : rows, 3, rows != 1);
+        if (pl.smem > 227 * 1024) continue;
+        CK(cudaMalloc(&d_planes, pl.n_vchunks * units * 4 * kScLevels * 4));
+        CK(cudaMemset(d_planes, 0xAB, pl.n_vchunks * units * 4 * kScLevels * 4));
+        StreamParams P = make_params(pl, vl, mode, true, true, d_planes);
         CK(cudaMemset(d_lc, 0, vl * 16)); CK(cudaMemset(d_lc_ref, 0, vl * 16));
         CK(cudaMemset(d_gc, 0, units * 64 * 8)); CK(cudaMemset(d_gc_ref, 0, units * 64 * 8));
-        launch_stream<true, true>(P, pl, 0);
+        CK(launch_stream(P, pl, true, true, 0));
         if (pl.slices > 1) k_fix_locus_n0<<<(unsigned)((vl + 255) / 256), 256>>>(d_lc, vl, n_genomes);
         dim3 eg((unsigned)((units * 64 + 255) / 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
         k_expand_planes<<<eg, 256>>>(d_planes, pl.n_vchunks, units, units * 64, d_gc);
@@ -279,8 +274,8 @@ int main(int argc, char** argv) {
         uint64_t dl = 0, dg = 0;
         for (size_t i = 0; i < a.size(); ++i) dl += a[i] != b[i];
         for (size_t i = 0; i < (size_t)n_genomes * 2; ++i) dg += ga[i] != gb[i];
-        std::printf("verify mode %2d ty %2d (grid %u, chunks %u): locus mismatches %llu, genome mismatches %llu  [g0 lo %u hi %u]\n", mode, pl.tyw,
-                    pl.n_ctas, pl.chunks_per_cta, (unsigned long long)dl, (unsigned long long)dg, ga[0], ga[1]);
+        std::printf("verify mode %2d shape %d R %3u (grid %ux%u, chunks %u, RL %u): locus mismatches %llu, genome mismatches %llu  [g0 lo %u hi %u]\n", mode, pl.shape,
+                    pl.rows_per_stage, pl.n_ctas, pl.slices, pl.chunks_per_cta, pl.v_row_lanes, (unsigned long long)dl, (unsigned long long)dg, ga[0], ga[1]);
         bad += (dl != 0) + (dg != 0);
         CK(cudaFree(d_planes));
       }
