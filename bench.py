@@ -4,7 +4,7 @@
 Metric: inbreeding genotype-loci/s (BASELINE.json `metric`) on config 2, the chr22 shape: 2,504 genomes x 1.1 M biallelic
 SNPs, per-locus allele counts + per-genome inbreeding (Simple estimator: class counts, expected class-frequency sums, F)
 with a gnomAD-style float AF vector per super-population. One "step" = one fused pass over one batch of synthetic input:
-per-locus preparation from the AF vectors, the streaming kernel k_count_moments over the 2-bit matrix, counter expansion,
+per-locus preparation from the AF vectors, the streaming kernel k_stream_count_ct over the 2-bit matrix, counter expansion,
 moment assembly and the closed-form estimator.
 
   value : whole-job genotype-loci/s with the inputs resident in HBM (CUDA events on the launching stream, max over ranks)
@@ -297,12 +297,12 @@ def run_ours(args):
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         k_ms = float(np.mean(kernel_ms)) if len(kernel_ms) else None
-        # algorithmic bytes of one k_count_moments launch: 2 bits per genotype + 2 B selection flags and 16 B of counts per locus
+        # algorithmic bytes of one k_stream_count launch: 2 bits per genotype + 2 B selection flags and 16 B of counts per locus
         alg_bytes = n * l / 4.0 + 2.0 * l + 16.0 * l
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
         traffic = None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "k_count_moments_traffic.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "k_stream_count_traffic.json")))
             if prof.get("n_genomes") == n and prof.get("n_loci") == l:
                 traffic = prof.get("dram_bytes_per_launch")
         except Exception:
@@ -314,10 +314,10 @@ def run_ours(args):
             "config": {"workload": workload_name(n, l, world), "n_genomes": n, "n_loci_per_gpu": l, "af_vectors": int(af.shape[0]),
                        "selection": "one window, all loci", "missing_rate": 0.001,
                        "l2": f"inputs ({l * rb / 1e6:.0f} MB matrix per GPU) are larger than the 126 MB L2; no flush needed",
-                       "step": "k_locus_prepare + k_reduce_totals + k_count_moments + k_expand_counts + k_moment_partials (+ NCCL all-reduce) + k_finalize_closed_form"},
+                       "step": "k_locus_prepare + k_reduce_totals + k_stream_count_ct + k_expand_planes + k_dropped_apply + k_rare_rows + k_moment_partials (+ NCCL all-reduce) + k_finalize_closed_form"},
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_count_moments", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_stream_count_ct<40,64>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * len(kernel_ms) / total_ms) if k_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes},

@@ -3,7 +3,8 @@
 
 #include "common.cuh"
 #include "locus_kernels.cuh"
-#include "count_moments.cuh"
+#include "stream_launch.cuh"
+#include "sparse_events.cuh"
 #include "sample_major.cuh"
 #include "misc_kernels.cuh"
 
@@ -52,14 +53,19 @@ struct kgl_b200_ctx {
   std::string err;
   uint64_t launches = 0;
 
-  // population
-  uint64_t N = 0, L = 0, row_bytes = 0, units = 0, Npad = 0;
+  // population. units = device row pitch in 128-bit units (>= host_units: wide populations are padded to 40-unit slices)
+  uint64_t N = 0, L = 0, row_bytes = 0, host_units = 0, units = 0, Npad = 0, padded_rows = 0;
   uint32_t n_pop = 0;
   bool have_geno = false, have_loci = false, have_superpop = false, unphased = false;
   DevBuf<uint8_t> d_packed;
   DevBuf<float> d_af;
-  DevBuf<uint8_t> d_superpop, d_sel, d_unit_pop;
+  DevBuf<uint8_t> d_superpop, d_sel, d_need32;
   DevBuf<uint64_t> d_popmask;
+  // dropped-cell index (built once per uploaded matrix)
+  DevBuf<DroppedCell> d_dropped;
+  DevBuf<unsigned long long> d_dropped_counter;
+  uint64_t n_dropped = 0;
+  bool dropped_indexed = false, dropped_valid = false;
   std::vector<float> h_af;
   std::vector<uint32_t> h_offsets;
   std::vector<uint8_t> h_superpop, h_sel;
@@ -67,8 +73,8 @@ struct kgl_b200_ctx {
   bool units_valid = false;
 
   // per-locus preparation
-  DevBuf<uint16_t> d_flags16;
-  DevBuf<uint32_t> d_selw;
+  DevBuf<uint16_t> d_flags16, d_sum64;
+  DevBuf<uint32_t> d_selw, d_rare_rows, d_n_rare;
   DevBuf<double> d_block_totals, d_totals;
   bool prep_valid = false;
 
@@ -78,8 +84,11 @@ struct kgl_b200_ctx {
   bool sm_valid = false;
 
   // fused pass outputs
-  DevBuf<uint32_t> d_locus_counts, d_planes, d_gcounts, d_nz_rare;
-  DevBuf<double> d_ecorr, d_partials, d_iter, d_f, d_bracket, d_chunk_out, d_inbreeding, d_grid;
+  DevBuf<uint32_t> d_locus_counts, d_planes;
+  DevBuf<uint8_t> d_scratch;            // per-genome accumulators of one pass, zeroed with a single memset
+  uint32_t *d_gcounts = nullptr, *d_n3 = nullptr, *d_nz_rare = nullptr;
+  double* d_ecorr = nullptr;
+  DevBuf<double> d_partials, d_iter, d_f, d_bracket, d_chunk_out, d_inbreeding, d_grid;
   DevBuf<uint32_t> d_done;
   DevBuf<unsigned long long> d_flag;
   DevBuf<uint64_t> d_genome_counts;
@@ -121,29 +130,21 @@ int use_device(kgl_b200_ctx* c) {
   return KGL_B200_OK;
 }
 
-// Super-population of every 128-bit unit (0xFF = mixed) and the per-population genome masks.
+// Per-population genome masks of every 128-bit unit (read as 32-bit halves by the streaming kernel) and the populations
+// present in every 32-genome group.
 int build_unit_tables(kgl_b200_ctx* c) {
   if (c->units_valid) return KGL_B200_OK;
   const uint64_t units = c->units;
-  std::vector<uint8_t> unit_pop(units, 0);
+  std::vector<uint8_t> need32(units * 2, 0);
   std::vector<uint64_t> popmask((size_t)KGL_B200_MAX_POP * units, 0);
-  c->any_mixed = false;
-  for (uint64_t u = 0; u < units; ++u) {
-    int first = -1;
-    bool mixed = false;
-    for (int b = 0; b < 64; ++b) {
-      const uint64_t g = u * 64 + b;
-      if (g >= c->N) break;
-      const int k = c->h_superpop[g];
-      popmask[(size_t)k * units + u] |= 1ull << b;
-      if (first < 0) first = k; else if (k != first) mixed = true;
-    }
-    unit_pop[u] = mixed ? 0xFF : (uint8_t)std::max(first, 0);
-    c->any_mixed |= mixed;
+  for (uint64_t g = 0; g < c->N; ++g) {
+    const int k = c->h_superpop[g];
+    popmask[(size_t)k * units + (g >> 6)] |= 1ull << (g & 63);
+    need32[g >> 5] |= (uint8_t)(1u << k);
   }
-  KGL_CUDA(c, c->d_unit_pop.ensure(units));
+  KGL_CUDA(c, c->d_need32.ensure(need32.size()));
   KGL_CUDA(c, c->d_popmask.ensure(popmask.size()));
-  KGL_CUDA(c, cudaMemcpyAsync(c->d_unit_pop.p, unit_pop.data(), units, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_need32.p, need32.data(), need32.size(), cudaMemcpyHostToDevice, c->stream));
   KGL_CUDA(c, cudaMemcpyAsync(c->d_popmask.p, popmask.data(), popmask.size() * 8, cudaMemcpyHostToDevice, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->units_valid = true;
@@ -162,23 +163,31 @@ int require_population(kgl_b200_ctx* c, bool need_loci) {
   return KGL_B200_OK;
 }
 
-// Selection flags, packed selection words and dense totals (once per selection).
+uint64_t term_words(uint64_t n_loci) {
+  const uint64_t nw = (n_loci + 31) / 32;
+  return (nw + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
+}
+
+// Selection flags, 64-row summaries, packed selection words, rare-major row list and dense totals (once per selection).
 int ensure_prepared(kgl_b200_ctx* c) {
   if (c->prep_valid) return KGL_B200_OK;
   const uint64_t L = c->L;
-  c->n_words = (L + 31) / 32;
-  c->n_words = (c->n_words + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
-  const unsigned nb = std::max(1u, blocks_for(L, kPrepThreads));
-  KGL_CUDA(c, c->d_flags16.ensure(L));
+  c->n_words = term_words(L);
+  const uint64_t span = std::max<uint64_t>(c->padded_rows, c->n_words * 32);
+  const unsigned nb = (unsigned)std::max<uint64_t>(1, (span + kPrepLociPerBlock - 1) / kPrepLociPerBlock);
+  KGL_CUDA(c, c->d_flags16.ensure(c->padded_rows));
+  KGL_CUDA(c, c->d_sum64.ensure(c->padded_rows / 64));
   KGL_CUDA(c, c->d_selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
+  KGL_CUDA(c, c->d_rare_rows.ensure(L));
+  KGL_CUDA(c, c->d_n_rare.ensure(1));
   KGL_CUDA(c, c->d_block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
   KGL_CUDA(c, c->d_totals.ensure(kMaxPop * TOT_COUNT));
-  KGL_CUDA(c, cudaMemsetAsync(c->d_selw.p, 0, (size_t)KGL_B200_MAX_POP * c->n_words * 4, c->stream));
-  KGL_CUDA(c, cudaMemsetAsync(c->d_block_totals.p, 0, (size_t)nb * kMaxPop * TOT_COUNT * 8, c->stream));
-  k_locus_prepare<<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, (int)c->n_pop, 0, c->d_flags16.p,
-                                                      c->d_selw.p, c->n_words, c->d_block_totals.p);
+  KGL_CUDA(c, cudaMemsetAsync(c->d_n_rare.p, 0, 4, c->stream));
+  k_locus_prepare<<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
+                                                      c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
+                                                      c->d_block_totals.p);
   KGL_LAUNCH_CHECK(c);
-  k_reduce_totals<<<1, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p);
+  k_reduce_totals<<<kMaxPop * TOT_COUNT, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p);
   KGL_LAUNCH_CHECK(c);
   c->prep_valid = true;
   return KGL_B200_OK;
@@ -187,68 +196,91 @@ int ensure_prepared(kgl_b200_ctx* c) {
 int ensure_sample_major(kgl_b200_ctx* c) {
   if (c->sm_valid) return KGL_B200_OK;
   c->n_gblocks = c->units * 2;
-  uint64_t nw = (c->L + 31) / 32;
-  nw = (nw + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
+  const uint64_t nw = term_words(c->L);
   c->n_words = nw;
   const size_t n = (size_t)c->n_gblocks * nw * 32;
   KGL_CUDA(c, c->d_sm_lo.ensure(n));
   KGL_CUDA(c, c->d_sm_hi.ensure(n));
   dim3 grid((unsigned)nw, (unsigned)((c->n_gblocks + 7) / 8));
-  k_to_sample_major<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->d_packed.p), c->row_bytes / 4, c->L,
+  k_to_sample_major<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->d_packed.p), c->units * 4, c->L,
                                                   c->n_gblocks, nw, c->d_sm_lo.p, c->d_sm_hi.p);
   KGL_LAUNCH_CHECK(c);
   c->sm_valid = true;
   return KGL_B200_OK;
 }
 
-struct CountLaunch { int sw, ty; unsigned slices, n_chunks; uint32_t rows_per_cta; };
-
-CountLaunch plan_count(const kgl_b200_ctx* c) {
-  CountLaunch p;
-  p.sw = (int)std::min<uint64_t>(c->units, kCountThreads);
-  p.ty = std::max(1, std::min(kCountMaxTY, kCountThreads / p.sw));
-  p.slices = (unsigned)((c->units + p.sw - 1) / p.sw);
-  const uint64_t group = (uint64_t)kCountUnroll * p.ty;
-  uint64_t target = std::max<uint64_t>(1, (uint64_t)c->sm_count * 2 / p.slices);
-  uint64_t rows = (c->L + target - 1) / target;
-  rows = std::max<uint64_t>(group, (rows + group - 1) / group * group);
-  const uint64_t max_rows = (uint64_t)kMaxRowsPerThread / kCountUnroll * kCountUnroll * p.ty;
-  rows = std::min(rows, max_rows);
-  p.rows_per_cta = (uint32_t)rows;
-  p.n_chunks = (unsigned)std::max<uint64_t>(1, (c->L + rows - 1) / rows);
-  return p;
+// The side list of code-3 cells (SURVEY flattener contract), built on the device once per uploaded matrix.
+// Populations with more than ~1.5% code-3 cells are not indexed: every pass scans the matrix for them instead.
+int build_dropped_index(kgl_b200_ctx* c) {
+  if (c->dropped_valid) return KGL_B200_OK;
+  const uint64_t n128 = c->L * c->units;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+  KGL_CUDA(c, c->d_dropped_counter.ensure(2));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_dropped_counter.p, 0, 16, c->stream));
+  k_dropped_count<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, c->d_dropped_counter.p);
+  KGL_LAUNCH_CHECK(c);
+  unsigned long long total = 0;
+  KGL_CUDA(c, cudaMemcpyAsync(&total, c->d_dropped_counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_dropped = total;
+  c->dropped_indexed = total <= std::max<uint64_t>(1u << 16, c->N * c->L / 64);
+  if (c->dropped_indexed && total > 0) {
+    KGL_CUDA(c, c->d_dropped.ensure(total));
+    k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units,
+                                                  c->d_dropped_counter.p + 1, c->d_dropped.p, total);
+    KGL_LAUNCH_CHECK(c);
+  }
+  c->dropped_valid = true;
+  return KGL_B200_OK;
 }
 
-// The fused streaming pass. raw: allele_count over all loci; otherwise over the selected loci with corrections.
+// Device storage of the genotype matrix: rows padded to a multiple of 256 (zero rows), row pitch c->units.
+int alloc_matrix(kgl_b200_ctx* c) {
+  c->padded_rows = (c->L + 255) / 256 * 256;
+  const size_t bytes = (size_t)c->padded_rows * c->units * 16;
+  KGL_CUDA(c, c->d_packed.ensure(bytes));
+  if (c->units != c->host_units) {
+    KGL_CUDA(c, cudaMemsetAsync(c->d_packed.p, 0, bytes, c->stream));
+  } else {
+    KGL_CUDA(c, cudaMemsetAsync(c->d_packed.p + (size_t)c->L * c->units * 16, 0, (size_t)(c->padded_rows - c->L) * c->units * 16, c->stream));
+  }
+  return KGL_B200_OK;
+}
+
+// The fused streaming pass + its sparse companions. raw: allele_count over all loci; otherwise over the selected loci.
+// Leaves d_gcounts {lo, hi}, d_n3, d_nz_rare, d_ecorr per genome and the per-locus counts.
 int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome) {
   int rc = build_unit_tables(c);
   if (rc) return rc;
-  const CountLaunch pl = plan_count(c);
-  const uint64_t vchunks = (uint64_t)pl.n_chunks * pl.ty;
+  rc = build_dropped_index(c);
+  if (rc) return rc;
+  const StreamPlan pl = plan_stream(c->units, c->L, c->sm_count);
+  if (pl.padded_rows > c->padded_rows) return fail(c, KGL_B200_ERR_STATE, "internal: stream plan needs more padded rows than allocated");
   if (want_locus_counts) {
     KGL_CUDA(c, c->d_locus_counts.ensure((size_t)c->L * 4));
     if (pl.slices > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_locus_counts.p, 0, (size_t)c->L * 16, c->stream));
   }
   if (want_genome) {
-    KGL_CUDA(c, c->d_planes.ensure((size_t)vchunks * c->units * 3 * 2 * kLevels));
-    KGL_CUDA(c, c->d_gcounts.ensure((size_t)c->Npad * 4));
-    KGL_CUDA(c, c->d_ecorr.ensure((size_t)c->Npad * 2));
-    KGL_CUDA(c, c->d_nz_rare.ensure(c->Npad));
-    KGL_CUDA(c, cudaMemsetAsync(c->d_gcounts.p, 0, (size_t)c->Npad * 16, c->stream));
-    KGL_CUDA(c, cudaMemsetAsync(c->d_ecorr.p, 0, (size_t)c->Npad * 16, c->stream));
-    KGL_CUDA(c, cudaMemsetAsync(c->d_nz_rare.p, 0, (size_t)c->Npad * 4, c->stream));
+    KGL_CUDA(c, c->d_planes.ensure((size_t)pl.n_vchunks * c->units * 4 * kScLevels));
+    // scratch: gcounts u32[Npad][2] | n3 u32[Npad] | nz_rare u32[Npad] | ecorr f64[Npad][2]
+    KGL_CUDA(c, c->d_scratch.ensure((size_t)c->Npad * 32));
+    c->d_gcounts = reinterpret_cast<uint32_t*>(c->d_scratch.p);
+    c->d_n3 = c->d_gcounts + c->Npad * 2;
+    c->d_nz_rare = c->d_n3 + c->Npad;
+    c->d_ecorr = reinterpret_cast<double*>(c->d_scratch.p + (size_t)c->Npad * 16);
+    KGL_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0, (size_t)c->Npad * 32, c->stream));
   }
-  CountParams P{};
+  StreamParams P{};
+  fill_stream_params(P, pl);
   P.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
-  P.units = c->units; P.n_loci = c->L; P.n_genomes = c->N;
-  P.rows_per_cta = pl.rows_per_cta; P.sw = pl.sw; P.ty = pl.ty;
-  P.flags16 = c->d_flags16.p; P.unit_pop = c->d_unit_pop.p; P.popmask = c->d_popmask.p;
-  P.superpop = c->d_superpop.p; P.af = c->d_af.p; P.n_pop = (int)c->n_pop;
-  P.raw = raw ? 1 : 0; P.multi_slice = pl.slices > 1 ? 1 : 0;
+  P.units = (uint32_t)c->units; P.n_loci = (uint32_t)c->L; P.n_genomes = (uint32_t)c->N;
+  P.flags16 = raw ? nullptr : c->d_flags16.p;
+  P.sum64 = raw ? nullptr : c->d_sum64.p;
+  P.popmask32 = reinterpret_cast<const uint32_t*>(c->d_popmask.p);     // little endian: u64 mask = {low half, high half}
+  P.need32 = c->d_need32.p;
+  P.n_pop = raw ? 1 : c->n_pop;
   P.locus_counts = want_locus_counts ? c->d_locus_counts.p : nullptr;
   P.planes = want_genome ? c->d_planes.p : nullptr;
-  P.ecorr = c->d_ecorr.p; P.nz_rare = c->d_nz_rare.p;
-  dim3 grid(pl.n_chunks, pl.slices);
   cudaEvent_t e0 = c->ev0, e1 = c->ev1;
   if (c->timer_used < kgl_b200_ctx::kTimerSlots) {
     if ((int)c->timer_ev.size() < 2 * (c->timer_used + 1)) {
@@ -261,9 +293,8 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     ++c->timer_used;
   }
   KGL_CUDA(c, cudaEventRecord(e0, c->stream));
-  if (c->any_mixed && !raw) k_count_moments<true><<<grid, kCountThreads, 0, c->stream>>>(P);
-  else k_count_moments<false><<<grid, kCountThreads, 0, c->stream>>>(P);
-  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, launch_stream(P, pl, want_locus_counts, want_genome, c->stream));
+  ++c->launches;
   KGL_CUDA(c, cudaEventRecord(e1, c->stream));
   c->ev_valid = true;
   c->last_e0 = e0; c->last_e1 = e1;
@@ -272,9 +303,29 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     KGL_LAUNCH_CHECK(c);
   }
   if (want_genome) {
-    dim3 eg(blocks_for(c->Npad, 256), (unsigned)((vchunks + kExpandChunkGroup - 1) / kExpandChunkGroup));
-    k_expand_counts<<<eg, 256, 0, c->stream>>>(c->d_planes.p, vchunks, c->units, c->Npad, c->d_gcounts.p);
+    dim3 eg(blocks_for(c->Npad, 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
+    k_expand_planes<<<eg, 256, 0, c->stream>>>(c->d_planes.p, pl.n_vchunks, c->units, c->Npad, c->d_gcounts);
     KGL_LAUNCH_CHECK(c);
+    const SparseOut so{c->d_n3, c->d_nz_rare, c->d_ecorr};
+    const uint16_t* fl = raw ? nullptr : c->d_flags16.p;
+    if (c->n_dropped > 0) {
+      if (c->dropped_indexed) {
+        k_dropped_apply<<<blocks_for(c->n_dropped, 256), 256, 0, c->stream>>>(c->d_dropped.p, c->n_dropped, fl, c->d_superpop.p,
+                                                                               c->d_af.p, c->L, so);
+      } else {
+        const uint64_t n128 = c->L * c->units;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+        k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
+                                                     c->d_superpop.p, c->d_af.p, c->L, so);
+      }
+      KGL_LAUNCH_CHECK(c);
+    }
+    if (!raw) {
+      k_rare_rows<<<c->sm_count, 256, 0, c->stream>>>(c->d_rare_rows.p, c->d_n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
+                                                       (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
+                                                       c->L, (int)c->n_pop, so);
+      KGL_LAUNCH_CHECK(c);
+    }
   }
   return KGL_B200_OK;
 }
@@ -286,7 +337,7 @@ int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts) {
   rc = launch_count(c, false, want_locus_counts, true);
   if (rc) return rc;
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
-  k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts.p, c->d_totals.p, c->d_ecorr.p, c->d_nz_rare.p,
+  k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->d_totals.p, c->d_ecorr, c->d_nz_rare,
                                                                   c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p);
   KGL_LAUNCH_CHECK(c);
   return KGL_B200_OK;
@@ -375,10 +426,11 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_unit_pop.release();
+  c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_need32.release();
   c->d_popmask.release(); c->d_flags16.release(); c->d_selw.release(); c->d_block_totals.release(); c->d_totals.release();
-  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_planes.release(); c->d_gcounts.release();
-  c->d_nz_rare.release(); c->d_ecorr.release(); c->d_partials.release(); c->d_iter.release(); c->d_f.release();
+  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_planes.release(); c->d_scratch.release();
+  c->d_dropped.release(); c->d_dropped_counter.release(); c->d_sum64.release(); c->d_rare_rows.release(); c->d_n_rare.release();
+  c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
   for (cudaEvent_t e : c->timer_ev) cudaEventDestroy(e);
@@ -439,8 +491,9 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   // (require_population reports what is missing at run time).
   if (c->have_loci && c->h_af.size() != (size_t)c->n_pop * n_loci) { c->have_loci = false; c->prep_valid = false; }
   if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
-  c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->units = row_bytes / 16; c->Npad = c->units * 64;
-  c->sm_valid = false; c->units_valid = false;
+  c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
+  c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
+  c->sm_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false;
   return KGL_B200_OK;
 }
 
@@ -448,11 +501,14 @@ int kgl_b200_upload_genotypes(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_lo
   if (!c || !packed) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   int rc = use_device(c); if (rc) return rc;
   rc = set_shape(c, n_genomes, n_loci, row_bytes); if (rc) return rc;
-  KGL_CUDA(c, c->d_packed.ensure((size_t)n_loci * row_bytes));
-  KGL_CUDA(c, cudaMemcpyAsync(c->d_packed.p, packed, (size_t)n_loci * row_bytes, cudaMemcpyHostToDevice, c->stream));
-  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  rc = alloc_matrix(c); if (rc) return rc;
+  if (c->units == c->host_units) {
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_packed.p, packed, (size_t)n_loci * row_bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    KGL_CUDA(c, cudaMemcpy2DAsync(c->d_packed.p, c->units * 16, packed, row_bytes, row_bytes, n_loci, cudaMemcpyHostToDevice, c->stream));
+  }
   c->have_geno = true;
-  return KGL_B200_OK;
+  return build_dropped_index(c);     // synchronises the stream
 }
 
 int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const float* af, const uint32_t* offsets) {
@@ -558,7 +614,7 @@ int kgl_b200_synth_genotypes(kgl_b200_ctx* c, uint64_t seed, uint64_t n_genomes,
   const uint64_t row_bytes = 16 * ((n_genomes + 63) / 64);
   rc = set_shape(c, n_genomes, n_loci, row_bytes);
   if (rc) return rc;
-  KGL_CUDA(c, c->d_packed.ensure((size_t)n_loci * row_bytes));
+  rc = alloc_matrix(c); if (rc) return rc;
   KGL_CUDA(c, c->d_inbreeding.ensure(n_genomes));
   KGL_CUDA(c, cudaMemcpyAsync(c->d_inbreeding.p, inbreeding, n_genomes * 8, cudaMemcpyHostToDevice, c->stream));
   const uint64_t total = n_loci * c->units;
@@ -566,9 +622,8 @@ int kgl_b200_synth_genotypes(kgl_b200_ctx* c, uint64_t seed, uint64_t n_genomes,
                                                         c->d_inbreeding.p, (uint64_t)(missing_rate * 16777216.0),
                                                         reinterpret_cast<uint4*>(c->d_packed.p));
   KGL_LAUNCH_CHECK(c);
-  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->have_geno = true;
-  return KGL_B200_OK;
+  return build_dropped_index(c);     // synchronises the stream
 }
 
 int kgl_b200_download_genotypes(kgl_b200_ctx* c, uint64_t n_bytes, void* packed) {
@@ -576,7 +631,7 @@ int kgl_b200_download_genotypes(kgl_b200_ctx* c, uint64_t n_bytes, void* packed)
   if (!c->have_geno) return fail(c, KGL_B200_ERR_STATE, "no genotype matrix on the device");
   if (n_bytes != c->L * c->row_bytes) return fail(c, KGL_B200_ERR_INVALID, "n_bytes must be n_loci*row_bytes");
   int rc = use_device(c); if (rc) return rc;
-  KGL_CUDA(c, cudaMemcpyAsync(packed, c->d_packed.p, n_bytes, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaMemcpy2DAsync(packed, c->row_bytes, c->d_packed.p, c->units * 16, c->row_bytes, c->L, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   return KGL_B200_OK;
 }
@@ -595,7 +650,7 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t*
     KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
   if (genome_counts) {
     KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 4));
-    k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts.p, c->N, c->L, c->d_genome_counts.p);
+    k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->L, c->d_genome_counts.p);
     KGL_LAUNCH_CHECK(c);
     KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_genome_counts.p, (size_t)c->N * 32, cudaMemcpyDeviceToHost, c->stream));
   }

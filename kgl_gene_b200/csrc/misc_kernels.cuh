@@ -17,14 +17,15 @@ constexpr int ITER_COUNT = 4;
 
 // Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
 __global__ void __launch_bounds__(256)
-k_moment_partials(const uint32_t* __restrict__ gcounts, const double* __restrict__ totals, const double* __restrict__ ecorr,
+k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set hi bits} over the selected rows */,
+                  const uint32_t* __restrict__ n3s, const double* __restrict__ totals, const double* __restrict__ ecorr,
                   const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
                   int unphased, double* __restrict__ partials) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
   const int k = superpop[g];
   const double* T = totals + k * TOT_COUNT;
-  const double n1 = gcounts[g * 4 + 0], n2 = gcounts[g * 4 + 1], n3 = gcounts[g * 4 + 2];
+  const double n3 = n3s[g], n1 = (double)gcounts[g * 2 + 0] - n3, n2 = (double)gcounts[g * 2 + 1] - n3;
   // hom-ref cells in q > 0.01 rows: all such rows minus the non-reference cells that sit in them
   const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - (double)nz_rare[g]);
   double* P = partials + g * PART_COUNT;
@@ -186,10 +187,11 @@ __global__ void k_fill_double(double* p, uint64_t n, double v) {
   if (i < n) p[i] = v;
 }
 
-__global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, uint64_t n_genomes, uint64_t n_loci, uint64_t* __restrict__ out) {
+__global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, const uint32_t* __restrict__ n3s, uint64_t n_genomes,
+                                    uint64_t n_loci, uint64_t* __restrict__ out) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
-  const uint64_t n1 = gcounts[g * 4], n2 = gcounts[g * 4 + 1], n3 = gcounts[g * 4 + 2];
+  const uint64_t n3 = n3s[g], n1 = gcounts[g * 2] - n3, n2 = gcounts[g * 2 + 1] - n3;
   out[g * 4 + 0] = n_loci - n1 - n2 - n3; out[g * 4 + 1] = n1; out[g * 4 + 2] = n2; out[g * 4 + 3] = n3;
 }
 

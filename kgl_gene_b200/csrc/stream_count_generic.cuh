@@ -80,7 +80,7 @@ k_stream_count_rt(const StreamParams P) {
   const uint32_t v_wcol = tid % (SU * 4), v_rl = tid / (SU * 4);
   const bool v_active = WANT_GENOME && v_wcol < W && v_rl < P.v_row_lanes;
   const uint32_t v_rows = R / P.v_row_lanes;                            // rows per V thread per stage, multiple of 8
-  const uint32_t v_row0 = v_rl * v_rows;
+  const uint32_t v_row0 = v_active ? v_rl * v_rows : 0;                // inactive threads still read (and discard) flags
   const uint32_t g32 = (unit0 + (v_wcol >> 2)) * 2 + (v_wcol & 1);       // this word's 32-genome group
   uint32_t need = 0, pm[kMaxPop];
 #pragma unroll
