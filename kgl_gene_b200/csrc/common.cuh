@@ -44,18 +44,21 @@ __device__ __forceinline__ LocusFreq locus_freq(float af) {
 }
 
 // alleleClassFrequencies(0.0) (freq.cpp:127-217 + freq.h:54-63) for one alt allele: normalised {majHom, majHet, minHom}.
-// (minHet is identically 0 with a single alt allele.) Operation order follows the reference so results are bit-equal.
+// (minHet is identically 0 with a single alt allele.) The products follow the reference's operation order. The reference
+// then divides each class by sum = q^2 + 2qp + p^2, which is 1 + e with |e| < 1e-15 because q = fl(1 - p); here the
+// division is the multiplication by 2 - sum (= 1/sum to within e^2 < 1e-30, and exact in floating point), so a term can
+// differ from the reference's by at most one unit in the last place -- and the kernels need no double-precision divide.
 __device__ __forceinline__ void class_freqs(double p, double& maj_hom, double& maj_het, double& min_hom) {
   const double major = fmax(0.0, __dsub_rn(1.0, p));                      // :140
   const double minor = p;                                                  // sum_minor_freq <= 1 after the clamp (:143-151)
-  double mh = __dadd_rn(__dmul_rn(0.0, minor), __dmul_rn(__dmul_rn(1.0, minor), minor));   // :158 with inbreeding = 0
-  double Mh = __dadd_rn(__dmul_rn(0.0, major), __dmul_rn(__dmul_rn(1.0, major), major));   // :176
-  double Mt = __dmul_rn(__dmul_rn(__dmul_rn(1.0, 2.0), major), minor);                      // :181
-  mh = fmax(0.0, mh); Mh = fmax(0.0, Mh); Mt = fmax(0.0, Mt);              // nonNegative()
-  const double sum = __dadd_rn(__dadd_rn(__dadd_rn(Mh, Mt), mh), 0.0);     // sumFrequencies() order: MH + Mt + mh + mt(=0)
-  maj_hom = __ddiv_rn(Mh, sum);
-  maj_het = __ddiv_rn(Mt, sum);
-  min_hom = __ddiv_rn(mh, sum);
+  double mh = __dmul_rn(minor, minor);                                     // :158 with inbreeding = 0
+  double Mh = __dmul_rn(major, major);                                     // :176
+  double Mt = __dmul_rn(__dmul_rn(2.0, major), minor);                     // :181
+  const double sum = __dadd_rn(__dadd_rn(Mh, Mt), mh);                     // sumFrequencies() order: MH + Mt + mh + mt(=0)
+  const double r = __dsub_rn(2.0, sum);
+  maj_hom = __dmul_rn(Mh, r);
+  maj_het = __dmul_rn(Mt, r);
+  min_hom = __dmul_rn(mh, r);
 }
 
 constexpr double kMinMajorFreq = 0.01;     // minimum_major_frequency, freq.cpp:532

@@ -8,6 +8,8 @@
 #include "sample_major.cuh"
 #include "misc_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -62,8 +64,11 @@ struct kgl_b200_ctx {
   DevBuf<uint8_t> d_superpop, d_sel, d_need32;
   DevBuf<uint64_t> d_popmask;
   // dropped-cell index (built once per uploaded matrix)
-  DevBuf<DroppedCell> d_dropped;
+  DevBuf<DroppedKey> d_dropped;          // sorted keys (genome << 32 | row)
+  DevBuf<uint64_t> d_dropped_seg;        // [Npad + 1] first key of every genome
   DevBuf<unsigned long long> d_dropped_counter;
+  DevBuf<DroppedKey> d_dropped_unsorted;
+  DevBuf<uint8_t> d_sort_temp;
   uint64_t n_dropped = 0;
   bool dropped_indexed = false, dropped_valid = false;
   std::vector<float> h_af;
@@ -76,7 +81,7 @@ struct kgl_b200_ctx {
   DevBuf<uint16_t> d_flags16, d_sum64;
   DevBuf<uint32_t> d_selw, d_rare_rows, d_n_rare;
   DevBuf<double> d_block_totals, d_totals;
-  bool prep_valid = false;
+  bool prep_valid = false, prep_has_w0 = false;
 
   // sample-major copy
   DevBuf<uint32_t> d_sm_lo, d_sm_hi;
@@ -169,8 +174,8 @@ uint64_t term_words(uint64_t n_loci) {
 }
 
 // Selection flags, 64-row summaries, packed selection words, rare-major row list and dense totals (once per selection).
-int ensure_prepared(kgl_b200_ctx* c) {
-  if (c->prep_valid) return KGL_B200_OK;
+int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
+  if (c->prep_valid && (c->prep_has_w0 || !want_w0)) return KGL_B200_OK;
   const uint64_t L = c->L;
   c->n_words = term_words(L);
   const uint64_t span = std::max<uint64_t>(c->padded_rows, c->n_words * 32);
@@ -183,13 +188,18 @@ int ensure_prepared(kgl_b200_ctx* c) {
   KGL_CUDA(c, c->d_block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
   KGL_CUDA(c, c->d_totals.ensure(kMaxPop * TOT_COUNT));
   KGL_CUDA(c, cudaMemsetAsync(c->d_n_rare.p, 0, 4, c->stream));
-  k_locus_prepare<<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
-                                                      c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
-                                                      c->d_block_totals.p);
+  if (want_w0)
+    k_locus_prepare<true><<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
+                                                              c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
+                                                              c->d_block_totals.p);
+  else
+    k_locus_prepare<false><<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
+                                                               c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
+                                                               c->d_block_totals.p);
   KGL_LAUNCH_CHECK(c);
   k_reduce_totals<<<kMaxPop * TOT_COUNT, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p);
   KGL_LAUNCH_CHECK(c);
-  c->prep_valid = true;
+  c->prep_valid = true; c->prep_has_w0 = want_w0;
   return KGL_B200_OK;
 }
 
@@ -224,11 +234,29 @@ int build_dropped_index(kgl_b200_ctx* c) {
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n_dropped = total;
   c->dropped_indexed = total <= std::max<uint64_t>(1u << 16, c->N * c->L / 64);
-  if (c->dropped_indexed && total > 0) {
-    KGL_CUDA(c, c->d_dropped.ensure(total));
-    k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units,
-                                                  c->d_dropped_counter.p + 1, c->d_dropped.p, total);
+  if (c->dropped_indexed) {
+    KGL_CUDA(c, c->d_dropped.ensure(std::max<uint64_t>(total, 1)));
+    KGL_CUDA(c, c->d_dropped_seg.ensure(c->Npad + 1));
+    if (total > 0) {
+      // unsorted keys and the sort's scratch space are transient
+      DevBuf<DroppedKey>& unsorted = c->d_dropped_unsorted;   // kept: re-uploads of the same shape allocate nothing
+      DevBuf<uint8_t>& temp = c->d_sort_temp;
+      KGL_CUDA(c, unsorted.ensure(total));
+      k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units,
+                                                    c->d_dropped_counter.p + 1, unsorted.p, total);
+      KGL_LAUNCH_CHECK(c);
+      int end_bit = 33;
+      while (end_bit < 64 && (c->Npad >> (end_bit - 32)) != 0) ++end_bit;
+      size_t temp_bytes = 0;
+      cudaError_t e = cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, unsorted.p, c->d_dropped.p, (uint64_t)total, 0, end_bit, c->stream);
+      if (e == cudaSuccess) e = temp.ensure(temp_bytes);
+      if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(temp.p, temp_bytes, unsorted.p, c->d_dropped.p, (uint64_t)total, 0, end_bit, c->stream);
+      KGL_CUDA(c, e);
+      c->launches += 2;
+    }
+    k_dropped_segments<<<blocks_for(c->Npad + 1, 256), 256, 0, c->stream>>>(c->d_dropped.p, total, c->Npad, c->d_dropped_seg.p);
     KGL_LAUNCH_CHECK(c);
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   c->dropped_valid = true;
   return KGL_B200_OK;
@@ -310,8 +338,8 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     const uint16_t* fl = raw ? nullptr : c->d_flags16.p;
     if (c->n_dropped > 0) {
       if (c->dropped_indexed) {
-        k_dropped_apply<<<blocks_for(c->n_dropped, 256), 256, 0, c->stream>>>(c->d_dropped.p, c->n_dropped, fl, c->d_superpop.p,
-                                                                               c->d_af.p, c->L, so);
+        k_dropped_apply<<<blocks_for(c->N * 32, 256), 256, 0, c->stream>>>(c->d_dropped.p, c->d_dropped_seg.p, c->N, fl, c->d_superpop.p,
+                                                                            c->d_af.p, c->L, so);
       } else {
         const uint64_t n128 = c->L * c->units;
         const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
@@ -331,14 +359,15 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
 }
 
 // Moments of all genomes over the selected loci into d_partials (phase 0 of every estimator).
-int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts) {
-  int rc = ensure_prepared(c);
+int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false) {
+  int rc = ensure_prepared(c, want_w0);
   if (rc) return rc;
   rc = launch_count(c, false, want_locus_counts, true);
   if (rc) return rc;
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
   k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->d_totals.p, c->d_ecorr, c->d_nz_rare,
-                                                                  c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p);
+                                                                  c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p,
+                                                                  simple_results ? c->d_results.p : nullptr);
   KGL_LAUNCH_CHECK(c);
   return KGL_B200_OK;
 }
@@ -429,7 +458,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_need32.release();
   c->d_popmask.release(); c->d_flags16.release(); c->d_selw.release(); c->d_block_totals.release(); c->d_totals.release();
   c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_planes.release(); c->d_scratch.release();
-  c->d_dropped.release(); c->d_dropped_counter.release(); c->d_sum64.release(); c->d_rare_rows.release(); c->d_n_rare.release();
+  c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release(); c->d_sum64.release(); c->d_rare_rows.release(); c->d_n_rare.release();
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
@@ -663,11 +692,8 @@ int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   int rc = use_device(c); if (rc) return rc;
   rc = require_population(c, true); if (rc) return rc;
   c->prep_valid = false;   // the AF vectors are an input of the pass: the per-locus preparation is part of every step
-  rc = enqueue_moments(c, true); if (rc) return rc;
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
-  k_finalize_closed_form<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_partials.p, c->N, KGL_B200_ALGO_SIMPLE, c->d_results.p, nullptr);
-  KGL_LAUNCH_CHECK(c);
-  return KGL_B200_OK;
+  return enqueue_moments(c, true, true);
 }
 
 int kgl_b200_fetch_locus_counts(kgl_b200_ctx* c, uint32_t* locus_counts) {
@@ -721,7 +747,7 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   int rc = use_device(c); if (rc) return rc;
   TermLaunch tl;
   if (c->phase == 0) {
-    rc = enqueue_moments(c, c->opt.count_loci != 0); if (rc) return rc;
+    rc = enqueue_moments(c, c->opt.count_loci != 0, false, c->algo == KGL_B200_ALGO_RITLAND); if (rc) return rc;
     if (c->algo == KGL_B200_ALGO_RITLAND) {
       rc = launch_terms<TERM_RITLAND>(c, 3, nullptr, 0, tl); if (rc) return rc;
       k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 3, c->d_totals.p,

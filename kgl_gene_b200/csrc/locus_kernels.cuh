@@ -17,16 +17,19 @@ enum { TOT_T = 0,       // number of selected valid loci
        TOT_COUNT };
 
 constexpr int kPrepThreads = 256;
-constexpr int kPrepIters = 8;                                   // 64-locus groups per warp
-constexpr int kPrepLociPerBlock = (kPrepThreads / 32) * 64 * kPrepIters;   // 4096
+constexpr int kPrepIters = 4;                                   // 64-locus groups per warp
+constexpr int kPrepLociPerBlock = (kPrepThreads / 32) * 64 * kPrepIters;   // 2048
 
 // flags16[l] bit k: locus selected for population k AND its AF vector is valid; bit 8+k: ... AND q_k <= 0.01 ("rare-q")
 // sum64[l/64]  low byte: AND over the group's rows of the low flag byte, high byte: OR (rows >= n_loci count as 0)
 // selw[k][w]   bit i: flags bit k of locus 32w+i (sample-major kernels)
 // rare_rows / n_rare: list of the rows with a rare-q bit (any order)
-// block_totals[block][k][TOT_COUNT]
+// block_totals[block][k][TOT_COUNT]   (TOT_W0 only when WANT_W0: it costs a double-precision divide per locus and
+//                                      only the Ritland estimator reads it)
 // A warp owns 64 consecutive loci per iteration (lane -> l, l+32), so the group summary and the selection words need no
-// shared memory; the totals stay in registers until the end of the block.
+// shared memory. The population loop is the OUTER loop: only one population's six totals are live at a time, which keeps
+// the kernel at ~64 registers and the SM full of warps to hide the double-precision divide latency.
+template <bool WANT_W0>
 __global__ void __launch_bounds__(kPrepThreads)
 k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, uint64_t n_loci, uint64_t padded_rows, int n_pop,
                 int select_all, uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64,
@@ -34,34 +37,38 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
                 double* __restrict__ block_totals) {
   __shared__ double s_tot[kPrepThreads / 32][kMaxPop][TOT_COUNT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double acc[kMaxPop][TOT_COUNT];
+  const uint64_t base = (uint64_t)blockIdx.x * kPrepLociPerBlock + (uint64_t)warp * 64 + lane;   // + it * 512 + half * 32
+  uint32_t fl[kPrepIters][2], sbits[kPrepIters][2];
 #pragma unroll
-  for (int k = 0; k < kMaxPop; ++k)
-#pragma unroll
-    for (int j = 0; j < TOT_COUNT; ++j) acc[k][j] = 0.0;
-
-  for (int it = 0; it < kPrepIters; ++it) {
-    const uint64_t l0 = (uint64_t)blockIdx.x * kPrepLociPerBlock + ((uint64_t)it * (kPrepThreads / 32) + warp) * 64 + lane;
-    if (l0 - lane >= padded_rows && l0 - lane >= n_words * 32) break;       // warp-uniform
-    uint32_t fls[2];
+  for (int it = 0; it < kPrepIters; ++it)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const uint64_t l = l0 + 32 * half;
-      const uint8_t s = (l < n_loci) ? (select_all ? 0x3f : sel[l]) : 0;
-      uint32_t fl = 0, rq = 0;
+      const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
+      fl[it][half] = 0;
+      sbits[it][half] = (l < n_loci) ? (select_all ? 0x3fu : (uint32_t)sel[l]) : 0u;
+    }
+
+  for (int k = 0; k < kMaxPop; ++k) {
+    double acc[TOT_COUNT];
 #pragma unroll
-      for (int k = 0; k < kMaxPop; ++k) {
+    for (int j = 0; j < TOT_COUNT; ++j) acc[j] = 0.0;
+    uint32_t n_t = 0, n_tq = 0;
+#pragma unroll
+    for (int it = 0; it < kPrepIters; ++it)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
         bool on = false;
-        if (k < n_pop && ((s >> k) & 1)) {
+        if (k < n_pop && ((sbits[it][half] >> k) & 1u)) {
           const LocusFreq f = locus_freq(af[(uint64_t)k * n_loci + l]);
           if (f.valid) {
             on = true;
-            fl |= 1u << k;
+            fl[it][half] |= 1u << k;
             double a, b, c;
             class_freqs(f.p, a, b, c);
-            acc[k][TOT_T] += 1.0; acc[k][TOT_EMAJHOM] += a; acc[k][TOT_EMAJHET] += b; acc[k][TOT_EMINHOM] += c;
-            if (f.q > kMinMajorFreq) { acc[k][TOT_TQ] += 1.0; acc[k][TOT_W0] += __dsub_rn(__ddiv_rn(1.0, f.q), 1.0); }
-            else rq |= 1u << k;
+            ++n_t; acc[TOT_EMAJHOM] += a; acc[TOT_EMAJHET] += b; acc[TOT_EMINHOM] += c;
+            if (f.q > kMinMajorFreq) { ++n_tq; if (WANT_W0) acc[TOT_W0] += __dsub_rn(__ddiv_rn(1.0, f.q), 1.0); }
+            else fl[it][half] |= 0x100u << k;
           }
         }
         const uint32_t word = __ballot_sync(kFull, on);
@@ -70,22 +77,28 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
           if (w < n_words) selw[(uint64_t)k * n_words + w] = word;
         }
       }
-      if (l < padded_rows) flags16[l] = (uint16_t)(fl | (rq << 8));
-      if (rq != 0 && rare_rows != nullptr) rare_rows[atomicAdd(n_rare, 1u)] = (uint32_t)l;
-      fls[half] = fl;
+    acc[TOT_T] = (double)n_t; acc[TOT_TQ] = (double)n_tq;
+#pragma unroll
+    for (int j = 0; j < TOT_COUNT; ++j) {
+      const double v = warp_sum(acc[j]);
+      if (lane == 0) s_tot[warp][k][j] = v;
     }
-    const uint32_t g_and = __reduce_and_sync(kFull, fls[0] & fls[1]);
-    const uint32_t g_or = __reduce_or_sync(kFull, fls[0] | fls[1]);
-    if (lane == 0 && l0 < padded_rows) sum64[l0 >> 6] = (uint16_t)(g_and | (g_or << 8));
   }
 
 #pragma unroll
-  for (int k = 0; k < kMaxPop; ++k)
+  for (int it = 0; it < kPrepIters; ++it) {
+    const uint64_t l0 = base + (uint64_t)it * (kPrepThreads / 32) * 64;
 #pragma unroll
-    for (int j = 0; j < TOT_COUNT; ++j) {
-      const double v = warp_sum(acc[k][j]);
-      if (lane == 0) s_tot[warp][k][j] = v;
+    for (int half = 0; half < 2; ++half) {
+      const uint64_t l = l0 + 32 * half;
+      if (l < padded_rows) flags16[l] = (uint16_t)fl[it][half];
+      if ((fl[it][half] >> 8) != 0 && rare_rows != nullptr) rare_rows[atomicAdd(n_rare, 1u)] = (uint32_t)l;
     }
+    const uint32_t g_and = __reduce_and_sync(kFull, fl[it][0] & fl[it][1]) & 0xFFu;
+    const uint32_t g_or = __reduce_or_sync(kFull, fl[it][0] | fl[it][1]) & 0xFFu;
+    if (lane == 0 && l0 < padded_rows) sum64[l0 >> 6] = (uint16_t)(g_and | (g_or << 8));
+  }
+
   __syncthreads();
   if (threadIdx.x < kMaxPop * TOT_COUNT) {
     const int k = threadIdx.x / TOT_COUNT, j = threadIdx.x % TOT_COUNT;

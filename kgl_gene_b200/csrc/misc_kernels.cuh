@@ -15,35 +15,6 @@ enum { PART_NMAJHOM = 0, PART_NMAJHET, PART_NMINHOM, PART_NMINHET,
 // root search slots 0..3 = {dLL, d2LL, clamped hom terms, clamped het terms}.
 constexpr int ITER_COUNT = 4;
 
-// Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
-__global__ void __launch_bounds__(256)
-k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set hi bits} over the selected rows */,
-                  const uint32_t* __restrict__ n3s, const double* __restrict__ totals, const double* __restrict__ ecorr,
-                  const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
-                  int unphased, double* __restrict__ partials) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_genomes) return;
-  const int k = superpop[g];
-  const double* T = totals + k * TOT_COUNT;
-  const double n3 = n3s[g], n1 = (double)gcounts[g * 2 + 0] - n3, n2 = (double)gcounts[g * 2 + 1] - n3;
-  // hom-ref cells in q > 0.01 rows: all such rows minus the non-reference cells that sit in them
-  const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - (double)nz_rare[g]);
-  double* P = partials + g * PART_COUNT;
-  P[PART_NMAJHOM] = n_majhom;
-  P[PART_NMAJHET] = n1;
-  P[PART_NMINHOM] = unphased ? 0.0 : n2;
-  P[PART_NMINHET] = unphased ? n2 : 0.0;
-  const double d_majhom = ecorr[g * 2 + 0], d_minhom = ecorr[g * 2 + 1];
-  // dropped cells: code 3 in selected rows (n3) and hom-ref cells of rare-q rows; their class frequencies leave the sums.
-  const double n_dropped = (T[TOT_T] - T[TOT_TQ]) - (double)nz_rare[g] + n3;   // rare-q rows that are hom-ref + code-3 cells
-  P[PART_EMAJHOM] = T[TOT_EMAJHOM] - d_majhom;
-  P[PART_EMINHOM] = T[TOT_EMINHOM] - d_minhom;
-  // the three normalised class frequencies of a locus sum to 1, so the dropped majHet mass is n_dropped - majHom - minHom
-  P[PART_EMAJHET] = T[TOT_EMAJHET] - (n_dropped - d_majhom - d_minhom);
-  P[PART_EMINHET] = 0.0;
-  for (int j = PART_RSUM; j < PART_COUNT; ++j) P[j] = 0.0;
-}
-
 // Adds the Ritland terms (reduced over locus chunks) to the partials.
 __global__ void __launch_bounds__(256)
 k_ritland_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_genomes_padded, int n_out,
@@ -85,12 +56,7 @@ __device__ __forceinline__ void fill_results(const double* P, kgl_b200_locus_res
 }
 
 // processSimple (calc.cpp:333-359) / processRitlandLocus (calc.cpp:423) closed forms from the (all-reduced) partials.
-__global__ void __launch_bounds__(256)
-k_finalize_closed_form(const double* __restrict__ partials, uint64_t n_genomes, int algorithm,
-                       kgl_b200_locus_results* __restrict__ out, double* __restrict__ f_out) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_genomes) return;
-  const double* P = partials + g * PART_COUNT;
+__device__ __forceinline__ kgl_b200_locus_results closed_form(const double* P, int algorithm) {
   kgl_b200_locus_results r;
   fill_results(P, r);
   double coeff = 0.0;
@@ -104,9 +70,50 @@ k_finalize_closed_form(const double* __restrict__ partials, uint64_t n_genomes, 
     }
   }
   r.inbred_allele_sum = coeff;
-  if (out) out[g] = r;
-  if (f_out) f_out[g] = coeff;
+  return r;
 }
+
+__global__ void __launch_bounds__(256)
+k_finalize_closed_form(const double* __restrict__ partials, uint64_t n_genomes, int algorithm,
+                       kgl_b200_locus_results* __restrict__ out, double* __restrict__ f_out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const kgl_b200_locus_results r = closed_form(partials + g * PART_COUNT, algorithm);
+  if (out) out[g] = r;
+  if (f_out) f_out[g] = r.inbred_allele_sum;
+}
+
+// Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
+__global__ void __launch_bounds__(256)
+k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set hi bits} over the selected rows */,
+                  const uint32_t* __restrict__ n3s, const double* __restrict__ totals, const double* __restrict__ ecorr,
+                  const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
+                  int unphased, double* __restrict__ partials,
+                  kgl_b200_locus_results* __restrict__ simple_out /* nullable: also apply processSimple (calc.cpp:333-359) */) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  const int k = superpop[g];
+  const double* T = totals + k * TOT_COUNT;
+  const double n3 = n3s[g], n1 = (double)gcounts[g * 2 + 0] - n3, n2 = (double)gcounts[g * 2 + 1] - n3;
+  // hom-ref cells in q > 0.01 rows: all such rows minus the non-reference cells that sit in them
+  const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - (double)nz_rare[g]);
+  double* P = partials + g * PART_COUNT;
+  P[PART_NMAJHOM] = n_majhom;
+  P[PART_NMAJHET] = n1;
+  P[PART_NMINHOM] = unphased ? 0.0 : n2;
+  P[PART_NMINHET] = unphased ? n2 : 0.0;
+  const double d_majhom = ecorr[g * 2 + 0], d_minhom = ecorr[g * 2 + 1];
+  // dropped cells: code 3 in selected rows (n3) and hom-ref cells of rare-q rows; their class frequencies leave the sums.
+  const double n_dropped = (T[TOT_T] - T[TOT_TQ]) - (double)nz_rare[g] + n3;   // rare-q rows that are hom-ref + code-3 cells
+  P[PART_EMAJHOM] = T[TOT_EMAJHOM] - d_majhom;
+  P[PART_EMINHOM] = T[TOT_EMINHOM] - d_minhom;
+  // the three normalised class frequencies of a locus sum to 1, so the dropped majHet mass is n_dropped - majHom - minHom
+  P[PART_EMAJHET] = T[TOT_EMAJHET] - (n_dropped - d_majhom - d_minhom);
+  P[PART_EMINHET] = 0.0;
+  for (int j = PART_RSUM; j < PART_COUNT; ++j) P[j] = 0.0;
+  if (simple_out) simple_out[g] = closed_form(P, KGL_B200_ALGO_SIMPLE);
+}
+
 
 // processHallME: f <- (1/n) * sum_hom f/(f+(1-f)a)   (calc.cpp:285). flag[0] = max |delta| bits (atomicMax on the ordered int).
 __global__ void __launch_bounds__(256)

@@ -5,15 +5,16 @@
 //   * code-3 cells (first variant not in the AF list, >2 variants, missing ...; SURVEY flattener contract): they are not
 //     classified, so the locus' class frequencies leave the genome's expected sums (kga_analysis_inbreed_freq.cpp:462-543)
 //   * rows whose major allele is rare for a population (q <= 0.01): a hom-ref genome is dropped there (freq.cpp:532-539)
-// Dropped cells are indexed ONCE per uploaded matrix (k_dropped_count / k_dropped_index, part of the upload: the index is
-// the "side list" of the flattener contract in device form); every pass then visits only the indexed cells. Populations
-// with too many code-3 cells for an index fall back to k_dropped_scan, which re-reads the matrix.
+// Dropped cells are indexed ONCE per uploaded matrix (k_dropped_count / k_dropped_index + a key sort, part of the upload:
+// the index is the "side list" of the flattener contract in device form, genome-major and row-sorted); every pass then
+// visits only the indexed cells, one warp per genome, without atomics and in a fixed summation order. Populations with
+// too many code-3 cells for an index fall back to k_dropped_scan, which re-reads the matrix.
 #pragma once
 #include "common.cuh"
 
 namespace kgl {
 
-struct DroppedCell { uint32_t row, genome; };
+typedef unsigned long long DroppedKey;     // (genome << 32) | row
 
 // ---- index construction (upload time) ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -27,10 +28,10 @@ k_dropped_count(const uint4* __restrict__ packed, uint64_t n_cells128, unsigned 
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
 }
 
-// Appends one DroppedCell per code-3 cell (any order). cursor starts at 0; capacity is the count from k_dropped_count.
+// Appends one key per code-3 cell (any order; sorted afterwards). cursor starts at 0; capacity = count of k_dropped_count.
 __global__ void __launch_bounds__(256)
 k_dropped_index(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t units, unsigned long long* __restrict__ cursor,
-                DroppedCell* __restrict__ cells, uint64_t capacity) {
+                DroppedKey* __restrict__ cells, uint64_t capacity) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +60,7 @@ k_dropped_index(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t 
       while (both) {
         const int b = __ffsll((long long)both) - 1;
         both &= both - 1;
-        if (o < capacity) cells[o] = DroppedCell{row, unit * 64 + (uint32_t)b};
+        if (o < capacity) cells[o] = ((DroppedKey)(unit * 64 + (uint32_t)b) << 32) | row;
         ++o;
       }
     }
@@ -75,21 +76,60 @@ struct SparseOut {
   double* ecorr;
 };
 
-// flags16 == null: raw mode (allele_count) -- every code-3 cell counts, no frequency corrections.
+// seg[g] = first key of genome g in the sorted key array (g = 0 .. n_genomes_padded inclusive).
 __global__ void __launch_bounds__(256)
-k_dropped_apply(const DroppedCell* __restrict__ cells, uint64_t n_cells, const uint16_t* __restrict__ flags16,
-                const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cells) return;
-  const DroppedCell c = cells[i];
-  if (flags16 == nullptr) { atomicAdd(&out.n3[c.genome], 1u); return; }
-  const int k = superpop[c.genome];
-  if (!((flags16[c.row] >> k) & 1u)) return;
-  atomicAdd(&out.n3[c.genome], 1u);
-  double a, h, m;
-  class_freqs(locus_freq(af[(uint64_t)k * n_loci + c.row]).p, a, h, m);
-  atomicAdd(&out.ecorr[(uint64_t)c.genome * 2 + 0], a);
-  atomicAdd(&out.ecorr[(uint64_t)c.genome * 2 + 1], m);
+k_dropped_segments(const DroppedKey* __restrict__ keys, uint64_t n_keys, uint64_t n_genomes_padded, uint64_t* __restrict__ seg) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > n_genomes_padded) return;
+  const DroppedKey want = (DroppedKey)g << 32;
+  uint64_t lo = 0, hi = n_keys;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < want) lo = mid + 1; else hi = mid;
+  }
+  seg[g] = lo;
+}
+
+// One warp per genome over its row-sorted dropped cells. flags16 == null: raw mode (allele_count) -- every code-3 cell
+// counts, no frequency corrections. Writes n3[g]; adds the class frequencies of the selected dropped loci to ecorr[g].
+__global__ void __launch_bounds__(256)
+k_dropped_apply(const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
+                const uint16_t* __restrict__ flags16, const uint8_t* __restrict__ superpop, const float* __restrict__ af,
+                uint64_t n_loci, SparseOut out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n_genomes) return;
+  const uint64_t i0 = seg[g], i1 = seg[g + 1];
+  if (flags16 == nullptr) { if (lane == 0) out.n3[g] = (uint32_t)(i1 - i0); return; }
+  const int k = superpop[g];
+  const float* afk = af + (uint64_t)k * n_loci;
+  uint32_t n = 0;
+  double sa = 0.0, sm = 0.0;
+  // four cells per lane and trip: the key, flag and frequency gathers of a trip are independent and overlap
+  for (uint64_t i = i0 + lane; i < i1; i += 128) {
+    uint32_t row[4], fl[4];
+    float fa[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) row[j] = (i + 32 * j < i1) ? (uint32_t)keys[i + 32 * j] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fl[j] = (row[j] != 0xFFFFFFFFu) ? (uint32_t)flags16[row[j]] : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fa[j] = ((fl[j] >> k) & 1u) ? afk[row[j]] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((fl[j] >> k) & 1u) {
+        double a, h, m;
+        class_freqs(locus_freq(fa[j]).p, a, h, m);
+        ++n; sa += a; sm += m;
+      }
+    }
+  }
+  n = __reduce_add_sync(kFull, n);
+  sa = warp_sum(sa); sm = warp_sum(sm);
+  if (lane == 0) {
+    out.n3[g] = n;
+    if (n) { atomicAdd(&out.ecorr[g * 2 + 0], sa); atomicAdd(&out.ecorr[g * 2 + 1], sm); }
+  }
 }
 
 // Fallback without an index: one thread per 128-bit unit-row.
@@ -118,41 +158,37 @@ k_dropped_scan(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t u
   }
 }
 
-// Rare-major rows (flags16 high byte != 0; listed by k_locus_prepare). One warp per listed row, lane = unit (looping):
-// for every genome whose population has q <= 0.01 at this row: hom-ref -> the locus is dropped for it; else nz_rare++.
+// Rare-major rows (flags16 high byte != 0; listed by k_locus_prepare). One thread per (listed row, unit): for every genome
+// whose population has q <= 0.01 at this row: hom-ref -> the locus is dropped for it; else nz_rare++.
 __global__ void __launch_bounds__(256)
 k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare, const uint4* __restrict__ packed,
             uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16, const uint64_t* __restrict__ popmask,
             const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n = *n_rare;
-  for (uint32_t r = warp; r < n; r += n_warps) {
-    const uint32_t row = rare_rows[r];
+  const uint64_t total = (uint64_t)(*n_rare) * units;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t row = rare_rows[t / units], u = (uint32_t)(t % units);
     const uint32_t rq = (uint32_t)flags16[row] >> 8;
+    const uint4 v = packed[(uint64_t)row * units + u];
+    const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
     for (int k = 0; k < n_pop; ++k) {
       if (!((rq >> k) & 1u)) continue;
+      const uint64_t mask = popmask[(uint64_t)k * units + u];
+      if (mask == 0) continue;
       double a, h, m;
       class_freqs(locus_freq(af[(uint64_t)k * n_loci + row]).p, a, h, m);
-      for (uint32_t u = lane; u < units; u += 32) {
-        const uint64_t mask = popmask[(uint64_t)k * units + u];
-        if (mask == 0) continue;
-        const uint4 v = packed[(uint64_t)row * units + u];
-        const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-        uint64_t homref = ~(lo | hi) & mask;
-        uint64_t nonref = (lo | hi) & mask;
-        while (homref) {
-          const int b = __ffsll((long long)homref) - 1;
-          homref &= homref - 1;
-          const uint64_t g = (uint64_t)u * 64 + b;
-          atomicAdd(&out.ecorr[g * 2 + 0], a);
-          atomicAdd(&out.ecorr[g * 2 + 1], m);
-        }
-        while (nonref) {
-          const int b = __ffsll((long long)nonref) - 1;
-          nonref &= nonref - 1;
-          atomicAdd(&out.nz_rare[(uint64_t)u * 64 + b], 1u);
-        }
+      uint64_t homref = ~(lo | hi) & mask;
+      uint64_t nonref = (lo | hi) & mask;
+      while (homref) {
+        const int b = __ffsll((long long)homref) - 1;
+        homref &= homref - 1;
+        const uint64_t g = (uint64_t)u * 64 + b;
+        atomicAdd(&out.ecorr[g * 2 + 0], a);
+        atomicAdd(&out.ecorr[g * 2 + 1], m);
+      }
+      while (nonref) {
+        const int b = __ffsll((long long)nonref) - 1;
+        nonref &= nonref - 1;
+        atomicAdd(&out.nz_rare[(uint64_t)u * 64 + b], 1u);
       }
     }
   }
