@@ -79,7 +79,7 @@ struct kgl_b200_ctx {
 
   // per-locus preparation
   DevBuf<uint16_t> d_flags16, d_sum64;
-  DevBuf<uint32_t> d_selw, d_rare_rows, d_n_rare;
+  DevBuf<uint32_t> d_selw, d_rare_rows, d_n_rare;   // d_n_rare: [0] rare-row count, [1] all-selected flag
   DevBuf<double> d_block_totals, d_totals;
   bool prep_valid = false, prep_has_w0 = false;
 
@@ -99,6 +99,8 @@ struct kgl_b200_ctx {
   DevBuf<uint64_t> d_genome_counts;
   DevBuf<kgl_b200_locus_results> d_results;
   DevBuf<uint32_t> d_ibs;
+  DevBuf<unsigned int> d_ticket;
+  bool tail_done = false;            // the last launch_count already assembled the per-genome results (fused tail)
 
   // iterative estimator state
   int algo = -1, phase = 0, iteration = 0;
@@ -184,7 +186,7 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
   KGL_CUDA(c, c->d_sum64.ensure(c->padded_rows / 64));
   KGL_CUDA(c, c->d_selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
   KGL_CUDA(c, c->d_rare_rows.ensure(L));
-  KGL_CUDA(c, c->d_n_rare.ensure(1));
+  KGL_CUDA(c, c->d_n_rare.ensure(2));
   KGL_CUDA(c, c->d_block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
   KGL_CUDA(c, c->d_totals.ensure(kMaxPop * TOT_COUNT));
   KGL_CUDA(c, cudaMemsetAsync(c->d_n_rare.p, 0, 4, c->stream));
@@ -197,7 +199,8 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
                                                                c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
                                                                c->d_block_totals.p);
   KGL_LAUNCH_CHECK(c);
-  k_reduce_totals<<<kMaxPop * TOT_COUNT, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p);
+  k_reduce_totals<<<kMaxPop * TOT_COUNT + 1, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p, c->d_flags16.p, c->d_sum64.p, L,
+                                                                  (1u << c->n_pop) - 1u, c->d_n_rare.p + 1);
   KGL_LAUNCH_CHECK(c);
   c->prep_valid = true; c->prep_has_w0 = want_w0;
   return KGL_B200_OK;
@@ -277,7 +280,7 @@ int alloc_matrix(kgl_b200_ctx* c) {
 
 // The fused streaming pass + its sparse companions. raw: allele_count over all loci; otherwise over the selected loci.
 // Leaves d_gcounts {lo, hi}, d_n3, d_nz_rare, d_ecorr per genome and the per-locus counts.
-int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome) {
+int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false) {
   int rc = build_unit_tables(c);
   if (rc) return rc;
   rc = build_dropped_index(c);
@@ -330,29 +333,32 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     k_fix_locus_n0<<<blocks_for(c->L, 256), 256, 0, c->stream>>>(c->d_locus_counts.p, c->L, (uint32_t)c->N);
     KGL_LAUNCH_CHECK(c);
   }
+  c->tail_done = false;
   if (want_genome) {
-    dim3 eg(blocks_for(c->Npad, 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
-    k_expand_planes<<<eg, 256, 0, c->stream>>>(c->d_planes.p, pl.n_vchunks, c->units, c->Npad, c->d_gcounts);
-    KGL_LAUNCH_CHECK(c);
     const SparseOut so{c->d_n3, c->d_nz_rare, c->d_ecorr};
     const uint16_t* fl = raw ? nullptr : c->d_flags16.p;
-    if (c->n_dropped > 0) {
+    {
+      dim3 eg(blocks_for(c->Npad, 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
+      k_expand_planes<<<eg, 256, 0, c->stream>>>(c->d_planes.p, pl.n_vchunks, c->units, c->Npad, c->d_gcounts);
+      KGL_LAUNCH_CHECK(c);
       if (c->dropped_indexed) {
-        k_dropped_apply<<<blocks_for(c->N * 32, 256), 256, 0, c->stream>>>(c->d_dropped.p, c->d_dropped_seg.p, c->N, fl, c->d_superpop.p,
+        k_dropped_apply<<<(unsigned)((c->N + 1) / 2), 256, 0, c->stream>>>(c->d_dropped.p, c->d_dropped_seg.p, c->N, fl,
+                                                                            raw ? nullptr : c->d_n_rare.p + 1, c->d_superpop.p,
                                                                             c->d_af.p, c->L, so);
-      } else {
+        KGL_LAUNCH_CHECK(c);
+      } else if (c->n_dropped > 0) {
         const uint64_t n128 = c->L * c->units;
         const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
         k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
                                                      c->d_superpop.p, c->d_af.p, c->L, so);
+        KGL_LAUNCH_CHECK(c);
       }
-      KGL_LAUNCH_CHECK(c);
-    }
-    if (!raw) {
-      k_rare_rows<<<c->sm_count, 256, 0, c->stream>>>(c->d_rare_rows.p, c->d_n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
-                                                       (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
-                                                       c->L, (int)c->n_pop, so);
-      KGL_LAUNCH_CHECK(c);
+      if (!raw) {
+        k_rare_rows<<<32, 256, 0, c->stream>>>(c->d_rare_rows.p, c->d_n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
+                                                             (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
+                                                             c->L, (int)c->n_pop, so);
+        KGL_LAUNCH_CHECK(c);
+      }
     }
   }
   return KGL_B200_OK;
@@ -362,8 +368,9 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
 int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false) {
   int rc = ensure_prepared(c, want_w0);
   if (rc) return rc;
-  rc = launch_count(c, false, want_locus_counts, true);
+  rc = launch_count(c, false, want_locus_counts, true, simple_results);
   if (rc) return rc;
+  if (c->tail_done) return KGL_B200_OK;
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
   k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->d_totals.p, c->d_ecorr, c->d_nz_rare,
                                                                   c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p,
@@ -461,7 +468,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release(); c->d_sum64.release(); c->d_rare_rows.release(); c->d_n_rare.release();
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
-  c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
+  c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
   for (cudaEvent_t e : c->timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -679,7 +686,7 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t*
     KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
   if (genome_counts) {
     KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 4));
-    k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->L, c->d_genome_counts.p);
+    if (!c->tail_done) k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->L, c->d_genome_counts.p);
     KGL_LAUNCH_CHECK(c);
     KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_genome_counts.p, (size_t)c->N * 32, cudaMemcpyDeviceToHost, c->stream));
   }

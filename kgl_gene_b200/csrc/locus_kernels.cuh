@@ -53,6 +53,15 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
 #pragma unroll
     for (int j = 0; j < TOT_COUNT; ++j) acc[j] = 0.0;
     uint32_t n_t = 0, n_tq = 0;
+    // all of this population's frequencies first: eight independent loads in flight instead of eight load->use chains
+    float afv[kPrepIters][2];
+#pragma unroll
+    for (int it = 0; it < kPrepIters; ++it)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
+        afv[it][half] = (k < n_pop && l < n_loci) ? __ldg(&af[(uint64_t)k * n_loci + l]) : 0.0f;
+      }
 #pragma unroll
     for (int it = 0; it < kPrepIters; ++it)
 #pragma unroll
@@ -60,7 +69,7 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
         const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
         bool on = false;
         if (k < n_pop && ((sbits[it][half] >> k) & 1u)) {
-          const LocusFreq f = locus_freq(af[(uint64_t)k * n_loci + l]);
+          const LocusFreq f = locus_freq(afv[it][half]);
           if (f.valid) {
             on = true;
             fl[it][half] |= 1u << k;
@@ -108,10 +117,23 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
   }
 }
 
-// Fixed-order reduction of the block totals: totals[item], one block per item, deterministic.
+// Fixed-order reduction of the block totals: totals[item], one block per item, deterministic. One extra block
+// (blockIdx.x == kMaxPop * TOT_COUNT) reduces the 64-row summaries: all_selected[0] = 1 iff every row < n_loci is selected
+// and valid for every population (then the sparse kernels need not look at the flags).
 __global__ void __launch_bounds__(256)
-k_reduce_totals(const double* __restrict__ block_totals, uint64_t n_blocks, double* __restrict__ totals) {
+k_reduce_totals(const double* __restrict__ block_totals, uint64_t n_blocks, double* __restrict__ totals,
+                const uint16_t* __restrict__ flags16, const uint16_t* __restrict__ sum64, uint64_t n_loci, uint32_t all_pops,
+                uint32_t* __restrict__ all_selected) {
   __shared__ double s[256];
+  if (blockIdx.x == kMaxPop * TOT_COUNT) {
+    uint32_t a = all_pops;
+    const uint64_t full_groups = n_loci / 64;                                // the last, partial group is checked row by row
+    for (uint64_t i = threadIdx.x; i < full_groups; i += 256) a &= sum64[i];
+    for (uint64_t l = full_groups * 64 + threadIdx.x; l < n_loci; l += 256) a &= flags16[l];
+    const int ok = __syncthreads_and((a & all_pops) == all_pops);
+    if (threadIdx.x == 0) all_selected[0] = ok ? 1u : 0u;
+    return;
+  }
   const int item = blockIdx.x;
   double v = 0.0;
   for (uint64_t b = threadIdx.x; b < n_blocks; b += 256) v += block_totals[b * kMaxPop * TOT_COUNT + item];

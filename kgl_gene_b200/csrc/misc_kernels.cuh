@@ -84,27 +84,24 @@ k_finalize_closed_form(const double* __restrict__ partials, uint64_t n_genomes, 
 }
 
 // Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
-__global__ void __launch_bounds__(256)
-k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set hi bits} over the selected rows */,
-                  const uint32_t* __restrict__ n3s, const double* __restrict__ totals, const double* __restrict__ ecorr,
-                  const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
-                  int unphased, double* __restrict__ partials,
-                  kgl_b200_locus_results* __restrict__ simple_out /* nullable: also apply processSimple (calc.cpp:333-359) */) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_genomes) return;
+__device__ __forceinline__ void moment_partials_one(uint64_t g, const uint32_t* gcounts, const uint32_t* n3s, const double* totals,
+                                                    const double* ecorr, const uint32_t* nz_rare, const uint8_t* superpop, int unphased,
+                                                    double* partials, kgl_b200_locus_results* simple_out) {
   const int k = superpop[g];
   const double* T = totals + k * TOT_COUNT;
-  const double n3 = n3s[g], n1 = (double)gcounts[g * 2 + 0] - n3, n2 = (double)gcounts[g * 2 + 1] - n3;
+  // __ldcg: in the fused tail kernel these were written by other blocks of the same grid
+  const double n3 = __ldcg(&n3s[g]), n1 = (double)__ldcg(&gcounts[g * 2 + 0]) - n3, n2 = (double)__ldcg(&gcounts[g * 2 + 1]) - n3;
+  const double nzr = (double)__ldcg(&nz_rare[g]);
   // hom-ref cells in q > 0.01 rows: all such rows minus the non-reference cells that sit in them
-  const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - (double)nz_rare[g]);
+  const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - nzr);
   double* P = partials + g * PART_COUNT;
   P[PART_NMAJHOM] = n_majhom;
   P[PART_NMAJHET] = n1;
   P[PART_NMINHOM] = unphased ? 0.0 : n2;
   P[PART_NMINHET] = unphased ? n2 : 0.0;
-  const double d_majhom = ecorr[g * 2 + 0], d_minhom = ecorr[g * 2 + 1];
+  const double d_majhom = __ldcg(&ecorr[g * 2 + 0]), d_minhom = __ldcg(&ecorr[g * 2 + 1]);
   // dropped cells: code 3 in selected rows (n3) and hom-ref cells of rare-q rows; their class frequencies leave the sums.
-  const double n_dropped = (T[TOT_T] - T[TOT_TQ]) - (double)nz_rare[g] + n3;   // rare-q rows that are hom-ref + code-3 cells
+  const double n_dropped = (T[TOT_T] - T[TOT_TQ]) - nzr + n3;
   P[PART_EMAJHOM] = T[TOT_EMAJHOM] - d_majhom;
   P[PART_EMINHOM] = T[TOT_EMINHOM] - d_minhom;
   // the three normalised class frequencies of a locus sum to 1, so the dropped majHet mass is n_dropped - majHom - minHom
@@ -114,6 +111,16 @@ k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set h
   if (simple_out) simple_out[g] = closed_form(P, KGL_B200_ALGO_SIMPLE);
 }
 
+__global__ void __launch_bounds__(256)
+k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set hi bits} over the selected rows */,
+                  const uint32_t* __restrict__ n3s, const double* __restrict__ totals, const double* __restrict__ ecorr,
+                  const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
+                  int unphased, double* __restrict__ partials,
+                  kgl_b200_locus_results* __restrict__ simple_out /* nullable: also apply processSimple (calc.cpp:333-359) */) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  moment_partials_one(g, gcounts, n3s, totals, ecorr, nz_rare, superpop, unphased, partials, simple_out);
+}
 
 // processHallME: f <- (1/n) * sum_hom f/(f+(1-f)a)   (calc.cpp:285). flag[0] = max |delta| bits (atomicMax on the ordered int).
 __global__ void __launch_bounds__(256)

@@ -120,7 +120,7 @@ __host__ __device__ inline size_t stream_smem_bytes(uint32_t slice_units, uint32
 }
 
 // Expand the bit-sliced counters: gcounts[g] = {set lo bits, set hi bits} summed over the virtual chunks.
-constexpr int kExpandGroup = 8;
+constexpr int kExpandGroup = 4;
 __global__ void __launch_bounds__(256)
 k_expand_planes(const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units, uint64_t n_genomes_padded,
                 uint32_t* __restrict__ gcounts /* [n_genomes_padded][2], zeroed */) {
@@ -132,7 +132,10 @@ k_expand_planes(const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_
   const uint64_t vc1 = min(vc0 + (uint64_t)kExpandGroup, n_vchunks);
   const uint64_t W = units * 4;
   uint32_t acc[2] = {0, 0};
-  for (uint64_t vc = vc0; vc < vc1; ++vc) {
+#pragma unroll
+  for (int q = 0; q < kExpandGroup; ++q) {
+    const uint64_t vc = vc0 + q;
+    if (vc >= vc1) break;
     const uint32_t* base = planes + vc * kScLevels * W + unit * 4 + h;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {

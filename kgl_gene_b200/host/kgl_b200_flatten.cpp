@@ -1,0 +1,167 @@
+// kgl_b200_flatten.cpp -- see kgl_b200_flatten.h.
+#include "kgl_b200_flatten.h"
+
+#include "kel_exec_env.h"
+#include "kgl_variant_db_freq.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <limits>
+#include <thread>
+
+namespace kgl = kellerberrin::genome;
+namespace b200 = kellerberrin::genome::b200;
+using kellerberrin::ExecEnv;
+
+const char* const b200::kSuperPopCodes[b200::kSuperPopCount] = {
+    kgl::FrequencyDatabaseRead::SUPER_POP_AFR_, kgl::FrequencyDatabaseRead::SUPER_POP_AMR_, kgl::FrequencyDatabaseRead::SUPER_POP_EAS_,
+    kgl::FrequencyDatabaseRead::SUPER_POP_EUR_, kgl::FrequencyDatabaseRead::SUPER_POP_SAS_, kgl::FrequencyDatabaseRead::SUPER_POP_ALL_};
+
+std::optional<uint8_t> b200::superPopIndex(const std::string& code) {
+  for (size_t k = 0; k < kSuperPopCount; ++k)
+    if (code == kSuperPopCodes[k]) return static_cast<uint8_t>(k);
+  return std::nullopt;
+}
+
+namespace {
+
+// Variant::analogous (kgl_variant_db.h:143) is equality of the HGVS string "{contig}:g.{offset}{ref}>{alt}"
+// (kgl_variant_db.cpp:287-290); the same test on the fields, without building two strings per call.
+bool analogous(const kgl::Variant& a, const kgl::Variant& b) {
+  return a.offset() == b.offset() && a.contigId() == b.contigId() &&
+         a.reference().getStringView() == b.reference().getStringView() &&
+         a.alternate().getStringView() == b.alternate().getStringView();
+}
+
+}  // namespace
+
+std::optional<b200::FlatContig> b200::PopulationFlattener::flatten(const PopulationDB& diploid_population,
+                                                                    const PopulationDB& af_population,
+                                                                    const SuperPopLookup& super_population,
+                                                                    bool unphased_population,
+                                                                    size_t threads) {
+  // Same preconditions as InbreedingAnalysis::populationInbreeding (kga_analysis_inbreed_diploid.cpp:26-41).
+  if (af_population.getMap().size() != 1) {
+    ExecEnv::log().error("PopulationFlattener::flatten; allele frequency population: {} has unexpected genome count: {}",
+                         af_population.populationId(), af_population.getMap().size());
+    return std::nullopt;
+  }
+  auto const& [af_genome_id, af_genome_ptr] = *af_population.getMap().begin();
+  if (af_genome_ptr->getMap().size() != 1) {
+    ExecEnv::log().error("PopulationFlattener::flatten; allele frequency genome: {} has more than 1 contig: {}", af_genome_id,
+                         af_genome_ptr->getMap().size());
+    return std::nullopt;
+  }
+  auto const& [contig_id, af_contig_ptr] = *af_genome_ptr->getMap().begin();
+
+  FlatContig flat;
+  flat.contig_id = contig_id;
+  flat.unphased = unphased_population;
+
+  // ---- locus table: one row per AF offset with exactly one distinct alt allele -----------------------------------------
+  std::vector<std::shared_ptr<const Variant>> locus_allele;
+  std::vector<std::array<float, kSuperPopCount>> locus_af;
+  for (auto const& [offset, offset_ptr] : af_contig_ptr->getMap()) {
+    const OffsetDBArray& variants = offset_ptr->getVariantArray();
+    if (variants.empty()) continue;
+    bool multi = false;
+    for (auto const& v : variants)
+      if (!analogous(*v, *variants.front())) { multi = true; break; }
+    if (multi) { ++flat.multi_allelic_skipped; continue; }
+    if (offset > std::numeric_limits<uint32_t>::max()) {
+      ExecEnv::log().error("PopulationFlattener::flatten; offset {} does not fit 32 bits", offset);
+      return std::nullopt;
+    }
+    std::array<float, kSuperPopCount> row{};
+    for (size_t k = 0; k < kSuperPopCount; ++k) {
+      row[k] = std::numeric_limits<float>::quiet_NaN();
+      // AlleleFreqVector keeps the first analogous variant that HAS a value for the super-population (freq.cpp:24-52).
+      for (auto const& v : variants) {
+        auto af_opt = FrequencyDatabaseRead::superPopFrequency(*v, kSuperPopCodes[k]);
+        if (af_opt) { row[k] = static_cast<float>(af_opt.value()); break; }   // stored as float by the parser: exact
+      }
+    }
+    flat.offsets.push_back(static_cast<uint32_t>(offset));
+    locus_allele.push_back(variants.front());
+    locus_af.push_back(row);
+  }
+  const size_t L = flat.offsets.size();
+  flat.af.resize(kSuperPopCount * L);
+  for (size_t l = 0; l < L; ++l)
+    for (size_t k = 0; k < kSuperPopCount; ++k) flat.af[k * L + l] = locus_af[l][k];
+  if (flat.multi_allelic_skipped > 0)
+    ExecEnv::log().warn("PopulationFlattener::flatten; contig: {}, {} multi-allelic offsets left out of the locus table", contig_id,
+                        flat.multi_allelic_skipped);
+
+  // ---- genome columns: genomes that have the contig, a PED record and a known super-population (diploid.cpp:121-140) -----
+  std::vector<std::shared_ptr<const ContigDB>> genome_contig;
+  for (auto const& [genome_id, genome_ptr] : diploid_population.getMap()) {
+    auto contig_opt = std::const_pointer_cast<const GenomeDB>(genome_ptr)->getContig(contig_id);
+    if (!contig_opt) continue;
+    auto code_opt = super_population(genome_id);
+    if (!code_opt) {
+      ExecEnv::log().error("PopulationFlattener::flatten; genome sample: {} does not have a PED record", genome_id);
+      continue;
+    }
+    auto index_opt = superPopIndex(code_opt.value());
+    if (!index_opt) {
+      ExecEnv::log().error("PopulationFlattener::flatten; locus set not found for super population: {}", code_opt.value());
+      continue;
+    }
+    flat.genome_ids.push_back(genome_id);
+    flat.superpop.push_back(index_opt.value());
+    genome_contig.push_back(contig_opt.value());
+  }
+  const size_t N = flat.genome_ids.size();
+  const size_t units = (N + 63) / 64;
+  flat.row_bytes = 16 * units;
+  flat.packed.assign(L * flat.row_bytes, 0);
+  if (N == 0 || L == 0) return flat;
+
+  // ---- genotype codes. A thread owns whole 64-genome units, so no two threads touch the same byte. -----------------------
+  if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+  threads = std::min(threads, units);
+  std::atomic<size_t> mixed_phase{0};
+  auto worker = [&](size_t t) {
+    size_t mixed = 0;
+    std::vector<const Variant*> snps;
+    for (size_t u = t; u < units; u += threads) {
+      for (size_t b = 0; b < 64 && u * 64 + b < N; ++b) {
+        const size_t g = u * 64 + b;
+        for (auto const& [offset, offset_ptr] : genome_contig[g]->getMap()) {
+          if (offset > std::numeric_limits<uint32_t>::max()) break;
+          auto it = std::lower_bound(flat.offsets.begin(), flat.offsets.end(), static_cast<uint32_t>(offset));
+          if (it == flat.offsets.end() || *it != offset) continue;          // not a locus of the AF list
+          const size_t l = static_cast<size_t>(it - flat.offsets.begin());
+          snps.clear();
+          for (auto const& v : offset_ptr->getVariantArray())
+            if (v->isSNP()) snps.push_back(v.get());                        // the genome side is SNP filtered (freq.cpp:436)
+          if (snps.empty()) continue;
+          unsigned code = 3;
+          const Variant& allele = *locus_allele[l];
+          if (analogous(*snps.front(), allele)) {
+            if (snps.size() == 1) code = 1;
+            else if (snps.size() == 2 && analogous(*snps.back(), allele)) {
+              const bool phased_pair = snps.front()->phaseId() != snps.back()->phaseId();   // Variant::homozygous
+              if (phased_pair == !unphased_population) code = 2; else ++mixed;
+            }
+          }
+          uint8_t* unit = flat.packed.data() + l * flat.row_bytes + u * 16;
+          if (code & 1u) unit[b >> 3] |= static_cast<uint8_t>(1u << (b & 7));
+          if (code & 2u) unit[8 + (b >> 3)] |= static_cast<uint8_t>(1u << (b & 7));
+        }
+      }
+    }
+    mixed_phase += mixed;
+  };
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  flat.mixed_phase_cells = mixed_phase;
+  if (flat.mixed_phase_cells > 0)
+    ExecEnv::log().warn("PopulationFlattener::flatten; contig: {}, {} allele pairs contradict the population's phasing and were dropped",
+                        contig_id, flat.mixed_phase_cells);
+  return flat;
+}

@@ -1,0 +1,73 @@
+// kgl_b200_flatten.h -- host side of the drop-in: flattens KGL_Gene's variant database into the arrays the C ABI
+// (include/kgl_b200.h) takes. Compiled against the KGL_Gene headers (C++23); see INTEGRATION.md.
+//
+// Input:  the diploid population (population -> genome -> contig -> offset -> variants; only NON-reference alleles are
+//         stored, kgl_variant_db_population.h:33) and the allele-frequency "genome" (1 genome, 1 contig, SNP and PASS
+//         filtered, kga_analysis_inbreed.cpp:67-81).
+// Output: one FlatContig per analysed contig: locus table (offset + the INFO AF float per super-population), the 2-bit
+//         loci-major genotype matrix and the super-population index of every genome column.
+//
+// The genotype code of (genome, locus) restates the classification in InbreedingCalculation::generateFrequencies
+// (kga_analysis_inbreed_freq.cpp:452-543) for a locus with ONE alt allele in the AF list:
+//   no SNP variant at the offset                                   -> 0   (MAJOR_HOMOZYGOUS if q > 0.01, decided on the device)
+//   1 variant, analogous to the AF allele                          -> 1   (MAJOR_HETEROZYGOUS, :464-472)
+//   2 variants, first analogous, front->homozygous(back)           -> 2   (MINOR_HOMOZYGOUS, :476-479)
+//   2 variants, both analogous, same phase (unphased populations)  -> 2 with FlatContig::unphased set: the reference
+//                                                                     classifies these MINOR_HETEROZYGOUS
+//   anything else (first variant not in the AF list, second not found, more than 2 variants) -> 3 (dropped)
+// Offsets whose AF entry lists more than one distinct alt allele are not representable with one frequency per locus;
+// they are left out of the locus table and counted in FlatContig::multi_allelic_skipped.
+#ifndef KGL_B200_FLATTEN_H
+#define KGL_B200_FLATTEN_H
+
+#include "kgl_variant_db_population.h"
+
+#include <cstdint>
+#include <functional>
+#include <optional>
+#include <string>
+#include <vector>
+
+namespace kellerberrin::genome::b200 {
+
+constexpr size_t kSuperPopCount = 6;                       // AFR, AMR, EAS, EUR, SAS, ALL (kgl_variant_db_freq.h:55-60)
+extern const char* const kSuperPopCodes[kSuperPopCount];
+// Index of a PED super-population code, or nullopt (the reference skips such genomes with an error, diploid.cpp:136).
+std::optional<uint8_t> superPopIndex(const std::string& code);
+
+struct FlatContig {
+  ContigId_t contig_id;
+  std::vector<GenomeId_t> genome_ids;                      // column order (std::map order of the population = reference row order)
+  std::vector<uint8_t> superpop;                           // [n_genomes]
+  std::vector<uint32_t> offsets;                           // [n_loci], strictly increasing
+  std::vector<float> af;                                   // [kSuperPopCount][n_loci], NaN = no value for that super-population
+  std::vector<uint8_t> packed;                             // [n_loci][row_bytes]
+  uint64_t row_bytes{0};
+  bool unphased{false};
+  size_t multi_allelic_skipped{0};
+  size_t mixed_phase_cells{0};                             // cells whose phase pattern contradicts `unphased` (coded 3)
+
+  [[nodiscard]] uint64_t nGenomes() const { return genome_ids.size(); }
+  [[nodiscard]] uint64_t nLoci() const { return offsets.size(); }
+};
+
+// genome id -> PED super-population code; nullopt = no PED record (genome is left out, as the reference does).
+using SuperPopLookup = std::function<std::optional<std::string>(const GenomeId_t&)>;
+
+class PopulationFlattener {
+
+public:
+
+  // af_population: 1 genome, 1 contig (checked; kga_analysis_inbreed_diploid.cpp:26,36). threads = 0: hardware_concurrency.
+  // unphased_population: the diploid data is DataStructureEnum::DiploidUnphased (all variants share one phase, Pf7).
+  static std::optional<FlatContig> flatten(const PopulationDB& diploid_population,
+                                           const PopulationDB& af_population,
+                                           const SuperPopLookup& super_population,
+                                           bool unphased_population,
+                                           size_t threads = 0);
+
+};
+
+}  // namespace kellerberrin::genome::b200
+
+#endif  // KGL_B200_FLATTEN_H

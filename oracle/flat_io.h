@@ -79,6 +79,19 @@ inline Flat readFlat(const std::string& path) {
   return fl;
 }
 
+inline void writeFlat(const std::string& path, const Flat& fl) {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) throw std::runtime_error("cannot write " + path);
+  Header h = fl.hdr;
+  std::memcpy(h.magic, "KGLFLAT1", 8);
+  std::fwrite(&h, sizeof(Header), 1, f);
+  std::fwrite(fl.offsets.data(), 4, fl.offsets.size(), f);
+  std::fwrite(fl.af.data(), 4, fl.af.size(), f);
+  std::fwrite(fl.superpop.data(), 1, fl.superpop.size(), f);
+  std::fwrite(fl.packed.data(), 1, fl.packed.size(), f);
+  std::fclose(f);
+}
+
 class TensorWriter {
  public:
   void add(const std::string& name, const char* dtype, std::vector<size_t> shape, const void* data, size_t bytes) {

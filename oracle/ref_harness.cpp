@@ -27,6 +27,7 @@
 #include "kga_analysis_inbreed_locus.h"
 
 #include "flat_io.h"
+#include "ref_population.h"
 
 #include <chrono>
 #include <cstdio>
@@ -66,16 +67,8 @@ struct Options {
 };
 Options g_opt;
 
-const char* const kSuperPops[6] = {"AFR", "AMR", "EAS", "EUR", "SAS", "ALL"};
-// INFO field names the reference resolves for DataSourceEnum::Genome1000 (kgl_variant_db_freq.h:87-92).
-const char* const kAfFields[6] = {"AFR_AF", "AMR_AF", "EAS_AF", "EUR_AF", "SAS_AF", "AF"};
-const std::string kContig = "chrFlat";
-
-std::string genomeName(uint32_t g) {
-  char buf[32];
-  std::snprintf(buf, sizeof buf, "G%07u", g);  // zero padded: lexicographic == numeric (std::map order)
-  return buf;
-}
+using kglref::kSuperPops;
+using kglref::kContig;
 
 struct GenomeOut {
   kga::LocusResults results;
@@ -90,68 +83,12 @@ void run() {
   const bool unphased = (flat.hdr.flags & kglflat::FLAG_UNPHASED) != 0;
   kglflat::TensorWriter out;
 
-  // ---- INFO evidence: six Float AF fields, Number=A ----------------------------------------------
-  kgl::EvidenceInfoSet info_set;
-  kgl::VCFInfoRecordMap info_map;
-  for (auto* field : kAfFields) {
-    info_set.insert(field);
-    info_map[field] = kgl::VCFInfoRecord{field, "", "Float", "A", "", ""};
-  }
-  kgl::EvidenceFactory evidence_factory(info_set);
-  evidence_factory.availableInfoFields(info_map);
-
-  // ---- AF "genome": 1 genome, 1 contig (kga_analysis_inbreed_diploid.cpp:26,36) --------------------
-  auto af_population = std::make_shared<kgl::PopulationDB>("AF_POPULATION", kgl::DataSourceEnum::Genome1000);
-  const std::vector<kgl::GenomeId_t> af_genome{"AF_GENOME"};
-  for (uint32_t l = 0; l < L; ++l) {
-    std::string info;
-    for (int k = 0; k < 6; ++k) {
-      const float af = flat.afAt(k, l);
-      if (std::isnan(af)) continue;  // field absent for this variant -> superPopFrequency() == nullopt
-      char buf[64];
-      std::snprintf(buf, sizeof buf, "%s%s=%.9g", info.empty() ? "" : ";", kAfFields[k], double(af));
-      info += buf;
-    }
-    auto block = evidence_factory.createVariantEvidence(std::move(info));
-    kgl::VariantEvidence evidence(l, kgl::DataSourceEnum::Genome1000, true, block, nullptr, 0, 1);
-    auto variant = std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], kgl::VariantPhase::UNPHASED, "",
-                                                        kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
-                                                        kgl::DNA5SequenceLinear(kgl::StringDNA5("G")), evidence);
-    if (!af_population->addVariant(variant, af_genome)) kel::ExecEnv::log().error("harness: AF addVariant failed at locus {}", l);
-  }
-
-  // ---- diploid population: only non-reference alleles are stored ---------------------
-  auto diploid = std::make_shared<kgl::PopulationDB>("DIPLOID", kgl::DataSourceEnum::Genome1000);
-  std::vector<kgl::GenomeId_t> genome_ids(N);
-  for (uint32_t g = 0; g < N; ++g) genome_ids[g] = genomeName(g);
-  std::vector<std::shared_ptr<const kgl::Variant>> locus_variant(L);  // phase-A copy, used for summaryByVariant
-  {
-    const kgl::VariantEvidence no_evidence(0, kgl::DataSourceEnum::Genome1000, true, nullptr, nullptr, 0, 1);
-    auto make = [&](uint32_t l, kgl::VariantPhase phase, const char* alt) {
-      return std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], phase, "",
-                                                  kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
-                                                  kgl::DNA5SequenceLinear(kgl::StringDNA5(alt)), no_evidence);
-    };
-    std::vector<kgl::GenomeId_t> first, second, other;
-    for (uint32_t l = 0; l < L; ++l) {
-      first.clear(); second.clear(); other.clear();
-      for (uint32_t g = 0; g < N; ++g) {
-        switch (flat.code(l, g)) {
-          case 1: first.push_back(genome_ids[g]); break;
-          case 2: first.push_back(genome_ids[g]); second.push_back(genome_ids[g]); break;
-          case 3: other.push_back(genome_ids[g]); break;  // an allele that is not in the AF list -> dropped (freq.cpp:462)
-          default: break;
-        }
-      }
-      const auto phase_a = unphased ? kgl::VariantPhase::UNPHASED : kgl::VariantPhase::DIPLOID_PHASE_A;
-      const auto phase_b = unphased ? kgl::VariantPhase::UNPHASED : kgl::VariantPhase::DIPLOID_PHASE_B;
-      auto va = make(l, phase_a, "G");
-      locus_variant[l] = va;
-      if (!first.empty() && !diploid->addVariant(va, first)) kel::ExecEnv::log().error("harness: addVariant A failed");
-      if (!second.empty() && !diploid->addVariant(make(l, phase_b, "G"), second)) kel::ExecEnv::log().error("harness: addVariant B failed");
-      if (!other.empty() && !diploid->addVariant(make(l, phase_a, "T"), other)) kel::ExecEnv::log().error("harness: addVariant X failed");
-    }
-  }
+  // ---- the populations, through the reference's own containers (ref_population.h) ---------------------
+  kglref::BuiltPopulations built = kglref::buildPopulations(flat, kgl::DataSourceEnum::Genome1000, kgl::DataSourceEnum::Genome1000);
+  auto& af_population = built.af_population;
+  auto& diploid = built.diploid;
+  auto& genome_ids = built.genome_ids;
+  auto& locus_variant = built.locus_variant;
   std::vector<uint32_t> present(N, 0);
   for (uint32_t g = 0; g < N; ++g) present[g] = diploid->getMap().contains(genome_ids[g]) ? 1 : 0;
   out.addU32("genome_present", {N}, present);

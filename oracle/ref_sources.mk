@@ -14,6 +14,20 @@ REF_TUS := \
   kgl_genomics/kgl_parser/kgl_variant_factory_vcf_parse_info.cpp kgl_genomics/kgl_parser/kgl_data_file_type.cpp \
   kgl_app/kgl_runtime.cpp kgl_app/kgl_runtime_resource.cpp
 
+# Additional reference TUs for the plugin harness (the whole INBREED analysis, its PED resource and CSV writer).
+PLUGIN_TUS := \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed.cpp \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed_diploid.cpp \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed_execute.cpp \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed_output.cpp \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed_args.cpp \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed_synthetic.cpp \
+  kga_analytic/kga_inbreed/kga_analysis_inbreed_syngen.cpp \
+  kgl_genomics/kgl_parser/kgl_hsgenealogy_parser.cpp \
+  kgl_genomics/kgl_parser/kgl_hsgenome_aux.cpp \
+  kgl_genomics/kgl_parser/kgl_square_parser.cpp \
+  kel_io/kel_mt_buffer.cpp kel_io/kel_basic_io.cpp
+
 REF_INCLUDES := contrib/edlib kel_utility kel_thread kel_io kgl_genomics kel_app kel_math kgl_app \
   kgl_genomics/kgl_parser kgl_genomics/kgl_evidence kgl_genomics/kgl_sequence kgl_genomics/kgl_database \
   kgl_genomics/kgl_classification kgl_genomics/kgl_genome kgl_genomics/kgl_genome_io kgl_genomics/kgl_variant_db \

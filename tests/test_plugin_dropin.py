@@ -1,0 +1,94 @@
+"""Drop-in tests through the reference's own plugin interface (oracle/_ref/kgl_plugin_harness).
+
+The harness links the UNMODIFIED reference INBREED analysis (kga::InbreedAnalysis and everything under it) and the
+product's host layer (kgl_gene_b200/host: PopulationFlattener + kga::InbreedB200Analysis over libkgl_b200.so) into one
+program, builds the populations through the reference's containers, and drives both analyses through
+VirtualAnalysis::{initialize,fileRead,iteration,finalize}Analysis. Each writes its CSV with the reference's CSV writer.
+
+CPU part: the flattener must reproduce, bit for bit, the flat population the reference containers were built from.
+GPU part: the two CSV files must agree (same header, same window columns, same genomes; coefficients to the 6
+significant digits the reference prints).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "kgl_plugin_harness")
+needs_harness = pytest.mark.skipif(not os.path.exists(HARNESS), reason="oracle/_ref/kgl_plugin_harness not built (make -C oracle plugin)")
+
+
+def run_harness(tmp_path, pop, *extra):
+    src = os.path.join(tmp_path, "in.flat")
+    work = os.path.join(tmp_path, "work")
+    pop.write(src)
+    env = dict(os.environ, KGL_REF_LOG=os.path.join(tmp_path, "harness.log"))
+    r = subprocess.run([HARNESS, src, work, *extra], capture_output=True, text=True, timeout=1200, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return work
+
+
+def read_csv(path):
+    with open(path) as f:
+        lines = [ln.rstrip("\n") for ln in f]
+    header, columns = lines[0], lines[1].split(",")
+    rows = {}
+    for ln in lines[2:]:
+        p = ln.split(",")
+        rows[p[0]] = (p[1:9], [float(x) for x in p[9:] if x != ""])
+    return header, columns, rows
+
+
+@needs_harness
+@pytest.mark.parametrize("unphased", [False, True])
+def test_flattener_reproduces_the_flat_population(tmp_path, unphased):
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(131, 1500, seed=17, spectrum="sfs", missing_rate=0.02, unphased=unphased, missing_af_rate=0.05)
+    work = run_harness(str(tmp_path), pop, "--no-reference", "--no-b200")
+    got = FlatPopulation.read(os.path.join(work, "flattened.flat"))
+    # genomes without any non-reference allele never enter a PopulationDB: compare the columns that exist
+    ids = [ln.strip() for ln in open(os.path.join(work, "flattened_genomes.txt"))]
+    cols = np.array([int(i[1:]) for i in ids])
+    # loci whose AF genome has no variant... every locus has one here; a locus with NaN AF for all pops still has a variant
+    assert np.array_equal(got.offsets, pop.offsets)
+    assert np.array_equal(got.af.view(np.uint32), pop.af.view(np.uint32))
+    assert np.array_equal(got.superpop, pop.superpop[cols])
+    assert got.unphased == unphased
+    assert np.array_equal(got.codes(), pop.codes()[:, cols])
+
+
+@needs_harness
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,rtol,atol", [("Simple", 2e-6, 1e-9), ("RitlandLocus", 2e-6, 1e-9),
+                                            # the reference's optimiser stops at xtol_abs = 1e-6 (kga_analysis_inbreed_calc.cpp:131-143)
+                                            ("Loglikelihood", 2e-6, 5e-6)])
+def test_plugin_csv_matches_reference_plugin(tmp_path, algo, rtol, atol):
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(96, 4000, seed=23, spectrum="dense", missing_rate=0.01, grouped=False)
+    work = run_harness(str(tmp_path), pop, "--algo", algo, "--spacing", "20", "--count", "600")
+    h_ref, c_ref, r_ref = read_csv(os.path.join(work, "INBREED", "harness_out.csv"))
+    h_new, c_new, r_new = read_csv(os.path.join(work, "INBREED_B200", "harness_out.csv"))
+    assert h_ref == h_new                      # parameter header line
+    assert c_ref == c_new and len(c_ref) > 9 + 2   # same window columns, several windows
+    assert sorted(r_ref) == sorted(r_new)      # same genomes
+    for g, (meta, vals) in r_ref.items():
+        meta2, vals2 = r_new[g]
+        assert meta == meta2 and len(vals) == len(vals2)
+        assert np.allclose(vals2, vals, rtol=rtol, atol=atol), (g, vals, vals2)
+
+
+@needs_harness
+@pytest.mark.gpu
+def test_plugin_unphased_population(tmp_path):
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(64, 3000, seed=29, spectrum="dense", missing_rate=0.0, unphased=True)
+    work = run_harness(str(tmp_path), pop, "--algo", "Simple", "--spacing", "0", "--count", "1000")
+    _, c_ref, r_ref = read_csv(os.path.join(work, "INBREED", "harness_out.csv"))
+    _, c_new, r_new = read_csv(os.path.join(work, "INBREED_B200", "harness_out.csv"))
+    assert c_ref == c_new and sorted(r_ref) == sorted(r_new)
+    for g, (_, vals) in r_ref.items():
+        assert np.allclose(vals, r_new[g][1], rtol=2e-6, atol=2e-8)
