@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--loci", type=int, default=N_LOCI)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kinship", action="store_true")
+    ap.add_argument("--kinship-loci", type=int, default=0, help="loci of the pairwise run (0 = the resident chr22-shape matrix)")
+    ap.add_argument("--kinship-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -288,6 +291,10 @@ def run_ours(args):
         lc2 = h_lc.numpy().view(np.uint32)
         assert np.array_equal(lc2, lc), "e2e per-locus counts differ from the resident run"
 
+    kin = None
+    if not args.no_kinship:
+        kin = run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, rb, SEED, superpop, inbreeding)
+
     if rank == 0:
         peaks = {}
         try:
@@ -323,6 +330,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
         }
+        if kin is not None:
+            line["kinship"] = kin
         if not args.no_cpu_baseline and world == 1:
             try:
                 r = cpu_reference_run(2)
@@ -335,6 +344,86 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+KINSHIP_METRIC = "kinship sample-pair-loci/s"
+LOP3_PER_CLK_SM = 62.45      # measured, profiles/r01_pipe_rates_kbench.log (kgl_gene_b200/csrc/tools/kbench.cu)
+POPC_PER_CLK_SM = 15.90
+
+
+def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, rb, seed, superpop, inbreeding):
+    """BASELINE.json's second metric: pairwise IBS over all sample pairs; 64 x 64 tiles of the upper triangle dealt round-robin
+    to the ranks, every rank holds the whole matrix, no collective in the data path."""
+    from kgl_gene_b200.shards import tiles_of_rank
+    from kgl_gene_b200.synth import make_loci
+    kl = args.kinship_loci or l
+    if world > 1 or kl != l:
+        # the pairwise job needs the SAME population on every rank (the inbreeding job above holds one locus shard per rank)
+        offsets, af = make_loci(kl, seed)
+        ctx.upload_loci(af, offsets)
+        ctx.set_genome_superpop(superpop)
+        ctx.synth_genotypes(seed, n, kl, inbreeding, missing_rate=0.001, locus_base=0)
+    side, n_up = ctx.ibs_tile_grid()
+    mine = tiles_of_rank(n_up, rank, world)
+    SLAB = 8192
+
+    def step():
+        done = 0
+        while done < mine:
+            k = min(SLAB, mine - done)
+            ctx.enqueue_ibs_tiles(rank + done * world, world, k)
+            done += k
+
+    step()                                   # builds the sample-major planes once (part of the upload, not of a pass)
+    torch.cuda.synchronize()
+    ctx.ibs_timer_reset()
+    launches0 = ctx.launch_count()
+    steps = max(1, args.kinship_steps)
+    ms = timed(step, steps, 1)
+    k_ms = ctx.ibs_timer_read()
+    launches = ctx.launch_count() - launches0
+    pair_loci = float(n) * (n + 1) / 2.0 * kl
+    value = pair_loci * steps / (ms * 1e-3)
+    # end to end: host matrix in, host tiles out
+    e2e = None
+    if not args.no_e2e and world == 1 and mine <= SLAB:
+        import ctypes as C
+        h_packed = torch.empty((kl, rb), dtype=torch.uint8, pin_memory=True)
+        ctx._check(ctx.lib.kgl_b200_download_genotypes(ctx.h, C.c_uint64(kl * rb), C.c_void_p(h_packed.data_ptr())), "download_genotypes")
+        h_tiles = torch.empty((mine, 64, 64, 4), dtype=torch.int32, pin_memory=True)
+
+        def step_e2e():
+            ctx.upload_genotypes_ptr(h_packed.data_ptr(), n, kl, rb)
+            ctx._check(ctx.lib.kgl_b200_run_ibs_tiles(ctx.h, C.c_uint64(rank), C.c_uint64(world), C.c_uint64(mine), C.c_void_p(h_tiles.data_ptr())), "run_ibs_tiles")
+
+        e_ms = timed(step_e2e, 2, 1)
+        e2e = {"value": pair_loci * 2 / (e_ms * 1e-3), "unit": "sample-pair-loci/s", "h2d_bytes_per_step": int(kl * rb),
+               "d2h_bytes_per_step": int(h_tiles.numel() * 4), "ms_per_step": e_ms / 2, "steps": 2}
+        t = h_tiles.numpy().view(np.uint32)
+        assert np.array_equal(t[..., :3].sum(-1), t[..., 3]), "IBS0 + IBS1 + IBS2 != valid"
+    if rank != 0:
+        return None
+    # INT-pipe roofline of the tile kernel: 5 LOP3 + 1 POPC per executed pair-word (two-plane form: 3 for the two difference
+    # vectors, 2 for the carry-save step); the ALU pipe issues 62.45 LOP3 per clk per SM (measured), POPC 15.9.
+    clk = 1.965e9
+    sms = 148
+    exec_pair_loci = float(mine) * 4096 * kl                   # this rank's launches, incl. padding genomes and diagonal halves
+    launches_per_step = (mine + SLAB - 1) // SLAB
+    k_s = float(np.mean(k_ms)) * launches_per_step * 1e-3 if len(k_ms) else None   # the timer ring also holds the warm-up step
+    peak = LOP3_PER_CLK_SM * sms * clk / 5.0 * 32.0
+    achieved = exec_pair_loci / k_s if k_s else None
+    return {"metric": KINSHIP_METRIC, "value": value, "unit": "sample-pair-loci/s", "ms_per_step": ms / steps, "steps": steps,
+            "n_gpus": world, "scaling": "strong",
+            "config": {"workload": f"pairwise IBS0/IBS1/IBS2/valid, {n} x {n} genomes over {kl} SNPs (BASELINE config 4 shape is 20M SNPs: "
+                                   f"the same tile kernel, 18x more words per tile), upper-triangle 64x64 tiles dealt to {world} GPU(s)",
+                       "tiles": int(n_up), "tiles_this_rank": int(mine), "missing_rate": 0.001},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "int-pipe (ALU/LOP3)", "kernel": "k_ibs_tiles<false,2> (+ k_ibs_missing_fix, k_ibs_finalize)",
+                         "achieved": achieved, "peak": peak, "unit": "executed pair-loci/s",
+                         "frac": (achieved / peak) if achieved else None,
+                         "peak_source": "62.45 LOP3/clk/SM (measured, kbench) x 148 SMs x 1.965 GHz / 5 LOP3 per 32 pair-loci",
+                         "survey_8d_peak_popc_bound": POPC_PER_CLK_SM * sms * clk / 3.0 * 32.0,
+                         "kernel_ms": k_s * 1e3 if k_s else None}}
 
 
 def main():

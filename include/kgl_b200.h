@@ -138,6 +138,15 @@ int kgl_b200_run_loglik_grid(kgl_b200_ctx* ctx, const double* grid, uint64_t n_g
  * the matrix is the one VariantDBVariant::genomeData() describes, kgl_variant_db_variant.h:49-51) */
 int kgl_b200_run_ibs(kgl_b200_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint32_t* out);
 
+/* The same matrix as 64 x 64 sample-pair tiles, the unit that is dealt to GPUs ("upper-triangular sample-pair
+ * tiles dealt block-cyclically"). The tile grid has tiles_per_side = ceil(n_genomes / 64) rows; only the upper triangle
+ * (ti <= tj) exists, numbered row-major: t = 0 is (0,0), t = 1 is (0,1), ... n_upper_tiles = side (side + 1) / 2.
+ * kgl_b200_run_ibs_tiles computes tiles first, first + stride, ... (count of them; rank r of R ranks passes first = r,
+ * stride = R) into out uint32[count][64][64][4] = {IBS0, IBS1, IBS2, valid}; cell [i][j] of tile (ti,tj) is the pair
+ * (64 ti + i, 64 tj + j); cells of padding genomes are 0. */
+int kgl_b200_ibs_tile_grid(kgl_b200_ctx* ctx, uint64_t* tiles_per_side, uint64_t* n_upper_tiles);
+int kgl_b200_run_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count, uint32_t* out);
+
 /* ---- resident / asynchronous building blocks (bench.py, multi-GPU drivers) ------------------------------------------ */
 /* Enqueue the fused pass on the context stream and return immediately; results stay in device buffers. */
 int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* ctx);
@@ -150,6 +159,13 @@ float kgl_b200_last_stream_kernel_ms(kgl_b200_ctx* ctx);
  * no host synchronisation lands inside a timed region. */
 int kgl_b200_kernel_timer_reset(kgl_b200_ctx* ctx);
 int kgl_b200_kernel_timer_read(kgl_b200_ctx* ctx, float* ms, uint32_t capacity, uint32_t* n);
+/* Resident form of kgl_b200_run_ibs_tiles (count <= 8192 per call): the tiles stay in a device buffer that
+ * kgl_b200_ibs_tiles_buffer exposes (uint32[count][64][64][4]) for a device-side gather. The ibs timer is the kernel timer
+ * of the pairwise tile kernel (k_ibs_tiles). */
+int kgl_b200_enqueue_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count);
+int kgl_b200_ibs_tiles_buffer(kgl_b200_ctx* ctx, void** device_ptr, uint64_t* n_u32);
+int kgl_b200_ibs_timer_reset(kgl_b200_ctx* ctx);
+int kgl_b200_ibs_timer_read(kgl_b200_ctx* ctx, float* ms, uint32_t capacity, uint32_t* n);
 /* Copy the per-locus allele counts of the last fused pass to the host: uint32[n_loci][4]. */
 int kgl_b200_fetch_locus_counts(kgl_b200_ctx* ctx, uint32_t* locus_counts);
 

@@ -7,6 +7,8 @@ import os
 
 import numpy as np
 
+from .shards import tiles_of_rank
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkgl_b200.so")
 
@@ -25,7 +27,8 @@ EXPORTS = [
     "kgl_b200_set_stream", "kgl_b200_synchronize", "kgl_b200_upload_genotypes", "kgl_b200_upload_loci",
     "kgl_b200_set_genome_superpop", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
-    "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs",
+    "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
+    "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
     "kgl_b200_inbreed_fetch", "kgl_b200_kernel_timer_reset", "kgl_b200_kernel_timer_read", "kgl_b200_fetch_locus_counts",
@@ -208,6 +211,37 @@ class KglB200:
         out = np.zeros((row_end - row_begin, self.n_genomes, 4), dtype=np.uint32)
         self._check(self.lib.kgl_b200_run_ibs(self.h, C.c_uint64(row_begin), C.c_uint64(row_end), _ptr(out)), "run_ibs")
         return out
+
+    def ibs_tile_grid(self):
+        side, n = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kgl_b200_ibs_tile_grid(self.h, C.byref(side), C.byref(n)), "ibs_tile_grid")
+        return int(side.value), int(n.value)
+
+    def ibs_tiles(self, first=0, stride=1, count=None) -> np.ndarray:
+        """Upper-triangle 64x64 tiles first, first+stride, ...: uint32[count][64][64][4] (rank r of R: first=r, stride=R)."""
+        if count is None:
+            count = tiles_of_rank(self.ibs_tile_grid()[1], first, stride)
+        out = np.zeros((count, 64, 64, 4), dtype=np.uint32)
+        if count:
+            self._check(self.lib.kgl_b200_run_ibs_tiles(self.h, C.c_uint64(first), C.c_uint64(stride), C.c_uint64(count), _ptr(out)), "run_ibs_tiles")
+        return out
+
+    def enqueue_ibs_tiles(self, first: int, stride: int, count: int):
+        self._check(self.lib.kgl_b200_enqueue_ibs_tiles(self.h, C.c_uint64(first), C.c_uint64(stride), C.c_uint64(count)), "enqueue_ibs_tiles")
+
+    def ibs_tiles_buffer(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.kgl_b200_ibs_tiles_buffer(self.h, C.byref(p), C.byref(n)), "ibs_tiles_buffer")
+        return int(p.value), int(n.value)
+
+    def ibs_timer_reset(self):
+        self._check(self.lib.kgl_b200_ibs_timer_reset(self.h), "ibs_timer_reset")
+
+    def ibs_timer_read(self) -> np.ndarray:
+        ms = np.zeros(256, dtype=np.float32)
+        n = C.c_uint32(0)
+        self._check(self.lib.kgl_b200_ibs_timer_read(self.h, _ptr(ms), C.c_uint32(256), C.byref(n)), "ibs_timer_read")
+        return ms[: n.value].copy()
 
     # ---- resident / multi-GPU building blocks ----
     def launch_count(self) -> int:

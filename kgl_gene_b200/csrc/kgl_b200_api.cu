@@ -7,6 +7,7 @@
 #include "sparse_events.cuh"
 #include "sample_major.cuh"
 #include "misc_kernels.cuh"
+#include "ibs_launch.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -99,6 +100,14 @@ struct kgl_b200_ctx {
   DevBuf<uint64_t> d_genome_counts;
   DevBuf<kgl_b200_locus_results> d_results;
   DevBuf<uint32_t> d_ibs;
+  // pairwise IBS (ibs_tile.cuh): planes of the dense kernel, tile list, accumulators, compact tile results
+  DevBuf<uint32_t> d_ibs_lo, d_ibs_hi, d_sm_valid, d_ibs_acc, d_ibs_tiles_out;
+  DevBuf<uint2> d_ibs_tiles;
+  int ibs_mode = -1;                 // 0: no code-3 cell; 1: in-kernel validity plane; 2: pre-masked planes + sparse repair
+  std::vector<cudaEvent_t> ibs_timer_ev;
+  int ibs_timer_used = 0;
+  uint64_t ibs_last_count = 0;
+  uint64_t ibs_tiles_key[4] = {~0ull, 0, 0, 0};   // the tile list on the device: {kind, first, stride, count}
   DevBuf<unsigned int> d_ticket;
   bool tail_done = false;            // the last launch_count already assembled the per-genome results (fused tail)
 
@@ -412,6 +421,102 @@ int launch_terms(kgl_b200_ctx* c, int n_out, const double* d_grid, int n_grid, T
   return KGL_B200_OK;
 }
 
+// ---- pairwise IBS ----------------------------------------------------------------------------------------------------
+// Planes of the dense kernel. No code-3 cell: the sample-major copy as it is. Indexed code-3 cells: pre-masked copies, the
+// sparse repair kernel does the rest. Otherwise: a validity plane and the three-plane kernel.
+int ensure_ibs_planes(kgl_b200_ctx* c) {
+  int rc = ensure_sample_major(c); if (rc) return rc;
+  rc = build_dropped_index(c); if (rc) return rc;
+  if (c->ibs_mode >= 0) return KGL_B200_OK;
+  const size_t n = (size_t)c->n_gblocks * c->n_words * 32;
+  const unsigned nb = blocks_for(n / 4, 256);
+  if (c->n_dropped == 0) {
+    c->ibs_mode = 0;
+  } else if (c->dropped_indexed) {
+    KGL_CUDA(c, c->d_ibs_lo.ensure(n));
+    KGL_CUDA(c, c->d_ibs_hi.ensure(n));
+    k_ibs_premask<<<nb, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_sm_lo.p), reinterpret_cast<const uint4*>(c->d_sm_hi.p), n / 4,
+                                              reinterpret_cast<uint4*>(c->d_ibs_lo.p), reinterpret_cast<uint4*>(c->d_ibs_hi.p));
+    KGL_LAUNCH_CHECK(c);
+    c->ibs_mode = 2;
+  } else {
+    KGL_CUDA(c, c->d_sm_valid.ensure(n));
+    k_valid_plane<<<nb, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_sm_lo.p), reinterpret_cast<const uint4*>(c->d_sm_hi.p), n / 4,
+                                              reinterpret_cast<uint4*>(c->d_sm_valid.p));
+    KGL_LAUNCH_CHECK(c);
+    c->ibs_mode = 1;
+  }
+  return KGL_B200_OK;
+}
+
+uint64_t ibs_side(const kgl_b200_ctx* c) { return (c->N + kIbsT - 1) / kIbsT; }
+
+// t-th tile of the row-major upper triangle (ti <= tj) of a side x side tile grid.
+uint2 ibs_upper_tile(uint64_t t, uint64_t side) {
+  // row ti starts at ti*side - ti*(ti-1)/2
+  uint64_t lo = 0, hi = side - 1;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi + 1) / 2;
+    const uint64_t start = mid * side - mid * (mid - 1) / 2;
+    if (start <= t) lo = mid; else hi = mid - 1;
+  }
+  const uint64_t start = lo * side - lo * (lo - 1) / 2;
+  return make_uint2((uint32_t)lo, (uint32_t)(lo + (t - start)));
+}
+
+constexpr uint64_t kIbsMaxTilesPerLaunch = 8192;     // 384 MB of accumulators
+
+// Dense kernel (+ sparse repair) over a host tile list; leaves acc[n][3][4096] in d_ibs_acc. n <= kIbsMaxTilesPerLaunch.
+// `key` identifies the list: a repeated request (the benchmark loop, HallME-style reruns) skips the upload and its sync.
+int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const uint64_t (&key)[4], uint32_t n_cached = 0) {
+  const uint32_t n = tiles.empty() ? n_cached : (uint32_t)tiles.size();
+  KGL_CUDA(c, c->d_ibs_tiles.ensure(n));
+  KGL_CUDA(c, c->d_ibs_acc.ensure((size_t)n * 3 * kIbsTileCells));
+  if (std::memcmp(key, c->ibs_tiles_key, sizeof key) != 0) {
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_tiles.p, tiles.data(), (size_t)n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));     // `tiles` is pageable host memory owned by the caller
+    std::memcpy(c->ibs_tiles_key, key, sizeof key);
+  }
+  const uint32_t words_used = (uint32_t)(((c->L + 31) / 32 + 1) / 2 * 2);
+  const IbsPlan pl = plan_ibs(n, words_used, c->sm_count);
+  IbsParams P{};
+  const bool premasked = c->ibs_mode == 2;
+  P.plane[0] = premasked ? c->d_ibs_lo.p : c->d_sm_lo.p;
+  P.plane[1] = premasked ? c->d_ibs_hi.p : c->d_sm_hi.p;
+  P.plane[2] = c->ibs_mode == 1 ? c->d_sm_valid.p : nullptr;
+  P.n_words = c->n_words; P.words_used = words_used; P.tiles = c->d_ibs_tiles.p; P.n_tiles = n;
+  P.words_per_chunk = pl.words_per_chunk; P.n_chunks = pl.n_chunks; P.acc = c->d_ibs_acc.p;
+  if (pl.n_chunks > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_ibs_acc.p, 0, (size_t)n * 3 * kIbsTileCells * 4, c->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->ibs_timer_used < kgl_b200_ctx::kTimerSlots) {
+    if ((int)c->ibs_timer_ev.size() < 2 * (c->ibs_timer_used + 1)) {
+      KGL_CUDA(c, cudaEventCreate(&e0));
+      KGL_CUDA(c, cudaEventCreate(&e1));
+      c->ibs_timer_ev.push_back(e0); c->ibs_timer_ev.push_back(e1);
+    }
+    e0 = c->ibs_timer_ev[2 * c->ibs_timer_used]; e1 = c->ibs_timer_ev[2 * c->ibs_timer_used + 1];
+    ++c->ibs_timer_used;
+  }
+  if (e0) KGL_CUDA(c, cudaEventRecord(e0, c->stream));
+  KGL_CUDA(c, launch_ibs(P, pl, c->ibs_mode == 1, c->stream));
+  ++c->launches;
+  if (e1) KGL_CUDA(c, cudaEventRecord(e1, c->stream));
+  if (c->ibs_mode == 2) {
+    k_ibs_missing_fix<<<n, 128, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), (uint32_t)c->units, c->d_dropped.p,
+                                                 c->d_dropped_seg.p, c->N, c->d_ibs_tiles.p, c->d_ibs_acc.p);
+    KGL_LAUNCH_CHECK(c);
+  }
+  return KGL_B200_OK;
+}
+
+int ibs_finalize(kgl_b200_ctx* c, uint32_t n_tiles, int mode, uint64_t row_begin, uint64_t row_end, int mirror, uint32_t* d_out) {
+  k_ibs_finalize<<<blocks_for((uint64_t)n_tiles * kIbsTileCells, 256), 256, 0, c->stream>>>(
+      c->d_ibs_acc.p, c->d_ibs_tiles.p, n_tiles, c->ibs_mode, c->ibs_mode == 2 ? c->d_dropped_seg.p : nullptr, (uint32_t)c->L, mode, c->N,
+      row_begin, row_end, mirror, d_out);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -469,7 +574,9 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
+  c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release();
   for (cudaEvent_t e : c->timer_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ibs_timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -529,7 +636,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
-  c->sm_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false;
+  c->sm_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
   return KGL_B200_OK;
 }
 
@@ -887,19 +994,106 @@ int kgl_b200_run_ibs(kgl_b200_ctx* c, uint64_t row_begin, uint64_t row_end, uint
   int rc = use_device(c); if (rc) return rc;
   rc = require_population(c, false); if (rc) return rc;
   if (row_begin >= row_end || row_end > c->N) return fail(c, KGL_B200_ERR_INVALID, "bad genome row range");
-  rc = ensure_sample_major(c); if (rc) return rc;
-  // slabs of rows keep the device result under ~1 GiB
-  const uint64_t slab_rows = std::max<uint64_t>(kIbsTile, ((1ull << 30) / (c->N * 16)) / kIbsTile * kIbsTile);
-  for (uint64_t r0 = row_begin; r0 < row_end; r0 += slab_rows) {
-    const uint64_t r1 = std::min(row_end, r0 + slab_rows);
-    const size_t n = (size_t)(r1 - r0) * c->N * 4;
-    KGL_CUDA(c, c->d_ibs.ensure(n));
-    dim3 grid((unsigned)((c->N + kIbsTile - 1) / kIbsTile), (unsigned)((r1 - r0 + kIbsTile - 1) / kIbsTile));
-    k_ibs_tile<<<grid, 256, 0, c->stream>>>(c->d_sm_lo.p, c->d_sm_hi.p, c->n_gblocks, c->n_words, c->N, r0, r1, c->d_ibs.p);
-    KGL_LAUNCH_CHECK(c);
-    KGL_CUDA(c, cudaMemcpyAsync(out + (size_t)(r0 - row_begin) * c->N * 4, c->d_ibs.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  rc = ensure_ibs_planes(c); if (rc) return rc;
+  const uint64_t side = ibs_side(c);
+  const bool whole = row_begin == 0 && row_end == c->N && c->N * c->N * 16 <= (2ull << 30);
+  if (whole) {
+    // the whole matrix: upper-triangle tiles, every tile also written transposed
+    KGL_CUDA(c, c->d_ibs.ensure((size_t)c->N * c->N * 4));
+    std::vector<uint2> tiles;
+    for (uint64_t t0 = 0, n_upper = side * (side + 1) / 2; t0 < n_upper; t0 += kIbsMaxTilesPerLaunch) {
+      tiles.clear();
+      for (uint64_t t = t0; t < std::min(n_upper, t0 + kIbsMaxTilesPerLaunch); ++t) tiles.push_back(ibs_upper_tile(t, side));
+      const uint64_t key[4] = {1, t0, 1, tiles.size()};
+      rc = ibs_compute_tiles(c, tiles, key); if (rc) return rc;
+      rc = ibs_finalize(c, (uint32_t)tiles.size(), 1, 0, c->N, 1, c->d_ibs.p); if (rc) return rc;
+    }
+    KGL_CUDA(c, cudaMemcpyAsync(out, c->d_ibs.p, (size_t)c->N * c->N * 16, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return KGL_B200_OK;
+  }
+  // a band of rows: every tile of the band's tile rows, in slabs that keep the device result under ~1 GiB
+  const uint64_t slab_tile_rows = std::max<uint64_t>(1, std::min<uint64_t>((1ull << 30) / (c->N * 16 * kIbsT), kIbsMaxTilesPerLaunch / side));
+  std::vector<uint2> tiles;
+  for (uint64_t tr0 = row_begin / kIbsT; tr0 * kIbsT < row_end; tr0 += slab_tile_rows) {
+    const uint64_t tr1 = std::min((row_end + kIbsT - 1) / kIbsT, tr0 + slab_tile_rows);
+    const uint64_t r0 = std::max(row_begin, tr0 * kIbsT), r1 = std::min(row_end, tr1 * kIbsT);
+    tiles.clear();
+    for (uint64_t ta = tr0; ta < tr1; ++ta)
+      for (uint64_t tb = 0; tb < side; ++tb) tiles.push_back(make_uint2((uint32_t)ta, (uint32_t)tb));
+    KGL_CUDA(c, c->d_ibs.ensure((size_t)(r1 - r0) * c->N * 4));
+    const uint64_t key[4] = {2, tr0, tr1, tiles.size()};
+    rc = ibs_compute_tiles(c, tiles, key); if (rc) return rc;
+    rc = ibs_finalize(c, (uint32_t)tiles.size(), 1, r0, r1, 0, c->d_ibs.p); if (rc) return rc;
+    KGL_CUDA(c, cudaMemcpyAsync(out + (size_t)(r0 - row_begin) * c->N * 4, c->d_ibs.p, (size_t)(r1 - r0) * c->N * 16, cudaMemcpyDeviceToHost, c->stream));
     KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  return KGL_B200_OK;
+}
+
+int kgl_b200_ibs_tile_grid(kgl_b200_ctx* c, uint64_t* tiles_per_side, uint64_t* n_upper_tiles) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  if (!c->have_geno) return fail(c, KGL_B200_ERR_STATE, "no genotype matrix uploaded");
+  const uint64_t side = ibs_side(c);
+  if (tiles_per_side) *tiles_per_side = side;
+  if (n_upper_tiles) *n_upper_tiles = side * (side + 1) / 2;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_enqueue_ibs_tiles(kgl_b200_ctx* c, uint64_t first, uint64_t stride, uint64_t count) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  const uint64_t side = ibs_side(c), n_upper = side * (side + 1) / 2;
+  if (stride == 0 || count == 0 || count > kIbsMaxTilesPerLaunch || first + (count - 1) * stride >= n_upper)
+    return fail(c, KGL_B200_ERR_INVALID, "bad tile range (count must be 1..8192 per call and stay inside the upper triangle)");
+  rc = ensure_ibs_planes(c); if (rc) return rc;
+  const uint64_t key[4] = {0, first, stride, count};
+  std::vector<uint2> tiles;
+  if (std::memcmp(key, c->ibs_tiles_key, sizeof key) != 0) {
+    tiles.resize(count);
+    for (uint64_t i = 0; i < count; ++i) tiles[i] = ibs_upper_tile(first + i * stride, side);
+  }
+  rc = ibs_compute_tiles(c, tiles, key, (uint32_t)count); if (rc) return rc;
+  KGL_CUDA(c, c->d_ibs_tiles_out.ensure((size_t)count * kIbsTileCells * 4));
+  rc = ibs_finalize(c, (uint32_t)count, 0, 0, 0, 0, c->d_ibs_tiles_out.p); if (rc) return rc;
+  c->ibs_last_count = count;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_ibs_tiles(kgl_b200_ctx* c, uint64_t first, uint64_t stride, uint64_t count, uint32_t* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  for (uint64_t done = 0; done < count; done += kIbsMaxTilesPerLaunch) {
+    const uint64_t n = std::min<uint64_t>(kIbsMaxTilesPerLaunch, count - done);
+    int rc = kgl_b200_enqueue_ibs_tiles(c, first + done * stride, stride, n); if (rc) return rc;
+    KGL_CUDA(c, cudaMemcpyAsync(out + (size_t)done * kIbsTileCells * 4, c->d_ibs_tiles_out.p, (size_t)n * kIbsTileCells * 16, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return KGL_B200_OK;
+}
+
+int kgl_b200_ibs_tiles_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_u32) {
+  if (!c || !device_ptr || !n_u32) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (c->ibs_last_count == 0) return fail(c, KGL_B200_ERR_STATE, "enqueue_ibs_tiles first");
+  *device_ptr = c->d_ibs_tiles_out.p;
+  *n_u32 = c->ibs_last_count * kIbsTileCells * 4;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_ibs_timer_reset(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  c->ibs_timer_used = 0;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_ibs_timer_read(kgl_b200_ctx* c, float* ms, uint32_t capacity, uint32_t* n) {
+  if (!c || !ms || !n) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint32_t k = 0;
+  for (int i = 0; i < c->ibs_timer_used && k < capacity; ++i, ++k)
+    KGL_CUDA(c, cudaEventElapsedTime(&ms[k], c->ibs_timer_ev[2 * i], c->ibs_timer_ev[2 * i + 1]));
+  *n = k;
   return KGL_B200_OK;
 }
 

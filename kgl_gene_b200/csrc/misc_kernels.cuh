@@ -1,4 +1,4 @@
-// misc_kernels.cuh -- estimator finalisation, iterative updates, pairwise IBS tiles and the synthetic generator.
+// misc_kernels.cuh -- estimator finalisation, iterative updates and the synthetic generator.
 #pragma once
 #include "common.cuh"
 #include "locus_kernels.cuh"
@@ -207,81 +207,6 @@ __global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, const 
   if (g >= n_genomes) return;
   const uint64_t n3 = n3s[g], n1 = gcounts[g * 2] - n3, n2 = gcounts[g * 2 + 1] - n3;
   out[g * 4 + 0] = n_loci - n1 - n2 - n3; out[g * 4 + 1] = n1; out[g * 4 + 2] = n2; out[g * 4 + 3] = n3;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// K4: pairwise IBS tile kernel. CTA = 64x64 genome pairs, thread = 4x4 pairs, 32-locus words staged in shared memory as
-// thermometer planes X = (g>=1), Y = (g==2), V = valid. Per pair and word: 2 XOR + 3 LOP3 + 3 POPC + 3 IADD.
-constexpr int kIbsTile = 64;
-constexpr int kIbsWords = 16;   // words per shared-memory stage
-
-__global__ void __launch_bounds__(256)
-k_ibs_tile(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi, uint64_t n_gblocks, uint64_t n_words,
-           uint64_t n_genomes, uint64_t row_begin, uint64_t row_end, uint32_t* __restrict__ out /* [rows][n_genomes][4] */) {
-  __shared__ __align__(16) uint32_t sA[3][kIbsWords][kIbsTile];
-  __shared__ __align__(16) uint32_t sB[3][kIbsWords][kIbsTile];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const uint64_t a0 = row_begin + (uint64_t)blockIdx.y * kIbsTile;   // rows of this tile
-  const uint64_t b0 = (uint64_t)blockIdx.x * kIbsTile;               // columns of this tile
-  uint32_t c0[4][4], c1[4][4], cv[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { c0[i][j] = 0; c1[i][j] = 0; cv[i][j] = 0; }
-
-  for (uint64_t w0 = 0; w0 < n_words; w0 += kIbsWords) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < kIbsWords * kIbsTile; i += 256) {
-      const int w = i / kIbsTile, gi = i % kIbsTile;
-      uint32_t lo = 0xFFFFFFFFu, hi = 0xFFFFFFFFu;
-      const uint64_t ga = a0 + gi;
-      if (ga < n_genomes && w0 + w < n_words) {
-        const uint64_t o = ((ga >> 5) * n_words + w0 + w) * 32 + (ga & 31);
-        lo = sm_lo[o]; hi = sm_hi[o];
-      }
-      sA[0][w][gi] = lo ^ hi; sA[1][w][gi] = hi & ~lo; sA[2][w][gi] = ~(lo & hi);
-      lo = 0xFFFFFFFFu; hi = 0xFFFFFFFFu;
-      const uint64_t gbb = b0 + gi;
-      if (gbb < n_genomes && w0 + w < n_words) {
-        const uint64_t o = ((gbb >> 5) * n_words + w0 + w) * 32 + (gbb & 31);
-        lo = sm_lo[o]; hi = sm_hi[o];
-      }
-      sB[0][w][gi] = lo ^ hi; sB[1][w][gi] = hi & ~lo; sB[2][w][gi] = ~(lo & hi);
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int w = 0; w < kIbsWords; ++w) {
-      const uint4 ax = *reinterpret_cast<const uint4*>(&sA[0][w][ty * 4]);
-      const uint4 ay = *reinterpret_cast<const uint4*>(&sA[1][w][ty * 4]);
-      const uint4 av = *reinterpret_cast<const uint4*>(&sA[2][w][ty * 4]);
-      const uint4 bx = *reinterpret_cast<const uint4*>(&sB[0][w][tx * 4]);
-      const uint4 by = *reinterpret_cast<const uint4*>(&sB[1][w][tx * 4]);
-      const uint4 bv = *reinterpret_cast<const uint4*>(&sB[2][w][tx * 4]);
-      const uint32_t AX[4] = {ax.x, ax.y, ax.z, ax.w}, AY[4] = {ay.x, ay.y, ay.z, ay.w}, AV[4] = {av.x, av.y, av.z, av.w};
-      const uint32_t BX[4] = {bx.x, bx.y, bx.z, bx.w}, BY[4] = {by.x, by.y, by.z, by.w}, BV[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t dx = AX[i] ^ BX[j], dy = AY[i] ^ BY[j], v = AV[i] & BV[j];
-          c0[i][j] += __popc(dx & dy & v);          // |ga-gb| == 2
-          c1[i][j] += __popc((dx ^ dy) & v);        // |ga-gb| == 1
-          cv[i][j] += __popc(v);
-        }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint64_t ga = a0 + ty * 4 + i;
-    if (ga >= row_end || ga >= n_genomes) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint64_t gbb = b0 + tx * 4 + j;
-      if (gbb >= n_genomes) continue;
-      *reinterpret_cast<uint4*>(out + ((ga - row_begin) * n_genomes + gbb) * 4) =
-          make_uint4(c0[i][j], c1[i][j], cv[i][j] - c0[i][j] - c1[i][j], cv[i][j]);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

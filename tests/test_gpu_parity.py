@@ -175,11 +175,68 @@ def test_hallme_fixed_point(gpu):
 
 
 def test_ibs_matches_oracle(gpu):
+    """Indexed code-3 cells: two-plane kernel on pre-masked planes + sparse repair (ibs_tile.cuh)."""
     from kgl_gene_b200.synth import make_population
     pop, _ = make_population(150, 3001, seed=21, missing_rate=0.03)
     gpu.upload_population(pop)
-    assert np.array_equal(gpu.ibs(), O.ibs(pop))
-    assert np.array_equal(gpu.ibs(64, 130), O.ibs(pop)[64:130])
+    want = O.ibs(pop)
+    assert np.array_equal(gpu.ibs(), want)
+    assert np.array_equal(gpu.ibs(64, 130), want[64:130])
+    assert np.array_equal(gpu.ibs(149, 150), want[149:150])
+
+
+@pytest.mark.parametrize("n,l,miss", [(70, 999, 0.0),        # no code-3 cell: the sample-major planes as they are
+                                      (300, 20000, 0.03),    # too many code-3 cells to index: in-kernel validity plane
+                                      (64, 64, 0.5),         # exactly one tile, two words, half the cells dropped
+                                      (1, 40, 0.1),          # a single genome
+                                      (129, 33000, 0.002)])  # several word chunks per tile
+def test_ibs_modes_and_edges(gpu, n, l, miss):
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(n, l, seed=3 + n, missing_rate=miss)
+    gpu.upload_population(pop)
+    want = O.ibs(pop)
+    got = gpu.ibs()
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, got.transpose(1, 0, 2))
+    assert np.array_equal(got[..., :3].sum(-1), got[..., 3])
+
+
+def test_ibs_tiles_dealt_to_ranks(gpu):
+    """The multi-GPU decomposition on one device: every 'rank' computes tiles rank, rank + world, ...; assembled = oracle."""
+    from kgl_gene_b200 import shards
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(200, 2500, seed=8, missing_rate=0.01)
+    gpu.upload_population(pop)
+    side, n_up = gpu.ibs_tile_grid()
+    assert side == 4 and n_up == 10
+    want = O.ibs(pop)
+    for world in (1, 3):
+        blocks = [gpu.ibs_tiles(first=r, stride=world) for r in range(world)]
+        assert np.array_equal(shards.assemble_ibs(pop.n_genomes, blocks), want)
+    # cells of padding genomes (200..255) read zero
+    last = gpu.ibs_tiles(first=n_up - 1, stride=1, count=1)[0]
+    assert np.all(last[200 - 192:, :, :] == 0) and np.all(last[:, 200 - 192:, :] == 0)
+
+
+def test_ibs_full_width_properties(gpu):
+    """chr22-shaped width on device-generated data: symmetry through independent tiles, diagonal, row sums vs allele counts."""
+    from kgl_gene_b200.synth import make_genomes, make_loci
+    n, l = 2504, 40_000
+    offsets, af = make_loci(l, 78)
+    superpop, f = make_genomes(n, 78)
+    gpu.upload_loci(af, offsets)
+    gpu.set_genome_superpop(superpop)
+    gpu.synth_genotypes(78, n, l, f, missing_rate=0.001)
+    _, gc = gpu.allele_count()
+    band = gpu.ibs(1000, 1100)                       # band path: every tile of two tile rows, no mirroring
+    full = gpu.ibs()                                 # upper triangle + mirrored
+    assert np.array_equal(full[1000:1100], band)
+    assert np.array_equal(full, full.transpose(1, 0, 2))
+    d = np.arange(n)
+    valid = (gc[:, 0] + gc[:, 1] + gc[:, 2]).astype(np.uint32)
+    assert np.array_equal(full[d, d, 3], valid) and np.array_equal(full[d, d, 2], valid)
+    assert np.all(full[d, d, 0] == 0) and np.all(full[d, d, 1] == 0)
+    assert np.array_equal(full[..., :3].sum(-1), full[..., 3])
 
 
 def test_device_generator_matches_numpy(gpu):
