@@ -284,7 +284,7 @@ def run_ours(args):
 
         e2e_steps = max(3, min(args.steps, 10))
         e2e_ms = timed(step_e2e, e2e_steps, 2)
-        h2d = l * rb + af.nbytes + n + l
+        h2d = l * rb + af.nbytes + offsets.nbytes + n      # matrix, AF vectors, locus offsets, super-populations (the selection is made on the device)
         d2h = 16 * l + RESULT_DTYPE.itemsize * n
         e2e = {"value": cells * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps}
@@ -321,7 +321,7 @@ def run_ours(args):
             "config": {"workload": workload_name(n, l, world), "n_genomes": n, "n_loci_per_gpu": l, "af_vectors": int(af.shape[0]),
                        "selection": "one window, all loci", "missing_rate": 0.001,
                        "l2": f"inputs ({l * rb / 1e6:.0f} MB matrix per GPU) are larger than the 126 MB L2; no flush needed",
-                       "step": "k_locus_prepare + k_reduce_totals + k_stream_count_ct + k_expand_planes + k_dropped_apply + k_rare_rows + k_moment_partials (+ NCCL all-reduce) + k_finalize_closed_form"},
+                       "step": "k_locus_prepare (flags + dense totals) + k_stream_count_ct + k_post (counter expansion | code-3 cells | rare-major rows) + k_moment_partials (+ NCCL all-reduce + k_finalize_closed_form at N > 1)"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_stream_count_ct<40,64>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

@@ -30,7 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++", "-o", LIB] + SOURCES
+           "-Xcompiler", "-fPIC", "-shared", "-Xcompiler", "-pthread", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++", "-o", LIB] + SOURCES
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)

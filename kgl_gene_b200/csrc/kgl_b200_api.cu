@@ -8,14 +8,17 @@
 #include "sample_major.cuh"
 #include "misc_kernels.cuh"
 #include "ibs_launch.cuh"
+#include "post_kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace kgl;
@@ -72,8 +75,13 @@ struct kgl_b200_ctx {
   DevBuf<uint8_t> d_sort_temp;
   uint64_t n_dropped = 0;
   bool dropped_indexed = false, dropped_valid = false;
+  // host mirrors of the locus tables, fetched from the device only when the host selection path needs them
   std::vector<float> h_af;
   std::vector<uint32_t> h_offsets;
+  bool h_loci_valid = false, have_offsets = false, h_sel_valid = false;
+  uint64_t loci_len = 0;               // n_loci of the uploaded AF table
+  DevBuf<uint32_t> d_offsets;
+  DevBuf<unsigned long long> d_sel_counts;
   std::vector<uint8_t> h_superpop, h_sel;
   bool any_mixed = false;
   bool units_valid = false;
@@ -109,6 +117,7 @@ struct kgl_b200_ctx {
   uint64_t ibs_last_count = 0;
   uint64_t ibs_tiles_key[4] = {~0ull, 0, 0, 0};   // the tile list on the device: {kind, first, stride, count}
   DevBuf<unsigned int> d_ticket;
+  bool fused_tail = false;           // KGL_B200_FUSED_TAIL=1: the last block of k_post assembles the per-genome results (slower: one block, serial)
   bool tail_done = false;            // the last launch_count already assembled the per-genome results (fused tail)
 
   // iterative estimator state
@@ -172,7 +181,7 @@ int require_population(kgl_b200_ctx* c, bool need_loci) {
   if (need_loci) {
     if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "no allele frequencies uploaded (kgl_b200_upload_loci)");
     if (!c->have_superpop) return fail(c, KGL_B200_ERR_STATE, "no genome super-populations set (kgl_b200_set_genome_superpop)");
-    if (c->h_sel.size() != c->L) return fail(c, KGL_B200_ERR_STATE, "locus selection does not match the genotype matrix");
+    if (c->loci_len != c->L) return fail(c, KGL_B200_ERR_STATE, "locus selection does not match the genotype matrix");
     for (uint64_t g = 0; g < c->N; ++g)
       if (c->h_superpop[g] >= c->n_pop) return fail(c, KGL_B200_ERR_INVALID, "genome super-population index out of range");
   }
@@ -182,6 +191,14 @@ int require_population(kgl_b200_ctx* c, bool need_loci) {
 uint64_t term_words(uint64_t n_loci) {
   const uint64_t nw = (n_loci + 31) / 32;
   return (nw + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
+}
+
+// Ticket counters of the "last block finishes the job" kernels: [0] k_locus_prepare, [1] k_post. They reset themselves.
+cudaError_t ensure_tickets(kgl_b200_ctx* c) {
+  if (c->d_ticket.p) return cudaSuccess;
+  cudaError_t e = c->d_ticket.ensure(2);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_ticket.p, 0, 8, c->stream);
+  return e;
 }
 
 // Selection flags, 64-row summaries, packed selection words, rare-major row list and dense totals (once per selection).
@@ -195,21 +212,19 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
   KGL_CUDA(c, c->d_sum64.ensure(c->padded_rows / 64));
   KGL_CUDA(c, c->d_selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
   KGL_CUDA(c, c->d_rare_rows.ensure(L));
-  KGL_CUDA(c, c->d_n_rare.ensure(2));
+  KGL_CUDA(c, c->d_n_rare.ensure(4));      // [0] rare-row count, [1] all-selected flag, [2] blocks with an unselected row
   KGL_CUDA(c, c->d_block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
   KGL_CUDA(c, c->d_totals.ensure(kMaxPop * TOT_COUNT));
-  KGL_CUDA(c, cudaMemsetAsync(c->d_n_rare.p, 0, 4, c->stream));
+  KGL_CUDA(c, ensure_tickets(c));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_n_rare.p, 0, 16, c->stream));
   if (want_w0)
     k_locus_prepare<true><<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
                                                               c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
-                                                              c->d_block_totals.p);
+                                                              c->d_block_totals.p, c->d_totals.p, c->d_n_rare.p + 1, c->d_ticket.p);
   else
     k_locus_prepare<false><<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
                                                                c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
-                                                               c->d_block_totals.p);
-  KGL_LAUNCH_CHECK(c);
-  k_reduce_totals<<<kMaxPop * TOT_COUNT + 1, 256, 0, c->stream>>>(c->d_block_totals.p, nb, c->d_totals.p, c->d_flags16.p, c->d_sum64.p, L,
-                                                                  (1u << c->n_pop) - 1u, c->d_n_rare.p + 1);
+                                                               c->d_block_totals.p, c->d_totals.p, c->d_n_rare.p + 1, c->d_ticket.p);
   KGL_LAUNCH_CHECK(c);
   c->prep_valid = true; c->prep_has_w0 = want_w0;
   return KGL_B200_OK;
@@ -289,7 +304,9 @@ int alloc_matrix(kgl_b200_ctx* c) {
 
 // The fused streaming pass + its sparse companions. raw: allele_count over all loci; otherwise over the selected loci.
 // Leaves d_gcounts {lo, hi}, d_n3, d_nz_rare, d_ecorr per genome and the per-locus counts.
-int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false) {
+// tail_mode: what the last block of k_post assembles -- 0 nothing, 1 the moment partials (d_partials; + the Simple closed
+// form into d_results when simple_results), 2 the raw per-genome counts (d_genome_counts).
+int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false, int tail_mode = 0) {
   int rc = build_unit_tables(c);
   if (rc) return rc;
   rc = build_dropped_index(c);
@@ -346,26 +363,39 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   if (want_genome) {
     const SparseOut so{c->d_n3, c->d_nz_rare, c->d_ecorr};
     const uint16_t* fl = raw ? nullptr : c->d_flags16.p;
-    {
-      dim3 eg(blocks_for(c->Npad, 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
+    const unsigned e_bx = blocks_for(c->Npad, 256), e_by = (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup);
+    if (c->dropped_indexed || c->n_dropped == 0) {
+      // one launch: counter expansion, indexed code-3 cells and rare-major rows side by side; the last block assembles
+      // the per-genome results (post_kernels.cuh)
+      PostParams Q{};
+      Q.planes = c->d_planes.p; Q.n_vchunks = pl.n_vchunks; Q.units = c->units; Q.n_genomes_padded = c->Npad; Q.gcounts = c->d_gcounts;
+      Q.e_bx = e_bx; Q.e_by = e_by;
+      Q.keys = c->d_dropped.p; Q.seg = c->d_dropped_seg.p; Q.d_blocks = c->n_dropped ? (unsigned)((c->N + 1) / 2) : 0u;
+      Q.rare_rows = c->d_rare_rows.p; Q.n_rare = c->d_n_rare.p; Q.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
+      Q.popmask = c->d_popmask.p; Q.r_blocks = raw ? 0u : 32u;
+      Q.n_genomes = c->N; Q.n_loci = c->L; Q.n_pop = (int)c->n_pop;
+      Q.flags16 = fl; Q.all_selected = raw ? nullptr : c->d_n_rare.p + 1; Q.superpop = c->d_superpop.p; Q.af = c->d_af.p;
+      Q.so = so;
+      Q.tail_mode = c->fused_tail ? tail_mode : 0; Q.unphased = c->unphased ? 1 : 0;
+      Q.totals = c->d_totals.p; Q.partials = c->d_partials.p; Q.results = simple_results ? c->d_results.p : nullptr;
+      Q.genome_counts = c->d_genome_counts.p; Q.ticket = c->d_ticket.p + 1;
+      KGL_CUDA(c, ensure_tickets(c));
+      k_post<<<e_bx * e_by + Q.d_blocks + Q.r_blocks, 256, 0, c->stream>>>(Q);
+      KGL_LAUNCH_CHECK(c);
+      c->tail_done = Q.tail_mode != 0;
+    } else {
+      dim3 eg(e_bx, e_by);
       k_expand_planes<<<eg, 256, 0, c->stream>>>(c->d_planes.p, pl.n_vchunks, c->units, c->Npad, c->d_gcounts);
       KGL_LAUNCH_CHECK(c);
-      if (c->dropped_indexed) {
-        k_dropped_apply<<<(unsigned)((c->N + 1) / 2), 256, 0, c->stream>>>(c->d_dropped.p, c->d_dropped_seg.p, c->N, fl,
-                                                                            raw ? nullptr : c->d_n_rare.p + 1, c->d_superpop.p,
-                                                                            c->d_af.p, c->L, so);
-        KGL_LAUNCH_CHECK(c);
-      } else if (c->n_dropped > 0) {
-        const uint64_t n128 = c->L * c->units;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
-        k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
-                                                     c->d_superpop.p, c->d_af.p, c->L, so);
-        KGL_LAUNCH_CHECK(c);
-      }
+      const uint64_t n128 = c->L * c->units;
+      const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+      k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
+                                                   c->d_superpop.p, c->d_af.p, c->L, so);
+      KGL_LAUNCH_CHECK(c);
       if (!raw) {
         k_rare_rows<<<32, 256, 0, c->stream>>>(c->d_rare_rows.p, c->d_n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
-                                                             (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
-                                                             c->L, (int)c->n_pop, so);
+                                               (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
+                                               c->L, (int)c->n_pop, so);
         KGL_LAUNCH_CHECK(c);
       }
     }
@@ -377,10 +407,10 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
 int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false) {
   int rc = ensure_prepared(c, want_w0);
   if (rc) return rc;
-  rc = launch_count(c, false, want_locus_counts, true, simple_results);
+  KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
+  rc = launch_count(c, false, want_locus_counts, true, simple_results, 1);
   if (rc) return rc;
   if (c->tail_done) return KGL_B200_OK;
-  KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
   k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->d_totals.p, c->d_ecorr, c->d_nz_rare,
                                                                   c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p,
                                                                   simple_results ? c->d_results.p : nullptr);
@@ -559,6 +589,7 @@ int kgl_b200_create(int device, kgl_b200_ctx** out) {
     return fail(nullptr, KGL_B200_ERR_CUDA, m);
   }
   c->stream = c->own_stream;
+  if (const char* e = std::getenv("KGL_B200_FUSED_TAIL")) c->fused_tail = e[0] == '1';
   *out = c;
   return KGL_B200_OK;
 }
@@ -574,7 +605,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
-  c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release();
+  c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
   for (cudaEvent_t e : c->timer_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ibs_timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -632,7 +663,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   if (n_genomes >= (1ull << 32) || n_loci >= (1ull << 32)) return fail(c, KGL_B200_ERR_INVALID, "dimension too large");
   // A matrix of a different shape starts a new population: stale loci / super-populations must be uploaded again
   // (require_population reports what is missing at run time).
-  if (c->have_loci && c->h_af.size() != (size_t)c->n_pop * n_loci) { c->have_loci = false; c->prep_valid = false; }
+  if (c->have_loci && c->loci_len != n_loci) { c->have_loci = false; c->prep_valid = false; }
   if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
@@ -660,13 +691,16 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   if (n_loci == 0) return fail(c, KGL_B200_ERR_INVALID, "n_loci is 0");
   if (c->have_geno && c->L != n_loci) c->have_geno = false;   // new population: the old matrix no longer applies
   int rc = use_device(c); if (rc) return rc;
-  c->h_af.assign(af, af + (size_t)n_pop * n_loci);
-  if (offsets) c->h_offsets.assign(offsets, offsets + n_loci); else c->h_offsets.clear();
+  c->h_loci_valid = false; c->have_offsets = offsets != nullptr; c->loci_len = n_loci;
   c->n_pop = n_pop;
   if (!c->have_geno) c->L = n_loci;
   KGL_CUDA(c, c->d_af.ensure((size_t)n_pop * n_loci));
   KGL_CUDA(c, cudaMemcpyAsync(c->d_af.p, af, (size_t)n_pop * n_loci * 4, cudaMemcpyHostToDevice, c->stream));
-  c->h_sel.assign(n_loci, 0);
+  if (offsets) {
+    KGL_CUDA(c, c->d_offsets.ensure(n_loci));
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_offsets.p, offsets, n_loci * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->h_sel_valid = false;            // device selection: all zero (nothing selected)
   KGL_CUDA(c, c->d_sel.ensure(n_loci));
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, n_loci, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -700,7 +734,7 @@ int kgl_b200_set_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, const uint8_t
   if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "upload_loci first");
   if (n_loci != c->L) return fail(c, KGL_B200_ERR_INVALID, "selection length differs from n_loci");
   int rc = use_device(c); if (rc) return rc;
-  c->h_sel.assign(selected, selected + n_loci);
+  c->h_sel_valid = false;
   KGL_CUDA(c, cudaMemcpyAsync(c->d_sel.p, selected, n_loci, cudaMemcpyHostToDevice, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->prep_valid = false;
@@ -709,49 +743,101 @@ int kgl_b200_set_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, const uint8_t
 
 int kgl_b200_get_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, uint8_t* selected) {
   if (!c || !selected) return fail(c, KGL_B200_ERR_INVALID, "null argument");
-  if (n_loci != c->h_sel.size()) return fail(c, KGL_B200_ERR_INVALID, "selection length differs from n_loci");
-  std::memcpy(selected, c->h_sel.data(), n_loci);
+  if (!c->have_loci || n_loci != c->loci_len) return fail(c, KGL_B200_ERR_INVALID, "selection length differs from n_loci");
+  int rc = use_device(c); if (rc) return rc;
+  KGL_CUDA(c, cudaMemcpyAsync(selected, c->d_sel.p, n_loci, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   return KGL_B200_OK;
 }
 
-// RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) per super-population. The spacing rule makes
-// the scan sequential in locus order; it runs once per window on the host copy of the AF vectors (not on the hot path).
+// RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) per super-population.
+//  * spacing == 0: every locus decides for itself -> one kernel over the device tables (k_select_dense), nothing crosses PCIe
+//    but six counters.
+//  * spacing  > 0: the rule "at least `spacing` after the previously ACCEPTED locus" is a sequential chain per population;
+//    the six chains run on six host threads over host mirrors of the tables (fetched from the device once per upload).
 int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64_t spacing, double min_af, double max_af,
                          uint64_t* n_selected) {
   if (!c) return KGL_B200_ERR_INVALID;
   if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "upload_loci first");
-  if (c->h_offsets.size() != c->L) return fail(c, KGL_B200_ERR_STATE, "select_loci needs the locus offsets (upload_loci with offsets)");
+  if (!c->have_offsets) return fail(c, KGL_B200_ERR_STATE, "select_loci needs the locus offsets (upload_loci with offsets)");
+  int rc = use_device(c); if (rc) return rc;
   min_af = std::min(std::max(min_af, 0.0), 1.0);     // LociiVectorArguments clamps (kga_analysis_inbreed_args.h:85-86)
   max_af = std::min(std::max(max_af, 0.0), 1.0);
-  std::vector<uint8_t> sel(c->L, 0);
-  for (uint32_t k = 0; k < c->n_pop; ++k) {
-    const float* af = c->h_af.data() + (size_t)k * c->L;
+  const uint64_t L = c->loci_len;
+  if (spacing == 0) {
+    KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
+    KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
+    k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
+                                                              c->d_sel.p, c->d_sel_counts.p);
+    KGL_LAUNCH_CHECK(c);
+    c->prep_valid = false; c->h_sel_valid = false;
+    if (n_selected) {
+      unsigned long long counts[kMaxPop];
+      KGL_CUDA(c, cudaMemcpyAsync(counts, c->d_sel_counts.p, kMaxPop * 8, cudaMemcpyDeviceToHost, c->stream));
+      KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+      for (uint32_t k = 0; k < c->n_pop; ++k) n_selected[k] = counts[k];
+    }
+    return KGL_B200_OK;
+  }
+  if (!c->h_loci_valid) {
+    c->h_af.resize((size_t)c->n_pop * L);
+    c->h_offsets.resize(L);
+    KGL_CUDA(c, cudaMemcpyAsync(c->h_af.data(), c->d_af.p, c->h_af.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaMemcpyAsync(c->h_offsets.data(), c->d_offsets.p, L * 4, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h_loci_valid = true;
+  }
+  std::vector<uint8_t> bits[kMaxPop];
+  uint64_t counts[kMaxPop] = {0, 0, 0, 0, 0, 0};
+  const uint64_t l_begin = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
+                                            [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
+  const uint64_t l_end = std::upper_bound(c->h_offsets.begin(), c->h_offsets.end(), upper,
+                                          [](uint64_t v, uint32_t o) { return v < (uint64_t)o; }) - c->h_offsets.begin();
+  auto chain = [&](uint32_t k) {
+    const float* af = c->h_af.data() + (size_t)k * L;
+    std::vector<uint8_t>& b = bits[k];
+    b.assign(l_end > l_begin ? l_end - l_begin : 0, 0);
     uint64_t previous_offset = 0, count = 0;
-    uint64_t l = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
-                                  [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
-    for (; l < c->L; ++l) {
+    for (uint64_t l = l_begin; l < l_end; ++l) {
       const uint64_t offset = c->h_offsets[l];
-      if (offset > upper) break;
       if (offset >= previous_offset + spacing || previous_offset == 0) {
         const float a = af[l];
         if (a != a) continue;                                    // empty AlleleFreqVector: invalid
         const double p = std::min(std::max((double)a, 0.0), 1.0);
         if (p == 0.0 || p < min_af || p > max_af) continue;
         previous_offset = offset;
-        sel[l] |= (uint8_t)(1u << k);
+        b[l - l_begin] = 1;
         ++count;
       }
     }
-    if (n_selected) n_selected[k] = count;
+    counts[k] = count;
+  };
+  if (l_end - l_begin > 50000 && c->n_pop > 1) {
+    std::vector<std::thread> th;
+    for (uint32_t k = 1; k < c->n_pop; ++k) th.emplace_back(chain, k);
+    chain(0);
+    for (auto& t : th) t.join();
+  } else {
+    for (uint32_t k = 0; k < c->n_pop; ++k) chain(k);
   }
-  return kgl_b200_set_locus_selection(c, c->L, sel.data());
+  // only the window crosses PCIe: the rest of the device mask is cleared in place
+  const uint64_t span = l_end > l_begin ? l_end - l_begin : 0;
+  std::vector<uint8_t> sel(span, 0);
+  for (uint32_t k = 0; k < c->n_pop; ++k)
+    for (uint64_t i = 0; i < span; ++i) sel[i] |= (uint8_t)(bits[k][i] << k);
+  if (n_selected) for (uint32_t k = 0; k < c->n_pop; ++k) n_selected[k] = counts[k];
+  KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, L, c->stream));
+  if (span) KGL_CUDA(c, cudaMemcpyAsync(c->d_sel.p + l_begin, sel.data(), span, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->prep_valid = false; c->h_sel_valid = false;
+  return KGL_B200_OK;
 }
 
 int kgl_b200_synth_genotypes(kgl_b200_ctx* c, uint64_t seed, uint64_t n_genomes, uint64_t n_loci, uint64_t locus_base,
                              const double* inbreeding, double missing_rate) {
   if (!c || !inbreeding) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   if (!c->have_loci || !c->have_superpop) return fail(c, KGL_B200_ERR_STATE, "upload_loci and set_genome_superpop first");
-  if (c->h_superpop.size() != n_genomes || c->h_af.size() != (size_t)c->n_pop * n_loci)
+  if (c->h_superpop.size() != n_genomes || c->loci_len != n_loci)
     return fail(c, KGL_B200_ERR_INVALID, "shape differs from the uploaded loci / super-populations");
   int rc = use_device(c); if (rc) return rc;
   const uint64_t row_bytes = 16 * ((n_genomes + 63) / 64);
@@ -788,11 +874,11 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t*
     rc = kgl_b200_set_genome_superpop(c, c->N, zeros.data()); if (rc) return rc;
     c->have_superpop = false;
   }
-  rc = launch_count(c, true, locus_counts != nullptr, genome_counts != nullptr); if (rc) return rc;
+  if (genome_counts) KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 4));
+  rc = launch_count(c, true, locus_counts != nullptr, genome_counts != nullptr, false, 2); if (rc) return rc;
   if (locus_counts)
     KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
   if (genome_counts) {
-    KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 4));
     if (!c->tail_done) k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->L, c->d_genome_counts.p);
     KGL_LAUNCH_CHECK(c);
     KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_genome_counts.p, (size_t)c->N * 32, cudaMemcpyDeviceToHost, c->stream));

@@ -34,8 +34,10 @@ __global__ void __launch_bounds__(kPrepThreads)
 k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, uint64_t n_loci, uint64_t padded_rows, int n_pop,
                 int select_all, uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64,
                 uint32_t* __restrict__ selw, uint64_t n_words, uint32_t* __restrict__ rare_rows, uint32_t* __restrict__ n_rare,
-                double* __restrict__ block_totals) {
+                double* __restrict__ block_totals, double* __restrict__ totals, uint32_t* __restrict__ all_selected,
+                unsigned int* __restrict__ ticket) {
   __shared__ double s_tot[kPrepThreads / 32][kMaxPop][TOT_COUNT];
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t base = (uint64_t)blockIdx.x * kPrepLociPerBlock + (uint64_t)warp * 64 + lane;   // + it * 512 + half * 32
   uint32_t fl[kPrepIters][2], sbits[kPrepIters][2];
@@ -115,35 +117,76 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
     for (int w = 0; w < kPrepThreads / 32; ++w) v += s_tot[w][k][j];
     block_totals[((uint64_t)blockIdx.x * kMaxPop + k) * TOT_COUNT + j] = v;
   }
+
+  // all_selected[1] (zeroed by the caller) counts the blocks that hold a row < n_loci which is not selected and valid for
+  // every population; all_selected[0] = 1 iff there is none (then the sparse kernels need not look at the flags).
+  {
+    const uint32_t all_pops = (1u << n_pop) - 1u;
+    bool ok = true;
+#pragma unroll
+    for (int it = 0; it < kPrepIters; ++it)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
+        if (l < n_loci && (fl[it][half] & all_pops) != all_pops) ok = false;
+      }
+    if (!__syncthreads_and(ok) && threadIdx.x == 0) atomicAdd(&all_selected[1], 1u);
+  }
+  // The block that finishes last reduces the block totals in a fixed order (lane-strided partial sums, then the warp
+  // tree), so the totals do not depend on the schedule.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  {
+    // thread t: item t % 36, block phase t / 36 (7 phases); fixed order: phase-strided partial sums, then phases 0..6
+    __shared__ double s_part[7][kMaxPop * TOT_COUNT];
+    constexpr int NI = kMaxPop * TOT_COUNT;
+    const int item = threadIdx.x % NI, phase = threadIdx.x / NI;
+    if (phase < 7) {
+      double v = 0.0;
+      for (uint64_t b = phase; b < gridDim.x; b += 7) v += __ldcg(&block_totals[b * NI + item]);
+      s_part[phase][item] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NI) {
+      double v = 0.0;
+#pragma unroll
+      for (int ph = 0; ph < 7; ++ph) v += s_part[ph][threadIdx.x];
+      totals[threadIdx.x] = v;
+    }
+  }
+  if (threadIdx.x == 0) { all_selected[0] = (__ldcg(&all_selected[1]) == 0) ? 1u : 0u; *ticket = 0; }
 }
 
-// Fixed-order reduction of the block totals: totals[item], one block per item, deterministic. One extra block
-// (blockIdx.x == kMaxPop * TOT_COUNT) reduces the 64-row summaries: all_selected[0] = 1 iff every row < n_loci is selected
-// and valid for every population (then the sparse kernels need not look at the flags).
+// RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) with lociiSpacing == 0: a locus is taken for
+// population k iff lower <= offset <= upper, its AF entry exists, and p = clamp(AF, 0, 1) satisfies p != 0 and
+// min_af <= p <= max_af (:53-54). sel[l] bit k; counts[k] += selected loci.
 __global__ void __launch_bounds__(256)
-k_reduce_totals(const double* __restrict__ block_totals, uint64_t n_blocks, double* __restrict__ totals,
-                const uint16_t* __restrict__ flags16, const uint16_t* __restrict__ sum64, uint64_t n_loci, uint32_t all_pops,
-                uint32_t* __restrict__ all_selected) {
-  __shared__ double s[256];
-  if (blockIdx.x == kMaxPop * TOT_COUNT) {
-    uint32_t a = all_pops;
-    const uint64_t full_groups = n_loci / 64;                                // the last, partial group is checked row by row
-    for (uint64_t i = threadIdx.x; i < full_groups; i += 256) a &= sum64[i];
-    for (uint64_t l = full_groups * 64 + threadIdx.x; l < n_loci; l += 256) a &= flags16[l];
-    const int ok = __syncthreads_and((a & all_pops) == all_pops);
-    if (threadIdx.x == 0) all_selected[0] = ok ? 1u : 0u;
-    return;
+k_select_dense(const float* __restrict__ af, const uint32_t* __restrict__ offsets, uint64_t n_loci, int n_pop, uint64_t lower,
+               uint64_t upper, double min_af, double max_af, uint8_t* __restrict__ sel, unsigned long long* __restrict__ counts) {
+  const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bits = 0;
+  if (l < n_loci) {
+    const uint64_t offset = offsets[l];
+    if (offset >= lower && offset <= upper) {
+      for (int k = 0; k < n_pop; ++k) {
+        const float a = af[(uint64_t)k * n_loci + l];
+        if (a != a) continue;
+        double p = (double)a;
+        p = p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p);
+        if (p == 0.0 || p < min_af || p > max_af) continue;
+        bits |= 1u << k;
+      }
+    }
+    sel[l] = (uint8_t)bits;
   }
-  const int item = blockIdx.x;
-  double v = 0.0;
-  for (uint64_t b = threadIdx.x; b < n_blocks; b += 256) v += block_totals[b * kMaxPop * TOT_COUNT + item];
-  s[threadIdx.x] = v;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-    __syncthreads();
+  for (int k = 0; k < n_pop; ++k) {
+    const uint32_t n = __popc(__ballot_sync(kFull, (bits >> k) & 1u));
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counts[k], (unsigned long long)n);
   }
-  if (threadIdx.x == 0) totals[item] = s[0];
 }
 
 }  // namespace kgl

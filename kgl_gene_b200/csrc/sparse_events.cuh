@@ -94,14 +94,14 @@ k_dropped_segments(const DroppedKey* __restrict__ keys, uint64_t n_keys, uint64_
 // in a fixed order, so the result does not depend on scheduling. flags16 == null: raw mode (allele_count) -- every
 // code-3 cell counts, no frequency corrections. Writes n3[g]; adds the class frequencies of the selected dropped loci
 // to ecorr[g].
-__global__ void __launch_bounds__(256)
-k_dropped_apply(const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
-                const uint16_t* __restrict__ flags16, const uint32_t* __restrict__ all_selected,
-                const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
+__device__ __forceinline__ void
+dropped_apply_block(uint32_t block, const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
+                    const uint16_t* __restrict__ flags16, const uint32_t* __restrict__ all_selected,
+                    const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
   __shared__ double s_sum[2][4][2];
   __shared__ uint32_t s_n[2][4];
   const uint32_t tid = threadIdx.x, lane = tid & 31, half = tid >> 7, w4 = (tid >> 5) & 3, t128 = tid & 127;
-  const uint64_t g = (uint64_t)blockIdx.x * 2 + half;
+  const uint64_t g = (uint64_t)block * 2 + half;
   const bool raw = flags16 == nullptr;
   uint32_t n = 0;
   double sa = 0.0, sm = 0.0;
@@ -148,6 +148,13 @@ k_dropped_apply(const DroppedKey* __restrict__ keys, const uint64_t* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256)
+k_dropped_apply(const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
+                const uint16_t* __restrict__ flags16, const uint32_t* __restrict__ all_selected,
+                const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
+  dropped_apply_block(blockIdx.x, keys, seg, n_genomes, flags16, all_selected, superpop, af, n_loci, out);
+}
+
 // Fallback without an index: one thread per 128-bit unit-row.
 __global__ void __launch_bounds__(256)
 k_dropped_scan(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t units, const uint16_t* __restrict__ flags16,
@@ -176,12 +183,12 @@ k_dropped_scan(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t u
 
 // Rare-major rows (flags16 high byte != 0; listed by k_locus_prepare). One thread per (listed row, unit): for every genome
 // whose population has q <= 0.01 at this row: hom-ref -> the locus is dropped for it; else nz_rare++.
-__global__ void __launch_bounds__(256)
-k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare, const uint4* __restrict__ packed,
-            uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16, const uint64_t* __restrict__ popmask,
-            const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
+__device__ __forceinline__ void
+rare_rows_block(uint32_t block, uint32_t n_blocks, const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare,
+                const uint4* __restrict__ packed, uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16,
+                const uint64_t* __restrict__ popmask, const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
   const uint64_t total = (uint64_t)(*n_rare) * units;
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t t = (uint64_t)block * blockDim.x + threadIdx.x; t < total; t += (uint64_t)n_blocks * blockDim.x) {
     const uint32_t row = rare_rows[t / units], u = (uint32_t)(t % units);
     const uint32_t rq = (uint32_t)flags16[row] >> 8;
     const uint4 v = packed[(uint64_t)row * units + u];
@@ -208,6 +215,13 @@ k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare, const uint4* __restrict__ packed,
+            uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16, const uint64_t* __restrict__ popmask,
+            const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
+  rare_rows_block(blockIdx.x, gridDim.x, rare_rows, n_rare, packed, units, n_genomes, flags16, popmask, af, n_loci, n_pop, out);
 }
 
 }  // namespace kgl

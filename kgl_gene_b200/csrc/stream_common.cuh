@@ -121,14 +121,14 @@ __host__ __device__ inline size_t stream_smem_bytes(uint32_t slice_units, uint32
 
 // Expand the bit-sliced counters: gcounts[g] = {set lo bits, set hi bits} summed over the virtual chunks.
 constexpr int kExpandGroup = 4;
-__global__ void __launch_bounds__(256)
-k_expand_planes(const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units, uint64_t n_genomes_padded,
-                uint32_t* __restrict__ gcounts /* [n_genomes_padded][2], zeroed */) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void
+expand_planes_block(uint32_t bx, uint32_t by, const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units,
+                    uint64_t n_genomes_padded, uint32_t* __restrict__ gcounts /* [n_genomes_padded][2], zeroed */) {
+  const uint64_t g = (uint64_t)bx * blockDim.x + threadIdx.x;
   if (g >= n_genomes_padded) return;
   const uint64_t unit = g >> 6;
   const int h = (int)((g >> 5) & 1), bit = (int)(g & 31);
-  const uint64_t vc0 = (uint64_t)blockIdx.y * kExpandGroup;
+  const uint64_t vc0 = (uint64_t)by * kExpandGroup;
   const uint64_t vc1 = min(vc0 + (uint64_t)kExpandGroup, n_vchunks);
   const uint64_t W = units * 4;
   uint32_t acc[2] = {0, 0};
@@ -147,6 +147,12 @@ k_expand_planes(const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_
   }
 #pragma unroll
   for (int p = 0; p < 2; ++p) if (acc[p]) atomicAdd(&gcounts[g * 2 + p], acc[p]);
+}
+
+__global__ void __launch_bounds__(256)
+k_expand_planes(const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units, uint64_t n_genomes_padded,
+                uint32_t* __restrict__ gcounts) {
+  expand_planes_block(blockIdx.x, blockIdx.y, planes, n_vchunks, units, n_genomes_padded, gcounts);
 }
 
 // multi-slice only: n0 = N - n1 - n2 - n3
