@@ -1,0 +1,244 @@
+// gram_i8.cuh -- K5: the genotype Gram matrix S = G G^T on the 5th-generation tensor cores (tcgen05.mma kind::i8, sm_100a).
+//
+// G[g][l] in {0,1,2} is the alt-allele dosage of genome g at locus l (code 3 -> 0), so S[i][j] = sum_l g_il g_jl is an exact
+// int32 for L < 2^29. The centred relationship matrix follows without floating point in the contraction:
+//     sum_l (g_il - 2 p_l)(g_jl - 2 p_l) = S[i][j] - 2 (Gp)_i - 2 (Gp)_j + 4 sum_l p_l^2
+// and, without code-3 cells, S also ties the tensor-core path to the popcount path: sum_l (g_il - g_jl)^2 = IBS1 + 4 IBS0
+// = S[i][i] + S[j][j] - 2 S[i][j]  (tests/test_gpu_parity.py).
+//
+// Operands never exist as int8 in HBM. Input is a genome-major 2-bit code matrix (16 loci per uint32, built once per
+// upload by k_codes16 from the sample-major planes); expander warps turn 32-bit words into 16 int8 each with two IMAD +
+// two LOP3 per four bytes (expand4) and write them straight into the 128-byte-swizzled K-major layout
+// tcgen05 reads. HBM/L2 traffic is therefore 1/4 byte per genotype, and the expansion costs 0.75 integer ops per operand
+// byte = 0.009 per MAC at a 128 x 256 tile -- under the 128-lane budget of an SM that retires 8,192 int8 MACs per clock.
+//
+// CTA = 9 warps: 0-3 epilogue (TMEM lane quadrants 0-3), 4 MMA issuer (one elected thread) + TMEM allocator, 5-8 expanders.
+// Work unit = (128 x 256 output tile, chunk of K); per K-stage of 128 loci: A 128 x 128 B, B 256 x 128 B (48 KB), 4 stages.
+//   expanders : wait empty[s] -> LDG (prefetched a stage ahead) -> expand -> st.shared (swizzled) -> fence.proxy.async -> arrive full[s]
+//   MMA       : wait full[s] -> 4 x tcgen05.mma (K = 32 each, descriptors advanced by 32 B inside the swizzle atom)
+//               -> tcgen05.commit empty[s]; after the unit's last stage tcgen05.commit tmem_full[a]
+//   epilogue  : wait tmem_full[a] -> tcgen05.ld 32x32b.x32 -> st / red.add to S (int32 adds commute: split-K is exact)
+//               -> arrive tmem_empty[a]. Two 256-column accumulators: the MMA of unit u+1 overlaps the epilogue of unit u.
+#pragma once
+#include "stream_common.cuh"
+
+namespace kgl {
+
+constexpr int kGramM = 128, kGramN = 256, kGramK = 128;         // tile; K-stage = 128 loci = 128 B per operand row
+constexpr int kGramStages = 4;
+constexpr int kGramThreads = 9 * 32;
+constexpr uint32_t kGramABytes = kGramM * kGramK, kGramBBytes = kGramN * kGramK;
+constexpr uint32_t kGramStageBytes = kGramABytes + kGramBBytes;  // 48 KB
+constexpr size_t kGramSmem = (size_t)kGramStages * kGramStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+struct GramParams {
+  const uint32_t* codes;      // [n_rows][pitch_words], 16 loci per word, 2 bits each, code 3 stored as 0; rows >= n_genomes zero
+  uint64_t pitch_words;       // multiple of 8 (one K-stage = 8 words)
+  uint32_t k_stages;          // ceil(n_loci / 128)
+  const uint2* tiles;         // (ti, tj): rows 128 ti .., columns 256 tj ..
+  uint32_t n_tiles;
+  uint32_t stages_per_chunk, n_chunks;
+  int32_t* out;               // [ld][ld]
+  uint64_t ld;
+};
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (UMMA::SmemDescriptor: start >> 4 in
+// [0,14), LBO [16,30) unused for swizzled K-major (1), SBO >> 4 in [32,46), version 1 at [46,48), SWIZZLE_128B = 2 at [61,64)).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA::InstrDescriptor for kind::i8: c_format S32 (2) at [4,6), a/b format unsigned 8-bit (0), K-major both, N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t kGramIdesc = (2u << 4) | ((uint32_t)(kGramN >> 3) << 17) | ((uint32_t)(kGramM >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kGramIdesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+// 16 two-bit codes -> 16 bytes
+// Four codes (one byte) -> four bytes in two carry-free multiply/mask steps: v * 0x1001 puts the high nibble at bit 16
+// (no overlap: v < 256), t * 0x41 puts the odd codes 6 bits up (t only has bits 0-3 and 16-19).
+__device__ __forceinline__ uint32_t expand4(uint32_t v) {
+  const uint32_t t = (v * 0x1001u) & 0x000F000Fu;
+  return (t * 0x41u) & 0x03030303u;
+}
+__device__ __forceinline__ uint4 expand16(uint32_t x) {
+  return make_uint4(expand4(x & 0xFFu), expand4((x >> 8) & 0xFFu), expand4((x >> 16) & 0xFFu), expand4(x >> 24));
+}
+
+__global__ void __launch_bounds__(kGramThreads, 1)
+k_gram_i8(const GramParams P) {
+  extern __shared__ unsigned char gram_smem_raw[];
+  // 1024-byte alignment for the 128-byte swizzle atoms
+  const uint32_t raw = smem_u32(gram_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* smem = gram_smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kGramStages * kGramStageBytes);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kGramStages);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * kGramStages), bar_tempty = smem_u32(bars + 2 * kGramStages + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGramStages + 4);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    for (int s = 0; s < kGramStages; ++s) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t n_units = P.n_tiles * P.n_chunks;
+
+  if (warp >= 5) {
+    // ===================== expanders: thread t owns A row t and B rows t, t + 128 =====================
+    const uint32_t t = tid - 5 * 32;
+    const uint32_t sw = t & 7;                                   // swizzle phase of rows t, t + 128 (both = t mod 8)
+    const uint32_t row_off = (t >> 3) * 1024 + sw * 128;
+    uint32_t s = 0, ph = 0, it = 0;
+    uint4 nx[3][2];                                              // next stage's 8 words of the three rows
+    auto fetch = [&](uint32_t u, uint32_t ks) {
+      const uint32_t chunk = u / P.n_tiles, tile = u - chunk * P.n_tiles;
+      const uint2 tc = P.tiles[tile];
+      const uint64_t w = (uint64_t)(chunk * P.stages_per_chunk + ks) * 8;
+      const uint64_t r0 = (uint64_t)tc.x * kGramM + t, r1 = (uint64_t)tc.y * kGramN + t;
+      const uint4* a = reinterpret_cast<const uint4*>(P.codes + r0 * P.pitch_words + w);
+      const uint4* b0 = reinterpret_cast<const uint4*>(P.codes + r1 * P.pitch_words + w);
+      const uint4* b1 = reinterpret_cast<const uint4*>(P.codes + (r1 + 128) * P.pitch_words + w);
+      nx[0][0] = __ldg(a); nx[0][1] = __ldg(a + 1);
+      nx[1][0] = __ldg(b0); nx[1][1] = __ldg(b0 + 1);
+      nx[2][0] = __ldg(b1); nx[2][1] = __ldg(b1 + 1);
+    };
+    uint32_t u = blockIdx.x, ks = 0;
+    auto stages_of = [&](uint32_t uu) {
+      const uint32_t chunk = uu / P.n_tiles;
+      const uint32_t k0 = chunk * P.stages_per_chunk;
+      return min(P.stages_per_chunk, P.k_stages - k0);
+    };
+    uint32_t ns = u < n_units ? stages_of(u) : 0;
+    if (u < n_units) fetch(u, 0);
+    while (u < n_units) {
+      uint4 cur[3][2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { cur[r][0] = nx[r][0]; cur[r][1] = nx[r][1]; }
+      // advance the cursor and prefetch
+      uint32_t u2 = u, ks2 = ks + 1, ns2 = ns;
+      if (ks2 == ns) { u2 = u + gridDim.x; ks2 = 0; ns2 = u2 < n_units ? stages_of(u2) : 0; }
+      if (u2 < n_units) fetch(u2, ks2);
+      if (it >= (uint32_t)kGramStages) mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      unsigned char* st = smem + (size_t)s * kGramStageBytes;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        unsigned char* row = st + (r == 0 ? 0u : kGramABytes + (r == 2 ? 128u * 128u : 0u)) + row_off;
+        const uint32_t wds[8] = {cur[r][0].x, cur[r][0].y, cur[r][0].z, cur[r][0].w, cur[r][1].x, cur[r][1].y, cur[r][1].z, cur[r][1].w};
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = expand16(wds[c]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar_full + 8 * s);
+      ++it;
+      if (++s == kGramStages) { s = 0; ph ^= 1; }
+      u = u2; ks = ks2; ns = ns2;
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    uint32_t s = 0, ph = 0, ui = 0;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const uint32_t chunk = u / P.n_tiles;
+      const uint32_t ns = min(P.stages_per_chunk, P.k_stages - chunk * P.stages_per_chunk);
+      const uint32_t a = ui & 1, aph = (ui >> 1) & 1;
+      if (ui >= 2) mbar_wait(bar_tempty + 8 * a, aph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + a * kGramN;
+      for (uint32_t k = 0; k < ns; ++k) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * kGramStageBytes, sb = sa + kGramABytes;
+#pragma unroll
+          for (uint32_t kk = 0; kk < kGramK / 32; ++kk)
+            tc_mma_i8(tmem_d, tc_smem_desc(sa + kk * 32), tc_smem_desc(sb + kk * 32), (k | kk) ? 1u : 0u);
+          tc_commit(bar_empty + 8 * s);
+          if (k + 1 == ns) tc_commit(bar_tfull + 8 * a);
+        }
+        __syncwarp();
+        if (++s == kGramStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue: warp q owns TMEM lanes 32 q .. 32 q + 31 =====================
+    uint32_t ui = 0;
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const uint32_t chunk = u / P.n_tiles, tile = u - chunk * P.n_tiles;
+      const uint2 tc = P.tiles[tile];
+      const uint32_t a = ui & 1, aph = (ui >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * a, aph);
+      tc_fence_after();
+      const uint64_t row = (uint64_t)tc.x * kGramM + warp * 32 + lane;
+      int32_t* orow = P.out + row * P.ld + (uint64_t)tc.y * kGramN;
+      const uint32_t taddr = tmem_base + a * kGramN + ((warp * 32) << 16);
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < (uint32_t)kGramN; c0 += 32) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (P.n_chunks > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (v[j]) atomicAdd(orow + c0 + j, (int32_t)v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * a);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
+// Genome-major 2-bit codes from the sample-major planes: codes[g][w16] holds loci 16 w16 .. 16 w16 + 15 of genome g,
+// code 3 -> 0. One thread per (genome, 32-locus word) -> two output words.
+__global__ void __launch_bounds__(256)
+k_codes16(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi, uint64_t n_gblocks, uint64_t n_words,
+          uint64_t pitch_words, uint32_t* __restrict__ codes) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // ((gb * n_words) + w) * 32 + lane
+  if (idx >= n_gblocks * n_words * 32) return;
+  const uint64_t lane = idx & 31, w = (idx >> 5) % n_words, gb = (idx >> 5) / n_words;
+  uint32_t lo = sm_lo[idx], hi = sm_hi[idx];
+  const uint32_t both = lo & hi;
+  lo &= ~both; hi &= ~both;
+  uint32_t out[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t a = (lo >> (16 * h)) & 0xFFFFu, b = (hi >> (16 * h)) & 0xFFFFu;
+    // spread 16 bits to even positions
+    a = (a | (a << 8)) & 0x00FF00FFu; a = (a | (a << 4)) & 0x0F0F0F0Fu; a = (a | (a << 2)) & 0x33333333u; a = (a | (a << 1)) & 0x55555555u;
+    b = (b | (b << 8)) & 0x00FF00FFu; b = (b | (b << 4)) & 0x0F0F0F0Fu; b = (b | (b << 2)) & 0x33333333u; b = (b | (b << 1)) & 0x55555555u;
+    out[h] = a | (b << 1);
+  }
+  uint32_t* o = codes + (gb * 32 + lane) * pitch_words + w * 2;
+  o[0] = out[0]; o[1] = out[1];
+}
+
+}  // namespace kgl
