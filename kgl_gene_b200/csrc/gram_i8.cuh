@@ -7,12 +7,13 @@
 // = S[i][i] + S[j][j] - 2 S[i][j]  (tests/test_gpu_parity.py).
 //
 // Operands never exist as int8 in HBM. Input is a genome-major 2-bit code matrix (16 loci per uint32, built once per
-// upload by k_codes16 from the sample-major planes); expander warps turn 32-bit words into 16 int8 each with two IMAD +
-// two LOP3 per four bytes (expand4) and write them straight into the 128-byte-swizzled K-major layout
-// tcgen05 reads. HBM/L2 traffic is therefore 1/4 byte per genotype, and the expansion costs 0.75 integer ops per operand
-// byte = 0.009 per MAC at a 128 x 256 tile -- under the 128-lane budget of an SM that retires 8,192 int8 MACs per clock.
+// upload by k_codes16 from the sample-major planes); expander warps turn every 32-bit word into 16 int8 with the byte
+// permuter (expand16: 9 integer ops per 16 bytes) and write them straight into the 128-byte-swizzled K-major layout
+// tcgen05 reads. HBM/L2 traffic is therefore 1/4 byte per genotype, and the expansion costs 0.56 integer ops per operand
+// byte = 0.0066 per MAC at a 128 x 256 tile.
 //
-// CTA = 9 warps: 0-3 epilogue (TMEM lane quadrants 0-3), 4 MMA issuer (one elected thread) + TMEM allocator, 5-8 expanders.
+// CTA = 17 warps: 0-3 epilogue (TMEM lane quadrants 0-3), 4 MMA issuer (one elected thread) + TMEM allocator, 5-16 expanders
+// (384 threads = one per operand row of a stage).
 // Work unit = (128 x 256 output tile, chunk of K); per K-stage of 128 loci: A 128 x 128 B, B 256 x 128 B (48 KB), 4 stages.
 //   expanders : wait empty[s] -> LDG (prefetched a stage ahead) -> expand -> st.shared (swizzled) -> fence.proxy.async -> arrive full[s]
 //   MMA       : wait full[s] -> 4 x tcgen05.mma (K = 32 each, descriptors advanced by 32 B inside the swizzle atom)
@@ -26,14 +27,21 @@ namespace kgl {
 
 constexpr int kGramM = 128, kGramN = 256, kGramK = 128;         // tile; K-stage = 128 loci = 128 B per operand row
 constexpr int kGramStages = 4;
-constexpr int kGramThreads = 9 * 32;
+constexpr int kGramExpWarps = 12;                                // expander warps: one thread per operand row of a stage (128 + 256)
+constexpr int kGramThreads = (5 + kGramExpWarps) * 32;
 constexpr uint32_t kGramABytes = kGramM * kGramK, kGramBBytes = kGramN * kGramK;
 constexpr uint32_t kGramStageBytes = kGramABytes + kGramBBytes;  // 48 KB
 constexpr size_t kGramSmem = (size_t)kGramStages * kGramStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
+// Code matrix layout ("row-block major"): uint32 [ld / 128][k_stages][128 rows][8 words]; a word holds 16 loci, 2 bits each,
+// code 3 stored as 0, rows >= n_genomes and loci >= n_loci zero. One K-stage of one 128-row block is 4 KB contiguous, so the
+// expanders' loads are fully coalesced (16 B per lane, 512 B per warp).
+__host__ __device__ inline uint64_t gram_code_index(uint64_t row, uint64_t word, uint64_t k_stages) {
+  return (((row >> 7) * k_stages + (word >> 3)) * 128 + (row & 127)) * 8 + (word & 7);
+}
+
 struct GramParams {
-  const uint32_t* codes;      // [n_rows][pitch_words], 16 loci per word, 2 bits each, code 3 stored as 0; rows >= n_genomes zero
-  uint64_t pitch_words;       // multiple of 8 (one K-stage = 8 words)
+  const uint32_t* codes;      // layout above
   uint32_t k_stages;          // ceil(n_loci / 128)
   const uint2* tiles;         // (ti, tj): rows 128 ti .., columns 256 tj ..
   uint32_t n_tiles;
@@ -62,15 +70,14 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kGramIdesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
-// 16 two-bit codes -> 16 bytes
-// Four codes (one byte) -> four bytes in two carry-free multiply/mask steps: v * 0x1001 puts the high nibble at bit 16
-// (no overlap: v < 256), t * 0x41 puts the odd codes 6 bits up (t only has bits 0-3 and 16-19).
-__device__ __forceinline__ uint32_t expand4(uint32_t v) {
-  const uint32_t t = (v * 0x1001u) & 0x000F000Fu;
-  return (t * 0x41u) & 0x03030303u;
-}
+// 16 two-bit codes -> 16 bytes with the byte permuter: a PRMT selector is four nibbles, so x & 0x3333 selects the bytes
+// {c0, c2, c4, c6} of the table {0,1,2,3} and (x >> 2) & 0x3333 the bytes {c1, c3, c5, c7}. The loci of a word come out
+// de-interleaved (even, odd, even, odd); A and B are expanded by the same function and a dot product does not care about
+// the order of its terms. 2 LOP3 + 3 SHF + 4 PRMT per 16 bytes.
 __device__ __forceinline__ uint4 expand16(uint32_t x) {
-  return make_uint4(expand4(x & 0xFFu), expand4((x >> 8) & 0xFFu), expand4((x >> 16) & 0xFFu), expand4(x >> 24));
+  const uint32_t m0 = x & 0x33333333u, m1 = (x >> 2) & 0x33333333u;
+  return make_uint4(__byte_perm(0x03020100u, 0u, m0), __byte_perm(0x03020100u, 0u, m1), __byte_perm(0x03020100u, 0u, m0 >> 16),
+                    __byte_perm(0x03020100u, 0u, m1 >> 16));
 }
 
 __global__ void __launch_bounds__(kGramThreads, 1)
@@ -87,7 +94,7 @@ k_gram_i8(const GramParams P) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (int s = 0; s < kGramStages; ++s) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kGramStages; ++s) { mbar_init(bar_full + 8 * s, kGramExpWarps * 32); mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -102,54 +109,53 @@ k_gram_i8(const GramParams P) {
   const uint32_t n_units = P.n_tiles * P.n_chunks;
 
   if (warp >= 5) {
-    // ===================== expanders: thread t owns A row t and B rows t, t + 128 =====================
+    // ===================== expanders: thread t owns one operand row of every stage: A row t (t < 128) or B row t - 128 ====
     const uint32_t t = tid - 5 * 32;
-    const uint32_t sw = t & 7;                                   // swizzle phase of rows t, t + 128 (both = t mod 8)
-    const uint32_t row_off = (t >> 3) * 1024 + sw * 128;
+    const uint32_t is_b = t >= (uint32_t)kGramM ? 1u : 0u;
+    const uint32_t r = is_b ? t - kGramM : t;                    // row inside the A tile / the B tile
+    const uint32_t sw = r & 7;                                   // swizzle phase of the row
+    const uint32_t row_off = (is_b ? kGramABytes : 0u) + (r >> 3) * 1024 + sw * 128;
     uint32_t s = 0, ph = 0, it = 0;
-    uint4 nx[3][2];                                              // next stage's 8 words of the three rows
-    auto fetch = [&](uint32_t u, uint32_t ks) {
-      const uint32_t chunk = u / P.n_tiles, tile = u - chunk * P.n_tiles;
-      const uint2 tc = P.tiles[tile];
-      const uint64_t w = (uint64_t)(chunk * P.stages_per_chunk + ks) * 8;
-      const uint64_t r0 = (uint64_t)tc.x * kGramM + t, r1 = (uint64_t)tc.y * kGramN + t;
-      const uint4* a = reinterpret_cast<const uint4*>(P.codes + r0 * P.pitch_words + w);
-      const uint4* b0 = reinterpret_cast<const uint4*>(P.codes + r1 * P.pitch_words + w);
-      const uint4* b1 = reinterpret_cast<const uint4*>(P.codes + (r1 + 128) * P.pitch_words + w);
-      nx[0][0] = __ldg(a); nx[0][1] = __ldg(a + 1);
-      nx[1][0] = __ldg(b0); nx[1][1] = __ldg(b0 + 1);
-      nx[2][0] = __ldg(b1); nx[2][1] = __ldg(b1 + 1);
-    };
-    uint32_t u = blockIdx.x, ks = 0;
+    constexpr int D = 3;                                          // register prefetch depth in stages (L2/HBM latency ~ one stage time)
+    uint4 nx[D][2];                                              // the row's eight words (128 loci) of a stage
+    struct Cursor { uint32_t u, ks, ns; };
     auto stages_of = [&](uint32_t uu) {
       const uint32_t chunk = uu / P.n_tiles;
-      const uint32_t k0 = chunk * P.stages_per_chunk;
-      return min(P.stages_per_chunk, P.k_stages - k0);
+      return min(P.stages_per_chunk, P.k_stages - chunk * P.stages_per_chunk);
     };
-    uint32_t ns = u < n_units ? stages_of(u) : 0;
-    if (u < n_units) fetch(u, 0);
-    while (u < n_units) {
-      uint4 cur[3][2];
+    auto advance = [&](Cursor& c) {
+      if (++c.ks == c.ns) { c.u += gridDim.x; c.ks = 0; c.ns = c.u < n_units ? stages_of(c.u) : 0; }
+    };
+    auto fetch = [&](const Cursor& c, uint4 (&dst)[2]) {
+      if (c.u >= n_units) return;
+      const uint32_t chunk = c.u / P.n_tiles, tile = c.u - chunk * P.n_tiles;
+      const uint2 tc = P.tiles[tile];
+      const uint64_t ks = (uint64_t)chunk * P.stages_per_chunk + c.ks;
+      const uint64_t block = is_b ? (uint64_t)2 * tc.y + (r >> 7) : (uint64_t)tc.x;
+      const uint4* src = reinterpret_cast<const uint4*>(P.codes + (block * P.k_stages + ks) * 1024 + (uint64_t)(r & 127) * 8);
+      dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+    };
+    Cursor cons{blockIdx.x, 0, 0}, pre;
+    cons.ns = cons.u < n_units ? stages_of(cons.u) : 0;
+    pre = cons;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) { cur[r][0] = nx[r][0]; cur[r][1] = nx[r][1]; }
-      // advance the cursor and prefetch
-      uint32_t u2 = u, ks2 = ks + 1, ns2 = ns;
-      if (ks2 == ns) { u2 = u + gridDim.x; ks2 = 0; ns2 = u2 < n_units ? stages_of(u2) : 0; }
-      if (u2 < n_units) fetch(u2, ks2);
-      if (it >= (uint32_t)kGramStages) mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      unsigned char* st = smem + (size_t)s * kGramStageBytes;
+    for (int j = 0; j < D; ++j) { fetch(pre, nx[j]); advance(pre); }
+    while (cons.u < n_units) {
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        unsigned char* row = st + (r == 0 ? 0u : kGramABytes + (r == 2 ? 128u * 128u : 0u)) + row_off;
-        const uint32_t wds[8] = {cur[r][0].x, cur[r][0].y, cur[r][0].z, cur[r][0].w, cur[r][1].x, cur[r][1].y, cur[r][1].z, cur[r][1].w};
+      for (int j = 0; j < D; ++j) {
+        if (cons.u >= n_units) break;
+        const uint32_t wds[8] = {nx[j][0].x, nx[j][0].y, nx[j][0].z, nx[j][0].w, nx[j][1].x, nx[j][1].y, nx[j][1].z, nx[j][1].w};
+        fetch(pre, nx[j]); advance(pre);
+        if (it >= (uint32_t)kGramStages) mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        unsigned char* row = smem + (size_t)s * kGramStageBytes + row_off;
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = expand16(wds[c]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_full + 8 * s);
+        ++it;
+        if (++s == kGramStages) { s = 0; ph ^= 1; }
+        advance(cons);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar_full + 8 * s);
-      ++it;
-      if (++s == kGramStages) { s = 0; ph ^= 1; }
-      u = u2; ks = ks2; ns = ns2;
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
@@ -221,7 +227,7 @@ k_gram_i8(const GramParams P) {
 // code 3 -> 0. One thread per (genome, 32-locus word) -> two output words.
 __global__ void __launch_bounds__(256)
 k_codes16(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi, uint64_t n_gblocks, uint64_t n_words,
-          uint64_t pitch_words, uint32_t* __restrict__ codes) {
+          uint64_t k_stages, uint64_t n_rows, uint32_t* __restrict__ codes /* zeroed */) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // ((gb * n_words) + w) * 32 + lane
   if (idx >= n_gblocks * n_words * 32) return;
   const uint64_t lane = idx & 31, w = (idx >> 5) % n_words, gb = (idx >> 5) / n_words;
@@ -237,8 +243,10 @@ k_codes16(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi
     b = (b | (b << 8)) & 0x00FF00FFu; b = (b | (b << 4)) & 0x0F0F0F0Fu; b = (b | (b << 2)) & 0x33333333u; b = (b | (b << 1)) & 0x55555555u;
     out[h] = a | (b << 1);
   }
-  uint32_t* o = codes + (gb * 32 + lane) * pitch_words + w * 2;
-  o[0] = out[0]; o[1] = out[1];
+  const uint64_t row = gb * 32 + lane;
+  if (row >= n_rows || w * 2 + 1 >= k_stages * 8) return;
+  codes[gram_code_index(row, w * 2, k_stages)] = out[0];
+  codes[gram_code_index(row, w * 2 + 1, k_stages)] = out[1];
 }
 
 }  // namespace kgl

@@ -12,14 +12,15 @@ using namespace kgl;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); std::exit(2); } } while (0)
 
 __global__ void k_fill_codes(uint32_t* codes, uint64_t n_rows, uint64_t pitch, uint64_t n_genomes, uint64_t n_loci, uint64_t seed) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rows * pitch) return;
-  const uint64_t g = i / pitch, w = i % pitch;
+  const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n_rows * pitch) return;
+  const uint64_t g = i0 / pitch, w = i0 % pitch;
+  const uint64_t i = gram_code_index(g, w, pitch / 8);
   uint32_t x = 0;
   if (g < n_genomes)
     for (int b = 0; b < 16; ++b) {
       if (w * 16 + b >= n_loci) break;
-      const uint64_t r = mix64(seed ^ (i * 16 + b));
+      const uint64_t r = mix64(seed ^ (i0 * 16 + b));
       const uint32_t u = (uint32_t)(r & 1023);
       const uint32_t code = u < 143 ? 1u : (u < 169 ? 2u : 0u);
       x |= code << (2 * b);
@@ -30,11 +31,9 @@ __global__ void k_fill_codes(uint32_t* codes, uint64_t n_rows, uint64_t pitch, u
 __global__ void k_ref_pairs(const uint32_t* codes, uint64_t pitch, const uint2* pairs, uint32_t n_pairs, long long* out) {
   const uint32_t p = blockIdx.x;
   if (p >= n_pairs) return;
-  const uint32_t* a = codes + (uint64_t)pairs[p].x * pitch;
-  const uint32_t* b = codes + (uint64_t)pairs[p].y * pitch;
   long long s = 0;
   for (uint64_t w = threadIdx.x; w < pitch; w += blockDim.x) {
-    const uint32_t x = a[w], y = b[w];
+    const uint32_t x = codes[gram_code_index(pairs[p].x, w, pitch / 8)], y = codes[gram_code_index(pairs[p].y, w, pitch / 8)];
     for (int k = 0; k < 16; ++k) s += (long long)((x >> (2 * k)) & 3) * ((y >> (2 * k)) & 3);
   }
   __shared__ long long sh[256];
@@ -44,11 +43,12 @@ __global__ void k_ref_pairs(const uint32_t* codes, uint64_t pitch, const uint2* 
 }
 
 int main(int argc, char** argv) {
-  uint64_t n_genomes = 2504, n_loci = 1100000; int reps = 3; uint32_t chunk_hint = 0;
+  uint64_t n_genomes = 2504, n_loci = 1100000; int reps = 3; uint32_t chunk_hint = 0; int skip = 0;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--genomes")) n_genomes = std::strtoull(argv[++i], nullptr, 10);
     else if (!std::strcmp(argv[i], "--loci")) n_loci = std::strtoull(argv[++i], nullptr, 10);
     else if (!std::strcmp(argv[i], "--reps")) reps = std::atoi(argv[++i]);
+    else if (!std::strcmp(argv[i], "--skip")) skip = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--chunk")) chunk_hint = (uint32_t)std::atoi(argv[++i]);
   }
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
@@ -66,8 +66,8 @@ int main(int argc, char** argv) {
   int32_t* d_out; CK(cudaMalloc(&d_out, ld * ld * 4));
   GramPlan pl = plan_gram((uint32_t)tiles.size(), k_stages, sms, chunk_hint);
   GramParams P{};
-  P.codes = d_codes; P.pitch_words = pitch; P.k_stages = k_stages; P.tiles = d_tiles; P.n_tiles = (uint32_t)tiles.size();
-  P.stages_per_chunk = pl.stages_per_chunk; P.n_chunks = pl.n_chunks; P.out = d_out; P.ld = ld;
+  P.codes = d_codes; P.k_stages = k_stages; P.tiles = d_tiles; P.n_tiles = (uint32_t)tiles.size();
+  P.stages_per_chunk = pl.stages_per_chunk; P.n_chunks = pl.n_chunks; P.out = d_out; P.ld = ld; (void)skip;
   std::printf("tiles %zu, chunks %u x %u stages, grid %u, smem %zu\n", tiles.size(), pl.n_chunks, pl.stages_per_chunk, pl.grid, kGramSmem);
   auto go = [&]() {
     if (pl.n_chunks > 1) CK(cudaMemsetAsync(d_out, 0, ld * ld * 4));
