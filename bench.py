@@ -346,6 +346,18 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def timed_local(ctx, torch, stream, fn, steps):
+    """CUDA-event timing of `steps` calls on this rank's stream (no cross-rank barrier)."""
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
 KINSHIP_METRIC = "kinship sample-pair-loci/s"
 LOP3_PER_CLK_SM = 62.45      # measured, profiles/r01_pipe_rates_kbench.log (kgl_gene_b200/csrc/tools/kbench.cu)
 POPC_PER_CLK_SM = 15.90
@@ -401,6 +413,31 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
                "d2h_bytes_per_step": int(h_tiles.numel() * 4), "ms_per_step": e_ms / 2, "steps": 2}
         t = h_tiles.numpy().view(np.uint32)
         assert np.array_equal(t[..., :3].sum(-1), t[..., 3]), "IBS0 + IBS1 + IBS2 != valid"
+    # tensor-core variant (K5): the dosage Gram matrix of the same population, int8 x int8 -> int32 on tcgen05. The contraction is
+    # not tile-sharded yet: every rank runs the whole matrix, rank 0 reports its own time (n_gpus 1 semantics).
+    grm = None
+    if rank == 0:
+        ctx.enqueue_gram()
+        torch.cuda.synchronize()
+        g_ms = timed_local(ctx, torch, stream, lambda: ctx.enqueue_gram(), steps)
+        gk_ms = ctx.last_gram_kernel_ms()
+        ld = (n + 255) // 256 * 256
+        n_tiles = sum(1 for ti in range(ld // 128) for tj in range(ti // 2, ld // 256))
+        k_stages = (kl + 127) // 128
+        ops = 2.0 * n_tiles * 128 * 256 * k_stages * 128
+        peak_tops = None
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak_tops = 2.0 * float(peaks.get("bf16_tflops_burst", peaks.get("bf16_tflops", 0.0))) or None
+        except Exception:
+            pass
+        peak_tops = peak_tops or 2.0 * 1608.9
+        grm = {"metric": "kinship sample-pair-loci/s (int8 Gram matrix on tcgen05)", "value": pair_loci / (g_ms * 1e-3), "unit": "sample-pair-loci/s",
+               "ms_per_step": g_ms, "n_gpus": 1, "kernel": "k_gram_i8 (tcgen05.mma kind::i8, TMEM accumulators, 128x256 tiles, in-kernel 2-bit -> int8 expansion)",
+               "roofline": {"bound": "tensor", "achieved": ops / (gk_ms * 1e-3) / 1e12, "peak": peak_tops, "unit": "int8 TOP/s",
+                            "frac": ops / (gk_ms * 1e-3) / 1e12 / peak_tops,
+                            "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 peak itself not measured by the driver)",
+                            "kernel_ms": gk_ms, "mma_only_ceiling_tops": 3512.0}}
     if rank != 0:
         return None
     # INT-pipe roofline of the tile kernel: 5 LOP3 + 1 POPC per executed pair-word (two-plane form: 3 for the two difference
@@ -417,7 +454,7 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
             "config": {"workload": f"pairwise IBS0/IBS1/IBS2/valid, {n} x {n} genomes over {kl} SNPs (BASELINE config 4 shape is 20M SNPs: "
                                    f"the same tile kernel, 18x more words per tile), upper-triangle 64x64 tiles dealt to {world} GPU(s)",
                        "tiles": int(n_up), "tiles_this_rank": int(mine), "missing_rate": 0.001},
-            "e2e": e2e, "gpu_launches": int(launches),
+            "e2e": e2e, "gpu_launches": int(launches), "grm_i8": grm,
             "roofline": {"bound": "int-pipe (ALU/LOP3)", "kernel": "k_ibs_tiles<false,2> (+ k_ibs_missing_fix, k_ibs_finalize)",
                          "achieved": achieved, "peak": peak, "unit": "executed pair-loci/s",
                          "frac": (achieved / peak) if achieved else None,

@@ -147,6 +147,15 @@ int kgl_b200_run_ibs(kgl_b200_ctx* ctx, uint64_t row_begin, uint64_t row_end, ui
 int kgl_b200_ibs_tile_grid(kgl_b200_ctx* ctx, uint64_t* tiles_per_side, uint64_t* n_upper_tiles);
 int kgl_b200_run_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count, uint32_t* out);
 
+/* Tensor-core variant of the pairwise path (BASELINE config 5): the dosage Gram matrix
+ * gram int32[n_genomes][n_genomes], gram[a][b] = sum over loci of g_a g_b with g in {0,1,2} (code 3 counts as 0: in the
+ * variant DB "no entry at the offset" is the reference genotype), contracted exactly in int8 x int8 -> int32 on
+ * tcgen05; and the centred relationship matrix grm double[n][n] = sum_l (g_a - 2 p_l)(g_b - 2 p_l) with p the AF column
+ * `pop` (absent AF -> 0), = gram - 2 (Gp)_a - 2 (Gp)_b + 4 sum p^2. Without code-3 cells gram[a][a] + gram[b][b] -
+ * 2 gram[a][b] = IBS1 + 4 IBS0 of kgl_b200_run_ibs. n_loci < 2^29. */
+int kgl_b200_run_gram(kgl_b200_ctx* ctx, int32_t* gram);
+int kgl_b200_run_grm(kgl_b200_ctx* ctx, uint32_t pop, double* grm);
+
 /* ---- resident / asynchronous building blocks (bench.py, multi-GPU drivers) ------------------------------------------ */
 /* Enqueue the fused pass on the context stream and return immediately; results stay in device buffers. */
 int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* ctx);
@@ -164,6 +173,9 @@ int kgl_b200_kernel_timer_read(kgl_b200_ctx* ctx, float* ms, uint32_t capacity, 
  * of the pairwise tile kernel (k_ibs_tiles). */
 int kgl_b200_enqueue_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count);
 int kgl_b200_ibs_tiles_buffer(kgl_b200_ctx* ctx, void** device_ptr, uint64_t* n_u32);
+/* Resident Gram contraction (the matrix stays on the device) and the milliseconds its tcgen05 kernel took. */
+int kgl_b200_enqueue_gram(kgl_b200_ctx* ctx);
+float kgl_b200_last_gram_kernel_ms(kgl_b200_ctx* ctx);
 int kgl_b200_ibs_timer_reset(kgl_b200_ctx* ctx);
 int kgl_b200_ibs_timer_read(kgl_b200_ctx* ctx, float* ms, uint32_t capacity, uint32_t* n);
 /* Copy the per-locus allele counts of the last fused pass to the host: uint32[n_loci][4]. */

@@ -28,6 +28,7 @@ EXPORTS = [
     "kgl_b200_set_genome_superpop", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
+    "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
@@ -62,6 +63,8 @@ def load_library() -> C.CDLL:
         lib.kgl_b200_launch_count.argtypes = [C.c_void_p]
         lib.kgl_b200_last_stream_kernel_ms.restype = C.c_float
         lib.kgl_b200_last_stream_kernel_ms.argtypes = [C.c_void_p]
+        lib.kgl_b200_last_gram_kernel_ms.restype = C.c_float
+        lib.kgl_b200_last_gram_kernel_ms.argtypes = [C.c_void_p]
         lib.kgl_b200_destroy.restype = None
         lib.kgl_b200_destroy.argtypes = [C.c_void_p]
         _lib = lib
@@ -211,6 +214,24 @@ class KglB200:
         out = np.zeros((row_end - row_begin, self.n_genomes, 4), dtype=np.uint32)
         self._check(self.lib.kgl_b200_run_ibs(self.h, C.c_uint64(row_begin), C.c_uint64(row_end), _ptr(out)), "run_ibs")
         return out
+
+    def gram(self) -> np.ndarray:
+        """Dosage Gram matrix int32[N][N] on the tensor cores (tcgen05 kind::i8)."""
+        out = np.zeros((self.n_genomes, self.n_genomes), dtype=np.int32)
+        self._check(self.lib.kgl_b200_run_gram(self.h, _ptr(out)), "run_gram")
+        return out
+
+    def grm(self, pop: int = 5) -> np.ndarray:
+        """Centred relationship matrix float64[N][N] for the AF column `pop`."""
+        out = np.zeros((self.n_genomes, self.n_genomes), dtype=np.float64)
+        self._check(self.lib.kgl_b200_run_grm(self.h, C.c_uint32(pop), _ptr(out)), "run_grm")
+        return out
+
+    def enqueue_gram(self):
+        self._check(self.lib.kgl_b200_enqueue_gram(self.h), "enqueue_gram")
+
+    def last_gram_kernel_ms(self) -> float:
+        return float(self.lib.kgl_b200_last_gram_kernel_ms(self.h))
 
     def ibs_tile_grid(self):
         side, n = C.c_uint64(), C.c_uint64()

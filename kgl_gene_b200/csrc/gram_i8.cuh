@@ -249,4 +249,73 @@ k_codes16(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi
   codes[gram_code_index(row, w * 2 + 1, k_stages)] = out[1];
 }
 
+// ---- rank-one terms of the centred matrix -----------------------------------------------------------------------------------
+// a[g] = sum_l p_l g_gl over the non-reference cells of genome g (lane per genome on the sample-major planes, the chunk's
+// frequencies in shared memory), in chunks of 2,048 loci that are then added in a fixed order.
+constexpr int kDotWords = 64;
+__global__ void __launch_bounds__(256)
+k_dosage_dot(const uint32_t* __restrict__ sm_lo, const uint32_t* __restrict__ sm_hi, uint64_t n_gblocks, uint64_t n_words, uint64_t n_loci,
+             const float* __restrict__ af_pop, double* __restrict__ chunk_out /* [n_chunks][n_gblocks * 32] */) {
+  __shared__ double s_p[kDotWords * 32];
+  const uint64_t w0 = (uint64_t)blockIdx.y * kDotWords;
+  for (int i = threadIdx.x; i < kDotWords * 32; i += 256) {
+    const uint64_t l = w0 * 32 + i;
+    double p = 0.0;
+    if (l < n_loci) { const float a = af_pop[l]; if (a == a) { p = (double)a; p = p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p); } }
+    s_p[i] = p;
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t gb = (uint64_t)blockIdx.x * 8 + warp;
+  if (gb >= n_gblocks) return;
+  double het = 0.0, hom = 0.0;
+  const uint64_t w1 = min(w0 + (uint64_t)kDotWords, n_words);
+  for (uint64_t w = w0; w < w1; ++w) {
+    const uint64_t o = (gb * n_words + w) * 32 + lane;
+    const uint32_t lo = sm_lo[o], hi = sm_hi[o], both = lo & hi;
+    uint32_t a = lo & ~both, b = hi & ~both;
+    const double* pw = s_p + (w - w0) * 32;
+    while (a) { const int i = __ffs(a) - 1; a &= a - 1; het += pw[i]; }
+    while (b) { const int i = __ffs(b) - 1; b &= b - 1; hom += pw[i]; }
+  }
+  chunk_out[(uint64_t)blockIdx.y * n_gblocks * 32 + gb * 32 + lane] = het + 2.0 * hom;
+}
+
+// gp[g] = sum of the chunks in order; gp[n_rows] = sum_l p_l^2 (block n_blocks - 1, fixed-order tree).
+__global__ void __launch_bounds__(256)
+k_dosage_reduce(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_rows, const float* __restrict__ af_pop, uint64_t n_loci,
+                double* __restrict__ gp) {
+  if (blockIdx.x == gridDim.x - 1) {
+    __shared__ double s[256];
+    double v = 0.0;
+    for (uint64_t l = threadIdx.x; l < n_loci; l += 256) {
+      const float a = af_pop[l];
+      if (a == a) { double p = (double)a; p = p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p); v += p * p; }
+    }
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) gp[n_rows] = s[0];
+    return;
+  }
+  const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (g >= n_rows) return;
+  double v = 0.0;
+  for (uint64_t c = 0; c < n_chunks; ++c) v += chunk_out[c * n_rows + g];
+  gp[g] = v;
+}
+
+// Upper-triangle tiles -> the caller's symmetric [n][n] matrix: int32 Gram matrix, or the centred double matrix
+// S - 2 (a_i + a_j) + 4 sum p^2.
+__global__ void __launch_bounds__(256)
+k_gram_finalize(const int32_t* __restrict__ gram, uint64_t ld, uint64_t n, const double* __restrict__ gp /* null: integer output */,
+                uint64_t gp_rows, void* __restrict__ out) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const uint64_t i = idx / n, j = idx % n;
+  const int32_t s = i <= j ? gram[i * ld + j] : gram[j * ld + i];
+  if (gp == nullptr) static_cast<int32_t*>(out)[idx] = s;
+  else static_cast<double*>(out)[idx] = ((double)s - 2.0 * (gp[i] + gp[j])) + 4.0 * gp[gp_rows];
+}
+
 }  // namespace kgl

@@ -9,6 +9,7 @@
 #include "misc_kernels.cuh"
 #include "ibs_launch.cuh"
 #include "post_kernels.cuh"
+#include "gram_launch.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -116,6 +117,15 @@ struct kgl_b200_ctx {
   int ibs_timer_used = 0;
   uint64_t ibs_last_count = 0;
   uint64_t ibs_tiles_key[4] = {~0ull, 0, 0, 0};   // the tile list on the device: {kind, first, stride, count}
+  // K5 (gram_i8.cuh): 2-bit code matrix in row-block-major layout, tile list, int32 Gram matrix, rank-one terms
+  DevBuf<uint32_t> d_codes16;
+  DevBuf<int32_t> d_gram;
+  DevBuf<uint2> d_gram_tiles;
+  DevBuf<double> d_gp_chunks, d_gp;
+  DevBuf<uint8_t> d_gram_out;
+  uint64_t gram_ld = 0, gram_tiles_ld = 0, gram_n_tiles = 0;
+  bool codes16_valid = false;
+  cudaEvent_t gram_e0 = nullptr, gram_e1 = nullptr;
   DevBuf<unsigned int> d_ticket;
   bool fused_tail = false;           // KGL_B200_FUSED_TAIL=1: the last block of k_post assembles the per-genome results (slower: one block, serial)
   bool tail_done = false;            // the last launch_count already assembled the per-genome results (fused tail)
@@ -547,6 +557,47 @@ int ibs_finalize(kgl_b200_ctx* c, uint32_t n_tiles, int mode, uint64_t row_begin
   return KGL_B200_OK;
 }
 
+// ---- K5: Gram matrix on the tensor cores -------------------------------------------------------------------------------
+int ensure_codes16(kgl_b200_ctx* c) {
+  int rc = ensure_sample_major(c); if (rc) return rc;
+  if (c->codes16_valid) return KGL_B200_OK;
+  c->gram_ld = (c->N + kGramN - 1) / kGramN * kGramN;
+  const uint64_t k_stages = (c->L + kGramK - 1) / kGramK;
+  const size_t words = (size_t)c->gram_ld * k_stages * 8;
+  KGL_CUDA(c, c->d_codes16.ensure(words));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_codes16.p, 0, words * 4, c->stream));
+  k_codes16<<<blocks_for((uint64_t)c->n_gblocks * c->n_words * 32, 256), 256, 0, c->stream>>>(c->d_sm_lo.p, c->d_sm_hi.p, c->n_gblocks, c->n_words,
+                                                                                              k_stages, c->gram_ld, c->d_codes16.p);
+  KGL_LAUNCH_CHECK(c);
+  c->codes16_valid = true;
+  return KGL_B200_OK;
+}
+
+int gram_compute(kgl_b200_ctx* c) {
+  int rc = ensure_codes16(c); if (rc) return rc;
+  const uint64_t ld = c->gram_ld;
+  if (c->gram_tiles_ld != ld) {
+    const std::vector<uint2> tiles = gram_upper_tiles(ld);
+    KGL_CUDA(c, c->d_gram_tiles.ensure(tiles.size()));
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_gram_tiles.p, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->gram_tiles_ld = ld; c->gram_n_tiles = tiles.size();
+  }
+  KGL_CUDA(c, c->d_gram.ensure((size_t)ld * ld));
+  const uint32_t k_stages = (uint32_t)((c->L + kGramK - 1) / kGramK);
+  const GramPlan pl = plan_gram((uint32_t)c->gram_n_tiles, k_stages, c->sm_count);
+  GramParams P{};
+  P.codes = c->d_codes16.p; P.k_stages = k_stages; P.tiles = c->d_gram_tiles.p; P.n_tiles = (uint32_t)c->gram_n_tiles;
+  P.stages_per_chunk = pl.stages_per_chunk; P.n_chunks = pl.n_chunks; P.out = c->d_gram.p; P.ld = ld;
+  if (pl.n_chunks > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_gram.p, 0, (size_t)ld * ld * 4, c->stream));
+  if (!c->gram_e0) { KGL_CUDA(c, cudaEventCreate(&c->gram_e0)); KGL_CUDA(c, cudaEventCreate(&c->gram_e1)); }
+  KGL_CUDA(c, cudaEventRecord(c->gram_e0, c->stream));
+  KGL_CUDA(c, launch_gram(P, pl, c->stream));
+  ++c->launches;
+  KGL_CUDA(c, cudaEventRecord(c->gram_e1, c->stream));
+  return KGL_B200_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -606,6 +657,9 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
   c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
+  c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
+  if (c->gram_e0) cudaEventDestroy(c->gram_e0);
+  if (c->gram_e1) cudaEventDestroy(c->gram_e1);
   for (cudaEvent_t e : c->timer_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ibs_timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -668,6 +722,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
   c->sm_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
+  c->codes16_valid = false;
   return KGL_B200_OK;
 }
 
@@ -1180,6 +1235,57 @@ int kgl_b200_ibs_timer_read(kgl_b200_ctx* c, float* ms, uint32_t capacity, uint3
   for (int i = 0; i < c->ibs_timer_used && k < capacity; ++i, ++k)
     KGL_CUDA(c, cudaEventElapsedTime(&ms[k], c->ibs_timer_ev[2 * i], c->ibs_timer_ev[2 * i + 1]));
   *n = k;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_enqueue_gram(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  if (c->L >= (1ull << 29)) return fail(c, KGL_B200_ERR_INVALID, "Gram matrix: more than 2^29 loci would overflow the int32 accumulators");
+  return gram_compute(c);
+}
+
+float kgl_b200_last_gram_kernel_ms(kgl_b200_ctx* c) {
+  if (!c || !c->gram_e1) return -1.0f;
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaEventSynchronize(c->gram_e1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, c->gram_e0, c->gram_e1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+int kgl_b200_run_gram(kgl_b200_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = kgl_b200_enqueue_gram(c); if (rc) return rc;
+  const size_t n2 = (size_t)c->N * c->N;
+  KGL_CUDA(c, c->d_gram_out.ensure(n2 * 4));
+  k_gram_finalize<<<blocks_for(n2, 256), 256, 0, c->stream>>>(c->d_gram.p, c->gram_ld, c->N, nullptr, 0, c->d_gram_out.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemcpyAsync(out, c->d_gram_out.p, n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_grm(kgl_b200_ctx* c, uint32_t pop, double* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->have_loci || c->loci_len != c->L) return fail(c, KGL_B200_ERR_STATE, "the centred matrix needs the allele frequencies (kgl_b200_upload_loci)");
+  if (pop >= c->n_pop) return fail(c, KGL_B200_ERR_INVALID, "population index out of range");
+  int rc = kgl_b200_enqueue_gram(c); if (rc) return rc;
+  const float* af_pop = c->d_af.p + (size_t)pop * c->L;
+  const uint64_t rows = c->n_gblocks * 32, n_chunks = (c->n_words + kDotWords - 1) / kDotWords;
+  KGL_CUDA(c, c->d_gp_chunks.ensure(n_chunks * rows));
+  KGL_CUDA(c, c->d_gp.ensure(rows + 1));
+  dim3 grid((unsigned)((c->n_gblocks + 7) / 8), (unsigned)n_chunks);
+  k_dosage_dot<<<grid, 256, 0, c->stream>>>(c->d_sm_lo.p, c->d_sm_hi.p, c->n_gblocks, c->n_words, c->L, af_pop, c->d_gp_chunks.p);
+  KGL_LAUNCH_CHECK(c);
+  k_dosage_reduce<<<blocks_for(rows, 256) + 1, 256, 0, c->stream>>>(c->d_gp_chunks.p, n_chunks, rows, af_pop, c->L, c->d_gp.p);
+  KGL_LAUNCH_CHECK(c);
+  const size_t n2 = (size_t)c->N * c->N;
+  KGL_CUDA(c, c->d_gram_out.ensure(n2 * 8));
+  k_gram_finalize<<<blocks_for(n2, 256), 256, 0, c->stream>>>(c->d_gram.p, c->gram_ld, c->N, c->d_gp.p, rows, c->d_gram_out.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemcpyAsync(out, c->d_gram_out.p, n2 * 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   return KGL_B200_OK;
 }
 

@@ -338,6 +338,39 @@ void kgl_oracle_ibs(const uint8_t* packed, size_t row_bytes, size_t n_genomes, s
   free(codes);
 }
 
+/* K5 checker: dosage Gram matrix S[a][b] = sum_l g_al g_bl with g in {0,1,2}, code 3 -> 0 (the DB's own convention: no entry at
+ * an offset = reference), and the centred form C[a][b] = sum_l (g_al - 2 p_l)(g_bl - 2 p_l) with p = clamp(AF,0,1)
+ * of one population column (absent AF -> 0). No reference routine exists (the GRM variant is ours). */
+void kgl_oracle_gram(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci, const float* af_pop /* nullable */,
+                     int32_t* gram, double* grm /* nullable */) {
+  uint8_t* d = (uint8_t*)malloc(n_genomes * n_loci + 1);
+  double* p = (double*)malloc((n_loci + 1) * sizeof(double));
+  for (size_t l = 0; l < n_loci; ++l) {
+    p[l] = (af_pop && !isnan(af_pop[l])) ? clamp01((double)af_pop[l]) : 0.0;
+    for (size_t g = 0; g < n_genomes; ++g) {
+      const unsigned c = cell_code(packed, row_bytes, l, g);
+      d[g * n_loci + l] = (uint8_t)(c == 3 ? 0 : c);
+    }
+  }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long ai = 0; ai < (long)n_genomes; ++ai) {
+    const size_t a = (size_t)ai;
+    for (size_t b = 0; b < n_genomes; ++b) {
+      const uint8_t* ga = d + a * n_loci;
+      const uint8_t* gb = d + b * n_loci;
+      long long s = 0;
+      double c = 0.0;
+      for (size_t l = 0; l < n_loci; ++l) {
+        s += (long long)ga[l] * gb[l];
+        if (grm) c += ((double)ga[l] - 2.0 * p[l]) * ((double)gb[l] - 2.0 * p[l]);
+      }
+      gram[a * n_genomes + b] = (int32_t)s;
+      if (grm) grm[a * n_genomes + b] = c;
+    }
+  }
+  free(d); free(p);
+}
+
 static inline uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ULL;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -64,6 +64,11 @@ void kgl_oracle_allele_count(const uint8_t* packed, size_t row_bytes, size_t n_g
 /* Pairwise IBS (no reference code; standard definitions). out u32[N][N][4] = ibs0, ibs1, ibs2, valid. */
 void kgl_oracle_ibs(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci, uint32_t* out);
 
+/* Dosage Gram matrix gram i32[N][N] = sum_l g_a g_b (code 3 -> 0) and, when af_pop and grm are given, the centred matrix
+ * grm f64[N][N] = sum_l (g_a - 2p)(g_b - 2p), p = clamp(af_pop[l], 0, 1), absent AF -> 0. No reference code. */
+void kgl_oracle_gram(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci, const float* af_pop,
+                     int32_t* gram, double* grm);
+
 /* Synthetic genotype law shared with the product's device generator (kgl_b200_synth_genotypes): counter-based
  * splitmix64 per cell, genotype drawn from {q^2+Fpq, 2pq(1-F), p^2+Fpq} (the law of
  * AlleleFreqVector::unadjustedAlleleClassFrequencies, kga_analysis_inbreed_freq.cpp:127-205). */

@@ -106,6 +106,20 @@ def ibs(pop) -> np.ndarray:
     return out
 
 
+def gram(pop, af_pop=None):
+    """(gram int32 [N][N], grm float64 [N][N] or None): dosage Gram matrix and its centred form for one AF column."""
+    n = pop.n_genomes
+    g = np.zeros((n, n), dtype=np.int32)
+    packed = np.ascontiguousarray(pop.packed)
+    if af_pop is None:
+        lib().kgl_oracle_gram(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(n), C.c_size_t(pop.n_loci), None, _p(g), None)
+        return g, None
+    af_pop = np.ascontiguousarray(af_pop, dtype=np.float32)
+    c = np.zeros((n, n), dtype=np.float64)
+    lib().kgl_oracle_gram(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(n), C.c_size_t(pop.n_loci), _p(af_pop), _p(g), _p(c))
+    return g, c
+
+
 def synth_genotypes(seed, n_genomes, n_loci, af, superpop, inbreeding, missing_rate=0.001, locus_base=0) -> np.ndarray:
     rb = 16 * ((n_genomes + 63) // 64)
     packed = np.zeros((n_loci, rb), dtype=np.uint8)

@@ -239,6 +239,41 @@ def test_ibs_full_width_properties(gpu):
     assert np.array_equal(full[..., :3].sum(-1), full[..., 3])
 
 
+@pytest.mark.parametrize("n,l,miss", [(150, 3001, 0.03), (1, 77, 0.0), (257, 130, 0.0), (300, 20000, 0.03), (64, 33000, 0.001)])
+def test_gram_tensor_core_matches_oracle(gpu, n, l, miss):
+    """K5: int8 x int8 -> int32 on tcgen05; bit-exact, and tied to the popcount path when nothing is coded 3."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(n, l, seed=100 + n, missing_rate=miss)
+    gpu.upload_population(pop)
+    want, want_c = O.gram(pop, pop.af[5])
+    got = gpu.gram()
+    assert np.array_equal(got, want)
+    got_c = gpu.grm(5)
+    assert np.allclose(got_c, want_c, rtol=1e-9, atol=1e-7)
+    if miss == 0.0:
+        ibs = gpu.ibs().astype(np.int64)
+        d = np.diag(got).astype(np.int64)
+        assert np.array_equal(d[:, None] + d[None, :] - 2 * got.astype(np.int64), ibs[..., 1] + 4 * ibs[..., 0])
+
+
+def test_gram_full_width_identity(gpu):
+    """chr22-shaped width on device-generated data without code-3 cells: the tensor-core and popcount paths must agree."""
+    from kgl_gene_b200.synth import make_genomes, make_loci
+    n, l = 2504, 50_000
+    offsets, af = make_loci(l, 79)
+    superpop, f = make_genomes(n, 79)
+    gpu.upload_loci(af, offsets)
+    gpu.set_genome_superpop(superpop)
+    gpu.synth_genotypes(79, n, l, f, missing_rate=0.0)
+    g = gpu.gram().astype(np.int64)
+    assert np.array_equal(g, g.T)
+    _, gc = gpu.allele_count()
+    assert np.array_equal(np.diag(g), (gc[:, 1] + 4 * gc[:, 2]).astype(np.int64))
+    ibs = gpu.ibs().astype(np.int64)
+    d = np.diag(g)
+    assert np.array_equal(d[:, None] + d[None, :] - 2 * g, ibs[..., 1] + 4 * ibs[..., 0])
+
+
 def test_device_generator_matches_numpy(gpu):
     from kgl_gene_b200.synth import make_genomes, make_loci, synth_codes
     from kgl_gene_b200.flatfile import pack_codes
