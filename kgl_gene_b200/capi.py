@@ -28,7 +28,7 @@ EXPORTS = [
     "kgl_b200_set_genome_superpop", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
-    "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms",
+    "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
@@ -214,6 +214,16 @@ class KglB200:
         out = np.zeros((row_end - row_begin, self.n_genomes, 4), dtype=np.uint32)
         self._check(self.lib.kgl_b200_run_ibs(self.h, C.c_uint64(row_begin), C.c_uint64(row_end), _ptr(out)), "run_ibs")
         return out
+
+    def binned_genome_counts(self, lower, upper, pop: int = 0, present_only: bool = True):
+        """(counts uint64[n_bins][N][4], rows uint64[n_bins]) -- CalcFWS' per-genome AlleleSummmary per AF bin."""
+        lo = np.ascontiguousarray(lower, dtype=np.float64)
+        hi = np.ascontiguousarray(upper, dtype=np.float64)
+        out = np.zeros((lo.shape[0], self.n_genomes, 4), dtype=np.uint64)
+        rows = np.zeros(lo.shape[0], dtype=np.uint64)
+        self._check(self.lib.kgl_b200_run_binned_genome_counts(self.h, C.c_uint32(pop), C.c_uint32(lo.shape[0]), _ptr(lo), _ptr(hi),
+                                                               C.c_int(int(present_only)), _ptr(out), _ptr(rows)), "run_binned_genome_counts")
+        return out, rows
 
     def gram(self) -> np.ndarray:
         """Dosage Gram matrix int32[N][N] on the tensor cores (tcgen05 kind::i8)."""

@@ -117,6 +117,12 @@ struct kgl_b200_ctx {
   int ibs_timer_used = 0;
   uint64_t ibs_last_count = 0;
   uint64_t ibs_tiles_key[4] = {~0ull, 0, 0, 0};   // the tile list on the device: {kind, first, stride, count}
+  // AF-bin passes (CalcFWS): row mask, its 64-row summaries, the all-genomes population tables
+  DevBuf<uint16_t> d_bin_flags, d_bin_sum64;
+  DevBuf<uint32_t> d_bin_popmask32, d_bin_state;   // d_bin_state: [0] all-selected flag (always 0), [1] rows in the bin
+  DevBuf<uint8_t> d_bin_need32, d_zero_superpop;
+  DevBuf<uint64_t> d_bin_out;
+  uint64_t bin_tables_n = 0, bin_tables_units = 0;
   // K5 (gram_i8.cuh): 2-bit code matrix in row-block-major layout, tile list, int32 Gram matrix, rank-one terms
   DevBuf<uint32_t> d_codes16;
   DevBuf<int32_t> d_gram;
@@ -314,10 +320,18 @@ int alloc_matrix(kgl_b200_ctx* c) {
 
 // The fused streaming pass + its sparse companions. raw: allele_count over all loci; otherwise over the selected loci.
 // Leaves d_gcounts {lo, hi}, d_n3, d_nz_rare, d_ecorr per genome and the per-locus counts.
+// Row mask that replaces the per-population selection flags of a pass: every genome belongs to "population 0" and a row
+// counts iff bit 0 of flags16 is set (the AF-bin passes of kgl_b200_run_binned_genome_counts).
+struct MaskOverride {
+  const uint16_t* flags16; const uint16_t* sum64; const uint32_t* popmask32; const uint8_t* need32;
+  const uint32_t* all_selected; const uint8_t* zero_superpop;
+};
+
 // tail_mode: what the last block of k_post assembles -- 0 nothing, 1 the moment partials (d_partials; + the Simple closed
 // form into d_results when simple_results), 2 the raw per-genome counts (d_genome_counts).
-int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false, int tail_mode = 0) {
-  int rc = build_unit_tables(c);
+int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false, int tail_mode = 0,
+                 const MaskOverride* mo = nullptr) {
+  int rc = mo ? KGL_B200_OK : build_unit_tables(c);
   if (rc) return rc;
   rc = build_dropped_index(c);
   if (rc) return rc;
@@ -341,11 +355,11 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   fill_stream_params(P, pl);
   P.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
   P.units = (uint32_t)c->units; P.n_loci = (uint32_t)c->L; P.n_genomes = (uint32_t)c->N;
-  P.flags16 = raw ? nullptr : c->d_flags16.p;
-  P.sum64 = raw ? nullptr : c->d_sum64.p;
-  P.popmask32 = reinterpret_cast<const uint32_t*>(c->d_popmask.p);     // little endian: u64 mask = {low half, high half}
-  P.need32 = c->d_need32.p;
-  P.n_pop = raw ? 1 : c->n_pop;
+  P.flags16 = mo ? mo->flags16 : (raw ? nullptr : c->d_flags16.p);
+  P.sum64 = mo ? mo->sum64 : (raw ? nullptr : c->d_sum64.p);
+  P.popmask32 = mo ? mo->popmask32 : reinterpret_cast<const uint32_t*>(c->d_popmask.p);     // little endian: u64 mask = {low half, high half}
+  P.need32 = mo ? mo->need32 : c->d_need32.p;
+  P.n_pop = (raw || mo) ? 1 : c->n_pop;
   P.locus_counts = want_locus_counts ? c->d_locus_counts.p : nullptr;
   P.planes = want_genome ? c->d_planes.p : nullptr;
   cudaEvent_t e0 = c->ev0, e1 = c->ev1;
@@ -372,7 +386,7 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   c->tail_done = false;
   if (want_genome) {
     const SparseOut so{c->d_n3, c->d_nz_rare, c->d_ecorr};
-    const uint16_t* fl = raw ? nullptr : c->d_flags16.p;
+    const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->d_flags16.p);
     const unsigned e_bx = blocks_for(c->Npad, 256), e_by = (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup);
     if (c->dropped_indexed || c->n_dropped == 0) {
       // one launch: counter expansion, indexed code-3 cells and rare-major rows side by side; the last block assembles
@@ -382,9 +396,10 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
       Q.e_bx = e_bx; Q.e_by = e_by;
       Q.keys = c->d_dropped.p; Q.seg = c->d_dropped_seg.p; Q.d_blocks = c->n_dropped ? (unsigned)((c->N + 1) / 2) : 0u;
       Q.rare_rows = c->d_rare_rows.p; Q.n_rare = c->d_n_rare.p; Q.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
-      Q.popmask = c->d_popmask.p; Q.r_blocks = raw ? 0u : 32u;
+      Q.popmask = c->d_popmask.p; Q.r_blocks = (raw || mo) ? 0u : 32u;
       Q.n_genomes = c->N; Q.n_loci = c->L; Q.n_pop = (int)c->n_pop;
-      Q.flags16 = fl; Q.all_selected = raw ? nullptr : c->d_n_rare.p + 1; Q.superpop = c->d_superpop.p; Q.af = c->d_af.p;
+      Q.flags16 = fl; Q.all_selected = mo ? mo->all_selected : (raw ? nullptr : c->d_n_rare.p + 1);
+      Q.superpop = mo ? mo->zero_superpop : c->d_superpop.p; Q.af = c->d_af.p;
       Q.so = so;
       Q.tail_mode = c->fused_tail ? tail_mode : 0; Q.unphased = c->unphased ? 1 : 0;
       Q.totals = c->d_totals.p; Q.partials = c->d_partials.p; Q.results = simple_results ? c->d_results.p : nullptr;
@@ -400,9 +415,9 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
       const uint64_t n128 = c->L * c->units;
       const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
       k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
-                                                   c->d_superpop.p, c->d_af.p, c->L, so);
+                                                   mo ? mo->zero_superpop : c->d_superpop.p, c->d_af.p, c->L, so);
       KGL_LAUNCH_CHECK(c);
-      if (!raw) {
+      if (!raw && !mo) {
         k_rare_rows<<<32, 256, 0, c->stream>>>(c->d_rare_rows.p, c->d_n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
                                                (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
                                                c->L, (int)c->n_pop, so);
@@ -657,6 +672,8 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
   c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
+  c->d_bin_flags.release(); c->d_bin_sum64.release(); c->d_bin_popmask32.release(); c->d_bin_state.release(); c->d_bin_need32.release();
+  c->d_zero_superpop.release(); c->d_bin_out.release();
   c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
   if (c->gram_e0) cudaEventDestroy(c->gram_e0);
   if (c->gram_e1) cudaEventDestroy(c->gram_e1);
@@ -1285,6 +1302,52 @@ int kgl_b200_run_grm(kgl_b200_ctx* c, uint32_t pop, double* out) {
   k_gram_finalize<<<blocks_for(n2, 256), 256, 0, c->stream>>>(c->d_gram.p, c->gram_ld, c->N, c->d_gp.p, rows, c->d_gram_out.p);
   KGL_LAUNCH_CHECK(c);
   KGL_CUDA(c, cudaMemcpyAsync(out, c->d_gram_out.p, n2 * 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+// CalcFWS::updateGenomeFWSMap (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:72-101) for all bins: per AF bin one masked pass of the
+// streaming kernel (the reference filters the population and rebuilds a VariantDBVariant per bin, :27-35).
+int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* c, uint32_t pop, uint32_t n_bins, const double* lower, const double* upper,
+                                      int present_only, uint64_t* genome_counts, uint64_t* bin_rows) {
+  if (!c || !lower || !upper || !genome_counts || n_bins == 0) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  if (!c->have_loci || c->loci_len != c->L) return fail(c, KGL_B200_ERR_STATE, "AF bins need the allele frequencies (kgl_b200_upload_loci)");
+  if (pop >= c->n_pop) return fail(c, KGL_B200_ERR_INVALID, "population index out of range");
+  // "variants of the population" = rows carried by at least one genome: needs the per-locus counts of a raw pass
+  if (present_only) { rc = launch_count(c, true, true, false); if (rc) return rc; }
+  if (c->bin_tables_n != c->N || c->bin_tables_units != c->units) {
+    std::vector<uint32_t> pm(c->units * 2, 0);
+    for (uint64_t g = 0; g < c->N; ++g) pm[g >> 5] |= 1u << (g & 31);
+    std::vector<uint8_t> need(c->units * 2, 1);
+    KGL_CUDA(c, c->d_bin_popmask32.ensure(pm.size()));
+    KGL_CUDA(c, c->d_bin_need32.ensure(need.size()));
+    KGL_CUDA(c, c->d_zero_superpop.ensure(c->Npad));
+    KGL_CUDA(c, c->d_bin_state.ensure(2));
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_bin_popmask32.p, pm.data(), pm.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_bin_need32.p, need.data(), need.size(), cudaMemcpyHostToDevice, c->stream));
+    KGL_CUDA(c, cudaMemsetAsync(c->d_zero_superpop.p, 0, c->Npad, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->bin_tables_n = c->N; c->bin_tables_units = c->units;
+  }
+  KGL_CUDA(c, c->d_bin_flags.ensure(c->padded_rows));
+  KGL_CUDA(c, c->d_bin_sum64.ensure(c->padded_rows / 64));
+  KGL_CUDA(c, c->d_bin_out.ensure((size_t)n_bins * c->N * 4 + n_bins));
+  const MaskOverride mo{c->d_bin_flags.p, c->d_bin_sum64.p, c->d_bin_popmask32.p, c->d_bin_need32.p, c->d_bin_state.p, c->d_zero_superpop.p};
+  for (uint32_t b = 0; b < n_bins; ++b) {
+    KGL_CUDA(c, cudaMemsetAsync(c->d_bin_state.p, 0, 8, c->stream));
+    k_bin_flags<<<blocks_for(c->padded_rows, 256), 256, 0, c->stream>>>(c->d_af.p + (size_t)pop * c->L, present_only ? c->d_locus_counts.p : nullptr,
+                                                                         c->L, c->padded_rows, lower[b], upper[b], c->d_bin_flags.p,
+                                                                         c->d_bin_sum64.p, c->d_bin_state.p + 1);
+    KGL_LAUNCH_CHECK(c);
+    rc = launch_count(c, false, false, true, false, 0, &mo); if (rc) return rc;
+    k_genome_counts_masked<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->d_bin_state.p + 1,
+                                                                         c->d_bin_out.p + (size_t)b * c->N * 4, c->d_bin_out.p + (size_t)n_bins * c->N * 4 + b);
+    KGL_LAUNCH_CHECK(c);
+  }
+  KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_bin_out.p, (size_t)n_bins * c->N * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (bin_rows) KGL_CUDA(c, cudaMemcpyAsync(bin_rows, c->d_bin_out.p + (size_t)n_bins * c->N * 4, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   return KGL_B200_OK;
 }

@@ -209,6 +209,50 @@ __global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, const 
   out[g * 4 + 0] = n_loci - n1 - n2 - n3; out[g * 4 + 1] = n1; out[g * 4 + 2] = n2; out[g * 4 + 3] = n3;
 }
 
+// ---- AF-bin passes (CalcFWS, kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:15-101) ------------------------------------------------
+// Row mask of one bin: the P7FrequencyFilter pair AF >= lower and not AF >= upper (kgl_variant_filter_Pf7.cpp:20-66; a
+// variant without the AF field passes both filters and is therefore in no bin); with locus_counts also "some genome
+// carries the variant" (a filtered PopulationDB only holds variants that occur). One thread per row, one warp-pair per
+// 64-row summary.
+__global__ void __launch_bounds__(256)
+k_bin_flags(const float* __restrict__ af_pop, const uint32_t* __restrict__ locus_counts /* nullable [L][4] */, uint64_t n_loci,
+            uint64_t padded_rows, double lower, double upper, uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64,
+            uint32_t* __restrict__ n_rows) {
+  __shared__ uint32_t s_bal[8];
+  const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = false;
+  if (l < n_loci) {
+    const float a = af_pop[l];
+    if (a == a) {
+      const double v = (double)a;
+      in = v >= lower && !(v >= upper);
+      if (in && locus_counts) in = (locus_counts[l * 4 + 1] + locus_counts[l * 4 + 2]) != 0;
+    }
+  }
+  if (l < padded_rows) flags16[l] = in ? 1u : 0u;
+  const uint32_t bal = __ballot_sync(kFull, in);
+  if ((threadIdx.x & 31) == 0) { s_bal[threadIdx.x >> 5] = bal; if (bal) atomicAdd(n_rows, (uint32_t)__popc(bal)); }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const uint64_t grp = (uint64_t)blockIdx.x * 4 + threadIdx.x;
+    if (grp * 64 < padded_rows) {
+      const uint32_t b0 = s_bal[threadIdx.x * 2], b1 = s_bal[threadIdx.x * 2 + 1];
+      const uint32_t all = (b0 == 0xFFFFFFFFu && b1 == 0xFFFFFFFFu) ? 1u : 0u, any = (b0 | b1) ? 1u : 0u;
+      sum64[grp] = (uint16_t)(all | (any << 8));
+    }
+  }
+}
+
+// AlleleSummmary of every genome over the masked rows: {referenceHomozygous_, minorHeterozygous_, minorHomozygous_, code 3}.
+__global__ void k_genome_counts_masked(const uint32_t* __restrict__ gcounts, const uint32_t* __restrict__ n3s, uint64_t n_genomes,
+                                       const uint32_t* __restrict__ n_rows, uint64_t* __restrict__ out, uint64_t* __restrict__ rows_out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0) *rows_out = *n_rows;
+  if (g >= n_genomes) return;
+  const uint64_t n3 = n3s[g], n1 = gcounts[g * 2] - n3, n2 = gcounts[g * 2 + 1] - n3;
+  out[g * 4 + 0] = (uint64_t)(*n_rows) - n1 - n2 - n3; out[g * 4 + 1] = n1; out[g * 4 + 2] = n2; out[g * 4 + 3] = n3;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Synthetic genotypes, bit-identical to kgl_gene_b200/synth.py (numpy) -- the tests compare the two cell by cell.
 // One thread = one 128-bit unit (64 genomes) of one locus row.

@@ -106,6 +106,26 @@ def ibs(pop) -> np.ndarray:
     return out
 
 
+def fws_bins(pop, af_col: int, bins, present_only=True):
+    """CalcFWS restated on the flat matrix with plain numpy loops (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:15-101; filter
+    kgl_variant_filter_Pf7.cpp:20-66): returns (counts uint64[n_bins][N][4], rows uint64[n_bins])."""
+    codes = pop.codes()                                  # [L][N]
+    af = pop.af[af_col].astype(np.float64)
+    present = ((codes == 1) | (codes == 2)).any(axis=1)
+    out = np.zeros((len(bins), pop.n_genomes, 4), dtype=np.uint64)
+    rows = np.zeros(len(bins), dtype=np.uint64)
+    for b, (lo, hi) in enumerate(bins):
+        with np.errstate(invalid="ignore"):
+            m = ~np.isnan(af) & (af >= lo) & ~(af >= hi)
+        if present_only:
+            m &= present
+        rows[b] = int(m.sum())
+        sub = codes[m]
+        for c in range(4):
+            out[b, :, c] = (sub == c).sum(axis=0)
+    return out, rows
+
+
 def gram(pop, af_pop=None):
     """(gram int32 [N][N], grm float64 [N][N] or None): dosage Gram matrix and its centred form for one AF column."""
     n = pop.n_genomes

@@ -274,6 +274,37 @@ def test_gram_full_width_identity(gpu):
     assert np.array_equal(d[:, None] + d[None, :] - 2 * g, ibs[..., 1] + 4 * ibs[..., 0])
 
 
+@pytest.mark.parametrize("n,l,miss,spectrum", [(131, 5000, 0.01, "sfs"), (500, 3000, 0.0, "dense"), (2504, 20000, 0.001, "sfs")])
+def test_fws_bins_match_oracle(gpu, n, l, miss, spectrum):
+    """N1: CalcFWS per-genome AlleleSummmary in the eleven AF bins + per-variant summaries + HeteroHomoZygous / F_IS."""
+    from kgl_gene_b200 import fws
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(n, l, seed=40 + n, missing_rate=miss, spectrum=spectrum, missing_af_rate=0.02)
+    gpu.upload_population(pop)
+    got = fws.calc_fws(gpu, pop=5)
+    want, want_rows = O.fws_bins(pop, 5, fws.FWS_BINS)
+    assert np.array_equal(got["bin_variants"], want_rows)
+    assert np.array_equal(got["genome_bins"], want[:, :, :3])
+    olc, ogc = O.allele_count(pop)
+    assert np.array_equal(got["variant_summary"], olc[:, :3])
+    # all loci, no presence filter: the bins partition the loci that have an AF value
+    allc, rows = gpu.binned_genome_counts([0.0], [2.0], pop=5, present_only=False)
+    assert int(rows[0]) == int((~np.isnan(pop.af[5])).sum())
+    w2, _ = O.fws_bins(pop, 5, [(0.0, 2.0)], present_only=False)
+    assert np.array_equal(allc, w2)
+    # HeteroHomoZygous bookkeeping on the raw per-genome counts
+    _, gc = gpu.allele_count()
+    hh = fws.hetero_homo_summary(gc)
+    codes = pop.codes()
+    assert np.array_equal(hh["total_variants"], ((codes == 1).sum(0) + 2 * (codes == 2).sum(0)).astype(np.uint64))
+    fis = fws.wrights_fis(hh, pop.superpop)
+    for k in np.unique(pop.superpop):
+        m = pop.superpop == k
+        h_exp = hh["heterozygous_reference_minor_alleles"][m].sum() / hh["total_variants"][m].sum()
+        h_obs = hh["heterozygous_reference_minor_alleles"][m] / hh["total_variants"][m]
+        assert np.allclose(fis[m], (h_exp - h_obs) / h_exp, rtol=1e-12)
+
+
 def test_device_generator_matches_numpy(gpu):
     from kgl_gene_b200.synth import make_genomes, make_loci, synth_codes
     from kgl_gene_b200.flatfile import pack_codes
