@@ -88,9 +88,21 @@ struct kgl_b200_ctx {
   bool units_valid = false;
 
   // per-locus preparation
-  DevBuf<uint16_t> d_flags16, d_sum64;
-  DevBuf<uint32_t> d_selw, d_rare_rows, d_n_rare;   // d_n_rare: [0] rare-row count, [1] all-selected flag
-  DevBuf<double> d_block_totals, d_totals;
+  // Outputs of k_locus_prepare, double-buffered: the preparation of pass i+1 runs on prep_stream while the sparse kernels
+  // of pass i still read the buffers of pass i (ensure_prepared). n_rare: [0] rare-row count, [1] all-selected flag,
+  // [2] blocks with an unselected row.
+  struct PrepSet {
+    DevBuf<uint16_t> flags16, sum64;
+    DevBuf<uint32_t> selw, rare_rows, n_rare;
+    DevBuf<double> block_totals, totals;
+    void release() { flags16.release(); sum64.release(); selw.release(); rare_rows.release(); n_rare.release(); block_totals.release(); totals.release(); }
+  } prep[2];
+  int par = 0;                                  // the set the current selection was prepared into
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t prep_done = nullptr, readers_done[2] = {nullptr, nullptr}, stream_pass_done = nullptr;
+  bool stream_pass_marked = false;
+  bool readers_marked[2] = {false, false};
+  bool inputs_async = false;                    // d_sel was last written by a kernel on the main stream without a host sync
   bool prep_valid = false, prep_has_w0 = false;
 
   // sample-major copy
@@ -209,11 +221,13 @@ uint64_t term_words(uint64_t n_loci) {
   return (nw + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
 }
 
-// Ticket counters of the "last block finishes the job" kernels: [0] k_locus_prepare, [1] k_post. They reset themselves.
+// Ticket counters of the "last block finishes the job" kernels: [0] k_post, [1], [2] k_locus_prepare per buffer set. They
+// reset themselves.
 cudaError_t ensure_tickets(kgl_b200_ctx* c) {
   if (c->d_ticket.p) return cudaSuccess;
-  cudaError_t e = c->d_ticket.ensure(2);
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_ticket.p, 0, 8, c->stream);
+  cudaError_t e = c->d_ticket.ensure(4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_ticket.p, 0, 16, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   return e;
 }
 
@@ -224,24 +238,47 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
   c->n_words = term_words(L);
   const uint64_t span = std::max<uint64_t>(c->padded_rows, c->n_words * 32);
   const unsigned nb = (unsigned)std::max<uint64_t>(1, (span + kPrepLociPerBlock - 1) / kPrepLociPerBlock);
-  KGL_CUDA(c, c->d_flags16.ensure(c->padded_rows));
-  KGL_CUDA(c, c->d_sum64.ensure(c->padded_rows / 64));
-  KGL_CUDA(c, c->d_selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
-  KGL_CUDA(c, c->d_rare_rows.ensure(L));
-  KGL_CUDA(c, c->d_n_rare.ensure(4));      // [0] rare-row count, [1] all-selected flag, [2] blocks with an unselected row
-  KGL_CUDA(c, c->d_block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
-  KGL_CUDA(c, c->d_totals.ensure(kMaxPop * TOT_COUNT));
+  if (!c->prep_stream) {
+    KGL_CUDA(c, cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
+    KGL_CUDA(c, cudaEventCreateWithFlags(&c->prep_done, cudaEventDisableTiming));
+    for (cudaEvent_t& e : c->readers_done) KGL_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    KGL_CUDA(c, cudaEventCreateWithFlags(&c->stream_pass_done, cudaEventDisableTiming));
+  }
   KGL_CUDA(c, ensure_tickets(c));
-  KGL_CUDA(c, cudaMemsetAsync(c->d_n_rare.p, 0, 16, c->stream));
+  // Everything enqueued on the main stream so far may read the current set: mark it, switch to the other set, and let the
+  // preparation start as soon as the readers of THAT set (marked one switch ago) are done -- i.e. concurrently with the
+  // tail (k_post, k_moment_partials) of the pass that is still running on the main stream.
+  KGL_CUDA(c, cudaEventRecord(c->readers_done[c->par], c->stream));
+  c->readers_marked[c->par] = true;
+  c->par ^= 1;
+  kgl_b200_ctx::PrepSet& S = c->prep[c->par];
+  KGL_CUDA(c, S.flags16.ensure(c->padded_rows));
+  KGL_CUDA(c, S.sum64.ensure(c->padded_rows / 64));
+  KGL_CUDA(c, S.selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
+  KGL_CUDA(c, S.rare_rows.ensure(L));
+  KGL_CUDA(c, S.n_rare.ensure(4));
+  KGL_CUDA(c, S.block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
+  KGL_CUDA(c, S.totals.ensure(kMaxPop * TOT_COUNT));
+  cudaStream_t ps = c->prep_stream;
+  if (c->readers_marked[c->par]) KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_done[c->par], 0));
+  // not before the last streaming kernel has finished: it owns every SM, a preparation block that slips in ahead of one of
+  // its persistent CTAs delays the whole pass
+  if (c->stream_pass_marked) KGL_CUDA(c, cudaStreamWaitEvent(ps, c->stream_pass_done, 0));
+  if (c->inputs_async) {            // the selection mask was just written by a kernel on the main stream
+    KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_done[c->par ^ 1], 0));
+    c->inputs_async = false;
+  }
+  KGL_CUDA(c, cudaMemsetAsync(S.n_rare.p, 0, 16, ps));
+  unsigned int* ticket = c->d_ticket.p + 1 + c->par;
   if (want_w0)
-    k_locus_prepare<true><<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
-                                                              c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
-                                                              c->d_block_totals.p, c->d_totals.p, c->d_n_rare.p + 1, c->d_ticket.p);
+    k_locus_prepare<true><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, S.flags16.p, S.sum64.p, S.selw.p,
+                                                       c->n_words, S.rare_rows.p, S.n_rare.p, S.block_totals.p, S.totals.p, S.n_rare.p + 1, ticket);
   else
-    k_locus_prepare<false><<<nb, kPrepThreads, 0, c->stream>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, c->d_flags16.p,
-                                                               c->d_sum64.p, c->d_selw.p, c->n_words, c->d_rare_rows.p, c->d_n_rare.p,
-                                                               c->d_block_totals.p, c->d_totals.p, c->d_n_rare.p + 1, c->d_ticket.p);
+    k_locus_prepare<false><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, S.flags16.p, S.sum64.p, S.selw.p,
+                                                        c->n_words, S.rare_rows.p, S.n_rare.p, S.block_totals.p, S.totals.p, S.n_rare.p + 1, ticket);
   KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaEventRecord(c->prep_done, ps));
+  KGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->prep_done, 0));
   c->prep_valid = true; c->prep_has_w0 = want_w0;
   return KGL_B200_OK;
 }
@@ -355,8 +392,8 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   fill_stream_params(P, pl);
   P.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
   P.units = (uint32_t)c->units; P.n_loci = (uint32_t)c->L; P.n_genomes = (uint32_t)c->N;
-  P.flags16 = mo ? mo->flags16 : (raw ? nullptr : c->d_flags16.p);
-  P.sum64 = mo ? mo->sum64 : (raw ? nullptr : c->d_sum64.p);
+  P.flags16 = mo ? mo->flags16 : (raw ? nullptr : c->prep[c->par].flags16.p);
+  P.sum64 = mo ? mo->sum64 : (raw ? nullptr : c->prep[c->par].sum64.p);
   P.popmask32 = mo ? mo->popmask32 : reinterpret_cast<const uint32_t*>(c->d_popmask.p);     // little endian: u64 mask = {low half, high half}
   P.need32 = mo ? mo->need32 : c->d_need32.p;
   P.n_pop = (raw || mo) ? 1 : c->n_pop;
@@ -377,6 +414,7 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   KGL_CUDA(c, launch_stream(P, pl, want_locus_counts, want_genome, c->stream));
   ++c->launches;
   KGL_CUDA(c, cudaEventRecord(e1, c->stream));
+  if (c->stream_pass_done) { KGL_CUDA(c, cudaEventRecord(c->stream_pass_done, c->stream)); c->stream_pass_marked = true; }
   c->ev_valid = true;
   c->last_e0 = e0; c->last_e1 = e1;
   if (want_locus_counts && pl.slices > 1) {
@@ -386,7 +424,7 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   c->tail_done = false;
   if (want_genome) {
     const SparseOut so{c->d_n3, c->d_nz_rare, c->d_ecorr};
-    const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->d_flags16.p);
+    const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->prep[c->par].flags16.p);
     const unsigned e_bx = blocks_for(c->Npad, 256), e_by = (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup);
     if (c->dropped_indexed || c->n_dropped == 0) {
       // one launch: counter expansion, indexed code-3 cells and rare-major rows side by side; the last block assembles
@@ -394,16 +432,16 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
       PostParams Q{};
       Q.planes = c->d_planes.p; Q.n_vchunks = pl.n_vchunks; Q.units = c->units; Q.n_genomes_padded = c->Npad; Q.gcounts = c->d_gcounts;
       Q.e_bx = e_bx; Q.e_by = e_by;
-      Q.keys = c->d_dropped.p; Q.seg = c->d_dropped_seg.p; Q.d_blocks = c->n_dropped ? (unsigned)((c->N + 1) / 2) : 0u;
-      Q.rare_rows = c->d_rare_rows.p; Q.n_rare = c->d_n_rare.p; Q.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
+      Q.keys = c->d_dropped.p; Q.seg = c->d_dropped_seg.p; Q.d_blocks = c->n_dropped ? (unsigned)((c->N + kDropGenomesPerBlock - 1) / kDropGenomesPerBlock) : 0u;
+      Q.rare_rows = c->prep[c->par].rare_rows.p; Q.n_rare = c->prep[c->par].n_rare.p; Q.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
       Q.popmask = c->d_popmask.p; Q.r_blocks = (raw || mo) ? 0u : 32u;
       Q.n_genomes = c->N; Q.n_loci = c->L; Q.n_pop = (int)c->n_pop;
-      Q.flags16 = fl; Q.all_selected = mo ? mo->all_selected : (raw ? nullptr : c->d_n_rare.p + 1);
+      Q.flags16 = fl; Q.all_selected = mo ? mo->all_selected : (raw ? nullptr : c->prep[c->par].n_rare.p + 1);
       Q.superpop = mo ? mo->zero_superpop : c->d_superpop.p; Q.af = c->d_af.p;
       Q.so = so;
       Q.tail_mode = c->fused_tail ? tail_mode : 0; Q.unphased = c->unphased ? 1 : 0;
-      Q.totals = c->d_totals.p; Q.partials = c->d_partials.p; Q.results = simple_results ? c->d_results.p : nullptr;
-      Q.genome_counts = c->d_genome_counts.p; Q.ticket = c->d_ticket.p + 1;
+      Q.totals = c->prep[c->par].totals.p; Q.partials = c->d_partials.p; Q.results = simple_results ? c->d_results.p : nullptr;
+      Q.genome_counts = c->d_genome_counts.p; Q.ticket = c->d_ticket.p;
       KGL_CUDA(c, ensure_tickets(c));
       k_post<<<e_bx * e_by + Q.d_blocks + Q.r_blocks, 256, 0, c->stream>>>(Q);
       KGL_LAUNCH_CHECK(c);
@@ -418,8 +456,8 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
                                                    mo ? mo->zero_superpop : c->d_superpop.p, c->d_af.p, c->L, so);
       KGL_LAUNCH_CHECK(c);
       if (!raw && !mo) {
-        k_rare_rows<<<32, 256, 0, c->stream>>>(c->d_rare_rows.p, c->d_n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
-                                               (uint32_t)c->units, (uint32_t)c->N, c->d_flags16.p, c->d_popmask.p, c->d_af.p,
+        k_rare_rows<<<32, 256, 0, c->stream>>>(c->prep[c->par].rare_rows.p, c->prep[c->par].n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
+                                               (uint32_t)c->units, (uint32_t)c->N, c->prep[c->par].flags16.p, c->d_popmask.p, c->d_af.p,
                                                c->L, (int)c->n_pop, so);
         KGL_LAUNCH_CHECK(c);
       }
@@ -436,7 +474,7 @@ int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results
   rc = launch_count(c, false, want_locus_counts, true, simple_results, 1);
   if (rc) return rc;
   if (c->tail_done) return KGL_B200_OK;
-  k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->d_totals.p, c->d_ecorr, c->d_nz_rare,
+  k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->prep[c->par].totals.p, c->d_ecorr, c->d_nz_rare,
                                                                   c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p,
                                                                   simple_results ? c->d_results.p : nullptr);
   KGL_LAUNCH_CHECK(c);
@@ -467,7 +505,7 @@ int launch_terms(kgl_b200_ctx* c, int n_out, const double* d_grid, int n_grid, T
   TermParams P{};
   P.sm_lo = c->d_sm_lo.p; P.sm_hi = c->d_sm_hi.p;
   P.n_gblocks = c->n_gblocks; P.n_words = c->n_words; P.n_loci = c->L; P.n_genomes = c->N;
-  P.selw = c->d_selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
+  P.selw = c->prep[c->par].selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
   P.unphased = c->unphased ? 1 : 0; P.words_per_chunk = tl.words_per_chunk;
   P.f = c->d_f.p; P.grid = d_grid; P.n_grid = n_grid;
   P.out = c->d_chunk_out.p; P.n_out = n_out; P.n_genomes_padded = c->Npad;
@@ -665,9 +703,9 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_need32.release();
-  c->d_popmask.release(); c->d_flags16.release(); c->d_selw.release(); c->d_block_totals.release(); c->d_totals.release();
+  c->d_popmask.release(); c->prep[0].release(); c->prep[1].release();
   c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_planes.release(); c->d_scratch.release();
-  c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release(); c->d_sum64.release(); c->d_rare_rows.release(); c->d_n_rare.release();
+  c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release();
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
@@ -681,6 +719,10 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   for (cudaEvent_t e : c->ibs_timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->prep_done) cudaEventDestroy(c->prep_done);
+  if (c->stream_pass_done) cudaEventDestroy(c->stream_pass_done);
+  for (cudaEvent_t e : c->readers_done) if (e) cudaEventDestroy(e);
+  if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -842,7 +884,7 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
     k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
                                                               c->d_sel.p, c->d_sel_counts.p);
     KGL_LAUNCH_CHECK(c);
-    c->prep_valid = false; c->h_sel_valid = false;
+    c->prep_valid = false; c->h_sel_valid = false; c->inputs_async = true;
     if (n_selected) {
       unsigned long long counts[kMaxPop];
       KGL_CUDA(c, cudaMemcpyAsync(counts, c->d_sel_counts.p, kMaxPop * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1022,7 +1064,7 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
     rc = enqueue_moments(c, c->opt.count_loci != 0, false, c->algo == KGL_B200_ALGO_RITLAND); if (rc) return rc;
     if (c->algo == KGL_B200_ALGO_RITLAND) {
       rc = launch_terms<TERM_RITLAND>(c, 3, nullptr, 0, tl); if (rc) return rc;
-      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 3, c->d_totals.p,
+      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 3, c->prep[c->par].totals.p,
                                                                        c->d_superpop.p, c->N, c->d_partials.p);
       KGL_LAUNCH_CHECK(c);
     }

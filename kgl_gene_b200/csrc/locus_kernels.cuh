@@ -40,17 +40,23 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t base = (uint64_t)blockIdx.x * kPrepLociPerBlock + (uint64_t)warp * 64 + lane;   // + it * 512 + half * 32
+  constexpr int kStep = (kPrepThreads / 32) * 64;                  // loci between two iterations of a warp
   uint32_t fl[kPrepIters][2], sbits[kPrepIters][2];
 #pragma unroll
   for (int it = 0; it < kPrepIters; ++it)
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
+      const uint64_t l = base + (uint64_t)(it * kStep + 32 * half);
       fl[it][half] = 0;
-      sbits[it][half] = (l < n_loci) ? (select_all ? 0x3fu : (uint32_t)sel[l]) : 0u;
+      sbits[it][half] = (l < n_loci) ? (select_all ? 0x3fu : (uint32_t)sel[l]) : 0u;     // 0 beyond n_loci: nothing is read there
     }
+  // rows past n_loci are never dereferenced: their selection bits are 0 and the frequency pointer is clamped to row 0
+  const uint64_t safe_base = base < n_loci ? base : 0;
+  const bool whole = base + (uint64_t)((kPrepIters - 1) * kStep + 32) < n_loci;          // all eight loci of this thread exist
 
-  for (int k = 0; k < kMaxPop; ++k) {
+  const float* afk = af + safe_base;
+  uint32_t* selw_k = selw;
+  for (int k = 0; k < n_pop; ++k, afk += n_loci, selw_k += n_words) {
     double acc[TOT_COUNT];
 #pragma unroll
     for (int j = 0; j < TOT_COUNT; ++j) acc[j] = 0.0;
@@ -60,17 +66,14 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
 #pragma unroll
     for (int it = 0; it < kPrepIters; ++it)
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
-        afv[it][half] = (k < n_pop && l < n_loci) ? __ldg(&af[(uint64_t)k * n_loci + l]) : 0.0f;
-      }
+      for (int half = 0; half < 2; ++half)
+        afv[it][half] = (whole || sbits[it][half]) ? __ldg(afk + (it * kStep + 32 * half)) : 0.0f;
 #pragma unroll
     for (int it = 0; it < kPrepIters; ++it)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
         bool on = false;
-        if (k < n_pop && ((sbits[it][half] >> k) & 1u)) {
+        if ((sbits[it][half] >> k) & 1u) {
           const LocusFreq f = locus_freq(afv[it][half]);
           if (f.valid) {
             on = true;
@@ -83,9 +86,9 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
           }
         }
         const uint32_t word = __ballot_sync(kFull, on);
-        if (lane == 0 && selw != nullptr && k < n_pop) {
-          const uint64_t w = l >> 5;
-          if (w < n_words) selw[(uint64_t)k * n_words + w] = word;
+        if (lane == 0 && selw != nullptr) {
+          const uint64_t w = (base + (uint64_t)(it * kStep + 32 * half)) >> 5;
+          if (w < n_words) selw_k[w] = word;
         }
       }
     acc[TOT_T] = (double)n_t; acc[TOT_TQ] = (double)n_tq;
@@ -95,6 +98,8 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
       if (lane == 0) s_tot[warp][k][j] = v;
     }
   }
+  if (lane < TOT_COUNT)
+    for (int k = n_pop; k < kMaxPop; ++k) s_tot[warp][k][lane] = 0.0;
 
 #pragma unroll
   for (int it = 0; it < kPrepIters; ++it) {

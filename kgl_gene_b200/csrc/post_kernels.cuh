@@ -33,14 +33,14 @@ struct PostParams {
 __global__ void __launch_bounds__(256)
 k_post(const PostParams P) {
   __shared__ int s_last;
-  // longest dependency chain first: rare rows (few blocks, a chain of five dependent loads), then the code-3 gathers, then
-  // the short expansion blocks
+  // the code-3 gathers are the long pole (one L2 sector per cell) and go first, in one wave; the rare rows (few blocks, a
+  // chain of five dependent loads) and the short expansion blocks fill in behind them
   const uint32_t b = blockIdx.x;
-  if (b < P.r_blocks) {
-    rare_rows_block(b, P.r_blocks, P.rare_rows, P.n_rare, P.packed, (uint32_t)P.units, (uint32_t)P.n_genomes,
+  if (b < P.d_blocks) {
+    dropped_apply_block(b, P.keys, P.seg, P.n_genomes, P.flags16, P.all_selected, P.superpop, P.af, P.n_loci, P.so);
+  } else if (b < P.d_blocks + P.r_blocks) {
+    rare_rows_block(b - P.d_blocks, P.r_blocks, P.rare_rows, P.n_rare, P.packed, (uint32_t)P.units, (uint32_t)P.n_genomes,
                     P.flags16, P.popmask, P.af, P.n_loci, P.n_pop, P.so);
-  } else if (b < P.r_blocks + P.d_blocks) {
-    dropped_apply_block(b - P.r_blocks, P.keys, P.seg, P.n_genomes, P.flags16, P.all_selected, P.superpop, P.af, P.n_loci, P.so);
   } else {
     const uint32_t e = b - P.r_blocks - P.d_blocks;
     expand_planes_block(e % P.e_bx, e / P.e_bx, P.planes, P.n_vchunks, P.units, P.n_genomes_padded, P.gcounts);

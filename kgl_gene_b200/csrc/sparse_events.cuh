@@ -90,35 +90,37 @@ k_dropped_segments(const DroppedKey* __restrict__ keys, uint64_t n_keys, uint64_
   seg[g] = lo;
 }
 
-// Two genomes per block, four warps per genome over the genome's row-sorted dropped cells; the partial sums are combined
+// Four genomes per block, two warps per genome over the genome's row-sorted dropped cells; the partial sums are combined
 // in a fixed order, so the result does not depend on scheduling. flags16 == null: raw mode (allele_count) -- every
 // code-3 cell counts, no frequency corrections. Writes n3[g]; adds the class frequencies of the selected dropped loci
 // to ecorr[g].
+constexpr int kDropGenomesPerBlock = 4;          // 64 threads (two warps) per genome: N / 4 blocks fit the machine in one wave
 __device__ __forceinline__ void
 dropped_apply_block(uint32_t block, const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
                     const uint16_t* __restrict__ flags16, const uint32_t* __restrict__ all_selected,
                     const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
-  __shared__ double s_sum[2][4][2];
-  __shared__ uint32_t s_n[2][4];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, half = tid >> 7, w4 = (tid >> 5) & 3, t128 = tid & 127;
-  const uint64_t g = (uint64_t)block * 2 + half;
+  constexpr int GPB = kDropGenomesPerBlock, TPG = 256 / GPB, WPG = TPG / 32;
+  __shared__ double s_sum[GPB][WPG][2];
+  __shared__ uint32_t s_n[GPB][WPG];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, gi = tid / TPG, wi = (tid % TPG) >> 5, tl = tid % TPG;
+  const uint64_t g = (uint64_t)block * GPB + gi;
   const bool raw = flags16 == nullptr;
   uint32_t n = 0;
   double sa = 0.0, sm = 0.0;
   if (g < n_genomes) {
     const uint64_t i0 = seg[g], i1 = seg[g + 1];
     if (raw) {
-      n = (t128 == 0) ? (uint32_t)(i1 - i0) : 0u;
+      n = (tl == 0) ? (uint32_t)(i1 - i0) : 0u;
     } else {
       const int k = superpop[g];
       const float* afk = af + (uint64_t)k * n_loci;
       const bool all_sel = all_selected[0] != 0;       // every row selected & valid for every population: skip the flag gather
       // four cells per thread and trip: the key, flag and frequency gathers of a trip are independent and overlap
-      for (uint64_t i = i0 + t128; i < i1; i += 512) {
+      for (uint64_t i = i0 + tl; i < i1; i += 4 * TPG) {
         uint32_t row[4], fl[4];
         float fa[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) row[j] = (i + 128 * j < i1) ? (uint32_t)keys[i + 128 * j] : 0xFFFFFFFFu;
+        for (int j = 0; j < 4; ++j) row[j] = (i + TPG * j < i1) ? (uint32_t)keys[i + TPG * j] : 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < 4; ++j) fl[j] = (row[j] == 0xFFFFFFFFu) ? 0u : (all_sel ? 0xFFu : (uint32_t)flags16[row[j]]);
 #pragma unroll
@@ -136,14 +138,17 @@ dropped_apply_block(uint32_t block, const DroppedKey* __restrict__ keys, const u
   }
   n = __reduce_add_sync(kFull, n);
   sa = warp_sum(sa); sm = warp_sum(sm);
-  if (lane == 0) { s_n[half][w4] = n; s_sum[half][w4][0] = sa; s_sum[half][w4][1] = sm; }
+  if (lane == 0) { s_n[gi][wi] = n; s_sum[gi][wi][0] = sa; s_sum[gi][wi][1] = sm; }
   __syncthreads();
-  if (t128 == 0 && g < n_genomes) {
-    const uint32_t nn = s_n[half][0] + s_n[half][1] + s_n[half][2] + s_n[half][3];
+  if (tl == 0 && g < n_genomes) {
+    uint32_t nn = 0;
+    double ta = 0.0, tm = 0.0;
+#pragma unroll
+    for (int w = 0; w < WPG; ++w) { nn += s_n[gi][w]; ta += s_sum[gi][w][0]; tm += s_sum[gi][w][1]; }   // fixed order
     out.n3[g] = nn;
     if (nn && !raw) {
-      atomicAdd(&out.ecorr[g * 2 + 0], ((s_sum[half][0][0] + s_sum[half][1][0]) + s_sum[half][2][0]) + s_sum[half][3][0]);
-      atomicAdd(&out.ecorr[g * 2 + 1], ((s_sum[half][0][1] + s_sum[half][1][1]) + s_sum[half][2][1]) + s_sum[half][3][1]);
+      atomicAdd(&out.ecorr[g * 2 + 0], ta);
+      atomicAdd(&out.ecorr[g * 2 + 1], tm);
     }
   }
 }
