@@ -413,27 +413,35 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
                "d2h_bytes_per_step": int(h_tiles.numel() * 4), "ms_per_step": e_ms / 2, "steps": 2}
         t = h_tiles.numpy().view(np.uint32)
         assert np.array_equal(t[..., :3].sum(-1), t[..., 3]), "IBS0 + IBS1 + IBS2 != valid"
-    # tensor-core variant (K5): the dosage Gram matrix of the same population, int8 x int8 -> int32 on tcgen05. The contraction is
-    # not tile-sharded yet: every rank runs the whole matrix, rank 0 reports its own time (n_gpus 1 semantics).
+    # tensor-core variant (K5): the dosage Gram matrix of the same population, int8 x int8 -> int32 on tcgen05. At N > 1 the
+    # 128 x 256 tiles are dealt to the ranks and the int32 matrix is assembled with one NCCL all-reduce (26 MB at 2,504 genomes).
+    from kgl_gene_b200.shards import allreduce_gram
+
+    def gram_step():
+        ctx.enqueue_gram_tiles(rank, world)
+        if world > 1:
+            allreduce_gram(ctx, dev)
+
+    gram_step()
+    g_ms = timed(gram_step, steps, 1) / steps
     grm = None
     if rank == 0:
-        ctx.enqueue_gram()
-        torch.cuda.synchronize()
-        g_ms = timed_local(ctx, torch, stream, lambda: ctx.enqueue_gram(), steps)
         gk_ms = ctx.last_gram_kernel_ms()
         ld = (n + 255) // 256 * 256
-        n_tiles = sum(1 for ti in range(ld // 128) for tj in range(ti // 2, ld // 256))
+        n_tiles_all = sum(1 for ti in range(ld // 128) for tj in range(ti // 2, ld // 256))
+        n_tiles = len(range(rank, n_tiles_all, world))
         k_stages = (kl + 127) // 128
         ops = 2.0 * n_tiles * 128 * 256 * k_stages * 128
         peak_tops = None
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak_tops = 2.0 * float(peaks.get("bf16_tflops_burst", peaks.get("bf16_tflops", 0.0))) or None
+            peak_tops = 2.0 * float(peaks.get("bf16_tflops", 0.0)) or None
         except Exception:
             pass
         peak_tops = peak_tops or 2.0 * 1608.9
         grm = {"metric": "kinship sample-pair-loci/s (int8 Gram matrix on tcgen05)", "value": pair_loci / (g_ms * 1e-3), "unit": "sample-pair-loci/s",
-               "ms_per_step": g_ms, "n_gpus": 1, "kernel": "k_gram_i8 (tcgen05.mma kind::i8, TMEM accumulators, 128x256 tiles, in-kernel 2-bit -> int8 expansion)",
+               "ms_per_step": g_ms, "n_gpus": world, "scaling": "strong",
+               "kernel": "k_gram_i8 (tcgen05.mma kind::i8, TMEM accumulators, 128x256 tiles, in-kernel 2-bit -> int8 expansion)",
                "roofline": {"bound": "tensor", "achieved": ops / (gk_ms * 1e-3) / 1e12, "peak": peak_tops, "unit": "int8 TOP/s",
                             "frac": ops / (gk_ms * 1e-3) / 1e12 / peak_tops,
                             "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 peak itself not measured by the driver)",

@@ -28,7 +28,7 @@ EXPORTS = [
     "kgl_b200_set_genome_superpop", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
-    "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms",
+    "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
@@ -239,6 +239,19 @@ class KglB200:
 
     def enqueue_gram(self):
         self._check(self.lib.kgl_b200_enqueue_gram(self.h), "enqueue_gram")
+
+    def enqueue_gram_tiles(self, first: int, stride: int):
+        self._check(self.lib.kgl_b200_enqueue_gram_tiles(self.h, C.c_uint64(first), C.c_uint64(stride)), "enqueue_gram_tiles")
+
+    def gram_buffer(self):
+        p, n, ld = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.kgl_b200_gram_buffer(self.h, C.byref(p), C.byref(n), C.byref(ld)), "gram_buffer")
+        return int(p.value), int(n.value), int(ld.value)
+
+    def fetch_gram(self) -> np.ndarray:
+        out = np.zeros((self.n_genomes, self.n_genomes), dtype=np.int32)
+        self._check(self.lib.kgl_b200_fetch_gram(self.h, _ptr(out)), "fetch_gram")
+        return out
 
     def last_gram_kernel_ms(self) -> float:
         return float(self.lib.kgl_b200_last_gram_kernel_ms(self.h))

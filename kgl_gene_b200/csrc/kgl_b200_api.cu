@@ -141,7 +141,7 @@ struct kgl_b200_ctx {
   DevBuf<uint2> d_gram_tiles;
   DevBuf<double> d_gp_chunks, d_gp;
   DevBuf<uint8_t> d_gram_out;
-  uint64_t gram_ld = 0, gram_tiles_ld = 0, gram_n_tiles = 0;
+  uint64_t gram_ld = 0, gram_tiles_ld = 0, gram_n_tiles = 0, gram_first = 0, gram_stride = 1;
   bool codes16_valid = false;
   cudaEvent_t gram_e0 = nullptr, gram_e1 = nullptr;
   DevBuf<unsigned int> d_ticket;
@@ -626,27 +626,32 @@ int ensure_codes16(kgl_b200_ctx* c) {
   return KGL_B200_OK;
 }
 
-int gram_compute(kgl_b200_ctx* c) {
+// Tiles first, first + stride, ... of the upper-triangle tile list (rank r of R: first = r, stride = R); the rest of the
+// matrix is left zero so that a SUM all-reduce of the int32 matrix over the ranks assembles it.
+int gram_compute(kgl_b200_ctx* c, uint64_t first = 0, uint64_t stride = 1) {
   int rc = ensure_codes16(c); if (rc) return rc;
   const uint64_t ld = c->gram_ld;
-  if (c->gram_tiles_ld != ld) {
-    const std::vector<uint2> tiles = gram_upper_tiles(ld);
+  if (c->gram_tiles_ld != ld || c->gram_first != first || c->gram_stride != stride) {
+    const std::vector<uint2> all = gram_upper_tiles(ld);
+    std::vector<uint2> tiles;
+    for (uint64_t t = first; t < all.size(); t += stride) tiles.push_back(all[t]);
+    if (tiles.empty()) tiles.push_back(all[0]);              // more ranks than tiles: nothing is launched (gram_n_tiles = 0)
+    c->gram_first = first; c->gram_stride = stride;
     KGL_CUDA(c, c->d_gram_tiles.ensure(tiles.size()));
     KGL_CUDA(c, cudaMemcpyAsync(c->d_gram_tiles.p, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
     KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->gram_tiles_ld = ld; c->gram_n_tiles = tiles.size();
+    c->gram_tiles_ld = ld; c->gram_n_tiles = first < all.size() ? tiles.size() : 0;
   }
   KGL_CUDA(c, c->d_gram.ensure((size_t)ld * ld));
   const uint32_t k_stages = (uint32_t)((c->L + kGramK - 1) / kGramK);
-  const GramPlan pl = plan_gram((uint32_t)c->gram_n_tiles, k_stages, c->sm_count);
+  const GramPlan pl = plan_gram((uint32_t)std::max<uint64_t>(c->gram_n_tiles, 1), k_stages, c->sm_count);
   GramParams P{};
   P.codes = c->d_codes16.p; P.k_stages = k_stages; P.tiles = c->d_gram_tiles.p; P.n_tiles = (uint32_t)c->gram_n_tiles;
   P.stages_per_chunk = pl.stages_per_chunk; P.n_chunks = pl.n_chunks; P.out = c->d_gram.p; P.ld = ld;
-  if (pl.n_chunks > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_gram.p, 0, (size_t)ld * ld * 4, c->stream));
+  if (pl.n_chunks > 1 || stride > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_gram.p, 0, (size_t)ld * ld * 4, c->stream));
   if (!c->gram_e0) { KGL_CUDA(c, cudaEventCreate(&c->gram_e0)); KGL_CUDA(c, cudaEventCreate(&c->gram_e1)); }
   KGL_CUDA(c, cudaEventRecord(c->gram_e0, c->stream));
-  KGL_CUDA(c, launch_gram(P, pl, c->stream));
-  ++c->launches;
+  if (c->gram_n_tiles > 0) { KGL_CUDA(c, launch_gram(P, pl, c->stream)); ++c->launches; }
   KGL_CUDA(c, cudaEventRecord(c->gram_e1, c->stream));
   return KGL_B200_OK;
 }
@@ -1297,12 +1302,36 @@ int kgl_b200_ibs_timer_read(kgl_b200_ctx* c, float* ms, uint32_t capacity, uint3
   return KGL_B200_OK;
 }
 
-int kgl_b200_enqueue_gram(kgl_b200_ctx* c) {
+int kgl_b200_enqueue_gram_tiles(kgl_b200_ctx* c, uint64_t first, uint64_t stride) {
   if (!c) return KGL_B200_ERR_INVALID;
+  if (stride == 0 || first >= stride) return fail(c, KGL_B200_ERR_INVALID, "need first < stride");
   int rc = use_device(c); if (rc) return rc;
   rc = require_population(c, false); if (rc) return rc;
   if (c->L >= (1ull << 29)) return fail(c, KGL_B200_ERR_INVALID, "Gram matrix: more than 2^29 loci would overflow the int32 accumulators");
-  return gram_compute(c);
+  return gram_compute(c, first, stride);
+}
+
+int kgl_b200_enqueue_gram(kgl_b200_ctx* c) { return kgl_b200_enqueue_gram_tiles(c, 0, 1); }
+
+int kgl_b200_gram_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_int32, uint64_t* ld) {
+  if (!c || !device_ptr || !n_int32) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->d_gram.p) return fail(c, KGL_B200_ERR_STATE, "enqueue_gram first");
+  *device_ptr = c->d_gram.p; *n_int32 = c->gram_ld * c->gram_ld;
+  if (ld) *ld = c->gram_ld;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_fetch_gram(kgl_b200_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->d_gram.p) return fail(c, KGL_B200_ERR_STATE, "enqueue_gram first");
+  int rc = use_device(c); if (rc) return rc;
+  const size_t n2 = (size_t)c->N * c->N;
+  KGL_CUDA(c, c->d_gram_out.ensure(n2 * 4));
+  k_gram_finalize<<<blocks_for(n2, 256), 256, 0, c->stream>>>(c->d_gram.p, c->gram_ld, c->N, nullptr, 0, c->d_gram_out.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemcpyAsync(out, c->d_gram_out.p, n2 * 4, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
 }
 
 float kgl_b200_last_gram_kernel_ms(kgl_b200_ctx* c) {
@@ -1316,13 +1345,7 @@ float kgl_b200_last_gram_kernel_ms(kgl_b200_ctx* c) {
 int kgl_b200_run_gram(kgl_b200_ctx* c, int32_t* out) {
   if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   int rc = kgl_b200_enqueue_gram(c); if (rc) return rc;
-  const size_t n2 = (size_t)c->N * c->N;
-  KGL_CUDA(c, c->d_gram_out.ensure(n2 * 4));
-  k_gram_finalize<<<blocks_for(n2, 256), 256, 0, c->stream>>>(c->d_gram.p, c->gram_ld, c->N, nullptr, 0, c->d_gram_out.p);
-  KGL_LAUNCH_CHECK(c);
-  KGL_CUDA(c, cudaMemcpyAsync(out, c->d_gram_out.p, n2 * 4, cudaMemcpyDeviceToHost, c->stream));
-  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  return KGL_B200_OK;
+  return kgl_b200_fetch_gram(c, out);
 }
 
 int kgl_b200_run_grm(kgl_b200_ctx* c, uint32_t pop, double* out) {

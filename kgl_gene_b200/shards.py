@@ -54,6 +54,16 @@ def run_inbreed_sharded(ctx, algorithm: str, device, group=None, **options):
     return ctx.inbreed_fetch()
 
 
+def allreduce_gram(ctx, device, group=None):
+    """SUM all-reduce of the context's int32 Gram matrix: every rank computed the tiles rank, rank + world, ... and left
+    the rest zero (kgl_b200_enqueue_gram_tiles)."""
+    import torch
+    import torch.distributed as dist
+    ptr, count, _ = ctx.gram_buffer()
+    t = torch.as_tensor(_RawCudaArray(ptr, count, "<i4"), device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
 # ------------------------------------------------------------------------------------------------ IBS tiles ----------
 def tile_side(n_genomes: int) -> int:
     return (n_genomes + TILE - 1) // TILE

@@ -256,6 +256,20 @@ def test_gram_tensor_core_matches_oracle(gpu, n, l, miss):
         assert np.array_equal(d[:, None] + d[None, :] - 2 * got.astype(np.int64), ibs[..., 1] + 4 * ibs[..., 0])
 
 
+def test_gram_tiles_dealt_to_ranks(gpu):
+    """The multi-GPU decomposition on one device: the tile subsets of three 'ranks' add up to the whole matrix."""
+    import ctypes as C
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(600, 4000, seed=12, missing_rate=0.01)
+    gpu.upload_population(pop)
+    want, _ = O.gram(pop)
+    total = np.zeros_like(want, dtype=np.int64)
+    for r in range(3):
+        gpu.enqueue_gram_tiles(r, 3)
+        total += gpu.fetch_gram()          # symmetric read-out of a partial matrix: off-diagonal cells of missing tiles are 0
+    assert np.array_equal(total, want.astype(np.int64))
+
+
 def test_gram_full_width_identity(gpu):
     """chr22-shaped width on device-generated data without code-3 cells: the tensor-core and popcount paths must agree."""
     from kgl_gene_b200.synth import make_genomes, make_loci
