@@ -41,5 +41,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libkgl_b200_host.so")
+HOST_SOURCES = [os.path.join(HERE, "host", "kgl_b200_vcf_ingest.cpp")]
+
+
+def build_host(force: bool = False) -> str:
+    """libkgl_b200_host.so: the host-only pieces that need neither CUDA nor the reference headers (VCF ingest)."""
+    deps = HOST_SOURCES + [os.path.join(HERE, "host", "kgl_b200_vcf_ingest.h")]
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
+        return HOST_LIB
+    cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-o", HOST_LIB] + HOST_SOURCES + ["-lz"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError("g++ failed building libkgl_b200_host.so")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))

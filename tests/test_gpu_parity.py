@@ -319,6 +319,25 @@ def test_fws_bins_match_oracle(gpu, n, l, miss, spectrum):
         assert np.allclose(fis[m], (h_exp - h_obs) / h_exp, rtol=1e-12)
 
 
+def test_vcf_ingest_to_device(gpu, tmp_path):
+    """N2 end to end: VCF text -> packed matrix (host ingest, no PopulationDB) -> device pass, against the oracle on the source."""
+    from kgl_gene_b200.synth import make_population
+    from kgl_gene_b200.vcf import ingest_vcf, write_vcf
+    pop, _ = make_population(200, 3000, seed=52, missing_rate=0.0)
+    path = str(tmp_path / "chr.vcf.gz")
+    write_vcf(pop, path)
+    got, names, _, st = ingest_vcf(path, superpop=pop.superpop)
+    assert st["kept"] == 3000 and len(names) == 200
+    gpu.upload_population(got)
+    gpu.select_loci()
+    lc, res = gpu.count_and_inbreed()
+    sel = O.select_all_pops(pop)
+    want = O.inbreed(pop, sel, "Simple")
+    assert np.array_equal(lc, O.allele_count(pop)[0])
+    assert np.array_equal(results_matrix(res)[0], results_matrix(want)[0])
+    assert rel_err(res["inbred_allele_sum"], want["inbred_allele_sum"]) < 1e-9
+
+
 def test_device_generator_matches_numpy(gpu):
     from kgl_gene_b200.synth import make_genomes, make_loci, synth_codes
     from kgl_gene_b200.flatfile import pack_codes

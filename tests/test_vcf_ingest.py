@@ -1,0 +1,75 @@
+"""N2: VCF genotype columns -> packed 2-bit matrix without a PopulationDB (kgl_gene_b200/host/kgl_b200_vcf_ingest.cpp).
+Round trips through VCF text, plus the reference parsers' edge rules (kgl_variant_factory_1000_impl.cpp:148-272,
+kgl_variant_factory_pf_impl.cpp:139-152). The reference's own VCF reader does not link here (Boost iostreams), so these
+rules are pinned by citation, not by its binary."""
+import os
+
+import numpy as np
+import pytest
+
+from kgl_gene_b200.synth import make_population
+from kgl_gene_b200.vcf import ingest_vcf, write_vcf
+
+
+def expected_codes(pop):
+    c = pop.codes().copy()
+    c[c == 3] = 0            # "." alleles are the reference allele for the 1000G parser
+    return c
+
+
+@pytest.mark.parametrize("suffix", [".vcf", ".vcf.gz"])
+def test_round_trip_phased(tmp_path, suffix):
+    pop, _ = make_population(131, 700, seed=4, missing_rate=0.01, missing_af_rate=0.05)
+    path = str(tmp_path / ("p" + suffix))
+    write_vcf(pop, path)
+    got, names, contig, st = ingest_vcf(path, n_threads=3)
+    assert contig == "22" and len(names) == 131 and names[5] == "G00005"
+    assert st["records"] == 700 and st["kept"] == 700 and st["malformed_genotypes"] == 0
+    assert np.array_equal(got.offsets, pop.offsets)
+    assert np.array_equal(got.af.view(np.uint32), pop.af.view(np.uint32))          # float bits survive repr -> strtof
+    assert np.array_equal(got.codes(), expected_codes(pop))
+    assert got.packed.shape == pop.packed.shape and not got.unphased
+
+
+def test_round_trip_unphased_pf7(tmp_path):
+    pop, _ = make_population(64, 300, seed=6, missing_rate=0.05, unphased=True)
+    path = str(tmp_path / "pf.vcf")
+    write_vcf(pop, path)
+    got, _, _, st = ingest_vcf(path, unphased=True)
+    assert got.unphased and st["kept"] == 300
+    assert np.array_equal(got.codes(), expected_codes(pop))                           # ./. genotypes are skipped: no variant
+
+
+def test_edge_rules(tmp_path):
+    pop, _ = make_population(4, 6, seed=1, missing_rate=0.0)
+    path = str(tmp_path / "e.vcf")
+    base = int(pop.offsets[-1]) + 100
+    extra = [
+        (5, f"22\t{base}\t.\tA\tG,T\t100\tPASS\tAF=0.1,0.2\tGT\t0|1\t1|2\t0|0\t2|2"),            # multi-allelic: left out
+        (5, f"22\t{base + 10}\t.\tAT\tA\t100\tPASS\tAF=0.1\tGT\t0|1\t0|0\t0|0\t1|1"),              # indel: left out
+        (5, f"22\t{base + 20}\t.\tA\tG\t100\tq10\tAF=0.25\tGT\t0|1\t1|1\t0|0\t.|1"),                # not PASS: kept, AF -> NaN
+        (5, f"22\t{base + 30}\t.\tA\tG\t100\tPASS\tEUR_AF=0.5;AF=0.125;DP=7\tGT:DP\t1|0:3\t0|2:1\t1:9\t-|1:2"),
+        (5, f"22\t{base + 40}\t.\tC\tT\t100\tPASS\tAF=0.3\tGT\t0|1\t0|0\t0|0\t0|0"),                # repeated POS below: both dropped
+        (5, f"22\t{base + 40}\t.\tC\tA\t100\tPASS\tAF=0.1\tGT\t0|0\t0|1\t0|0\t0|0"),
+    ]
+    write_vcf(pop, path, extra_lines=extra)
+    got, _, _, st = ingest_vcf(path, n_threads=1)
+    assert st["records"] == 12 and st["kept"] == 8 and st["skipped_multi_allelic"] == 3 and st["skipped_non_snp"] == 1
+    assert st["not_pass"] == 1
+    assert got.offsets.tolist()[6:] == [base + 20 - 1, base + 30 - 1]
+    assert np.all(np.isnan(got.af[:, 6]))                                               # not PASS
+    assert got.codes()[6].tolist() == [1, 2, 0, 1]                                      # ".|1": "." is the reference allele
+    # 1|0 -> het; 0|2 -> index beyond the ALT list: whole genotype reference; "1" haploid on an autosome: reference; -|1 het
+    assert got.codes()[7].tolist() == [1, 0, 0, 1] and st["malformed_genotypes"] == 2
+    assert got.af[5, 7] == np.float32(0.125) and got.af[3, 7] == np.float32(0.5) and np.isnan(got.af[0, 7])
+
+
+def test_ingested_population_feeds_the_oracle(tmp_path):
+    """The ingested matrix is a valid input of the hot path: same allele counts as the population it was written from."""
+    import oracle_py as O
+    pop, _ = make_population(70, 400, seed=8, missing_rate=0.0)
+    path = str(tmp_path / "o.vcf.gz")
+    write_vcf(pop, path)
+    got, _, _, _ = ingest_vcf(path)
+    a, b = O.allele_count(got), O.allele_count(pop)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
