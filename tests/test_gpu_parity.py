@@ -338,6 +338,27 @@ def test_vcf_ingest_to_device(gpu, tmp_path):
     assert rel_err(res["inbred_allele_sum"], want["inbred_allele_sum"]) < 1e-9
 
 
+@pytest.mark.parametrize("algo,tol", [("Simple", 0.02), ("RitlandLocus", 0.03), ("HallME", 0.03), ("Loglikelihood", 0.02)])
+def test_synthetic_self_check(gpu, tmp_path, algo, tol):
+    """N4: the reference's Synthetic mode (101 genomes, planted F = -0.5 .. 0.5): every estimator recovers the planted
+    coefficient (HallME estimates max(F, 0): an EM over a mixture weight)."""
+    from kgl_gene_b200 import synthetic
+    from kgl_gene_b200.synth import make_loci
+    offsets, af = make_loci(60_000, 17, spectrum="dense")
+    ids, syn, calc = synthetic.synthetic_self_check(gpu, af, offsets, algorithm=algo, seed=5)
+    assert len(ids) == 101 and syn[0] == -0.5 and abs(syn[-1] - 0.5) < 1e-12
+    # For F < 0 the class law leaves the simplex at small p (p^2 + F p q < 0 below p = -F q): the draw is clipped there, in the
+    # reference's generator as well, so the planted value is only recovered approximately on the negative side.
+    pos = syn >= 0.0 if algo != "HallME" else syn > 0.05
+    assert np.max(np.abs(calc[pos] - syn[pos])) < tol, np.max(np.abs(calc[pos] - syn[pos]))
+    if algo != "HallME":
+        neg = syn < -0.02
+        assert np.all(calc[neg] < 0.0) and np.all(calc[neg] >= syn[neg] - 0.03)       # clipped towards zero, never beyond the plant
+        assert np.corrcoef(calc, syn)[0, 1] > 0.99
+    synthetic.write_synthetic_csv(str(tmp_path / "syn.csv"), ids, syn, calc)
+    assert open(tmp_path / "syn.csv").readline().strip() == "Sample,SynInbreed,CalcInbreed"
+
+
 def test_device_generator_matches_numpy(gpu):
     from kgl_gene_b200.synth import make_genomes, make_loci, synth_codes
     from kgl_gene_b200.flatfile import pack_codes
