@@ -55,6 +55,18 @@ def parse_args():
     return ap.parse_args()
 
 
+def stream_kernel_name(n_genomes: int) -> str:
+    """The streaming kernel plan_stream picks for this width (kgl_gene_b200/csrc/stream_common.cuh)."""
+    units = (n_genomes + 63) // 64
+    if units > 56:
+        units = (units + 39) // 40 * 40
+    if units == 8:
+        return "k_stream_count_ct<8,256>"
+    if units % 40 == 0:
+        return "k_stream_count_ct<40,64>" + (f" x {units // 40} slices" if units > 40 else "")
+    return "k_stream_count_rt (runtime shape)"
+
+
 def workload_name(n, l, world):
     base = f"1000G chr22 shape: {n} genomes x {l} biallelic SNPs, per-locus allele counts + Simple inbreeding, 6 float AF vectors"
     return base if world == 1 else base + f" per GPU (locus-sharded, {world} shards, partial sums all-reduced)"
@@ -324,7 +336,7 @@ def run_ours(args):
                        "step": "k_locus_prepare (flags + dense totals) + k_stream_count_ct + k_post (counter expansion | code-3 cells | rare-major rows) + k_moment_partials (+ NCCL all-reduce + k_finalize_closed_form at N > 1)"},
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_stream_count_ct<40,64>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": stream_kernel_name(n), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": k_ms, "kernel_share_of_step": (k_ms * len(kernel_ms) / total_ms) if k_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes},
