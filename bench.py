@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes "NCCL version ..." to STDOUT at debug level VERSION; stdout carries exactly one JSON line here.
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 N_GENOMES = 2504
 N_LOCI = 1_100_000
