@@ -6,6 +6,7 @@
 #include "stream_launch.cuh"
 #include "sparse_events.cuh"
 #include "sample_major.cuh"
+#include "terms_fast.cuh"
 #include "misc_kernels.cuh"
 #include "ibs_launch.cuh"
 #include "post_kernels.cuh"
@@ -107,8 +108,9 @@ struct kgl_b200_ctx {
 
   // sample-major copy
   DevBuf<uint32_t> d_sm_lo, d_sm_hi;
+  DevBuf<uint2> d_sm_codes;             // interleaved codes of the same cells (terms_fast.cuh)
   uint64_t n_gblocks = 0, n_words = 0;
-  bool sm_valid = false;
+  bool sm_valid = false, codes_valid = false;
 
   // fused pass outputs
   DevBuf<uint32_t> d_locus_counts, d_planes;
@@ -118,6 +120,13 @@ struct kgl_b200_ctx {
   DevBuf<double> d_partials, d_iter, d_f, d_bracket, d_chunk_out, d_inbreeding, d_grid;
   DevBuf<uint32_t> d_done;
   DevBuf<unsigned long long> d_flag;
+  // table-driven estimator sweeps (terms_fast.cuh): per-genome limits of the feasible region, lane states of the last
+  // Newton sweep, chunk outputs of the exact fallback
+  DevBuf<double> d_limits, d_slow_out;
+  DevBuf<uint8_t> d_lane_state;
+  DevBuf<uint32_t> d_n_slow, d_list;    // d_list: genomes whose root search is still running (late Newton sweeps)
+  uint64_t list_len = 0;
+  bool limits_valid = false;
   DevBuf<uint64_t> d_genome_counts;
   DevBuf<kgl_b200_locus_results> d_results;
   DevBuf<uint32_t> d_ibs;
@@ -514,6 +523,89 @@ int launch_terms(kgl_b200_ctx* c, int n_out, const double* d_grid, int n_grid, T
   return KGL_B200_OK;
 }
 
+// Interleaved 2-bit copy of the sample-major planes for the table-driven sweeps (built on first use, as the planes are).
+int ensure_sample_codes(kgl_b200_ctx* c) {
+  int rc = ensure_sample_major(c);
+  if (rc) return rc;
+  if (c->codes_valid) return KGL_B200_OK;
+  const size_t n = (size_t)c->n_gblocks * c->n_words * 32;
+  KGL_CUDA(c, c->d_sm_codes.ensure(n));
+  k_to_sample_codes<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->d_sm_lo.p, c->d_sm_hi.p, n, c->d_sm_codes.p);
+  KGL_LAUNCH_CHECK(c);
+  c->codes_valid = true;
+  return KGL_B200_OK;
+}
+
+// Table-driven sweeps (terms_fast.cuh). One CTA per SM walks a contiguous range of 128-locus tiles over all genome blocks.
+struct FastLaunch { dim3 grid; uint32_t tiles_per_chunk, slots; uint64_t n_chunks; };
+
+template <int MODE>
+int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
+  int rc = ensure_sample_major(c);
+  if (rc) return rc;
+  const uint64_t gblocks = list_len ? (list_len + 31) / 32 : std::min<uint64_t>(c->n_gblocks, (c->N + 31) / 32);
+  // warps per CTA: of 16..32 the count that leaves the fewest genome-block slots empty (more warps on a tie)
+  int warps = 16; double best = -1.0;
+  for (int w = 16; w <= kFastMaxWarps; ++w) {
+    const uint64_t sl = std::min<uint64_t>(8, (gblocks + w - 1) / w);
+    const uint64_t rows = (gblocks + (uint64_t)w * sl - 1) / ((uint64_t)w * sl);
+    const double filled = (double)gblocks / (double)(rows * sl * w);
+    if (filled >= best) { best = filled; warps = w; }
+  }
+  const uint32_t slots = (uint32_t)std::min<uint64_t>(8, (gblocks + warps - 1) / warps);
+  const uint64_t gy = (gblocks + (uint64_t)warps * slots - 1) / ((uint64_t)warps * slots);
+  const uint64_t n_tiles = (c->n_words + kFastTileWords - 1) / kFastTileWords;
+  const uint64_t want = std::max<uint64_t>(1, (uint64_t)c->sm_count / gy);
+  const uint64_t tpc = std::max<uint64_t>(1, (n_tiles + want - 1) / want);
+  fl.tiles_per_chunk = (uint32_t)tpc; fl.slots = slots;
+  fl.n_chunks = (n_tiles + tpc - 1) / tpc;
+  fl.grid = dim3((unsigned)fl.n_chunks, (unsigned)gy);
+  constexpr int NACC = FastAcc<MODE>::N;
+  KGL_CUDA(c, c->d_chunk_out.ensure((size_t)fl.n_chunks * c->Npad * NACC));
+  rc = ensure_sample_codes(c);
+  if (rc) return rc;
+  FastParams P{};
+  P.codes = c->d_sm_codes.p;
+  P.n_gblocks = gblocks; P.n_words = c->n_words; P.n_loci = c->L; P.n_genomes = c->N; P.n_genomes_padded = c->Npad;
+  P.selw = c->prep[c->par].selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
+  P.unphased = c->unphased ? 1 : 0; P.tiles_per_chunk = fl.tiles_per_chunk; P.slots = slots;
+  P.f = c->d_f.p; P.out = c->d_chunk_out.p;
+  P.list = list_len ? c->d_list.p : nullptr; P.n_list = list_len;
+  const size_t smem = fast_smem_bytes(MODE, slots, warps);
+  KGL_CUDA(c, cudaFuncSetAttribute(k_terms_fast<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_terms_fast<MODE><<<fl.grid, warps * 32, smem, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+// One Newton sweep of the log-likelihood root search: the table-driven kernel, its reduction, and the exact cell-by-cell
+// evaluation for the genomes the reduction marks (none in the normal case: the fallback kernels then return at once).
+template <int MODE>
+int newton_sweep(kgl_b200_ctx* c) {
+  FastLaunch fl;
+  int rc = launch_fast<MODE>(c, fl, c->list_len); if (rc) return rc;
+  const unsigned nb = blocks_for(c->N, 256);
+  KGL_CUDA(c, cudaMemsetAsync(c->d_n_slow.p, 0, 4, c->stream));
+  k_newton_reduce<<<blocks_for(c->list_len ? c->list_len : c->N, 256), 256, 0, c->stream>>>(
+      c->d_chunk_out.p, FastAcc<MODE>::N, fl.n_chunks, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len, c->d_f.p,
+      c->d_limits.p, c->d_done.p, c->d_iter.p, c->d_lane_state.p, c->d_n_slow.p);
+  KGL_LAUNCH_CHECK(c);
+  TermLaunch tl = plan_terms(c);
+  KGL_CUDA(c, c->d_slow_out.ensure((size_t)tl.n_chunks * c->Npad * 4));
+  TermParams P{};
+  P.sm_lo = c->d_sm_lo.p; P.sm_hi = c->d_sm_hi.p;
+  P.n_gblocks = c->n_gblocks; P.n_words = c->n_words; P.n_loci = c->L; P.n_genomes = c->N;
+  P.selw = c->prep[c->par].selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
+  P.unphased = c->unphased ? 1 : 0; P.words_per_chunk = tl.words_per_chunk;
+  P.f = c->d_f.p; P.out = c->d_slow_out.p; P.n_out = 4; P.n_genomes_padded = c->Npad;
+  P.lane_state = c->d_lane_state.p; P.n_slow = c->d_n_slow.p;
+  k_genome_terms<TERM_NEWTON><<<tl.grid, kTermWarps * 32, 0, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  k_newton_add_slow<<<nb, 256, 0, c->stream>>>(c->d_slow_out.p, tl.n_chunks, c->Npad, c->N, c->d_lane_state.p, c->d_n_slow.p, c->d_iter.p);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
 // ---- pairwise IBS ----------------------------------------------------------------------------------------------------
 // Planes of the dense kernel. No code-3 cell: the sample-major copy as it is. Indexed code-3 cells: pre-masked copies, the
 // sparse repair kernel does the rest. Otherwise: a validity plane and the three-plane kernel.
@@ -717,6 +809,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
   c->d_bin_flags.release(); c->d_bin_sum64.release(); c->d_bin_popmask32.release(); c->d_bin_state.release(); c->d_bin_need32.release();
   c->d_zero_superpop.release(); c->d_bin_out.release();
+  c->d_list.release(); c->d_sm_codes.release(); c->d_limits.release(); c->d_slow_out.release(); c->d_lane_state.release(); c->d_n_slow.release();
   c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
   if (c->gram_e0) cudaEventDestroy(c->gram_e0);
   if (c->gram_e1) cudaEventDestroy(c->gram_e1);
@@ -785,7 +878,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
-  c->sm_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
+  c->sm_valid = false; c->codes_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
   c->codes16_valid = false;
   return KGL_B200_OK;
 }
@@ -1058,34 +1151,46 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   KGL_CUDA(c, c->d_done.ensure(c->Npad));
   KGL_CUDA(c, c->d_flag.ensure(1));
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
+  KGL_CUDA(c, c->d_limits.ensure((size_t)c->Npad * 3));
+  KGL_CUDA(c, c->d_lane_state.ensure(c->Npad));
+  KGL_CUDA(c, c->d_n_slow.ensure(1));
+  KGL_CUDA(c, c->d_list.ensure(c->Npad));
+  c->limits_valid = false; c->list_len = 0;
   return KGL_B200_OK;
 }
 
 int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   if (!c || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
   int rc = use_device(c); if (rc) return rc;
-  TermLaunch tl;
+  FastLaunch fl;
   if (c->phase == 0) {
     rc = enqueue_moments(c, c->opt.count_loci != 0, false, c->algo == KGL_B200_ALGO_RITLAND); if (rc) return rc;
     if (c->algo == KGL_B200_ALGO_RITLAND) {
-      rc = launch_terms<TERM_RITLAND>(c, 3, nullptr, 0, tl); if (rc) return rc;
-      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 3, c->prep[c->par].totals.p,
+      rc = launch_fast<FAST_RITLAND>(c, fl); if (rc) return rc;
+      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, 2, c->prep[c->par].totals.p,
                                                                        c->d_superpop.p, c->N, c->d_partials.p);
+      KGL_LAUNCH_CHECK(c);
+    }
+    if (c->algo == KGL_B200_ALGO_LOGLIKELIHOOD) {   // heterozygous cells of THIS locus shard, before the partials are all-reduced
+      k_stash_nhet<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_partials.p, PART_COUNT, PART_NMAJHET, PART_NMINHET, c->N, c->d_limits.p);
       KGL_LAUNCH_CHECK(c);
     }
     return KGL_B200_OK;
   }
   const unsigned nb = blocks_for(c->N, 256);
   if (c->algo == KGL_B200_ALGO_HALLME) {
-    rc = launch_terms<TERM_HALL>(c, 1, nullptr, 0, tl); if (rc) return rc;
-    k_iter_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 1, c->N, 0, 1, c->d_iter.p);
+    rc = launch_fast<FAST_HALL>(c, fl); if (rc) return rc;
+    k_hall_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, c->N, c->d_iter.p);
     KGL_LAUNCH_CHECK(c);
     return KGL_B200_OK;
   }
-  rc = launch_terms<TERM_NEWTON>(c, 4, nullptr, 0, tl); if (rc) return rc;
-  k_iter_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, tl.n_chunks, c->Npad, 4, c->N, 0, 4, c->d_iter.p);
-  KGL_LAUNCH_CHECK(c);
-  return KGL_B200_OK;
+  if (!c->limits_valid) {      // once per root search: the selection is fixed between inbreed_begin and inbreed_fetch
+    rc = launch_fast<FAST_LIMITS>(c, fl); if (rc) return rc;
+    k_limits_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, c->N, c->d_limits.p);
+    KGL_LAUNCH_CHECK(c);
+    c->limits_valid = true;
+  }
+  return c->unphased ? newton_sweep<FAST_NEWTON_U>(c) : newton_sweep<FAST_NEWTON>(c);
 }
 
 int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_doubles) {
@@ -1142,6 +1247,14 @@ int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
   KGL_CUDA(c, cudaMemcpyAsync(&flag, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   *finished = (flag == 0 || c->iteration >= c->opt.ll_max_iterations) ? 1 : 0;
+  // flag = genomes still searching. Once they are a minority the sweeps gather them through a list: the work of a sweep
+  // follows the number of live genomes, not N (every rank sees the same done flags, so the same list).
+  c->list_len = 0;
+  if (!*finished && flag * 2 <= c->N) {
+    k_compact_active<<<1, 1024, 0, c->stream>>>(c->d_done.p, c->N, c->d_list.p);
+    KGL_LAUNCH_CHECK(c);
+    c->list_len = flag;
+  }
   return KGL_B200_OK;
 }
 

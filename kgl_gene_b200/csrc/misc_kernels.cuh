@@ -22,15 +22,17 @@ k_ritland_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint
                    double* __restrict__ partials) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
-  double s0 = 0.0, s2 = 0.0, c2x = 0.0;
+  // chunk outputs of k_terms_fast<FAST_RITLAND>: {sum of (1/p - 1) over hom-alt cells with p > 0.001 minus sum of (1/q - 1)
+  // over the non-reference cells of q > 0.01 rows, number of hom-alt cells with p <= 0.001}
+  double sdiff = 0.0, c2x = 0.0;
   for (uint64_t c = 0; c < n_chunks; ++c) {
     const double* o = chunk_out + (c * n_genomes_padded + g) * n_out;
-    s0 += o[0]; s2 += o[1]; c2x += o[2];
+    sdiff += o[0]; c2x += o[1];
   }
   const int k = superpop[g];
   double* P = partials + g * PART_COUNT;
   const double n_het = P[PART_NMAJHET] + P[PART_NMINHET];
-  P[PART_RSUM] = (totals[k * TOT_COUNT + TOT_W0] - s0) + s2 - n_het;
+  P[PART_RSUM] = (totals[k * TOT_COUNT + TOT_W0] + sdiff) - n_het;
   P[PART_RCOUNT] = P[PART_NMAJHOM] + (P[PART_NMINHOM] - c2x) + n_het;
 }
 
@@ -175,13 +177,17 @@ k_ll_step(const double* __restrict__ iter, uint64_t n_genomes, double tol, doubl
   const double x = f[g];
   if (hom_clamped || g1 > 0.0) a = x; else b = x;
   double nx = 0.5 * (a + b);
+  bool newton_converged = false;
   if (!hom_clamped && g2 < 0.0) {
     const double cand = x - g1 / g2;
-    if (cand > a && cand < b) nx = cand;
+    // a Newton step below the tolerance ends the search even when rounding puts it on the bracket's edge (x itself is an
+    // end of the bracket by now); without this test such a genome falls back to ~40 bisection passes over the matrix
+    if (fabs(cand - x) < tol) { nx = (cand > a && cand < b) ? cand : x; newton_converged = true; }
+    else if (cand > a && cand < b) nx = cand;
   }
   bracket[g * 2 + 0] = a; bracket[g * 2 + 1] = b;
   f[g] = nx;
-  if (fabs(nx - x) < tol || (b - a) < tol) done[g] = 1;
+  if (newton_converged || fabs(nx - x) < tol || (b - a) < tol) done[g] = 1;
   else atomicAdd(flag, 1ull);
 }
 

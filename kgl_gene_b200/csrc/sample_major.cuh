@@ -75,6 +75,10 @@ struct TermParams {
   double* out;                 // [n_chunks][n_genomes_padded][n_out]
   int n_out;
   uint64_t n_genomes_padded;
+  // NEWTON as the exact fallback of k_terms_fast (terms_fast.cuh): only genomes with lane_state == 2 are evaluated, and
+  // nothing at all when *n_slow == 0. Both null: every genome.
+  const uint8_t* lane_state;
+  const uint32_t* n_slow;
 };
 
 template <int MODE> struct TermAcc { static constexpr int N = (MODE == TERM_GRID) ? kGridMax : (MODE == TERM_NEWTON) ? 4 : 3; };
@@ -88,7 +92,8 @@ k_genome_terms(const TermParams P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t gb = (uint64_t)blockIdx.x * kTermWarps + warp;
   const uint64_t g = gb * 32 + lane;
-  const bool live = gb < P.n_gblocks && g < P.n_genomes;
+  if (P.n_slow && *P.n_slow == 0) return;
+  const bool live = gb < P.n_gblocks && g < P.n_genomes && (!P.lane_state || P.lane_state[g] == 2);
   const int k = live ? P.superpop[g] : 0;
   const double f = (MODE == TERM_HALL || MODE == TERM_NEWTON) ? (live ? P.f[g] : 0.0) : 0.0;
 

@@ -5,6 +5,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o kbench kbench.cu
 #include "../stream_launch.cuh"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -40,6 +41,67 @@ __global__ void __launch_bounds__(256) k_pipe(uint32_t* out, int iters, uint32_t
 #pragma unroll
   for (int i = 0; i < 8; ++i) r ^= a[i];
   if (r == 0x12345678u) out[0] = r;
+}
+
+// FP64 pipe: the estimator passes behind the streaming kernel (terms_fast.cuh) are bound by it.
+//   0 DFMA   1 DADD   2 MUFU.RCP64H (rcp.approx.ftz.f64)   3 fast reciprocal (MUFU + 3 DFMA)   4 IEEE divide (__ddiv_rn)
+template <int OP>
+__global__ void __launch_bounds__(256) k_pipe_f64(double* out, int iters, double seed) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + 1e-3 * (threadIdx.x + 1) + 0.125 * i;
+  const double b = 1.0 + 1e-9 * seed, c = 1e-7 * seed;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) a[i] = fma(a[i], b, c);
+      else if (OP == 1) a[i] = __dadd_rn(a[i], c);
+      else if (OP == 2) { double x; asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a[i])); a[i] = x; }
+      else if (OP == 3) { double x; asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a[i]));
+                          const double e = fma(-a[i], x, 1.0); a[i] = fma(x, fma(e, e, e), x) + b; }
+      else if (OP == 4) a[i] = __ddiv_rn(b, a[i]) + b;
+    }
+  }
+  double r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += a[i];
+  if (r == 0.12345) out[0] = r;
+}
+
+// Accuracy of MUFU.RCP64H and of the refinements used by terms_fast.cuh, against the IEEE divide, over a log-uniform sweep.
+__global__ void k_rcp_accuracy(double* out /* [3] max relative errors: x0, x0(1+e), x0(1+e+e^2) */, int n) {
+  double m0 = 0, m1 = 0, m2 = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double d = exp2(-40.0 + 80.0 * (double)i / n) * (1.0 + 0.37 * (double)(i % 977) / 977.0);
+    double x; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double ref = 1.0 / d, e = fma(-d, x, 1.0);
+    const double x1 = fma(x, e, x), x2 = fma(x, fma(e, e, e), x);
+    m0 = fmax(m0, fabs(x - ref) / ref); m1 = fmax(m1, fabs(x1 - ref) / ref); m2 = fmax(m2, fabs(x2 - ref) / ref);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o)); m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(m0));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(m1));
+    atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(m2));
+  }
+}
+
+template <int OP>
+static void pipe_rate_f64(const char* name, double* d_out, int sms, double clk_ghz) {
+  const int iters = 1024, blocks = sms * 8;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_pipe_f64<OP><<<blocks, 256>>>(d_out, 16, 1.0);
+  CK(cudaEventRecord(e0));
+  k_pipe_f64<OP><<<blocks, 256>>>(d_out, iters, 1.0);
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  const double inner = (double)blocks * 256 * iters * 8;
+  const double per_s = inner / (ms * 1e-3);
+  std::printf("pipe %-22s %8.3f ms  %.3e inner-ops/s  = %.2f inner/clk/SM at %.3f GHz\n", name, ms, per_s, per_s / sms / (clk_ghz * 1e9), clk_ghz);
 }
 
 template <int OP>
@@ -162,6 +224,19 @@ int main(int argc, char** argv) {
     pipe_rate<6>("LOP3+IMAD", 2, d_out, sms, clk);
     pipe_rate<8>("POPC+IADD+REDUX", 3, d_out, sms, clk);
     pipe_rate<9>("IADD+LOP3", 2, d_out, sms, clk);
+    pipe_rate_f64<0>("DFMA", (double*)d_out, sms, clk);
+    pipe_rate_f64<1>("DADD", (double*)d_out, sms, clk);
+    pipe_rate_f64<2>("MUFU.RCP64H", (double*)d_out, sms, clk);
+    pipe_rate_f64<3>("rcp (MUFU+3DFMA)+DADD", (double*)d_out, sms, clk);
+    pipe_rate_f64<4>("IEEE div + DADD", (double*)d_out, sms, clk);
+    {
+      double* d_acc; CK(cudaMalloc(&d_acc, 24)); CK(cudaMemset(d_acc, 0, 24));
+      k_rcp_accuracy<<<sms * 4, 256>>>(d_acc, 1 << 26);
+      double h[3]; CK(cudaMemcpy(h, d_acc, 24, cudaMemcpyDeviceToHost));
+      std::printf("rcp accuracy (max relative error over 2^26 arguments in [2^-40, 2^40]): MUFU.RCP64H %.3e (2^%.1f), one step x0(1+e) %.3e, x0(1+e+e^2) %.3e\n",
+                  h[0], std::log2(h[0]), h[1], h[2]);
+      CK(cudaFree(d_acc));
+    }
   }
 
   const uint64_t units = stream_units_padded((n_genomes + 63) / 64);

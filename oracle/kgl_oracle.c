@@ -192,11 +192,14 @@ static double log_likelihood_argmax(const locus_term* terms, size_t n, double st
     const int hom_clamped = sig >= 4294967296.0;
     if (hom_clamped || g1 > 0.0) a = x; else b = x;
     double nx = 0.5 * (a + b);
+    int newton_converged = 0;
     if (!hom_clamped && g2 < 0.0) {
       const double cand = x - g1 / g2;
-      if (cand > a && cand < b) nx = cand;
+      /* a Newton step below the tolerance ends the search even when rounding puts it on the bracket's edge */
+      if (fabs(cand - x) < tol) { nx = (cand > a && cand < b) ? cand : x; newton_converged = 1; }
+      else if (cand > a && cand < b) nx = cand;
     }
-    const int stop = fabs(nx - x) < tol || (b - a) < tol;
+    const int stop = newton_converged || fabs(nx - x) < tol || (b - a) < tol;
     x = nx;
     if (stop) break;
   }
