@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kinship", action="store_true")
+    ap.add_argument("--no-estimators", action="store_true", help="skip the RitlandLocus / HallME / Loglikelihood timings")
     ap.add_argument("--kinship-loci", type=int, default=0, help="loci of the pairwise run (0 = the resident chr22-shape matrix)")
     ap.add_argument("--kinship-steps", type=int, default=3)
     return ap.parse_args()
@@ -306,6 +307,10 @@ def run_ours(args):
         lc2 = h_lc.numpy().view(np.uint32)
         assert np.array_equal(lc2, lc), "e2e per-locus counts differ from the resident run"
 
+    est = None
+    if not args.no_estimators:
+        est = run_estimators(ctx, torch, dist, dev, stream, world, n, l, allreduce_partials)
+
     kin = None
     if not args.no_kinship:
         kin = run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, rb, SEED, superpop, inbreeding)
@@ -345,6 +350,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks,
         }
+        if est is not None:
+            line["estimators"] = est
         if kin is not None:
             line["kinship"] = kin
         if not args.no_cpu_baseline and world == 1:
@@ -359,6 +366,59 @@ def run_ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# FP64 instructions per cell of the table-driven sweeps (kgl_gene_b200/csrc/terms_fast.cuh) and the measured DFMA issue rate
+# of one B200 (profiles/r01_pipe_rates_f64_kbench.log: 56.35 lanes per clk per SM x 148 SMs x 1.965 GHz).
+FP64_OPS_PER_CELL = {"HallME": 4, "Loglikelihood": 5}
+FP64_PEAK_OPS = 56.35 * 148 * 1.965e9
+
+
+def run_estimators(ctx, torch, dist, dev, stream, world, n, l, allreduce_partials):
+    """The other three estimators of kga_inbreed on the resident shard: whole-estimator time (all sweeps, the all-reduce of
+    every sweep at N > 1) and the time of one full sweep against the FP64 pipe."""
+    out = {}
+    for algorithm in ("RitlandLocus", "HallME", "Loglikelihood"):
+        def run():
+            ev = []
+            ctx.inbreed_begin(algorithm)
+            finished = False
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            while not finished:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.inbreed_accumulate()
+                e1.record(stream)
+                if world > 1:
+                    allreduce_partials()
+                finished = ctx.inbreed_update()
+                ev.append((e0, e1))
+            a1.record(stream)
+            torch.cuda.synchronize()
+            return [a.elapsed_time(b) for a, b in ev], a0.elapsed_time(a1)
+        run()                                   # warm-up: derived copies, buffers
+        if world > 1:
+            dist.barrier()
+        ms, total = run()
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+        cells = float(n) * float(l) * world
+        o = {"passes": len(ms), "ms": total, "genotype_loci_per_s": cells / (total * 1e-3)}
+        if algorithm in FP64_OPS_PER_CELL:
+            full = sorted(ms[1:])[-3:] if algorithm == "Loglikelihood" else ms[1:]     # full sweeps (late Newton sweeps gather few genomes)
+            sweep = float(np.median(full))
+            cells_rank = float(n) * float(l)
+            achieved = cells_rank * FP64_OPS_PER_CELL[algorithm] / (sweep * 1e-3)
+            o["sweep_ms"] = sweep
+            o["roofline"] = {"bound": "fp64 pipe", "kernel": "k_terms_fast<%s>" % ("HALL" if algorithm == "HallME" else "NEWTON"),
+                             "achieved": achieved, "peak": FP64_PEAK_OPS, "unit": "FP64 lane-ops/s", "frac": achieved / FP64_PEAK_OPS,
+                             "fp64_ops_per_cell": FP64_OPS_PER_CELL[algorithm],
+                             "peak_source": "measured DFMA issue rate (kbench, profiles/r01_pipe_rates_f64_kbench.log)"}
+        out[algorithm] = o
+    return out
 
 
 def timed_local(ctx, torch, stream, fn, steps):

@@ -163,6 +163,33 @@ def test_all_estimators_match_oracle(gpu, case):
     assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-9
 
 
+@pytest.mark.parametrize("unphased", [False, True], ids=["phased", "unphased"])
+def test_loglikelihood_clamped_terms(gpu, unphased):
+    """The likelihood's clamps (calc.cpp:108-124). Heterozygous cells at loci with 2 p q < 1e-10 are clamped at every f: the
+    table-driven Newton sweep hands such genomes to the cell-by-cell kernel (terms_fast.cuh, state 2). In an unphased
+    population a hom-alt pair is the heterozygous term 2 (1-f) p p, clamped from above where it exceeds 1: the sweep counts
+    those cells per genome and f. Both must land on the oracle's optimum."""
+    from kgl_gene_b200.flatfile import pack_codes, unpack_codes
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(96, 5000, seed=31, unphased=unphased)
+    pop.af[:, ::50] = np.float32(1e-11)
+    pop.af[:, 3::40] = np.float32(0.95)
+    codes = unpack_codes(pop.packed, pop.n_genomes)
+    codes[::50, ::3] = 1                      # every third genome is heterozygous at the 1e-11 loci
+    pop.packed = pack_codes(codes)
+    sel = O.select_all_pops(pop)
+    gpu.upload_population(pop)
+    gpu.select_loci()
+    got = gpu.inbreed("Loglikelihood")
+    want = O.inbreed(pop, sel, "Loglikelihood")
+    c_got, _ = results_matrix(got)
+    c_want, _ = results_matrix(want)
+    assert np.array_equal(c_got, c_want)
+    assert np.max(np.abs(got["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-9
+    grid = np.array([-0.2, 0.0, 0.1, 0.6])
+    assert rel_err(gpu.loglik_grid(grid), O.loglik_grid(pop, sel, grid)) < 1e-12
+
+
 def test_hallme_fixed_point(gpu):
     from kgl_gene_b200.synth import make_population
     pop, _ = make_population(96, 6000, seed=11)
