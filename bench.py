@@ -30,9 +30,28 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL writes "NCCL version ..." to STDOUT at debug level VERSION; stdout carries exactly one JSON line here.
+# stdout carries exactly one JSON line. Libraries write there too (NCCL prints "NCCL version ..." to stdout from C), so
+# file descriptor 1 is pointed at stderr for the life of the process and the JSON line goes to a private copy of the
+# original stdout.
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 N_GENOMES = 2504
 N_LOCI = 1_100_000
@@ -123,7 +142,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------- clocks ---------
@@ -362,7 +381,7 @@ def run_ours(args):
                                         "sample": r["sample"]}
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -548,6 +567,7 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
 
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
