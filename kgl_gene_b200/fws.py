@@ -30,8 +30,15 @@ def calc_fws(ctx, pop: int = 0, bins=FWS_BINS):
     lower = [b[0] for b in bins]
     upper = [b[1] for b in bins]
     counts, rows = ctx.binned_genome_counts(lower, upper, pop=pop, present_only=True)
-    return {"variant_summary": lc[:, :3].copy(), "present": (lc[:, 1] + lc[:, 2]) > 0,
-            "genome_bins": counts[:, :, :3].copy(), "bin_variants": rows}
+    # AlleleSummmary counts copies of THIS variant (kgl_variant_db_variant.cpp:73-103): a genome that carries some other
+    # allele at the offset (code 3) has none and is referenceHomozygous_ for the column -- pinned against the reference's
+    # own CalcFWS in tests/golden (ref_fws_genome, ref_fws_variant).
+    variant_summary = lc[:, :3].copy()
+    variant_summary[:, 0] += lc[:, 3]
+    genome_bins = counts[:, :, :3].copy()
+    genome_bins[:, :, 0] += counts[:, :, 3]
+    return {"variant_summary": variant_summary, "present": (lc[:, 1] + lc[:, 2]) > 0,
+            "genome_bins": genome_bins, "bin_variants": rows}
 
 
 def hetero_homo_summary(genome_counts: np.ndarray) -> dict:

@@ -25,6 +25,7 @@
 #include "kgl_variant_factory_vcf_evidence.h"
 #include "kga_analysis_inbreed_calc.h"
 #include "kga_analysis_inbreed_locus.h"
+#include "kga_analysis_PfEMP_FWS.h"
 
 #include "flat_io.h"
 #include "ref_population.h"
@@ -63,6 +64,7 @@ struct Options {
   long seed{-1};      // >= 0: std::random_device is pinned to this value (see ref_stubs.cpp)
   size_t repeat{1};   // time the per-genome fan-out this many times (bench.py --impl reference)
   bool variantdb{true};
+  bool fws{false};
   bool quiet{true};
 };
 Options g_opt;
@@ -236,6 +238,39 @@ void run() {
     out.addU64("summary_population", {3}, pop);
     out.addF64("variantdb_meta", {3}, std::vector<double>{double(variant_db.variantMap().size()), double(variant_db.genomeMap().size()), seconds});
   }
+  // ---- CalcFWS (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:15-101) on a population whose variants carry the INFO AF ----------
+  if (g_opt.fws) {
+    t0 = Clock::now();
+    kglref::BuiltPopulations pf = kglref::buildPopulations(flat, kgl::DataSourceEnum::Genome1000, kgl::DataSourceEnum::Genome1000, true);
+    kga::CalcFWS calc_fws;
+    calc_fws.calcFwsStatistics(pf.diploid);
+    constexpr size_t B = kga::FWS_FREQUENCY_ARRAY_SIZE;
+    std::vector<uint64_t> fws_genome(size_t(N) * B * 3, 0), fws_variant(size_t(L) * 3, 0);
+    std::vector<uint32_t> fws_genome_present(N, 0), fws_variant_present(L, 0);
+    for (uint32_t g = 0; g < N; ++g) {
+      auto it = calc_fws.getGenomeMap().find(pf.genome_ids[g]);
+      if (it == calc_fws.getGenomeMap().end()) continue;
+      fws_genome_present[g] = 1;
+      for (size_t b = 0; b < B; ++b) {
+        const auto& s = it->second[b];
+        fws_genome[(g * B + b) * 3 + 0] = s.referenceHomozygous_; fws_genome[(g * B + b) * 3 + 1] = s.minorHeterozygous_;
+        fws_genome[(g * B + b) * 3 + 2] = s.minorHomozygous_;
+      }
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+      auto it = calc_fws.getVariantMap().find(pf.locus_variant[l]->HGVS());
+      if (it == calc_fws.getVariantMap().end()) continue;
+      fws_variant_present[l] = 1;
+      fws_variant[l * 3 + 0] = it->second.referenceHomozygous_; fws_variant[l * 3 + 1] = it->second.minorHeterozygous_;
+      fws_variant[l * 3 + 2] = it->second.minorHomozygous_;
+    }
+    std::fprintf(stderr, "[ref] CalcFWS            %zu genomes x %zu bins  %.3f s\n", calc_fws.getGenomeMap().size(), B,
+                 std::chrono::duration<double>(Clock::now() - t0).count());
+    out.addU64("fws_genome", {N, B, 3}, fws_genome);            // refHom, het, minorHom per genome per AF bin
+    out.addU32("fws_genome_present", {N}, fws_genome_present);
+    out.addU64("fws_variant", {L, 3}, fws_variant);             // per "A>G" variant over all genomes
+    out.addU32("fws_variant_present", {L}, fws_variant_present);
+  }
   out.write(g_opt.out_path);
 }
 
@@ -274,6 +309,7 @@ class HarnessEnv {
       else if (a == "--seed") g_opt.seed = std::stol(next());
       else if (a == "--repeat") g_opt.repeat = std::max<size_t>(1, std::stoull(next()));
       else if (a == "--no-variantdb") g_opt.variantdb = false;
+      else if (a == "--fws") g_opt.fws = true;
       else if (a == "--verbose") g_opt.quiet = false;
       else pos.push_back(a);
     }

@@ -44,7 +44,11 @@ struct BuiltPopulations {
   std::vector<std::shared_ptr<const kgl::Variant>> locus_variant;   // phase-A copy of every locus' "A>G" variant
 };
 
-inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSourceEnum af_source, kgl::DataSourceEnum diploid_source) {
+// diploid_evidence: the genotype population's own "A>G" variants carry the locus' INFO block (as the variants of a Pf7 VCF
+// do) -- what P7FrequencyFilter (kgl_variant_filter_Pf7.cpp:20-66) reads in CalcFWS. The "A>T" stand-ins of code 3 stay
+// without evidence: a variant without the AF field passes both frequency filters and therefore lands in no bin.
+inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSourceEnum af_source, kgl::DataSourceEnum diploid_source,
+                                         bool diploid_evidence = false) {
   const uint32_t N = flat.N(), L = flat.L();
   const bool unphased = (flat.hdr.flags & kglflat::FLAG_UNPHASED) != 0;
   const char* const* fields = afFields(af_source);
@@ -63,6 +67,8 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
   // ---- AF "genome": 1 genome, 1 contig (kga_analysis_inbreed_diploid.cpp:26,36) --------------------
   out.af_population = std::make_shared<kgl::PopulationDB>("AF_POPULATION", af_source);
   const std::vector<kgl::GenomeId_t> af_genome{"AF_GENOME"};
+  std::vector<kgl::VariantEvidence> locus_evidence;
+  if (diploid_evidence) locus_evidence.reserve(L);
   for (uint32_t l = 0; l < L; ++l) {
     std::string info;
     for (int k = 0; k < 6; ++k) {
@@ -74,6 +80,7 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
     }
     auto block = evidence_factory.createVariantEvidence(std::move(info));
     kgl::VariantEvidence evidence(l, af_source, true, block, nullptr, 0, 1);
+    if (diploid_evidence) locus_evidence.emplace_back(l, diploid_source, true, block, nullptr, 0, 1);
     auto variant = std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], kgl::VariantPhase::UNPHASED, "",
                                                         kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
                                                         kgl::DNA5SequenceLinear(kgl::StringDNA5("G")), evidence);
@@ -87,9 +94,10 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
   out.locus_variant.resize(L);
   const kgl::VariantEvidence no_evidence(0, diploid_source, true, nullptr, nullptr, 0, 1);
   auto make = [&](uint32_t l, kgl::VariantPhase phase, const char* alt) {
+    const bool with_info = diploid_evidence && alt[0] == 'G';
     return std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], phase, "",
                                                 kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
-                                                kgl::DNA5SequenceLinear(kgl::StringDNA5(alt)), no_evidence);
+                                                kgl::DNA5SequenceLinear(kgl::StringDNA5(alt)), with_info ? locus_evidence[l] : no_evidence);
   };
   std::vector<kgl::GenomeId_t> first, second, other;
   for (uint32_t l = 0; l < L; ++l) {

@@ -19,6 +19,7 @@
 #include "kel_optimize.h"
 #include "kgl_variant_factory_vcf_parse_cigar.h"
 #include "kgl_genome_genome.h"
+#include "kgl_pf7_fws_parser.h"
 
 #include <algorithm>
 #include <atomic>
@@ -242,3 +243,8 @@ std::string kgl::ParseVCFCigar::generateCigar(const std::string& reference, cons
 std::optional<std::shared_ptr<const kgl::ContigReference>> kgl::GenomeReference::getContigSequence(const ContigId_t&) const {
   return std::nullopt;
 }
+
+// CalcFWS::writeGenomeResults (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:147) looks the published FWS of a sample up in the Pf7
+// metadata resource, whose parser needs the Boost-based file IO. The harness only calls CalcFWS::calcFwsStatistics; the
+// writer is never reached.
+double kgl::Pf7FwsResource::getFWS(const GenomeId_t&) const { return 0.0; }

@@ -43,7 +43,7 @@ def main():
             pop.af[:, ::7] = np.float32(0.995)
             pop.af[:, 3::11] = np.float32(0.0005)
             pop.af[:, 5::13] = np.float32(1.0)
-        ref = O.run_reference(pop, grid=21, **ref_kw)
+        ref = O.run_reference(pop, grid=21, fws=True, **ref_kw)
         stderr = ref.pop("_stderr")
         arrays = {"in_offsets": pop.offsets, "in_af": pop.af, "in_superpop": pop.superpop, "in_packed": pop.packed,
                   "in_n_genomes": np.array([pop.n_genomes]), "in_unphased": np.array([int(pop.unphased)]),

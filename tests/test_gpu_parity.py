@@ -315,6 +315,19 @@ def test_gram_full_width_identity(gpu):
     assert np.array_equal(d[:, None] + d[None, :] - 2 * g, ibs[..., 1] + 4 * ibs[..., 0])
 
 
+def test_golden_calc_fws(gpu, golden):
+    """CalcFWS against the reference's own kga_analysis_PfEMP_FWS.cpp (compiled into oracle/_ref, golden ref_fws_*): per-genome
+    AlleleSummmary in the eleven AF bins and the per-variant summaries, bit-exact."""
+    from kgl_gene_b200 import fws
+    name, pop, ref, _ = golden
+    gpu.upload_population(pop)
+    got = fws.calc_fws(gpu, pop=5)
+    assert np.array_equal(np.transpose(got["genome_bins"], (1, 0, 2)), ref["fws_genome"])
+    m = ref["fws_variant_present"] == 1
+    assert np.array_equal(got["present"], m)
+    assert np.array_equal(got["variant_summary"][m].astype(np.uint64), ref["fws_variant"][m])
+
+
 @pytest.mark.parametrize("n,l,miss,spectrum", [(131, 5000, 0.01, "sfs"), (500, 3000, 0.0, "dense"), (2504, 20000, 0.001, "sfs")])
 def test_fws_bins_match_oracle(gpu, n, l, miss, spectrum):
     """N1: CalcFWS per-genome AlleleSummmary in the eleven AF bins + per-variant summaries + HeteroHomoZygous / F_IS."""
@@ -325,9 +338,11 @@ def test_fws_bins_match_oracle(gpu, n, l, miss, spectrum):
     got = fws.calc_fws(gpu, pop=5)
     want, want_rows = O.fws_bins(pop, 5, fws.FWS_BINS)
     assert np.array_equal(got["bin_variants"], want_rows)
-    assert np.array_equal(got["genome_bins"], want[:, :, :3])
+    assert np.array_equal(got["genome_bins"][:, :, 1:], want[:, :, 1:3])
+    assert np.array_equal(got["genome_bins"][:, :, 0], want[:, :, 0] + want[:, :, 3])      # other-allele cells count as refHom
     olc, ogc = O.allele_count(pop)
-    assert np.array_equal(got["variant_summary"], olc[:, :3])
+    assert np.array_equal(got["variant_summary"][:, 1:], olc[:, 1:3])
+    assert np.array_equal(got["variant_summary"][:, 0], olc[:, 0] + olc[:, 3])
     # all loci, no presence filter: the bins partition the loci that have an AF value
     allc, rows = gpu.binned_genome_counts([0.0], [2.0], pop=5, present_only=False)
     assert int(rows[0]) == int((~np.isnan(pop.af[5])).sum())

@@ -88,6 +88,24 @@ def test_allele_summaries_match_variantdb(golden):
     assert np.array_equal(ref["summary_population"], sg[present].sum(axis=0))
 
 
+def test_calc_fws_restatement_matches_reference(golden):
+    """oracle_py.fws_bins against the reference's CalcFWS::calcFwsStatistics (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:15-101,
+    P7FrequencyFilter kgl_variant_filter_Pf7.cpp:20-66) run by the harness on a population whose variants carry INFO AF."""
+    from kgl_gene_b200.fws import FWS_BINS
+    name, pop, ref, _ = golden
+    want, rows = O.fws_bins(pop, 5, FWS_BINS)                       # [bin][genome][code]
+    got = ref["fws_genome"]                                          # [genome][bin]{refHom, het, minorHom}
+    w = np.transpose(want, (1, 0, 2))
+    assert np.array_equal(got[:, :, 1], w[:, :, 1]) and np.array_equal(got[:, :, 2], w[:, :, 2])
+    assert np.array_equal(got[:, :, 0], w[:, :, 0] + w[:, :, 3])     # a cell with another allele has no copy of this variant
+    assert np.array_equal(got.sum(axis=2), np.broadcast_to(rows[None, :], got.shape[:2]))   # every genome sees every column of its bin
+    lc, _ = O.allele_count(pop)
+    m = ref["fws_variant_present"] == 1
+    assert np.array_equal(m, (lc[:, 1] + lc[:, 2]) > 0)
+    fv = ref["fws_variant"]
+    assert np.array_equal(fv[m, 1], lc[m, 1]) and np.array_equal(fv[m, 2], lc[m, 2]) and np.array_equal(fv[m, 0], lc[m, 0] + lc[m, 3])
+
+
 def test_synthetic_generator_matches_numpy():
     from kgl_gene_b200.synth import make_population
     pop, f = make_population(77, 300, seed=5)
