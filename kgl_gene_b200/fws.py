@@ -41,21 +41,26 @@ def calc_fws(ctx, pop: int = 0, bins=FWS_BINS):
             "genome_bins": genome_bins, "bin_variants": rows}
 
 
-def hetero_homo_summary(genome_counts: np.ndarray) -> dict:
-    """HeteroHomoZygous::updateVariantAnalysisType for a biallelic SNP matrix, from the per-genome code counts
-    uint64[N][4] of kgl_b200_run_allele_count: a het cell is one variant entry at its offset, a hom-alt cell two.
+def hetero_homo_summary(genome_counts: np.ndarray, other_allele_entries: int = 1) -> dict:
+    """HeteroHomoZygous::updateVariantAnalysisType (kga_analysis_PfEMP_heterozygous.cpp:61-105) for a biallelic SNP matrix, from
+    the per-genome code counts uint64[N][4] of kgl_b200_run_allele_count: a het cell is one variant entry at its offset, a
+    hom-alt cell two, a code-3 cell `other_allele_entries` entries of some other allele (1 = the flattener's usual case and
+    what the reference harness builds; 0 = the cell carries nothing, e.g. a missing call).
 
-      total_variants_ = snp_count_                       = n1 + 2 n2     (every entry is a SNP here; indel_count_ = 0)
-      heterozygous_reference_minor_alleles_              = n1            (offsets with exactly one entry, :85-87)
-      homozygous_minor_alleles_                          = n2            (UniqueUnphasedFilter over two identical entries, :93-96)
-      heterozygous_minor_alleles_                        = 0             (needs two different alts at one offset)
+      total_variants_ = snp_count_                       = n1 + 2 n2 + n3  (every entry is a SNP here; indel_count_ = 0)
+      heterozygous_reference_minor_alleles_              = n1 + n3         (offsets with exactly one entry, :85-87)
+      homozygous_minor_alleles_                          = n2              (UniqueUnphasedFilter over two identical entries, :93-96)
+      heterozygous_minor_alleles_                        = 0               (needs two different alts at one offset)
+
+    Pinned against the reference's own translation unit (tests/golden, ref_hetero_homo).
     """
     n1 = genome_counts[:, 1].astype(np.uint64)
     n2 = genome_counts[:, 2].astype(np.uint64)
-    total = n1 + 2 * n2
+    n3 = genome_counts[:, 3].astype(np.uint64) * np.uint64(1 if other_allele_entries else 0)
+    total = n1 + 2 * n2 + n3
     return {"total_variants": total, "snp_count": total.copy(), "indel_count": np.zeros_like(total),
-            "heterozygous_reference_minor_alleles": n1, "homozygous_minor_alleles": n2,
-            "heterozygous_minor_alleles": np.zeros_like(total)}
+            "heterozygous_reference_minor_alleles": n1 + n3, "homozygous_minor_alleles": n2,
+            "heterozygous_minor_alleles": np.zeros_like(total), "homozygous_reference_alleles": np.zeros_like(total)}
 
 
 def wrights_fis(summary: dict, location_of_genome: np.ndarray) -> np.ndarray:

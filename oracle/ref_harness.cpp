@@ -270,6 +270,20 @@ void run() {
     out.addU32("fws_genome_present", {N}, fws_genome_present);
     out.addU64("fws_variant", {L, 3}, fws_variant);             // per "A>G" variant over all genomes
     out.addU32("fws_variant_present", {L}, fws_variant_present);
+    // HeteroHomoZygous::updateVariantAnalysisType (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105), applied to every
+    // offset of every genome exactly as analyzeVariantPopulation does (:14-58); the harness population has one contig.
+    std::vector<uint64_t> hh(size_t(N) * 7, 0);
+    for (uint32_t g = 0; g < N; ++g) {
+      auto genome_opt = pf.diploid->getGenome(pf.genome_ids[g]);
+      if (!genome_opt) continue;
+      kga::VariantAnalysisType rec;
+      for (auto const& [contig_id, contig_ptr] : genome_opt.value()->getMap())
+        for (auto const& [offset, offset_ptr] : contig_ptr->getMap()) kga::HeteroHomoZygous::updateVariantAnalysisType(offset_ptr, rec);
+      hh[g * 7 + 0] = rec.total_variants_; hh[g * 7 + 1] = rec.snp_count_; hh[g * 7 + 2] = rec.indel_count_;
+      hh[g * 7 + 3] = rec.homozygous_minor_alleles_; hh[g * 7 + 4] = rec.heterozygous_minor_alleles_;
+      hh[g * 7 + 5] = rec.heterozygous_reference_minor_alleles_; hh[g * 7 + 6] = rec.homozygous_reference_alleles_;
+    }
+    out.addU64("hetero_homo", {N, 7}, hh);   // total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef
   }
   out.write(g_opt.out_path);
 }

@@ -6,6 +6,7 @@ REF_TUS := \
   kga_analytic/kga_inbreed/kga_analysis_inbreed_freq.cpp \
   kga_analytic/kga_inbreed/kga_analysis_inbreed_locus.cpp \
   kga_analytic/kga_PfEMP/kga_analysis_PfEMP_FWS.cpp \
+  kga_analytic/kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp \
   $(patsubst $(REF)/%,%,$(wildcard $(REF)/kgl_genomics/kgl_variant_db/*.cpp)) \
   $(patsubst $(REF)/%,%,$(wildcard $(REF)/kgl_genomics/kgl_variant_filter/*.cpp)) \
   $(patsubst $(REF)/%,%,$(wildcard $(REF)/kgl_genomics/kgl_evidence/*.cpp)) \

@@ -20,6 +20,7 @@
 #include "kgl_variant_factory_vcf_parse_cigar.h"
 #include "kgl_genome_genome.h"
 #include "kgl_pf7_fws_parser.h"
+#include "kgl_Pf7_physical_distance.h"
 
 #include <algorithm>
 #include <atomic>
@@ -248,3 +249,9 @@ std::optional<std::shared_ptr<const kgl::ContigReference>> kgl::GenomeReference:
 // metadata resource, whose parser needs the Boost-based file IO. The harness only calls CalcFWS::calcFwsStatistics; the
 // writer is never reached.
 double kgl::Pf7FwsResource::getFWS(const GenomeId_t&) const { return 0.0; }
+
+// HeteroHomoZygous::location_summary (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp) walks the Pf7 sample metadata (city /
+// country radii, FWS thresholds), whose parsers need the Boost-based file IO. The harness calls only the static per-offset
+// rule HeteroHomoZygous::updateVariantAnalysisType (:61-105); these two are never reached.
+std::vector<kgl::GenomeId_t> kgl::Pf7FwsResource::filterFWS(FwsFilterType, double, const std::vector<GenomeId_t>& sample_vector) const { return sample_vector; }
+std::vector<std::string> kgl::Pf7SampleLocation::sampleRadius(const std::string&, double, bool) const { return {}; }

@@ -29,8 +29,11 @@ def test_oracle_fws_bins_partition_present_variants():
 def test_hetero_homo_and_fis():
     gc = np.array([[10, 4, 1, 0], [8, 6, 1, 0], [12, 0, 0, 3], [5, 5, 5, 0]], dtype=np.uint64)
     s = fws.hetero_homo_summary(gc)
-    assert s["total_variants"].tolist() == [6, 8, 0, 15]
-    assert s["heterozygous_reference_minor_alleles"].tolist() == [4, 6, 0, 5]
+    assert s["total_variants"].tolist() == [6, 8, 3, 15]          # a code-3 cell is one entry of another allele
+    assert s["heterozygous_reference_minor_alleles"].tolist() == [4, 6, 3, 5]
+    s0 = fws.hetero_homo_summary(gc, other_allele_entries=0)       # ... or nothing at all (a missing call)
+    assert s0["total_variants"].tolist() == [6, 8, 0, 15] and s0["heterozygous_reference_minor_alleles"].tolist() == [4, 6, 0, 5]
+    s = s0
     assert s["homozygous_minor_alleles"].tolist() == [1, 1, 0, 5]
     fis = fws.wrights_fis(s, np.array([0, 0, 0, 1]))
     h_exp = 10 / 14

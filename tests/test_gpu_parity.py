@@ -326,6 +326,13 @@ def test_golden_calc_fws(gpu, golden):
     m = ref["fws_variant_present"] == 1
     assert np.array_equal(got["present"], m)
     assert np.array_equal(got["variant_summary"][m].astype(np.uint64), ref["fws_variant"][m])
+    # HeteroHomoZygous::updateVariantAnalysisType run by the harness over every offset of every genome
+    _, gc = gpu.allele_count()
+    hh = fws.hetero_homo_summary(gc)
+    want = ref["hetero_homo"]       # total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef
+    for j, key in enumerate(["total_variants", "snp_count", "indel_count", "homozygous_minor_alleles", "heterozygous_minor_alleles",
+                             "heterozygous_reference_minor_alleles", "homozygous_reference_alleles"]):
+        assert np.array_equal(hh[key], want[:, j]), key
 
 
 @pytest.mark.parametrize("n,l,miss,spectrum", [(131, 5000, 0.01, "sfs"), (500, 3000, 0.0, "dense"), (2504, 20000, 0.001, "sfs")])
@@ -352,7 +359,7 @@ def test_fws_bins_match_oracle(gpu, n, l, miss, spectrum):
     _, gc = gpu.allele_count()
     hh = fws.hetero_homo_summary(gc)
     codes = pop.codes()
-    assert np.array_equal(hh["total_variants"], ((codes == 1).sum(0) + 2 * (codes == 2).sum(0)).astype(np.uint64))
+    assert np.array_equal(hh["total_variants"], ((codes == 1).sum(0) + 2 * (codes == 2).sum(0) + (codes == 3).sum(0)).astype(np.uint64))
     fis = fws.wrights_fis(hh, pop.superpop)
     for k in np.unique(pop.superpop):
         m = pop.superpop == k

@@ -106,6 +106,19 @@ def test_calc_fws_restatement_matches_reference(golden):
     assert np.array_equal(fv[m, 1], lc[m, 1]) and np.array_equal(fv[m, 2], lc[m, 2]) and np.array_equal(fv[m, 0], lc[m, 0] + lc[m, 3])
 
 
+def test_hetero_homo_rule_matches_reference(golden):
+    """kgl_gene_b200.fws.hetero_homo_summary (host mirror of HeteroHomoZygous::updateVariantAnalysisType,
+    kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105) against the reference TU run over every offset of every genome."""
+    from kgl_gene_b200.fws import hetero_homo_summary
+    name, pop, ref, _ = golden
+    _, gc = O.allele_count(pop)
+    hh = hetero_homo_summary(gc)
+    want = ref["hetero_homo"]
+    for j, key in enumerate(["total_variants", "snp_count", "indel_count", "homozygous_minor_alleles", "heterozygous_minor_alleles",
+                             "heterozygous_reference_minor_alleles", "homozygous_reference_alleles"]):
+        assert np.array_equal(hh[key], want[:, j]), (name, key)
+
+
 def test_synthetic_generator_matches_numpy():
     from kgl_gene_b200.synth import make_population
     pop, f = make_population(77, 300, seed=5)
