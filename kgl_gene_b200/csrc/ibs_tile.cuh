@@ -233,8 +233,15 @@ k_ibs_premask(const uint4* __restrict__ lo, const uint4* __restrict__ hi, uint64
   hi_m[i] = make_uint4(b.x & ~a.x, b.y & ~a.y, b.z & ~a.z, b.w & ~a.w);
 }
 
-constexpr int kIbsFixLevels = 16;               // rows per genome between counter flushes: 65,535
+constexpr int kIbsFixLevels = 16;               // counter levels; 32,760 rows per genome between flushes
+constexpr int kIbsFixLow = 4;                   // levels 0..3 take 8 rows at a time; then level 3 (weight 8) moves into levels 4..15
 
+// Sparse repair of the code-3 cells (dense-minus-sparse). A thread owns one genome of one side of a tile and one
+// segment (blockIdx.y of gridDim.y) of that genome's dropped rows; it adds the partner unit's three 64-bit vectors (hom-alt,
+// het, code 3) into bit-sliced counters. The counters are two-stage: a row costs a ripple through levels 0..3; after 8 rows
+// (residue <= 7, so no carry leaves level 3) the bit of level 3 moves up, and levels 4..15 count units of 8 -- a third of the
+// logic of a 16-level ripple per row. With gridDim.y > 1 plane 2 (J) must be zero on
+// entry and is accumulated atomically.
 __global__ void __launch_bounds__(128)
 k_ibs_missing_fix(const uint4* __restrict__ packed, uint32_t units, const unsigned long long* __restrict__ keys,
                   const uint64_t* __restrict__ seg, uint64_t n_genomes, const uint2* __restrict__ tiles, uint32_t* __restrict__ acc) {
@@ -243,9 +250,14 @@ k_ibs_missing_fix(const uint4* __restrict__ packed, uint32_t units, const unsign
   const uint32_t side = threadIdx.x >> 6, al = threadIdx.x & 63;
   const uint64_t a = (uint64_t)(side ? tc.y : tc.x) * kIbsT + al;
   const uint32_t partner = side ? tc.x : tc.y;
+  const bool split = gridDim.y > 1;
   uint32_t* out = acc + (size_t)tile * 3 * kIbsTileCells;
   uint64_t k = 0, k_end = 0;
-  if (a < n_genomes) { k = seg[a]; k_end = seg[a + 1]; }
+  if (a < n_genomes) {
+    const uint64_t k0 = seg[a], len = seg[a + 1] - k0;
+    k = k0 + len * blockIdx.y / gridDim.y;
+    k_end = k0 + len * (blockIdx.y + 1) / gridDim.y;
+  }
   bool first = true;
   do {
     uint64_t cnt[3][kIbsFixLevels];
@@ -253,17 +265,32 @@ k_ibs_missing_fix(const uint4* __restrict__ packed, uint32_t units, const unsign
     for (int q = 0; q < 3; ++q)
 #pragma unroll
       for (int lv = 0; lv < kIbsFixLevels; ++lv) cnt[q][lv] = 0;
-    const uint64_t k_stop = min(k_end, k + (uint64_t)((1u << kIbsFixLevels) - 1));
-    for (; k < k_stop; ++k) {
-      const uint32_t row = (uint32_t)keys[k];
-      const uint4 v = __ldg(packed + (size_t)row * units + partner);
-      const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-      uint64_t x[3] = {hi & ~lo, lo & ~hi, lo & hi};
+    const uint64_t k_stop = min(k_end, k + (uint64_t)((1u << (kIbsFixLevels - 1)) - 8));
+    while (k < k_stop) {
+      const uint64_t k_low = min(k_stop, k + 8);
+      for (; k < k_low; ++k) {
+        const uint32_t row = (uint32_t)keys[k];
+        const uint4 v = __ldg(packed + (size_t)row * units + partner);
+        const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        uint64_t x[3] = {hi & ~lo, lo & ~hi, lo & hi};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          uint64_t carry = x[q];
+#pragma unroll
+          for (int lv = 0; lv < kIbsFixLow; ++lv) {
+            const uint64_t t = cnt[q][lv] & carry;
+            cnt[q][lv] ^= carry;
+            carry = t;
+          }
+        }
+      }
+      // the low counter held at most 7 before these <= 8 rows: its level 3 (weight 8) moves into level 4 (weight 8) and clears
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        uint64_t carry = x[q];
+        uint64_t carry = cnt[q][kIbsFixLow - 1];
+        cnt[q][kIbsFixLow - 1] = 0;
 #pragma unroll
-        for (int lv = 0; lv < kIbsFixLevels; ++lv) {
+        for (int lv = kIbsFixLow; lv < kIbsFixLevels; ++lv) {
           const uint64_t t = cnt[q][lv] & carry;
           cnt[q][lv] ^= carry;
           carry = t;
@@ -276,14 +303,19 @@ k_ibs_missing_fix(const uint4* __restrict__ packed, uint32_t units, const unsign
       for (int q = 0; q < 3; ++q) {
         uint32_t s = 0;
 #pragma unroll
-        for (int lv = 0; lv < kIbsFixLevels; ++lv) s |= (uint32_t)((cnt[q][lv] >> b) & 1ull) << lv;
+        for (int lv = 0; lv < kIbsFixLow - 1; ++lv) s += (uint32_t)((cnt[q][lv] >> b) & 1ull) << lv;
+        // level kIbsFixLow - 1 was moved up: levels >= kIbsFixLow count units of 2^(kIbsFixLow - 1)
+#pragma unroll
+        for (int lv = kIbsFixLow; lv < kIbsFixLevels; ++lv) s += (uint32_t)((cnt[q][lv] >> b) & 1ull) << (lv - 1);
         c[q] = s;
       }
       const uint32_t cell = side ? (uint32_t)b * kIbsT + al : al * kIbsT + (uint32_t)b;
       if (c[0]) atomicSub(out + cell, c[0]);
       if (c[1]) atomicSub(out + kIbsTileCells + cell, c[1]);
       if (side == 0) {                            // J is symmetric: side 0 alone writes it
-        if (first) out[2 * kIbsTileCells + cell] = c[2]; else if (c[2]) out[2 * kIbsTileCells + cell] += c[2];
+        if (split) { if (c[2]) atomicAdd(out + 2 * kIbsTileCells + cell, c[2]); }
+        else if (first) out[2 * kIbsTileCells + cell] = c[2];
+        else if (c[2]) out[2 * kIbsTileCells + cell] += c[2];
       }
     }
     first = false;

@@ -687,8 +687,16 @@ int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const ui
   ++c->launches;
   if (e1) KGL_CUDA(c, cudaEventRecord(e1, c->stream));
   if (c->ibs_mode == 2) {
-    k_ibs_missing_fix<<<n, 128, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), (uint32_t)c->units, c->d_dropped.p,
-                                                 c->d_dropped_seg.p, c->N, c->d_ibs_tiles.p, c->d_ibs_acc.p);
+    // every genome's dropped rows are cut into segments so that the repair fills the GPU also when few tiles are dealt to it
+    // (multi-GPU): about eight 128-thread CTAs per SM, and no segment shorter than ~256 rows on average
+    const uint64_t avg_rows = c->n_dropped / std::max<uint64_t>(1, c->N);
+    uint32_t segs = (uint32_t)std::max<uint64_t>(1, ((uint64_t)c->sm_count * 8 + n - 1) / n);
+    segs = (uint32_t)std::min<uint64_t>(segs, std::max<uint64_t>(1, avg_rows / 256));
+    segs = std::min<uint32_t>(segs, 64);
+    if (segs > 1 && pl.n_chunks == 1)      // plane 2 (J) is accumulated atomically then: clear it (the whole buffer is cleared when chunked)
+      KGL_CUDA(c, cudaMemset2DAsync(c->d_ibs_acc.p + 2 * kIbsTileCells, (size_t)3 * kIbsTileCells * 4, 0, (size_t)kIbsTileCells * 4, n, c->stream));
+    k_ibs_missing_fix<<<dim3(n, segs), 128, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), (uint32_t)c->units, c->d_dropped.p,
+                                                             c->d_dropped_seg.p, c->N, c->d_ibs_tiles.p, c->d_ibs_acc.p);
     KGL_LAUNCH_CHECK(c);
   }
   return KGL_B200_OK;
