@@ -124,6 +124,31 @@ def cpu_reference_run(repeat: int):
     return dict(cells=cells, seconds=secs, cores=cores, kind=kind, sample=what)
 
 
+def cpu_port_run():
+    """SURVEY 8d (ii), the "fair CPU" line: the flat C restatement (oracle/kgl_oracle.c, OpenMP over genomes) doing counts +
+    Simple on a bounded sample of the same generator, all host threads. Reported next to the reference figure; never the
+    thing measured as the product."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import make_genomes, make_loci
+    n, l = 2504, 40_000
+    offsets, af = make_loci(l, SEED)
+    superpop, inbreeding = make_genomes(n, SEED)
+    pop = FlatPopulation(offsets, af, superpop, O.synth_genotypes(SEED, n, l, af, superpop, inbreeding), n, False)
+    sel = O.select_all_pops(pop)
+    O.inbreed(pop, sel, "Simple")
+    secs = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        O.allele_count(pop)
+        O.inbreed(pop, sel, "Simple")
+        secs.append(time.perf_counter() - t0)
+    cores = O.threads()
+    return {"value": float(n) * float(l) / float(np.median(secs)), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle C restatement on the flat 2-bit matrix (OpenMP, {cores} threads): allele counts + Simple on {n} genomes x {l} loci of the bench generator"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -381,6 +406,10 @@ def run_ours(args):
                                         "sample": r["sample"]}
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+            try:
+                line["cpu_baseline_port"] = cpu_port_run()
+            except Exception as ex:
+                line["cpu_baseline_port"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
         emit(line)
     ctx.close()
     if world > 1:
