@@ -73,6 +73,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-kinship", action="store_true")
     ap.add_argument("--no-estimators", action="store_true", help="skip the RitlandLocus / HallME / Loglikelihood timings")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-genome partial sums of the locus shards meet -- 'peer': inside the step's own kernel over "
+                         "NVLink peer memory (CUDA IPC); 'nccl': an NCCL all-reduce between the step's kernels")
     ap.add_argument("--kinship-loci", type=int, default=0, help="loci of the pairwise run (0 = the resident chr22-shape matrix)")
     ap.add_argument("--kinship-steps", type=int, default=3)
     return ap.parse_args()
@@ -266,14 +269,34 @@ def run_ours(args):
         t = torch.as_tensor(RawCudaArray(ptr, cnt, "<f8"), device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
+    def step_nccl():
+        ctx.inbreed_begin("Simple", count_loci=True)
+        ctx.inbreed_accumulate()
+        allreduce_partials()
+        ctx.inbreed_update()
+
+    use_peer = world > 1 and args.exchange == "peer"
+    if use_peer:
+        # exchange regions of all ranks, mapped into every rank once (CUDA IPC handles travel over the process group)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_export())
+        ctx.peer_attach(rank, world, handles)
+        # the fused exchange against the NCCL path, once, before anything is timed
+        step_nccl()
+        want = ctx.inbreed_fetch()
+        ctx.enqueue_count_and_inbreed_peer()
+        got = ctx.inbreed_fetch()
+        for fld in ("major_homo_count", "major_hetero_count", "minor_homo_count", "minor_hetero_count", "total_allele_count"):
+            assert np.array_equal(got[fld], want[fld]), fld
+        assert np.max(np.abs(got["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-12, "peer exchange differs from the NCCL all-reduce"
+
     def step_resident():
         if world == 1:
             ctx.enqueue_count_and_inbreed()
+        elif use_peer:
+            ctx.enqueue_count_and_inbreed_peer()
         else:
-            ctx.inbreed_begin("Simple", count_loci=True)
-            ctx.inbreed_accumulate()
-            allreduce_partials()
-            ctx.inbreed_update()
+            step_nccl()
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -335,10 +358,10 @@ def run_ours(args):
             if world == 1:
                 ctx.count_and_inbreed_into(h_lc.data_ptr(), h_res.data_ptr())
             else:
-                ctx.inbreed_begin("Simple", count_loci=True)
-                ctx.inbreed_accumulate()
-                allreduce_partials()
-                ctx.inbreed_update()
+                if use_peer:
+                    ctx.enqueue_count_and_inbreed_peer()
+                else:
+                    step_nccl()
                 ctx._check(ctx.lib.kgl_b200_inbreed_fetch(ctx.h, C.c_void_p(h_res.data_ptr())), "inbreed_fetch")
                 ctx._check(ctx.lib.kgl_b200_fetch_locus_counts(ctx.h, C.c_void_p(h_lc.data_ptr())), "fetch_locus_counts")
 
@@ -385,7 +408,10 @@ def run_ours(args):
             "config": {"workload": workload_name(n, l, world), "n_genomes": n, "n_loci_per_gpu": l, "af_vectors": int(af.shape[0]),
                        "selection": "one window, all loci", "missing_rate": 0.001,
                        "l2": f"inputs ({l * rb / 1e6:.0f} MB matrix per GPU) are larger than the 126 MB L2; no flush needed",
-                       "step": "k_locus_prepare (flags + dense totals) + k_stream_count_ct + k_post (counter expansion | code-3 cells | rare-major rows) + k_moment_partials (+ NCCL all-reduce + k_finalize_closed_form at N > 1)"},
+                       "step": "k_locus_prepare (flags + dense totals) + k_stream_count_ct + k_post (counter expansion | code-3 cells | rare-major rows) + k_moment_partials"
+                               + ("" if world == 1 else (" + k_peer_exchange (signal, wait, gather the partial sums of all ranks over NVLink peer memory, fixed-order sum, closed form; no NCCL call in the step)"
+                                                         if use_peer else " + NCCL all-reduce + k_finalize_closed_form")),
+                       "exchange": None if world == 1 else args.exchange},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": stream_kernel_name(n), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

@@ -209,6 +209,19 @@ int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* ctx, void** device_ptr, uint6
 int kgl_b200_inbreed_update(kgl_b200_ctx* ctx, int* finished);
 int kgl_b200_inbreed_fetch(kgl_b200_ctx* ctx, kgl_b200_locus_results* out);
 
+/* The same locus-sharded step (allele counts + Simple, one rank per GPU of one node) with the exchange done by the step's
+ * own kernel over NVLink peer memory instead of an all-reduce by the caller: every rank exports its exchange region once
+ * (a CUDA IPC handle of KGL_B200_PEER_HANDLE_BYTES bytes, after its matrix is on the device), the caller gathers the
+ * handles of all ranks (any transport) and attaches them; each kgl_b200_enqueue_count_and_inbreed_peer() then runs the fused
+ * pass on the rank's shard and one kernel that signals the peers, waits for their partial sums, adds them in rank order and
+ * applies the closed form. All ranks must call it the same number of times. Results: kgl_b200_inbreed_fetch,
+ * kgl_b200_fetch_locus_counts. Replaces InbreedingAnalysis::processResults' per-genome fan-out over one population
+ * (kga_analysis_inbreed_diploid.cpp:98-160) when that population is sharded by locus over GPUs. */
+#define KGL_B200_PEER_HANDLE_BYTES 64
+int kgl_b200_peer_export(kgl_b200_ctx* ctx, void* handle /* KGL_B200_PEER_HANDLE_BYTES */);
+int kgl_b200_peer_attach(kgl_b200_ctx* ctx, uint32_t rank, uint32_t world, const void* handles /* world x KGL_B200_PEER_HANDLE_BYTES */);
+int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

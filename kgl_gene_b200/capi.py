@@ -33,6 +33,7 @@ EXPORTS = [
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
     "kgl_b200_inbreed_fetch", "kgl_b200_kernel_timer_reset", "kgl_b200_kernel_timer_read", "kgl_b200_fetch_locus_counts",
+    "kgl_b200_peer_export", "kgl_b200_peer_attach", "kgl_b200_enqueue_count_and_inbreed_peer",
 ]
 
 
@@ -307,6 +308,20 @@ class KglB200:
         lc = np.zeros((self.n_loci, 4), dtype=np.uint32)
         self._check(self.lib.kgl_b200_fetch_locus_counts(self.h, _ptr(lc)), "fetch_locus_counts")
         return lc
+
+    def peer_export(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's exchange region; gather the handles of all ranks and peer_attach them."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.kgl_b200_peer_export(self.h, buf), "peer_export")
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, handles: list[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._check(self.lib.kgl_b200_peer_attach(self.h, C.c_uint32(rank), C.c_uint32(world), C.c_char_p(blob)), "peer_attach")
+
+    def enqueue_count_and_inbreed_peer(self):
+        self._check(self.lib.kgl_b200_enqueue_count_and_inbreed_peer(self.h), "enqueue_count_and_inbreed_peer")
 
     def inbreed_begin(self, algorithm: str, hall_start=None, hall_sweeps=0, ll_tolerance=0.0, ll_max_iterations=0, count_loci=False):
         opt = InbreedOptions()

@@ -124,6 +124,12 @@ struct kgl_b200_ctx {
   // Newton sweep, chunk outputs of the exact fallback
   DevBuf<double> d_limits, d_slow_out;
   DevBuf<uint8_t> d_lane_state;
+  // peer-memory exchange of the locus-sharded step (misc_kernels.cuh, k_peer_exchange)
+  DevBuf<unsigned char> d_xchg;
+  uint64_t xchg_npad = 0, peer_epoch = 0;
+  uint32_t peer_rank = 0, peer_world = 0;
+  std::vector<void*> peer_base;           // mapped exchange regions of the other ranks (nullptr for our own slot)
+  double* partials_target = nullptr;      // where the moment kernels write (d_partials unless a peer step redirects them)
   DevBuf<uint32_t> d_n_slow, d_list;    // d_list: genomes whose root search is still running (late Newton sweeps)
   uint64_t list_len = 0;
   bool limits_valid = false;
@@ -449,7 +455,8 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
       Q.superpop = mo ? mo->zero_superpop : c->d_superpop.p; Q.af = c->d_af.p;
       Q.so = so;
       Q.tail_mode = c->fused_tail ? tail_mode : 0; Q.unphased = c->unphased ? 1 : 0;
-      Q.totals = c->prep[c->par].totals.p; Q.partials = c->d_partials.p; Q.results = simple_results ? c->d_results.p : nullptr;
+      Q.totals = c->prep[c->par].totals.p; Q.partials = c->partials_target ? c->partials_target : c->d_partials.p;
+      Q.results = simple_results ? c->d_results.p : nullptr;
       Q.genome_counts = c->d_genome_counts.p; Q.ticket = c->d_ticket.p;
       KGL_CUDA(c, ensure_tickets(c));
       k_post<<<e_bx * e_by + Q.d_blocks + Q.r_blocks, 256, 0, c->stream>>>(Q);
@@ -484,7 +491,8 @@ int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results
   if (rc) return rc;
   if (c->tail_done) return KGL_B200_OK;
   k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->prep[c->par].totals.p, c->d_ecorr, c->d_nz_rare,
-                                                                  c->d_superpop.p, c->N, c->unphased ? 1 : 0, c->d_partials.p,
+                                                                  c->d_superpop.p, c->N, c->unphased ? 1 : 0,
+                                                                  c->partials_target ? c->partials_target : c->d_partials.p,
                                                                   simple_results ? c->d_results.p : nullptr);
   KGL_LAUNCH_CHECK(c);
   return KGL_B200_OK;
@@ -817,6 +825,8 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
   c->d_bin_flags.release(); c->d_bin_sum64.release(); c->d_bin_popmask32.release(); c->d_bin_state.release(); c->d_bin_need32.release();
   c->d_zero_superpop.release(); c->d_bin_out.release();
+  for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
+  c->peer_base.clear(); c->d_xchg.release();
   c->d_list.release(); c->d_sm_codes.release(); c->d_limits.release(); c->d_slow_out.release(); c->d_lane_state.release(); c->d_n_slow.release();
   c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
   if (c->gram_e0) cudaEventDestroy(c->gram_e0);
@@ -1114,6 +1124,69 @@ int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   c->prep_valid = false;   // the AF vectors are an input of the pass: the per-locus preparation is part of every step
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
   return enqueue_moments(c, true, true);
+}
+
+// ---- locus-sharded step with the exchange over peer memory -----------------------------------------------------------
+static size_t xchg_bytes(uint64_t npad) { return (size_t)2 * npad * PART_COUNT * 8 + kPeerMaxRanks * 8; }
+
+int kgl_b200_peer_export(kgl_b200_ctx* c, void* handle) {
+  if (!c || !handle) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  if (c->Npad == 0) return fail(c, KGL_B200_ERR_STATE, "upload the genotype matrix (or synthesise it) before exporting the exchange region");
+  static_assert(sizeof(cudaIpcMemHandle_t) == KGL_B200_PEER_HANDLE_BYTES, "handle size");
+  for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
+  c->peer_base.clear(); c->peer_world = 0;
+  KGL_CUDA(c, c->d_xchg.ensure(xchg_bytes(c->Npad)));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_xchg.p, 0, xchg_bytes(c->Npad), c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->xchg_npad = c->Npad; c->peer_epoch = 0;
+  cudaIpcMemHandle_t h;
+  KGL_CUDA(c, cudaIpcGetMemHandle(&h, c->d_xchg.p));
+  std::memcpy(handle, &h, sizeof h);
+  return KGL_B200_OK;
+}
+
+int kgl_b200_peer_attach(kgl_b200_ctx* c, uint32_t rank, uint32_t world, const void* handles) {
+  if (!c || !handles) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (world == 0 || world > (uint32_t)kPeerMaxRanks || rank >= world) return fail(c, KGL_B200_ERR_INVALID, "bad rank / world");
+  if (c->d_xchg.p == nullptr || c->xchg_npad != c->Npad) return fail(c, KGL_B200_ERR_STATE, "kgl_b200_peer_export first");
+  int rc = use_device(c); if (rc) return rc;
+  c->peer_base.assign(world, nullptr);
+  for (uint32_t r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * sizeof h, sizeof h);
+    void* p = nullptr;
+    KGL_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[r] = p;
+  }
+  c->peer_rank = rank; c->peer_world = world;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, true); if (rc) return rc;
+  if (c->peer_world == 0 || c->xchg_npad != c->Npad) return fail(c, KGL_B200_ERR_STATE, "kgl_b200_peer_export / kgl_b200_peer_attach first");
+  c->prep_valid = false;   // the AF vectors are an input of the pass, as in kgl_b200_enqueue_count_and_inbreed
+  KGL_CUDA(c, c->d_results.ensure(c->Npad));
+  KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
+  KGL_CUDA(c, ensure_tickets(c));
+  const uint64_t epoch = ++c->peer_epoch;
+  const uint64_t parity_doubles = c->Npad * PART_COUNT;
+  c->partials_target = reinterpret_cast<double*>(c->d_xchg.p) + (epoch & 1ull) * parity_doubles;
+  rc = enqueue_moments(c, true, false);
+  c->partials_target = nullptr;
+  if (rc) return rc;
+  PeerParams P{};
+  for (uint32_t r = 0; r < c->peer_world; ++r) P.base[r] = static_cast<unsigned char*>(r == c->peer_rank ? (void*)c->d_xchg.p : c->peer_base[r]);
+  P.rank = c->peer_rank; P.world = c->peer_world; P.parity_doubles = parity_doubles; P.epoch = epoch; P.n_genomes = c->N;
+  P.partials_out = c->d_partials.p; P.results = c->d_results.p; P.ticket = c->d_ticket.p;
+  k_peer_exchange<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  c->algo = KGL_B200_ALGO_SIMPLE; c->phase = 0;     // kgl_b200_inbreed_fetch copies d_results
+  return KGL_B200_OK;
 }
 
 int kgl_b200_fetch_locus_counts(kgl_b200_ctx* c, uint32_t* locus_counts) {

@@ -124,6 +124,71 @@ k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set h
   moment_partials_one(g, gcounts, n3s, totals, ecorr, nz_rare, superpop, unphased, partials, simple_out);
 }
 
+// ---- locus-sharded exchange over NVLink peer memory (kgl_b200_enqueue_count_and_inbreed_peer) ------------------------------
+// Every rank owns an exchange region [2 parities][n_genomes_padded][PART_COUNT] doubles + 64 flags, mapped into every peer
+// (CUDA IPC). A step: the moment kernel of rank r writes its partials into parity (epoch & 1) of its own region;
+// k_peer_exchange then (1) publishes `epoch` into flag[r] of every peer's region, (2) waits until its own flags of all
+// ranks have reached `epoch`, (3) reads the partials of every rank straight from peer memory, adds them in rank order (the same
+// order on every rank: bit-identical results everywhere) and applies the Simple closed form. One launch replaces
+// all-reduce + finalize; there is no NCCL call on the step's path. Two parities suffice: a rank can be at most one step ahead
+// of a peer, because its next exchange waits for that peer's next flag.
+constexpr int kPeerMaxRanks = 64;
+struct PeerParams {
+  unsigned char* base[kPeerMaxRanks];   // exchange regions, index = rank (own region included)
+  uint32_t rank, world;
+  uint64_t parity_doubles;              // n_genomes_padded * PART_COUNT
+  uint64_t epoch;
+  uint64_t n_genomes;
+  double* partials_out;                 // reduced partials (local copy, for inbreed_fetch-style consumers)
+  kgl_b200_locus_results* results;
+  unsigned int* ticket;                 // zero-initialised; returns to zero
+};
+
+__device__ __forceinline__ unsigned long long* peer_flags(unsigned char* base, uint64_t parity_doubles) {
+  return reinterpret_cast<unsigned long long*>(base + 2 * parity_doubles * 8);
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_exchange(const PeerParams P) {
+  __shared__ int s_dummy;
+  // (1) publish: the moment kernel that preceded this launch on the stream has completed, its stores are in this GPU's L2
+  if (blockIdx.x == 0 && threadIdx.x < P.world) {
+    __threadfence_system();
+    unsigned long long* f = peer_flags(P.base[threadIdx.x], P.parity_doubles) + P.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"((unsigned long long)P.epoch) : "memory");
+  }
+  // (2) wait for every rank's flag in the local region
+  if (threadIdx.x < P.world) {
+    const unsigned long long* f = peer_flags(P.base[P.rank], P.parity_doubles) + threadIdx.x;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v < P.epoch) __nanosleep(100);
+    } while (v < P.epoch);
+  }
+  __syncthreads();
+  (void)s_dummy;
+  // (3) gather + fixed-order sum + closed form
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.n_genomes) return;
+  double sum[PART_COUNT];
+#pragma unroll
+  for (int j = 0; j < PART_COUNT; ++j) sum[j] = 0.0;
+  const uint64_t off = (P.epoch & 1ull) * P.parity_doubles + g * PART_COUNT;
+  for (uint32_t r = 0; r < P.world; ++r) {
+    const double* src = reinterpret_cast<const double*>(P.base[r]) + off;
+#pragma unroll
+    for (int j = 0; j < PART_COUNT; j += 2) {
+      double a, b;
+      asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(src + j) : "memory");
+      sum[j] += a; sum[j + 1] += b;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PART_COUNT; ++j) P.partials_out[g * PART_COUNT + j] = sum[j];
+  P.results[g] = closed_form(sum, KGL_B200_ALGO_SIMPLE);
+}
+
 // processHallME: f <- (1/n) * sum_hom f/(f+(1-f)a)   (calc.cpp:285). flag[0] = max |delta| bits (atomicMax on the ordered int).
 __global__ void __launch_bounds__(256)
 k_hall_update(const double* __restrict__ partials, const double* __restrict__ iter, uint64_t n_genomes, double* __restrict__ f,

@@ -3,6 +3,8 @@
 Integer results (allele counts, class counts, locus selection, IBS) must be bit-exact; floating-point results must
 agree within 1e-6 relative (BASELINE.json north_star) -- the assertions below use far tighter bounds where the
 arithmetic allows it."""
+import os
+
 import numpy as np
 import pytest
 
@@ -468,3 +470,22 @@ def test_full_width_properties_on_device_generated_population(gpu):
     assert np.all(counts[:, 4] <= l) and np.all(counts[:, 1] == gc[:, 1]) and np.all(counts[:, 2] == gc[:, 2])
     assert np.allclose(freqs.sum(axis=1), counts[:, 4], rtol=1e-12)                       # Q8: class frequencies sum to n
     assert np.corrcoef(res["inbred_allele_sum"], f)[0, 1] > 0.99                          # recovers the planted F
+
+
+def test_peer_exchange_two_gpus():
+    """Locus-sharded step with the exchange over NVLink peer memory (kgl_b200_enqueue_count_and_inbreed_peer): two ranks through
+    bench.py, which asserts the fused exchange against the NCCL all-reduce path before timing. Needs two GPUs."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "3", "--warmup", "3", "--loci", "200000",
+           "--no-kinship", "--no-estimators", "--no-e2e", "--no-cpu-baseline"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["config"]["exchange"] == "peer" and line["value"] > 0
