@@ -168,25 +168,38 @@ k_peer_exchange(const PeerParams P) {
   }
   __syncthreads();
   (void)s_dummy;
-  // (3) gather + fixed-order sum + closed form
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= P.n_genomes) return;
-  double sum[PART_COUNT];
+  // (3) gather + fixed-order sum + closed form. Eight lanes per genome, one pair of doubles each; the loads of up to eight
+  // ranks are in flight together (an NVLink round trip is ~1.5 us: serialised they would cost more than the all-reduce).
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t g = t >> 3;
+  const int jp = (int)(t & 7);
+  const bool live = g < P.n_genomes;
+  double s0 = 0.0, s1 = 0.0;
+  if (live) {
+    const uint64_t off = (P.epoch & 1ull) * P.parity_doubles + g * PART_COUNT + jp * 2;
+    for (uint32_t r0 = 0; r0 < P.world; r0 += 8) {
+      double a[8], b[8];
 #pragma unroll
-  for (int j = 0; j < PART_COUNT; ++j) sum[j] = 0.0;
-  const uint64_t off = (P.epoch & 1ull) * P.parity_doubles + g * PART_COUNT;
-  for (uint32_t r = 0; r < P.world; ++r) {
-    const double* src = reinterpret_cast<const double*>(P.base[r]) + off;
+      for (int i = 0; i < 8; ++i) {
+        a[i] = 0.0; b[i] = 0.0;
+        if (r0 + i < P.world) {
+          const double* src = reinterpret_cast<const double*>(P.base[r0 + i]) + off;
+          asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[i]), "=d"(b[i]) : "l"(src) : "memory");
+        }
+      }
 #pragma unroll
-    for (int j = 0; j < PART_COUNT; j += 2) {
-      double a, b;
-      asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(src + j) : "memory");
-      sum[j] += a; sum[j + 1] += b;
+      for (int i = 0; i < 8; ++i) if (r0 + i < P.world) { s0 += a[i]; s1 += b[i]; }    // rank order
     }
+    P.partials_out[g * PART_COUNT + jp * 2] = s0;
+    P.partials_out[g * PART_COUNT + jp * 2 + 1] = s1;
   }
+  __syncwarp();
+  if (live && jp == 0) {
+    double sum[PART_COUNT];
 #pragma unroll
-  for (int j = 0; j < PART_COUNT; ++j) P.partials_out[g * PART_COUNT + j] = sum[j];
-  P.results[g] = closed_form(sum, KGL_B200_ALGO_SIMPLE);
+    for (int j = 0; j < PART_COUNT; ++j) sum[j] = __ldcg(P.partials_out + g * PART_COUNT + j);
+    P.results[g] = closed_form(sum, KGL_B200_ALGO_SIMPLE);
+  }
 }
 
 // processHallME: f <- (1/n) * sum_hom f/(f+(1-f)a)   (calc.cpp:285). flag[0] = max |delta| bits (atomicMax on the ordered int).
