@@ -133,6 +133,7 @@ k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set h
 // all-reduce + finalize; there is no NCCL call on the step's path. Two parities suffice: a rank can be at most one step ahead
 // of a peer, because its next exchange waits for that peer's next flag.
 constexpr int kPeerMaxRanks = 64;
+constexpr unsigned long long kPeerTimeoutNs = 10ull * 1000 * 1000 * 1000;   // 10 s
 struct PeerParams {
   unsigned char* base[kPeerMaxRanks];   // exchange regions, index = rank (own region included)
   uint32_t rank, world;
@@ -150,24 +151,32 @@ __device__ __forceinline__ unsigned long long* peer_flags(unsigned char* base, u
 
 __global__ void __launch_bounds__(256)
 k_peer_exchange(const PeerParams P) {
-  __shared__ int s_dummy;
+  __shared__ int s_timed_out;
   // (1) publish: the moment kernel that preceded this launch on the stream has completed, its stores are in this GPU's L2
   if (blockIdx.x == 0 && threadIdx.x < P.world) {
     __threadfence_system();
     unsigned long long* f = peer_flags(P.base[threadIdx.x], P.parity_doubles) + P.rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"((unsigned long long)P.epoch) : "memory");
   }
-  // (2) wait for every rank's flag in the local region
+  // (2) wait for every rank's flag in the local region. A peer that never arrives (its process died) must not hang the GPU:
+  // after kPeerTimeoutNs the step gives up and every coefficient of this rank becomes NaN.
+  if (threadIdx.x == 0) s_timed_out = 0;
+  __syncthreads();
   if (threadIdx.x < P.world) {
     const unsigned long long* f = peer_flags(P.base[P.rank], P.parity_doubles) + threadIdx.x;
-    unsigned long long v;
+    unsigned long long v, t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (v < P.epoch) __nanosleep(100);
+      if (v < P.epoch) {
+        __nanosleep(100);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > kPeerTimeoutNs) { s_timed_out = 1; break; }
+      }
     } while (v < P.epoch);
   }
   __syncthreads();
-  (void)s_dummy;
+  const bool timed_out = s_timed_out != 0;
   // (3) gather + fixed-order sum + closed form. Eight lanes per genome, one pair of doubles each; the loads of up to eight
   // ranks are in flight together (an NVLink round trip is ~1.5 us: serialised they would cost more than the all-reduce).
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,7 +207,9 @@ k_peer_exchange(const PeerParams P) {
     double sum[PART_COUNT];
 #pragma unroll
     for (int j = 0; j < PART_COUNT; ++j) sum[j] = __ldcg(P.partials_out + g * PART_COUNT + j);
-    P.results[g] = closed_form(sum, KGL_B200_ALGO_SIMPLE);
+    kgl_b200_locus_results r = closed_form(sum, KGL_B200_ALGO_SIMPLE);
+    if (timed_out) r.inbred_allele_sum = __longlong_as_double(0x7ff8000000000000ll);
+    P.results[g] = r;
   }
 }
 
