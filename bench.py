@@ -444,7 +444,7 @@ def run_ours(args):
 
 # FP64 instructions per cell of the table-driven sweeps (kgl_gene_b200/csrc/terms_fast.cuh) and the measured DFMA issue rate
 # of one B200 (profiles/r01_pipe_rates_f64_kbench.log: 56.35 lanes per clk per SM x 148 SMs x 1.965 GHz).
-FP64_OPS_PER_CELL = {"HallME": 4, "Loglikelihood": 5}
+FP64_OPS_PER_CELL = {"HallME": 3.5, "Loglikelihood": 5}
 FP64_PEAK_OPS = 56.35 * 148 * 1.965e9
 
 

@@ -11,8 +11,9 @@
 // heterozygous or dropped code, ...) read a neutral entry (1e300 -> reciprocal 1e-300, absorbed by the sums), so the inner
 // loop has no predicate at all.
 //
-//   HALL    f/(f + (1-f) a) = 1/(1 + a k), k = (1-f)/f per genome    cell: DFMA, reciprocal (MUFU.RCP64H + 2 DFMA), DADD
-//   NEWTON  t = (1-a)/(a + f (1-a)) = 1/(f + r), r = a/(1-a)         cell: DADD, reciprocal, DADD (sum t), DFMA (sum t^2)
+//   HALL    f/(f + (1-f) a) = 1/(1 + a k), k = (1-f)/f per genome    3.5 FP64 instructions per cell
+//   NEWTON  t = (1-a)/(a + f (1-a)) = 1/(f + r), r = a/(1-a)         5 per cell (sum t, sum t^2)
+//           two cells share one reciprocal (MUFU.RCP64H + 2 DFMA): fast_cell2
 //   LIMITS  (once per root search) per genome: the left end of its feasible region fmin = max over homozygous cells of
 //           (1e-10 - a^2)/(a (1-a))  [prob = a^2 + f a (1-a) >= small_prob, calc.cpp:108-110] and the smallest 2 a a2 over its
 //           heterozygous cells -- so the Newton sweep needs no per-cell clamp test: a genome left of fmin is "clamped"
@@ -21,8 +22,8 @@
 //   RITLAND sum over cells of v[locus][code], v = (1/p - 1)[hom-alt, p > 0.001] - (1/q - 1)[non-reference, q > 0.01]: one
 //           DADD per cell; the hom-alt cells of p <= 0.001 loci are counted with a mask and POPC per word.
 // Late Newton sweeps gather only the genomes that are still searching (FastParams::list).
-// Measured on 2,504 x 1.1 M (B200): HALL 1.16 ms, NEWTON 1.33 ms per sweep = 61 % of the FP64 pipe's issue rate (ncu:
-// profiles/r01_terms_fast_newton_ncu_*); the cell-by-cell kernels they replace took 6.6 / 8.3 ms.
+// Measured on 2,504 x 1.1 M (B200): HALL 1.06 ms, NEWTON 1.27 ms per sweep = 56 / 65 % of the measured FP64 issue rate (ncu:
+// profiles/r01_terms_fast_{hall,newton}_ncu_*); the cell-by-cell kernels they replace took 6.6 / 8.3 ms.
 #pragma once
 #include "common.cuh"
 
@@ -31,12 +32,13 @@ namespace kgl {
 // FAST_NEWTON_U: unphased populations (Q6). A hom-alt pair is a heterozygous term 2 (1-f) p p there, which -- unlike 2 p q --
 // can exceed 1 and is then clamped (calc.cpp:124): the sweep also counts, per genome, the code-2 cells with 2 p p (1-f) > 1.
 enum { FAST_RITLAND = 0, FAST_HALL = 1, FAST_NEWTON = 2, FAST_LIMITS = 3, FAST_NEWTON_U = 4 };
-constexpr int kFastMaxWarps = 32;                    // CTA = 16, 20 or 24 warps (the count that wastes the fewest genome-block slots)
+constexpr int kFastMaxWarps = 24;                    // CTA = 16, 20 or 24 warps (the count that wastes the fewest genome-block slots)
 constexpr int kFastBodyWords = 4;                    // words of the unrolled inner body
 constexpr int kFastTileWords = 8;                    // words per table tile (two bodies)
 constexpr int kFastTile = kFastTileWords * 32;       // loci per table tile
-constexpr double kHuge = 1e300;
-constexpr double kHallHuge = 1e150;                  // HALL: a of a cell that does not count, and the cap of |(1-f)/f|
+constexpr double kHuge = 1e300;                      // LIMITS: +-infinity stand-in
+constexpr double kNeutral = 1e150;                   // NEWTON: r of a cell that does not count (the product of two stays finite)
+constexpr double kHallHuge = 1e60;                   // HALL: a of a cell that does not count, and the cap of |(1-f)/f|
 
 // Table entry of one (population, locus, genotype code): E doubles. Rows are padded so that consecutive populations start
 // 8 (E = 1) / 16 (E = 2) banks apart.
@@ -110,38 +112,50 @@ __device__ __forceinline__ uint32_t cell_addr(uint32_t z, uint32_t base) {
   return a;
 }
 
+template <int E, int OFF>
+__device__ __forceinline__ void lds_entry(uint32_t addr, double& v0, double& v1) {
+  if (E == 1) { asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v0) : "r"(addr), "n"(OFF)); v1 = 0.0; }
+  else asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v0), "=d"(v1) : "r"(addr), "n"(OFF));
+}
+
+// Two cells (loci J, J+1 of a code half) per step. The iterative modes share ONE reciprocal between the two denominators:
+//   1/d1 + 1/d2 = (d1 + d2) x,  1/d1^2 + 1/d2^2 = ((d1 + d2) x)^2 - 2 x,  x = 1/(d1 d2)
+// which halves the MUFU traffic and, for HALL, takes the FP64 instructions per cell from 4 to 3.5. A neutral entry (1e150 /
+// 1e60) paired with a real one contributes (d1 + 1e150)/(d1 1e150) = 1/d1 to within 1e-150; two neutral entries give 2e-150.
 template <int MODE, int TW, int HALF, int J>
-__device__ __forceinline__ void fast_cell(uint32_t z, uint32_t base, double f, double upper, double (&acc)[FastAcc<MODE>::N]) {
+__device__ __forceinline__ void fast_cell2(uint32_t z, uint32_t base, double f, double upper, double (&acc)[FastAcc<MODE>::N]) {
   constexpr int E = fast_entry(MODE);
-  constexpr int kOff = (TW * 32 + HALF * 16 + J) * 4 * E * 8;      // byte offset of the locus inside the body's part of the row
-  const uint32_t a = cell_addr<E, J>(z, base);
-  if (E == 1) {
-    double v; asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(kOff));
-    if (MODE == FAST_NEWTON) {
-      const double x = fast_rcp(__dadd_rn(f, v));                    // t = 1/(f + r)
-      acc[0] = __dadd_rn(acc[0], x); acc[1] = fma(x, x, acc[1]);
-    } else if (MODE == FAST_HALL) {
-      acc[0] = __dadd_rn(acc[0], fast_rcp(fma(v, f, 1.0)));          // f here is (1-f)/f: f/(f + (1-f) a) = 1/(1 + a (1-f)/f)
-    } else {  // FAST_RITLAND
-      acc[0] = __dadd_rn(acc[0], v);
-    }
-  } else {
-    double v0, v1; asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v0), "=d"(v1) : "r"(a), "n"(kOff));
+  constexpr int kOff = (TW * 32 + HALF * 16 + J) * 4 * E * 8;      // byte offset of locus J inside the body's part of the row
+  const uint32_t a1 = cell_addr<E, J>(z, base), a2 = cell_addr<E, J + 1>(z, base);
+  double v0, v1, w0, w1;
+  lds_entry<E, kOff>(a1, v0, v1);
+  lds_entry<E, kOff + 4 * E * 8>(a2, w0, w1);
+  if (MODE == FAST_HALL) {
+    const double d1 = fma(v0, f, 1.0), d2 = fma(w0, f, 1.0);        // f here is (1-f)/f: f/(f + (1-f) a) = 1/(1 + a (1-f)/f)
+    const double x = fast_rcp(__dmul_rn(d1, d2));
+    acc[0] = fma(__dadd_rn(d1, d2), x, acc[0]);
+  } else if (MODE == FAST_NEWTON || MODE == FAST_NEWTON_U) {
+    const double d1 = __dadd_rn(f, v0), d2 = __dadd_rn(f, w0);      // t = 1/(f + r)
+    const double x = fast_rcp(__dmul_rn(d1, d2));
+    const double u = __dmul_rn(__dadd_rn(d1, d2), x);               // t1 + t2
+    acc[0] = __dadd_rn(acc[0], u);
+    acc[1] = fma(-2.0, x, fma(u, u, acc[1]));                       // t1^2 + t2^2 = (t1 + t2)^2 - 2 t1 t2
     if (MODE == FAST_NEWTON_U) {
-      const double x = fast_rcp(__dadd_rn(f, v0));
-      acc[0] = __dadd_rn(acc[0], x); acc[1] = fma(x, x, acc[1]);
       if (v1 > upper) acc[2] = __dadd_rn(acc[2], 1.0);
-    } else {  // FAST_LIMITS
-      acc[0] = fmax(acc[0], v0); acc[1] = fmin(acc[1], v1);
+      if (w1 > upper) acc[2] = __dadd_rn(acc[2], 1.0);
     }
+  } else if (MODE == FAST_LIMITS) {
+    acc[0] = fmax(acc[0], fmax(v0, w0)); acc[1] = fmin(acc[1], fmin(v1, w1));
+  } else {  // FAST_RITLAND
+    acc[0] = __dadd_rn(acc[0], __dadd_rn(v0, w0));
   }
 }
 
 template <int MODE, int TW, int HALF, int J>
 struct FastHalf {
   static __device__ __forceinline__ void run(uint32_t z, uint32_t base, double f, double upper, double (&acc)[FastAcc<MODE>::N]) {
-    fast_cell<MODE, TW, HALF, J>(z, base, f, upper, acc);
-    FastHalf<MODE, TW, HALF, J + 1>::run(z, base, f, upper, acc);
+    fast_cell2<MODE, TW, HALF, J>(z, base, f, upper, acc);
+    FastHalf<MODE, TW, HALF, J + 2>::run(z, base, f, upper, acc);
   }
 };
 template <int MODE, int TW, int HALF>
@@ -212,10 +226,10 @@ k_terms_fast(const FastParams P) {
       double* e = tab + kk * STRIDE + j * 4 * E;             // e[code * E + k]
       if (MODE == FAST_NEWTON || MODE == FAST_NEWTON_U) {
         const double uq = __dsub_rn(1.0, q), up = __dsub_rn(1.0, p);
-        e[0 * E] = (ref_in && uq > 0.0) ? __ddiv_rn(q, uq) : kHuge;
-        e[1 * E] = kHuge;
-        e[2 * E] = (alt_in && up > 0.0) ? __ddiv_rn(p, up) : kHuge;
-        e[3 * E] = kHuge;
+        e[0 * E] = (ref_in && uq > 0.0) ? __ddiv_rn(q, uq) : kNeutral;
+        e[1 * E] = kNeutral;
+        e[2 * E] = (alt_in && up > 0.0) ? __ddiv_rn(p, up) : kNeutral;
+        e[3 * E] = kNeutral;
         if (MODE == FAST_NEWTON_U) { e[1] = 0.0; e[3] = 0.0; e[5] = sel ? __dmul_rn(__dmul_rn(2.0, p), p) : 0.0; e[7] = 0.0; }
       } else if (MODE == FAST_HALL) {
         // a; a cell that does not count, or whose denominator would be zero at every f (a = 0, calc.cpp:268), gets 1e150:
