@@ -30,7 +30,9 @@ struct PostParams {
   unsigned int* ticket;
 };
 
-__global__ void __launch_bounds__(256)
+// 6 blocks per SM (40 registers) and 16 counter chunks per expansion block: the 626 + 32 + 190 blocks of the chr22 shape are
+// resident together. With 48 registers and 740 expansion blocks the grid needed 1.9 waves and the roles ran one after the other.
+__global__ void __launch_bounds__(256, 6)
 k_post(const PostParams P) {
   __shared__ int s_last;
   // the code-3 gathers are the long pole (one L2 sector per cell) and go first, in one wave; the rare rows (few blocks, a

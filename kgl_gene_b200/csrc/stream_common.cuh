@@ -120,7 +120,7 @@ __host__ __device__ inline size_t stream_smem_bytes(uint32_t slice_units, uint32
 }
 
 // Expand the bit-sliced counters: gcounts[g] = {set lo bits, set hi bits} summed over the virtual chunks.
-constexpr int kExpandGroup = 4;
+constexpr int kExpandGroup = 16;
 __device__ __forceinline__ void
 expand_planes_block(uint32_t bx, uint32_t by, const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units,
                     uint64_t n_genomes_padded, uint32_t* __restrict__ gcounts /* [n_genomes_padded][2], zeroed */) {
