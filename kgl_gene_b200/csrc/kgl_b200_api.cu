@@ -77,13 +77,12 @@ struct kgl_b200_ctx {
   DevBuf<uint8_t> d_sort_temp;
   uint64_t n_dropped = 0;
   bool dropped_indexed = false, dropped_valid = false;
-  // host mirrors of the locus tables, fetched from the device only when the host selection path needs them
-  std::vector<float> h_af;
-  std::vector<uint32_t> h_offsets;
-  bool h_loci_valid = false, have_offsets = false, h_sel_valid = false;
+  bool have_offsets = false, h_sel_valid = false;
   uint64_t loci_len = 0;               // n_loci of the uploaded AF table
   DevBuf<uint32_t> d_offsets;
   DevBuf<unsigned long long> d_sel_counts;
+  DevBuf<uint32_t> d_chain_u32;          // spaced selection: next-valid table, two jump tables, block summaries
+  DevBuf<uint8_t> d_chain_mark;
   std::vector<uint8_t> h_superpop, h_sel;
   bool any_mixed = false;
   bool units_valid = false;
@@ -827,6 +826,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_zero_superpop.release(); c->d_bin_out.release();
   for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
   c->peer_base.clear(); c->d_xchg.release();
+  c->d_chain_u32.release(); c->d_chain_mark.release();
   c->d_list.release(); c->d_sm_codes.release(); c->d_limits.release(); c->d_slow_out.release(); c->d_lane_state.release(); c->d_n_slow.release();
   c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
   if (c->gram_e0) cudaEventDestroy(c->gram_e0);
@@ -921,7 +921,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   if (n_loci == 0) return fail(c, KGL_B200_ERR_INVALID, "n_loci is 0");
   if (c->have_geno && c->L != n_loci) c->have_geno = false;   // new population: the old matrix no longer applies
   int rc = use_device(c); if (rc) return rc;
-  c->h_loci_valid = false; c->have_offsets = offsets != nullptr; c->loci_len = n_loci;
+  c->have_offsets = offsets != nullptr; c->loci_len = n_loci;
   c->n_pop = n_pop;
   if (!c->have_geno) c->L = n_loci;
   KGL_CUDA(c, c->d_af.ensure((size_t)n_pop * n_loci));
@@ -1009,57 +1009,46 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
     }
     return KGL_B200_OK;
   }
-  if (!c->h_loci_valid) {
-    c->h_af.resize((size_t)c->n_pop * L);
-    c->h_offsets.resize(L);
-    KGL_CUDA(c, cudaMemcpyAsync(c->h_af.data(), c->d_af.p, c->h_af.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    KGL_CUDA(c, cudaMemcpyAsync(c->h_offsets.data(), c->d_offsets.p, L * 4, cudaMemcpyDeviceToHost, c->stream));
+  // spacing > 0: the candidates (k_select_dense), then the accept chain by pointer doubling (locus_kernels.cuh)
+  const uint64_t n_blocks = (L + kChainBlock - 1) / kChainBlock;
+  KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
+  KGL_CUDA(c, c->d_chain_u32.ensure((size_t)c->n_pop * (3 * L + 2 * n_blocks)));
+  KGL_CUDA(c, c->d_chain_mark.ensure((size_t)c->n_pop * L));
+  uint32_t* next_valid = c->d_chain_u32.p;
+  uint32_t* jump_a = next_valid + (size_t)c->n_pop * L;
+  uint32_t* jump_b = jump_a + (size_t)c->n_pop * L;
+  uint32_t* block_first = jump_b + (size_t)c->n_pop * L;
+  uint32_t* block_after = block_first + (size_t)c->n_pop * n_blocks;
+  KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
+  k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
+                                                            c->d_sel.p, c->d_sel_counts.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_chain_mark.p, 0, (size_t)c->n_pop * L, c->stream));
+  const dim3 grid_l(blocks_for(L, 256), c->n_pop);
+  k_chain_next_valid<<<dim3((unsigned)n_blocks, c->n_pop), kChainBlock, 0, c->stream>>>(c->d_sel.p, L, n_blocks, next_valid, block_first);
+  KGL_LAUNCH_CHECK(c);
+  k_chain_block_suffix<<<c->n_pop, 32, 0, c->stream>>>(block_first, n_blocks, block_after);
+  KGL_LAUNCH_CHECK(c);
+  k_chain_successor<<<grid_l, 256, 0, c->stream>>>(c->d_sel.p, c->d_offsets.p, L, n_blocks, spacing, next_valid, block_after, jump_a,
+                                                   c->d_chain_mark.p);
+  KGL_LAUNCH_CHECK(c);
+  int rounds = 1;
+  while ((1ull << rounds) < L + 1) ++rounds;
+  for (int r = 0; r < rounds; ++r) {
+    k_chain_round<<<grid_l, 256, 0, c->stream>>>(c->d_sel.p, L, jump_a, jump_b, c->d_chain_mark.p);
+    KGL_LAUNCH_CHECK(c);
+    std::swap(jump_a, jump_b);
+  }
+  k_chain_finish<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_chain_mark.p, L, (int)c->n_pop, c->d_sel.p, c->d_sel_counts.p);
+  KGL_LAUNCH_CHECK(c);
+  c->prep_valid = false; c->h_sel_valid = false; c->inputs_async = true;
+  if (n_selected) {
+    unsigned long long counts[kMaxPop];
+    KGL_CUDA(c, cudaMemcpyAsync(counts, c->d_sel_counts.p, kMaxPop * 8, cudaMemcpyDeviceToHost, c->stream));
     KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->h_loci_valid = true;
+    for (uint32_t k = 0; k < c->n_pop; ++k) n_selected[k] = counts[k];
   }
-  std::vector<uint8_t> bits[kMaxPop];
-  uint64_t counts[kMaxPop] = {0, 0, 0, 0, 0, 0};
-  const uint64_t l_begin = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
-                                            [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
-  const uint64_t l_end = std::upper_bound(c->h_offsets.begin(), c->h_offsets.end(), upper,
-                                          [](uint64_t v, uint32_t o) { return v < (uint64_t)o; }) - c->h_offsets.begin();
-  auto chain = [&](uint32_t k) {
-    const float* af = c->h_af.data() + (size_t)k * L;
-    std::vector<uint8_t>& b = bits[k];
-    b.assign(l_end > l_begin ? l_end - l_begin : 0, 0);
-    uint64_t previous_offset = 0, count = 0;
-    for (uint64_t l = l_begin; l < l_end; ++l) {
-      const uint64_t offset = c->h_offsets[l];
-      if (offset >= previous_offset + spacing || previous_offset == 0) {
-        const float a = af[l];
-        if (a != a) continue;                                    // empty AlleleFreqVector: invalid
-        const double p = std::min(std::max((double)a, 0.0), 1.0);
-        if (p == 0.0 || p < min_af || p > max_af) continue;
-        previous_offset = offset;
-        b[l - l_begin] = 1;
-        ++count;
-      }
-    }
-    counts[k] = count;
-  };
-  if (l_end - l_begin > 50000 && c->n_pop > 1) {
-    std::vector<std::thread> th;
-    for (uint32_t k = 1; k < c->n_pop; ++k) th.emplace_back(chain, k);
-    chain(0);
-    for (auto& t : th) t.join();
-  } else {
-    for (uint32_t k = 0; k < c->n_pop; ++k) chain(k);
-  }
-  // only the window crosses PCIe: the rest of the device mask is cleared in place
-  const uint64_t span = l_end > l_begin ? l_end - l_begin : 0;
-  std::vector<uint8_t> sel(span, 0);
-  for (uint32_t k = 0; k < c->n_pop; ++k)
-    for (uint64_t i = 0; i < span; ++i) sel[i] |= (uint8_t)(bits[k][i] << k);
-  if (n_selected) for (uint32_t k = 0; k < c->n_pop; ++k) n_selected[k] = counts[k];
-  KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, L, c->stream));
-  if (span) KGL_CUDA(c, cudaMemcpyAsync(c->d_sel.p + l_begin, sel.data(), span, cudaMemcpyHostToDevice, c->stream));
-  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->prep_valid = false; c->h_sel_valid = false;
   return KGL_B200_OK;
 }
 

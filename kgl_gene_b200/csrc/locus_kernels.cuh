@@ -194,4 +194,118 @@ k_select_dense(const float* __restrict__ af, const uint32_t* __restrict__ offset
   }
 }
 
+// ---- spaced selection on the device (getAllelesFromTo with SamplingDistance > 0, kga_analysis_inbreed_locus.cpp:21-72) ------
+// The reference walks the window in offset order and accepts a locus when it is a candidate (valid frequency vector inside
+// [min_af, max_af], the bits k_select_dense leaves in sel) and `offset >= previous_offset + spacing || previous_offset == 0`
+// (:38), previous_offset being the offset of the last ACCEPTED locus. That is a chain over the candidates: it starts at the
+// first candidate of the window, and the successor of an accepted locus i is the first candidate j > i with
+// offset[j] >= offset[i] + spacing (the next candidate if offset[i] == 0). The chain is marked in parallel by pointer doubling:
+// round r marks the successors 2^r steps ahead of every marked locus and squares the jump table, so ceil(log2 L) + 1 rounds
+// mark a chain of any length (marking a locus "early" is harmless: whatever a marked locus jumps to is on the chain).
+constexpr uint32_t kChainEnd = 0xFFFFFFFFu;
+constexpr int kChainBlock = 256;
+
+// next_valid[k][l]: first candidate of population k at or after l INSIDE l's 256-locus block (kChainEnd: none);
+// block_first[k][b]: first candidate of block b.
+__global__ void __launch_bounds__(kChainBlock)
+k_chain_next_valid(const uint8_t* __restrict__ sel, uint64_t n_loci, uint64_t n_blocks, uint32_t* __restrict__ next_valid,
+                   uint32_t* __restrict__ block_first) {
+  __shared__ uint32_t s_first[kChainBlock / 32];
+  const int k = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t l = (uint64_t)blockIdx.x * kChainBlock + threadIdx.x;
+  const bool valid = l < n_loci && ((sel[l] >> k) & 1u);
+  const uint32_t bal = __ballot_sync(kFull, valid);
+  if (lane == 0) s_first[warp] = bal ? (uint32_t)(l + __ffs(bal) - 1) : kChainEnd;
+  __syncthreads();
+  uint32_t nv = kChainEnd;
+  const uint32_t rest = bal >> lane;
+  if (rest) nv = (uint32_t)l + (uint32_t)__ffs(rest) - 1;
+  else for (int w = warp + 1; w < kChainBlock / 32; ++w) if (s_first[w] != kChainEnd) { nv = s_first[w]; break; }
+  if (l < n_loci) next_valid[(uint64_t)k * n_loci + l] = nv;
+  if (threadIdx.x == 0) {
+    uint32_t f = kChainEnd;
+    for (int w = 0; w < kChainBlock / 32; ++w) if (s_first[w] != kChainEnd) { f = s_first[w]; break; }
+    block_first[(uint64_t)k * n_blocks + blockIdx.x] = f;
+  }
+}
+
+// block_after[k][b]: first candidate in any block > b. One warp per population walks the blocks backwards, 32 at a time.
+__global__ void __launch_bounds__(32)
+k_chain_block_suffix(const uint32_t* __restrict__ block_first, uint64_t n_blocks, uint32_t* __restrict__ block_after) {
+  const int k = blockIdx.x, lane = threadIdx.x;
+  uint32_t carry = kChainEnd;                                         // first candidate beyond the current group of 32 blocks
+  for (int64_t g0 = (int64_t)((n_blocks + 31) / 32 * 32) - 32; g0 >= 0; g0 -= 32) {
+    const uint64_t b = (uint64_t)g0 + lane;
+    const uint32_t f = b < n_blocks ? block_first[(uint64_t)k * n_blocks + b] : kChainEnd;
+    // suffix minimum over the lanes above this one (candidates are indices, blocks are ordered: the minimum is the first)
+    uint32_t after = carry, group_first = carry;
+    for (int o = 31; o >= 0; --o) {                                   // every lane takes part in every shuffle
+      const uint32_t v = __shfl_sync(kFull, f, o);
+      if (v != kChainEnd) { group_first = v; if (o > lane) after = v; }
+    }
+    if (b < n_blocks) block_after[(uint64_t)k * n_blocks + b] = after;
+    carry = group_first;
+  }
+}
+
+__device__ __forceinline__ uint32_t chain_next_valid(const uint32_t* next_valid, const uint32_t* block_after, uint64_t n_loci,
+                                                     uint64_t n_blocks, int k, uint64_t l) {
+  if (l >= n_loci) return kChainEnd;
+  const uint32_t nv = next_valid[(uint64_t)k * n_loci + l];
+  return nv != kChainEnd ? nv : block_after[(uint64_t)k * n_blocks + l / kChainBlock];
+}
+
+// jump[k][i] = successor of candidate i; mark[k][.] = 1 at the first candidate of the window.
+__global__ void __launch_bounds__(256)
+k_chain_successor(const uint8_t* __restrict__ sel, const uint32_t* __restrict__ offsets, uint64_t n_loci, uint64_t n_blocks,
+                  uint64_t spacing, const uint32_t* __restrict__ next_valid, const uint32_t* __restrict__ block_after,
+                  uint32_t* __restrict__ jump, uint8_t* __restrict__ mark) {
+  const int k = blockIdx.y;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_loci) return;
+  if (i == 0) {
+    const uint32_t start = chain_next_valid(next_valid, block_after, n_loci, n_blocks, k, 0);
+    if (start != kChainEnd) mark[(uint64_t)k * n_loci + start] = 1;
+  }
+  if (!((sel[i] >> k) & 1u)) return;
+  const uint64_t o = offsets[i];
+  uint64_t t = i + 1;
+  if (o != 0) {                                        // lower_bound(offsets, o + spacing) in (i, n_loci)
+    const uint64_t want = o + spacing;
+    uint64_t lo = i + 1, hi = n_loci;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((uint64_t)offsets[mid] < want) lo = mid + 1; else hi = mid; }
+    t = lo;
+  }
+  jump[(uint64_t)k * n_loci + i] = chain_next_valid(next_valid, block_after, n_loci, n_blocks, k, t);
+}
+
+__global__ void __launch_bounds__(256)
+k_chain_round(const uint8_t* __restrict__ sel, uint64_t n_loci, const uint32_t* __restrict__ jump_in, uint32_t* __restrict__ jump_out,
+              uint8_t* __restrict__ mark) {
+  const int k = blockIdx.y;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_loci || !((sel[i] >> k) & 1u)) return;
+  const uint64_t base = (uint64_t)k * n_loci;
+  const uint32_t j = jump_in[base + i];
+  if (j == kChainEnd) { jump_out[base + i] = kChainEnd; return; }
+  if (mark[base + i]) mark[base + j] = 1;
+  jump_out[base + i] = jump_in[base + j];
+}
+
+// sel[l] = accepted bits; counts[k] += accepted loci.
+__global__ void __launch_bounds__(256)
+k_chain_finish(const uint8_t* __restrict__ mark, uint64_t n_loci, int n_pop, uint8_t* __restrict__ sel, unsigned long long* __restrict__ counts) {
+  const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t bits = 0;
+  if (l < n_loci) {
+    const uint32_t cand = sel[l];
+    for (int k = 0; k < n_pop; ++k) if (((cand >> k) & 1u) && mark[(uint64_t)k * n_loci + l]) bits |= 1u << k;
+    sel[l] = (uint8_t)bits;
+  }
+  for (int k = 0; k < n_pop; ++k) {
+    const uint32_t n = __popc(__ballot_sync(kFull, (bits >> k) & 1u));
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counts[k], (unsigned long long)n);
+  }
+}
+
 }  // namespace kgl

@@ -165,6 +165,27 @@ def test_all_estimators_match_oracle(gpu, case):
     assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-9
 
 
+@pytest.mark.parametrize("kw", [
+    dict(spacing=1),                                             # below the 10 bp locus spacing: every candidate is accepted
+    dict(spacing=10), dict(spacing=11), dict(spacing=1000),
+    dict(spacing=1000, lower=123_456, upper=2_000_000, min_af=0.02, max_af=0.4),
+    dict(spacing=10**7),                                         # one accepted locus per population
+    dict(spacing=250, lower=5_000_000, upper=6_000_000),         # empty window
+], ids=lambda kw: "-".join(f"{k}{v}" for k, v in kw.items()))
+def test_spaced_selection_on_the_device(gpu, kw):
+    """getAllelesFromTo with SamplingDistance > 0 (kga_analysis_inbreed_locus.cpp:21-72): the accept chain is marked on the device
+    by pointer doubling (locus_kernels.cuh); bit-exact against the oracle's sequential walk, per super-population, on a
+    population large enough for many 256-locus blocks and missing frequencies; the first locus sits at offset 0."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(64, 300_000, seed=77, missing_af_rate=0.1)
+    pop.offsets = (pop.offsets - pop.offsets[0]).astype(np.uint32)          # offsets 0, 10, 20, ...: the previous_offset == 0 rule
+    gpu.upload_population(pop)
+    counts = gpu.select_loci(**kw)
+    want = O.select_all_pops(pop, **kw)
+    assert np.array_equal(gpu.get_locus_selection(), sel_bits(want))
+    assert np.array_equal(counts[: want.shape[0]], want.sum(axis=1).astype(np.uint64))
+
+
 @pytest.mark.parametrize("unphased", [False, True], ids=["phased", "unphased"])
 def test_loglikelihood_clamped_terms(gpu, unphased):
     """The likelihood's clamps (calc.cpp:108-124). Heterozygous cells at loci with 2 p q < 1e-10 are clamped at every f: the
