@@ -77,6 +77,7 @@ struct kgl_b200_ctx {
   DevBuf<uint8_t> d_sort_temp;
   uint64_t n_dropped = 0;
   bool dropped_indexed = false, dropped_valid = false;
+  std::vector<uint32_t> h_offsets;     // host copy of the locus offsets (they arrive from the host): window -> row range
   bool have_offsets = false, h_sel_valid = false;
   uint64_t loci_len = 0;               // n_loci of the uploaded AF table
   DevBuf<uint32_t> d_offsets;
@@ -929,6 +930,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   if (offsets) {
     KGL_CUDA(c, c->d_offsets.ensure(n_loci));
     KGL_CUDA(c, cudaMemcpyAsync(c->d_offsets.p, offsets, n_loci * 4, cudaMemcpyHostToDevice, c->stream));
+    c->h_offsets.assign(offsets, offsets + n_loci);
   }
   c->h_sel_valid = false;            // device selection: all zero (nothing selected)
   KGL_CUDA(c, c->d_sel.ensure(n_loci));
@@ -1009,39 +1011,48 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
     }
     return KGL_B200_OK;
   }
-  // spacing > 0: the candidates (k_select_dense), then the accept chain by pointer doubling (locus_kernels.cuh)
-  const uint64_t n_blocks = (L + kChainBlock - 1) / kChainBlock;
+  // spacing > 0: the candidates (k_select_dense), then the accept chain by pointer doubling (locus_kernels.cuh) over the rows
+  // of the window only -- a contig is usually swept in many short windows
+  const uint64_t l_begin = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
+                                            [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
+  const uint64_t l_end = std::upper_bound(c->h_offsets.begin(), c->h_offsets.end(), upper,
+                                          [](uint64_t v, uint32_t o) { return v < (uint64_t)o; }) - c->h_offsets.begin();
+  const uint64_t span = l_end > l_begin ? l_end - l_begin : 0;
   KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
-  KGL_CUDA(c, c->d_chain_u32.ensure((size_t)c->n_pop * (3 * L + 2 * n_blocks)));
-  KGL_CUDA(c, c->d_chain_mark.ensure((size_t)c->n_pop * L));
-  uint32_t* next_valid = c->d_chain_u32.p;
-  uint32_t* jump_a = next_valid + (size_t)c->n_pop * L;
-  uint32_t* jump_b = jump_a + (size_t)c->n_pop * L;
-  uint32_t* block_first = jump_b + (size_t)c->n_pop * L;
-  uint32_t* block_after = block_first + (size_t)c->n_pop * n_blocks;
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
   k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
                                                             c->d_sel.p, c->d_sel_counts.p);
   KGL_LAUNCH_CHECK(c);
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
-  KGL_CUDA(c, cudaMemsetAsync(c->d_chain_mark.p, 0, (size_t)c->n_pop * L, c->stream));
-  const dim3 grid_l(blocks_for(L, 256), c->n_pop);
-  k_chain_next_valid<<<dim3((unsigned)n_blocks, c->n_pop), kChainBlock, 0, c->stream>>>(c->d_sel.p, L, n_blocks, next_valid, block_first);
-  KGL_LAUNCH_CHECK(c);
-  k_chain_block_suffix<<<c->n_pop, 32, 0, c->stream>>>(block_first, n_blocks, block_after);
-  KGL_LAUNCH_CHECK(c);
-  k_chain_successor<<<grid_l, 256, 0, c->stream>>>(c->d_sel.p, c->d_offsets.p, L, n_blocks, spacing, next_valid, block_after, jump_a,
-                                                   c->d_chain_mark.p);
-  KGL_LAUNCH_CHECK(c);
-  int rounds = 1;
-  while ((1ull << rounds) < L + 1) ++rounds;
-  for (int r = 0; r < rounds; ++r) {
-    k_chain_round<<<grid_l, 256, 0, c->stream>>>(c->d_sel.p, L, jump_a, jump_b, c->d_chain_mark.p);
+  if (span) {
+    const uint64_t n_blocks = (span + kChainBlock - 1) / kChainBlock;
+    KGL_CUDA(c, c->d_chain_u32.ensure((size_t)c->n_pop * (3 * span + 2 * n_blocks)));
+    KGL_CUDA(c, c->d_chain_mark.ensure((size_t)c->n_pop * span));
+    uint32_t* next_valid = c->d_chain_u32.p;
+    uint32_t* jump_a = next_valid + (size_t)c->n_pop * span;
+    uint32_t* jump_b = jump_a + (size_t)c->n_pop * span;
+    uint32_t* block_first = jump_b + (size_t)c->n_pop * span;
+    uint32_t* block_after = block_first + (size_t)c->n_pop * n_blocks;
+    uint8_t* sel_w = c->d_sel.p + l_begin;                 // all tables below are indexed relative to the window
+    const uint32_t* off_w = c->d_offsets.p + l_begin;
+    KGL_CUDA(c, cudaMemsetAsync(c->d_chain_mark.p, 0, (size_t)c->n_pop * span, c->stream));
+    const dim3 grid_l(blocks_for(span, 256), c->n_pop);
+    k_chain_next_valid<<<dim3((unsigned)n_blocks, c->n_pop), kChainBlock, 0, c->stream>>>(sel_w, span, n_blocks, next_valid, block_first);
     KGL_LAUNCH_CHECK(c);
-    std::swap(jump_a, jump_b);
+    k_chain_block_suffix<<<c->n_pop, 32, 0, c->stream>>>(block_first, n_blocks, block_after);
+    KGL_LAUNCH_CHECK(c);
+    k_chain_successor<<<grid_l, 256, 0, c->stream>>>(sel_w, off_w, span, n_blocks, spacing, next_valid, block_after, jump_a, c->d_chain_mark.p);
+    KGL_LAUNCH_CHECK(c);
+    int rounds = 1;
+    while ((1ull << rounds) < span + 1) ++rounds;
+    for (int r = 0; r < rounds; ++r) {
+      k_chain_round<<<grid_l, 256, 0, c->stream>>>(sel_w, span, jump_a, jump_b, c->d_chain_mark.p);
+      KGL_LAUNCH_CHECK(c);
+      std::swap(jump_a, jump_b);
+    }
+    k_chain_finish<<<blocks_for(span, 256), 256, 0, c->stream>>>(c->d_chain_mark.p, span, (int)c->n_pop, sel_w, c->d_sel_counts.p);
+    KGL_LAUNCH_CHECK(c);
   }
-  k_chain_finish<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_chain_mark.p, L, (int)c->n_pop, c->d_sel.p, c->d_sel_counts.p);
-  KGL_LAUNCH_CHECK(c);
   c->prep_valid = false; c->h_sel_valid = false; c->inputs_async = true;
   if (n_selected) {
     unsigned long long counts[kMaxPop];
