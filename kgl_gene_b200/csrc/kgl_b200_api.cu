@@ -1182,7 +1182,7 @@ int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
   PeerParams P{};
   for (uint32_t r = 0; r < c->peer_world; ++r) P.base[r] = static_cast<unsigned char*>(r == c->peer_rank ? (void*)c->d_xchg.p : c->peer_base[r]);
   P.rank = c->peer_rank; P.world = c->peer_world; P.parity_doubles = parity_doubles; P.epoch = epoch; P.n_genomes = c->N;
-  P.partials_out = c->d_partials.p; P.results = c->d_results.p; P.ticket = c->d_ticket.p;
+  P.partials_out = c->d_partials.p; P.results = c->d_results.p;
   k_peer_exchange<<<blocks_for(c->N * 8, 256), 256, 0, c->stream>>>(P);
   KGL_LAUNCH_CHECK(c);
   c->algo = KGL_B200_ALGO_SIMPLE; c->phase = 0;     // kgl_b200_inbreed_fetch copies d_results

@@ -142,7 +142,6 @@ struct PeerParams {
   uint64_t n_genomes;
   double* partials_out;                 // reduced partials (local copy, for inbreed_fetch-style consumers)
   kgl_b200_locus_results* results;
-  unsigned int* ticket;                 // zero-initialised; returns to zero
 };
 
 __device__ __forceinline__ unsigned long long* peer_flags(unsigned char* base, uint64_t parity_doubles) {
