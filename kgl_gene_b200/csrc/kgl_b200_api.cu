@@ -99,7 +99,8 @@ struct kgl_b200_ctx {
     void release() { flags16.release(); sum64.release(); selw.release(); rare_rows.release(); n_rare.release(); block_totals.release(); totals.release(); }
   } prep[2];
   int par = 0;                                  // the set the current selection was prepared into
-  cudaStream_t prep_stream = nullptr;
+  cudaStream_t prep_stream = nullptr, copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;      // chunked upload: one event per row chunk
   cudaEvent_t prep_done = nullptr, readers_done[2] = {nullptr, nullptr}, stream_pass_done = nullptr;
   bool stream_pass_marked = false;
   bool readers_marked[2] = {false, false};
@@ -316,30 +317,16 @@ int ensure_sample_major(kgl_b200_ctx* c) {
 
 // The side list of code-3 cells (SURVEY flattener contract), built on the device once per uploaded matrix.
 // Populations with more than ~1.5% code-3 cells are not indexed: every pass scans the matrix for them instead.
-int build_dropped_index(kgl_b200_ctx* c) {
-  if (c->dropped_valid) return KGL_B200_OK;
-  const uint64_t n128 = c->L * c->units;
-  const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
-  KGL_CUDA(c, c->d_dropped_counter.ensure(2));
-  KGL_CUDA(c, cudaMemsetAsync(c->d_dropped_counter.p, 0, 16, c->stream));
-  k_dropped_count<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, c->d_dropped_counter.p);
-  KGL_LAUNCH_CHECK(c);
-  unsigned long long total = 0;
-  KGL_CUDA(c, cudaMemcpyAsync(&total, c->d_dropped_counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+// Sort + segment table of the n keys in d_dropped_unsorted (n <= its capacity), or the "not indexed" verdict.
+int finish_dropped_index(kgl_b200_ctx* c, unsigned long long total) {
   c->n_dropped = total;
   c->dropped_indexed = total <= std::max<uint64_t>(1u << 16, c->N * c->L / 64);
   if (c->dropped_indexed) {
     KGL_CUDA(c, c->d_dropped.ensure(std::max<uint64_t>(total, 1)));
     KGL_CUDA(c, c->d_dropped_seg.ensure(c->Npad + 1));
     if (total > 0) {
-      // unsorted keys and the sort's scratch space are transient
       DevBuf<DroppedKey>& unsorted = c->d_dropped_unsorted;   // kept: re-uploads of the same shape allocate nothing
       DevBuf<uint8_t>& temp = c->d_sort_temp;
-      KGL_CUDA(c, unsorted.ensure(total));
-      k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units,
-                                                    c->d_dropped_counter.p + 1, unsorted.p, total);
-      KGL_LAUNCH_CHECK(c);
       int end_bit = 33;
       while (end_bit < 64 && (c->Npad >> (end_bit - 32)) != 0) ++end_bit;
       size_t temp_bytes = 0;
@@ -355,6 +342,29 @@ int build_dropped_index(kgl_b200_ctx* c) {
   }
   c->dropped_valid = true;
   return KGL_B200_OK;
+}
+
+// The side list of code-3 cells (SURVEY flattener contract), built on the device once per matrix that is already resident
+// (device-generated populations; uploads index while they copy, see kgl_b200_upload_genotypes).
+// Populations with more than ~1.5% code-3 cells are not indexed: every pass scans the matrix for them instead.
+int build_dropped_index(kgl_b200_ctx* c) {
+  if (c->dropped_valid) return KGL_B200_OK;
+  const uint64_t n128 = c->L * c->units;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+  KGL_CUDA(c, c->d_dropped_counter.ensure(2));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_dropped_counter.p, 0, 16, c->stream));
+  k_dropped_count<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, c->d_dropped_counter.p);
+  KGL_LAUNCH_CHECK(c);
+  unsigned long long total = 0;
+  KGL_CUDA(c, cudaMemcpyAsync(&total, c->d_dropped_counter.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (total > 0 && total <= std::max<uint64_t>(1u << 16, c->N * c->L / 64)) {
+    KGL_CUDA(c, c->d_dropped_unsorted.ensure(total));
+    k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, 0, (uint32_t)c->units,
+                                                  c->d_dropped_counter.p + 1, c->d_dropped_unsorted.p, total);
+    KGL_LAUNCH_CHECK(c);
+  }
+  return finish_dropped_index(c, total);
 }
 
 // Device storage of the genotype matrix: rows padded to a multiple of 256 (zero rows), row pitch c->units.
@@ -840,6 +850,8 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   if (c->stream_pass_done) cudaEventDestroy(c->stream_pass_done);
   for (cudaEvent_t e : c->readers_done) if (e) cudaEventDestroy(e);
   if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (cudaEvent_t ev : c->chunk_ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -907,13 +919,56 @@ int kgl_b200_upload_genotypes(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_lo
   int rc = use_device(c); if (rc) return rc;
   rc = set_shape(c, n_genomes, n_loci, row_bytes); if (rc) return rc;
   rc = alloc_matrix(c); if (rc) return rc;
-  if (c->units == c->host_units) {
-    KGL_CUDA(c, cudaMemcpyAsync(c->d_packed.p, packed, (size_t)n_loci * row_bytes, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    KGL_CUDA(c, cudaMemcpy2DAsync(c->d_packed.p, c->units * 16, packed, row_bytes, row_bytes, n_loci, cudaMemcpyHostToDevice, c->stream));
-  }
   c->have_geno = true;
-  return build_dropped_index(c);     // synchronises the stream
+  if (c->units != c->host_units) {        // padded device pitch (wide populations): one strided copy, then the index
+    KGL_CUDA(c, cudaMemcpy2DAsync(c->d_packed.p, c->units * 16, packed, row_bytes, row_bytes, n_loci, cudaMemcpyHostToDevice, c->stream));
+    return build_dropped_index(c);        // synchronises the stream
+  }
+  // The matrix crosses PCIe in row chunks on a copy stream; the code-3 cells of a chunk are listed (k_dropped_index) as soon
+  // as it has landed, i.e. while the next chunk is still copying. The key buffer is sized for 0.25 % code-3 cells; a
+  // population with more is indexed again with the exact size (the cursor has counted them all).
+  if (!c->copy_stream) KGL_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  constexpr int kChunks = 16;
+  while ((int)c->chunk_ev.size() < kChunks) {
+    cudaEvent_t ev = nullptr;
+    KGL_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->chunk_ev.push_back(ev);
+  }
+  const uint64_t limit = std::max<uint64_t>(1u << 16, c->N * c->L / 64);             // indexed iff total <= limit
+  const uint64_t cap = std::min<uint64_t>(limit, std::max<uint64_t>(1u << 16, c->N * c->L / 400));
+  KGL_CUDA(c, c->d_dropped_unsorted.ensure(cap));
+  KGL_CUDA(c, c->d_dropped_counter.ensure(2));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_dropped_counter.p, 0, 16, c->stream));
+  // the copy stream must not overtake work already queued on the context stream (the memsets of alloc_matrix)
+  KGL_CUDA(c, cudaEventRecord(c->chunk_ev[0], c->stream));
+  KGL_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));
+  const uint64_t rows_per_chunk = ((n_loci + kChunks - 1) / kChunks + 255) / 256 * 256;
+  int ci = 0;
+  for (uint64_t r0 = 0; r0 < n_loci; r0 += rows_per_chunk, ++ci) {
+    const uint64_t rows = std::min<uint64_t>(rows_per_chunk, n_loci - r0);
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_packed.p + r0 * row_bytes, static_cast<const uint8_t*>(packed) + r0 * row_bytes, rows * row_bytes,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+    KGL_CUDA(c, cudaEventRecord(c->chunk_ev[ci], c->copy_stream));
+    KGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_ev[ci], 0));
+    const uint64_t n128 = rows * c->units;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+    k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p) + r0 * c->units, n128, r0 * c->units,
+                                                  (uint32_t)c->units, c->d_dropped_counter.p + 1, c->d_dropped_unsorted.p, cap);
+    KGL_LAUNCH_CHECK(c);
+  }
+  unsigned long long total = 0;
+  KGL_CUDA(c, cudaMemcpyAsync(&total, c->d_dropped_counter.p + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));      // every chunk has landed: the host buffer is free again
+  if (total > cap && total <= limit) {
+    KGL_CUDA(c, c->d_dropped_unsorted.ensure(total));
+    KGL_CUDA(c, cudaMemsetAsync(c->d_dropped_counter.p, 0, 16, c->stream));
+    const uint64_t n128 = c->L * c->units;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+    k_dropped_index<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, 0, (uint32_t)c->units,
+                                                  c->d_dropped_counter.p + 1, c->d_dropped_unsorted.p, total);
+    KGL_LAUNCH_CHECK(c);
+  }
+  return finish_dropped_index(c, total);
 }
 
 int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const float* af, const uint32_t* offsets) {

@@ -28,10 +28,11 @@ k_dropped_count(const uint4* __restrict__ packed, uint64_t n_cells128, unsigned 
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
 }
 
-// Appends one key per code-3 cell (any order; sorted afterwards). cursor starts at 0; capacity = count of k_dropped_count.
+// Appends one key per code-3 cell of a range of units (any order; sorted afterwards). The cursor keeps counting past the
+// capacity, so the caller learns the true total and can retry with an exact allocation.
 __global__ void __launch_bounds__(256)
-k_dropped_index(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t units, unsigned long long* __restrict__ cursor,
-                DroppedKey* __restrict__ cells, uint64_t capacity) {
+k_dropped_index(const uint4* __restrict__ packed /* first unit of the range */, uint64_t n_cells128, uint64_t cell0 /* its global unit index */,
+                uint32_t units, unsigned long long* __restrict__ cursor, DroppedKey* __restrict__ cells, uint64_t capacity) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +57,7 @@ k_dropped_index(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t 
       if (lane == 0) start = atomicAdd(cursor, (unsigned long long)warp_total);
       start = __shfl_sync(kFull, start, 0);
       uint64_t o = start + (incl - n);
-      const uint32_t row = (uint32_t)(i / units), unit = (uint32_t)(i % units);
+      const uint32_t row = (uint32_t)((cell0 + i) / units), unit = (uint32_t)((cell0 + i) % units);
       while (both) {
         const int b = __ffsll((long long)both) - 1;
         both &= both - 1;
