@@ -276,11 +276,23 @@ def run_ours(args):
         ctx.inbreed_update()
 
     use_peer = world > 1 and args.exchange == "peer"
+    exchange_note = args.exchange
     if use_peer:
         # exchange regions of all ranks, mapped into every rank once (CUDA IPC handles travel over the process group)
+        from kgl_gene_b200.capi import KglError
         handles = [None] * world
         dist.all_gather_object(handles, ctx.peer_export())
-        ctx.peer_attach(rank, world, handles)
+        attached = torch.ones(1, device=dev, dtype=torch.int32)
+        try:
+            ctx.peer_attach(rank, world, handles)
+        except KglError as ex:        # e.g. a container that forbids CUDA IPC between its processes
+            attached.zero_()
+            sys.stderr.write(f"bench.py: rank {rank}: peer_attach failed ({ex}); the ranks fall back to --exchange nccl\n")
+        dist.all_reduce(attached, op=dist.ReduceOp.MIN)
+        if int(attached.item()) == 0:
+            use_peer = False
+            exchange_note = "nccl (CUDA IPC peer mapping unavailable on this box)"
+    if use_peer:
         # the fused exchange against the NCCL path, once, before anything is timed
         step_nccl()
         want = ctx.inbreed_fetch()
@@ -411,7 +423,7 @@ def run_ours(args):
                        "step": "k_locus_prepare (flags + dense totals) + k_stream_count_ct + k_post (counter expansion | code-3 cells | rare-major rows) + k_moment_partials"
                                + ("" if world == 1 else (" + k_peer_exchange (signal, wait, gather the partial sums of all ranks over NVLink peer memory, fixed-order sum, closed form; no NCCL call in the step)"
                                                          if use_peer else " + NCCL all-reduce + k_finalize_closed_form")),
-                       "exchange": None if world == 1 else args.exchange},
+                       "exchange": None if world == 1 else exchange_note},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": stream_kernel_name(n), "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
