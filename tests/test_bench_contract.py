@@ -1,0 +1,34 @@
+"""The driver-facing contract of bench.py that can be checked without a GPU: the reference arm prints exactly one JSON line
+on stdout with the keys the driver reads, and the GPU arm refuses to run (no CPU fallback) when there is no device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, proc.stdout[:500]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "inbreeding genotype-loci/s" and line["unit"] == "genotype-loci/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
+
+
+def test_gpu_arm_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode != 0 and proc.stdout.strip() == ""
+    assert "no CPU fallback" in proc.stderr or "no CUDA device" in proc.stderr
