@@ -131,6 +131,8 @@ struct kgl_b200_ctx {
   uint32_t peer_rank = 0, peer_world = 0;
   std::vector<void*> peer_base;           // mapped exchange regions of the other ranks (nullptr for our own slot)
   double* partials_target = nullptr;      // where the moment kernels write (d_partials unless a peer step redirects them)
+  DevBuf<double2> d_terms_table;         // per-run table constants of the HALL / NEWTON sweeps (terms_fast.cuh)
+  int table_mode = -1;                   // mode the table was built for (-1: none); reset by inbreed_begin
   DevBuf<uint32_t> d_n_slow, d_list;    // d_list: genomes whose root search is still running (late Newton sweeps)
   uint64_t list_len = 0;
   bool limits_valid = false;
@@ -589,6 +591,17 @@ int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
   P.unphased = c->unphased ? 1 : 0; P.tiles_per_chunk = fl.tiles_per_chunk; P.slots = slots;
   P.f = c->d_f.p; P.out = c->d_chunk_out.p;
   P.list = list_len ? c->d_list.p : nullptr; P.n_list = list_len;
+  if (MODE == FAST_HALL || MODE == FAST_NEWTON) {
+    // the per-locus constants of the run: built before its first sweep, reused by every later one
+    if (c->table_mode != MODE) {
+      KGL_CUDA(c, c->d_terms_table.ensure((size_t)c->n_pop * c->n_words * 32));
+      k_terms_table<MODE><<<dim3(blocks_for(c->n_words * 32, 256), c->n_pop), 256, 0, c->stream>>>(
+          c->prep[c->par].selw.p, c->d_af.p, c->L, c->n_words, (int)c->n_pop, c->unphased ? 1 : 0, c->d_terms_table.p);
+      KGL_LAUNCH_CHECK(c);
+      c->table_mode = MODE;
+    }
+    P.table = c->d_terms_table.p;
+  }
   const size_t smem = fast_smem_bytes(MODE, slots, warps);
   KGL_CUDA(c, cudaFuncSetAttribute(k_terms_fast<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_terms_fast<MODE><<<fl.grid, warps * 32, smem, c->stream>>>(P);
@@ -837,6 +850,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_zero_superpop.release(); c->d_bin_out.release();
   for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
   c->peer_base.clear(); c->d_xchg.release();
+  c->d_terms_table.release();
   c->d_chain_u32.release(); c->d_chain_mark.release();
   c->d_list.release(); c->d_sm_codes.release(); c->d_limits.release(); c->d_slow_out.release(); c->d_lane_state.release(); c->d_n_slow.release();
   c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
@@ -1291,7 +1305,7 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   KGL_CUDA(c, c->d_lane_state.ensure(c->Npad));
   KGL_CUDA(c, c->d_n_slow.ensure(1));
   KGL_CUDA(c, c->d_list.ensure(c->Npad));
-  c->limits_valid = false; c->list_len = 0;
+  c->limits_valid = false; c->list_len = 0; c->table_mode = -1;
   return KGL_B200_OK;
 }
 

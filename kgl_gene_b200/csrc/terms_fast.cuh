@@ -61,6 +61,10 @@ struct FastParams {
   // Late Newton sweeps: only the genomes still searching, gathered through a list. Lane i of compact block b works on genome
   // list[32 b + i]; n_gblocks counts compact blocks and out is indexed by the compact position. Null: every genome.
   const uint32_t* list; uint64_t n_list;
+  // HALL / NEWTON sweeps after the first: the two per-locus constants {hom-ref entry, hom-alt entry} of every population,
+  // computed once per estimator run by k_terms_table instead of once per tile and CTA ([n_pop][n_words * 32]). Null: the tile
+  // build computes them (single-sweep modes).
+  const double2* table;
 };
 
 // Interleaved code copy of the sample-major planes: word (gb, w, lane) -> {cells 0..15, cells 16..31}, cell i of a half at
@@ -168,6 +172,33 @@ __device__ __forceinline__ void fast_word(uint2 z, uint32_t base, double f, doub
   FastHalf<MODE, TW, 1, 0>::run(z.y, base, f, upper, acc);
 }
 
+// The two table constants of one (population, locus) for the single-value modes: {entry of code 0, entry of code 2}.
+template <int MODE>
+__device__ __forceinline__ double2 fast_constants(bool sel, double p, double q, bool unphased) {
+  const bool ref_in = sel && q > kMinMajorFreq;          // the hom-ref cell counts (freq.cpp:532)
+  const bool alt_in = sel && !unphased;                  // the hom-alt cell is MINOR_HOMOZYGOUS (phased populations)
+  if (MODE == FAST_HALL) {
+    // a; a cell that does not count, or whose denominator would be zero at every f (a = 0, calc.cpp:268), gets 1e60: its
+    // term vanishes in the sum
+    return make_double2((ref_in && q > 0.0) ? q : kHallHuge, (alt_in && p > 0.0) ? p : kHallHuge);
+  }
+  const double uq = __dsub_rn(1.0, q), up = __dsub_rn(1.0, p);      // NEWTON: r = a / (1 - a)
+  return make_double2((ref_in && uq > 0.0) ? __ddiv_rn(q, uq) : kNeutral, (alt_in && up > 0.0) ? __ddiv_rn(p, up) : kNeutral);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_terms_table(const uint32_t* __restrict__ selw, const float* __restrict__ af, uint64_t n_loci, uint64_t n_words, int n_pop,
+              int unphased, double2* __restrict__ table) {
+  const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kk = blockIdx.y;
+  if (l >= n_words * 32 || kk >= n_pop) return;
+  const bool sel = l < n_loci && ((selw[(uint64_t)kk * n_words + (l >> 5)] >> (l & 31)) & 1u);
+  double p = 0.0, q = 1.0;
+  if (sel) { const LocusFreq lf = locus_freq(af[(uint64_t)kk * n_loci + l]); p = lf.p; q = lf.q; }
+  table[(uint64_t)kk * n_words * 32 + l] = fast_constants<MODE>(sel, p, q, unphased != 0);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kFastMaxWarps * 32, 1)
 k_terms_fast(const FastParams P) {
@@ -218,6 +249,13 @@ k_terms_fast(const FastParams P) {
       const int kk = idx / kFastTile, j = idx % kFastTile;
       const uint64_t w = t * kFastTileWords + (j >> 5);
       const uint64_t l = t * kFastTile + j;
+      if ((MODE == FAST_HALL || MODE == FAST_NEWTON) && P.table) {            // constants from the per-run table
+        const double neutral = (MODE == FAST_HALL) ? kHallHuge : kNeutral;
+        const double2 v = w < P.n_words ? P.table[(uint64_t)kk * P.n_words * 32 + l] : make_double2(neutral, neutral);
+        double* e = tab + kk * STRIDE + j * 4;
+        e[0] = v.x; e[1] = neutral; e[2] = v.y; e[3] = neutral;
+        continue;
+      }
       const bool sel = w < P.n_words && l < P.n_loci && ((P.selw[(uint64_t)kk * P.n_words + w] >> (j & 31)) & 1u);
       double p = 0.0, q = 1.0;
       if (sel) { const LocusFreq lf = locus_freq(P.af[(uint64_t)kk * P.n_loci + l]); p = lf.p; q = lf.q; }
@@ -225,17 +263,12 @@ k_terms_fast(const FastParams P) {
       const bool alt_in = sel && !P.unphased;                 // the hom-alt cell is MINOR_HOMOZYGOUS (phased populations)
       double* e = tab + kk * STRIDE + j * 4 * E;             // e[code * E + k]
       if (MODE == FAST_NEWTON || MODE == FAST_NEWTON_U) {
-        const double uq = __dsub_rn(1.0, q), up = __dsub_rn(1.0, p);
-        e[0 * E] = (ref_in && uq > 0.0) ? __ddiv_rn(q, uq) : kNeutral;
-        e[1 * E] = kNeutral;
-        e[2 * E] = (alt_in && up > 0.0) ? __ddiv_rn(p, up) : kNeutral;
-        e[3 * E] = kNeutral;
+        const double2 v = fast_constants<FAST_NEWTON>(sel, p, q, P.unphased != 0);
+        e[0 * E] = v.x; e[1 * E] = kNeutral; e[2 * E] = v.y; e[3 * E] = kNeutral;
         if (MODE == FAST_NEWTON_U) { e[1] = 0.0; e[3] = 0.0; e[5] = sel ? __dmul_rn(__dmul_rn(2.0, p), p) : 0.0; e[7] = 0.0; }
       } else if (MODE == FAST_HALL) {
-        // a; a cell that does not count, or whose denominator would be zero at every f (a = 0, calc.cpp:268), gets 1e150:
-        // its term vanishes in the sum
-        e[0] = (ref_in && q > 0.0) ? q : kHallHuge; e[1] = kHallHuge;
-        e[2] = (alt_in && p > 0.0) ? p : kHallHuge; e[3] = kHallHuge;
+        const double2 v = fast_constants<FAST_HALL>(sel, p, q, P.unphased != 0);
+        e[0] = v.x; e[1] = kHallHuge; e[2] = v.y; e[3] = kHallHuge;
       } else if (MODE == FAST_LIMITS) {
         // {left end of the feasible region of a homozygous cell, 2 a a2 of a heterozygous cell}
         const double uq = __dsub_rn(1.0, q), up = __dsub_rn(1.0, p);
