@@ -133,6 +133,7 @@ struct kgl_b200_ctx {
   double* partials_target = nullptr;      // where the moment kernels write (d_partials unless a peer step redirects them)
   DevBuf<double2> d_terms_table;         // per-run table constants of the HALL / NEWTON sweeps (terms_fast.cuh)
   int table_mode = -1;                   // mode the table was built for (-1: none); reset by inbreed_begin
+  DevBuf<uint32_t> d_list_count;         // length of d_list on the device (sweeps between two host checks shrink it)
   DevBuf<uint32_t> d_n_slow, d_list;    // d_list: genomes whose root search is still running (late Newton sweeps)
   uint64_t list_len = 0;
   bool limits_valid = false;
@@ -572,10 +573,15 @@ int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
     const double filled = (double)gblocks / (double)(rows * sl * w);
     if (filled >= best) { best = filled; warps = w; }
   }
+  // A handful of genome blocks (late Newton sweeps over the list of unfinished genomes, small populations) cannot fill 16
+  // warps: small CTAs instead, four of them per SM, each with a quarter of the tiles -- the sweep is then bound by the
+  // per-tile latency of a few warps, and four CTAs per SM overlap it.
+  int ctas_per_sm = 1;
+  if (gblocks <= 8) { warps = gblocks <= 4 ? 4 : 8; ctas_per_sm = 4; }
   const uint32_t slots = (uint32_t)std::min<uint64_t>(8, (gblocks + warps - 1) / warps);
   const uint64_t gy = (gblocks + (uint64_t)warps * slots - 1) / ((uint64_t)warps * slots);
   const uint64_t n_tiles = (c->n_words + kFastTileWords - 1) / kFastTileWords;
-  const uint64_t want = std::max<uint64_t>(1, (uint64_t)c->sm_count / gy);
+  const uint64_t want = std::max<uint64_t>(1, (uint64_t)c->sm_count * ctas_per_sm / gy);
   const uint64_t tpc = std::max<uint64_t>(1, (n_tiles + want - 1) / want);
   fl.tiles_per_chunk = (uint32_t)tpc; fl.slots = slots;
   fl.n_chunks = (n_tiles + tpc - 1) / tpc;
@@ -590,7 +596,7 @@ int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
   P.selw = c->prep[c->par].selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
   P.unphased = c->unphased ? 1 : 0; P.tiles_per_chunk = fl.tiles_per_chunk; P.slots = slots;
   P.f = c->d_f.p; P.out = c->d_chunk_out.p;
-  P.list = list_len ? c->d_list.p : nullptr; P.n_list = list_len;
+  P.list = list_len ? c->d_list.p : nullptr; P.n_list = list_len; P.n_list_dev = list_len ? c->d_list_count.p : nullptr;
   if (MODE == FAST_HALL || MODE == FAST_NEWTON) {
     // the per-locus constants of the run: built before its first sweep, reused by every later one
     if (c->table_mode != MODE) {
@@ -618,7 +624,8 @@ int newton_sweep(kgl_b200_ctx* c) {
   const unsigned nb = blocks_for(c->N, 256);
   KGL_CUDA(c, cudaMemsetAsync(c->d_n_slow.p, 0, 4, c->stream));
   k_newton_reduce<<<blocks_for(c->list_len ? c->list_len : c->N, 256), 256, 0, c->stream>>>(
-      c->d_chunk_out.p, FastAcc<MODE>::N, fl.n_chunks, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len, c->d_f.p,
+      c->d_chunk_out.p, FastAcc<MODE>::N, fl.n_chunks, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len,
+      c->list_len ? c->d_list_count.p : nullptr, c->d_f.p,
       c->d_limits.p, c->d_done.p, c->d_iter.p, c->d_lane_state.p, c->d_n_slow.p);
   KGL_LAUNCH_CHECK(c);
   TermLaunch tl = plan_terms(c);
@@ -850,7 +857,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_zero_superpop.release(); c->d_bin_out.release();
   for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
   c->peer_base.clear(); c->d_xchg.release();
-  c->d_terms_table.release();
+  c->d_terms_table.release(); c->d_list_count.release();
   c->d_chain_u32.release(); c->d_chain_mark.release();
   c->d_list.release(); c->d_sm_codes.release(); c->d_limits.release(); c->d_slow_out.release(); c->d_lane_state.release(); c->d_n_slow.release();
   c->d_codes16.release(); c->d_gram.release(); c->d_gram_tiles.release(); c->d_gp_chunks.release(); c->d_gp.release(); c->d_gram_out.release();
@@ -1305,6 +1312,7 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   KGL_CUDA(c, c->d_lane_state.ensure(c->Npad));
   KGL_CUDA(c, c->d_n_slow.ensure(1));
   KGL_CUDA(c, c->d_list.ensure(c->Npad));
+  KGL_CUDA(c, c->d_list_count.ensure(1));
   c->limits_valid = false; c->list_len = 0; c->table_mode = -1;
   return KGL_B200_OK;
 }
@@ -1394,6 +1402,14 @@ int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
   ++c->iteration;
   k_ll_step<<<nb, 256, 0, c->stream>>>(c->d_iter.p, c->N, c->opt.ll_tolerance, c->d_f.p, c->d_bracket.p, c->d_done.p, c->d_flag.p);
   KGL_LAUNCH_CHECK(c);
+  // Late sweeps work on a short list of genomes and cost less than a host round trip: while the list is in use the host
+  // looks at the number of unfinished genomes only every fourth sweep; in between the list is re-compacted on the device and
+  // its length read there (a sweep over an empty list returns at once, a finished genome ignores further steps).
+  if (c->list_len && (c->iteration & 3) != 0 && c->iteration < c->opt.ll_max_iterations) {
+    k_compact_active<<<1, 1024, 0, c->stream>>>(c->d_done.p, c->N, c->d_list.p, c->d_list_count.p);
+    KGL_LAUNCH_CHECK(c);
+    return KGL_B200_OK;
+  }
   KGL_CUDA(c, cudaMemcpyAsync(&flag, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   *finished = (flag == 0 || c->iteration >= c->opt.ll_max_iterations) ? 1 : 0;
@@ -1401,7 +1417,7 @@ int kgl_b200_inbreed_update(kgl_b200_ctx* c, int* finished) {
   // follows the number of live genomes, not N (every rank sees the same done flags, so the same list).
   c->list_len = 0;
   if (!*finished && flag * 2 <= c->N) {
-    k_compact_active<<<1, 1024, 0, c->stream>>>(c->d_done.p, c->N, c->d_list.p);
+    k_compact_active<<<1, 1024, 0, c->stream>>>(c->d_done.p, c->N, c->d_list.p, c->d_list_count.p);
     KGL_LAUNCH_CHECK(c);
     c->list_len = flag;
   }

@@ -61,6 +61,7 @@ struct FastParams {
   // Late Newton sweeps: only the genomes still searching, gathered through a list. Lane i of compact block b works on genome
   // list[32 b + i]; n_gblocks counts compact blocks and out is indexed by the compact position. Null: every genome.
   const uint32_t* list; uint64_t n_list;
+  const uint32_t* n_list_dev;  // when set: the list's current length on the device (<= n_list, which sized the grid)
   // HALL / NEWTON sweeps after the first: the two per-locus constants {hom-ref entry, hom-alt entry} of every population,
   // computed once per estimator run by k_terms_table instead of once per tile and CTA ([n_pop][n_words * 32]). Null: the tile
   // build computes them (single-sweep modes).
@@ -225,10 +226,12 @@ k_terms_fast(const FastParams P) {
 
   // The codes of the next (tile, body, genome block) are requested before the current ones are worked on.
   constexpr uint64_t kNoGenome = ~0ull;
+  const uint64_t n_list = (P.list && P.n_list_dev) ? min(P.n_list, (uint64_t)*P.n_list_dev) : P.n_list;
+  if (P.list && n_list == 0) return;                                      // every genome has finished: nothing to sweep
   auto genome_of = [&](uint32_t s) -> uint64_t {                          // the lane's genome in slot s
     const uint64_t pos = (gb_first + (uint64_t)s * n_warps) * 32 + lane;
     if (!P.list) return pos;
-    return pos < P.n_list ? (uint64_t)P.list[pos] : kNoGenome;
+    return pos < n_list ? (uint64_t)P.list[pos] : kNoGenome;
   };
   auto load_codes = [&](uint64_t t, int body, uint32_t s, uint2 (&z)[kFastBodyWords]) {
     const uint64_t g = genome_of(s);
@@ -374,9 +377,10 @@ constexpr double kLimitMargin = 1e-9;
 __global__ void __launch_bounds__(256)
 k_newton_reduce(const double* __restrict__ chunk_out, int n_out /* 2, or 3 with the upper-clamped count */, uint64_t n_chunks,
                 uint64_t n_genomes_padded, uint64_t n_genomes, const uint32_t* __restrict__ list, uint64_t n_list,
-                const double* __restrict__ f, const double* __restrict__ limits, const uint32_t* __restrict__ done,
+                const uint32_t* __restrict__ n_list_dev, const double* __restrict__ f, const double* __restrict__ limits, const uint32_t* __restrict__ done,
                 double* __restrict__ iter, uint8_t* __restrict__ state, uint32_t* __restrict__ n_slow) {
   const uint64_t pos = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // position in chunk_out
+  if (list && n_list_dev) n_list = min(n_list, (uint64_t)*n_list_dev);
   if (pos >= (list ? n_list : n_genomes)) return;
   const uint64_t g = list ? list[pos] : pos;
   double* I = iter + g * 4;
@@ -404,7 +408,7 @@ k_newton_reduce(const double* __restrict__ chunk_out, int n_out /* 2, or 3 with 
 
 // Ordered list of the genomes whose root search has not finished (one block; N is at most a few hundred thousand).
 __global__ void __launch_bounds__(1024)
-k_compact_active(const uint32_t* __restrict__ done, uint64_t n_genomes, uint32_t* __restrict__ list) {
+k_compact_active(const uint32_t* __restrict__ done, uint64_t n_genomes, uint32_t* __restrict__ list, uint32_t* __restrict__ count) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -423,6 +427,7 @@ k_compact_active(const uint32_t* __restrict__ done, uint64_t n_genomes, uint32_t
     if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 32; ++w) t += s_warp[w]; s_base += t; }
     __syncthreads();
   }
+  if (threadIdx.x == 0) *count = s_base;
 }
 
 // Adds the exact evaluation of the state-2 genomes (chunk outputs of k_genome_terms<TERM_NEWTON>, 4 per genome).
