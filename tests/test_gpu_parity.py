@@ -493,6 +493,64 @@ def test_full_width_properties_on_device_generated_population(gpu):
     assert np.corrcoef(res["inbred_allele_sum"], f)[0, 1] > 0.99                          # recovers the planted F
 
 
+@pytest.mark.parametrize("algo", ["Simple", "RitlandLocus", "HallME", "Loglikelihood"])
+def test_locus_sharded_estimators_two_contexts(algo):
+    """The split estimator protocol of the C ABI (inbreed_begin / accumulate / partials_buffer / update / fetch) with two locus
+    shards: two contexts on one GPU play two ranks, their partial-sum buffers are summed on the device between accumulate and
+    update exactly as the all-reduce does. The result must equal the unsharded run (and the oracle): covers the per-shard
+    heterozygous counts, the per-shard feasibility limits and the list of unfinished genomes of the likelihood search."""
+    import torch
+    from kgl_gene_b200.capi import KglB200
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.shards import _RawCudaArray
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(200, 9000, seed=61, missing_rate=0.004)
+    cut = 5000 - 32 * 3 + 7                                            # not a multiple of anything
+    shards = [FlatPopulation(pop.offsets[a:b], np.ascontiguousarray(pop.af[:, a:b]), pop.superpop, np.ascontiguousarray(pop.packed[a:b]),
+                             pop.n_genomes, pop.unphased) for a, b in ((0, cut), (cut, pop.n_loci))]
+    dev = torch.device("cuda", 0)
+    ctxs = [KglB200(0) for _ in shards]
+    try:
+        for c, sh in zip(ctxs, shards):
+            c.upload_population(sh)
+            c.select_loci()
+        opts = dict(hall_start=np.linspace(0.05, 0.5, pop.n_genomes), hall_sweeps=50) if algo == "HallME" else {}
+        for c in ctxs:
+            c.inbreed_begin(algo, **opts)
+        finished, passes = False, 0
+        while not finished:
+            for c in ctxs:
+                c.inbreed_accumulate()
+                c.synchronize()
+            bufs = []
+            for c in ctxs:
+                ptr, cnt = c.inbreed_partials_buffer()
+                bufs.append(torch.as_tensor(_RawCudaArray(ptr, cnt, "<f8"), device=dev))
+            total = bufs[0] + bufs[1]
+            for b in bufs:
+                b.copy_(total)
+            torch.cuda.synchronize()
+            fin = [c.inbreed_update() for c in ctxs]
+            assert fin[0] == fin[1]
+            finished = fin[0]
+            passes += 1
+            assert passes < 400
+        got = [c.inbreed_fetch() for c in ctxs]
+    finally:
+        for c in ctxs:
+            c.close()
+    sel = O.select_all_pops(pop)
+    kw = dict(start=opts["hall_start"], sweeps=50) if algo == "HallME" else {}
+    want = O.inbreed(pop, sel, algo, **kw)
+    c_want, f_want = results_matrix(want)
+    for g in got:
+        c_got, f_got = results_matrix(g)
+        assert np.array_equal(c_got, c_want)
+        assert rel_err(f_got[:, :3], f_want[:, :3]) < TIGHT
+        assert np.max(np.abs(g["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-9
+    assert np.array_equal(got[0]["inbred_allele_sum"], got[1]["inbred_allele_sum"])      # both "ranks" hold the same bits
+
+
 def test_peer_exchange_two_gpus():
     """Locus-sharded step with the exchange over NVLink peer memory (kgl_b200_enqueue_count_and_inbreed_peer): two ranks through
     bench.py, which asserts the fused exchange against the NCCL all-reduce path before timing. Needs two GPUs."""
