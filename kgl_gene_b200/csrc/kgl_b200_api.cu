@@ -78,6 +78,7 @@ struct kgl_b200_ctx {
   uint64_t n_dropped = 0;
   bool dropped_indexed = false, dropped_valid = false;
   std::vector<uint32_t> h_offsets;     // host copy of the locus offsets (they arrive from the host): window -> row range
+  uint64_t sel_row_lo = 0, sel_row_hi = ~0ull;   // rows that can be selected (the window of the last select_loci); [0, inf): unknown
   bool have_offsets = false, h_sel_valid = false;
   uint64_t loci_len = 0;               // n_loci of the uploaded AF table
   DevBuf<uint32_t> d_offsets;
@@ -580,7 +581,11 @@ int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
   if (gblocks <= 8) { warps = gblocks <= 4 ? 4 : 8; ctas_per_sm = 4; }
   const uint32_t slots = (uint32_t)std::min<uint64_t>(8, (gblocks + warps - 1) / warps);
   const uint64_t gy = (gblocks + (uint64_t)warps * slots - 1) / ((uint64_t)warps * slots);
-  const uint64_t n_tiles = (c->n_words + kFastTileWords - 1) / kFastTileWords;
+  // only the tiles of the selection window are swept (a contig is usually analysed in many short windows)
+  const uint64_t all_tiles = (c->n_words + kFastTileWords - 1) / kFastTileWords;
+  const uint64_t tile_begin = std::min<uint64_t>(all_tiles, c->sel_row_lo / kFastTile);
+  const uint64_t tile_end = std::max<uint64_t>(tile_begin, std::min<uint64_t>(all_tiles, c->sel_row_hi == ~0ull ? all_tiles : (c->sel_row_hi + kFastTile - 1) / kFastTile));
+  const uint64_t n_tiles = std::max<uint64_t>(1, tile_end - tile_begin);
   const uint64_t want = std::max<uint64_t>(1, (uint64_t)c->sm_count * ctas_per_sm / gy);
   const uint64_t tpc = std::max<uint64_t>(1, (n_tiles + want - 1) / want);
   fl.tiles_per_chunk = (uint32_t)tpc; fl.slots = slots;
@@ -595,6 +600,7 @@ int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
   P.n_gblocks = gblocks; P.n_words = c->n_words; P.n_loci = c->L; P.n_genomes = c->N; P.n_genomes_padded = c->Npad;
   P.selw = c->prep[c->par].selw.p; P.af = c->d_af.p; P.superpop = c->d_superpop.p; P.n_pop = (int)c->n_pop;
   P.unphased = c->unphased ? 1 : 0; P.tiles_per_chunk = fl.tiles_per_chunk; P.slots = slots;
+  P.tile_begin = tile_begin; P.tile_end = tile_end;
   P.f = c->d_f.p; P.out = c->d_chunk_out.p;
   P.list = list_len ? c->d_list.p : nullptr; P.n_list = list_len; P.n_list_dev = list_len ? c->d_list_count.p : nullptr;
   if (MODE == FAST_HALL || MODE == FAST_NEWTON) {
@@ -1009,6 +1015,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
     c->h_offsets.assign(offsets, offsets + n_loci);
   }
   c->h_sel_valid = false;            // device selection: all zero (nothing selected)
+  c->sel_row_lo = 0; c->sel_row_hi = ~0ull;
   KGL_CUDA(c, c->d_sel.ensure(n_loci));
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, n_loci, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1043,6 +1050,7 @@ int kgl_b200_set_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, const uint8_t
   if (n_loci != c->L) return fail(c, KGL_B200_ERR_INVALID, "selection length differs from n_loci");
   int rc = use_device(c); if (rc) return rc;
   c->h_sel_valid = false;
+  c->sel_row_lo = 0; c->sel_row_hi = ~0ull;
   KGL_CUDA(c, cudaMemcpyAsync(c->d_sel.p, selected, n_loci, cudaMemcpyHostToDevice, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->prep_valid = false;
@@ -1072,6 +1080,12 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
   min_af = std::min(std::max(min_af, 0.0), 1.0);     // LociiVectorArguments clamps (kga_analysis_inbreed_args.h:85-86)
   max_af = std::min(std::max(max_af, 0.0), 1.0);
   const uint64_t L = c->loci_len;
+  // rows of the window [lower, upper] (the offsets are sorted): what the spaced chain walks and the estimator sweeps visit
+  const uint64_t l_begin = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
+                                            [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
+  const uint64_t l_end = std::upper_bound(c->h_offsets.begin(), c->h_offsets.end(), upper,
+                                          [](uint64_t v, uint32_t o) { return v < (uint64_t)o; }) - c->h_offsets.begin();
+  c->sel_row_lo = l_begin; c->sel_row_hi = std::max(l_begin, l_end);
   if (spacing == 0) {
     KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
     KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
@@ -1089,10 +1103,6 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
   }
   // spacing > 0: the candidates (k_select_dense), then the accept chain by pointer doubling (locus_kernels.cuh) over the rows
   // of the window only -- a contig is usually swept in many short windows
-  const uint64_t l_begin = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
-                                            [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
-  const uint64_t l_end = std::upper_bound(c->h_offsets.begin(), c->h_offsets.end(), upper,
-                                          [](uint64_t v, uint32_t o) { return v < (uint64_t)o; }) - c->h_offsets.begin();
   const uint64_t span = l_end > l_begin ? l_end - l_begin : 0;
   KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));

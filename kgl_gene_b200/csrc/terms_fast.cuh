@@ -54,6 +54,7 @@ struct FastParams {
   const float* af;             // [n_pop][n_loci]
   const uint8_t* superpop;     // [n_genomes]
   int n_pop, unphased;
+  uint64_t tile_begin, tile_end;   // tiles that can hold a selected locus (the window of the last select_loci); others are skipped
   uint32_t tiles_per_chunk;    // grid.x chunks of this many tiles
   uint32_t slots;              // genome blocks per warp; grid.y = ceil(n_gblocks / (warps per CTA * slots))
   const double* f;             // [n_genomes_padded] current iterate (HALL / NEWTON)
@@ -215,9 +216,8 @@ k_terms_fast(const FastParams P) {
   const uint64_t gb_first = (uint64_t)blockIdx.y * n_warps * P.slots + warp;      // this warp's genome blocks: gb_first + s * n_warps
   const uint32_t my_slots = gb_first >= P.n_gblocks ? 0u
       : (uint32_t)min((uint64_t)P.slots, (P.n_gblocks - gb_first + n_warps - 1) / n_warps);
-  const uint64_t n_tiles = (P.n_words + kFastTileWords - 1) / kFastTileWords;
-  const uint64_t t_begin = (uint64_t)blockIdx.x * P.tiles_per_chunk;
-  const uint64_t t_end = min(t_begin + (uint64_t)P.tiles_per_chunk, n_tiles);
+  const uint64_t t_begin = P.tile_begin + (uint64_t)blockIdx.x * P.tiles_per_chunk;
+  const uint64_t t_end = min(t_begin + (uint64_t)P.tiles_per_chunk, P.tile_end);
   const double init0 = (MODE == FAST_LIMITS) ? -kHuge : 0.0, init1 = (MODE == FAST_LIMITS) ? kHuge : 0.0;
 
   for (uint32_t s = 0; s < P.slots; ++s)
