@@ -629,7 +629,7 @@ int newton_sweep(kgl_b200_ctx* c) {
   int rc = launch_fast<MODE>(c, fl, c->list_len); if (rc) return rc;
   const unsigned nb = blocks_for(c->N, 256);
   KGL_CUDA(c, cudaMemsetAsync(c->d_n_slow.p, 0, 4, c->stream));
-  k_newton_reduce<<<blocks_for(c->list_len ? c->list_len : c->N, 256), 256, 0, c->stream>>>(
+  k_newton_reduce<<<blocks_for((c->list_len ? c->list_len : c->N) * 8, 256), 256, 0, c->stream>>>(
       c->d_chunk_out.p, FastAcc<MODE>::N, fl.n_chunks, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len,
       c->list_len ? c->d_list_count.p : nullptr, c->d_f.p,
       c->d_limits.p, c->d_done.p, c->d_iter.p, c->d_lane_state.p, c->d_n_slow.p);
@@ -1348,7 +1348,7 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   const unsigned nb = blocks_for(c->N, 256);
   if (c->algo == KGL_B200_ALGO_HALLME) {
     rc = launch_fast<FAST_HALL>(c, fl); if (rc) return rc;
-    k_hall_reduce<<<nb, 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, c->N, c->d_iter.p);
+    k_hall_reduce<<<blocks_for(c->N * 8, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, c->N, c->d_iter.p);
     KGL_LAUNCH_CHECK(c);
     return KGL_B200_OK;
   }
