@@ -43,6 +43,7 @@ extern "C" {
 #define KGL_B200_ERR_CUDA       3   /* a CUDA call failed; see kgl_b200_last_error */
 #define KGL_B200_ERR_NO_DEVICE  4   /* no usable sm_100 GPU */
 #define KGL_B200_ERR_NOMEM      5
+#define KGL_B200_ERR_PEER       6   /* a peer rank did not reach the exchange in time; export / attach the regions again */
 
 #define KGL_B200_MAX_POP 6
 
@@ -216,10 +217,16 @@ int kgl_b200_inbreed_fetch(kgl_b200_ctx* ctx, kgl_b200_locus_results* out);
  * pass on the rank's shard and one kernel that signals the peers, waits for their partial sums, adds them in rank order and
  * applies the closed form. All ranks must call it the same number of times. Results: kgl_b200_inbreed_fetch,
  * kgl_b200_fetch_locus_counts. Replaces InbreedingAnalysis::processResults' per-genome fan-out over one population
- * (kga_analysis_inbreed_diploid.cpp:98-160) when that population is sharded by locus over GPUs. */
+ * (kga_analysis_inbreed_diploid.cpp:98-160) when that population is sharded by locus over GPUs.
+ * Handles of regions exported by contexts of the SAME process (several GPUs driven by one process, or two contexts on one GPU)
+ * are recognised by kgl_b200_peer_attach and mapped directly (CUDA IPC handles cannot be opened by their own process).
+ * A peer that does not reach an exchange within the timeout (default 10 s; kgl_b200_peer_set_timeout_ms) makes that step
+ * fail: its result rows read NaN / zero sums and kgl_b200_inbreed_fetch / kgl_b200_fetch_locus_counts return
+ * KGL_B200_ERR_PEER until the regions have been exported and attached again. */
 #define KGL_B200_PEER_HANDLE_BYTES 64
 int kgl_b200_peer_export(kgl_b200_ctx* ctx, void* handle /* KGL_B200_PEER_HANDLE_BYTES */);
 int kgl_b200_peer_attach(kgl_b200_ctx* ctx, uint32_t rank, uint32_t world, const void* handles /* world x KGL_B200_PEER_HANDLE_BYTES */);
+int kgl_b200_peer_set_timeout_ms(kgl_b200_ctx* ctx, uint64_t milliseconds);
 int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* ctx);
 
 #ifdef __cplusplus

@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building libkgl_b200.so")
-    with open(os.path.join(HERE, "csrc", "ptxas_report.txt"), "w") as f:
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)          # untracked: the ptxas -v report of this build
+    with open(os.path.join(ROOT, "build", "ptxas_report.txt"), "w") as f:
         f.write(proc.stderr)
     return LIB
 

@@ -33,7 +33,7 @@ EXPORTS = [
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
     "kgl_b200_inbreed_fetch", "kgl_b200_kernel_timer_reset", "kgl_b200_kernel_timer_read", "kgl_b200_fetch_locus_counts",
-    "kgl_b200_peer_export", "kgl_b200_peer_attach", "kgl_b200_enqueue_count_and_inbreed_peer",
+    "kgl_b200_peer_export", "kgl_b200_peer_attach", "kgl_b200_peer_set_timeout_ms", "kgl_b200_enqueue_count_and_inbreed_peer",
 ]
 
 
@@ -319,6 +319,9 @@ class KglB200:
         blob = b"".join(handles)
         assert len(blob) == 64 * world
         self._check(self.lib.kgl_b200_peer_attach(self.h, C.c_uint32(rank), C.c_uint32(world), C.c_char_p(blob)), "peer_attach")
+
+    def peer_set_timeout_ms(self, milliseconds: int):
+        self._check(self.lib.kgl_b200_peer_set_timeout_ms(self.h, C.c_uint64(milliseconds)), "peer_set_timeout_ms")
 
     def enqueue_count_and_inbreed_peer(self):
         self._check(self.lib.kgl_b200_enqueue_count_and_inbreed_peer(self.h), "enqueue_count_and_inbreed_peer")

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -28,6 +29,12 @@ using namespace kgl;
 namespace {
 
 thread_local std::string tl_create_error;
+
+// Exchange regions exported by contexts of THIS process (kgl_b200_peer_export): a CUDA IPC handle cannot be opened by the
+// process that created it, so kgl_b200_peer_attach maps such regions directly.
+struct LocalPeerRegion { unsigned char handle[KGL_B200_PEER_HANDLE_BYTES]; void* ptr; int device; const void* owner; };
+std::mutex g_peer_mu;
+std::vector<LocalPeerRegion> g_peer_regions;
 
 template <class T>
 struct DevBuf {
@@ -131,6 +138,10 @@ struct kgl_b200_ctx {
   uint64_t xchg_npad = 0, peer_epoch = 0;
   uint32_t peer_rank = 0, peer_world = 0;
   std::vector<void*> peer_base;           // mapped exchange regions of the other ranks (nullptr for our own slot)
+  std::vector<uint8_t> peer_ipc;          // 1: peer_base[r] was opened with cudaIpcOpenMemHandle (closed on detach)
+  DevBuf<unsigned int> d_peer_error;      // set by k_peer_exchange when a peer did not arrive in time
+  uint64_t peer_timeout_ms = 10000;
+  bool peer_results = false;              // d_results / d_locus_counts were produced by a peer step: the fetches check d_peer_error
   double* partials_target = nullptr;      // where the moment kernels write (d_partials unless a peer step redirects them)
   DevBuf<double2> d_terms_table;         // per-run table constants of the HALL / NEWTON sweeps (terms_fast.cuh)
   int table_mode = -1;                   // mode the table was built for (-1: none); reset by inbreed_begin
@@ -195,6 +206,18 @@ int fail(kgl_b200_ctx* c, int code, const std::string& msg) {
     cudaError_t e_ = cudaGetLastError();                                                                    \
     if (e_ != cudaSuccess) return fail((c), KGL_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
   } while (0)
+
+void peer_detach(kgl_b200_ctx* c) {
+  for (size_t r = 0; r < c->peer_base.size(); ++r)
+    if (c->peer_base[r] && r < c->peer_ipc.size() && c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  c->peer_base.clear(); c->peer_ipc.clear(); c->peer_world = 0;
+}
+
+void peer_unregister(const kgl_b200_ctx* c) {
+  std::lock_guard<std::mutex> lock(g_peer_mu);
+  for (size_t i = 0; i < g_peer_regions.size();)
+    if (g_peer_regions[i].owner == c) g_peer_regions.erase(g_peer_regions.begin() + i); else ++i;
+}
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -861,8 +884,8 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
   c->d_bin_flags.release(); c->d_bin_sum64.release(); c->d_bin_popmask32.release(); c->d_bin_state.release(); c->d_bin_need32.release();
   c->d_zero_superpop.release(); c->d_bin_out.release();
-  for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
-  c->peer_base.clear(); c->d_xchg.release();
+  peer_detach(c); peer_unregister(c);
+  c->d_xchg.release(); c->d_peer_error.release();
   c->d_terms_table.release(); c->d_list_count.release();
   c->d_chain_u32.release(); c->d_chain_mark.release();
   c->d_list.release(); c->d_sm_codes.release(); c->d_limits.release(); c->d_slow_out.release(); c->d_lane_state.release(); c->d_n_slow.release();
@@ -1070,7 +1093,7 @@ int kgl_b200_get_locus_selection(kgl_b200_ctx* c, uint64_t n_loci, uint8_t* sele
 //  * spacing == 0: every locus decides for itself -> one kernel over the device tables (k_select_dense), nothing crosses PCIe
 //    but six counters.
 //  * spacing  > 0: the rule "at least `spacing` after the previously ACCEPTED locus" is a sequential chain per population;
-//    the six chains run on six host threads over host mirrors of the tables (fetched from the device once per upload).
+//    the chains of all populations are marked on the device by pointer doubling (k_chain_*, locus_kernels.cuh).
 int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64_t spacing, double min_af, double max_af,
                          uint64_t* n_selected) {
   if (!c) return KGL_B200_ERR_INVALID;
@@ -1208,6 +1231,7 @@ int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   int rc = use_device(c); if (rc) return rc;
   rc = require_population(c, true); if (rc) return rc;
   c->prep_valid = false;   // the AF vectors are an input of the pass: the per-locus preparation is part of every step
+  c->peer_results = false;
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
   return enqueue_moments(c, true, true);
 }
@@ -1220,15 +1244,21 @@ int kgl_b200_peer_export(kgl_b200_ctx* c, void* handle) {
   int rc = use_device(c); if (rc) return rc;
   if (c->Npad == 0) return fail(c, KGL_B200_ERR_STATE, "upload the genotype matrix (or synthesise it) before exporting the exchange region");
   static_assert(sizeof(cudaIpcMemHandle_t) == KGL_B200_PEER_HANDLE_BYTES, "handle size");
-  for (void* p : c->peer_base) if (p) cudaIpcCloseMemHandle(p);
-  c->peer_base.clear(); c->peer_world = 0;
+  peer_detach(c); peer_unregister(c);
   KGL_CUDA(c, c->d_xchg.ensure(xchg_bytes(c->Npad)));
+  KGL_CUDA(c, c->d_peer_error.ensure(1));
   KGL_CUDA(c, cudaMemsetAsync(c->d_xchg.p, 0, xchg_bytes(c->Npad), c->stream));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_peer_error.p, 0, 4, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->xchg_npad = c->Npad; c->peer_epoch = 0;
+  c->xchg_npad = c->Npad; c->peer_epoch = 0; c->peer_results = false;
   cudaIpcMemHandle_t h;
   KGL_CUDA(c, cudaIpcGetMemHandle(&h, c->d_xchg.p));
   std::memcpy(handle, &h, sizeof h);
+  LocalPeerRegion reg{};
+  std::memcpy(reg.handle, &h, sizeof h);
+  reg.ptr = c->d_xchg.p; reg.device = c->device; reg.owner = c;
+  std::lock_guard<std::mutex> lock(g_peer_mu);
+  g_peer_regions.push_back(reg);
   return KGL_B200_OK;
 }
 
@@ -1237,16 +1267,40 @@ int kgl_b200_peer_attach(kgl_b200_ctx* c, uint32_t rank, uint32_t world, const v
   if (world == 0 || world > (uint32_t)kPeerMaxRanks || rank >= world) return fail(c, KGL_B200_ERR_INVALID, "bad rank / world");
   if (c->d_xchg.p == nullptr || c->xchg_npad != c->Npad) return fail(c, KGL_B200_ERR_STATE, "kgl_b200_peer_export first");
   int rc = use_device(c); if (rc) return rc;
+  peer_detach(c);
   c->peer_base.assign(world, nullptr);
+  c->peer_ipc.assign(world, 0);
   for (uint32_t r = 0; r < world; ++r) {
     if (r == rank) continue;
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * sizeof h, sizeof h);
+    const unsigned char* hb = static_cast<const unsigned char*>(handles) + (size_t)r * KGL_B200_PEER_HANDLE_BYTES;
     void* p = nullptr;
-    KGL_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    int peer_device = -1;
+    {
+      std::lock_guard<std::mutex> lock(g_peer_mu);
+      for (const LocalPeerRegion& reg : g_peer_regions)
+        if (std::memcmp(reg.handle, hb, KGL_B200_PEER_HANDLE_BYTES) == 0) { p = reg.ptr; peer_device = reg.device; break; }
+    }
+    if (p) {                                   // a region of this process: mapped already; another GPU needs peer access
+      if (peer_device != c->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+        KGL_CUDA(c, e);
+      }
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, hb, sizeof h);
+      KGL_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_ipc[r] = 1;
+    }
     c->peer_base[r] = p;
   }
   c->peer_rank = rank; c->peer_world = world;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_peer_set_timeout_ms(kgl_b200_ctx* c, uint64_t milliseconds) {
+  if (!c || milliseconds == 0) return fail(c, KGL_B200_ERR_INVALID, "timeout must be positive");
+  c->peer_timeout_ms = milliseconds;
   return KGL_B200_OK;
 }
 
@@ -1268,20 +1322,36 @@ int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
   PeerParams P{};
   for (uint32_t r = 0; r < c->peer_world; ++r) P.base[r] = static_cast<unsigned char*>(r == c->peer_rank ? (void*)c->d_xchg.p : c->peer_base[r]);
   P.rank = c->peer_rank; P.world = c->peer_world; P.parity_doubles = parity_doubles; P.epoch = epoch; P.n_genomes = c->N;
-  P.partials_out = c->d_partials.p; P.results = c->d_results.p;
-  k_peer_exchange<<<blocks_for(c->N * 8, 256), 256, 0, c->stream>>>(P);
+  P.timeout_ns = c->peer_timeout_ms * 1000000ull;
+  P.partials_out = c->d_partials.p; P.results = c->d_results.p; P.error_word = c->d_peer_error.p;
+  k_peer_publish<<<1, kPeerMaxRanks, 0, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  // one resident wave at most: every block of the exchange spins on the peers' flags
+  const unsigned grid = std::min<unsigned>(blocks_for(c->N * 8, 256), (unsigned)c->sm_count * 4u);
+  k_peer_exchange<<<grid, 256, 0, c->stream>>>(P);
   KGL_LAUNCH_CHECK(c);
   c->algo = KGL_B200_ALGO_SIMPLE; c->phase = 0;     // kgl_b200_inbreed_fetch copies d_results
+  c->peer_results = true;
   return KGL_B200_OK;
+}
+
+// After a stream synchronisation: did the last peer step time out? (The word was copied with the results.)
+static int peer_verdict(kgl_b200_ctx* c, unsigned int word) {
+  if (word == 0) return KGL_B200_OK;
+  peer_detach(c);                                 // the epochs of the ranks no longer agree: start over with export / attach
+  c->peer_results = false;
+  return fail(c, KGL_B200_ERR_PEER, "peer exchange timed out: a rank did not reach the step; export and attach the exchange regions again");
 }
 
 int kgl_b200_fetch_locus_counts(kgl_b200_ctx* c, uint32_t* locus_counts) {
   if (!c || !locus_counts) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   if (c->d_locus_counts.cap < (size_t)c->L * 4) return fail(c, KGL_B200_ERR_STATE, "no per-locus counts have been computed");
   int rc = use_device(c); if (rc) return rc;
+  unsigned int peer_word = 0;
+  if (c->peer_results) KGL_CUDA(c, cudaMemcpyAsync(&peer_word, c->d_peer_error.p, 4, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  return KGL_B200_OK;
+  return peer_verdict(c, peer_word);
 }
 
 int kgl_b200_run_count_and_inbreed(kgl_b200_ctx* c, uint32_t* locus_counts, kgl_b200_locus_results* out) {
@@ -1300,7 +1370,7 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   if (algorithm < KGL_B200_ALGO_SIMPLE || algorithm > KGL_B200_ALGO_LOGLIKELIHOOD) return fail(c, KGL_B200_ERR_INVALID, "unknown algorithm");
   int rc = use_device(c); if (rc) return rc;
   rc = require_population(c, true); if (rc) return rc;
-  c->algo = algorithm; c->phase = 0; c->iteration = 0;
+  c->algo = algorithm; c->phase = 0; c->iteration = 0; c->peer_results = false;
   c->opt = options ? *options : kgl_b200_inbreed_options{};
   c->hall_start.clear();
   if (c->opt.hall_start) c->hall_start.assign(c->opt.hall_start, c->opt.hall_start + c->N);
@@ -1441,9 +1511,11 @@ int kgl_b200_inbreed_fetch(kgl_b200_ctx* c, kgl_b200_locus_results* out) {
     k_store_coeff<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_partials.p, c->d_f.p, c->N, c->d_results.p);
     KGL_LAUNCH_CHECK(c);
   }
+  unsigned int peer_word = 0;
+  if (c->peer_results) KGL_CUDA(c, cudaMemcpyAsync(&peer_word, c->d_peer_error.p, 4, cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaMemcpyAsync(out, c->d_results.p, (size_t)c->N * sizeof(kgl_b200_locus_results), cudaMemcpyDeviceToHost, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  return KGL_B200_OK;
+  return peer_verdict(c, peer_word);
 }
 
 int kgl_b200_run_inbreed(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbreed_options* options, kgl_b200_locus_results* out) {

@@ -133,32 +133,42 @@ k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set h
 // all-reduce + finalize; there is no NCCL call on the step's path. Two parities suffice: a rank can be at most one step ahead
 // of a peer, because its next exchange waits for that peer's next flag.
 constexpr int kPeerMaxRanks = 64;
-constexpr unsigned long long kPeerTimeoutNs = 10ull * 1000 * 1000 * 1000;   // 10 s
+constexpr unsigned long long kPeerTimeoutNsDefault = 10ull * 1000 * 1000 * 1000;   // 10 s
 struct PeerParams {
   unsigned char* base[kPeerMaxRanks];   // exchange regions, index = rank (own region included)
   uint32_t rank, world;
   uint64_t parity_doubles;              // n_genomes_padded * PART_COUNT
   uint64_t epoch;
   uint64_t n_genomes;
+  unsigned long long timeout_ns;
   double* partials_out;                 // reduced partials (local copy, for inbreed_fetch-style consumers)
   kgl_b200_locus_results* results;
+  unsigned int* error_word;             // set to 1 when a peer did not arrive in time; checked by the fetch entry points
 };
 
 __device__ __forceinline__ unsigned long long* peer_flags(unsigned char* base, uint64_t parity_doubles) {
   return reinterpret_cast<unsigned long long*>(base + 2 * parity_doubles * 8);
 }
 
-__global__ void __launch_bounds__(256)
-k_peer_exchange(const PeerParams P) {
-  __shared__ int s_timed_out;
-  // (1) publish: the moment kernel that preceded this launch on the stream has completed, its stores are in this GPU's L2
-  if (blockIdx.x == 0 && threadIdx.x < P.world) {
-    __threadfence_system();
+// Publishes this rank's epoch into every peer's region. A launch of its own, ahead of k_peer_exchange on the stream: the
+// waiting blocks of k_peer_exchange then never depend on one of their own grid being scheduled first.
+__global__ void __launch_bounds__(kPeerMaxRanks)
+k_peer_publish(const PeerParams P) {
+  if (threadIdx.x < P.world) {
+    __threadfence_system();             // the moment kernel that preceded this launch has completed: its stores are in L2
     unsigned long long* f = peer_flags(P.base[threadIdx.x], P.parity_doubles) + P.rank;
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"((unsigned long long)P.epoch) : "memory");
   }
+}
+
+// Grid: at most one resident wave (the host caps it); genomes are walked with a grid stride.
+__global__ void __launch_bounds__(256)
+k_peer_exchange(const PeerParams P) {
+  __shared__ int s_timed_out;
   // (2) wait for every rank's flag in the local region. A peer that never arrives (its process died) must not hang the GPU:
-  // after kPeerTimeoutNs the step gives up and every coefficient of this rank becomes NaN.
+  // after the timeout the step gives up, every result row of this rank becomes NaN / zero and the error word is set --
+  // kgl_b200_inbreed_fetch / kgl_b200_fetch_locus_counts then fail with KGL_B200_ERR_PEER until the regions are exported and
+  // attached again.
   if (threadIdx.x == 0) s_timed_out = 0;
   __syncthreads();
   if (threadIdx.x < P.world) {
@@ -170,45 +180,53 @@ k_peer_exchange(const PeerParams P) {
       if (v < P.epoch) {
         __nanosleep(100);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > kPeerTimeoutNs) { s_timed_out = 1; break; }
+        if (t1 - t0 > P.timeout_ns) { s_timed_out = 1; break; }
       }
     } while (v < P.epoch);
   }
   __syncthreads();
   const bool timed_out = s_timed_out != 0;
+  if (timed_out && threadIdx.x == 0) atomicExch(P.error_word, 1u);
   // (3) gather + fixed-order sum + closed form. Eight lanes per genome, one pair of doubles each; the loads of up to eight
   // ranks are in flight together (an NVLink round trip is ~1.5 us: serialised they would cost more than the all-reduce).
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t g = t >> 3;
-  const int jp = (int)(t & 7);
-  const bool live = g < P.n_genomes;
-  double s0 = 0.0, s1 = 0.0;
-  if (live) {
-    const uint64_t off = (P.epoch & 1ull) * P.parity_doubles + g * PART_COUNT + jp * 2;
-    for (uint32_t r0 = 0; r0 < P.world; r0 += 8) {
-      double a[8], b[8];
+  const uint64_t n_items = (P.n_genomes * 8 + 31) / 32 * 32;          // whole warps: every lane reaches the __syncwarp
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t g = t >> 3;
+    const int jp = (int)(t & 7);
+    const bool live = g < P.n_genomes;
+    double s0 = 0.0, s1 = 0.0;
+    if (live) {
+      if (!timed_out) {
+        const uint64_t off = (P.epoch & 1ull) * P.parity_doubles + g * PART_COUNT + jp * 2;
+        for (uint32_t r0 = 0; r0 < P.world; r0 += 8) {
+          double a[8], b[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a[i] = 0.0; b[i] = 0.0;
-        if (r0 + i < P.world) {
-          const double* src = reinterpret_cast<const double*>(P.base[r0 + i]) + off;
-          asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[i]), "=d"(b[i]) : "l"(src) : "memory");
+          for (int i = 0; i < 8; ++i) {
+            a[i] = 0.0; b[i] = 0.0;
+            if (r0 + i < P.world) {
+              const double* src = reinterpret_cast<const double*>(P.base[r0 + i]) + off;
+              asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[i]), "=d"(b[i]) : "l"(src) : "memory");
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (r0 + i < P.world) { s0 += a[i]; s1 += b[i]; }    // rank order
         }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (r0 + i < P.world) { s0 += a[i]; s1 += b[i]; }    // rank order
+      P.partials_out[g * PART_COUNT + jp * 2] = s0;
+      P.partials_out[g * PART_COUNT + jp * 2 + 1] = s1;
     }
-    P.partials_out[g * PART_COUNT + jp * 2] = s0;
-    P.partials_out[g * PART_COUNT + jp * 2 + 1] = s1;
-  }
-  __syncwarp();
-  if (live && jp == 0) {
-    double sum[PART_COUNT];
+    __syncwarp();
+    if (live && jp == 0) {
+      double sum[PART_COUNT];
 #pragma unroll
-    for (int j = 0; j < PART_COUNT; ++j) sum[j] = __ldcg(P.partials_out + g * PART_COUNT + j);
-    kgl_b200_locus_results r = closed_form(sum, KGL_B200_ALGO_SIMPLE);
-    if (timed_out) r.inbred_allele_sum = __longlong_as_double(0x7ff8000000000000ll);
-    P.results[g] = r;
+      for (int j = 0; j < PART_COUNT; ++j) sum[j] = __ldcg(P.partials_out + g * PART_COUNT + j);
+      kgl_b200_locus_results r = closed_form(sum, KGL_B200_ALGO_SIMPLE);
+      if (timed_out) {                   // the whole row: no count or sum of a step that did not complete is reported
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        r.major_hetero_freq = r.minor_hetero_freq = r.minor_homo_freq = r.major_homo_freq = r.inbred_allele_sum = nan;
+      }
+      P.results[g] = r;
+    }
   }
 }
 

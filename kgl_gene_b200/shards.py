@@ -29,22 +29,49 @@ def locus_shard(n_loci: int, rank: int, world: int, align: int = 256) -> tuple[i
     return min(b0 * align, n_loci), min(b1 * align, n_loci)
 
 
-def allreduce_partials(ctx, device, group=None):
-    """SUM all-reduce of the context's per-genome partial-sum buffer across the ranks (NCCL on the context's GPU)."""
-    import torch
-    import torch.distributed as dist
-    ptr, count = ctx.inbreed_partials_buffer()
-    t = torch.as_tensor(_RawCudaArray(ptr, count, "<f8"), device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-
-
 class _RawCudaArray:
     def __init__(self, ptr: int, n: int, typestr: str):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
+def bind_to_current_stream(ctx, device):
+    """Orders the context's kernels with the collectives torch issues on `device`.
+
+    dist.all_reduce is ordered against torch's CURRENT stream only, while a context enqueues on its own non-blocking stream
+    unless told otherwise. With a real torch stream current, the context is bound to it (kgl_b200_set_stream) and stream
+    order does the rest: returns None. With the legacy default stream current -- handle 0, which the C ABI reads as "the
+    context's own stream" -- the two cannot share a stream: returns that stream and the helpers below synchronise explicitly
+    on both sides of the collective."""
+    import torch
+    s = torch.cuda.current_stream(device)
+    if s.cuda_stream != 0:
+        ctx.set_stream(s.cuda_stream)
+        return None
+    return s
+
+
+def _allreduce_device_buffer(ctx, ptr, count, typestr, device, group):
+    import torch
+    import torch.distributed as dist
+    fence = bind_to_current_stream(ctx, device)
+    if fence is not None:
+        ctx.synchronize()                 # the buffer is complete before the collective reads it
+    t = torch.as_tensor(_RawCudaArray(ptr, count, typestr), device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if fence is not None:
+        fence.synchronize()               # ... and reduced before the context's next kernel reads it
+
+
+def allreduce_partials(ctx, device, group=None):
+    """SUM all-reduce of the context's per-genome partial-sum buffer across the ranks (NCCL on the context's GPU), ordered
+    after the kernels that fill it and before the ones that consume it (bind_to_current_stream)."""
+    ptr, count = ctx.inbreed_partials_buffer()
+    _allreduce_device_buffer(ctx, ptr, count, "<f8", device, group)
+
+
 def run_inbreed_sharded(ctx, algorithm: str, device, group=None, **options):
     """The estimator state machine of the C ABI with the all-reduce in the middle: every rank holds a locus shard."""
+    bind_to_current_stream(ctx, device)
     ctx.inbreed_begin(algorithm, **options)
     finished = False
     while not finished:
@@ -57,11 +84,8 @@ def run_inbreed_sharded(ctx, algorithm: str, device, group=None, **options):
 def allreduce_gram(ctx, device, group=None):
     """SUM all-reduce of the context's int32 Gram matrix: every rank computed the tiles rank, rank + world, ... and left
     the rest zero (kgl_b200_enqueue_gram_tiles)."""
-    import torch
-    import torch.distributed as dist
     ptr, count, _ = ctx.gram_buffer()
-    t = torch.as_tensor(_RawCudaArray(ptr, count, "<i4"), device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    _allreduce_device_buffer(ctx, ptr, count, "<i4", device, group)
 
 
 # ------------------------------------------------------------------------------------------------ IBS tiles ----------

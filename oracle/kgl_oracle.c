@@ -222,13 +222,23 @@ void kgl_oracle_inbreed(const uint8_t* packed, size_t row_bytes, size_t n_genome
                         const float* af, size_t n_pop, const uint8_t* selected, const uint8_t* superpop,
                         int unphased, int algorithm, const double* start, int sweeps,
                         kgl_oracle_locus_results* out) {
-  (void)n_pop;
+  kgl_oracle_inbreed_some(packed, row_bytes, n_genomes, n_loci, af, n_pop, selected, superpop, unphased, algorithm, start, sweeps,
+                          NULL, n_genomes, out);
+}
+
+/* The same for a list of genomes (genomes == NULL: 0 .. n_some-1); out[i] belongs to genomes[i]. Every genome is an
+ * independent task in the reference (kga_analysis_inbreed_diploid.cpp:117-150), so a subset is exact for its members. */
+void kgl_oracle_inbreed_some(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                             const float* af, size_t n_pop, const uint8_t* selected, const uint8_t* superpop,
+                             int unphased, int algorithm, const double* start, int sweeps,
+                             const uint32_t* genomes, size_t n_some, kgl_oracle_locus_results* out) {
+  (void)n_pop; (void)n_genomes;
 #pragma omp parallel
   {
     locus_term* terms = (locus_term*)malloc(sizeof(locus_term) * (n_loci ? n_loci : 1));
 #pragma omp for schedule(dynamic, 1)
-    for (long gi = 0; gi < (long)n_genomes; ++gi) {
-      const size_t g = (size_t)gi;
+    for (long gi = 0; gi < (long)n_some; ++gi) {
+      const size_t g = genomes ? (size_t)genomes[gi] : (size_t)gi;
       const size_t k = superpop[g];
       kgl_oracle_locus_results r;
       const size_t n = generate_frequencies(packed, row_bytes, n_loci, g, af + k * n_loci, selected + k * n_loci,
@@ -281,7 +291,7 @@ void kgl_oracle_inbreed(const uint8_t* packed, size_t row_bytes, size_t n_genome
           r.inbred_allele_sum = log_likelihood_argmax(terms, n, simple);
         } break;
       }
-      out[g] = r;
+      out[gi] = r;
     }
     free(terms);
   }
@@ -307,15 +317,26 @@ void kgl_oracle_loglik_grid(const uint8_t* packed, size_t row_bytes, size_t n_ge
 
 void kgl_oracle_allele_count(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
                              uint32_t* locus_counts, uint64_t* genome_counts) {
-  /* The byte-at-a-time switch of kgl_variant_db_variant.cpp:142-163 / :196-217, on 2-bit cells. */
+  /* The byte-at-a-time switch of kgl_variant_db_variant.cpp:142-163 / :196-217, on 2-bit cells. Loci are dealt to the
+   * threads; every thread keeps its own per-genome counters (integer sums: the order does not matter). */
   memset(locus_counts, 0, n_loci * 4 * sizeof(uint32_t));
   memset(genome_counts, 0, n_genomes * 4 * sizeof(uint64_t));
-  for (size_t l = 0; l < n_loci; ++l)
-    for (size_t g = 0; g < n_genomes; ++g) {
-      const unsigned c = cell_code(packed, row_bytes, l, g);
-      ++locus_counts[l * 4 + c];
-      ++genome_counts[g * 4 + c];
+#pragma omp parallel
+  {
+    uint64_t* mine = (uint64_t*)calloc(n_genomes * 4 + 1, sizeof(uint64_t));
+#pragma omp for schedule(static)
+    for (long li = 0; li < (long)n_loci; ++li) {
+      const size_t l = (size_t)li;
+      for (size_t g = 0; g < n_genomes; ++g) {
+        const unsigned c = cell_code(packed, row_bytes, l, g);
+        ++locus_counts[l * 4 + c];
+        ++mine[g * 4 + c];
+      }
     }
+#pragma omp critical
+    for (size_t i = 0; i < n_genomes * 4; ++i) genome_counts[i] += mine[i];
+    free(mine);
+  }
 }
 
 void kgl_oracle_ibs(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci, uint32_t* out) {
@@ -339,6 +360,68 @@ void kgl_oracle_ibs(const uint8_t* packed, size_t row_bytes, size_t n_genomes, s
     }
   }
   free(codes);
+}
+
+/* 64 x 64 bit-matrix transpose (recursive block swap): on return bit j of a[i] is bit i of the old a[j]. */
+static void transpose64(uint64_t a[64]) {
+  uint64_t m = 0x00000000FFFFFFFFULL;
+  for (int j = 32; j != 0; j >>= 1, m ^= (m << j)) {
+    for (int k = 0; k < 64; k = (k + j + 1) & ~j) {
+      const uint64_t t = ((a[k] >> j) ^ a[k + j]) & m;
+      a[k] ^= t << j;
+      a[k + j] ^= t;
+    }
+  }
+}
+
+/* Popcount restatement of pairwise IBS "for scale" (SURVEY 8c/8d): genome-major thermometer bit-planes over 64-locus words,
+ * X = (g >= 1), Y = (g == 2), V = (g != 3); for a pair dX = Xa ^ Xb, dY = Ya ^ Yb, v = Va & Vb:
+ *   IBS0 = popc(dX & dY & v), IBS2 = popc(~(dX | dY) & v), IBS1 = popc(v) - IBS0 - IBS2.
+ * Independent of the naive loop above (which it is checked against in tests/) and of the device kernel's two-plane / carry-save
+ * form. out u32[row_end - row_begin][N][4]. */
+void kgl_oracle_ibs_band_popcount(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                                  size_t row_begin, size_t row_end, uint32_t* out) {
+  const size_t n_words = (n_loci + 63) / 64, units = row_bytes / 16;
+  uint64_t* X = (uint64_t*)calloc(n_genomes * n_words + 1, 8);
+  uint64_t* Y = (uint64_t*)calloc(n_genomes * n_words + 1, 8);
+  uint64_t* V = (uint64_t*)calloc(n_genomes * n_words + 1, 8);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long ui = 0; ui < (long)units; ++ui) {
+    const size_t u = (size_t)ui;
+    uint64_t lo[64], hi[64];
+    for (size_t w = 0; w < n_words; ++w) {
+      for (size_t i = 0; i < 64; ++i) {
+        const size_t l = w * 64 + i;
+        if (l < n_loci) { memcpy(&lo[i], packed + l * row_bytes + u * 16, 8); memcpy(&hi[i], packed + l * row_bytes + u * 16 + 8, 8); }
+        else { lo[i] = ~0ULL; hi[i] = ~0ULL; }                       /* beyond the last locus: code 3, never valid */
+      }
+      transpose64(lo); transpose64(hi);                               /* now word b = the 64 loci of genome 64u + b */
+      for (size_t b = 0; b < 64 && u * 64 + b < n_genomes; ++b) {
+        const uint64_t l0 = lo[b], h0 = hi[b], valid = ~(l0 & h0);
+        X[(u * 64 + b) * n_words + w] = (l0 | h0) & valid;
+        Y[(u * 64 + b) * n_words + w] = h0 & valid;
+        V[(u * 64 + b) * n_words + w] = valid;
+      }
+    }
+  }
+#pragma omp parallel for schedule(dynamic, 1)
+  for (long ai = (long)row_begin; ai < (long)row_end; ++ai) {
+    const size_t a = (size_t)ai;
+    const uint64_t *xa = X + a * n_words, *ya = Y + a * n_words, *va = V + a * n_words;
+    for (size_t b = 0; b < n_genomes; ++b) {
+      const uint64_t *xb = X + b * n_words, *yb = Y + b * n_words, *vb = V + b * n_words;
+      uint64_t c0 = 0, c2 = 0, cv = 0;
+      for (size_t w = 0; w < n_words; ++w) {
+        const uint64_t dx = xa[w] ^ xb[w], dy = ya[w] ^ yb[w], v = va[w] & vb[w];
+        c0 += (uint64_t)__builtin_popcountll(dx & dy & v);
+        c2 += (uint64_t)__builtin_popcountll(~(dx | dy) & v);
+        cv += (uint64_t)__builtin_popcountll(v);
+      }
+      uint32_t* o = out + ((a - row_begin) * n_genomes + b) * 4;
+      o[0] = (uint32_t)c0; o[1] = (uint32_t)(cv - c0 - c2); o[2] = (uint32_t)c2; o[3] = (uint32_t)cv;
+    }
+  }
+  free(X); free(Y); free(V);
 }
 
 /* K5 checker: dosage Gram matrix S[a][b] = sum_l g_al g_bl with g in {0,1,2}, code 3 -> 0 (the DB's own convention: no entry at

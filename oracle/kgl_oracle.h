@@ -50,6 +50,13 @@ void kgl_oracle_inbreed(const uint8_t* packed, size_t row_bytes, size_t n_genome
                         int unphased, int algorithm, const double* start, int sweeps,
                         kgl_oracle_locus_results* out);
 
+/* The same for the listed genomes only (out[i] belongs to genomes[i]; NULL = the first n_some): checks at full BASELINE
+ * width where the 50-sweep / root-search estimators over every genome would take minutes of CPU. */
+void kgl_oracle_inbreed_some(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                             const float* af, size_t n_pop, const uint8_t* selected, const uint8_t* superpop,
+                             int unphased, int algorithm, const double* start, int sweeps,
+                             const uint32_t* genomes, size_t n_some, kgl_oracle_locus_results* out);
+
 /* InbreedingCalculation::logLikelihood (kga_analysis_inbreed_calc.cpp:94-129) on a grid of f values. out[g][i]. */
 void kgl_oracle_loglik_grid(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
                             const float* af, size_t n_pop, const uint8_t* selected, const uint8_t* superpop,
@@ -63,6 +70,11 @@ void kgl_oracle_allele_count(const uint8_t* packed, size_t row_bytes, size_t n_g
 
 /* Pairwise IBS (no reference code; standard definitions). out u32[N][N][4] = ibs0, ibs1, ibs2, valid. */
 void kgl_oracle_ibs(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci, uint32_t* out);
+
+/* The same counts for the genomes [row_begin, row_end) against all genomes by AND/XOR + popcount over 64-locus words of
+ * genome-major bit-planes ("popcount CPU restatement for scale"). out u32[row_end - row_begin][N][4]. */
+void kgl_oracle_ibs_band_popcount(const uint8_t* packed, size_t row_bytes, size_t n_genomes, size_t n_loci,
+                                  size_t row_begin, size_t row_end, uint32_t* out);
 
 /* Dosage Gram matrix gram i32[N][N] = sum_l g_a g_b (code 3 -> 0) and, when af_pop and grm are given, the centred matrix
  * grm f64[N][N] = sum_l (g_a - 2p)(g_b - 2p), p = clamp(af_pop[l], 0, 1), absent AF -> 0. No reference code. */

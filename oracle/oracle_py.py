@@ -65,16 +65,20 @@ def select_all_pops(pop, **kw):
     return np.stack([select_loci(pop.offsets, pop.af[k], **kw)[0] for k in range(pop.af.shape[0])])
 
 
-def inbreed(pop, selected, algorithm: str, start=None, sweeps: int = 50) -> np.ndarray:
-    out = np.zeros(pop.n_genomes, dtype=RESULT_DTYPE)
+def inbreed(pop, selected, algorithm: str, start=None, sweeps: int = 50, genomes=None) -> np.ndarray:
+    """genomes: optional list of genome indices -- the result then has one row per listed genome (start stays indexed by genome)."""
+    gl = None if genomes is None else np.ascontiguousarray(genomes, dtype=np.uint32)
+    n_some = pop.n_genomes if gl is None else gl.shape[0]
+    out = np.zeros(n_some, dtype=RESULT_DTYPE)
     packed = np.ascontiguousarray(pop.packed)
     af = np.ascontiguousarray(pop.af, dtype=np.float32)
     selected = np.ascontiguousarray(selected, dtype=np.uint8)
     sp = np.ascontiguousarray(pop.superpop, dtype=np.uint8)
     st = None if start is None else np.ascontiguousarray(start, dtype=np.float64)
-    lib().kgl_oracle_inbreed(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci),
-                             _p(af), C.c_size_t(af.shape[0]), _p(selected), _p(sp), C.c_int(int(pop.unphased)),
-                             C.c_int(ALGORITHMS[algorithm]), None if st is None else _p(st), C.c_int(sweeps), _p(out))
+    lib().kgl_oracle_inbreed_some(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci),
+                                  _p(af), C.c_size_t(af.shape[0]), _p(selected), _p(sp), C.c_int(int(pop.unphased)),
+                                  C.c_int(ALGORITHMS[algorithm]), None if st is None else _p(st), C.c_int(sweeps),
+                                  None if gl is None else _p(gl), C.c_size_t(n_some), _p(out))
     return out
 
 
@@ -103,6 +107,15 @@ def ibs(pop) -> np.ndarray:
     out = np.zeros((pop.n_genomes, pop.n_genomes, 4), dtype=np.uint32)
     packed = np.ascontiguousarray(pop.packed)
     lib().kgl_oracle_ibs(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci), _p(out))
+    return out
+
+
+def ibs_band_popcount(pop, row_begin: int, row_end: int) -> np.ndarray:
+    """IBS of genomes [row_begin, row_end) against all genomes by the popcount restatement (scale checker)."""
+    out = np.zeros((row_end - row_begin, pop.n_genomes, 4), dtype=np.uint32)
+    packed = np.ascontiguousarray(pop.packed)
+    lib().kgl_oracle_ibs_band_popcount(_p(packed), C.c_size_t(pop.row_bytes), C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci),
+                                       C.c_size_t(row_begin), C.c_size_t(row_end), _p(out))
     return out
 
 

@@ -120,6 +120,12 @@ CASES = [
     dict(n_genomes=1, n_loci=100, seed=4, spectrum="dense"),                                # single genome
     dict(n_genomes=2504, n_loci=3000, seed=5, spectrum="sfs", missing_rate=0.02, missing_af_rate=0.02),
     dict(n_genomes=130, n_loci=31, seed=6, spectrum="dense"),                               # fewer loci than one word
+    # BASELINE config 1 width (449..512 genomes = 8 units: k_stream_count_ct<8,256>), phased and unphased,
+    # every row selected (even seeds: spacing 0) and a spaced, masked selection (odd seeds: spacing 20)
+    dict(n_genomes=500, n_loci=30000, seed=7, spectrum="sfs", missing_rate=0.004, missing_af_rate=0.01),
+    dict(n_genomes=500, n_loci=30000, seed=8, spectrum="sfs", unphased=True),
+    dict(n_genomes=449, n_loci=12001, seed=9, spectrum="dense", unphased=True, grouped=False, missing_af_rate=0.03),
+    dict(n_genomes=512, n_loci=25600, seed=10, spectrum="sfs", grouped=False),
 ]
 
 

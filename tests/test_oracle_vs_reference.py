@@ -147,3 +147,34 @@ def test_live_reference_run_matches_oracle():
     sel = O.select_all_pops(pop, spacing=15)
     for algo in ("Simple", "RitlandLocus"):
         assert np.array_equal(O.inbreed(pop, sel, algo)["inbred_allele_sum"], ref[algo + "_coeff"])
+
+
+# ---------------------------------------------------------------------------------------------- scale checkers ----------
+@pytest.mark.parametrize("n,l,miss", [(150, 3001, 0.03), (70, 999, 0.0), (1, 40, 0.1), (130, 64, 0.5), (65, 129, 0.2)])
+def test_popcount_ibs_restatement_equals_naive_loop(n, l, miss):
+    """"plus a popcount CPU restatement for scale" -- thermometer bit-planes + popcount against the naive O(N^2 L) loop."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(n, l, seed=21 + n, missing_rate=miss)
+    want = O.ibs(pop)
+    assert np.array_equal(O.ibs_band_popcount(pop, 0, n), want)
+    if n > 100:
+        assert np.array_equal(O.ibs_band_popcount(pop, 64, 130), want[64:130])
+
+
+def test_inbreed_subset_equals_full_run():
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(90, 4000, seed=14)
+    sel = O.select_all_pops(pop, spacing=15)
+    some = np.array([3, 89, 40, 0], dtype=np.uint32)
+    start = np.linspace(0.05, 0.5, pop.n_genomes)
+    for algo, kw in (("Simple", {}), ("RitlandLocus", {}), ("HallME", dict(start=start, sweeps=50)), ("Loglikelihood", {})):
+        assert O.inbreed(pop, sel, algo, genomes=some, **kw).tobytes() == O.inbreed(pop, sel, algo, **kw)[some].tobytes()
+
+
+def test_parallel_allele_count_is_exact():
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(333, 5000, seed=15, missing_rate=0.02)
+    lc, gc = O.allele_count(pop)
+    codes = pop.codes()
+    for c in range(4):
+        assert np.array_equal(lc[:, c], (codes == c).sum(1)) and np.array_equal(gc[:, c], (codes == c).sum(0))
