@@ -9,7 +9,7 @@
 #include "terms_fast.cuh"
 #include "misc_kernels.cuh"
 #include "ibs_launch.cuh"
-#include "post_kernels.cuh"
+#include "tail_kernels.cuh"
 #include "gram_launch.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -82,8 +82,10 @@ struct kgl_b200_ctx {
   DevBuf<unsigned long long> d_dropped_counter;
   DevBuf<DroppedKey> d_dropped_unsorted;
   DevBuf<uint8_t> d_sort_temp;
+  DevBuf<uint2> d_dropped_cells;         // per indexed cell {row, frequency float of the genome's population} (k_dropped_cells)
   uint64_t n_dropped = 0;
   bool dropped_indexed = false, dropped_valid = false;
+  int dropped_cells_state = 0;           // 0: stale; 1: rows only (no frequencies uploaded yet); 2: rows + frequencies
   std::vector<uint32_t> h_offsets;     // host copy of the locus offsets (they arrive from the host): window -> row range
   uint64_t sel_row_lo = 0, sel_row_hi = ~0ull;   // rows that can be selected (the window of the last select_loci); [0, inf): unknown
   bool have_offsets = false, h_sel_valid = false;
@@ -97,14 +99,21 @@ struct kgl_b200_ctx {
   bool units_valid = false;
 
   // per-locus preparation
-  // Outputs of k_locus_prepare, double-buffered: the preparation of pass i+1 runs on prep_stream while the sparse kernels
-  // of pass i still read the buffers of pass i (ensure_prepared). n_rare: [0] rare-row count, [1] all-selected flag,
-  // [2] blocks with an unselected row.
+  // Outputs of k_locus_prepare, double-buffered: the preparation of pass i+1 runs on prep_stream while the tail kernel
+  // of pass i still reads the buffers of pass i (ensure_prepared). acc: every accumulator of a preparation in one allocation,
+  // zeroed with one memset -- {uint32 blocks with an unselected row, 3 x pad} | totals_fx u64[6][TOT_COUNT] |
+  // ecorr_fx u64[Npad][2] | nz_rare u32[Npad].
   struct PrepSet {
     DevBuf<uint16_t> flags16, sum64;
-    DevBuf<uint32_t> selw, rare_rows, n_rare;
-    DevBuf<double> block_totals, totals;
-    void release() { flags16.release(); sum64.release(); selw.release(); rare_rows.release(); n_rare.release(); block_totals.release(); totals.release(); }
+    DevBuf<uint32_t> selw;
+    DevBuf<uint8_t> acc;
+    static constexpr size_t kTotalsOff = 16, kEcorrOff = 16 + kMaxPop * TOT_COUNT * 8;
+    static size_t acc_bytes(uint64_t npad) { return kEcorrOff + (size_t)npad * 20; }
+    uint32_t* unselected_blocks() const { return reinterpret_cast<uint32_t*>(acc.p); }
+    unsigned long long* totals_fx() const { return reinterpret_cast<unsigned long long*>(acc.p + kTotalsOff); }
+    unsigned long long* ecorr_fx() const { return reinterpret_cast<unsigned long long*>(acc.p + kEcorrOff); }
+    uint32_t* nz_rare(uint64_t npad) const { return reinterpret_cast<uint32_t*>(acc.p + kEcorrOff + npad * 16); }
+    void release() { flags16.release(); sum64.release(); selw.release(); acc.release(); }
   } prep[2];
   int par = 0;                                  // the set the current selection was prepared into
   cudaStream_t prep_stream = nullptr, copy_stream = nullptr;
@@ -113,7 +122,7 @@ struct kgl_b200_ctx {
   bool stream_pass_marked = false;
   bool readers_marked[2] = {false, false};
   bool inputs_async = false;                    // d_sel was last written by a kernel on the main stream without a host sync
-  bool prep_valid = false, prep_has_w0 = false;
+  bool prep_valid = false, prep_has_w0 = false, prep_has_selw = false;
 
   // sample-major copy
   DevBuf<uint32_t> d_sm_lo, d_sm_hi;
@@ -122,10 +131,11 @@ struct kgl_b200_ctx {
   bool sm_valid = false, codes_valid = false;
 
   // fused pass outputs
-  DevBuf<uint32_t> d_locus_counts, d_planes;
+  DevBuf<uint32_t> d_locus_counts, d_cta_counts;
   DevBuf<uint8_t> d_scratch;            // per-genome accumulators of one pass, zeroed with a single memset
-  uint32_t *d_gcounts = nullptr, *d_n3 = nullptr, *d_nz_rare = nullptr;
-  double* d_ecorr = nullptr;
+  uint32_t *d_gcounts = nullptr, *d_n3 = nullptr;
+  unsigned long long* d_ecorr_scan = nullptr;   // fallback path (code-3 cells not indexed): k_dropped_scan's fixed-point sums
+  DevBuf<uint8_t> d_zero_rare;           // zeros standing in for the rare-row accumulators of a pass without a preparation
   DevBuf<double> d_partials, d_iter, d_f, d_bracket, d_chunk_out, d_inbreeding, d_grid;
   DevBuf<uint32_t> d_done;
   DevBuf<unsigned long long> d_flag;
@@ -175,9 +185,7 @@ struct kgl_b200_ctx {
   uint64_t gram_ld = 0, gram_tiles_ld = 0, gram_n_tiles = 0, gram_first = 0, gram_stride = 1;
   bool codes16_valid = false;
   cudaEvent_t gram_e0 = nullptr, gram_e1 = nullptr;
-  DevBuf<unsigned int> d_ticket;
-  bool fused_tail = false;           // KGL_B200_FUSED_TAIL=1: the last block of k_post assembles the per-genome results (slower: one block, serial)
-  bool tail_done = false;            // the last launch_count already assembled the per-genome results (fused tail)
+  bool tail_done = false;            // the last launch_count already assembled the per-genome partial sums (k_tail)
 
   // iterative estimator state
   int algo = -1, phase = 0, iteration = 0;
@@ -264,19 +272,12 @@ uint64_t term_words(uint64_t n_loci) {
   return (nw + kTermTileWords - 1) / kTermTileWords * kTermTileWords;
 }
 
-// Ticket counters of the "last block finishes the job" kernels: [0] k_post, [1], [2] k_locus_prepare per buffer set. They
-// reset themselves.
-cudaError_t ensure_tickets(kgl_b200_ctx* c) {
-  if (c->d_ticket.p) return cudaSuccess;
-  cudaError_t e = c->d_ticket.ensure(4);
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->d_ticket.p, 0, 16, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  return e;
-}
-
-// Selection flags, 64-row summaries, packed selection words, rare-major row list and dense totals (once per selection).
-int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
-  if (c->prep_valid && (c->prep_has_w0 || !want_w0)) return KGL_B200_OK;
+// Selection flags, 64-row summaries, packed selection words, rare-major rows and dense totals (once per selection).
+int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false, bool want_selw = false) {
+  if (c->prep_valid && (c->prep_has_w0 || !want_w0) && (c->prep_has_selw || !want_selw)) return KGL_B200_OK;
+  want_w0 = want_w0 || (c->prep_valid && c->prep_has_w0);          // a repeat keeps what the earlier one produced
+  want_selw = want_selw || (c->prep_valid && c->prep_has_selw);
+  int rc = build_unit_tables(c); if (rc) return rc;
   const uint64_t L = c->L;
   c->n_words = term_words(L);
   const uint64_t span = std::max<uint64_t>(c->padded_rows, c->n_words * 32);
@@ -287,21 +288,18 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
     for (cudaEvent_t& e : c->readers_done) KGL_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     KGL_CUDA(c, cudaEventCreateWithFlags(&c->stream_pass_done, cudaEventDisableTiming));
   }
-  KGL_CUDA(c, ensure_tickets(c));
   // Everything enqueued on the main stream so far may read the current set: mark it, switch to the other set, and let the
   // preparation start as soon as the readers of THAT set (marked one switch ago) are done -- i.e. concurrently with the
-  // tail (k_post, k_moment_partials) of the pass that is still running on the main stream.
+  // tail kernel of the pass that is still running on the main stream.
   KGL_CUDA(c, cudaEventRecord(c->readers_done[c->par], c->stream));
   c->readers_marked[c->par] = true;
   c->par ^= 1;
   kgl_b200_ctx::PrepSet& S = c->prep[c->par];
   KGL_CUDA(c, S.flags16.ensure(c->padded_rows));
   KGL_CUDA(c, S.sum64.ensure(c->padded_rows / 64));
-  KGL_CUDA(c, S.selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
-  KGL_CUDA(c, S.rare_rows.ensure(L));
-  KGL_CUDA(c, S.n_rare.ensure(4));
-  KGL_CUDA(c, S.block_totals.ensure((size_t)nb * kMaxPop * TOT_COUNT));
-  KGL_CUDA(c, S.totals.ensure(kMaxPop * TOT_COUNT));
+  if (want_selw) KGL_CUDA(c, S.selw.ensure((size_t)KGL_B200_MAX_POP * c->n_words));
+  const size_t acc_bytes = kgl_b200_ctx::PrepSet::acc_bytes(c->Npad);
+  KGL_CUDA(c, S.acc.ensure(acc_bytes));
   cudaStream_t ps = c->prep_stream;
   if (c->readers_marked[c->par]) KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_done[c->par], 0));
   // not before the last streaming kernel has finished: it owns every SM, a preparation block that slips in ahead of one of
@@ -311,18 +309,22 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false) {
     KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_done[c->par ^ 1], 0));
     c->inputs_async = false;
   }
-  KGL_CUDA(c, cudaMemsetAsync(S.n_rare.p, 0, 16, ps));
-  unsigned int* ticket = c->d_ticket.p + 1 + c->par;
-  if (want_w0)
-    k_locus_prepare<true><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, S.flags16.p, S.sum64.p, S.selw.p,
-                                                       c->n_words, S.rare_rows.p, S.n_rare.p, S.block_totals.p, S.totals.p, S.n_rare.p + 1, ticket);
-  else
-    k_locus_prepare<false><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, 0, S.flags16.p, S.sum64.p, S.selw.p,
-                                                        c->n_words, S.rare_rows.p, S.n_rare.p, S.block_totals.p, S.totals.p, S.n_rare.p + 1, ticket);
+  KGL_CUDA(c, cudaMemsetAsync(S.acc.p, 0, acc_bytes, ps));
+  const uint4* packed = reinterpret_cast<const uint4*>(c->d_packed.p);
+  const double fx = fx_scale_for(L);
+#define KGL_PREP(W0, SELW)                                                                                                          \
+  k_locus_prepare<W0, SELW><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, S.flags16.p,     \
+      S.sum64.p, SELW ? S.selw.p : nullptr, c->n_words, packed, (uint32_t)c->units, c->d_popmask.p, S.nz_rare(c->Npad),            \
+      S.ecorr_fx(), fx, S.totals_fx(), S.unselected_blocks())
+  if (want_w0 && want_selw) KGL_PREP(true, true);
+  else if (want_w0) KGL_PREP(true, false);
+  else if (want_selw) KGL_PREP(false, true);
+  else KGL_PREP(false, false);
+#undef KGL_PREP
   KGL_LAUNCH_CHECK(c);
   KGL_CUDA(c, cudaEventRecord(c->prep_done, ps));
   KGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->prep_done, 0));
-  c->prep_valid = true; c->prep_has_w0 = want_w0;
+  c->prep_valid = true; c->prep_has_w0 = want_w0; c->prep_has_selw = want_selw;
   return KGL_B200_OK;
 }
 
@@ -367,7 +369,7 @@ int finish_dropped_index(kgl_b200_ctx* c, unsigned long long total) {
     KGL_LAUNCH_CHECK(c);
     KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  c->dropped_valid = true;
+  c->dropped_valid = true; c->dropped_cells_state = 0;
   return KGL_B200_OK;
 }
 
@@ -407,18 +409,38 @@ int alloc_matrix(kgl_b200_ctx* c) {
   return KGL_B200_OK;
 }
 
-// The fused streaming pass + its sparse companions. raw: allele_count over all loci; otherwise over the selected loci.
-// Leaves d_gcounts {lo, hi}, d_n3, d_nz_rare, d_ecorr per genome and the per-locus counts.
+// Per-cell side list {row, frequency float of the genome's population} of the indexed code-3 cells, for k_tail. Follows the
+// key index (once per matrix) and the frequency table / super-populations (rebuilt when either is uploaded again).
+int ensure_dropped_cells(kgl_b200_ctx* c, bool want_af) {
+  if (!c->dropped_indexed || c->n_dropped == 0) return KGL_B200_OK;
+  const bool have_af = c->have_loci && c->have_superpop && c->loci_len == c->L;
+  if (want_af && !have_af) return fail(c, KGL_B200_ERR_STATE, "internal: the code-3 side list needs the allele frequencies");
+  const int want_state = have_af ? 2 : 1;
+  if (c->dropped_cells_state >= want_state) return KGL_B200_OK;
+  KGL_CUDA(c, c->d_dropped_cells.ensure(c->n_dropped));
+  k_dropped_cells<<<blocks_for(c->n_dropped, 256), 256, 0, c->stream>>>(c->d_dropped.p, c->n_dropped, have_af ? c->d_superpop.p : nullptr,
+                                                                        c->d_af.p, c->L, c->d_dropped_cells.p);
+  KGL_LAUNCH_CHECK(c);
+  c->dropped_cells_state = want_state;
+  return KGL_B200_OK;
+}
+
+DenseTotals dense_totals(const kgl_b200_ctx* c, const kgl_b200_ctx::PrepSet& S) {
+  const double fx = fx_scale_for(c->L);
+  return DenseTotals{S.totals_fx(), 1.0 / fx, 128.0 / fx};
+}
+
+// The fused streaming pass + its tail. raw: allele_count over all loci; otherwise over the selected loci.
 // Row mask that replaces the per-population selection flags of a pass: every genome belongs to "population 0" and a row
 // counts iff bit 0 of flags16 is set (the AF-bin passes of kgl_b200_run_binned_genome_counts).
 struct MaskOverride {
   const uint16_t* flags16; const uint16_t* sum64; const uint32_t* popmask32; const uint8_t* need32;
-  const uint32_t* all_selected; const uint8_t* zero_superpop;
+  const uint8_t* zero_superpop;
 };
 
-// tail_mode: what the last block of k_post assembles -- 0 nothing, 1 the moment partials (d_partials; + the Simple closed
-// form into d_results when simple_results), 2 the raw per-genome counts (d_genome_counts).
-int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false, int tail_mode = 0,
+// want_moments: the tail assembles the moment partials of every genome (d_partials; + the Simple closed form into d_results
+// when simple_results); otherwise it leaves the raw per-genome counts d_gcounts {set lo bits, set hi bits} and d_n3.
+int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false, bool want_moments = false,
                  const MaskOverride* mo = nullptr) {
   int rc = mo ? KGL_B200_OK : build_unit_tables(c);
   if (rc) return rc;
@@ -430,15 +452,16 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     KGL_CUDA(c, c->d_locus_counts.ensure((size_t)c->L * 4));
     if (pl.slices > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_locus_counts.p, 0, (size_t)c->L * 16, c->stream));
   }
+  const bool indexed = c->dropped_indexed || c->n_dropped == 0;
   if (want_genome) {
-    KGL_CUDA(c, c->d_planes.ensure((size_t)pl.n_vchunks * c->units * 4 * kScLevels));
-    // scratch: gcounts u32[Npad][2] | n3 u32[Npad] | nz_rare u32[Npad] | ecorr f64[Npad][2]
+    KGL_CUDA(c, c->d_cta_counts.ensure((size_t)pl.n_ctas * 2 * c->Npad));
+    // scratch: gcounts u32[Npad][2] | n3 u32[Npad] | pad u32[Npad] | ecorr_scan u64[Npad][2] (fallback path only)
     KGL_CUDA(c, c->d_scratch.ensure((size_t)c->Npad * 32));
     c->d_gcounts = reinterpret_cast<uint32_t*>(c->d_scratch.p);
     c->d_n3 = c->d_gcounts + c->Npad * 2;
-    c->d_nz_rare = c->d_n3 + c->Npad;
-    c->d_ecorr = reinterpret_cast<double*>(c->d_scratch.p + (size_t)c->Npad * 16);
-    KGL_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0, (size_t)c->Npad * 32, c->stream));
+    c->d_ecorr_scan = reinterpret_cast<unsigned long long*>(c->d_scratch.p + (size_t)c->Npad * 16);
+    if (!indexed) KGL_CUDA(c, cudaMemsetAsync(c->d_scratch.p, 0, (size_t)c->Npad * 32, c->stream));
+    if (indexed) { rc = ensure_dropped_cells(c, want_moments); if (rc) return rc; }
   }
   StreamParams P{};
   fill_stream_params(P, pl);
@@ -450,7 +473,8 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   P.need32 = mo ? mo->need32 : c->d_need32.p;
   P.n_pop = (raw || mo) ? 1 : c->n_pop;
   P.locus_counts = want_locus_counts ? c->d_locus_counts.p : nullptr;
-  P.planes = want_genome ? c->d_planes.p : nullptr;
+  P.cta_counts = want_genome ? c->d_cta_counts.p : nullptr;
+  P.n_genomes_padded = (uint32_t)c->Npad;
   cudaEvent_t e0 = c->ev0, e1 = c->ev1;
   if (c->timer_used < kgl_b200_ctx::kTimerSlots) {
     if ((int)c->timer_ev.size() < 2 * (c->timer_used + 1)) {
@@ -474,65 +498,57 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     KGL_LAUNCH_CHECK(c);
   }
   c->tail_done = false;
-  if (want_genome) {
-    const SparseOut so{c->d_n3, c->d_nz_rare, c->d_ecorr};
-    const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->prep[c->par].flags16.p);
-    const unsigned e_bx = blocks_for(c->Npad, 256), e_by = (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup);
-    if (c->dropped_indexed || c->n_dropped == 0) {
-      // one launch: counter expansion, indexed code-3 cells and rare-major rows side by side; the last block assembles
-      // the per-genome results (post_kernels.cuh)
-      PostParams Q{};
-      Q.planes = c->d_planes.p; Q.n_vchunks = pl.n_vchunks; Q.units = c->units; Q.n_genomes_padded = c->Npad; Q.gcounts = c->d_gcounts;
-      Q.e_bx = e_bx; Q.e_by = e_by;
-      Q.keys = c->d_dropped.p; Q.seg = c->d_dropped_seg.p; Q.d_blocks = c->n_dropped ? (unsigned)((c->N + kDropGenomesPerBlock - 1) / kDropGenomesPerBlock) : 0u;
-      Q.rare_rows = c->prep[c->par].rare_rows.p; Q.n_rare = c->prep[c->par].n_rare.p; Q.packed = reinterpret_cast<const uint4*>(c->d_packed.p);
-      Q.popmask = c->d_popmask.p; Q.r_blocks = (raw || mo) ? 0u : 32u;
-      Q.n_genomes = c->N; Q.n_loci = c->L; Q.n_pop = (int)c->n_pop;
-      Q.flags16 = fl; Q.all_selected = mo ? mo->all_selected : (raw ? nullptr : c->prep[c->par].n_rare.p + 1);
-      Q.superpop = mo ? mo->zero_superpop : c->d_superpop.p; Q.af = c->d_af.p;
-      Q.so = so;
-      Q.tail_mode = c->fused_tail ? tail_mode : 0; Q.unphased = c->unphased ? 1 : 0;
-      Q.totals = c->prep[c->par].totals.p; Q.partials = c->partials_target ? c->partials_target : c->d_partials.p;
-      Q.results = simple_results ? c->d_results.p : nullptr;
-      Q.genome_counts = c->d_genome_counts.p; Q.ticket = c->d_ticket.p;
-      KGL_CUDA(c, ensure_tickets(c));
-      k_post<<<e_bx * e_by + Q.d_blocks + Q.r_blocks, 256, 0, c->stream>>>(Q);
-      KGL_LAUNCH_CHECK(c);
-      c->tail_done = Q.tail_mode != 0;
-    } else {
-      dim3 eg(e_bx, e_by);
-      k_expand_planes<<<eg, 256, 0, c->stream>>>(c->d_planes.p, pl.n_vchunks, c->units, c->Npad, c->d_gcounts);
-      KGL_LAUNCH_CHECK(c);
-      const uint64_t n128 = c->L * c->units;
-      const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
-      k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
-                                                   mo ? mo->zero_superpop : c->d_superpop.p, c->d_af.p, c->L, so);
-      KGL_LAUNCH_CHECK(c);
-      if (!raw && !mo) {
-        k_rare_rows<<<32, 256, 0, c->stream>>>(c->prep[c->par].rare_rows.p, c->prep[c->par].n_rare.p, reinterpret_cast<const uint4*>(c->d_packed.p),
-                                               (uint32_t)c->units, (uint32_t)c->N, c->prep[c->par].flags16.p, c->d_popmask.p, c->d_af.p,
-                                               c->L, (int)c->n_pop, so);
-        KGL_LAUNCH_CHECK(c);
-      }
+  if (!want_genome) return KGL_B200_OK;
+  const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->prep[c->par].flags16.p);
+  const kgl_b200_ctx::PrepSet& S = c->prep[c->par];
+  const bool prepared = !raw && !mo;
+  const double fx = fx_scale_for(c->L);
+  if (indexed) {
+    TailParams T{};
+    T.cta_counts = c->d_cta_counts.p; T.n_ctas = pl.n_ctas; T.n_genomes_padded = c->Npad;
+    T.cells = c->n_dropped ? c->d_dropped_cells.p : nullptr; T.seg = c->d_dropped_seg.p;
+    T.row_lo = 0; T.row_hi = 0xFFFFFFFFu;
+    if (prepared && c->sel_row_hi != ~0ull && (c->sel_row_lo > 0 || c->sel_row_hi < c->L)) {   // a proper window
+      T.row_lo = (uint32_t)c->sel_row_lo; T.row_hi = (uint32_t)std::min<uint64_t>(c->sel_row_hi, 0xFFFFFFFEull);
     }
+    T.n_genomes = c->N; T.flags16 = fl;
+    T.unselected_blocks = prepared ? S.unselected_blocks() : nullptr;
+    T.superpop = mo ? mo->zero_superpop : c->d_superpop.p;
+    T.want_moments = want_moments ? 1 : 0; T.unphased = c->unphased ? 1 : 0;
+    T.nz_rare = prepared ? S.nz_rare(c->Npad) : nullptr; T.ecorr_rare_fx = prepared ? S.ecorr_fx() : nullptr; T.fx_inv = 1.0 / fx;
+    T.totals = dense_totals(c, S); T.partials = c->partials_target ? c->partials_target : c->d_partials.p;
+    T.results = simple_results ? c->d_results.p : nullptr;
+    T.gcounts = c->d_gcounts; T.n3 = c->d_n3;
+    k_tail<<<blocks_for(c->N, kTailGenomesPerBlock), 256, 0, c->stream>>>(T);
+    KGL_LAUNCH_CHECK(c);
+    c->tail_done = want_moments;
+    return KGL_B200_OK;
+  }
+  // populations whose code-3 cells are too many to index: separate kernels, the matrix is scanned for the cells
+  k_sum_cta_counts<<<blocks_for(c->Npad, 256), 256, 0, c->stream>>>(c->d_cta_counts.p, pl.n_ctas, c->Npad, c->d_gcounts);
+  KGL_LAUNCH_CHECK(c);
+  const uint64_t n128 = c->L * c->units;
+  const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
+  k_dropped_scan<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(c->d_packed.p), n128, (uint32_t)c->units, fl,
+                                               mo ? mo->zero_superpop : c->d_superpop.p, c->d_af.p, c->L, c->d_n3, c->d_ecorr_scan, fx);
+  KGL_LAUNCH_CHECK(c);
+  if (want_moments) {
+    k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, dense_totals(c, S), c->d_ecorr_scan, S.nz_rare(c->Npad),
+                                                                    S.ecorr_fx(), 1.0 / fx, c->d_superpop.p, c->N, c->unphased ? 1 : 0,
+                                                                    c->partials_target ? c->partials_target : c->d_partials.p,
+                                                                    simple_results ? c->d_results.p : nullptr);
+    KGL_LAUNCH_CHECK(c);
+    c->tail_done = true;
   }
   return KGL_B200_OK;
 }
 
 // Moments of all genomes over the selected loci into d_partials (phase 0 of every estimator).
-int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false) {
-  int rc = ensure_prepared(c, want_w0);
+int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false, bool want_selw = false) {
+  int rc = ensure_prepared(c, want_w0, want_selw);
   if (rc) return rc;
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
-  rc = launch_count(c, false, want_locus_counts, true, simple_results, 1);
-  if (rc) return rc;
-  if (c->tail_done) return KGL_B200_OK;
-  k_moment_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->prep[c->par].totals.p, c->d_ecorr, c->d_nz_rare,
-                                                                  c->d_superpop.p, c->N, c->unphased ? 1 : 0,
-                                                                  c->partials_target ? c->partials_target : c->d_partials.p,
-                                                                  simple_results ? c->d_results.p : nullptr);
-  KGL_LAUNCH_CHECK(c);
-  return KGL_B200_OK;
+  return launch_count(c, false, want_locus_counts, true, simple_results, true);
 }
 
 struct TermLaunch { dim3 grid; uint32_t words_per_chunk; uint64_t n_chunks; };
@@ -865,7 +881,6 @@ int kgl_b200_create(int device, kgl_b200_ctx** out) {
     return fail(nullptr, KGL_B200_ERR_CUDA, m);
   }
   c->stream = c->own_stream;
-  if (const char* e = std::getenv("KGL_B200_FUSED_TAIL")) c->fused_tail = e[0] == '1';
   *out = c;
   return KGL_B200_OK;
 }
@@ -876,11 +891,11 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_need32.release();
   c->d_popmask.release(); c->prep[0].release(); c->prep[1].release();
-  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_planes.release(); c->d_scratch.release();
+  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_cta_counts.release(); c->d_scratch.release(); c->d_dropped_cells.release(); c->d_zero_rare.release();
   c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release();
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
-  c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release(); c->d_ticket.release();
+  c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
   c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
   c->d_bin_flags.release(); c->d_bin_sum64.release(); c->d_bin_popmask32.release(); c->d_bin_state.release(); c->d_bin_need32.release();
   c->d_zero_superpop.release(); c->d_bin_out.release();
@@ -959,7 +974,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
-  c->sm_valid = false; c->codes_valid = false; c->units_valid = false; c->dropped_valid = false; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
+  c->sm_valid = false; c->codes_valid = false; c->units_valid = false; c->dropped_valid = false; c->dropped_cells_state = 0; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
   c->codes16_valid = false;
   return KGL_B200_OK;
 }
@@ -1042,7 +1057,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   KGL_CUDA(c, c->d_sel.ensure(n_loci));
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, n_loci, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->have_loci = true; c->prep_valid = false;
+  c->have_loci = true; c->prep_valid = false; c->dropped_cells_state = 0;
   return KGL_B200_OK;
 }
 
@@ -1056,7 +1071,7 @@ int kgl_b200_set_genome_superpop(kgl_b200_ctx* c, uint64_t n_genomes, const uint
   KGL_CUDA(c, c->d_superpop.ensure(n_genomes));
   KGL_CUDA(c, cudaMemcpyAsync(c->d_superpop.p, superpop, n_genomes, cudaMemcpyHostToDevice, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->have_superpop = true; c->units_valid = false;
+  c->have_superpop = true; c->units_valid = false; c->dropped_cells_state = 0; c->prep_valid = false;
   if (!c->have_geno) c->N = n_genomes;
   return KGL_B200_OK;
 }
@@ -1214,11 +1229,11 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t*
     c->have_superpop = false;
   }
   if (genome_counts) KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 4));
-  rc = launch_count(c, true, locus_counts != nullptr, genome_counts != nullptr, false, 2); if (rc) return rc;
+  rc = launch_count(c, true, locus_counts != nullptr, genome_counts != nullptr); if (rc) return rc;
   if (locus_counts)
     KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
   if (genome_counts) {
-    if (!c->tail_done) k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->L, c->d_genome_counts.p);
+    k_genome_counts_raw<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->L, c->d_genome_counts.p);
     KGL_LAUNCH_CHECK(c);
     KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_genome_counts.p, (size_t)c->N * 32, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -1312,7 +1327,6 @@ int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
   c->prep_valid = false;   // the AF vectors are an input of the pass, as in kgl_b200_enqueue_count_and_inbreed
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
-  KGL_CUDA(c, ensure_tickets(c));
   const uint64_t epoch = ++c->peer_epoch;
   const uint64_t parity_doubles = c->Npad * PART_COUNT;
   c->partials_target = reinterpret_cast<double*>(c->d_xchg.p) + (epoch & 1ull) * parity_doubles;
@@ -1402,10 +1416,10 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   int rc = use_device(c); if (rc) return rc;
   FastLaunch fl;
   if (c->phase == 0) {
-    rc = enqueue_moments(c, c->opt.count_loci != 0, false, c->algo == KGL_B200_ALGO_RITLAND); if (rc) return rc;
+    rc = enqueue_moments(c, c->opt.count_loci != 0, false, c->algo == KGL_B200_ALGO_RITLAND, c->algo != KGL_B200_ALGO_SIMPLE); if (rc) return rc;
     if (c->algo == KGL_B200_ALGO_RITLAND) {
       rc = launch_fast<FAST_RITLAND>(c, fl); if (rc) return rc;
-      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, 2, c->prep[c->par].totals.p,
+      k_ritland_partials<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, 2, dense_totals(c, c->prep[c->par]),
                                                                        c->d_superpop.p, c->N, c->d_partials.p);
       KGL_LAUNCH_CHECK(c);
     }
@@ -1533,7 +1547,7 @@ int kgl_b200_run_loglik_grid(kgl_b200_ctx* c, const double* grid, uint64_t n_gri
   if (!c || !grid || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   int rc = use_device(c); if (rc) return rc;
   rc = require_population(c, true); if (rc) return rc;
-  rc = ensure_prepared(c); if (rc) return rc;
+  rc = ensure_prepared(c, false, true); if (rc) return rc;
   KGL_CUDA(c, c->d_grid.ensure(kGridMax));
   for (uint64_t g0 = 0; g0 < n_grid; g0 += kGridMax) {
     const int ng = (int)std::min<uint64_t>(kGridMax, n_grid - g0);
@@ -1760,14 +1774,14 @@ int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* c, uint32_t pop, uint32_t n_
   KGL_CUDA(c, c->d_bin_flags.ensure(c->padded_rows));
   KGL_CUDA(c, c->d_bin_sum64.ensure(c->padded_rows / 64));
   KGL_CUDA(c, c->d_bin_out.ensure((size_t)n_bins * c->N * 4 + n_bins));
-  const MaskOverride mo{c->d_bin_flags.p, c->d_bin_sum64.p, c->d_bin_popmask32.p, c->d_bin_need32.p, c->d_bin_state.p, c->d_zero_superpop.p};
+  const MaskOverride mo{c->d_bin_flags.p, c->d_bin_sum64.p, c->d_bin_popmask32.p, c->d_bin_need32.p, c->d_zero_superpop.p};
   for (uint32_t b = 0; b < n_bins; ++b) {
     KGL_CUDA(c, cudaMemsetAsync(c->d_bin_state.p, 0, 8, c->stream));
     k_bin_flags<<<blocks_for(c->padded_rows, 256), 256, 0, c->stream>>>(c->d_af.p + (size_t)pop * c->L, present_only ? c->d_locus_counts.p : nullptr,
                                                                          c->L, c->padded_rows, lower[b], upper[b], c->d_bin_flags.p,
                                                                          c->d_bin_sum64.p, c->d_bin_state.p + 1);
     KGL_LAUNCH_CHECK(c);
-    rc = launch_count(c, false, false, true, false, 0, &mo); if (rc) return rc;
+    rc = launch_count(c, false, false, true, false, false, &mo); if (rc) return rc;
     k_genome_counts_masked<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->d_bin_state.p + 1,
                                                                          c->d_bin_out.p + (size_t)b * c->N * 4, c->d_bin_out.p + (size_t)n_bins * c->N * 4 + b);
     KGL_LAUNCH_CHECK(c);

@@ -16,29 +16,54 @@ enum { TOT_T = 0,       // number of selected valid loci
        TOT_W0,          // sum over q > 0.01 loci of (1/q - 1): the Ritland term of a hom-ref genome (calc.cpp:397-401)
        TOT_COUNT };
 
+// The totals are accumulated by the preparation blocks with 64-bit integer atomics -- counts as they are, sums in fixed point
+// (terms in [0, 1]; TOT_W0 terms are below 128) -- so they are exact sums of the rounded terms, independent of the schedule,
+// and need no "last block" pass.
+struct DenseTotals {
+  const unsigned long long* fx;   // [kMaxPop][TOT_COUNT]
+  double inv, inv_w0;             // 1 / scale of the class-frequency sums, of TOT_W0
+  __device__ __forceinline__ double get(int k, int j) const {
+    const long long v = (long long)__ldcg(&fx[k * TOT_COUNT + j]);
+    return (j == TOT_T || j == TOT_TQ) ? (double)v : (double)v * (j == TOT_W0 ? inv_w0 : inv);
+  }
+};
+
 constexpr int kPrepThreads = 256;
 constexpr int kPrepIters = 4;                                   // 64-locus groups per warp
 constexpr int kPrepLociPerBlock = (kPrepThreads / 32) * 64 * kPrepIters;   // 2048
 
 // flags16[l] bit k: locus selected for population k AND its AF vector is valid; bit 8+k: ... AND q_k <= 0.01 ("rare-q")
 // sum64[l/64]  low byte: AND over the group's rows of the low flag byte, high byte: OR (rows >= n_loci count as 0)
-// selw[k][w]   bit i: flags bit k of locus 32w+i (sample-major kernels)
-// rare_rows / n_rare: list of the rows with a rare-q bit (any order)
-// block_totals[block][k][TOT_COUNT]   (TOT_W0 only when WANT_W0: it costs a double-precision divide per locus and
-//                                      only the Ritland estimator reads it)
+// selw[k][w]   bit i: flags bit k of locus 32w+i (sample-major kernels; only with WANT_SELW -- the Simple step has no use
+//              for it and the 48 ballots per thread were a fifth of the kernel)
+// totals_fx[k][TOT_COUNT] (zeroed by the caller; TOT_W0 only when WANT_W0: it costs a double-precision divide per locus and
+//              only the Ritland estimator reads it)
+// rare-major rows (some population has q <= 0.01 there: a hom-ref genome of that population is dropped, freq.cpp:532-539) are
+// settled by the block that finds them, right behind its loci: nz_rare[g] += non-reference cells of the population's genomes in
+// the row, ecorr_fx[g][2] += class frequencies {majHom, minHom} of the hom-ref ones (64-bit fixed point: the atomic adds commute).
+//
+// The expected class frequencies alleleClassFrequencies(0.0) of a locus are {q^2, 2qp, p^2} / (q^2 + 2qp + p^2) (freq.cpp:127-217,
+// freq.h:54-63). q = fl(1 - p) is exact for every float p >= 2^-29, so the divisor is (q + p)^2 = 1 up to the rounding of the
+// three products, |divisor - 1| < 3e-16: the dense totals accumulate the products themselves (three DFMA per locus and
+// population instead of nine multiplies, two adds and a subtract); a total differs from the reference's by < 1e-15 relative.
+//
 // A warp owns 64 consecutive loci per iteration (lane -> l, l+32), so the group summary and the selection words need no
-// shared memory. The population loop is the OUTER loop: only one population's six totals are live at a time, which keeps
-// the kernel at ~64 registers and the SM full of warps to hide the double-precision divide latency.
-template <bool WANT_W0>
+// shared memory. The population loop is the OUTER loop: only one population's totals are live at a time.
+constexpr int kPrepRareMax = kPrepLociPerBlock;
+template <bool WANT_W0, bool WANT_SELW>
 __global__ void __launch_bounds__(kPrepThreads)
 k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, uint64_t n_loci, uint64_t padded_rows, int n_pop,
-                int select_all, uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64,
-                uint32_t* __restrict__ selw, uint64_t n_words, uint32_t* __restrict__ rare_rows, uint32_t* __restrict__ n_rare,
-                double* __restrict__ block_totals, double* __restrict__ totals, uint32_t* __restrict__ all_selected,
-                unsigned int* __restrict__ ticket) {
+                uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64, uint32_t* __restrict__ selw, uint64_t n_words,
+                const uint4* __restrict__ packed, uint32_t units, const uint64_t* __restrict__ popmask,
+                uint32_t* __restrict__ nz_rare, unsigned long long* __restrict__ ecorr_fx, double fx,
+                unsigned long long* __restrict__ totals_fx, uint32_t* __restrict__ unselected_blocks) {
   __shared__ double s_tot[kPrepThreads / 32][kMaxPop][TOT_COUNT];
-  __shared__ int s_last;
+  __shared__ uint32_t s_rare[kPrepRareMax];
+  __shared__ uint16_t s_rare_fl[kPrepRareMax];
+  __shared__ uint32_t s_n_rare;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_n_rare = 0;
+  __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kPrepLociPerBlock + (uint64_t)warp * 64 + lane;   // + it * 512 + half * 32
   constexpr int kStep = (kPrepThreads / 32) * 64;                  // loci between two iterations of a warp
   uint32_t fl[kPrepIters][2], sbits[kPrepIters][2];
@@ -48,7 +73,7 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
     for (int half = 0; half < 2; ++half) {
       const uint64_t l = base + (uint64_t)(it * kStep + 32 * half);
       fl[it][half] = 0;
-      sbits[it][half] = (l < n_loci) ? (select_all ? 0x3fu : (uint32_t)sel[l]) : 0u;     // 0 beyond n_loci: nothing is read there
+      sbits[it][half] = (l < n_loci) ? (uint32_t)sel[l] : 0u;      // 0 beyond n_loci: nothing is read there
     }
   // rows past n_loci are never dereferenced: their selection bits are 0 and the frequency pointer is clamped to row 0
   const uint64_t safe_base = base < n_loci ? base : 0;
@@ -57,9 +82,7 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
   const float* afk = af + safe_base;
   uint32_t* selw_k = selw;
   for (int k = 0; k < n_pop; ++k, afk += n_loci, selw_k += n_words) {
-    double acc[TOT_COUNT];
-#pragma unroll
-    for (int j = 0; j < TOT_COUNT; ++j) acc[j] = 0.0;
+    double e_majhom = 0.0, e_majhet = 0.0, e_minhom = 0.0, w0 = 0.0;
     uint32_t n_t = 0, n_tq = 0;
     // all of this population's frequencies first: eight independent loads in flight instead of eight load->use chains
     float afv[kPrepIters][2];
@@ -72,26 +95,32 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
     for (int it = 0; it < kPrepIters; ++it)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        bool on = false;
-        if ((sbits[it][half] >> k) & 1u) {
-          const LocusFreq f = locus_freq(afv[it][half]);
-          if (f.valid) {
-            on = true;
-            fl[it][half] |= 1u << k;
-            double a, b, c;
-            class_freqs(f.p, a, b, c);
-            ++n_t; acc[TOT_EMAJHOM] += a; acc[TOT_EMAJHET] += b; acc[TOT_EMINHOM] += c;
-            if (f.q > kMinMajorFreq) { ++n_tq; if (WANT_W0) acc[TOT_W0] += __dsub_rn(__ddiv_rn(1.0, f.q), 1.0); }
-            else fl[it][half] |= 0x100u << k;
+        const float a = afv[it][half];
+        const bool on = ((sbits[it][half] >> k) & 1u) && !(a != a);
+        if (on) {
+          double p = (double)a;
+          p = p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p);
+          double q = __dsub_rn(1.0, p);
+          q = q < 0.0 ? 0.0 : q;
+          fl[it][half] |= 1u << k;
+          ++n_t;
+          e_majhom = fma(q, q, e_majhom);
+          e_majhet = fma(__dadd_rn(q, q), p, e_majhet);
+          e_minhom = fma(p, p, e_minhom);
+          if (q > kMinMajorFreq) { ++n_tq; if (WANT_W0) w0 += __dsub_rn(__ddiv_rn(1.0, q), 1.0); }
+          else fl[it][half] |= 0x100u << k;
+        }
+        if (WANT_SELW) {
+          const uint32_t word = __ballot_sync(kFull, on);
+          if (lane == 0) {
+            const uint64_t w = (base + (uint64_t)(it * kStep + 32 * half)) >> 5;
+            if (w < n_words) selw_k[w] = word;
           }
         }
-        const uint32_t word = __ballot_sync(kFull, on);
-        if (lane == 0 && selw != nullptr) {
-          const uint64_t w = (base + (uint64_t)(it * kStep + 32 * half)) >> 5;
-          if (w < n_words) selw_k[w] = word;
-        }
       }
+    double acc[TOT_COUNT];
     acc[TOT_T] = (double)n_t; acc[TOT_TQ] = (double)n_tq;
+    acc[TOT_EMAJHOM] = e_majhom; acc[TOT_EMAJHET] = e_majhet; acc[TOT_EMINHOM] = e_minhom; acc[TOT_W0] = w0;
 #pragma unroll
     for (int j = 0; j < TOT_COUNT; ++j) {
       const double v = warp_sum(acc[j]);
@@ -108,7 +137,10 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
     for (int half = 0; half < 2; ++half) {
       const uint64_t l = l0 + 32 * half;
       if (l < padded_rows) flags16[l] = (uint16_t)fl[it][half];
-      if ((fl[it][half] >> 8) != 0 && rare_rows != nullptr) rare_rows[atomicAdd(n_rare, 1u)] = (uint32_t)l;
+      if ((fl[it][half] >> 8) != 0 && nz_rare != nullptr) {
+        const uint32_t slot = atomicAdd(&s_n_rare, 1u);
+        s_rare[slot] = (uint32_t)l; s_rare_fl[slot] = (uint16_t)(fl[it][half] >> 8);
+      }
     }
     const uint32_t g_and = __reduce_and_sync(kFull, fl[it][0] & fl[it][1]) & 0xFFu;
     const uint32_t g_or = __reduce_or_sync(kFull, fl[it][0] | fl[it][1]) & 0xFFu;
@@ -118,13 +150,60 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
   __syncthreads();
   if (threadIdx.x < kMaxPop * TOT_COUNT) {
     const int k = threadIdx.x / TOT_COUNT, j = threadIdx.x % TOT_COUNT;
-    double v = 0.0;
-    for (int w = 0; w < kPrepThreads / 32; ++w) v += s_tot[w][k][j];
-    block_totals[((uint64_t)blockIdx.x * kMaxPop + k) * TOT_COUNT + j] = v;
+    if (k < n_pop) {
+      double v = 0.0;
+      for (int w = 0; w < kPrepThreads / 32; ++w) v += s_tot[w][k][j];
+      const double scale = (j == TOT_T || j == TOT_TQ) ? 1.0 : (j == TOT_W0 ? fx * (1.0 / 128.0) : fx);
+      const long long q = __double2ll_rn(v * scale);
+      if (q != 0) atomicAdd(&totals_fx[k * TOT_COUNT + j], (unsigned long long)q);
+    }
   }
 
-  // all_selected[1] (zeroed by the caller) counts the blocks that hold a row < n_loci which is not selected and valid for
-  // every population; all_selected[0] = 1 iff there is none (then the sparse kernels need not look at the flags).
+  // ---- the block's rare-major rows: one thread per (row, 128-bit unit); the loads of an item do not depend on each other ----
+  {
+    const uint32_t n_rare_blk = s_n_rare;
+    const uint64_t total = (uint64_t)n_rare_blk * units;
+    for (uint64_t t = threadIdx.x; t < total; t += kPrepThreads) {
+      const uint32_t slot = (uint32_t)(t / units), u = (uint32_t)(t % units);
+      const uint32_t row = s_rare[slot];
+      uint32_t rq = s_rare_fl[slot];                       // populations with q <= 0.01 at this row (selected & valid)
+      const uint4 v = packed[(uint64_t)row * units + u];
+      float a6[kMaxPop];
+      uint64_t m6[kMaxPop];
+#pragma unroll
+      for (int k = 0; k < kMaxPop; ++k) {
+        const bool on = (rq >> k) & 1u;
+        a6[k] = on ? af[(uint64_t)k * n_loci + row] : 0.0f;
+        m6[k] = on ? popmask[(uint64_t)k * units + u] : 0ull;
+      }
+      const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+#pragma unroll
+      for (int k = 0; k < kMaxPop; ++k) {
+        const uint64_t mask = m6[k];
+        if (mask == 0) continue;
+        double ca, ch, cm;
+        class_freqs(locus_freq(a6[k]).p, ca, ch, cm);
+        const unsigned long long qa = (unsigned long long)__double2ll_rn(ca * fx), qm = (unsigned long long)__double2ll_rn(cm * fx);
+        uint64_t homref = ~(lo | hi) & mask;
+        uint64_t nonref = (lo | hi) & mask;
+        while (homref) {
+          const int b = __ffsll((long long)homref) - 1;
+          homref &= homref - 1;
+          const uint64_t g = (uint64_t)u * 64 + b;
+          atomicAdd(&ecorr_fx[g * 2 + 0], qa);
+          atomicAdd(&ecorr_fx[g * 2 + 1], qm);
+        }
+        while (nonref) {
+          const int b = __ffsll((long long)nonref) - 1;
+          nonref &= nonref - 1;
+          atomicAdd(&nz_rare[(uint64_t)u * 64 + b], 1u);
+        }
+      }
+    }
+  }
+
+  // unselected_blocks (zeroed by the caller) counts the blocks that hold a row < n_loci which is not selected and valid for
+  // every population: 0 at the end = the sparse kernels need not look at the flags.
   {
     const uint32_t all_pops = (1u << n_pop) - 1u;
     bool ok = true;
@@ -135,35 +214,8 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
         const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
         if (l < n_loci && (fl[it][half] & all_pops) != all_pops) ok = false;
       }
-    if (!__syncthreads_and(ok) && threadIdx.x == 0) atomicAdd(&all_selected[1], 1u);
+    if (!__syncthreads_and(ok) && threadIdx.x == 0) atomicAdd(unselected_blocks, 1u);
   }
-  // The block that finishes last reduces the block totals in a fixed order (lane-strided partial sums, then the warp
-  // tree), so the totals do not depend on the schedule.
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  {
-    // thread t: item t % 36, block phase t / 36 (7 phases); fixed order: phase-strided partial sums, then phases 0..6
-    __shared__ double s_part[7][kMaxPop * TOT_COUNT];
-    constexpr int NI = kMaxPop * TOT_COUNT;
-    const int item = threadIdx.x % NI, phase = threadIdx.x / NI;
-    if (phase < 7) {
-      double v = 0.0;
-      for (uint64_t b = phase; b < gridDim.x; b += 7) v += __ldcg(&block_totals[b * NI + item]);
-      s_part[phase][item] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < NI) {
-      double v = 0.0;
-#pragma unroll
-      for (int ph = 0; ph < 7; ++ph) v += s_part[ph][threadIdx.x];
-      totals[threadIdx.x] = v;
-    }
-  }
-  if (threadIdx.x == 0) { all_selected[0] = (__ldcg(&all_selected[1]) == 0) ? 1u : 0u; *ticket = 0; }
 }
 
 // RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) with lociiSpacing == 0: a locus is taken for

@@ -18,7 +18,7 @@ constexpr int ITER_COUNT = 4;
 // Adds the Ritland terms (reduced over locus chunks) to the partials.
 __global__ void __launch_bounds__(256)
 k_ritland_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint64_t n_genomes_padded, int n_out,
-                   const double* __restrict__ totals, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
+                   const DenseTotals totals, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
                    double* __restrict__ partials) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
@@ -32,7 +32,7 @@ k_ritland_partials(const double* __restrict__ chunk_out, uint64_t n_chunks, uint
   const int k = superpop[g];
   double* P = partials + g * PART_COUNT;
   const double n_het = P[PART_NMAJHET] + P[PART_NMINHET];
-  P[PART_RSUM] = (totals[k * TOT_COUNT + TOT_W0] + sdiff) - n_het;
+  P[PART_RSUM] = (totals.get(k, TOT_W0) + sdiff) - n_het;
   P[PART_RCOUNT] = P[PART_NMAJHOM] + (P[PART_NMINHOM] - c2x) + n_het;
 }
 
@@ -86,22 +86,23 @@ k_finalize_closed_form(const double* __restrict__ partials, uint64_t n_genomes, 
 }
 
 // Moments of this locus shard from the fused pass: counts (vertical counters), dense totals and sparse corrections.
-__device__ __forceinline__ void moment_partials_one(uint64_t g, const uint32_t* gcounts, const uint32_t* n3s, const double* totals,
-                                                    const double* ecorr, const uint32_t* nz_rare, const uint8_t* superpop, int unphased,
-                                                    double* partials, kgl_b200_locus_results* simple_out) {
-  const int k = superpop[g];
-  const double* T = totals + k * TOT_COUNT;
-  // __ldcg: in the fused tail kernel these were written by other blocks of the same grid
-  const double n3 = __ldcg(&n3s[g]), n1 = (double)__ldcg(&gcounts[g * 2 + 0]) - n3, n2 = (double)__ldcg(&gcounts[g * 2 + 1]) - n3;
-  const double nzr = (double)__ldcg(&nz_rare[g]);
+// n_lo / n_hi: set lo / hi bits of the genome over its selected rows; n3: code-3 cells among them; nzr: non-reference cells in
+// rare-major rows; d_majhom / d_minhom: class frequencies of the genome's dropped loci (code-3 cells + hom-ref cells of
+// rare-major rows).
+__device__ __forceinline__ void moment_partials_from(uint64_t g, double n_lo, double n_hi, double n3, double nzr, double d_majhom,
+                                                     double d_minhom, const DenseTotals& totals, int k, int unphased,
+                                                     double* __restrict__ partials, kgl_b200_locus_results* __restrict__ simple_out) {
+  double T[TOT_COUNT];
+#pragma unroll
+  for (int j = 0; j < TOT_W0; ++j) T[j] = totals.get(k, j);
+  const double n1 = n_lo - n3, n2 = n_hi - n3;
   // hom-ref cells in q > 0.01 rows: all such rows minus the non-reference cells that sit in them
   const double n_majhom = T[TOT_TQ] - ((n1 + n2 + n3) - nzr);
-  double* P = partials + g * PART_COUNT;
+  double P[PART_COUNT];
   P[PART_NMAJHOM] = n_majhom;
   P[PART_NMAJHET] = n1;
   P[PART_NMINHOM] = unphased ? 0.0 : n2;
   P[PART_NMINHET] = unphased ? n2 : 0.0;
-  const double d_majhom = __ldcg(&ecorr[g * 2 + 0]), d_minhom = __ldcg(&ecorr[g * 2 + 1]);
   // dropped cells: code 3 in selected rows (n3) and hom-ref cells of rare-q rows; their class frequencies leave the sums.
   const double n_dropped = (T[TOT_T] - T[TOT_TQ]) - nzr + n3;
   P[PART_EMAJHOM] = T[TOT_EMAJHOM] - d_majhom;
@@ -109,19 +110,29 @@ __device__ __forceinline__ void moment_partials_one(uint64_t g, const uint32_t* 
   // the three normalised class frequencies of a locus sum to 1, so the dropped majHet mass is n_dropped - majHom - minHom
   P[PART_EMAJHET] = T[TOT_EMAJHET] - (n_dropped - d_majhom - d_minhom);
   P[PART_EMINHET] = 0.0;
+#pragma unroll
   for (int j = PART_RSUM; j < PART_COUNT; ++j) P[j] = 0.0;
+  double2* dst = reinterpret_cast<double2*>(partials + g * PART_COUNT);
+#pragma unroll
+  for (int j = 0; j < PART_COUNT / 2; ++j) dst[j] = make_double2(P[2 * j], P[2 * j + 1]);
   if (simple_out) simple_out[g] = closed_form(P, KGL_B200_ALGO_SIMPLE);
 }
 
+// Fallback path (populations whose code-3 cells are not indexed): assembles the partials from the arrays the separate kernels
+// left (k_sum_cta_counts, k_dropped_scan, k_rare_rows).
 __global__ void __launch_bounds__(256)
 k_moment_partials(const uint32_t* __restrict__ gcounts /* [g]{set lo bits, set hi bits} over the selected rows */,
-                  const uint32_t* __restrict__ n3s, const double* __restrict__ totals, const double* __restrict__ ecorr,
-                  const uint32_t* __restrict__ nz_rare, const uint8_t* __restrict__ superpop, uint64_t n_genomes,
-                  int unphased, double* __restrict__ partials,
+                  const uint32_t* __restrict__ n3s, const DenseTotals totals,
+                  const unsigned long long* __restrict__ ecorr_scan_fx, const uint32_t* __restrict__ nz_rare,
+                  const unsigned long long* __restrict__ ecorr_rare_fx, double fx_inv, const uint8_t* __restrict__ superpop,
+                  uint64_t n_genomes, int unphased, double* __restrict__ partials,
                   kgl_b200_locus_results* __restrict__ simple_out /* nullable: also apply processSimple (calc.cpp:333-359) */) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
-  moment_partials_one(g, gcounts, n3s, totals, ecorr, nz_rare, superpop, unphased, partials, simple_out);
+  const double da = (double)(long long)(ecorr_scan_fx[g * 2 + 0] + ecorr_rare_fx[g * 2 + 0]) * fx_inv;
+  const double dm = (double)(long long)(ecorr_scan_fx[g * 2 + 1] + ecorr_rare_fx[g * 2 + 1]) * fx_inv;
+  moment_partials_from(g, (double)gcounts[g * 2], (double)gcounts[g * 2 + 1], (double)n3s[g], (double)nz_rare[g], da, dm, totals,
+                       superpop[g], unphased, partials, simple_out);
 }
 
 // ---- locus-sharded exchange over NVLink peer memory (kgl_b200_enqueue_count_and_inbreed_peer) ------------------------------

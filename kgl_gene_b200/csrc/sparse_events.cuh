@@ -6,9 +6,13 @@
 //     classified, so the locus' class frequencies leave the genome's expected sums (kga_analysis_inbreed_freq.cpp:462-543)
 //   * rows whose major allele is rare for a population (q <= 0.01): a hom-ref genome is dropped there (freq.cpp:532-539)
 // Dropped cells are indexed ONCE per uploaded matrix (k_dropped_count / k_dropped_index + a key sort, part of the upload:
-// the index is the "side list" of the flattener contract in device form, genome-major and row-sorted); every pass then
-// visits only the indexed cells, one warp per genome, without atomics and in a fixed summation order. Populations with
-// too many code-3 cells for an index fall back to k_dropped_scan, which re-reads the matrix.
+// the index is the "side list" of the flattener contract in device form, genome-major and row-sorted; k_dropped_cells adds
+// the cell's own allele frequency, so that a pass reads 8 sequential bytes per cell instead of gathering a 32-byte sector
+// from the frequency table); every pass then visits only the indexed cells, two warps per genome, without atomics and in a
+// fixed summation order (k_tail, tail_kernels.cuh). Populations with too many code-3 cells for an index fall back to
+// k_dropped_scan, which re-reads the matrix.
+// Sums that ARE accumulated with atomics (rare-major rows, the scan fallback) are kept in 64-bit fixed point: integer adds
+// commute, so every result is independent of the schedule (the scale leaves room for n_loci terms below 1).
 #pragma once
 #include "common.cuh"
 
@@ -69,13 +73,28 @@ k_dropped_index(const uint4* __restrict__ packed /* first unit of the range */, 
 }
 
 // ---- per pass ---------------------------------------------------------------------------------------------------------------
-// Accumulators per genome: n3[g] (code-3 cells in rows selected for the genome), nz_rare[g] (non-reference cells in
-// rare-major rows), ecorr[g][2] (sum over the genome's dropped loci of e_majHom, e_minHom).
-struct SparseOut {
-  uint32_t* n3;
-  uint32_t* nz_rare;
-  double* ecorr;
-};
+// Fixed-point scale of the atomically accumulated class-frequency sums: terms lie in [0, 1], at most n_loci of them per genome.
+inline double fx_scale_for(uint64_t n_loci) {
+  int bits = 1;
+  while (bits < 40 && (n_loci >> bits) != 0) ++bits;
+  return (double)(1ull << (62 - bits));
+}
+__device__ __forceinline__ void fx_add(unsigned long long* acc, double v, double fx) {
+  atomicAdd(acc, (unsigned long long)__double2ll_rn(v * fx));
+}
+
+// Side list entry of a code-3 cell: its row and the frequency float of the GENOME'S population at that row.
+__global__ void __launch_bounds__(256)
+k_dropped_cells(const DroppedKey* __restrict__ keys, uint64_t n_keys, const uint8_t* __restrict__ superpop /* nullable: rows only */,
+                const float* __restrict__ af, uint64_t n_loci, uint2* __restrict__ cells) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys) return;
+  const DroppedKey key = keys[i];
+  const uint32_t row = (uint32_t)key, g = (uint32_t)(key >> 32);
+  float a = 0.0f;
+  if (superpop) a = af[(uint64_t)superpop[g] * n_loci + row];
+  cells[i] = make_uint2(row, __float_as_uint(a));
+}
 
 // seg[g] = first key of genome g in the sorted key array (g = 0 .. n_genomes_padded inclusive).
 __global__ void __launch_bounds__(256)
@@ -91,80 +110,12 @@ k_dropped_segments(const DroppedKey* __restrict__ keys, uint64_t n_keys, uint64_
   seg[g] = lo;
 }
 
-// Four genomes per block, two warps per genome over the genome's row-sorted dropped cells; the partial sums are combined
-// in a fixed order, so the result does not depend on scheduling. flags16 == null: raw mode (allele_count) -- every
-// code-3 cell counts, no frequency corrections. Writes n3[g]; adds the class frequencies of the selected dropped loci
-// to ecorr[g].
-constexpr int kDropGenomesPerBlock = 4;          // 64 threads (two warps) per genome: N / 4 blocks fit the machine in one wave
-__device__ __forceinline__ void
-dropped_apply_block(uint32_t block, const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
-                    const uint16_t* __restrict__ flags16, const uint32_t* __restrict__ all_selected,
-                    const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
-  constexpr int GPB = kDropGenomesPerBlock, TPG = 256 / GPB, WPG = TPG / 32;
-  __shared__ double s_sum[GPB][WPG][2];
-  __shared__ uint32_t s_n[GPB][WPG];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, gi = tid / TPG, wi = (tid % TPG) >> 5, tl = tid % TPG;
-  const uint64_t g = (uint64_t)block * GPB + gi;
-  const bool raw = flags16 == nullptr;
-  uint32_t n = 0;
-  double sa = 0.0, sm = 0.0;
-  if (g < n_genomes) {
-    const uint64_t i0 = seg[g], i1 = seg[g + 1];
-    if (raw) {
-      n = (tl == 0) ? (uint32_t)(i1 - i0) : 0u;
-    } else {
-      const int k = superpop[g];
-      const float* afk = af + (uint64_t)k * n_loci;
-      const bool all_sel = all_selected[0] != 0;       // every row selected & valid for every population: skip the flag gather
-      // four cells per thread and trip: the key, flag and frequency gathers of a trip are independent and overlap
-      for (uint64_t i = i0 + tl; i < i1; i += 4 * TPG) {
-        uint32_t row[4], fl[4];
-        float fa[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) row[j] = (i + TPG * j < i1) ? (uint32_t)keys[i + TPG * j] : 0xFFFFFFFFu;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) fl[j] = (row[j] == 0xFFFFFFFFu) ? 0u : (all_sel ? 0xFFu : (uint32_t)flags16[row[j]]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) fa[j] = ((fl[j] >> k) & 1u) ? afk[row[j]] : 0.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if ((fl[j] >> k) & 1u) {
-            double a, h, m;
-            class_freqs(locus_freq(fa[j]).p, a, h, m);
-            ++n; sa += a; sm += m;
-          }
-        }
-      }
-    }
-  }
-  n = __reduce_add_sync(kFull, n);
-  sa = warp_sum(sa); sm = warp_sum(sm);
-  if (lane == 0) { s_n[gi][wi] = n; s_sum[gi][wi][0] = sa; s_sum[gi][wi][1] = sm; }
-  __syncthreads();
-  if (tl == 0 && g < n_genomes) {
-    uint32_t nn = 0;
-    double ta = 0.0, tm = 0.0;
-#pragma unroll
-    for (int w = 0; w < WPG; ++w) { nn += s_n[gi][w]; ta += s_sum[gi][w][0]; tm += s_sum[gi][w][1]; }   // fixed order
-    out.n3[g] = nn;
-    if (nn && !raw) {
-      atomicAdd(&out.ecorr[g * 2 + 0], ta);
-      atomicAdd(&out.ecorr[g * 2 + 1], tm);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-k_dropped_apply(const DroppedKey* __restrict__ keys, const uint64_t* __restrict__ seg, uint64_t n_genomes,
-                const uint16_t* __restrict__ flags16, const uint32_t* __restrict__ all_selected,
-                const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
-  dropped_apply_block(blockIdx.x, keys, seg, n_genomes, flags16, all_selected, superpop, af, n_loci, out);
-}
-
-// Fallback without an index: one thread per 128-bit unit-row.
+// Fallback without an index: one thread per 128-bit unit-row. n3[g] += code-3 cells in rows selected for the genome;
+// ecorr_fx[g][2] += their {majHom, minHom} class frequencies (fixed point). flags16 == null: raw mode, every cell counts.
 __global__ void __launch_bounds__(256)
 k_dropped_scan(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t units, const uint16_t* __restrict__ flags16,
-               const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, SparseOut out) {
+               const uint8_t* __restrict__ superpop, const float* __restrict__ af, uint64_t n_loci, uint32_t* __restrict__ n3,
+               unsigned long long* __restrict__ ecorr_fx, double fx) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells128; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = ld_stream_u4(packed + i);
     uint64_t both = (uint64_t)(v.x & v.z) | ((uint64_t)(v.y & v.w) << 32);
@@ -175,26 +126,29 @@ k_dropped_scan(const uint4* __restrict__ packed, uint64_t n_cells128, uint32_t u
       const int b = __ffsll((long long)both) - 1;
       both &= both - 1;
       const uint32_t g = unit * 64 + (uint32_t)b;
-      if (flags16 == nullptr) { atomicAdd(&out.n3[g], 1u); continue; }
+      if (flags16 == nullptr) { atomicAdd(&n3[g], 1u); continue; }
       const int k = superpop[g];
       if (!((fl >> k) & 1u)) continue;
-      atomicAdd(&out.n3[g], 1u);
+      atomicAdd(&n3[g], 1u);
       double a, h, m;
       class_freqs(locus_freq(af[(uint64_t)k * n_loci + row]).p, a, h, m);
-      atomicAdd(&out.ecorr[(uint64_t)g * 2 + 0], a);
-      atomicAdd(&out.ecorr[(uint64_t)g * 2 + 1], m);
+      fx_add(&ecorr_fx[(uint64_t)g * 2 + 0], a, fx);
+      fx_add(&ecorr_fx[(uint64_t)g * 2 + 1], m, fx);
     }
   }
 }
 
 // Rare-major rows (flags16 high byte != 0; listed by k_locus_prepare). One thread per (listed row, unit): for every genome
-// whose population has q <= 0.01 at this row: hom-ref -> the locus is dropped for it; else nz_rare++.
-__device__ __forceinline__ void
-rare_rows_block(uint32_t block, uint32_t n_blocks, const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare,
-                const uint4* __restrict__ packed, uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16,
-                const uint64_t* __restrict__ popmask, const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
+// whose population has q <= 0.01 at this row: hom-ref -> the locus is dropped for it (its class frequencies leave the
+// expected sums, freq.cpp:532-539); else nz_rare++. Runs behind k_locus_prepare on the preparation stream: its outputs belong
+// to the selection, not to a pass.
+__global__ void __launch_bounds__(256)
+k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare, const uint4* __restrict__ packed,
+            uint32_t units, const uint16_t* __restrict__ flags16, const uint64_t* __restrict__ popmask,
+            const float* __restrict__ af, uint64_t n_loci, int n_pop, uint32_t* __restrict__ nz_rare,
+            unsigned long long* __restrict__ ecorr_fx, double fx) {
   const uint64_t total = (uint64_t)(*n_rare) * units;
-  for (uint64_t t = (uint64_t)block * blockDim.x + threadIdx.x; t < total; t += (uint64_t)n_blocks * blockDim.x) {
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t row = rare_rows[t / units], u = (uint32_t)(t % units);
     const uint32_t rq = (uint32_t)flags16[row] >> 8;
     const uint4 v = packed[(uint64_t)row * units + u];
@@ -211,23 +165,16 @@ rare_rows_block(uint32_t block, uint32_t n_blocks, const uint32_t* __restrict__ 
         const int b = __ffsll((long long)homref) - 1;
         homref &= homref - 1;
         const uint64_t g = (uint64_t)u * 64 + b;
-        atomicAdd(&out.ecorr[g * 2 + 0], a);
-        atomicAdd(&out.ecorr[g * 2 + 1], m);
+        fx_add(&ecorr_fx[g * 2 + 0], a, fx);
+        fx_add(&ecorr_fx[g * 2 + 1], m, fx);
       }
       while (nonref) {
         const int b = __ffsll((long long)nonref) - 1;
         nonref &= nonref - 1;
-        atomicAdd(&out.nz_rare[(uint64_t)u * 64 + b], 1u);
+        atomicAdd(&nz_rare[(uint64_t)u * 64 + b], 1u);
       }
     }
   }
-}
-
-__global__ void __launch_bounds__(256)
-k_rare_rows(const uint32_t* __restrict__ rare_rows, const uint32_t* __restrict__ n_rare, const uint4* __restrict__ packed,
-            uint32_t units, uint32_t n_genomes, const uint16_t* __restrict__ flags16, const uint64_t* __restrict__ popmask,
-            const float* __restrict__ af, uint64_t n_loci, int n_pop, SparseOut out) {
-  rare_rows_block(blockIdx.x, gridDim.x, rare_rows, n_rare, packed, units, n_genomes, flags16, popmask, af, n_loci, n_pop, out);
 }
 
 }  // namespace kgl

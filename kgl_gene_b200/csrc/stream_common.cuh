@@ -37,7 +37,8 @@ struct StreamParams {
   uint32_t n_pop;
   uint32_t multi_slice;       // gridDim.y > 1: per-locus counts are combined with global atomics
   uint32_t* locus_counts;     // [n_loci][4] or null
-  uint32_t* planes;           // [n_vchunks][kScLevels][4*units] or null; vchunk = (cta*chunks_per_cta + chunk)*RL + row lane
+  uint32_t* cta_counts;       // [gridDim.x][2][n_genomes_padded] or null: set lo / hi bits per genome over the CTA's selected rows
+  uint32_t n_genomes_padded;  // units * 64
 };
 
 // ---- mbarrier / TMA bulk-copy helpers ----------------------------------------------------------------------------------
@@ -114,45 +115,62 @@ __device__ __forceinline__ void vc_finish(VCount& v) {
   v.p8 = 0; v.p16 = 0;
 }
 
-// Dynamic shared memory: uint4 stage[n_stages][R][slice_units] ; uint16_t flags[n_stages][R] ; uint64_t full[8], empty[8]
+// Dynamic shared memory: uint4 stage[n_stages][R][slice_units] ; uint16_t flags[n_stages][R] ; uint64_t full[8], empty[8] ;
+// uint32_t cnt[slice_units * 4][32] (per-genome counts of the CTA, filled when the bit-sliced counters are flushed)
 __host__ __device__ inline size_t stream_smem_bytes(uint32_t slice_units, uint32_t rows, uint32_t n_stages) {
-  return (size_t)n_stages * rows * slice_units * 16 + (size_t)n_stages * rows * 2 + 2 * kScMaxStages * 8 + 64;
+  return (size_t)n_stages * rows * slice_units * 16 + (size_t)n_stages * rows * 2 + 2 * kScMaxStages * 8 + 64 + (size_t)slice_units * 512;
 }
+__device__ __forceinline__ uint32_t* stream_smem_counts(uint64_t* s_bar) { return reinterpret_cast<uint32_t*>(s_bar + 2 * kScMaxStages); }
 
-// Expand the bit-sliced counters: gcounts[g] = {set lo bits, set hi bits} summed over the virtual chunks.
-constexpr int kExpandGroup = 16;
-__device__ __forceinline__ void
-expand_planes_block(uint32_t bx, uint32_t by, const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units,
-                    uint64_t n_genomes_padded, uint32_t* __restrict__ gcounts /* [n_genomes_padded][2], zeroed */) {
-  const uint64_t g = (uint64_t)bx * blockDim.x + threadIdx.x;
-  if (g >= n_genomes_padded) return;
-  const uint64_t unit = g >> 6;
-  const int h = (int)((g >> 5) & 1), bit = (int)(g & 31);
-  const uint64_t vc0 = (uint64_t)by * kExpandGroup;
-  const uint64_t vc1 = min(vc0 + (uint64_t)kExpandGroup, n_vchunks);
-  const uint64_t W = units * 4;
-  uint32_t acc[2] = {0, 0};
+// Flush of one thread's bit-sliced counter (32 genomes of one plane-word column, kScLevels = 12 bits each) into the CTA's
+// count array: levels are gathered four at a time into nibbles (genome 4n + k sits in nibble n of pass k), so a genome's
+// count is three nibbles -- ~350 instructions per flush instead of 3 x 384 single-bit moves.
+// The count array is swizzled: counter `bit` of word column `col` lives at col * 32 + ((bit + col) & 31), so the 32 lanes of a
+// warp (consecutive columns, same bit) hit 32 different banks instead of one.
+__device__ __forceinline__ void vc_flush_counts(const VCount& v, uint32_t* __restrict__ s_cnt, uint32_t col) {
+  static_assert(kScLevels == 12, "three nibbles per counter");
+  uint32_t* cnt32 = s_cnt + col * 32;
 #pragma unroll
-  for (int q = 0; q < kExpandGroup; ++q) {
-    const uint64_t vc = vc0 + q;
-    if (vc >= vc1) break;
-    const uint32_t* base = planes + vc * kScLevels * W + unit * 4 + h;
+  for (int k = 0; k < 4; ++k) {
+    uint32_t A = 0, B = 0, Cg = 0;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      uint32_t c = 0;
+    for (int j = 0; j < 4; ++j) {
+      A |= ((v.c[j] >> k) & 0x11111111u) << j;
+      B |= ((v.c[4 + j] >> k) & 0x11111111u) << j;
+      Cg |= ((v.c[8 + j] >> k) & 0x11111111u) << j;
+    }
 #pragma unroll
-      for (int lv = 0; lv < kScLevels; ++lv) c |= ((base[(size_t)lv * W + p * 2] >> bit) & 1u) << lv;
-      acc[p] += c;
+    for (int n = 0; n < 8; ++n) {
+      const uint32_t c = ((A >> (4 * n)) & 15u) | (((B >> (4 * n)) & 15u) << 4) | (((Cg >> (4 * n)) & 15u) << 8);
+      if (c) atomicAdd(&cnt32[(4 * n + k + col) & 31], c);
     }
   }
-#pragma unroll
-  for (int p = 0; p < 2; ++p) if (acc[p]) atomicAdd(&gcounts[g * 2 + p], acc[p]);
 }
 
+// End of a CTA: its count array goes to cta_counts[blockIdx.x][plane][genome]. Word column j of unit u holds plane j >> 1 of
+// the genomes 64 u + 32 (j & 1) .. + 31. Called by `n_threads` threads (index t) after they have synchronised.
+__device__ __forceinline__ void stream_store_counts(const StreamParams& P, const uint32_t* __restrict__ s_cnt, uint32_t unit0,
+                                                    uint32_t n_cols, uint32_t t, uint32_t n_threads) {
+  uint32_t* out = P.cta_counts + (size_t)blockIdx.x * 2 * P.n_genomes_padded;
+  for (uint32_t i = t; i < n_cols * 32; i += n_threads) {
+    const uint32_t col = i >> 5, bit = i & 31;
+    const uint32_t unit = unit0 + (col >> 2), j = col & 3;
+    out[(size_t)(j >> 1) * P.n_genomes_padded + unit * 64 + (j & 1) * 32 + bit] = s_cnt[col * 32 + ((bit + col) & 31)];
+  }
+}
+
+// gcounts[g] = {set lo bits, set hi bits} summed over the CTAs (the tail kernel does this itself; used by the fallback path of
+// populations whose code-3 cells are too many to index, and by tools/kbench).
 __global__ void __launch_bounds__(256)
-k_expand_planes(const uint32_t* __restrict__ planes, uint64_t n_vchunks, uint64_t units, uint64_t n_genomes_padded,
-                uint32_t* __restrict__ gcounts) {
-  expand_planes_block(blockIdx.x, blockIdx.y, planes, n_vchunks, units, n_genomes_padded, gcounts);
+k_sum_cta_counts(const uint32_t* __restrict__ cta_counts, uint32_t n_ctas, uint64_t n_genomes_padded, uint32_t* __restrict__ gcounts) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes_padded) return;
+  uint32_t a = 0, b = 0;
+  for (uint32_t c = 0; c < n_ctas; ++c) {
+    a += cta_counts[((size_t)c * 2 + 0) * n_genomes_padded + g];
+    b += cta_counts[((size_t)c * 2 + 1) * n_genomes_padded + g];
+  }
+  gcounts[g * 2 + 0] = a; gcounts[g * 2 + 1] = b;
 }
 
 // multi-slice only: n0 = N - n1 - n2 - n3
@@ -171,7 +189,7 @@ struct StreamPlan {
   uint32_t units_padded;      // device row pitch in units (>= units; a multiple of slice_units for the compile-time shapes)
   uint32_t slice_units, slices, rows_per_stage, h_parts, h_units, v_row_lanes, n_stages, threads;
   uint32_t total_stages, stages_per_cta, n_ctas, flush_stages, chunks_per_cta;
-  uint64_t n_vchunks, padded_rows;
+  uint64_t padded_rows;
   size_t smem;
 };
 
@@ -208,7 +226,7 @@ inline StreamPlan plan_stream(uint64_t units_padded, uint64_t n_loci, int sm_cou
   p.v_row_lanes = rl;
   p.threads = p.shape == 0 ? (uint32_t)kScThreads : (8 + p.slice_units * R / 256 + 1) * 32;
   const size_t stage_bytes = (size_t)R * p.slice_units * 16 + R * 2;
-  int S = stages_hint > 0 ? stages_hint : (int)((200 * 1024) / stage_bytes);
+  int S = stages_hint > 0 ? stages_hint : (int)((200 * 1024 - (size_t)p.slice_units * 512) / stage_bytes);
   if (S > kScMaxStages) S = kScMaxStages;
   if (S < 2) S = 2;
   p.n_stages = (uint32_t)S;
@@ -222,7 +240,6 @@ inline StreamPlan plan_stream(uint64_t units_padded, uint64_t n_loci, int sm_cou
   if (p.n_ctas == 0) p.n_ctas = 1;
   p.flush_stages = (uint32_t)kScMaxCalls / ((R / rl) / 8);
   p.chunks_per_cta = (p.stages_per_cta + p.flush_stages - 1) / p.flush_stages;
-  p.n_vchunks = (uint64_t)p.n_ctas * p.chunks_per_cta * rl;
   p.padded_rows = (uint64_t)p.total_stages * R;
   p.smem = stream_smem_bytes(p.slice_units, R, p.n_stages);
   return p;

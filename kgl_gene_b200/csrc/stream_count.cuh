@@ -108,6 +108,7 @@ k_stream_count_ct(const StreamParams P) {
   uint16_t* s_flags = reinterpret_cast<uint16_t*>(s_stage + (size_t)S * R * SU);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_flags + (size_t)S * R) + 15) & ~(uintptr_t)15);
   const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + kScMaxStages);
+  uint32_t* s_cnt = stream_smem_counts(s_bar);                          // [W][32] per-genome counts of this CTA
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool raw = P.flags16 == nullptr;
@@ -122,6 +123,8 @@ k_stream_count_ct(const StreamParams P) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (WANT_GENOME)
+    for (uint32_t i = tid; i < (uint32_t)W * 32; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
 
   if (warp == N_CONSUMER_WARPS) {
@@ -215,15 +218,13 @@ k_stream_count_ct(const StreamParams P) {
   const uint32_t all_pops = (1u << P.n_pop) - 1u;
   VCount C;
   vc_clear(C);
-  uint32_t chunk = 0, stages_in_chunk = 0;
+  uint32_t stages_in_chunk = 0;
 
+  // the counters hold up to 4,095 rows: every flush_stages stages (and at the end) they are added to the CTA's count array
   auto flush = [&]() {
-    const uint64_t vchunk = ((uint64_t)blockIdx.x * P.chunks_per_cta + chunk) * RL + v_rl;
-    uint32_t* out = P.planes + vchunk * kScLevels * (4ull * P.units) + (unit0 * 4 + v_wcol);
-#pragma unroll
-    for (int lv = 0; lv < kScLevels; ++lv) out[(size_t)lv * 4 * P.units] = C.c[lv];
+    vc_flush_counts(C, s_cnt, v_wcol);
     vc_clear(C);
-    stages_in_chunk = 0; ++chunk;
+    stages_in_chunk = 0;
   };
 
   for (uint32_t it = 0; it < n_iters; ++it) {
@@ -266,9 +267,10 @@ k_stream_count_ct(const StreamParams P) {
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     if (++s == S) { s = 0; ph ^= 1; }
   }
-  // every virtual chunk is written, also the ones that saw no rows
   if (WANT_GENOME) {
-    while (chunk < P.chunks_per_cta) flush();
+    flush();
+    asm volatile("bar.sync 1, %0;" ::"n"(V_WARPS * 32) : "memory");    // the V warps only: H warps and the producer have left
+    stream_store_counts(P, s_cnt, unit0, W, vt, V_WARPS * 32);
   }
 }
 

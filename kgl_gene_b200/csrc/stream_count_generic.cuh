@@ -15,7 +15,7 @@ __device__ __forceinline__ uint32_t popc3(uint32_t a, uint32_t b, uint32_t c) {
   return __popc(l) + 2u * __popc(h);
 }
 
-// WANT_LOCUS requires P.locus_counts, WANT_GENOME requires P.planes.
+// WANT_LOCUS requires P.locus_counts, WANT_GENOME requires P.cta_counts.
 template <bool WANT_LOCUS, bool WANT_GENOME>
 __global__ void __launch_bounds__(kScThreads, 1)
 k_stream_count_rt(const StreamParams P) {
@@ -27,6 +27,7 @@ k_stream_count_rt(const StreamParams P) {
   uint16_t* s_flags = reinterpret_cast<uint16_t*>(s_stage + (size_t)S * R * SU);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_flags + (size_t)S * R) + 15) & ~(uintptr_t)15);
   const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + kScMaxStages);
+  uint32_t* s_cnt = stream_smem_counts(s_bar);                          // [SU * 4][32] per-genome counts of this CTA
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool raw = P.flags16 == nullptr;
@@ -41,6 +42,8 @@ k_stream_count_rt(const StreamParams P) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (WANT_GENOME)
+    for (uint32_t i = tid; i < SU * 4 * 32; i += blockDim.x) s_cnt[i] = 0;
   __syncthreads();
 
   if (warp == kScConsumerWarps) {
@@ -95,19 +98,15 @@ k_stream_count_rt(const StreamParams P) {
 
   VCount C;
   vc_clear(C);
-  uint32_t calls = 0, chunk = 0, stages_in_chunk = 0;
+  uint32_t calls = 0, stages_in_chunk = 0;
   uint32_t s = 0, ph = 0;
 
+  // the counters hold up to 4,095 rows: every flush_stages stages (and at the end) they are added to the CTA's count array
   auto flush = [&]() {
     vc_finish(C);
-    if (v_active) {
-      const uint64_t vchunk = ((uint64_t)blockIdx.x * P.chunks_per_cta + chunk) * P.v_row_lanes + v_rl;
-      uint32_t* out = P.planes + vchunk * kScLevels * (4ull * P.units) + (unit0 * 4 + v_wcol);
-#pragma unroll
-      for (int lv = 0; lv < kScLevels; ++lv) out[(size_t)lv * 4 * P.units] = C.c[lv];
-    }
+    if (v_active) vc_flush_counts(C, s_cnt, v_wcol);
     vc_clear(C);
-    calls = 0; stages_in_chunk = 0; ++chunk;
+    calls = 0; stages_in_chunk = 0;
   };
 
   for (uint32_t it = 0; it < n_iters; ++it) {
@@ -215,9 +214,10 @@ k_stream_count_rt(const StreamParams P) {
     if (++s == S) { s = 0; ph ^= 1; }
   }
 
-  // every virtual chunk is written, also the ones that saw no rows
   if (WANT_GENOME) {
-    while (chunk < P.chunks_per_cta) flush();
+    flush();
+    asm volatile("bar.sync 1, %0;" ::"n"(kScConsumerThreads) : "memory");    // the consumer warps only: the producer has left
+    stream_store_counts(P, s_cnt, unit0, W, tid, kScConsumerThreads);
   }
 }
 

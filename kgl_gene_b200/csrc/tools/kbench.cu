@@ -288,7 +288,7 @@ int main(int argc, char** argv) {
     P.flags16 = flags_mode < 0 ? nullptr : d_flags[flags_mode];
     P.sum64 = flags_mode < 0 ? nullptr : d_sum64[flags_mode];
     P.need32 = d_need; P.popmask32 = d_popmask; P.n_pop = 6; P.locus_counts = wl ? d_lc : nullptr;
-    P.planes = wg ? planes : nullptr;
+    P.cta_counts = wg ? planes : nullptr; P.n_genomes_padded = (uint32_t)(units * 64);
     return P;
   };
 
@@ -306,7 +306,7 @@ int main(int argc, char** argv) {
     if (only_cfg >= 0 && cfg_index != only_cfg) continue;
     StreamPlan pl = plan_stream(units, n_loci, sms, c.rows, c.stages, !c.generic);
     if (pl.smem > 227 * 1024 || pl.rows_per_stage * pl.h_parts != (uint32_t)kScHThreads) { std::printf("%-28s skipped (smem %zu)\n", c.name, pl.smem); continue; }
-    CK(cudaMalloc(&d_planes, pl.n_vchunks * units * 4 * kScLevels * 4));
+    CK(cudaMalloc(&d_planes, (size_t)pl.n_ctas * 2 * units * 64 * 4));
     StreamParams P = make_params(pl, n_loci, c.flags_mode, c.wl, c.wg, d_planes);
     auto go = [&]() { CK(launch_stream(P, pl, c.wl, c.wg, 0)); };
     for (int w = 0; w < 3; ++w) go();
@@ -329,15 +329,14 @@ int main(int argc, char** argv) {
       for (int rows : {0, 1, 64, 128, 256}) {
         StreamPlan pl = plan_stream(units, vl, sms, rows == 1 ? 0 : rows, 3, rows != 1);
         if (pl.smem > 227 * 1024) continue;
-        CK(cudaMalloc(&d_planes, pl.n_vchunks * units * 4 * kScLevels * 4));
-        CK(cudaMemset(d_planes, 0xAB, pl.n_vchunks * units * 4 * kScLevels * 4));
+        CK(cudaMalloc(&d_planes, (size_t)pl.n_ctas * 2 * units * 64 * 4));
+        CK(cudaMemset(d_planes, 0xAB, (size_t)pl.n_ctas * 2 * units * 64 * 4));
         StreamParams P = make_params(pl, vl, mode, true, true, d_planes);
         CK(cudaMemset(d_lc, 0, vl * 16)); CK(cudaMemset(d_lc_ref, 0, vl * 16));
         CK(cudaMemset(d_gc, 0, units * 64 * 8)); CK(cudaMemset(d_gc_ref, 0, units * 64 * 8));
         CK(launch_stream(P, pl, true, true, 0));
         if (pl.slices > 1) k_fix_locus_n0<<<(unsigned)((vl + 255) / 256), 256>>>(d_lc, vl, n_genomes);
-        dim3 eg((unsigned)((units * 64 + 255) / 256), (unsigned)((pl.n_vchunks + kExpandGroup - 1) / kExpandGroup));
-        k_expand_planes<<<eg, 256>>>(d_planes, pl.n_vchunks, units, units * 64, d_gc);
+        k_sum_cta_counts<<<(unsigned)((units * 64 + 255) / 256), 256>>>(d_planes, pl.n_ctas, units * 64, d_gc);
         k_ref_locus<<<(unsigned)((vl * units + 255) / 256), 256>>>(d_packed, vl, units, d_lc_ref);
         k_fix_locus_n0<<<(unsigned)((vl + 255) / 256), 256>>>(d_lc_ref, vl, n_genomes);
         dim3 rg((n_genomes + 127) / 128, 64);
