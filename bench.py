@@ -251,7 +251,7 @@ def run_ours(args):
     ctx = KglB200(local_rank)
     # a real (non-default) stream: the C ABI treats a NULL handle as "use the context's own stream", and CUDA events must
     # be recorded on the stream the kernels run on
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)      # the streaming kernel's stream outranks the context's side streams
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
@@ -321,6 +321,7 @@ def run_ours(args):
         e0.record(stream)
         for _ in range(steps):
             fn()
+        ctx.flush()              # the tail of the last pass runs on a side stream: the closing event is ordered after it
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -420,7 +421,7 @@ def run_ours(args):
             "config": {"workload": workload_name(n, l, world), "n_genomes": n, "n_loci_per_gpu": l, "af_vectors": int(af.shape[0]),
                        "selection": "one window, all loci", "missing_rate": 0.001,
                        "l2": f"inputs ({l * rb / 1e6:.0f} MB matrix per GPU) are larger than the 126 MB L2; no flush needed",
-                       "step": "k_locus_prepare (flags + dense totals) + k_stream_count_ct + k_post (counter expansion | code-3 cells | rare-major rows) + k_moment_partials"
+                       "step": "k_locus_prepare (flags, dense totals, rare-major rows; side stream, next to the previous pass's streaming kernel) + k_stream_count_ct (per-locus counts, per-genome counts) + k_tail (code-3 cells, moments, Simple closed form; side stream, next to the next pass's streaming kernel)"
                                + ("" if world == 1 else (" + k_peer_exchange (signal, wait, gather the partial sums of all ranks over NVLink peer memory, fixed-order sum, closed form; no NCCL call in the step)"
                                                          if use_peer else " + NCCL all-reduce + k_finalize_closed_form")),
                        "exchange": None if world == 1 else exchange_note},

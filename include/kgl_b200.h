@@ -168,8 +168,13 @@ int kgl_b200_run_gram(kgl_b200_ctx* ctx, int32_t* gram);
 int kgl_b200_run_grm(kgl_b200_ctx* ctx, uint32_t pop, double* grm);
 
 /* ---- resident / asynchronous building blocks (bench.py, multi-GPU drivers) ------------------------------------------ */
-/* Enqueue the fused pass on the context stream and return immediately; results stay in device buffers. */
+/* Enqueue the fused pass and return immediately; results stay in device buffers. The pass is spread over three streams -- the
+ * streaming kernel on the context stream, the preparation of a pass and the tail of the pass before it on two internal
+ * streams, where they run next to the streaming kernel -- so consecutive calls overlap. Every other entry point orders the
+ * context stream after the pending tail before it does anything; kgl_b200_flush does only that (no host synchronisation), e.g.
+ * before an event is recorded on the context stream to time a sequence of passes. */
 int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* ctx);
+int kgl_b200_flush(kgl_b200_ctx* ctx);
 /* Number of kernels this context has launched so far. */
 uint64_t kgl_b200_launch_count(const kgl_b200_ctx* ctx);
 /* Milliseconds the dominant streaming kernel (k_count_moments) took in the most recent enqueue/run, measured with

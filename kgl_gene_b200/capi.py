@@ -30,7 +30,7 @@ EXPORTS = [
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
     "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
-    "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
+    "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_flush", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
     "kgl_b200_inbreed_fetch", "kgl_b200_kernel_timer_reset", "kgl_b200_kernel_timer_read", "kgl_b200_fetch_locus_counts",
     "kgl_b200_peer_export", "kgl_b200_peer_attach", "kgl_b200_peer_set_timeout_ms", "kgl_b200_enqueue_count_and_inbreed_peer",
@@ -203,6 +203,10 @@ class KglB200:
 
     def enqueue_count_and_inbreed(self):
         self._check(self.lib.kgl_b200_enqueue_count_and_inbreed(self.h), "enqueue_count_and_inbreed")
+
+    def flush(self):
+        """Orders the context stream after everything enqueued so far (the tail of the last pass runs on a side stream)."""
+        self._check(self.lib.kgl_b200_flush(self.h), "flush")
 
     def loglik_grid(self, grid) -> np.ndarray:
         grid = np.ascontiguousarray(grid, dtype=np.float64)

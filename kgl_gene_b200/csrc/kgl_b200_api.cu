@@ -116,11 +116,18 @@ struct kgl_b200_ctx {
     void release() { flags16.release(); sum64.release(); selw.release(); acc.release(); }
   } prep[2];
   int par = 0;                                  // the set the current selection was prepared into
-  cudaStream_t prep_stream = nullptr, copy_stream = nullptr;
+  // Three streams per pass: the streaming kernel on the context stream; the preparation of the NEXT pass and the
+  // tail of the PREVIOUS pass on two side streams, where they run next to the streaming kernel's CTAs (72 registers x 608
+  // threads leave room for one 256-thread block of either on every SM).
+  cudaStream_t prep_stream = nullptr, tail_stream = nullptr, copy_stream = nullptr;
   std::vector<cudaEvent_t> chunk_ev;      // chunked upload: one event per row chunk
-  cudaEvent_t prep_done = nullptr, readers_done[2] = {nullptr, nullptr}, stream_pass_done = nullptr;
-  bool stream_pass_marked = false;
+  cudaEvent_t prep_done = nullptr, inputs_ready = nullptr;
+  cudaEvent_t readers_main[2] = {nullptr, nullptr}, readers_tail[2] = {nullptr, nullptr};   // readers of prep[par] so far
   bool readers_marked[2] = {false, false};
+  cudaEvent_t stream_done[2] = {nullptr, nullptr}, tail_done[2] = {nullptr, nullptr};       // per cta_counts buffer
+  bool tail_marked[2] = {false, false};
+  int cbuf = 0;                                 // the cta_counts buffer of the most recent pass
+  bool tail_pending = false;                    // a tail runs on tail_stream that the context stream has not been ordered after
   bool inputs_async = false;                    // d_sel was last written by a kernel on the main stream without a host sync
   bool prep_valid = false, prep_has_w0 = false, prep_has_selw = false;
 
@@ -131,7 +138,7 @@ struct kgl_b200_ctx {
   bool sm_valid = false, codes_valid = false;
 
   // fused pass outputs
-  DevBuf<uint32_t> d_locus_counts, d_cta_counts;
+  DevBuf<uint32_t> d_locus_counts, d_cta_counts[2];
   DevBuf<uint8_t> d_scratch;            // per-genome accumulators of one pass, zeroed with a single memset
   uint32_t *d_gcounts = nullptr, *d_n3 = nullptr;
   unsigned long long* d_ecorr_scan = nullptr;   // fallback path (code-3 cells not indexed): k_dropped_scan's fixed-point sums
@@ -185,7 +192,6 @@ struct kgl_b200_ctx {
   uint64_t gram_ld = 0, gram_tiles_ld = 0, gram_n_tiles = 0, gram_first = 0, gram_stride = 1;
   bool codes16_valid = false;
   cudaEvent_t gram_e0 = nullptr, gram_e1 = nullptr;
-  bool tail_done = false;            // the last launch_count already assembled the per-genome partial sums (k_tail)
 
   // iterative estimator state
   int algo = -1, phase = 0, iteration = 0;
@@ -229,8 +235,46 @@ void peer_unregister(const kgl_b200_ctx* c) {
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
-int use_device(kgl_b200_ctx* c) {
+// Orders the context stream after the tail of the last pass (no host synchronisation).
+int join_tail(kgl_b200_ctx* c) {
+  if (c->tail_pending) {
+    KGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->tail_done[c->cbuf], 0));
+    c->tail_pending = false;
+  }
+  return KGL_B200_OK;
+}
+
+// Every entry point starts here. Only the resident pass (kgl_b200_enqueue_count_and_inbreed[_peer]) leaves its tail running on
+// the side stream; whatever is called next is ordered after it first -- unless it is another such pass (join = false).
+int use_device(kgl_b200_ctx* c, bool join = true) {
   KGL_CUDA(c, cudaSetDevice(c->device));
+  return join ? join_tail(c) : KGL_B200_OK;
+}
+
+int ensure_side_streams(kgl_b200_ctx* c) {
+  if (c->prep_stream) return KGL_B200_OK;
+  int least = 0, greatest = 0;
+  KGL_CUDA(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  // The side kernels run NEXT to the streaming kernel, whose 180 KB of dynamic shared memory force the largest shared-memory
+  // carve-out on the SM: they ask for the same carve-out, so that an SM never has to be drained to switch configurations.
+  const int max_shared = cudaSharedmemCarveoutMaxShared;
+  KGL_CUDA(c, cudaFuncSetAttribute(k_locus_prepare<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_locus_prepare<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_locus_prepare<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_locus_prepare<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_peer_publish, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_peer_exchange, cudaFuncAttributePreferredSharedMemoryCarveout, max_shared));
+  KGL_CUDA(c, cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, least));
+  KGL_CUDA(c, cudaStreamCreateWithPriority(&c->tail_stream, cudaStreamNonBlocking, least));
+  KGL_CUDA(c, cudaEventCreateWithFlags(&c->prep_done, cudaEventDisableTiming));
+  KGL_CUDA(c, cudaEventCreateWithFlags(&c->inputs_ready, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    KGL_CUDA(c, cudaEventCreateWithFlags(&c->readers_main[i], cudaEventDisableTiming));
+    KGL_CUDA(c, cudaEventCreateWithFlags(&c->readers_tail[i], cudaEventDisableTiming));
+    KGL_CUDA(c, cudaEventCreateWithFlags(&c->stream_done[i], cudaEventDisableTiming));
+    KGL_CUDA(c, cudaEventCreateWithFlags(&c->tail_done[i], cudaEventDisableTiming));
+  }
   return KGL_B200_OK;
 }
 
@@ -281,17 +325,14 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false, bool want_selw = fals
   const uint64_t L = c->L;
   c->n_words = term_words(L);
   const uint64_t span = std::max<uint64_t>(c->padded_rows, c->n_words * 32);
-  const unsigned nb = (unsigned)std::max<uint64_t>(1, (span + kPrepLociPerBlock - 1) / kPrepLociPerBlock);
-  if (!c->prep_stream) {
-    KGL_CUDA(c, cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking));
-    KGL_CUDA(c, cudaEventCreateWithFlags(&c->prep_done, cudaEventDisableTiming));
-    for (cudaEvent_t& e : c->readers_done) KGL_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    KGL_CUDA(c, cudaEventCreateWithFlags(&c->stream_pass_done, cudaEventDisableTiming));
-  }
-  // Everything enqueued on the main stream so far may read the current set: mark it, switch to the other set, and let the
-  // preparation start as soon as the readers of THAT set (marked one switch ago) are done -- i.e. concurrently with the
-  // tail kernel of the pass that is still running on the main stream.
-  KGL_CUDA(c, cudaEventRecord(c->readers_done[c->par], c->stream));
+  const uint64_t n_tiles = std::max<uint64_t>(1, (span + kPrepLociPerBlock - 1) / kPrepLociPerBlock);
+  const unsigned nb = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)c->sm_count * 2);
+  rc = ensure_side_streams(c); if (rc) return rc;
+  // Everything enqueued so far may read the current set (the streaming kernels on the context stream, the tails on the tail
+  // stream): mark both, switch to the other set, and let the preparation start as soon as the readers of THAT set (marked one
+  // switch ago) are done. It does not wait for the streaming kernel of the pass before it: it runs next to it.
+  KGL_CUDA(c, cudaEventRecord(c->readers_main[c->par], c->stream));
+  KGL_CUDA(c, cudaEventRecord(c->readers_tail[c->par], c->tail_stream));
   c->readers_marked[c->par] = true;
   c->par ^= 1;
   kgl_b200_ctx::PrepSet& S = c->prep[c->par];
@@ -301,21 +342,22 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false, bool want_selw = fals
   const size_t acc_bytes = kgl_b200_ctx::PrepSet::acc_bytes(c->Npad);
   KGL_CUDA(c, S.acc.ensure(acc_bytes));
   cudaStream_t ps = c->prep_stream;
-  if (c->readers_marked[c->par]) KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_done[c->par], 0));
-  // not before the last streaming kernel has finished: it owns every SM, a preparation block that slips in ahead of one of
-  // its persistent CTAs delays the whole pass
-  if (c->stream_pass_marked) KGL_CUDA(c, cudaStreamWaitEvent(ps, c->stream_pass_done, 0));
-  if (c->inputs_async) {            // the selection mask was just written by a kernel on the main stream
-    KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_done[c->par ^ 1], 0));
+  if (c->readers_marked[c->par]) {
+    KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_main[c->par], 0));
+    KGL_CUDA(c, cudaStreamWaitEvent(ps, c->readers_tail[c->par], 0));
+  }
+  if (c->inputs_async) {            // the selection mask / frequency table was just written on the context stream without a host sync
+    KGL_CUDA(c, cudaEventRecord(c->inputs_ready, c->stream));
+    KGL_CUDA(c, cudaStreamWaitEvent(ps, c->inputs_ready, 0));
     c->inputs_async = false;
   }
   KGL_CUDA(c, cudaMemsetAsync(S.acc.p, 0, acc_bytes, ps));
   const uint4* packed = reinterpret_cast<const uint4*>(c->d_packed.p);
   const double fx = fx_scale_for(L);
 #define KGL_PREP(W0, SELW)                                                                                                          \
-  k_locus_prepare<W0, SELW><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, (int)c->n_pop, S.flags16.p,     \
-      S.sum64.p, SELW ? S.selw.p : nullptr, c->n_words, packed, (uint32_t)c->units, c->d_popmask.p, S.nz_rare(c->Npad),            \
-      S.ecorr_fx(), fx, S.totals_fx(), S.unselected_blocks())
+  k_locus_prepare<W0, SELW><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, n_tiles, (int)c->n_pop,         \
+      S.flags16.p, S.sum64.p, SELW ? S.selw.p : nullptr, c->n_words, packed, (uint32_t)c->units, c->d_popmask.p,                   \
+      S.nz_rare(c->Npad), S.ecorr_fx(), fx, S.totals_fx(), S.unselected_blocks())
   if (want_w0 && want_selw) KGL_PREP(true, true);
   else if (want_w0) KGL_PREP(true, false);
   else if (want_selw) KGL_PREP(false, true);
@@ -425,6 +467,13 @@ int ensure_dropped_cells(kgl_b200_ctx* c, bool want_af) {
   return KGL_B200_OK;
 }
 
+// End of what a pass put on the tail stream: the event later passes (reuse of the cta_counts buffer) and joins wait for.
+int mark_tail(kgl_b200_ctx* c, bool join) {
+  KGL_CUDA(c, cudaEventRecord(c->tail_done[c->cbuf], c->tail_stream));
+  c->tail_marked[c->cbuf] = true;
+  return join ? join_tail(c) : KGL_B200_OK;
+}
+
 DenseTotals dense_totals(const kgl_b200_ctx* c, const kgl_b200_ctx::PrepSet& S) {
   const double fx = fx_scale_for(c->L);
   return DenseTotals{S.totals_fx(), 1.0 / fx, 128.0 / fx};
@@ -440,8 +489,10 @@ struct MaskOverride {
 
 // want_moments: the tail assembles the moment partials of every genome (d_partials; + the Simple closed form into d_results
 // when simple_results); otherwise it leaves the raw per-genome counts d_gcounts {set lo bits, set hi bits} and d_n3.
+// defer_join: the tail stays on the tail stream and the context stream is NOT ordered after it (the resident pass: the next
+// pass's streaming kernel may start while this tail runs); the next entry point joins (use_device).
 int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_genome, bool simple_results = false, bool want_moments = false,
-                 const MaskOverride* mo = nullptr) {
+                 const MaskOverride* mo = nullptr, bool defer_join = false) {
   int rc = mo ? KGL_B200_OK : build_unit_tables(c);
   if (rc) return rc;
   rc = build_dropped_index(c);
@@ -453,8 +504,13 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     if (pl.slices > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_locus_counts.p, 0, (size_t)c->L * 16, c->stream));
   }
   const bool indexed = c->dropped_indexed || c->n_dropped == 0;
+  rc = ensure_side_streams(c); if (rc) return rc;
   if (want_genome) {
-    KGL_CUDA(c, c->d_cta_counts.ensure((size_t)pl.n_ctas * 2 * c->Npad));
+    // the tail of the pass before the last one may still read the buffer this pass writes
+    if (c->tail_pending && !defer_join) { rc = join_tail(c); if (rc) return rc; }
+    c->cbuf ^= 1;
+    if (c->tail_marked[c->cbuf]) KGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->tail_done[c->cbuf], 0));
+    KGL_CUDA(c, c->d_cta_counts[c->cbuf].ensure((size_t)pl.n_ctas * 2 * c->Npad));
     // scratch: gcounts u32[Npad][2] | n3 u32[Npad] | pad u32[Npad] | ecorr_scan u64[Npad][2] (fallback path only)
     KGL_CUDA(c, c->d_scratch.ensure((size_t)c->Npad * 32));
     c->d_gcounts = reinterpret_cast<uint32_t*>(c->d_scratch.p);
@@ -473,7 +529,7 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   P.need32 = mo ? mo->need32 : c->d_need32.p;
   P.n_pop = (raw || mo) ? 1 : c->n_pop;
   P.locus_counts = want_locus_counts ? c->d_locus_counts.p : nullptr;
-  P.cta_counts = want_genome ? c->d_cta_counts.p : nullptr;
+  P.cta_counts = want_genome ? c->d_cta_counts[c->cbuf].p : nullptr;
   P.n_genomes_padded = (uint32_t)c->Npad;
   cudaEvent_t e0 = c->ev0, e1 = c->ev1;
   if (c->timer_used < kgl_b200_ctx::kTimerSlots) {
@@ -490,22 +546,23 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   KGL_CUDA(c, launch_stream(P, pl, want_locus_counts, want_genome, c->stream));
   ++c->launches;
   KGL_CUDA(c, cudaEventRecord(e1, c->stream));
-  if (c->stream_pass_done) { KGL_CUDA(c, cudaEventRecord(c->stream_pass_done, c->stream)); c->stream_pass_marked = true; }
   c->ev_valid = true;
   c->last_e0 = e0; c->last_e1 = e1;
   if (want_locus_counts && pl.slices > 1) {
     k_fix_locus_n0<<<blocks_for(c->L, 256), 256, 0, c->stream>>>(c->d_locus_counts.p, c->L, (uint32_t)c->N);
     KGL_LAUNCH_CHECK(c);
   }
-  c->tail_done = false;
   if (!want_genome) return KGL_B200_OK;
   const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->prep[c->par].flags16.p);
   const kgl_b200_ctx::PrepSet& S = c->prep[c->par];
   const bool prepared = !raw && !mo;
   const double fx = fx_scale_for(c->L);
   if (indexed) {
+    // the tail runs on its own stream, behind this pass's streaming kernel
+    KGL_CUDA(c, cudaEventRecord(c->stream_done[c->cbuf], c->stream));
+    KGL_CUDA(c, cudaStreamWaitEvent(c->tail_stream, c->stream_done[c->cbuf], 0));
     TailParams T{};
-    T.cta_counts = c->d_cta_counts.p; T.n_ctas = pl.n_ctas; T.n_genomes_padded = c->Npad;
+    T.cta_counts = c->d_cta_counts[c->cbuf].p; T.n_ctas = pl.n_ctas; T.n_genomes_padded = c->Npad;
     T.cells = c->n_dropped ? c->d_dropped_cells.p : nullptr; T.seg = c->d_dropped_seg.p;
     T.row_lo = 0; T.row_hi = 0xFFFFFFFFu;
     if (prepared && c->sel_row_hi != ~0ull && (c->sel_row_lo > 0 || c->sel_row_hi < c->L)) {   // a proper window
@@ -519,13 +576,14 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
     T.totals = dense_totals(c, S); T.partials = c->partials_target ? c->partials_target : c->d_partials.p;
     T.results = simple_results ? c->d_results.p : nullptr;
     T.gcounts = c->d_gcounts; T.n3 = c->d_n3;
-    k_tail<<<blocks_for(c->N, kTailGenomesPerBlock), 256, 0, c->stream>>>(T);
+    k_tail<<<blocks_for(c->N, kTailGenomesPerBlock), 256, 0, c->tail_stream>>>(T);
     KGL_LAUNCH_CHECK(c);
-    c->tail_done = want_moments;
-    return KGL_B200_OK;
+    c->tail_pending = true;
+    if (!defer_join) return mark_tail(c, true);
+    return KGL_B200_OK;              // the caller adds what else belongs on the tail stream and calls mark_tail(c, false)
   }
   // populations whose code-3 cells are too many to index: separate kernels, the matrix is scanned for the cells
-  k_sum_cta_counts<<<blocks_for(c->Npad, 256), 256, 0, c->stream>>>(c->d_cta_counts.p, pl.n_ctas, c->Npad, c->d_gcounts);
+  k_sum_cta_counts<<<blocks_for(c->Npad, 256), 256, 0, c->stream>>>(c->d_cta_counts[c->cbuf].p, pl.n_ctas, c->Npad, c->d_gcounts);
   KGL_LAUNCH_CHECK(c);
   const uint64_t n128 = c->L * c->units;
   const unsigned grid = (unsigned)std::min<uint64_t>((n128 + 255) / 256, (uint64_t)c->sm_count * 16);
@@ -538,17 +596,17 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
                                                                     c->partials_target ? c->partials_target : c->d_partials.p,
                                                                     simple_results ? c->d_results.p : nullptr);
     KGL_LAUNCH_CHECK(c);
-    c->tail_done = true;
   }
   return KGL_B200_OK;
 }
 
 // Moments of all genomes over the selected loci into d_partials (phase 0 of every estimator).
-int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false, bool want_selw = false) {
+int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results = false, bool want_w0 = false, bool want_selw = false,
+                    bool defer_join = false) {
   int rc = ensure_prepared(c, want_w0, want_selw);
   if (rc) return rc;
   KGL_CUDA(c, c->d_partials.ensure((size_t)c->Npad * PART_COUNT));
-  return launch_count(c, false, want_locus_counts, true, simple_results, true);
+  return launch_count(c, false, want_locus_counts, true, simple_results, true, nullptr, defer_join);
 }
 
 struct TermLaunch { dim3 grid; uint32_t words_per_chunk; uint64_t n_chunks; };
@@ -874,7 +932,11 @@ int kgl_b200_create(int device, kgl_b200_ctx** out) {
   auto* c = new kgl_b200_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+  // the context stream carries the streaming kernel: highest priority, so that its CTAs are placed before the blocks of the
+  // side streams (preparation, tail) when both are ready
+  int pr_least = 0, pr_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest);
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, pr_greatest) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     std::string m = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
     delete c;
@@ -889,9 +951,11 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+  if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);
   c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_need32.release();
   c->d_popmask.release(); c->prep[0].release(); c->prep[1].release();
-  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_cta_counts.release(); c->d_scratch.release(); c->d_dropped_cells.release(); c->d_zero_rare.release();
+  c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_cta_counts[0].release(); c->d_cta_counts[1].release(); c->d_scratch.release(); c->d_dropped_cells.release(); c->d_zero_rare.release();
   c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release();
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
@@ -911,10 +975,14 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   for (cudaEvent_t e : c->ibs_timer_ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->tail_stream) cudaStreamSynchronize(c->tail_stream);
+  if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);
   if (c->prep_done) cudaEventDestroy(c->prep_done);
-  if (c->stream_pass_done) cudaEventDestroy(c->stream_pass_done);
-  for (cudaEvent_t e : c->readers_done) if (e) cudaEventDestroy(e);
+  if (c->inputs_ready) cudaEventDestroy(c->inputs_ready);
+  for (int i = 0; i < 2; ++i)
+    for (cudaEvent_t e : {c->readers_main[i], c->readers_tail[i], c->stream_done[i], c->tail_done[i]}) if (e) cudaEventDestroy(e);
   if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
+  if (c->tail_stream) cudaStreamDestroy(c->tail_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (cudaEvent_t ev : c->chunk_ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1114,7 +1182,7 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
   if (!c) return KGL_B200_ERR_INVALID;
   if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "upload_loci first");
   if (!c->have_offsets) return fail(c, KGL_B200_ERR_STATE, "select_loci needs the locus offsets (upload_loci with offsets)");
-  int rc = use_device(c); if (rc) return rc;
+  int rc = use_device(c, false); if (rc) return rc;     // the selection mask is not read by a tail that may still be running
   min_af = std::min(std::max(min_af, 0.0), 1.0);     // LociiVectorArguments clamps (kga_analysis_inbreed_args.h:85-86)
   max_af = std::min(std::max(max_af, 0.0), 1.0);
   const uint64_t L = c->loci_len;
@@ -1243,12 +1311,18 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t*
 
 int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   if (!c) return KGL_B200_ERR_INVALID;
-  int rc = use_device(c); if (rc) return rc;
+  int rc = use_device(c, false); if (rc) return rc;      // the tail of the pass before may still be running: it is not waited for
   rc = require_population(c, true); if (rc) return rc;
   c->prep_valid = false;   // the AF vectors are an input of the pass: the per-locus preparation is part of every step
   c->peer_results = false;
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
-  return enqueue_moments(c, true, true);
+  rc = enqueue_moments(c, true, true, false, false, true); if (rc) return rc;
+  return mark_tail(c, false);
+}
+
+int kgl_b200_flush(kgl_b200_ctx* c) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  return use_device(c);
 }
 
 // ---- locus-sharded step with the exchange over peer memory -----------------------------------------------------------
@@ -1321,7 +1395,7 @@ int kgl_b200_peer_set_timeout_ms(kgl_b200_ctx* c, uint64_t milliseconds) {
 
 int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
   if (!c) return KGL_B200_ERR_INVALID;
-  int rc = use_device(c); if (rc) return rc;
+  int rc = use_device(c, false); if (rc) return rc;
   rc = require_population(c, true); if (rc) return rc;
   if (c->peer_world == 0 || c->xchg_npad != c->Npad) return fail(c, KGL_B200_ERR_STATE, "kgl_b200_peer_export / kgl_b200_peer_attach first");
   c->prep_valid = false;   // the AF vectors are an input of the pass, as in kgl_b200_enqueue_count_and_inbreed
@@ -1330,23 +1404,25 @@ int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
   const uint64_t epoch = ++c->peer_epoch;
   const uint64_t parity_doubles = c->Npad * PART_COUNT;
   c->partials_target = reinterpret_cast<double*>(c->d_xchg.p) + (epoch & 1ull) * parity_doubles;
-  rc = enqueue_moments(c, true, false);
+  rc = enqueue_moments(c, true, false, false, false, true);
   c->partials_target = nullptr;
   if (rc) return rc;
+  // the exchange follows the tail on the tail stream (the context stream when the population's code-3 cells are not indexed)
+  cudaStream_t xs = c->tail_pending ? c->tail_stream : c->stream;
   PeerParams P{};
   for (uint32_t r = 0; r < c->peer_world; ++r) P.base[r] = static_cast<unsigned char*>(r == c->peer_rank ? (void*)c->d_xchg.p : c->peer_base[r]);
   P.rank = c->peer_rank; P.world = c->peer_world; P.parity_doubles = parity_doubles; P.epoch = epoch; P.n_genomes = c->N;
   P.timeout_ns = c->peer_timeout_ms * 1000000ull;
   P.partials_out = c->d_partials.p; P.results = c->d_results.p; P.error_word = c->d_peer_error.p;
-  k_peer_publish<<<1, kPeerMaxRanks, 0, c->stream>>>(P);
+  k_peer_publish<<<1, kPeerMaxRanks, 0, xs>>>(P);
   KGL_LAUNCH_CHECK(c);
   // one resident wave at most: every block of the exchange spins on the peers' flags
   const unsigned grid = std::min<unsigned>(blocks_for(c->N * 8, 256), (unsigned)c->sm_count * 4u);
-  k_peer_exchange<<<grid, 256, 0, c->stream>>>(P);
+  k_peer_exchange<<<grid, 256, 0, xs>>>(P);
   KGL_LAUNCH_CHECK(c);
   c->algo = KGL_B200_ALGO_SIMPLE; c->phase = 0;     // kgl_b200_inbreed_fetch copies d_results
   c->peer_results = true;
-  return KGL_B200_OK;
+  return mark_tail(c, false);
 }
 
 // After a stream synchronisation: did the last peer step time out? (The word was copied with the results.)
@@ -1370,6 +1446,7 @@ int kgl_b200_fetch_locus_counts(kgl_b200_ctx* c, uint32_t* locus_counts) {
 
 int kgl_b200_run_count_and_inbreed(kgl_b200_ctx* c, uint32_t* locus_counts, kgl_b200_locus_results* out) {
   int rc = kgl_b200_enqueue_count_and_inbreed(c); if (rc) return rc;
+  rc = join_tail(c); if (rc) return rc;
   if (locus_counts)
     KGL_CUDA(c, cudaMemcpyAsync(locus_counts, c->d_locus_counts.p, (size_t)c->L * 16, cudaMemcpyDeviceToHost, c->stream));
   if (out)

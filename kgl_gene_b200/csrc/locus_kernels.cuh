@@ -49,11 +49,19 @@ constexpr int kPrepLociPerBlock = (kPrepThreads / 32) * 64 * kPrepIters;   // 20
 //
 // A warp owns 64 consecutive loci per iteration (lane -> l, l+32), so the group summary and the selection words need no
 // shared memory. The population loop is the OUTER loop: only one population's totals are live at a time.
+// Persistent grid (one or two blocks per SM): a block walks tiles of kPrepLociPerBlock loci with a grid stride, in groups of 512
+// loci (a warp owns 64 consecutive loci of a group: lane -> l, l + 32, so the 64-row summary and the selection words need no
+// shared memory). The kernel is built to run NEXT to a CTA of the streaming kernel on the same SM (<= 80 registers x 256
+// threads, 15 KB of shared memory: kgl_b200_api.cu hides the preparation of pass i+1 behind the streaming kernel of pass i), i.e.
+// with eight warps per SM and HBM saturated by its neighbour: the twelve frequencies of a thread's two loci (six populations) are
+// loaded one group AHEAD of their use, and the per-population sums stay in registers until the block ends (one warp reduction and
+// 36 integer atomics per block instead of one per tile and population).
 constexpr int kPrepRareMax = kPrepLociPerBlock;
+constexpr int kPrepGroup = (kPrepThreads / 32) * 64;             // 512 loci per group
 template <bool WANT_W0, bool WANT_SELW>
-__global__ void __launch_bounds__(kPrepThreads)
-k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, uint64_t n_loci, uint64_t padded_rows, int n_pop,
-                uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64, uint32_t* __restrict__ selw, uint64_t n_words,
+__global__ void __maxnreg__(96)
+k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, uint64_t n_loci, uint64_t padded_rows, uint64_t n_tiles,
+                int n_pop, uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64, uint32_t* __restrict__ selw, uint64_t n_words,
                 const uint4* __restrict__ packed, uint32_t units, const uint64_t* __restrict__ popmask,
                 uint32_t* __restrict__ nz_rare, unsigned long long* __restrict__ ecorr_fx, double fx,
                 unsigned long long* __restrict__ totals_fx, uint32_t* __restrict__ unselected_blocks) {
@@ -62,127 +70,121 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
   __shared__ uint16_t s_rare_fl[kPrepRareMax];
   __shared__ uint32_t s_n_rare;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_n_rare = 0;
-  __syncthreads();
-  const uint64_t base = (uint64_t)blockIdx.x * kPrepLociPerBlock + (uint64_t)warp * 64 + lane;   // + it * 512 + half * 32
-  constexpr int kStep = (kPrepThreads / 32) * 64;                  // loci between two iterations of a warp
-  uint32_t fl[kPrepIters][2], sbits[kPrepIters][2];
+  const uint32_t all_pops = (1u << n_pop) - 1u;
+  bool all_ok = true;
+  // per population: sum q^2, sum p^2 (the heterozygous class is what is left of the count: the three classes of a locus sum to one)
+  double e_majhom[kMaxPop], e_minhom[kMaxPop], w0[WANT_W0 ? kMaxPop : 1];
+  uint32_t n_t[kMaxPop], n_tq[kMaxPop];
 #pragma unroll
-  for (int it = 0; it < kPrepIters; ++it)
+  for (int k = 0; k < kMaxPop; ++k) { e_majhom[k] = 0.0; e_minhom[k] = 0.0; n_t[k] = 0; n_tq[k] = 0; if (WANT_W0) w0[k] = 0.0; }
+
+  // groups of this block, in order: tile blockIdx.x groups 0..3, tile blockIdx.x + gridDim.x groups 0..3, ...
+  const uint64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint64_t n_groups = my_tiles * kPrepIters;
+  auto group_base = [&](uint64_t q) -> uint64_t {       // first locus of this thread in group q
+    const uint64_t tile = blockIdx.x + (q / kPrepIters) * gridDim.x;
+    return tile * kPrepLociPerBlock + (q % kPrepIters) * kPrepGroup + (uint64_t)warp * 64 + lane;
+  };
+  // The frequencies of a group are LOADED one group ahead of their use (registers: a prefetch hint can be dropped by a memory
+  // system that the neighbouring streaming kernel keeps saturated, a load cannot), and pulled into L2 two groups ahead of that.
+  float nxt[2][kMaxPop];
+  uint32_t nsel[2];
+  auto fetch = [&](uint64_t q) {
+    const uint64_t base0 = group_base(q);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const uint64_t l = base + (uint64_t)(it * kStep + 32 * half);
-      fl[it][half] = 0;
-      sbits[it][half] = (l < n_loci) ? (uint32_t)sel[l] : 0u;      // 0 beyond n_loci: nothing is read there
+      const uint64_t l = base0 + 32 * half;
+      const bool in = l < n_loci;
+      nsel[half] = in ? (uint32_t)sel[l] : 0u;
+#pragma unroll
+      for (int k = 0; k < kMaxPop; ++k) nxt[half][k] = (in && k < n_pop) ? __ldg(af + (uint64_t)k * n_loci + l) : 0.0f;
     }
-  // rows past n_loci are never dereferenced: their selection bits are 0 and the frequency pointer is clamped to row 0
-  const uint64_t safe_base = base < n_loci ? base : 0;
-  const bool whole = base + (uint64_t)((kPrepIters - 1) * kStep + 32) < n_loci;          // all eight loci of this thread exist
+  };
+  auto prefetch = [&](uint64_t q) {
+    if (lane < 2 * n_pop) {
+      const uint64_t l = group_base(q) - lane + 32 * (lane & 1);
+      if (l < n_loci) asm volatile("prefetch.global.L2 [%0];" ::"l"(af + (uint64_t)(lane >> 1) * n_loci + l));
+    }
+  };
+  if (n_groups > 0) fetch(0);
+  if (n_groups > 1) prefetch(1);
+  if (n_groups > 2) prefetch(2);
 
-  const float* afk = af + safe_base;
-  uint32_t* selw_k = selw;
-  for (int k = 0; k < n_pop; ++k, afk += n_loci, selw_k += n_words) {
-    double e_majhom = 0.0, e_majhet = 0.0, e_minhom = 0.0, w0 = 0.0;
-    uint32_t n_t = 0, n_tq = 0;
-    // all of this population's frequencies first: eight independent loads in flight instead of eight load->use chains
-    float afv[kPrepIters][2];
+  for (uint64_t q = 0; q < n_groups; ++q) {
+    if (q % kPrepIters == 0) {
+      if (threadIdx.x == 0) s_n_rare = 0;
+      __syncthreads();
+    }
+    float cur[2][kMaxPop];
+    uint32_t csel[2];
 #pragma unroll
-    for (int it = 0; it < kPrepIters; ++it)
+    for (int half = 0; half < 2; ++half) {
+      csel[half] = nsel[half];
 #pragma unroll
-      for (int half = 0; half < 2; ++half)
-        afv[it][half] = (whole || sbits[it][half]) ? __ldg(afk + (it * kStep + 32 * half)) : 0.0f;
+      for (int k = 0; k < kMaxPop; ++k) cur[half][k] = nxt[half][k];
+    }
+    if (q + 1 < n_groups) fetch(q + 1);
+    if (q + 3 < n_groups) prefetch(q + 3);
+    const uint64_t base = group_base(q);
+    uint32_t fl[2] = {0, 0};
 #pragma unroll
-    for (int it = 0; it < kPrepIters; ++it)
+    for (int half = 0; half < 2; ++half) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float a = afv[it][half];
-        const bool on = ((sbits[it][half] >> k) & 1u) && !(a != a);
+      for (int k = 0; k < kMaxPop; ++k) {
+        const float a = cur[half][k];
+        const bool on = ((csel[half] >> k) & 1u) && !(a != a) && k < n_pop;
         if (on) {
-          double p = (double)a;
-          p = p < 0.0 ? 0.0 : (p > 1.0 ? 1.0 : p);
-          double q = __dsub_rn(1.0, p);
-          q = q < 0.0 ? 0.0 : q;
-          fl[it][half] |= 1u << k;
-          ++n_t;
-          e_majhom = fma(q, q, e_majhom);
-          e_majhet = fma(__dadd_rn(q, q), p, e_majhet);
-          e_minhom = fma(p, p, e_minhom);
-          if (q > kMinMajorFreq) { ++n_tq; if (WANT_W0) w0 += __dsub_rn(__ddiv_rn(1.0, q), 1.0); }
-          else fl[it][half] |= 0x100u << k;
+          // clamp(AF, 0, 1) (freq.cpp:47) on the float: the widening conversion is exact and monotone, so the clamp commutes
+          // with it; q = 1 - p then lies in [0, 1] by itself (majorAlleleFrequency(), freq.cpp:119-123)
+          const double p = (double)fminf(fmaxf(a, 0.0f), 1.0f);
+          const double qf = __dsub_rn(1.0, p);
+          fl[half] |= 1u << k;
+          ++n_t[k];
+          e_majhom[k] = fma(qf, qf, e_majhom[k]);
+          e_minhom[k] = fma(p, p, e_minhom[k]);
+          if (qf > kMinMajorFreq) { ++n_tq[k]; if (WANT_W0) w0[k] += __dsub_rn(__ddiv_rn(1.0, qf), 1.0); }
+          else fl[half] |= 0x100u << k;
         }
         if (WANT_SELW) {
           const uint32_t word = __ballot_sync(kFull, on);
-          if (lane == 0) {
-            const uint64_t w = (base + (uint64_t)(it * kStep + 32 * half)) >> 5;
-            if (w < n_words) selw_k[w] = word;
+          if (lane == 0 && k < n_pop) {
+            const uint64_t w = (base + 32 * half) >> 5;
+            if (w < n_words) selw[(uint64_t)k * n_words + w] = word;
           }
         }
       }
-    double acc[TOT_COUNT];
-    acc[TOT_T] = (double)n_t; acc[TOT_TQ] = (double)n_tq;
-    acc[TOT_EMAJHOM] = e_majhom; acc[TOT_EMAJHET] = e_majhet; acc[TOT_EMINHOM] = e_minhom; acc[TOT_W0] = w0;
-#pragma unroll
-    for (int j = 0; j < TOT_COUNT; ++j) {
-      const double v = warp_sum(acc[j]);
-      if (lane == 0) s_tot[warp][k][j] = v;
-    }
-  }
-  if (lane < TOT_COUNT)
-    for (int k = n_pop; k < kMaxPop; ++k) s_tot[warp][k][lane] = 0.0;
-
-#pragma unroll
-  for (int it = 0; it < kPrepIters; ++it) {
-    const uint64_t l0 = base + (uint64_t)it * (kPrepThreads / 32) * 64;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const uint64_t l = l0 + 32 * half;
-      if (l < padded_rows) flags16[l] = (uint16_t)fl[it][half];
-      if ((fl[it][half] >> 8) != 0 && nz_rare != nullptr) {
+      const uint64_t l = base + 32 * half;
+      if (l < padded_rows) flags16[l] = (uint16_t)fl[half];
+      if ((fl[half] >> 8) != 0 && nz_rare != nullptr) {
         const uint32_t slot = atomicAdd(&s_n_rare, 1u);
-        s_rare[slot] = (uint32_t)l; s_rare_fl[slot] = (uint16_t)(fl[it][half] >> 8);
+        s_rare[slot] = (uint32_t)l; s_rare_fl[slot] = (uint16_t)(fl[half] >> 8);
       }
+      if (l < n_loci && (fl[half] & all_pops) != all_pops) all_ok = false;
     }
-    const uint32_t g_and = __reduce_and_sync(kFull, fl[it][0] & fl[it][1]) & 0xFFu;
-    const uint32_t g_or = __reduce_or_sync(kFull, fl[it][0] | fl[it][1]) & 0xFFu;
-    if (lane == 0 && l0 < padded_rows) sum64[l0 >> 6] = (uint16_t)(g_and | (g_or << 8));
-  }
-
-  __syncthreads();
-  if (threadIdx.x < kMaxPop * TOT_COUNT) {
-    const int k = threadIdx.x / TOT_COUNT, j = threadIdx.x % TOT_COUNT;
-    if (k < n_pop) {
-      double v = 0.0;
-      for (int w = 0; w < kPrepThreads / 32; ++w) v += s_tot[w][k][j];
-      const double scale = (j == TOT_T || j == TOT_TQ) ? 1.0 : (j == TOT_W0 ? fx * (1.0 / 128.0) : fx);
-      const long long q = __double2ll_rn(v * scale);
-      if (q != 0) atomicAdd(&totals_fx[k * TOT_COUNT + j], (unsigned long long)q);
+    {
+      const uint64_t l0 = base - lane;
+      const uint32_t g_and = __reduce_and_sync(kFull, fl[0] & fl[1]) & 0xFFu;
+      const uint32_t g_or = __reduce_or_sync(kFull, fl[0] | fl[1]) & 0xFFu;
+      if (lane == 0 && l0 < padded_rows) sum64[l0 >> 6] = (uint16_t)(g_and | (g_or << 8));
     }
-  }
+    if (q % kPrepIters != kPrepIters - 1) continue;
 
-  // ---- the block's rare-major rows: one thread per (row, 128-bit unit); the loads of an item do not depend on each other ----
-  {
-    const uint32_t n_rare_blk = s_n_rare;
-    const uint64_t total = (uint64_t)n_rare_blk * units;
+    // ---- end of a tile: its rare-major rows, one thread per (row, 128-bit unit); the loads of an item do not depend on each other ----
+    __syncthreads();
+    const uint32_t n_rare_tile = s_n_rare;
+    const uint64_t total = (uint64_t)n_rare_tile * units;
     for (uint64_t t = threadIdx.x; t < total; t += kPrepThreads) {
       const uint32_t slot = (uint32_t)(t / units), u = (uint32_t)(t % units);
       const uint32_t row = s_rare[slot];
-      uint32_t rq = s_rare_fl[slot];                       // populations with q <= 0.01 at this row (selected & valid)
+      const uint32_t rq = s_rare_fl[slot];                 // populations with q <= 0.01 at this row (selected & valid)
       const uint4 v = packed[(uint64_t)row * units + u];
-      float a6[kMaxPop];
-      uint64_t m6[kMaxPop];
-#pragma unroll
-      for (int k = 0; k < kMaxPop; ++k) {
-        const bool on = (rq >> k) & 1u;
-        a6[k] = on ? af[(uint64_t)k * n_loci + row] : 0.0f;
-        m6[k] = on ? popmask[(uint64_t)k * units + u] : 0ull;
-      }
       const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-#pragma unroll
-      for (int k = 0; k < kMaxPop; ++k) {
-        const uint64_t mask = m6[k];
+      for (int k = 0; k < n_pop; ++k) {
+        if (!((rq >> k) & 1u)) continue;
+        const uint64_t mask = popmask[(uint64_t)k * units + u];
         if (mask == 0) continue;
         double ca, ch, cm;
-        class_freqs(locus_freq(a6[k]).p, ca, ch, cm);
+        class_freqs(locus_freq(af[(uint64_t)k * n_loci + row]).p, ca, ch, cm);
         const unsigned long long qa = (unsigned long long)__double2ll_rn(ca * fx), qm = (unsigned long long)__double2ll_rn(cm * fx);
         uint64_t homref = ~(lo | hi) & mask;
         uint64_t nonref = (lo | hi) & mask;
@@ -202,20 +204,38 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
     }
   }
 
+  // the block's sums: one warp reduction per (population, total), then one 64-bit integer atomic each
+#pragma unroll
+  for (int k = 0; k < kMaxPop; ++k) {
+    double acc[TOT_COUNT];
+    acc[TOT_T] = (double)n_t[k]; acc[TOT_TQ] = (double)n_tq[k];
+    acc[TOT_EMAJHOM] = e_majhom[k]; acc[TOT_EMAJHET] = 0.0; acc[TOT_EMINHOM] = e_minhom[k]; acc[TOT_W0] = WANT_W0 ? w0[WANT_W0 ? k : 0] : 0.0;
+#pragma unroll
+    for (int j = 0; j < TOT_COUNT; ++j) {
+      const double v = warp_sum(acc[j]);
+      if (lane == 0) s_tot[warp][k][j] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxPop * TOT_COUNT) {
+    const int k = threadIdx.x / TOT_COUNT, j = threadIdx.x % TOT_COUNT;
+    if (k < n_pop) {
+      double v = 0.0;
+      if (j == TOT_EMAJHET) {      // 2qp summed = count - sum q^2 - sum p^2: q + p = 1, so the three products of a locus add up to one
+        double t = 0.0, a = 0.0, m = 0.0;
+        for (int w = 0; w < kPrepThreads / 32; ++w) { t += s_tot[w][k][TOT_T]; a += s_tot[w][k][TOT_EMAJHOM]; m += s_tot[w][k][TOT_EMINHOM]; }
+        v = (t - a) - m;
+      } else {
+        for (int w = 0; w < kPrepThreads / 32; ++w) v += s_tot[w][k][j];
+      }
+      const double scale = (j == TOT_T || j == TOT_TQ) ? 1.0 : (j == TOT_W0 ? fx * (1.0 / 128.0) : fx);
+      const long long qv = __double2ll_rn(v * scale);
+      if (qv != 0) atomicAdd(&totals_fx[k * TOT_COUNT + j], (unsigned long long)qv);
+    }
+  }
   // unselected_blocks (zeroed by the caller) counts the blocks that hold a row < n_loci which is not selected and valid for
   // every population: 0 at the end = the sparse kernels need not look at the flags.
-  {
-    const uint32_t all_pops = (1u << n_pop) - 1u;
-    bool ok = true;
-#pragma unroll
-    for (int it = 0; it < kPrepIters; ++it)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint64_t l = base + (uint64_t)it * (kPrepThreads / 32) * 64 + 32 * half;
-        if (l < n_loci && (fl[it][half] & all_pops) != all_pops) ok = false;
-      }
-    if (!__syncthreads_and(ok) && threadIdx.x == 0) atomicAdd(unselected_blocks, 1u);
-  }
+  if (!__syncthreads_and(all_ok) && threadIdx.x == 0) atomicAdd(unselected_blocks, 1u);
 }
 
 // RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) with lociiSpacing == 0: a locus is taken for

@@ -89,7 +89,7 @@ __host__ __device__ constexpr int ct_threads(int su, int r) { return (kCtHWarps 
 
 // P.slice_units == SU, P.rows_per_stage == R, P.units a multiple of SU (the device row pitch is padded by the upload).
 template <int SU, int R, bool WANT_LOCUS, bool WANT_GENOME>
-__global__ void __launch_bounds__(ct_threads(SU, R), 1)
+__global__ void __maxnreg__(64)
 k_stream_count_ct(const StreamParams P) {
   constexpr int PARTS = kScHThreads / R;        // lanes that share a row in the H role
   constexpr int HU = SU / PARTS;                // units per H thread

@@ -5,21 +5,30 @@
 
 namespace kgl {
 
+// The kernels ask for the largest shared-memory carve-out (228 KB): an SM changes its carve-out only when it is idle, so a
+// co-running kernel of a side stream (preparation, tail: kgl_b200_api.cu) must find the configuration it needs already in place
+// -- with the default carve-out (the smallest that fits, 196 KB for the 181 KB of the <40,64> shape) a 15 KB block does not fit
+// next to a streaming CTA and waits for the whole kernel (measured: tools/kbench --cfg -2).
+template <class K>
+inline cudaError_t stream_kernel_attributes(K kernel, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 template <bool WL, bool WG>
 inline cudaError_t launch_stream_variant(const StreamParams& P, const StreamPlan& pl, cudaStream_t st) {
   dim3 grid(pl.n_ctas, pl.slices);
-  cudaError_t e;
+  static size_t configured[3] = {0, 0, 0};      // per template instance: the dynamic shared-memory size the kernel was last set up for
+  cudaError_t e = cudaSuccess;
   if (pl.shape == 1) {
-    e = cudaFuncSetAttribute(k_stream_count_ct<40, 64, WL, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return e;
+    if (configured[1] != pl.smem) { e = stream_kernel_attributes(k_stream_count_ct<40, 64, WL, WG>, pl.smem); if (e != cudaSuccess) return e; configured[1] = pl.smem; }
     k_stream_count_ct<40, 64, WL, WG><<<grid, pl.threads, pl.smem, st>>>(P);
   } else if (pl.shape == 2) {
-    e = cudaFuncSetAttribute(k_stream_count_ct<8, 256, WL, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return e;
+    if (configured[2] != pl.smem) { e = stream_kernel_attributes(k_stream_count_ct<8, 256, WL, WG>, pl.smem); if (e != cudaSuccess) return e; configured[2] = pl.smem; }
     k_stream_count_ct<8, 256, WL, WG><<<grid, pl.threads, pl.smem, st>>>(P);
   } else {
-    e = cudaFuncSetAttribute(k_stream_count_rt<WL, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return e;
+    if (configured[0] != pl.smem) { e = stream_kernel_attributes(k_stream_count_rt<WL, WG>, pl.smem); if (e != cudaSuccess) return e; configured[0] = pl.smem; }
     k_stream_count_rt<WL, WG><<<grid, pl.threads, pl.smem, st>>>(P);
   }
   return cudaGetLastError();

@@ -196,6 +196,18 @@ __global__ void __launch_bounds__(256) k_read_only(const uint4* packed, uint64_t
   if (acc == 0x12345678u) out[0] = acc;
 }
 
+// Co-residency probe: a block that spins for `ns` nanoseconds, with or without a static shared-memory footprint.
+template <int SMEM_WORDS>
+__global__ void __launch_bounds__(256) k_spin(unsigned long long ns, unsigned* sink) {
+  __shared__ unsigned s_pad[SMEM_WORDS];
+  s_pad[threadIdx.x % SMEM_WORDS] = threadIdx.x;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned acc = 0;
+  do { acc += s_pad[(threadIdx.x * 7 + acc) % SMEM_WORDS]; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < ns);
+  if (acc == 0xFFFFFFFFu) *sink = acc;
+}
+
 int main(int argc, char** argv) {
   uint64_t n_loci = 1100000; uint32_t n_genomes = 2504; int reps = 10; int do_pipes = 1; uint64_t verify_loci = 65536; int only_cfg = -1; int do_verify = 1;
   for (int i = 1; i < argc; ++i) {
@@ -319,6 +331,46 @@ int main(int argc, char** argv) {
                 matrix_bytes / (ms / reps * 1e-3) / 1e9, pl.shape, pl.n_ctas, pl.slices, pl.rows_per_stage, pl.slice_units, pl.h_parts, pl.v_row_lanes,
                 pl.n_stages, pl.smem >> 10);
     CK(cudaFree(d_planes));
+  }
+
+  // ---- co-residency: does a small kernel on a second stream run NEXT to the streaming kernel? ----
+  if (only_cfg == -2) {
+    int least, greatest;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    unsigned* d_sink; CK(cudaMalloc(&d_sink, 4));
+    for (int stages : {0, 2, 1}) {                 // 0: auto (4 stages, 180 KB); 2: 100 KB; 1: 2 stages and the spin kernel launched FIRST
+      const bool spin_first = stages == 1;
+      StreamPlan pl = plan_stream(units, n_loci, sms, 0, stages == 0 ? 0 : 2);
+      CK(cudaMalloc(&d_planes, (size_t)pl.n_ctas * 2 * units * 64 * 4));
+      StreamParams P = make_params(pl, n_loci, 0, true, true, d_planes);
+      for (int equal_prio = 0; equal_prio < 2; ++equal_prio) {
+        cudaStream_t sa, sb;
+        CK(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, greatest));
+        CK(cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, equal_prio ? greatest : least));
+        for (int smem : {0, 1}) {
+          float t[3];
+          for (int mode = 0; mode < 3; ++mode) {      // 0: streaming kernel alone; 1: spin alone (148 blocks x 50 us); 2: both
+            CK(cudaDeviceSynchronize());
+            cudaEvent_t a0, a1, b1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1)); CK(cudaEventCreate(&b1));
+            CK(cudaEventRecord(a0, sa));
+            CK(cudaStreamWaitEvent(sb, a0, 0));
+            auto spin = [&]() { if (smem) k_spin<3600><<<sms, 256, 0, sb>>>(50000ull, d_sink); else k_spin<32><<<sms, 256, 0, sb>>>(50000ull, d_sink); };
+            if (mode != 0 && spin_first) spin();
+            if (mode != 1) CK(launch_stream(P, pl, true, true, sa));
+            if (mode != 0 && !spin_first) spin();
+            CK(cudaEventRecord(b1, sb));
+            CK(cudaStreamWaitEvent(sa, b1, 0));
+            CK(cudaEventRecord(a1, sa));
+            CK(cudaEventSynchronize(a1));
+            CK(cudaEventElapsedTime(&t[mode], a0, a1));
+          }
+          std::printf("corun stages %u smem %zu KB, spin %s, %s priority, spin smem %s: stream %.4f  spin %.4f  both %.4f ms\n", pl.n_stages, pl.smem >> 10,
+                      spin_first ? "first" : "second", equal_prio ? "equal" : "lower", smem ? "14 KB" : "128 B", t[0], t[1], t[2]);
+        }
+      }
+      CK(cudaFree(d_planes));
+    }
+    return 0;
   }
 
   // ---- correctness on a prefix of the matrix ----
