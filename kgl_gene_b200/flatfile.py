@@ -31,6 +31,16 @@ class FlatPopulation:
     packed: np.ndarray       # uint8 [L, row_bytes]
     n_genomes: int
     unphased: bool = False
+    # Multi-allelic loci (include/kgl_b200.h, kgl_b200_upload_multi_allelic). At the listed rows `af` is NaN for every
+    # super-population and `packed` holds only 0 (hom-ref) and 3 (see multi_cells).
+    multi_rows: np.ndarray | None = None     # uint32 [M] rows of the locus table, ascending
+    multi_af: np.ndarray | None = None       # float32 [6, M, 3] per allele slot, NaN = none
+    multi_cells: np.ndarray | None = None    # uint8 [M, N]: 0 hom-ref; low nibble first variant's slot + 1 (4: not in the list), high
+                                             # nibble the second's (0: none); 0xFF: more than two variants
+
+    @property
+    def n_multi(self) -> int:
+        return 0 if self.multi_rows is None else int(self.multi_rows.shape[0])
 
     @property
     def n_loci(self) -> int:
@@ -46,7 +56,7 @@ class FlatPopulation:
 
     def write(self, path: str) -> None:
         hdr = struct.pack("<8s5I9I", b"KGLFLAT1", self.n_genomes, self.n_loci, self.af.shape[0], self.row_bytes,
-                          FLAG_UNPHASED if self.unphased else 0, *([0] * 9))
+                          FLAG_UNPHASED if self.unphased else 0, self.n_multi, *([0] * 8))
         assert len(hdr) == 64
         with open(path, "wb") as f:
             f.write(hdr)
@@ -54,19 +64,28 @@ class FlatPopulation:
             f.write(np.ascontiguousarray(self.af, dtype="<f4").tobytes())
             f.write(np.ascontiguousarray(self.superpop, dtype=np.uint8).tobytes())
             f.write(np.ascontiguousarray(self.packed, dtype=np.uint8).tobytes())
+            if self.n_multi:
+                f.write(np.ascontiguousarray(self.multi_rows, dtype="<u4").tobytes())
+                f.write(np.ascontiguousarray(self.multi_af, dtype="<f4").tobytes())
+                f.write(np.ascontiguousarray(self.multi_cells, dtype=np.uint8).tobytes())
 
     @staticmethod
     def read(path: str) -> "FlatPopulation":
         with open(path, "rb") as f:
             hdr = f.read(64)
-            magic, n, l, npop, rb, flags = struct.unpack("<8s5I", hdr[:28])
+            magic, n, l, npop, rb, flags, n_multi = struct.unpack("<8s6I", hdr[:32])
             if magic != b"KGLFLAT1":
                 raise ValueError(f"{path}: bad magic")
             offsets = np.frombuffer(f.read(4 * l), dtype="<u4").copy()
             af = np.frombuffer(f.read(4 * npop * l), dtype="<f4").reshape(npop, l).copy()
             superpop = np.frombuffer(f.read(n), dtype=np.uint8).copy()
             packed = np.frombuffer(f.read(l * rb), dtype=np.uint8).reshape(l, rb).copy()
-        return FlatPopulation(offsets, af, superpop, packed, n, bool(flags & FLAG_UNPHASED))
+            pop = FlatPopulation(offsets, af, superpop, packed, n, bool(flags & FLAG_UNPHASED))
+            if n_multi:
+                pop.multi_rows = np.frombuffer(f.read(4 * n_multi), dtype="<u4").copy()
+                pop.multi_af = np.frombuffer(f.read(4 * npop * n_multi * 3), dtype="<f4").reshape(npop, n_multi, 3).copy()
+                pop.multi_cells = np.frombuffer(f.read(n_multi * n), dtype=np.uint8).reshape(n_multi, n).copy()
+        return pop
 
 
 def pack_codes(codes: np.ndarray) -> np.ndarray:

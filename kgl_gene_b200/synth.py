@@ -83,3 +83,60 @@ def make_population(n_genomes: int, n_loci: int, seed: int = 20261018, spectrum:
     pop = FlatPopulation(offsets, af, superpop, pack_codes(codes), n_genomes, unphased)
     assert pop.row_bytes == row_bytes_for(n_genomes)
     return pop, inbreeding
+
+
+def add_multi_allelic(pop: FlatPopulation, n_multi: int, seed: int, unknown_rate: float = 0.01, three_rate: float = 0.003) -> FlatPopulation:
+    """Turns `n_multi` loci of `pop` into multi-allelic loci (two or three alternate alleles, FlatPopulation.multi_*): per
+    super-population allele frequencies, some alleles without a frequency for a population, a few loci whose frequencies
+    sum above 1 (invalid for that population), just above 1 (valid, normalised) or above 0.99 (rare major allele); every
+    genome's two haplotypes are drawn from the locus' allele frequencies of its population. A few cells carry an allele that
+    is not in the list (slot 4) or more than two variants (0xFF). In place; returns pop."""
+    rng = np.random.default_rng(seed)
+    n_pop, n_loci, n = pop.af.shape[0], pop.n_loci, pop.n_genomes
+    rows = np.sort(rng.choice(n_loci, size=min(n_multi, n_loci), replace=False)).astype(np.uint32)
+    m_count = rows.shape[0]
+    n_alleles = rng.integers(2, 4, size=m_count)
+    af = np.full((n_pop, m_count, 3), np.nan, dtype=np.float32)
+    for m in range(m_count):
+        a = int(n_alleles[m])
+        for k in range(n_pop):
+            total = rng.beta(0.6, 1.6) * 0.9 + 1e-3
+            kind = rng.integers(0, 40)
+            if kind == 0:
+                total = 1.2                      # sum > 1 + 1e-5: the vector is invalid for this population
+            elif kind == 1:
+                total = 1.000004                 # sum in (1, 1 + 1e-5]: valid, the class frequencies are normalised by the sum
+            elif kind == 2:
+                total = 0.995                    # q <= 0.01: a hom-ref genome is dropped
+            parts = rng.dirichlet(np.ones(a)) * total
+            af[k, m, :a] = parts.astype(np.float32)
+            if rng.random() < 0.08:
+                af[k, m, rng.integers(0, a)] = np.nan        # this allele has no frequency for the population
+            if rng.random() < 0.02:
+                af[k, m, :] = np.nan                         # nor has any: empty vector
+    cells = np.zeros((m_count, n), dtype=np.uint8)
+    sp = pop.superpop.astype(np.int64)
+    for m in range(m_count):
+        a = int(n_alleles[m])
+        p = np.nan_to_num(af[:, m, :a].astype(np.float64), nan=0.0)           # [n_pop, a]
+        tot = p.sum(axis=1, keepdims=True)
+        p = np.where(tot > 1.0, p / np.maximum(tot, 1e-300), p)
+        cum = np.cumsum(np.concatenate([np.maximum(0.0, 1.0 - p.sum(axis=1, keepdims=True)), p], axis=1), axis=1)   # ref first
+        u = rng.random((2, n))
+        hap = (u[:, :, None] >= cum[sp][None, :, :]).sum(axis=2)              # 0 = ref, 1..a = allele slot + 1
+        hap = np.minimum(hap, a)
+        h1, h2 = hap[0], hap[1]
+        first = np.where(h1 > 0, h1, h2)
+        second = np.where((h1 > 0) & (h2 > 0), h2, 0)
+        cell = (first | (second << 4)).astype(np.uint8)
+        if a < 3:
+            unk = (rng.random(n) < unknown_rate) & (cell != 0)
+            swap_first = rng.random(n) < 0.5
+            cell = np.where(unk & swap_first, (cell & 0xF0) | 4, cell)
+            cell = np.where(unk & ~swap_first & (cell >> 4 != 0), (cell & 0x0F) | (4 << 4), cell).astype(np.uint8)
+        cell = np.where(rng.random(n) < three_rate, 0xFF, cell).astype(np.uint8)
+        cells[m] = cell
+    pop.af[:, rows] = np.nan
+    pop.packed[rows] = pack_codes(np.where(cells != 0, 3, 0).astype(np.uint8))
+    pop.multi_rows, pop.multi_af, pop.multi_cells = rows, af, cells
+    return pop

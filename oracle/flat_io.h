@@ -9,6 +9,11 @@
 //    `packed` is the product's canonical loci-major layout (include/kgl_b200.h): per locus a row of
 //    128-bit units, unit u = {u64 lo-plane, u64 hi-plane} of genomes 64u..64u+63, code = lo + 2*hi
 //    (0 hom-ref, 1 het, 2 hom-alt, 3 dropped/missing).
+//    Multi-allelic loci (optional trailing section; header.reserved[0] = M > 0): u32 multi_rows[M] | f32 multi_af[6][M][3] |
+//    u8 multi_cells[M][N]. At the listed rows of the locus table the main `af` is NaN and `packed` holds only 0 (hom-ref) and 3
+//    (see multi_cells). multi_af[k][m][a] = frequency of allele slot a (0..2) for super-population k, NaN = none. multi_cells:
+//    0 = hom-ref; low nibble = first variant's allele slot + 1 (4 = an allele that is not in the locus' list), high nibble =
+//    the second variant's (0 = there is none); 0xFF = more than two variants at the offset.
 //  * KGLTENS1: named little-endian arrays: "KGLTENS1" | u64 json_len | json | raw data (8-byte aligned)
 //      json = [{"name":..,"dtype":"f64|u64|u32|f32|u8","shape":[..],"offset":..}, ...]
 #pragma once
@@ -41,7 +46,13 @@ struct Flat {
   std::vector<float> af;          // [6][L]
   std::vector<uint8_t> superpop;  // [N]
   std::vector<uint8_t> packed;    // [L][row_bytes]
+  std::vector<uint32_t> multi_rows;   // [M]
+  std::vector<float> multi_af;        // [6][M][3]
+  std::vector<uint8_t> multi_cells;   // [M][N]
 
+  uint32_t M() const { return hdr.reserved[0]; }
+  float multiAf(uint32_t pop, uint32_t m, uint32_t a) const { return multi_af[(size_t(pop) * M() + m) * 3 + a]; }
+  uint8_t multiCell(uint32_t m, uint32_t g) const { return multi_cells[size_t(m) * hdr.n_genomes + g]; }
   uint32_t N() const { return hdr.n_genomes; }
   uint32_t L() const { return hdr.n_loci; }
   float afAt(uint32_t pop, uint32_t locus) const { return af[size_t(pop) * hdr.n_loci + locus]; }
@@ -75,6 +86,14 @@ inline Flat readFlat(const std::string& path) {
   rd(fl.af.data(), fl.af.size() * 4);
   rd(fl.superpop.data(), N);
   rd(fl.packed.data(), fl.packed.size());
+  if (const size_t M = fl.M()) {
+    fl.multi_rows.resize(M);
+    fl.multi_af.resize(size_t(fl.hdr.n_superpop) * M * 3);
+    fl.multi_cells.resize(M * N);
+    rd(fl.multi_rows.data(), M * 4);
+    rd(fl.multi_af.data(), fl.multi_af.size() * 4);
+    rd(fl.multi_cells.data(), fl.multi_cells.size());
+  }
   std::fclose(f);
   return fl;
 }
@@ -89,6 +108,11 @@ inline void writeFlat(const std::string& path, const Flat& fl) {
   std::fwrite(fl.af.data(), 4, fl.af.size(), f);
   std::fwrite(fl.superpop.data(), 1, fl.superpop.size(), f);
   std::fwrite(fl.packed.data(), 1, fl.packed.size(), f);
+  if (fl.M()) {
+    std::fwrite(fl.multi_rows.data(), 4, fl.multi_rows.size(), f);
+    std::fwrite(fl.multi_af.data(), 4, fl.multi_af.size(), f);
+    std::fwrite(fl.multi_cells.data(), 1, fl.multi_cells.size(), f);
+  }
   std::fclose(f);
 }
 

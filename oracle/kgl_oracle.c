@@ -44,6 +44,108 @@ static inline int allele_valid(float af, double* p) {
 /* majorAlleleFrequency(): clamp(1 - clamp(sum,0,1), 0, 1)  (kga_analysis_inbreed_freq.cpp:113-123). */
 static inline double major_freq(double p) { return clamp01(1.0 - clamp01(p)); }
 
+/* ---- multi-allelic loci (oracle/flat_io.h trailing section; set with kgl_oracle_set_multi, test infrastructure: not thread safe) */
+static struct {
+  size_t n_multi, n_genomes, n_loci, n_pop;
+  uint32_t* rows; float* af; uint8_t* cells; int32_t* multi_of;
+} g_multi;
+
+void kgl_oracle_set_multi(size_t n_multi, const uint32_t* rows, const float* af, const uint8_t* cells, size_t n_pop,
+                          size_t n_genomes, size_t n_loci) {
+  free(g_multi.rows); free(g_multi.af); free(g_multi.cells); free(g_multi.multi_of);
+  memset(&g_multi, 0, sizeof g_multi);
+  if (n_multi == 0) return;
+  g_multi.n_multi = n_multi; g_multi.n_genomes = n_genomes; g_multi.n_loci = n_loci; g_multi.n_pop = n_pop;
+  g_multi.rows = (uint32_t*)malloc(n_multi * 4); memcpy(g_multi.rows, rows, n_multi * 4);
+  g_multi.af = (float*)malloc(n_pop * n_multi * 3 * 4); memcpy(g_multi.af, af, n_pop * n_multi * 3 * 4);
+  g_multi.cells = (uint8_t*)malloc(n_multi * n_genomes); memcpy(g_multi.cells, cells, n_multi * n_genomes);
+  g_multi.multi_of = (int32_t*)malloc(n_loci * 4);
+  for (size_t l = 0; l < n_loci; ++l) g_multi.multi_of[l] = -1;
+  for (size_t m = 0; m < n_multi; ++m) g_multi.multi_of[rows[m]] = (int32_t)m;
+}
+
+static inline int multi_index(size_t locus) {
+  return (g_multi.n_multi && locus < g_multi.n_loci) ? g_multi.multi_of[locus] : -1;
+}
+
+/* AlleleFreqVector of a multi-allelic locus for one super-population (kga_analysis_inbreed_freq.cpp:18-57): the alleles that have
+ * a frequency for the population, in the order of the locus' variant array, each clamped to [0,1] (:47). slot[i] = allele slot. */
+typedef struct { int n; int slot[3]; double p[3]; } allele_vector;
+static allele_vector multi_vector(int m, size_t pop) {
+  allele_vector v; v.n = 0;
+  for (int a = 0; a < 3; ++a) {
+    const float f = g_multi.af[(pop * g_multi.n_multi + (size_t)m) * 3 + (size_t)a];
+    if (isnan(f)) continue;
+    v.slot[v.n] = a; v.p[v.n] = clamp01((double)f); ++v.n;
+  }
+  return v;
+}
+static double vector_sum(const allele_vector* v) { double s = 0.0; for (int i = 0; i < v->n; ++i) s += v->p[i]; return s; }   /* sumAlleleFrequencies() :97 */
+static int vector_valid(const allele_vector* v) {                                 /* checkValidAlleleVector() :61-75 */
+  if (vector_sum(v) - 1.0 > 1.0e-05) return 0;                                    /* epsilon_class_ (freq.h) */
+  return v->n > 0;
+}
+static int vector_find(const allele_vector* v, int slot) { for (int i = 0; i < v->n; ++i) if (v->slot[i] == slot) return i; return -1; }
+
+/* alleleClassFrequencies(0.0) (:127-217 + normalize(), freq.h:54-63) of an allele vector: {majHom, majHet, minHom, minHet}. */
+static void vector_class_freqs(const allele_vector* v, double out[4]) {
+  const double inbreeding = 0.0;
+  double sum_minor_freq = 0.0;
+  for (int i = 0; i < v->n; ++i) sum_minor_freq += v->p[i];
+  const double major_frequency = fmax(0.0, 1.0 - sum_minor_freq);                 /* :140 */
+  double f[3];
+  for (int i = 0; i < v->n; ++i) f[i] = (sum_minor_freq > 1.0) ? v->p[i] / sum_minor_freq : v->p[i];   /* :143-151 */
+  double minor_homozygous = 0.0;
+  for (int i = 0; i < v->n; ++i) minor_homozygous += (inbreeding * f[i]) + ((1.0 - inbreeding) * f[i] * f[i]);   /* :158 */
+  double minor_heterozygous = 0.0;
+  for (int i = 0; i < v->n; ++i)
+    for (int j = i + 1; j < v->n; ++j) minor_heterozygous += (1.0 - inbreeding) * 2.0 * f[i] * f[j];              /* :170 */
+  double major_homozygous = (inbreeding * major_frequency) + ((1.0 - inbreeding) * major_frequency * major_frequency);   /* :176 */
+  double major_heterozygous = 0.0;
+  for (int i = 0; i < v->n; ++i) major_heterozygous += (1.0 - inbreeding) * 2.0 * major_frequency * f[i];        /* :181 */
+  major_homozygous = fmax(0.0, major_homozygous); major_heterozygous = fmax(0.0, major_heterozygous);
+  minor_homozygous = fmax(0.0, minor_homozygous); minor_heterozygous = fmax(0.0, minor_heterozygous);
+  const double sum_freqs = major_homozygous + major_heterozygous + minor_homozygous + minor_heterozygous;
+  out[0] = major_homozygous / sum_freqs; out[1] = major_heterozygous / sum_freqs;
+  out[2] = minor_homozygous / sum_freqs; out[3] = minor_heterozygous / sum_freqs;
+}
+
+size_t kgl_oracle_select_loci_pop(const uint32_t* offsets, const float* af, size_t n_loci, size_t pop,
+                                  uint64_t lower, uint64_t upper, uint64_t spacing, uint64_t count,
+                                  double min_af, double max_af, int mode, uint8_t* selected, size_t* last_index) {
+  /* kgl_oracle_select_loci with the multi-allelic loci of kgl_oracle_set_multi: sum_frequencies = clamp(sum of the allele
+   * frequencies, 0, 1) (minorAlleleFrequencies(), freq.cpp:107-111); af = the population's row of the main table. */
+  size_t n_selected = 0;
+  uint64_t previous_offset = 0;
+  memset(selected, 0, n_loci);
+  size_t l = 0;
+  while (l < n_loci && offsets[l] < lower) ++l;
+  for (; l < n_loci; ++l) {
+    const uint64_t offset = offsets[l];
+    if (mode == 0) { if (offset > upper) break; }
+    else { if (n_selected >= count) break; }
+    if (offset >= previous_offset + spacing || previous_offset == 0) {
+      double sum_frequencies;
+      const int m = multi_index(l);
+      if (m >= 0) {
+        const allele_vector v = multi_vector(m, pop);
+        if (!vector_valid(&v)) continue;
+        sum_frequencies = clamp01(vector_sum(&v));
+      } else {
+        double p;
+        if (!allele_valid(af[l], &p)) continue;
+        sum_frequencies = clamp01(p);
+      }
+      if (sum_frequencies == 0.0 || sum_frequencies < min_af || sum_frequencies > max_af) continue;
+      previous_offset = offset;
+      selected[l] = 1;
+      if (last_index) *last_index = l;
+      ++n_selected;
+    }
+  }
+  return n_selected;
+}
+
 size_t kgl_oracle_select_loci(const uint32_t* offsets, const float* af, size_t n_loci,
                               uint64_t lower, uint64_t upper, uint64_t spacing, uint64_t count,
                               double min_af, double max_af, int mode, uint8_t* selected, size_t* last_index) {
@@ -77,12 +179,51 @@ enum { CLS_MAJOR_HOM = 0, CLS_MAJOR_HET = 1, CLS_MINOR_HET = 2, CLS_MINOR_HOM = 
 
 /* generateFrequencies (kga_analysis_inbreed_freq.cpp:425-583) for one genome; returns the number of classified loci. */
 static size_t generate_frequencies(const uint8_t* packed, size_t row_bytes, size_t n_loci, size_t genome,
-                                   const float* af_pop, const uint8_t* sel_pop, int unphased,
+                                   const float* af_pop, const uint8_t* sel_pop, int unphased, size_t pop,
                                    locus_term* terms, kgl_oracle_locus_results* r) {
   size_t n = 0;
   memset(r, 0, sizeof *r);
   for (size_t l = 0; l < n_loci; ++l) {
     if (!sel_pop[l]) continue;                               /* locus_list holds only the selected loci (:439) */
+    const int m = multi_index(l);
+    if (m >= 0) {
+      /* a locus with several alternate alleles: the general form of the classification (:452-543) */
+      const allele_vector v = multi_vector(m, pop);
+      if (!vector_valid(&v)) continue;                       /* :445-449 */
+      const double q = clamp01(1.0 - clamp01(vector_sum(&v)));   /* majorAlleleFrequency() :113-123 */
+      const uint8_t cell = g_multi.cells[(size_t)m * g_multi.n_genomes + genome];
+      locus_term t;
+      if (cell == 0) {                                       /* no variant at the offset (:521-541) */
+        if (!(q > 0.01)) continue;
+        t.cls = CLS_MAJOR_HOM; t.first = q; t.second = q;
+      } else if (cell == 0xFF) {
+        continue;                                            /* more than two variants: neither size() == 1 nor == 2 */
+      } else {
+        const int first = (cell & 15) - 1, second = (cell >> 4) - 1;
+        const int i = first < 3 ? vector_find(&v, first) : -1;
+        if (i < 0) continue;                                 /* the front variant is not in the AF list (:462) */
+        if (second < 0) {                                    /* one variant: MAJOR_HETEROZYGOUS (:464-472) */
+          t.cls = CLS_MAJOR_HET; t.first = v.p[i]; t.second = q;
+        } else if (second == first && !unphased) {           /* front->homozygous(back): same allele, different phase (:476) */
+          t.cls = CLS_MINOR_HOM; t.first = v.p[i]; t.second = v.p[i];
+        } else {                                             /* different alleles, or the same allele unphased (Q6): :482-511 */
+          const int j = second < 3 ? vector_find(&v, second) : -1;
+          if (j < 0) continue;                               /* second minor not found (:500) */
+          t.cls = CLS_MINOR_HET; t.first = v.p[i]; t.second = v.p[j];
+        }
+      }
+      terms[n++] = t;
+      double cf[4];
+      vector_class_freqs(&v, cf);
+      r->major_homo_freq += cf[0]; r->major_hetero_freq += cf[1]; r->minor_homo_freq += cf[2]; r->minor_hetero_freq += cf[3];
+      switch (t.cls) {
+        case CLS_MINOR_HOM: ++r->minor_homo_count; break;
+        case CLS_MAJOR_HET: ++r->major_hetero_count; break;
+        case CLS_MINOR_HET: ++r->minor_hetero_count; break;
+        default: ++r->major_homo_count; break;
+      }
+      continue;
+    }
     double p;
     if (!allele_valid(af_pop[l], &p)) continue;              /* :445-449 */
     const double q = major_freq(p);
@@ -242,7 +383,7 @@ void kgl_oracle_inbreed_some(const uint8_t* packed, size_t row_bytes, size_t n_g
       const size_t k = superpop[g];
       kgl_oracle_locus_results r;
       const size_t n = generate_frequencies(packed, row_bytes, n_loci, g, af + k * n_loci, selected + k * n_loci,
-                                            unphased, terms, &r);
+                                            unphased, k, terms, &r);
       switch (algorithm) {
         case KGL_ORACLE_SIMPLE: {                              /* processSimple (calc.cpp:319-365) */
           double homozygous_inbreeding = 0.0;
@@ -308,7 +449,7 @@ void kgl_oracle_loglik_grid(const uint8_t* packed, size_t row_bytes, size_t n_ge
     for (long gi = 0; gi < (long)n_genomes; ++gi) {
       const size_t g = (size_t)gi, k = superpop[g];
       kgl_oracle_locus_results r;
-      const size_t n = generate_frequencies(packed, row_bytes, n_loci, g, af + k * n_loci, selected + k * n_loci, unphased, terms, &r);
+      const size_t n = generate_frequencies(packed, row_bytes, n_loci, g, af + k * n_loci, selected + k * n_loci, unphased, k, terms, &r);
       for (size_t i = 0; i < n_grid; ++i) out[g * n_grid + i] = log_likelihood(grid[i], terms, n);
     }
     free(terms);

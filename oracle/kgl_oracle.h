@@ -40,6 +40,18 @@ size_t kgl_oracle_select_loci(const uint32_t* offsets, const float* af, size_t n
                               uint64_t lower, uint64_t upper, uint64_t spacing, uint64_t count,
                               double min_af, double max_af, int mode, uint8_t* selected, size_t* last_index);
 
+/* Multi-allelic loci (oracle/flat_io.h, trailing section of KGLFLAT1): rows of the locus table with up to three alternate
+ * alleles -- af f32[n_pop][n_multi][3] per allele slot (NaN = none), cells u8[n_multi][n_genomes] (0 hom-ref; low nibble the
+ * first variant's slot + 1, 4 = not in the list; high nibble the second variant's, 0 = none; 0xFF = more than two variants).
+ * Copied; used by every later kgl_oracle_select_loci_pop / kgl_oracle_inbreed* / kgl_oracle_loglik_grid call until reset with
+ * n_multi = 0. The general forms of AlleleFreqVector, alleleClassFrequencies and the classification
+ * (kga_analysis_inbreed_freq.cpp:18-57,127-217,452-543) apply at those rows. */
+void kgl_oracle_set_multi(size_t n_multi, const uint32_t* rows, const float* af, const uint8_t* cells, size_t n_pop,
+                          size_t n_genomes, size_t n_loci);
+size_t kgl_oracle_select_loci_pop(const uint32_t* offsets, const float* af, size_t n_loci, size_t pop,
+                                  uint64_t lower, uint64_t upper, uint64_t spacing, uint64_t count,
+                                  double min_af, double max_af, int mode, uint8_t* selected, size_t* last_index);
+
 /* InbreedingCalculation::generateFrequencies + process{Simple,RitlandLocus,HallME,LogLikelihood}
  * (kga_analysis_inbreed_freq.cpp:425-583, kga_analysis_inbreed_calc.cpp:319,375,226,154), biallelic loci.
  * selected: u8[n_pop][n_loci] from kgl_oracle_select_loci; superpop: u8[n_genomes]; unphased: SURVEY Q6.

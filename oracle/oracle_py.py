@@ -60,13 +60,37 @@ def select_loci(offsets, af_pop, lower=0, upper=10**9, spacing=0, count=10**9, m
     return sel, int(last.value)
 
 
-def select_all_pops(pop, **kw):
-    """uint8 [6, L] selection masks, one per super-population."""
-    return np.stack([select_loci(pop.offsets, pop.af[k], **kw)[0] for k in range(pop.af.shape[0])])
+def set_multi(pop) -> None:
+    """Hands the population's multi-allelic loci (or none) to the C restatement; every entry point below calls it."""
+    if getattr(pop, "n_multi", 0):
+        rows = np.ascontiguousarray(pop.multi_rows, dtype=np.uint32)
+        af = np.ascontiguousarray(pop.multi_af, dtype=np.float32)
+        cells = np.ascontiguousarray(pop.multi_cells, dtype=np.uint8)
+        lib().kgl_oracle_set_multi(C.c_size_t(rows.shape[0]), _p(rows), _p(af), _p(cells), C.c_size_t(af.shape[0]),
+                                   C.c_size_t(pop.n_genomes), C.c_size_t(pop.n_loci))
+    else:
+        lib().kgl_oracle_set_multi(C.c_size_t(0), None, None, None, C.c_size_t(0), C.c_size_t(0), C.c_size_t(0))
+
+
+def select_all_pops(pop, lower=0, upper=10**9, spacing=0, count=10**9, min_af=0.0, max_af=1.0, mode=0):
+    """uint8 [6, L] selection masks, one per super-population (multi-allelic loci included)."""
+    set_multi(pop)
+    lib().kgl_oracle_select_loci_pop.restype = C.c_size_t
+    offsets = np.ascontiguousarray(pop.offsets, dtype=np.uint32)
+    out = []
+    for k in range(pop.af.shape[0]):
+        af_pop = np.ascontiguousarray(pop.af[k], dtype=np.float32)
+        sel = np.zeros(offsets.shape[0], dtype=np.uint8)
+        lib().kgl_oracle_select_loci_pop(_p(offsets), _p(af_pop), C.c_size_t(offsets.shape[0]), C.c_size_t(k), C.c_uint64(lower),
+                                         C.c_uint64(upper), C.c_uint64(spacing), C.c_uint64(count), C.c_double(min_af),
+                                         C.c_double(max_af), C.c_int(mode), _p(sel), None)
+        out.append(sel)
+    return np.stack(out)
 
 
 def inbreed(pop, selected, algorithm: str, start=None, sweeps: int = 50, genomes=None) -> np.ndarray:
     """genomes: optional list of genome indices -- the result then has one row per listed genome (start stays indexed by genome)."""
+    set_multi(pop)
     gl = None if genomes is None else np.ascontiguousarray(genomes, dtype=np.uint32)
     n_some = pop.n_genomes if gl is None else gl.shape[0]
     out = np.zeros(n_some, dtype=RESULT_DTYPE)
@@ -83,6 +107,7 @@ def inbreed(pop, selected, algorithm: str, start=None, sweeps: int = 50, genomes
 
 
 def loglik_grid(pop, selected, grid) -> np.ndarray:
+    set_multi(pop)
     grid = np.ascontiguousarray(grid, dtype=np.float64)
     out = np.zeros((pop.n_genomes, grid.shape[0]), dtype=np.float64)
     packed = np.ascontiguousarray(pop.packed)

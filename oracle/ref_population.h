@@ -4,6 +4,11 @@
 // everything downstream of it is reference code. Only non-reference alleles are stored:
 //   code 1 -> one "A>G" variant, code 2 -> two (phase A and B; both UNPHASED for an unphased population),
 //   code 3 -> one "A>T" variant, an allele that is not in the AF list and therefore dropped (freq.cpp:462).
+// Multi-allelic loci (flat_io.h, trailing section): allele slot a of the locus is the SNP "A>" + "GCT"[a]; the AF population
+// holds one variant per slot at the offset (each with its own INFO block), a genome holds the one or two variants its cell
+// names, FIRST variant first (generateFrequencies looks the front of the offset array up first, freq.cpp:462-511); slot 4 of
+// a cell is the first base of "GCT" the locus does not list; 0xFF puts three variants at the offset (dropped: neither
+// size() == 1 nor == 2).
 #pragma once
 #include "kgl_variant_db_population.h"
 #include "kgl_variant_factory_vcf_evidence.h"
@@ -69,7 +74,37 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
   const std::vector<kgl::GenomeId_t> af_genome{"AF_GENOME"};
   std::vector<kgl::VariantEvidence> locus_evidence;
   if (diploid_evidence) locus_evidence.reserve(L);
+  std::vector<int> multi_of(L, -1);
+  for (uint32_t m = 0; m < flat.M(); ++m) multi_of[flat.multi_rows[m]] = int(m);
+  static const char* const kAltBases[3] = {"G", "C", "T"};
+  auto slots_of = [&](uint32_t m) {          // number of allele slots the locus lists (a slot is listed if any population has its AF)
+    uint32_t n = 0;
+    for (uint32_t a = 0; a < 3; ++a)
+      for (int k = 0; k < 6; ++k) if (!std::isnan(flat.multiAf(k, m, a))) n = a + 1;
+    return n;
+  };
   for (uint32_t l = 0; l < L; ++l) {
+    if (multi_of[l] >= 0) {
+      const uint32_t m = uint32_t(multi_of[l]), n_slots = slots_of(m);
+      for (uint32_t a = 0; a < n_slots; ++a) {
+        std::string info;
+        for (int k = 0; k < 6; ++k) {
+          const float af = flat.multiAf(k, m, a);
+          if (std::isnan(af)) continue;
+          char buf[64];
+          std::snprintf(buf, sizeof buf, "%s%s=%.9g", info.empty() ? "" : ";", fields[k], double(af));
+          info += buf;
+        }
+        auto block = evidence_factory.createVariantEvidence(std::move(info));
+        kgl::VariantEvidence evidence(l, af_source, true, block, nullptr, 0, 1);
+        auto variant = std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], kgl::VariantPhase::UNPHASED, "",
+                                                            kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
+                                                            kgl::DNA5SequenceLinear(kgl::StringDNA5(kAltBases[a])), evidence);
+        if (!out.af_population->addVariant(variant, af_genome)) kel::ExecEnv::log().error("harness: AF addVariant failed at multi locus {}", l);
+      }
+      if (diploid_evidence) locus_evidence.emplace_back(l, diploid_source, true, nullptr, nullptr, 0, 1);
+      continue;
+    }
     std::string info;
     for (int k = 0; k < 6; ++k) {
       const float af = flat.afAt(k, l);
@@ -101,6 +136,30 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
   };
   std::vector<kgl::GenomeId_t> first, second, other;
   for (uint32_t l = 0; l < L; ++l) {
+    const auto phase_a0 = unphased ? kgl::VariantPhase::UNPHASED : kgl::VariantPhase::DIPLOID_PHASE_A;
+    const auto phase_b0 = unphased ? kgl::VariantPhase::UNPHASED : kgl::VariantPhase::DIPLOID_PHASE_B;
+    if (multi_of[l] >= 0) {
+      const uint32_t m = uint32_t(multi_of[l]), n_slots = slots_of(m);
+      out.locus_variant[l] = make(l, phase_a0, "G");
+      auto alt_of = [&](unsigned slot1) -> const char* {     // slot1 = slot + 1; 4 = the first base the locus does not list
+        if (slot1 <= 3) return kAltBases[slot1 - 1];
+        return n_slots < 3 ? kAltBases[n_slots] : "N";
+      };
+      for (uint32_t g = 0; g < N; ++g) {
+        const uint8_t cell = flat.multiCell(m, g);
+        if (cell == 0) continue;
+        const std::vector<kgl::GenomeId_t> one{out.genome_ids[g]};
+        if (cell == 0xFF) {
+          out.diploid->addVariant(make(l, phase_a0, "G"), one);
+          out.diploid->addVariant(make(l, phase_b0, "G"), one);
+          out.diploid->addVariant(make(l, phase_a0, "C"), one);
+          continue;
+        }
+        out.diploid->addVariant(make(l, phase_a0, alt_of(cell & 15u)), one);
+        if (cell >> 4) out.diploid->addVariant(make(l, phase_b0, alt_of(cell >> 4)), one);
+      }
+      continue;
+    }
     first.clear(); second.clear(); other.clear();
     for (uint32_t g = 0; g < N; ++g) {
       switch (flat.code(l, g)) {

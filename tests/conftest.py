@@ -10,7 +10,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(os.path.abspath(__
         sys.path.insert(0, p)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["sfs_phased", "dense_spacing_af", "unphased_pf", "missing_af_ragged", "rare_major"]
+GOLDEN_CASES = ["sfs_phased", "dense_spacing_af", "unphased_pf", "missing_af_ragged", "rare_major", "multi_allelic", "multi_allelic_unphased"]
 
 
 def pytest_configure(config):
@@ -23,6 +23,8 @@ def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     pop = FlatPopulation(z["in_offsets"], z["in_af"], z["in_superpop"], z["in_packed"], int(z["in_n_genomes"][0]),
                          bool(z["in_unphased"][0]))
+    if "in_multi_rows" in z.files:
+        pop.multi_rows, pop.multi_af, pop.multi_cells = z["in_multi_rows"], z["in_multi_af"], z["in_multi_cells"]
     ref = {k[4:]: z[k] for k in z.files if k.startswith("ref_")}
     sel_kw = dict(spacing=int(z["arg_spacing"][0]), min_af=float(z["arg_min_af"][0]), max_af=float(z["arg_max_af"][0]),
                   lower=int(z["arg_lower"][0]), upper=int(z["arg_upper"][0]))

@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import oracle_py as O  # noqa: E402
-from kgl_gene_b200.synth import make_population  # noqa: E402
+from kgl_gene_b200.synth import add_multi_allelic, make_population  # noqa: E402
 
 CASES = {
     # name: (make_population kwargs, harness kwargs)
@@ -29,7 +29,12 @@ CASES = {
     "missing_af_ragged": (dict(n_genomes=70, n_loci=600, seed=404, spectrum="sfs", missing_af_rate=0.05, missing_rate=0.02,
                                grouped=False), dict(seed=5, min_af=0.01)),
     "rare_major": (dict(n_genomes=20, n_loci=500, seed=505, spectrum="sfs"), dict(seed=9)),   # af pushed towards 1 below
+    # loci with two or three alternate alleles (add_multi_allelic below): AlleleFreqVector over several alleles, MINOR_HETEROZYGOUS
+    # with two different alleles, the normalised class frequencies of kga_analysis_inbreed_freq.cpp:127-217
+    "multi_allelic": (dict(n_genomes=60, n_loci=1400, seed=606, spectrum="sfs", missing_af_rate=0.01), dict(seed=13, spacing=15)),
+    "multi_allelic_unphased": (dict(n_genomes=30, n_loci=900, seed=707, spectrum="dense", unphased=True), dict(seed=15)),
 }
+MULTI = {"multi_allelic": (160, 61), "multi_allelic_unphased": (120, 71)}      # name: (loci made multi-allelic, seed)
 
 
 def main():
@@ -43,11 +48,15 @@ def main():
             pop.af[:, ::7] = np.float32(0.995)
             pop.af[:, 3::11] = np.float32(0.0005)
             pop.af[:, 5::13] = np.float32(1.0)
-        ref = O.run_reference(pop, grid=21, fws=True, **ref_kw)
+        if name in MULTI:
+            add_multi_allelic(pop, *MULTI[name])
+        ref = O.run_reference(pop, grid=21, fws=name not in MULTI, **ref_kw)
         stderr = ref.pop("_stderr")
         arrays = {"in_offsets": pop.offsets, "in_af": pop.af, "in_superpop": pop.superpop, "in_packed": pop.packed,
                   "in_n_genomes": np.array([pop.n_genomes]), "in_unphased": np.array([int(pop.unphased)]),
                   "in_true_inbreeding": inbreeding}
+        if pop.n_multi:
+            arrays.update(in_multi_rows=pop.multi_rows, in_multi_af=pop.multi_af, in_multi_cells=pop.multi_cells)
         for k in ("spacing", "min_af", "max_af", "lower", "upper", "seed"):
             default = {"spacing": 0, "min_af": 0.0, "max_af": 1.0, "lower": 0, "upper": 10**9, "seed": 0}[k]
             arrays["arg_" + k] = np.array([ref_kw.get(k, default)], dtype=np.float64)
