@@ -98,6 +98,19 @@ int kgl_b200_set_genome_superpop(kgl_b200_ctx* ctx, uint64_t n_genomes, const ui
 /* Pf7-style population: all variants UNPHASED, so a hom-alt pair is classified MINOR_HETEROZYGOUS. */
 int kgl_b200_set_unphased(kgl_b200_ctx* ctx, int unphased);
 
+/* Loci with several alternate alleles (the "3 + side list" rows of the flattener contract; call after the three uploads above).
+ * rows[n_multi]: ascending rows of the locus table -- there the frequency table is ignored (treated as "no value") and the matrix
+ * holds only 0 (hom-ref) and 3 (see cells). af float[n_pop][n_multi][3]: frequency of allele slot 0..2 (the order of the locus'
+ * variant array) per super-population, NaN = the allele has no value for it. cells uint8[n_multi][n_genomes]: 0 = hom-ref; low
+ * nibble = allele slot + 1 of the FIRST variant at the offset (4 = an allele that is not in the list), high nibble = the second
+ * variant's (0 = none); 0xFF = more than two variants. The general form of the reference's classification applies there:
+ * AlleleFreqVector over several alleles, major frequency = complement of their sum, MINOR_HETEROZYGOUS for two different
+ * alleles, the class frequencies of alleleClassFrequencies (kga_analysis_inbreed_freq.cpp:18-57,127-217,452-543). For the pairwise
+ * kernels such a cell is "missing". kgl_b200_run_multi_allele_count: per-allele summaries (one VariantDBVariant column per
+ * allele, kgl_variant_db_variant.cpp:14-30): counts uint32[n_multi][3][3] = genomes with 0, 1, 2 copies of allele slot a. */
+int kgl_b200_upload_multi_allelic(kgl_b200_ctx* ctx, uint64_t n_multi, const uint32_t* rows, const float* af, const uint8_t* cells);
+int kgl_b200_run_multi_allele_count(kgl_b200_ctx* ctx, uint32_t* counts);
+
 /* Locus selection for the current window. kgl_b200_select_loci applies RetrieveLociiVector::getLociiFromTo
  * (kga_analysis_inbreed_locus.cpp:21-72,76) to every super-population: loci with lower <= offset <= upper, at least
  * `spacing` apart, valid AF with 0 < AF and min_af <= AF <= max_af. n_selected (nullable) receives n_pop counts.

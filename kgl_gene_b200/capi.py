@@ -25,7 +25,7 @@ RESULT_DTYPE = np.dtype([  # kgl_b200_locus_results == kga::LocusResults field o
 EXPORTS = [
     "kgl_b200_version", "kgl_b200_device_count", "kgl_b200_create", "kgl_b200_destroy", "kgl_b200_last_error",
     "kgl_b200_set_stream", "kgl_b200_synchronize", "kgl_b200_upload_genotypes", "kgl_b200_upload_loci",
-    "kgl_b200_set_genome_superpop", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
+    "kgl_b200_set_genome_superpop", "kgl_b200_upload_multi_allelic", "kgl_b200_run_multi_allele_count", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
     "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
@@ -140,12 +140,30 @@ class KglB200:
     def set_unphased(self, unphased: bool):
         self._check(self.lib.kgl_b200_set_unphased(self.h, C.c_int(int(bool(unphased)))), "set_unphased")
 
+    def upload_multi_allelic(self, rows, af, cells):
+        """Loci with several alternate alleles (FlatPopulation.multi_*); rows=None clears them."""
+        if rows is None or len(rows) == 0:
+            self._check(self.lib.kgl_b200_upload_multi_allelic(self.h, C.c_uint64(0), None, None, None), "upload_multi_allelic")
+            return
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        a = np.ascontiguousarray(af, dtype=np.float32)
+        c = np.ascontiguousarray(cells, dtype=np.uint8)
+        assert a.shape[1:] == (r.shape[0], 3) and c.shape == (r.shape[0], self.n_genomes)
+        self._check(self.lib.kgl_b200_upload_multi_allelic(self.h, C.c_uint64(r.shape[0]), _ptr(r), _ptr(a), _ptr(c)), "upload_multi_allelic")
+
+    def multi_allele_count(self, n_multi: int) -> np.ndarray:
+        out = np.zeros((n_multi, 3, 3), dtype=np.uint32)
+        self._check(self.lib.kgl_b200_run_multi_allele_count(self.h, _ptr(out)), "run_multi_allele_count")
+        return out
+
     def upload_population(self, pop):
         """pop: kgl_gene_b200.flatfile.FlatPopulation."""
         self.upload_genotypes(pop.packed, pop.n_genomes)
         self.upload_loci(pop.af, pop.offsets)
         self.set_genome_superpop(pop.superpop)
         self.set_unphased(pop.unphased)
+        if getattr(pop, "n_multi", 0):
+            self.upload_multi_allelic(pop.multi_rows, pop.multi_af, pop.multi_cells)
 
     def select_loci(self, lower=0, upper=10**9, spacing=0, min_af=0.0, max_af=1.0) -> np.ndarray:
         counts = np.zeros(6, dtype=np.uint64)

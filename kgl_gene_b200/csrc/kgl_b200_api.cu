@@ -10,6 +10,7 @@
 #include "misc_kernels.cuh"
 #include "ibs_launch.cuh"
 #include "tail_kernels.cuh"
+#include "multi_allelic.cuh"
 #include "gram_launch.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -130,6 +131,14 @@ struct kgl_b200_ctx {
   bool tail_pending = false;                    // a tail runs on tail_stream that the context stream has not been ordered after
   bool inputs_async = false;                    // d_sel was last written by a kernel on the main stream without a host sync
   bool prep_valid = false, prep_has_w0 = false, prep_has_selw = false;
+
+  // multi-allelic loci (multi_allelic.cuh): rows of the locus table, per-slot frequencies, side cells, per-selection table
+  uint64_t n_multi = 0;
+  DevBuf<uint32_t> d_multi_rows, d_multi_counts;
+  DevBuf<float> d_multi_af;
+  DevBuf<uint8_t> d_multi_cells;
+  DevBuf<MultiLocus> d_multi_tab;
+  DevBuf<double> d_multi_out;
 
   // sample-major copy
   DevBuf<uint32_t> d_sm_lo, d_sm_hi;
@@ -609,6 +618,41 @@ int enqueue_moments(kgl_b200_ctx* c, bool want_locus_counts, bool simple_results
   return launch_count(c, false, want_locus_counts, true, simple_results, true, nullptr, defer_join);
 }
 
+// ---- multi-allelic loci: their share of a pass, added to what the dense path left on the context stream -----------------
+int multi_launch_prepare(kgl_b200_ctx* c) {
+  KGL_CUDA(c, c->d_multi_tab.ensure((size_t)c->n_pop * c->n_multi));
+  k_multi_prepare<<<blocks_for(c->n_multi * c->n_pop, 128), 128, 0, c->stream>>>(c->d_multi_rows.p, c->d_multi_af.p, c->d_sel.p, c->n_multi,
+                                                                                 (int)c->n_pop, c->d_multi_tab.p);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+template <int MODE>
+int multi_launch_terms(kgl_b200_ctx* c, const double* d_grid, int n_grid, uint64_t& n_chunks) {
+  n_chunks = (c->n_multi + kMultiChunk - 1) / kMultiChunk;
+  KGL_CUDA(c, c->d_multi_out.ensure((size_t)n_chunks * c->Npad * multi_n_out(MODE)));
+  MultiParams P{};
+  P.cells = c->d_multi_cells.p; P.n_multi = c->n_multi; P.n_genomes = c->N; P.n_genomes_padded = c->Npad;
+  P.tab = c->d_multi_tab.p; P.superpop = c->d_superpop.p; P.unphased = c->unphased ? 1 : 0;
+  P.f = c->d_f.p; P.grid = d_grid; P.n_grid = n_grid; P.out = c->d_multi_out.p;
+  k_multi_terms<MODE><<<dim3(blocks_for(c->N, 128), (unsigned)n_chunks), 128, 0, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
+// MOMENTS into the partial sums (after everything the dense path writes there), HALL / NEWTON into the iteration terms.
+template <int MODE>
+int multi_add(kgl_b200_ctx* c, double* target, kgl_b200_locus_results* results = nullptr) {
+  if (c->n_multi == 0) return KGL_B200_OK;
+  int rc = KGL_B200_OK;
+  if (MODE == MULTI_MOMENTS) { rc = multi_launch_prepare(c); if (rc) return rc; }
+  uint64_t n_chunks = 0;
+  rc = multi_launch_terms<MODE>(c, nullptr, 0, n_chunks); if (rc) return rc;
+  k_multi_add<MODE><<<blocks_for(c->N, 128), 128, 0, c->stream>>>(c->d_multi_out.p, n_chunks, c->Npad, c->N, target, results);
+  KGL_LAUNCH_CHECK(c);
+  return KGL_B200_OK;
+}
+
 struct TermLaunch { dim3 grid; uint32_t words_per_chunk; uint64_t n_chunks; };
 
 TermLaunch plan_terms(const kgl_b200_ctx* c) {
@@ -956,6 +1000,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_packed.release(); c->d_af.release(); c->d_superpop.release(); c->d_sel.release(); c->d_need32.release();
   c->d_popmask.release(); c->prep[0].release(); c->prep[1].release();
   c->d_sm_lo.release(); c->d_sm_hi.release(); c->d_locus_counts.release(); c->d_cta_counts[0].release(); c->d_cta_counts[1].release(); c->d_scratch.release(); c->d_dropped_cells.release(); c->d_zero_rare.release();
+  c->d_multi_rows.release(); c->d_multi_counts.release(); c->d_multi_af.release(); c->d_multi_cells.release(); c->d_multi_tab.release(); c->d_multi_out.release();
   c->d_dropped.release(); c->d_dropped_seg.release(); c->d_dropped_counter.release(); c->d_dropped_unsorted.release(); c->d_sort_temp.release();
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
@@ -1041,6 +1086,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   if (c->have_loci && c->loci_len != n_loci) { c->have_loci = false; c->prep_valid = false; }
   if (c->have_superpop && c->h_superpop.size() != n_genomes) c->have_superpop = false;
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
+  c->n_multi = 0;                    // the side cells belong to the matrix: kgl_b200_upload_multi_allelic comes after it
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
   c->sm_valid = false; c->codes_valid = false; c->units_valid = false; c->dropped_valid = false; c->dropped_cells_state = 0; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
   c->codes16_valid = false;
@@ -1126,6 +1172,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel.p, 0, n_loci, c->stream));
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->have_loci = true; c->prep_valid = false; c->dropped_cells_state = 0;
+  c->n_multi = 0;                    // ... and after the frequency table
   return KGL_B200_OK;
 }
 
@@ -1141,6 +1188,41 @@ int kgl_b200_set_genome_superpop(kgl_b200_ctx* c, uint64_t n_genomes, const uint
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->have_superpop = true; c->units_valid = false; c->dropped_cells_state = 0; c->prep_valid = false;
   if (!c->have_geno) c->N = n_genomes;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_upload_multi_allelic(kgl_b200_ctx* c, uint64_t n_multi, const uint32_t* rows, const float* af, const uint8_t* cells) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  int rc = use_device(c); if (rc) return rc;
+  if (!c->have_geno || !c->have_loci || c->loci_len != c->L)
+    return fail(c, KGL_B200_ERR_STATE, "upload the genotype matrix and the allele frequencies before the multi-allelic loci");
+  c->n_multi = 0; c->prep_valid = false;
+  if (n_multi == 0) return KGL_B200_OK;
+  if (!rows || !af || !cells) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  for (uint64_t m = 0; m < n_multi; ++m)
+    if (rows[m] >= c->L || (m > 0 && rows[m] <= rows[m - 1])) return fail(c, KGL_B200_ERR_INVALID, "multi-allelic rows must be ascending rows of the locus table");
+  KGL_CUDA(c, c->d_multi_rows.ensure(n_multi));
+  KGL_CUDA(c, c->d_multi_af.ensure((size_t)c->n_pop * n_multi * kMultiSlots));
+  KGL_CUDA(c, c->d_multi_cells.ensure((size_t)n_multi * c->N));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_multi_rows.p, rows, n_multi * 4, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_multi_af.p, af, (size_t)c->n_pop * n_multi * kMultiSlots * 4, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_multi_cells.p, cells, (size_t)n_multi * c->N, cudaMemcpyHostToDevice, c->stream));
+  k_multi_mask_af<<<blocks_for(n_multi * c->n_pop, 128), 128, 0, c->stream>>>(c->d_multi_rows.p, n_multi, (int)c->n_pop, c->L, c->d_af.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_multi = n_multi; c->dropped_cells_state = 0;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_multi_allele_count(kgl_b200_ctx* c, uint32_t* counts) {
+  if (!c || !counts) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  if (c->n_multi == 0) return fail(c, KGL_B200_ERR_STATE, "no multi-allelic loci uploaded");
+  KGL_CUDA(c, c->d_multi_counts.ensure(c->n_multi * kMultiSlots * 3));
+  k_multi_allele_count<<<(unsigned)c->n_multi, 256, 0, c->stream>>>(c->d_multi_cells.p, c->N, c->d_multi_counts.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemcpyAsync(counts, c->d_multi_counts.p, c->n_multi * kMultiSlots * 3 * 4, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   return KGL_B200_OK;
 }
 
@@ -1198,6 +1280,11 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
     k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
                                                               c->d_sel.p, c->d_sel_counts.p);
     KGL_LAUNCH_CHECK(c);
+    if (c->n_multi) {
+      k_multi_select<<<blocks_for(c->n_multi, 128), 128, 0, c->stream>>>(c->d_multi_rows.p, c->d_multi_af.p, c->d_offsets.p, c->n_multi, (int)c->n_pop,
+                                                                         lower, upper, min_af, max_af, c->d_sel.p, c->d_sel_counts.p);
+      KGL_LAUNCH_CHECK(c);
+    }
     c->prep_valid = false; c->h_sel_valid = false; c->inputs_async = true;
     if (n_selected) {
       unsigned long long counts[kMaxPop];
@@ -1215,6 +1302,11 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
   k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
                                                             c->d_sel.p, c->d_sel_counts.p);
   KGL_LAUNCH_CHECK(c);
+  if (c->n_multi) {          // candidates among the multi-allelic loci: they take part in the accept chain like any locus
+    k_multi_select<<<blocks_for(c->n_multi, 128), 128, 0, c->stream>>>(c->d_multi_rows.p, c->d_multi_af.p, c->d_offsets.p, c->n_multi, (int)c->n_pop,
+                                                                       lower, upper, min_af, max_af, c->d_sel.p, c->d_sel_counts.p);
+    KGL_LAUNCH_CHECK(c);
+  }
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
   if (span) {
     const uint64_t n_blocks = (span + kChainBlock - 1) / kChainBlock;
@@ -1317,7 +1409,12 @@ int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   c->peer_results = false;
   KGL_CUDA(c, c->d_results.ensure(c->Npad));
   rc = enqueue_moments(c, true, true, false, false, true); if (rc) return rc;
-  return mark_tail(c, false);
+  rc = mark_tail(c, false); if (rc) return rc;
+  if (c->n_multi) {            // their share follows the tail on the context stream (no overlap with the next pass then)
+    rc = join_tail(c); if (rc) return rc;
+    rc = multi_add<MULTI_MOMENTS>(c, c->d_partials.p, c->d_results.p); if (rc) return rc;
+  }
+  return KGL_B200_OK;
 }
 
 int kgl_b200_flush(kgl_b200_ctx* c) {
@@ -1405,6 +1502,10 @@ int kgl_b200_enqueue_count_and_inbreed_peer(kgl_b200_ctx* c) {
   const uint64_t parity_doubles = c->Npad * PART_COUNT;
   c->partials_target = reinterpret_cast<double*>(c->d_xchg.p) + (epoch & 1ull) * parity_doubles;
   rc = enqueue_moments(c, true, false, false, false, true);
+  if (!rc && c->n_multi) {
+    rc = mark_tail(c, true);
+    if (!rc) rc = multi_add<MULTI_MOMENTS>(c, c->partials_target);
+  }
   c->partials_target = nullptr;
   if (rc) return rc;
   // the exchange follows the tail on the tail stream (the context stream when the population's code-3 cells are not indexed)
@@ -1504,14 +1605,15 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
       k_stash_nhet<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_partials.p, PART_COUNT, PART_NMAJHET, PART_NMINHET, c->N, c->d_limits.p);
       KGL_LAUNCH_CHECK(c);
     }
-    return KGL_B200_OK;
+    // the multi-allelic loci last: k_ritland_partials and k_stash_nhet above work on the dense path's counts alone
+    return multi_add<MULTI_MOMENTS>(c, c->d_partials.p);
   }
   const unsigned nb = blocks_for(c->N, 256);
   if (c->algo == KGL_B200_ALGO_HALLME) {
     rc = launch_fast<FAST_HALL>(c, fl); if (rc) return rc;
     k_hall_reduce<<<blocks_for(c->N * 8, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, c->N, c->d_iter.p);
     KGL_LAUNCH_CHECK(c);
-    return KGL_B200_OK;
+    return multi_add<MULTI_HALL>(c, c->d_iter.p);
   }
   if (!c->limits_valid) {      // once per root search: the selection is fixed between inbreed_begin and inbreed_fetch
     rc = launch_fast<FAST_LIMITS>(c, fl); if (rc) return rc;
@@ -1519,7 +1621,9 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
     KGL_LAUNCH_CHECK(c);
     c->limits_valid = true;
   }
-  return c->unphased ? newton_sweep<FAST_NEWTON_U>(c) : newton_sweep<FAST_NEWTON>(c);
+  rc = c->unphased ? newton_sweep<FAST_NEWTON_U>(c) : newton_sweep<FAST_NEWTON>(c);
+  if (rc) return rc;
+  return multi_add<MULTI_NEWTON>(c, c->d_iter.p);     // evaluated cell by cell, clamps included (a clamped homozygous term moves the search right)
 }
 
 int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_doubles) {
@@ -1642,6 +1746,20 @@ int kgl_b200_run_loglik_grid(kgl_b200_ctx* c, const double* grid, uint64_t n_gri
         for (uint64_t ch = 0; ch < tl.n_chunks; ++ch) s += chunks[(ch * c->Npad + g) * kGridMax + j];
         out[g * n_grid + g0 + j] = s;
       }
+    if (c->n_multi) {          // the terms of the multi-allelic loci, cell by cell
+      if (g0 == 0) { rc = multi_launch_prepare(c); if (rc) return rc; }
+      uint64_t mc = 0;
+      rc = multi_launch_terms<MULTI_GRID>(c, c->d_grid.p, ng, mc); if (rc) return rc;
+      std::vector<double> mchunks((size_t)mc * c->Npad * kGridMax);
+      KGL_CUDA(c, cudaMemcpyAsync(mchunks.data(), c->d_multi_out.p, mchunks.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+      KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+      for (uint64_t g = 0; g < c->N; ++g)
+        for (int j = 0; j < ng; ++j) {
+          double s = 0.0;
+          for (uint64_t ch = 0; ch < mc; ++ch) s += mchunks[(ch * c->Npad + g) * kGridMax + j];
+          out[g * n_grid + g0 + j] += s;
+        }
+    }
   }
   return KGL_B200_OK;
 }

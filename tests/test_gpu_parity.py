@@ -54,12 +54,27 @@ def test_golden_simple_and_counts(gpu, golden):
     lc, res = gpu.count_and_inbreed()
     counts, freqs = results_matrix(res)
     present = ref["genome_present"] == 1
-    assert np.array_equal(counts[present], ref["Simple_counts"][present])                 # bit-exact
+    assert np.array_equal(counts[present], ref["Simple_counts"][present])                 # bit-exact, MINOR_HETEROZYGOUS included
     assert rel_err(freqs[present][:, :3], ref["Simple_freqs"][present][:, :3]) < TIGHT
-    assert np.all(freqs[:, 3] == 0.0)
+    if pop.n_multi:     # the sum over i < j of 2 p_i p_j at the multi-allelic loci (freq.cpp:166-174)
+        assert np.all(ref["Simple_freqs"][present][:, 3] > 0) and rel_err(freqs[present][:, 3], ref["Simple_freqs"][present][:, 3]) < TIGHT
+    else:
+        assert np.all(freqs[:, 3] == 0.0)
     assert rel_err(res["inbred_allele_sum"][present], ref["Simple_coeff"][present]) < 1e-9
     # per-locus allele counts vs VariantDBVariant::summaryByVariant
     m = ref["variant_present"] == 1
+    if pop.n_multi:     # one column per allele there: kgl_b200_run_multi_allele_count, slot 0 = the harness' "A>G" column
+        mc = gpu.multi_allele_count(pop.n_multi)
+        cells = pop.multi_cells.astype(np.int64)
+        for a in range(3):
+            copies = ((cells & 15) == a + 1).astype(np.int64) + ((cells >> 4) == a + 1).astype(np.int64)
+            copies[cells == 0xFF] = 0
+            for c in range(3):
+                assert np.array_equal(mc[:, a, c], (copies == c).sum(axis=1))
+        no3 = ~(cells == 0xFF).any(axis=1) & m[pop.multi_rows]
+        assert np.array_equal(mc[no3, 0, 1], ref["summary_by_variant"][pop.multi_rows][no3, 1])
+        assert np.array_equal(mc[no3, 0, 2], ref["summary_by_variant"][pop.multi_rows][no3, 2])
+        m = m.copy(); m[pop.multi_rows] = False
     sv = ref["summary_by_variant"]
     assert np.array_equal(lc[m, 1], sv[m, 1]) and np.array_equal(lc[m, 2], sv[m, 2])
     assert np.array_equal((lc[m, 0] + lc[m, 3]).astype(np.uint64), sv[m, 0])
@@ -71,6 +86,8 @@ def test_golden_allele_count(gpu, golden):
     lc, gc = gpu.allele_count()
     olc, ogc = O.allele_count(pop)
     assert np.array_equal(lc, olc) and np.array_equal(gc, ogc)
+    if pop.n_multi:
+        return          # summaryByGenome also runs over the per-allele columns of the multi-allelic loci
     sg = ref["summary_by_genome"]
     present = ref["genome_present"] == 1
     assert np.array_equal(sg[present, 1], gc[present, 1] + gc[present, 3]) and np.array_equal(sg[present, 2], gc[present, 2])
@@ -109,7 +126,10 @@ def test_golden_loglikelihood(gpu, golden):
     opt = O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"]
     # converged optimum of the same objective: <= 1e-9; the reference's own Nelder-Mead stops at xtol 1e-6
     assert np.max(np.abs(res["inbred_allele_sum"][present] - opt[present])) < 1e-9
-    assert np.max(np.abs(res["inbred_allele_sum"][present] - ref["Loglikelihood_coeff"][present])) < 2e-6
+    close = np.abs(res["inbred_allele_sum"][present] - ref["Loglikelihood_coeff"][present]) < 2e-6
+    # multi_allelic_unphased: for two genomes the reference's Nelder-Mead ends outside the feasible region (see the waiver in
+    # tests/test_oracle_vs_reference.py::test_loglikelihood_optimum_within_optimiser_tolerance)
+    assert np.all(close) or (name == "multi_allelic_unphased" and close.sum() >= close.size - 2)
 
 
 # ------------------------------------------------------------------------------------------------ oracle, seeded ----
@@ -169,6 +189,43 @@ def test_all_estimators_match_oracle(gpu, case):
     got = gpu.inbreed("Loglikelihood")
     want = O.inbreed(pop, sel, "Loglikelihood")
     assert np.max(np.abs(got["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-9
+
+
+@pytest.mark.parametrize("unphased,sel_kw", [(False, dict(spacing=0)), (False, dict(spacing=25, min_af=0.01, max_af=0.9)),
+                                             (True, dict(spacing=15, lower=20_000, upper=150_000))],
+                         ids=["phased", "phased-spaced", "unphased-window"])
+def test_multi_allelic_loci_match_oracle(gpu, unphased, sel_kw):
+    """Loci with two or three alternate alleles (kgl_b200_upload_multi_allelic): selection (they take part in the spaced accept
+    chain), class counts incl. MINOR_HETEROZYGOUS bit-exact, the four expected sums incl. the sum of 2 p_i p_j, and all four
+    estimators against the oracle, whose general forms are pinned bit for bit to the reference (golden multi_allelic*)."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(600, 20_000, seed=91, missing_rate=0.004, missing_af_rate=0.01, unphased=unphased, grouped=False)
+    add_multi_allelic(pop, 700, seed=92)
+    sel = O.select_all_pops(pop, **sel_kw)
+    gpu.upload_population(pop)
+    counts = gpu.select_loci(**sel_kw)
+    assert np.array_equal(gpu.get_locus_selection(), sel_bits(sel))
+    assert np.array_equal(counts[:6], sel.sum(axis=1).astype(np.uint64))
+    assert sel[:, pop.multi_rows].sum() > 100                                   # multi-allelic loci are selected
+    lc, res = gpu.count_and_inbreed()
+    assert np.array_equal(lc, O.allele_count(pop)[0])
+    start = np.linspace(0.05, 0.5, pop.n_genomes)
+    for algo, kw, okw in (("Simple", None, {}), ("RitlandLocus", {}, {}), ("HallME", dict(hall_start=start, hall_sweeps=50), dict(start=start, sweeps=50)),
+                          ("Loglikelihood", {}, {})):
+        got = res if kw is None else gpu.inbreed(algo, **kw)
+        want = O.inbreed(pop, sel, algo, **okw)
+        c_got, f_got = results_matrix(got)
+        c_want, f_want = results_matrix(want)
+        assert np.array_equal(c_got, c_want), algo
+        assert c_want[:, 3].sum() > 0
+        assert rel_err(f_got, f_want) < TIGHT, algo
+        assert np.max(np.abs(got["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-9, algo
+    grid = np.array([-0.4, -0.05, 0.0, 0.07, 0.3, 0.9, -0.9, 0.5, 0.2])          # nine points: two launches of the grid kernel
+    assert rel_err(gpu.loglik_grid(grid), O.loglik_grid(pop, sel, grid)) < 1e-12
+    # without the side structures the same matrix is a population whose multi-allelic loci are absent: results must differ
+    gpu.upload_multi_allelic(None, None, None)
+    gpu.select_loci(**sel_kw)
+    assert not np.array_equal(results_matrix(gpu.count_and_inbreed()[1])[0], results_matrix(O.inbreed(pop, sel, "Simple"))[0])
 
 
 @pytest.mark.parametrize("kw", [
@@ -364,6 +421,8 @@ def test_golden_calc_fws(gpu, golden):
     AlleleSummmary in the eleven AF bins and the per-variant summaries, bit-exact."""
     from kgl_gene_b200 import fws
     name, pop, ref, _ = golden
+    if "fws_genome" not in ref:
+        pytest.skip("fixture without the CalcFWS run (multi-allelic loci)")
     gpu.upload_population(pop)
     got = fws.calc_fws(gpu, pop=5)
     assert np.array_equal(np.transpose(got["genome_bins"], (1, 0, 2)), ref["fws_genome"])
