@@ -140,7 +140,10 @@ bool kga::InbreedB200Analysis::iterationAnalysis() {
 
   }
 
+  // One walk over the variant database and ONE upload per iteration, shared by every parameter block (the reference walks
+  // the database once per genome, locus and block): everything after it works on flat arrays that are resident on the GPU.
   bool ok = true;
+  bool resident = false;
   for (auto& param_output : parameter_output_vector_) {
 
     // Set the allele frequency source for this population.
@@ -151,7 +154,13 @@ bool kga::InbreedB200Analysis::iterationAnalysis() {
 
     } else {
 
-      ok = populationInbreeding(unphased_population_, *diploid_population_, *genealogy_data_, diploid_is_unphased_, param_output) and ok;
+      if (not resident) {
+
+        if (not uploadPopulation(unphased_population_, *diploid_population_, *genealogy_data_, diploid_is_unphased_)) { ok = false; break; }
+        resident = true;
+
+      }
+      ok = windowLoop(unphased_population_, param_output) and ok;
 
     }
 
@@ -160,8 +169,52 @@ bool kga::InbreedB200Analysis::iterationAnalysis() {
   // Clear the data structures.
   diploid_population_ = nullptr;
   unphased_population_ = nullptr;
+  flat_.reset();
 
   return ok;
+
+}
+
+bool kga::InbreedB200Analysis::check(int rc, const char* what) {
+
+  if (rc != KGL_B200_OK) ExecEnv::log().error("InbreedB200Analysis; {} failed [{}]: {}", what, rc, kgl_b200_last_error(context_));
+  return rc == KGL_B200_OK;
+
+}
+
+// Flattens the populations (host/kgl_b200_flatten.cpp) and makes them resident on the device.
+bool kga::InbreedB200Analysis::uploadPopulation(const std::shared_ptr<const PopulationDB>& unphased_ptr,
+                                                const PopulationDB& diploid_population,
+                                                const HsGenomeGenealogyData& ped_data,
+                                                bool unphased_diploid) {
+
+  if (not ensureContext()) return false;
+  flat_.reset();
+  auto super_population = [&ped_data](const GenomeId_t& genome_id) -> std::optional<std::string> {
+    auto record_opt = ped_data.getGenomeGenealogyRecord(genome_id);
+    if (not record_opt) return std::nullopt;
+    return record_opt.value().superPopulation();
+  };
+  auto flat_opt = b200::PopulationFlattener::flatten(diploid_population, *unphased_ptr, super_population, unphased_diploid);
+  if (not flat_opt) return false;
+  flat_ = std::make_unique<b200::FlatContig>(std::move(flat_opt.value()));
+  const b200::FlatContig& flat = *flat_;
+  if (flat.nGenomes() == 0 or flat.nLoci() == 0) {
+
+    ExecEnv::log().warn("InbreedB200Analysis::uploadPopulation; contig: {} has no genomes or no loci to analyse", flat.contig_id);
+    return true;
+
+  }
+
+  if (not check(kgl_b200_upload_genotypes(context_, flat.nGenomes(), flat.nLoci(), flat.row_bytes, flat.packed.data()), "upload_genotypes")) return false;
+  if (not check(kgl_b200_upload_loci(context_, flat.nLoci(), b200::kSuperPopCount, flat.af.data(), flat.offsets.data()), "upload_loci")) return false;
+  if (not check(kgl_b200_set_genome_superpop(context_, flat.nGenomes(), flat.superpop.data()), "set_genome_superpop")) return false;
+  if (not check(kgl_b200_set_unphased(context_, flat.unphased ? 1 : 0), "set_unphased")) return false;
+  if (not check(kgl_b200_upload_multi_allelic(context_, flat.nMulti(), flat.multi_rows.data(), flat.multi_af.data(), flat.multi_cells.data()),
+                "upload_multi_allelic")) return false;
+  ExecEnv::log().info("InbreedB200Analysis; contig: {}, {} genomes x {} loci resident on the device ({} multi-allelic loci)", flat.contig_id,
+                      flat.nGenomes(), flat.nLoci(), flat.nMulti());
+  return true;
 
 }
 
@@ -171,44 +224,28 @@ bool kga::InbreedB200Analysis::populationInbreeding(const std::shared_ptr<const 
                                                     bool unphased_diploid,
                                                     InbreedParamOutput& param_output) {
 
-  if (not ensureContext()) return false;
+  if (not uploadPopulation(unphased_ptr, diploid_population, ped_data, unphased_diploid)) return false;
+  return windowLoop(unphased_ptr, param_output);
+
+}
+
+// The window loop of InbreedingAnalysis::populationInbreeding (kga_analysis_inbreed_diploid.cpp:45-75) over the resident
+// population: windows are defined on the "ALL" super-population by the reference's own RetrieveLociiVector (host, once per
+// window); every super-population then selects its loci inside the window on the C ABI.
+bool kga::InbreedB200Analysis::windowLoop(const std::shared_ptr<const PopulationDB>& unphased_ptr, InbreedParamOutput& param_output) {
+
+  if (not flat_) return false;
+  const b200::FlatContig& flat = *flat_;
+  if (flat.nGenomes() == 0 or flat.nLoci() == 0) return true;
 
   auto algorithm_opt = algorithmCode(param_output.getParameters().inbreedingAlgorthim());
   if (not algorithm_opt) {
 
-    ExecEnv::log().error("InbreedB200Analysis::populationInbreeding, Inbreeding algorithm not found: {}", param_output.getParameters().inbreedingAlgorthim());
+    ExecEnv::log().error("InbreedB200Analysis::windowLoop, Inbreeding algorithm not found: {}", param_output.getParameters().inbreedingAlgorthim());
     return false;
 
   }
 
-  // One walk over the variant database; everything after it works on flat arrays.
-  auto super_population = [&ped_data](const GenomeId_t& genome_id) -> std::optional<std::string> {
-    auto record_opt = ped_data.getGenomeGenealogyRecord(genome_id);
-    if (not record_opt) return std::nullopt;
-    return record_opt.value().superPopulation();
-  };
-  auto flat_opt = b200::PopulationFlattener::flatten(diploid_population, *unphased_ptr, super_population, unphased_diploid);
-  if (not flat_opt) return false;
-  const b200::FlatContig& flat = flat_opt.value();
-  if (flat.nGenomes() == 0 or flat.nLoci() == 0) {
-
-    ExecEnv::log().warn("InbreedB200Analysis::populationInbreeding; contig: {} has no genomes or no loci to analyse", flat.contig_id);
-    return true;
-
-  }
-
-  auto check = [this](int rc, const char* what) {
-    if (rc != KGL_B200_OK) ExecEnv::log().error("InbreedB200Analysis; {} failed [{}]: {}", what, rc, kgl_b200_last_error(context_));
-    return rc == KGL_B200_OK;
-  };
-  if (not check(kgl_b200_upload_genotypes(context_, flat.nGenomes(), flat.nLoci(), flat.row_bytes, flat.packed.data()), "upload_genotypes")) return false;
-  if (not check(kgl_b200_upload_loci(context_, flat.nLoci(), b200::kSuperPopCount, flat.af.data(), flat.offsets.data()), "upload_loci")) return false;
-  if (not check(kgl_b200_set_genome_superpop(context_, flat.nGenomes(), flat.superpop.data()), "set_genome_superpop")) return false;
-  if (not check(kgl_b200_set_unphased(context_, flat.unphased ? 1 : 0), "set_unphased")) return false;
-
-  // The window loop of InbreedingAnalysis::populationInbreeding (kga_analysis_inbreed_diploid.cpp:45-75): windows are defined
-  // on the "ALL" super-population by the reference's own RetrieveLociiVector (host, once per window); every
-  // super-population then selects its loci inside the window on the C ABI.
   auto const& [af_genome_id, af_genome_ptr] = *unphased_ptr->getMap().begin();
   auto const& [contig_id, contig_ptr] = *af_genome_ptr->getMap().begin();
 

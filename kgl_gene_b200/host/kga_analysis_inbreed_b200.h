@@ -42,8 +42,15 @@ public:
   [[nodiscard]] bool iterationAnalysis() override;
   [[nodiscard]] bool finalizeAnalysis() override;
 
-  // The window loop of InbreedingAnalysis::populationInbreeding (kga_analysis_inbreed_diploid.cpp:18-79) on the device.
-  // Public so that a host program that already holds the populations and the PED data can call it directly.
+  // InbreedingAnalysis::populationInbreeding (kga_analysis_inbreed_diploid.cpp:18-79) on the device: uploadPopulation (one
+  // flatten + one upload) followed by windowLoop. iterationAnalysis calls the two halves itself, so that every parameter block
+  // of an iteration works on the same resident population. Public so that a host program that already holds the populations
+  // and the PED data can call them directly.
+  [[nodiscard]] bool uploadPopulation(const std::shared_ptr<const PopulationDB>& unphased_ptr,
+                                      const PopulationDB& diploid_population,
+                                      const HsGenomeGenealogyData& ped_data,
+                                      bool unphased_diploid);
+  [[nodiscard]] bool windowLoop(const std::shared_ptr<const PopulationDB>& unphased_ptr, InbreedParamOutput& param_output);
   [[nodiscard]] bool populationInbreeding(const std::shared_ptr<const PopulationDB>& unphased_ptr,
                                           const PopulationDB& diploid_population,
                                           const HsGenomeGenealogyData& ped_data,
@@ -60,8 +67,10 @@ private:
   bool diploid_is_unphased_{false};
   int device_{0};
   kgl_b200_ctx* context_{nullptr};
+  std::unique_ptr<b200::FlatContig> flat_;               // the population that is resident on the device
 
   [[nodiscard]] bool ensureContext();
+  [[nodiscard]] bool check(int rc, const char* what);
   [[nodiscard]] bool writeResults();
 
 };

@@ -59,40 +59,69 @@ std::optional<b200::FlatContig> b200::PopulationFlattener::flatten(const Populat
   flat.contig_id = contig_id;
   flat.unphased = unphased_population;
 
-  // ---- locus table: one row per AF offset with exactly one distinct alt allele -----------------------------------------
-  std::vector<std::shared_ptr<const Variant>> locus_allele;
+  // ---- locus table: one row per AF offset; offsets with several distinct alt alleles also get the side structures ---------
+  constexpr size_t kSlots = 3;
+  std::vector<std::shared_ptr<const Variant>> locus_allele;            // the first (or only) allele of every row
   std::vector<std::array<float, kSuperPopCount>> locus_af;
+  std::vector<int64_t> multi_of;                                       // row -> index into the multi-allelic tables, -1
+  std::vector<std::vector<std::shared_ptr<const Variant>>> multi_alleles;
+  std::vector<std::array<float, kSuperPopCount * kSlots>> multi_af_rows;
+  const float kNone = std::numeric_limits<float>::quiet_NaN();
   for (auto const& [offset, offset_ptr] : af_contig_ptr->getMap()) {
     const OffsetDBArray& variants = offset_ptr->getVariantArray();
     if (variants.empty()) continue;
-    bool multi = false;
-    for (auto const& v : variants)
-      if (!analogous(*v, *variants.front())) { multi = true; break; }
-    if (multi) { ++flat.multi_allelic_skipped; continue; }
+    // the distinct alleles, in the order of the variant array (AlleleFreqVector's duplicate test, freq.cpp:31-42)
+    std::vector<std::shared_ptr<const Variant>> alleles;
+    for (auto const& v : variants) {
+      bool seen = false;
+      for (auto const& a : alleles) if (analogous(*v, *a)) { seen = true; break; }
+      if (not seen) alleles.push_back(v);
+    }
+    if (alleles.size() > kSlots) { ++flat.too_many_alleles_skipped; continue; }
     if (offset > std::numeric_limits<uint32_t>::max()) {
       ExecEnv::log().error("PopulationFlattener::flatten; offset {} does not fit 32 bits", offset);
       return std::nullopt;
     }
-    std::array<float, kSuperPopCount> row{};
-    for (size_t k = 0; k < kSuperPopCount; ++k) {
-      row[k] = std::numeric_limits<float>::quiet_NaN();
-      // AlleleFreqVector keeps the first analogous variant that HAS a value for the super-population (freq.cpp:24-52).
+    // AlleleFreqVector keeps, per allele, the first analogous variant that HAS a value for the super-population (freq.cpp:24-52).
+    auto allele_af = [&](const Variant& allele, size_t k) -> float {
       for (auto const& v : variants) {
+        if (not analogous(*v, allele)) continue;
         auto af_opt = FrequencyDatabaseRead::superPopFrequency(*v, kSuperPopCodes[k]);
-        if (af_opt) { row[k] = static_cast<float>(af_opt.value()); break; }   // stored as float by the parser: exact
+        if (af_opt) return static_cast<float>(af_opt.value());            // stored as float by the parser: exact
       }
+      return kNone;
+    };
+    std::array<float, kSuperPopCount> row{};
+    if (alleles.size() == 1) {
+      for (size_t k = 0; k < kSuperPopCount; ++k) row[k] = allele_af(*alleles.front(), k);
+      multi_of.push_back(-1);
+    } else {
+      std::array<float, kSuperPopCount * kSlots> mrow{};
+      mrow.fill(kNone);
+      for (size_t k = 0; k < kSuperPopCount; ++k)
+        for (size_t a = 0; a < alleles.size(); ++a) mrow[k * kSlots + a] = allele_af(*alleles[a], k);
+      row.fill(kNone);                                                 // the frequency table is not used at such a row
+      multi_of.push_back(static_cast<int64_t>(multi_alleles.size()));
+      flat.multi_rows.push_back(static_cast<uint32_t>(flat.offsets.size()));
+      multi_alleles.push_back(alleles);
+      multi_af_rows.push_back(mrow);
     }
     flat.offsets.push_back(static_cast<uint32_t>(offset));
-    locus_allele.push_back(variants.front());
+    locus_allele.push_back(alleles.front());
     locus_af.push_back(row);
   }
   const size_t L = flat.offsets.size();
+  const size_t M = flat.multi_rows.size();
   flat.af.resize(kSuperPopCount * L);
   for (size_t l = 0; l < L; ++l)
     for (size_t k = 0; k < kSuperPopCount; ++k) flat.af[k * L + l] = locus_af[l][k];
-  if (flat.multi_allelic_skipped > 0)
-    ExecEnv::log().warn("PopulationFlattener::flatten; contig: {}, {} multi-allelic offsets left out of the locus table", contig_id,
-                        flat.multi_allelic_skipped);
+  flat.multi_af.resize(kSuperPopCount * M * kSlots);
+  for (size_t m = 0; m < M; ++m)
+    for (size_t k = 0; k < kSuperPopCount; ++k)
+      for (size_t a = 0; a < kSlots; ++a) flat.multi_af[(k * M + m) * kSlots + a] = multi_af_rows[m][k * kSlots + a];
+  if (flat.too_many_alleles_skipped > 0)
+    ExecEnv::log().warn("PopulationFlattener::flatten; contig: {}, {} offsets with more than three alt alleles left out of the locus table",
+                        contig_id, flat.too_many_alleles_skipped);
 
   // ---- genome columns: genomes that have the contig, a PED record and a known super-population (diploid.cpp:121-140) -----
   std::vector<std::shared_ptr<const ContigDB>> genome_contig;
@@ -117,6 +146,7 @@ std::optional<b200::FlatContig> b200::PopulationFlattener::flatten(const Populat
   const size_t units = (N + 63) / 64;
   flat.row_bytes = 16 * units;
   flat.packed.assign(L * flat.row_bytes, 0);
+  flat.multi_cells.assign(M * N, 0);
   if (N == 0 || L == 0) return flat;
 
   // ---- genotype codes. A thread owns whole 64-genome units, so no two threads touch the same byte. -----------------------
@@ -139,6 +169,31 @@ std::optional<b200::FlatContig> b200::PopulationFlattener::flatten(const Populat
             if (v->isSNP()) snps.push_back(v.get());                        // the genome side is SNP filtered (freq.cpp:436)
           if (snps.empty()) continue;
           unsigned code = 3;
+          if (multi_of[l] >= 0) {
+            // several alt alleles: the side cell names the first and the second variant's allele (generateFrequencies looks the
+            // FRONT of the offset array up first, freq.cpp:462); 4 = not in the locus' list; 0xFF = more than two variants, or a
+            // same-allele pair whose phases contradict the population's phasing
+            auto const& alleles = multi_alleles[multi_of[l]];
+            auto slot_of = [&](const Variant& v) -> unsigned {
+              for (size_t a = 0; a < alleles.size(); ++a) if (analogous(v, *alleles[a])) return static_cast<unsigned>(a) + 1;
+              return 4;
+            };
+            unsigned cell = 0xFF;
+            if (snps.size() == 1) cell = slot_of(*snps.front());
+            else if (snps.size() == 2) {
+              const unsigned s1 = slot_of(*snps.front()), s2 = slot_of(*snps.back());
+              cell = s1 | (s2 << 4);
+              if (s1 == s2 && s1 != 4) {
+                const bool phased_pair = snps.front()->phaseId() != snps.back()->phaseId();
+                if (phased_pair == unphased_population) { cell = 0xFF; ++mixed; }
+              }
+            }
+            flat.multi_cells[static_cast<size_t>(multi_of[l]) * N + g] = static_cast<uint8_t>(cell);
+            uint8_t* unit3 = flat.packed.data() + l * flat.row_bytes + u * 16;
+            unit3[b >> 3] |= static_cast<uint8_t>(1u << (b & 7));
+            unit3[8 + (b >> 3)] |= static_cast<uint8_t>(1u << (b & 7));
+            continue;
+          }
           const Variant& allele = *locus_allele[l];
           if (analogous(*snps.front(), allele)) {
             if (snps.size() == 1) code = 1;

@@ -15,8 +15,10 @@
 //   2 variants, both analogous, same phase (unphased populations)  -> 2 with FlatContig::unphased set: the reference
 //                                                                     classifies these MINOR_HETEROZYGOUS
 //   anything else (first variant not in the AF list, second not found, more than 2 variants) -> 3 (dropped)
-// Offsets whose AF entry lists more than one distinct alt allele are not representable with one frequency per locus;
-// they are left out of the locus table and counted in FlatContig::multi_allelic_skipped.
+// Offsets whose AF entry lists several distinct alt alleles keep their row of the locus table (so that locus selection, the
+// spacing chain and the window counts see them, kga_analysis_inbreed_locus.cpp:21-72) with "no value" in the frequency table,
+// and are described by the side structures FlatContig::multi_* (include/kgl_b200.h, kgl_b200_upload_multi_allelic): per-allele
+// frequencies and one byte per genome naming the one or two alleles it carries. The matrix holds 0 / 3 there.
 #ifndef KGL_B200_FLATTEN_H
 #define KGL_B200_FLATTEN_H
 
@@ -44,11 +46,18 @@ struct FlatContig {
   std::vector<uint8_t> packed;                             // [n_loci][row_bytes]
   uint64_t row_bytes{0};
   bool unphased{false};
-  size_t multi_allelic_skipped{0};
+  // multi-allelic loci: rows of the locus table, per allele slot frequencies [kSuperPopCount][n_multi][3] (NaN = none), side
+  // cells [n_multi][n_genomes] (0 hom-ref; low nibble first variant's slot + 1, 4 = not in the list; high nibble the second
+  // variant's, 0 = none; 0xFF = more than two variants)
+  std::vector<uint32_t> multi_rows;
+  std::vector<float> multi_af;
+  std::vector<uint8_t> multi_cells;
+  size_t too_many_alleles_skipped{0};                      // offsets with more than three distinct alt alleles (not a SNP locus)
   size_t mixed_phase_cells{0};                             // cells whose phase pattern contradicts `unphased` (coded 3)
 
   [[nodiscard]] uint64_t nGenomes() const { return genome_ids.size(); }
   [[nodiscard]] uint64_t nLoci() const { return offsets.size(); }
+  [[nodiscard]] uint64_t nMulti() const { return multi_rows.size(); }
 };
 
 // genome id -> PED super-population code; nullopt = no PED record (genome is left out, as the reference does).

@@ -96,19 +96,26 @@ void run() {
   auto resources = std::make_shared<kgl::AnalysisResources>();
   resources->addResource(std::shared_ptr<const kgl::ResourceBase>(genealogy, static_cast<const GenealogyTypeTag*>(genealogy.get())));
 
-  // ---- one parameter block, the fields of kga_analysis_inbreed_args.h:164-172 ----------------------------
-  kgl::ParameterMap block;
-  block.insert("AnalysisType", "FALSE");
-  block.insert("OutputFile", "harness_out");
-  block.insert("Algorithm", g_opt.algorithm);
-  block.insert("MinAlleleFreq", g_opt.min_af);
-  block.insert("MaxAlleleFreq", g_opt.max_af);
-  block.insert("LowerWindow", g_opt.lower);
-  block.insert("UpperWindow", g_opt.upper);
-  block.insert("LociiCount", g_opt.count);
-  block.insert("SamplingDistance", g_opt.spacing);
+  // ---- parameter blocks, the fields of kga_analysis_inbreed_args.h:164-172; --algo A,B,C makes one block per algorithm (output
+  // harness_out.csv for a single algorithm, harness_out_<algorithm>.csv otherwise) -----------------------------------------
+  std::vector<std::string> algorithms;
+  { std::string t; for (char ch : g_opt.algorithm + ",") { if (ch == ',') { if (!t.empty()) algorithms.push_back(t); t.clear(); } else t += ch; } }
+  std::vector<kgl::ParameterMap> blocks;
+  for (auto const& algorithm : algorithms) {
+    kgl::ParameterMap block;
+    block.insert("AnalysisType", "FALSE");
+    block.insert("OutputFile", algorithms.size() == 1 ? std::string("harness_out") : "harness_out_" + algorithm);
+    block.insert("Algorithm", algorithm);
+    block.insert("MinAlleleFreq", g_opt.min_af);
+    block.insert("MaxAlleleFreq", g_opt.max_af);
+    block.insert("LowerWindow", g_opt.lower);
+    block.insert("UpperWindow", g_opt.upper);
+    block.insert("LociiCount", g_opt.count);
+    block.insert("SamplingDistance", g_opt.spacing);
+    blocks.push_back(block);
+  }
   kgl::ActiveParameterList parameters;
-  parameters.addNamedParameterVector(kgl::NamedParameterVector{"HarnessBlock", kgl::ParameterVector{block}});
+  parameters.addNamedParameterVector(kgl::NamedParameterVector{"HarnessBlock", kgl::ParameterVector{blocks}});
 
   const std::vector<std::shared_ptr<const kgl::DataDB>> data_files{built.diploid, built.af_population};
 
@@ -128,11 +135,13 @@ void run() {
     out.hdr.n_genomes = uint32_t(f.nGenomes()); out.hdr.n_loci = uint32_t(f.nLoci()); out.hdr.n_superpop = 6;
     out.hdr.row_bytes = uint32_t(f.row_bytes); out.hdr.flags = f.unphased ? kglflat::FLAG_UNPHASED : 0;
     out.offsets = f.offsets; out.af = f.af; out.superpop = f.superpop; out.packed = f.packed;
+    out.hdr.reserved[0] = uint32_t(f.nMulti());
+    out.multi_rows = f.multi_rows; out.multi_af = f.multi_af; out.multi_cells = f.multi_cells;
     kglflat::writeFlat(g_opt.work_dir + "/flattened.flat", out);
     std::ofstream ids(g_opt.work_dir + "/flattened_genomes.txt");
     for (auto const& id : f.genome_ids) ids << id << '\n';
-    std::fprintf(stderr, "[plugin] flattener: %zu genomes x %zu loci, %zu multi-allelic skipped, %zu mixed-phase cells\n",
-                 size_t(f.nGenomes()), size_t(f.nLoci()), f.multi_allelic_skipped, f.mixed_phase_cells);
+    std::fprintf(stderr, "[plugin] flattener: %zu genomes x %zu loci, %zu multi-allelic loci, %zu mixed-phase cells\n",
+                 size_t(f.nGenomes()), size_t(f.nLoci()), size_t(f.nMulti()), f.mixed_phase_cells);
   }
 
   if (g_opt.run_reference && !runAnalysis(kga::InbreedAnalysis::IDENT, parameters, resources, data_files)) g_exit_code = 4;

@@ -82,6 +82,47 @@ def test_plugin_csv_matches_reference_plugin(tmp_path, algo, rtol, atol):
 
 
 @needs_harness
+def test_flattener_emits_the_multi_allelic_side_structures(tmp_path):
+    """Offsets with several alt alleles in the AF population: the row stays in the locus table (frequency "no value", matrix
+    codes 0 / 3) and the side structures name every allele's frequencies and every genome's one or two alleles, bit for bit
+    what the reference containers were built from."""
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(77, 1200, seed=19, spectrum="sfs", missing_rate=0.01, missing_af_rate=0.03)
+    add_multi_allelic(pop, 140, seed=20)
+    work = run_harness(str(tmp_path), pop, "--no-reference", "--no-b200")
+    got = FlatPopulation.read(os.path.join(work, "flattened.flat"))
+    ids = [ln.strip() for ln in open(os.path.join(work, "flattened_genomes.txt"))]
+    cols = np.array([int(i[1:]) for i in ids])
+    assert np.array_equal(got.offsets, pop.offsets)
+    assert np.array_equal(got.af.view(np.uint32), pop.af.view(np.uint32))
+    assert np.array_equal(got.codes(), pop.codes()[:, cols])
+    assert np.array_equal(got.multi_rows, pop.multi_rows)
+    assert np.array_equal(got.multi_af.view(np.uint32), pop.multi_af.view(np.uint32))
+    assert np.array_equal(got.multi_cells, pop.multi_cells[:, cols])
+
+
+@needs_harness
+@pytest.mark.gpu
+def test_plugin_multi_allelic_contig_and_shared_upload(tmp_path):
+    """A contig with multi-allelic sites (normal for 1000 Genomes), three parameter blocks in one iteration: the drop-in
+    flattens and uploads ONCE (kga_analysis_inbreed_b200.cpp, iterationAnalysis) and every block's CSV equals the unmodified
+    reference analysis' -- spacing > 0, so a dropped multi-allelic locus would shift the whole accept chain."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(90, 4000, seed=31, spectrum="dense", missing_rate=0.01, grouped=False)
+    add_multi_allelic(pop, 400, seed=32)
+    work = run_harness(str(tmp_path), pop, "--algo", "Simple,RitlandLocus,Loglikelihood", "--spacing", "20", "--count", "600")
+    log = open(os.path.join(str(tmp_path), "harness.log")).read()
+    assert log.count("resident on the device") == 1 and "400 multi-allelic loci" in log
+    for algo, atol in (("Simple", 1e-9), ("RitlandLocus", 1e-9), ("Loglikelihood", 5e-6)):
+        h_ref, c_ref, r_ref = read_csv(os.path.join(work, "INBREED", f"harness_out_{algo}.csv"))
+        h_new, c_new, r_new = read_csv(os.path.join(work, "INBREED_B200", f"harness_out_{algo}.csv"))
+        assert h_ref == h_new and c_ref == c_new and len(c_ref) > 9 + 2 and sorted(r_ref) == sorted(r_new)
+        for g, (meta, vals) in r_ref.items():
+            assert np.allclose(r_new[g][1], vals, rtol=2e-6, atol=atol), (algo, g)
+
+
+@needs_harness
 @pytest.mark.gpu
 def test_plugin_unphased_population(tmp_path):
     from kgl_gene_b200.synth import make_population
