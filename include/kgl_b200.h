@@ -118,6 +118,18 @@ int kgl_b200_run_multi_allele_count(kgl_b200_ctx* ctx, uint32_t* counts);
 int kgl_b200_select_loci(kgl_b200_ctx* ctx, uint64_t lower, uint64_t upper, uint64_t spacing,
                          double min_af, double max_af, uint64_t* n_selected);
 int kgl_b200_set_locus_selection(kgl_b200_ctx* ctx, uint64_t n_loci, const uint8_t* selected);
+/* RetrieveLociiVector::getLociiCount (kga_analysis_inbreed_locus.cpp:159-183): how InbreedingAnalysis::populationInbreeding
+ * defines its windows (kga_analysis_inbreed_diploid.cpp:48-51,69-73). The first `count` loci of super-population `pop` that
+ * the accept rule of kgl_b200_select_loci takes from `lower` on: *n_found of them (<= count), *last_offset = offset of the last
+ * one (the window's upper bound). Replaces the selection. */
+int kgl_b200_count_loci(kgl_b200_ctx* ctx, uint32_t pop, uint64_t lower, uint64_t spacing, uint64_t count, double min_af, double max_af,
+                        uint64_t* n_found, uint64_t* last_offset);
+/* Per-locus verdict of the variant-level population filters, applied by kgl_b200_select_loci / kgl_b200_count_loci and the AF-bin
+ * passes: keep uint8[n_loci], 0 = the locus is never selected (its genotypes still count in kgl_b200_run_allele_count). What the
+ * reference does by copying the population through viewFilter: AndFilter(SNPFilter(), PassFilter()) on the frequency source
+ * (kga_analysis_inbreed.cpp:79), P7VariantFilter / P7FrequencyFilter / SNPFilter of FilterPf7::qualityFilter
+ * (kga_analysis_library/kga_analysis_lib_PfFilter.cpp:62-92). NULL clears it; kgl_b200_upload_loci clears it. */
+int kgl_b200_set_locus_filter(kgl_b200_ctx* ctx, uint64_t n_loci, const uint8_t* keep);
 int kgl_b200_get_locus_selection(kgl_b200_ctx* ctx, uint64_t n_loci, uint8_t* selected);
 
 /* Synthetic population generated on the device (configs too large to stage through a PopulationDB; the law is

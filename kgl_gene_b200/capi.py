@@ -26,7 +26,7 @@ EXPORTS = [
     "kgl_b200_version", "kgl_b200_device_count", "kgl_b200_create", "kgl_b200_destroy", "kgl_b200_last_error",
     "kgl_b200_set_stream", "kgl_b200_synchronize", "kgl_b200_upload_genotypes", "kgl_b200_upload_loci",
     "kgl_b200_set_genome_superpop", "kgl_b200_upload_multi_allelic", "kgl_b200_run_multi_allele_count", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
-    "kgl_b200_get_locus_selection", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
+    "kgl_b200_get_locus_selection", "kgl_b200_count_loci", "kgl_b200_set_locus_filter", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
     "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
@@ -170,6 +170,20 @@ class KglB200:
         self._check(self.lib.kgl_b200_select_loci(self.h, C.c_uint64(lower), C.c_uint64(upper), C.c_uint64(spacing),
                                                   C.c_double(min_af), C.c_double(max_af), _ptr(counts)), "select_loci")
         return counts
+
+    def count_loci(self, pop=5, lower=0, spacing=0, count=1000, min_af=0.0, max_af=1.0):
+        """RetrieveLociiVector::getLociiCount: (loci found <= count, offset of the last one)."""
+        n, last = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.kgl_b200_count_loci(self.h, C.c_uint32(pop), C.c_uint64(lower), C.c_uint64(spacing), C.c_uint64(count),
+                                                 C.c_double(min_af), C.c_double(max_af), C.byref(n), C.byref(last)), "count_loci")
+        return int(n.value), int(last.value)
+
+    def set_locus_filter(self, keep):
+        if keep is None:
+            self._check(self.lib.kgl_b200_set_locus_filter(self.h, C.c_uint64(0), None), "set_locus_filter")
+            return
+        k = np.ascontiguousarray(keep, dtype=np.uint8)
+        self._check(self.lib.kgl_b200_set_locus_filter(self.h, C.c_uint64(k.shape[0]), _ptr(k)), "set_locus_filter")
 
     def set_locus_selection(self, selected_bits: np.ndarray):
         s = np.ascontiguousarray(selected_bits, dtype=np.uint8)

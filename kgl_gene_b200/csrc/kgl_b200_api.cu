@@ -92,6 +92,8 @@ struct kgl_b200_ctx {
   bool have_offsets = false, h_sel_valid = false;
   uint64_t loci_len = 0;               // n_loci of the uploaded AF table
   DevBuf<uint32_t> d_offsets;
+  DevBuf<uint8_t> d_locus_keep;          // verdict of the variant-level filters per locus (kgl_b200_set_locus_filter)
+  bool keep_valid = false;
   DevBuf<unsigned long long> d_sel_counts;
   DevBuf<uint32_t> d_chain_u32;          // spaced selection: next-valid table, two jump tables, block summaries
   DevBuf<uint8_t> d_chain_mark;
@@ -1005,7 +1007,7 @@ void kgl_b200_destroy(kgl_b200_ctx* c) {
   c->d_partials.release(); c->d_iter.release(); c->d_f.release();
   c->d_bracket.release(); c->d_chunk_out.release(); c->d_inbreeding.release(); c->d_grid.release(); c->d_done.release();
   c->d_flag.release(); c->d_genome_counts.release(); c->d_results.release(); c->d_ibs.release();
-  c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release();
+  c->d_ibs_lo.release(); c->d_ibs_hi.release(); c->d_sm_valid.release(); c->d_ibs_acc.release(); c->d_ibs_tiles_out.release(); c->d_ibs_tiles.release(); c->d_offsets.release(); c->d_sel_counts.release(); c->d_locus_keep.release();
   c->d_bin_flags.release(); c->d_bin_sum64.release(); c->d_bin_popmask32.release(); c->d_bin_state.release(); c->d_bin_need32.release();
   c->d_zero_superpop.release(); c->d_bin_out.release();
   peer_detach(c); peer_unregister(c);
@@ -1173,6 +1175,7 @@ int kgl_b200_upload_loci(kgl_b200_ctx* c, uint64_t n_loci, uint32_t n_pop, const
   KGL_CUDA(c, cudaStreamSynchronize(c->stream));
   c->have_loci = true; c->prep_valid = false; c->dropped_cells_state = 0;
   c->n_multi = 0;                    // ... and after the frequency table
+  c->keep_valid = false;
   return KGL_B200_OK;
 }
 
@@ -1278,11 +1281,11 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
     KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
     KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
     k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
-                                                              c->d_sel.p, c->d_sel_counts.p);
+                                                              c->keep_valid ? c->d_locus_keep.p : nullptr, c->d_sel.p, c->d_sel_counts.p);
     KGL_LAUNCH_CHECK(c);
     if (c->n_multi) {
       k_multi_select<<<blocks_for(c->n_multi, 128), 128, 0, c->stream>>>(c->d_multi_rows.p, c->d_multi_af.p, c->d_offsets.p, c->n_multi, (int)c->n_pop,
-                                                                         lower, upper, min_af, max_af, c->d_sel.p, c->d_sel_counts.p);
+                                                                         lower, upper, min_af, max_af, c->keep_valid ? c->d_locus_keep.p : nullptr, c->d_sel.p, c->d_sel_counts.p);
       KGL_LAUNCH_CHECK(c);
     }
     c->prep_valid = false; c->h_sel_valid = false; c->inputs_async = true;
@@ -1300,11 +1303,11 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
   KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
   k_select_dense<<<blocks_for(L, 256), 256, 0, c->stream>>>(c->d_af.p, c->d_offsets.p, L, (int)c->n_pop, lower, upper, min_af, max_af,
-                                                            c->d_sel.p, c->d_sel_counts.p);
+                                                            c->keep_valid ? c->d_locus_keep.p : nullptr, c->d_sel.p, c->d_sel_counts.p);
   KGL_LAUNCH_CHECK(c);
   if (c->n_multi) {          // candidates among the multi-allelic loci: they take part in the accept chain like any locus
     k_multi_select<<<blocks_for(c->n_multi, 128), 128, 0, c->stream>>>(c->d_multi_rows.p, c->d_multi_af.p, c->d_offsets.p, c->n_multi, (int)c->n_pop,
-                                                                       lower, upper, min_af, max_af, c->d_sel.p, c->d_sel_counts.p);
+                                                                       lower, upper, min_af, max_af, c->keep_valid ? c->d_locus_keep.p : nullptr, c->d_sel.p, c->d_sel_counts.p);
     KGL_LAUNCH_CHECK(c);
   }
   KGL_CUDA(c, cudaMemsetAsync(c->d_sel_counts.p, 0, kMaxPop * 8, c->stream));
@@ -1345,6 +1348,54 @@ int kgl_b200_select_loci(kgl_b200_ctx* c, uint64_t lower, uint64_t upper, uint64
     for (uint32_t k = 0; k < c->n_pop; ++k) n_selected[k] = counts[k];
   }
   return KGL_B200_OK;
+}
+
+int kgl_b200_set_locus_filter(kgl_b200_ctx* c, uint64_t n_loci, const uint8_t* keep) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  if (!c->have_loci) return fail(c, KGL_B200_ERR_STATE, "upload_loci first");
+  int rc = use_device(c); if (rc) return rc;
+  c->keep_valid = false; c->prep_valid = false;
+  if (!keep) return KGL_B200_OK;
+  if (n_loci != c->loci_len) return fail(c, KGL_B200_ERR_INVALID, "filter length differs from n_loci");
+  KGL_CUDA(c, c->d_locus_keep.ensure(n_loci));
+  KGL_CUDA(c, cudaMemcpyAsync(c->d_locus_keep.p, keep, n_loci, cudaMemcpyHostToDevice, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->keep_valid = true;
+  return KGL_B200_OK;
+}
+
+// RetrieveLociiVector::getLociiCount (kga_analysis_inbreed_locus.cpp:159-183 over getAllelesCount, :105-156): the first `count`
+// accepted loci of one super-population from `lower` on. The accept rule is the one of kgl_b200_select_loci (same kernels); the
+// rows are searched in growing spans until `count` loci are found or the contig ends -- accepting a locus only depends on the
+// loci before it, so a truncated span gives the same prefix. Leaves the selection of the last span in place.
+int kgl_b200_count_loci(kgl_b200_ctx* c, uint32_t pop, uint64_t lower, uint64_t spacing, uint64_t count, double min_af, double max_af,
+                        uint64_t* n_found, uint64_t* last_offset) {
+  if (!c || !n_found || !last_offset) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  if (!c->have_loci || !c->have_offsets) return fail(c, KGL_B200_ERR_STATE, "upload_loci (with offsets) first");
+  if (pop >= c->n_pop) return fail(c, KGL_B200_ERR_INVALID, "population index out of range");
+  *n_found = 0; *last_offset = 0;
+  const uint64_t L = c->loci_len;
+  const uint64_t l_begin = std::lower_bound(c->h_offsets.begin(), c->h_offsets.end(), lower,
+                                            [](uint32_t o, uint64_t v) { return (uint64_t)o < v; }) - c->h_offsets.begin();
+  if (l_begin >= L || count == 0) return KGL_B200_OK;
+  KGL_CUDA(c, c->d_sel_counts.ensure(kMaxPop));
+  uint64_t span = std::max<uint64_t>(4096, std::min<uint64_t>(L, count * 16));
+  for (;;) {
+    const uint64_t l_end = std::min<uint64_t>(L, l_begin + span);
+    int rc = kgl_b200_select_loci(c, lower, c->h_offsets[l_end - 1], spacing, min_af, max_af, nullptr); if (rc) return rc;
+    unsigned long long* out = c->d_sel_counts.p;            // reused as {found, last row}
+    k_rank_find<<<1, 1024, 0, c->stream>>>(c->d_sel.p, l_begin, l_end, (int)pop, count, out);
+    KGL_LAUNCH_CHECK(c);
+    unsigned long long h[2] = {0, 0};
+    KGL_CUDA(c, cudaMemcpyAsync(h, out, 16, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h[0] >= count || l_end == L) {
+      *n_found = h[0];
+      if (h[0] > 0) *last_offset = c->h_offsets[h[1]];
+      return KGL_B200_OK;
+    }
+    span *= 8;
+  }
 }
 
 int kgl_b200_synth_genotypes(kgl_b200_ctx* c, uint64_t seed, uint64_t n_genomes, uint64_t n_loci, uint64_t locus_base,
@@ -1973,8 +2024,8 @@ int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* c, uint32_t pop, uint32_t n_
   for (uint32_t b = 0; b < n_bins; ++b) {
     KGL_CUDA(c, cudaMemsetAsync(c->d_bin_state.p, 0, 8, c->stream));
     k_bin_flags<<<blocks_for(c->padded_rows, 256), 256, 0, c->stream>>>(c->d_af.p + (size_t)pop * c->L, present_only ? c->d_locus_counts.p : nullptr,
-                                                                         c->L, c->padded_rows, lower[b], upper[b], c->d_bin_flags.p,
-                                                                         c->d_bin_sum64.p, c->d_bin_state.p + 1);
+                                                                         c->L, c->padded_rows, lower[b], upper[b], c->keep_valid ? c->d_locus_keep.p : nullptr,
+                                                                         c->d_bin_flags.p, c->d_bin_sum64.p, c->d_bin_state.p + 1);
     KGL_LAUNCH_CHECK(c);
     rc = launch_count(c, false, false, true, false, false, &mo); if (rc) return rc;
     k_genome_counts_masked<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->d_bin_state.p + 1,

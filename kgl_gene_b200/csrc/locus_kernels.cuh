@@ -241,14 +241,17 @@ k_locus_prepare(const float* __restrict__ af, const uint8_t* __restrict__ sel, u
 // RetrieveLociiVector::getAllelesFromTo (kga_analysis_inbreed_locus.cpp:21-72) with lociiSpacing == 0: a locus is taken for
 // population k iff lower <= offset <= upper, its AF entry exists, and p = clamp(AF, 0, 1) satisfies p != 0 and
 // min_af <= p <= max_af (:53-54). sel[l] bit k; counts[k] += selected loci.
+// keep (nullable): per-locus verdict of the variant-level filters (kgl_b200_set_locus_filter: SNP and PASS of the frequency
+// source, kga_analysis_inbreed.cpp:79; the Pf7 INFO-field filters, kga_analysis_lib_PfFilter.cpp:62-92) -- 0 = the locus is no candidate.
 __global__ void __launch_bounds__(256)
 k_select_dense(const float* __restrict__ af, const uint32_t* __restrict__ offsets, uint64_t n_loci, int n_pop, uint64_t lower,
-               uint64_t upper, double min_af, double max_af, uint8_t* __restrict__ sel, unsigned long long* __restrict__ counts) {
+               uint64_t upper, double min_af, double max_af, const uint8_t* __restrict__ keep, uint8_t* __restrict__ sel,
+               unsigned long long* __restrict__ counts) {
   const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t bits = 0;
   if (l < n_loci) {
     const uint64_t offset = offsets[l];
-    if (offset >= lower && offset <= upper) {
+    if (offset >= lower && offset <= upper && (keep == nullptr || keep[l] != 0)) {
       for (int k = 0; k < n_pop; ++k) {
         const float a = af[(uint64_t)k * n_loci + l];
         if (a != a) continue;
@@ -264,6 +267,37 @@ k_select_dense(const float* __restrict__ af, const uint32_t* __restrict__ offset
     const uint32_t n = __popc(__ballot_sync(kFull, (bits >> k) & 1u));
     if ((threadIdx.x & 31) == 0 && n) atomicAdd(&counts[k], (unsigned long long)n);
   }
+}
+
+// RetrieveLociiVector::getAllelesCount (kga_analysis_inbreed_locus.cpp:105-156) on an accepted-locus mask: the first `count`
+// loci of population k at or after row `begin` (the walk stops as soon as `count` loci have been taken, :117). out[0] = loci
+// found (<= count), out[1] = row of the last one. One block; the rows are walked 1,024 at a time.
+__global__ void __launch_bounds__(1024)
+k_rank_find(const uint8_t* __restrict__ sel, uint64_t begin, uint64_t end, int k, uint64_t count, unsigned long long* __restrict__ out) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ unsigned long long s_found, s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_found = 0; s_last = ~0ull; }
+  __syncthreads();
+  for (uint64_t l0 = begin; l0 < end; l0 += 1024) {
+    const uint64_t l = l0 + threadIdx.x;
+    const bool on = l < end && ((sel[l] >> k) & 1u);
+    const uint32_t bal = __ballot_sync(kFull, on);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    unsigned long long before = s_found;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const unsigned long long rank = before + __popc(bal & ((1u << lane) - 1u));     // loci found before this one
+    uint32_t total = 0;
+    for (int w = 0; w < 32; ++w) total += s_warp[w];
+    // the last locus that is still taken: rank count - 1, or the last one found when there are fewer
+    if (on && (rank + 1 == count || (rank + 1 < count && rank + 1 == s_found + total))) s_last = l;
+    __syncthreads();
+    if (threadIdx.x == 0) s_found = min((unsigned long long)count, s_found + total);
+    __syncthreads();
+    if (s_found >= count) break;
+  }
+  if (threadIdx.x == 0) { out[0] = s_found; out[1] = s_last; }
 }
 
 // ---- spaced selection on the device (getAllelesFromTo with SamplingDistance > 0, kga_analysis_inbreed_locus.cpp:21-72) ------

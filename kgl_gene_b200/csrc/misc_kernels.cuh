@@ -339,8 +339,8 @@ __global__ void k_genome_counts_raw(const uint32_t* __restrict__ gcounts, const 
 // 64-row summary.
 __global__ void __launch_bounds__(256)
 k_bin_flags(const float* __restrict__ af_pop, const uint32_t* __restrict__ locus_counts /* nullable [L][4] */, uint64_t n_loci,
-            uint64_t padded_rows, double lower, double upper, uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64,
-            uint32_t* __restrict__ n_rows) {
+            uint64_t padded_rows, double lower, double upper, const uint8_t* __restrict__ keep /* nullable: kgl_b200_set_locus_filter */,
+            uint16_t* __restrict__ flags16, uint16_t* __restrict__ sum64, uint32_t* __restrict__ n_rows) {
   __shared__ uint32_t s_bal[8];
   const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool in = false;
@@ -350,6 +350,7 @@ k_bin_flags(const float* __restrict__ af_pop, const uint32_t* __restrict__ locus
       const double v = (double)a;
       in = v >= lower && !(v >= upper);
       if (in && locus_counts) in = (locus_counts[l * 4 + 1] + locus_counts[l * 4 + 2]) != 0;
+      if (in && keep) in = keep[l] != 0;
     }
   }
   if (l < padded_rows) flags16[l] = in ? 1u : 0u;

@@ -50,14 +50,14 @@ __device__ __forceinline__ MultiVector multi_vector(const float* __restrict__ af
 // left their bits clear (NaN in the frequency table). Runs before the spaced accept chain, which then treats them like any locus.
 __global__ void __launch_bounds__(128)
 k_multi_select(const uint32_t* __restrict__ rows, const float* __restrict__ af, const uint32_t* __restrict__ offsets, uint64_t n_multi,
-               int n_pop, uint64_t lower, uint64_t upper, double min_af, double max_af, uint8_t* __restrict__ sel,
-               unsigned long long* __restrict__ counts) {
+               int n_pop, uint64_t lower, uint64_t upper, double min_af, double max_af, const uint8_t* __restrict__ keep,
+               uint8_t* __restrict__ sel, unsigned long long* __restrict__ counts) {
   const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_multi) return;
   const uint32_t row = rows[m];
   const uint64_t offset = offsets[row];
   uint32_t bits = 0;
-  if (offset >= lower && offset <= upper) {
+  if (offset >= lower && offset <= upper && (keep == nullptr || keep[row] != 0)) {
     for (int k = 0; k < n_pop; ++k) {
       const MultiVector v = multi_vector(af + ((uint64_t)k * n_multi + m) * kMultiSlots);
       if (!v.valid) continue;

@@ -249,15 +249,23 @@ bool kga::InbreedB200Analysis::windowLoop(const std::shared_ptr<const Population
   auto const& [af_genome_id, af_genome_ptr] = *unphased_ptr->getMap().begin();
   auto const& [contig_id, contig_ptr] = *af_genome_ptr->getMap().begin();
 
+  // Windows are defined on the "ALL" super-population (kga_analysis_inbreed_diploid.cpp:48-51,69-73): the first LociiCount
+  // accepted loci from the window's lower bound, RetrieveLociiVector::getLociiCount -- on the device, kgl_b200_count_loci.
+  constexpr uint32_t kAllPop = b200::kSuperPopCount - 1;
   InbreedingParameters local_params = param_output.getParameters();
-  std::vector<ContigOffset_t> locii_vector = RetrieveLociiVector::getLociiCount(contig_ptr, FrequencyDatabaseRead::SUPER_POP_ALL_,
-                                                                                local_params.lociiArguments());
-  if (locii_vector.empty()) return true;       // (the reference dereferences .back() of an empty vector here)
-  local_params.lociiArguments().upperOffset(locii_vector.back());
+  uint64_t window_loci = 0, window_upper = 0;
+  auto next_window = [&]() {
+    auto const& a = local_params.lociiArguments();
+    return check(kgl_b200_count_loci(context_, kAllPop, a.lowerOffset(), a.lociiSpacing(), a.lociiCount(), a.minAlleleFrequency(),
+                                     a.maxAlleleFrequency(), &window_loci, &window_upper), "count_loci");
+  };
+  if (not next_window()) return false;
+  if (window_loci == 0) return true;           // (the reference dereferences .back() of an empty vector here)
+  local_params.lociiArguments().upperOffset(window_upper);
 
   std::vector<kgl_b200_locus_results> results(flat.nGenomes());
   while (local_params.lociiArguments().upperOffset() < param_output.getParameters().lociiArguments().upperOffset()
-         and locii_vector.size() >= 100) {
+         and window_loci >= 100) {
 
     auto const& args = local_params.lociiArguments();
     if (not check(kgl_b200_select_loci(context_, args.lowerOffset(), args.upperOffset(), args.lociiSpacing(),
@@ -282,9 +290,9 @@ bool kga::InbreedB200Analysis::windowLoop(const std::shared_ptr<const Population
     param_output.addColumn(InbreedingResultColumn(result_ident, results_map));
 
     local_params.lociiArguments().lowerOffset(local_params.lociiArguments().upperOffset());
-    locii_vector = RetrieveLociiVector::getLociiCount(contig_ptr, FrequencyDatabaseRead::SUPER_POP_ALL_, local_params.lociiArguments());
-    if (locii_vector.empty()) break;
-    local_params.lociiArguments().upperOffset(locii_vector.back());
+    if (not next_window()) return false;
+    if (window_loci == 0) break;
+    local_params.lociiArguments().upperOffset(window_upper);
 
   }
 

@@ -635,3 +635,43 @@ def test_peer_exchange_two_gpus():
     assert line["n_gpus"] == 2 and line["value"] > 0
     if line["config"]["exchange"] != "peer":
         pytest.skip("CUDA IPC peer mapping unavailable on this box: " + line["config"]["exchange"])
+
+
+@pytest.mark.parametrize("multi", [False, True], ids=["biallelic", "multi-allelic"])
+def test_count_limited_selection_and_locus_filter(gpu, multi):
+    """N3: RetrieveLociiVector::getLociiCount on the device (kgl_b200_count_loci: how the window loop of populationInbreeding finds
+    a window's upper bound, kga_analysis_inbreed_diploid.cpp:48-51) against the oracle's count-mode walk, and the per-locus
+    verdict of the variant-level filters (kgl_b200_set_locus_filter) against the oracle on the filtered locus table."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(96, 120_000, seed=55, missing_af_rate=0.05)
+    if multi:
+        add_multi_allelic(pop, 3000, seed=56)
+    gpu.upload_population(pop)
+    for k, kw in ((5, dict(lower=0, spacing=0, count=1000)), (5, dict(lower=400_000, spacing=1000, count=1000)),
+                  (0, dict(lower=123_457, spacing=37, count=5000, min_af=0.01, max_af=0.6)), (2, dict(lower=900_000, spacing=500, count=10_000)),
+                  (5, dict(lower=1_300_000, spacing=0, count=100)), (3, dict(lower=0, spacing=10**7, count=50))):
+        want = O.select_all_pops(pop, mode=1, **kw)[k]
+        offs = pop.offsets[want == 1]
+        n, last = gpu.count_loci(pop=k, **kw)
+        assert n == len(offs), (k, kw)
+        if n:
+            assert last == int(offs[-1]), (k, kw)
+    # locus filter: a filtered locus is no candidate -- the spaced chain runs over the loci that are left
+    rng = np.random.default_rng(5)
+    keep = (rng.random(pop.n_loci) < 0.8).astype(np.uint8)
+    gpu.set_locus_filter(keep)
+    gpu.select_loci(spacing=40)
+    from kgl_gene_b200.flatfile import FlatPopulation
+    filtered = FlatPopulation(pop.offsets, pop.af.copy(), pop.superpop, pop.packed, pop.n_genomes, pop.unphased)
+    filtered.af[:, keep == 0] = np.nan                   # the oracle's view of a filtered locus: no frequency, no candidate
+    if multi:
+        filtered.multi_rows, filtered.multi_cells = pop.multi_rows, pop.multi_cells
+        filtered.multi_af = pop.multi_af.copy()
+        filtered.multi_af[:, keep[pop.multi_rows] == 0, :] = np.nan
+    want = O.select_all_pops(filtered, spacing=40)
+    assert np.array_equal(gpu.get_locus_selection(), sel_bits(want))
+    res = gpu.inbreed("Simple")
+    assert np.array_equal(results_matrix(res)[0], results_matrix(O.inbreed(filtered, want, "Simple"))[0])
+    gpu.set_locus_filter(None)
+    gpu.select_loci(spacing=40)
+    assert np.array_equal(gpu.get_locus_selection(), sel_bits(O.select_all_pops(pop, spacing=40)))
