@@ -183,6 +183,20 @@ int kgl_b200_run_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, u
 int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* ctx, uint32_t pop, uint32_t n_bins, const double* lower, const double* upper,
                                       int present_only, uint64_t* genome_counts, uint64_t* bin_rows);
 
+/* HeteroHomoZygous::updateVariantAnalysisType for every genome (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105), one raw
+ * counting pass + the multi-allelic side cells: out uint64[n_genomes][7] = {total_variants_, snp_count_, indel_count_,
+ * homozygous_minor_alleles_, heterozygous_minor_alleles_, heterozygous_reference_minor_alleles_, homozygous_reference_alleles_}
+ * (the matrix path holds SNPs only: indel_count_ = 0; a code-3 cell of an ordinary row stands for other_allele_entries entries
+ * of some other allele). kgl_b200_location_fis: HeteroHomoZygous::UpdateSampleLocation (:362-412) on those records -- host
+ * arithmetic, no context: locations 0..n_locations-1 with their sample lists (location_begin[n_locations + 1] into
+ * location_members; what Pf7SampleLocation::sampleRadius returns for the location), every genome's city and country location
+ * (>= n_locations: none), its QC verdict (NULL: all pass); a city with fewer than min_location_samples QC-pass samples (the
+ * reference's MINIMUM_LOCATION_SAMPLES_ = 20) falls back to the country; fis[g] = (H_exp - H_obs) / H_exp, 0 where undefined. */
+int kgl_b200_run_hetero_homo(kgl_b200_ctx* ctx, int other_allele_entries, uint64_t* out);
+int kgl_b200_location_fis(uint64_t n_genomes, const uint64_t* hetero_homo, uint32_t n_locations, const uint64_t* location_begin,
+                          const uint32_t* location_members, const uint32_t* city_of_genome, const uint32_t* country_of_genome,
+                          const uint8_t* qc_pass, uint32_t min_location_samples, double* fis);
+
 /* Tensor-core variant of the pairwise path (BASELINE config 5): the dosage Gram matrix
  * gram int32[n_genomes][n_genomes], gram[a][b] = sum over loci of g_a g_b with g in {0,1,2} (code 3 counts as 0: in the
  * variant DB "no entry at the offset" is the reference genotype), contracted exactly in int8 x int8 -> int32 on

@@ -28,7 +28,7 @@ EXPORTS = [
     "kgl_b200_set_genome_superpop", "kgl_b200_upload_multi_allelic", "kgl_b200_run_multi_allele_count", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_count_loci", "kgl_b200_set_locus_filter", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
     "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
-    "kgl_b200_run_binned_genome_counts", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
+    "kgl_b200_run_binned_genome_counts", "kgl_b200_run_hetero_homo", "kgl_b200_location_fis", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_flush", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
     "kgl_b200_inbreed_begin", "kgl_b200_inbreed_accumulate", "kgl_b200_inbreed_partials_buffer", "kgl_b200_inbreed_update",
@@ -74,6 +74,26 @@ def load_library() -> C.CDLL:
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def location_fis(hetero_homo: np.ndarray, location_members: list, city_of_genome, country_of_genome, qc_pass=None,
+                 min_location_samples: int = 20) -> np.ndarray:
+    """kgl_b200_location_fis: Wright's F_IS of every genome against its location aggregate (UpdateSampleLocation)."""
+    lib = load_library()
+    hh = np.ascontiguousarray(hetero_homo, dtype=np.uint64)
+    n = hh.shape[0]
+    begin = np.zeros(len(location_members) + 1, dtype=np.uint64)
+    begin[1:] = np.cumsum([len(m) for m in location_members])
+    members = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.uint32) for m in location_members]) if location_members else np.zeros(0), dtype=np.uint32)
+    city = np.ascontiguousarray(city_of_genome, dtype=np.uint32)
+    country = np.ascontiguousarray(country_of_genome, dtype=np.uint32)
+    qc = None if qc_pass is None else np.ascontiguousarray(qc_pass, dtype=np.uint8)
+    out = np.zeros(n, dtype=np.float64)
+    rc = lib.kgl_b200_location_fis(C.c_uint64(n), _ptr(hh), C.c_uint32(len(location_members)), _ptr(begin), _ptr(members), _ptr(city),
+                                   _ptr(country), _ptr(qc), C.c_uint32(min_location_samples), _ptr(out))
+    if rc != 0:
+        raise KglError(f"location_fis failed [{rc}]")
+    return out
 
 
 class KglB200:
@@ -261,6 +281,12 @@ class KglB200:
         self._check(self.lib.kgl_b200_run_binned_genome_counts(self.h, C.c_uint32(pop), C.c_uint32(lo.shape[0]), _ptr(lo), _ptr(hi),
                                                                C.c_int(int(present_only)), _ptr(out), _ptr(rows)), "run_binned_genome_counts")
         return out, rows
+
+    def hetero_homo(self, other_allele_entries: int = 1) -> np.ndarray:
+        """HeteroHomoZygous::updateVariantAnalysisType per genome: uint64[N][7] = total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef."""
+        out = np.zeros((self.n_genomes, 7), dtype=np.uint64)
+        self._check(self.lib.kgl_b200_run_hetero_homo(self.h, C.c_int(other_allele_entries), _ptr(out)), "run_hetero_homo")
+        return out
 
     def gram(self) -> np.ndarray:
         """Dosage Gram matrix int32[N][N] on the tensor cores (tcgen05 kind::i8)."""

@@ -1452,6 +1452,60 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* c, uint32_t* locus_counts, uint64_t*
   return KGL_B200_OK;
 }
 
+int kgl_b200_run_hetero_homo(kgl_b200_ctx* c, int other_allele_entries, uint64_t* out) {
+  if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  if (!c->have_superpop) {   // raw counting needs no super-populations: treat everyone as population 0
+    std::vector<uint8_t> zeros(c->N, 0);
+    rc = kgl_b200_set_genome_superpop(c, c->N, zeros.data()); if (rc) return rc;
+    c->have_superpop = false;
+  }
+  rc = launch_count(c, true, false, true); if (rc) return rc;
+  KGL_CUDA(c, c->d_genome_counts.ensure((size_t)c->N * 7));
+  k_hetero_homo<<<blocks_for(c->N, 128), 128, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->n_multi ? c->d_multi_cells.p : nullptr, c->n_multi, c->N,
+                                                              other_allele_entries ? 1u : 0u, c->d_genome_counts.p);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemcpyAsync(out, c->d_genome_counts.p, (size_t)c->N * 56, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  return KGL_B200_OK;
+}
+
+// HeteroHomoZygous::UpdateSampleLocation (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:362-412) on the records of
+// kgl_b200_run_hetero_homo. Host arithmetic over n_genomes records (no device work): the location aggregates of
+// HeteroHomoZygous::location_summary (:266-358: sums over the location's samples, radii_samples_OK_ = its QC-pass samples), the
+// city -> country fallback below MINIMUM_LOCATION_SAMPLES_ (:375-388) and Wright's F_IS = (H_exp - H_obs) / H_exp.
+int kgl_b200_location_fis(uint64_t n_genomes, const uint64_t* hetero_homo, uint32_t n_locations, const uint64_t* location_begin,
+                          const uint32_t* location_members, const uint32_t* city_of_genome, const uint32_t* country_of_genome,
+                          const uint8_t* qc_pass, uint32_t min_location_samples, double* fis) {
+  if (!hetero_homo || !location_begin || !location_members || !city_of_genome || !country_of_genome || !fis) return KGL_B200_ERR_INVALID;
+  std::vector<uint64_t> total(n_locations, 0), het(n_locations, 0), ok(n_locations, 0);
+  for (uint32_t loc = 0; loc < n_locations; ++loc)
+    for (uint64_t i = location_begin[loc]; i < location_begin[loc + 1]; ++i) {
+      const uint32_t g = location_members[i];
+      if (g >= n_genomes) return KGL_B200_ERR_INVALID;
+      total[loc] += hetero_homo[(size_t)g * 7 + 0];
+      het[loc] += hetero_homo[(size_t)g * 7 + 4] + hetero_homo[(size_t)g * 7 + 5];
+      ok[loc] += (!qc_pass || qc_pass[g]) ? 1u : 0u;
+    }
+  for (uint64_t g = 0; g < n_genomes; ++g) {
+    fis[g] = 0.0;
+    uint32_t loc = city_of_genome[g];
+    if (loc >= n_locations) continue;                        // no location record: the reference logs an error and leaves 0
+    if (ok[loc] < min_location_samples) {
+      loc = country_of_genome[g];
+      if (loc >= n_locations) continue;
+    }
+    const uint64_t g_total = hetero_homo[g * 7 + 0], g_het = hetero_homo[g * 7 + 4] + hetero_homo[g * 7 + 5];
+    if (total[loc] > 0 && g_total > 0) {
+      const double expected_heterozygosity = static_cast<double>(het[loc]) / static_cast<double>(total[loc]);
+      const double observed_heterozygosity = static_cast<double>(g_het) / static_cast<double>(g_total);
+      fis[g] = (expected_heterozygosity - observed_heterozygosity) / expected_heterozygosity;
+    }
+  }
+  return KGL_B200_OK;
+}
+
 int kgl_b200_enqueue_count_and_inbreed(kgl_b200_ctx* c) {
   if (!c) return KGL_B200_ERR_INVALID;
   int rc = use_device(c, false); if (rc) return rc;      // the tail of the pass before may still be running: it is not waited for

@@ -256,6 +256,38 @@ k_multi_allele_count(const uint8_t* __restrict__ cells, uint64_t n_genomes, uint
   if (threadIdx.x < kMultiSlots * 3) counts[m * kMultiSlots * 3 + threadIdx.x] = (&s_c[0][0])[threadIdx.x];
 }
 
+// HeteroHomoZygous::updateVariantAnalysisType (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105) for every genome, from the raw
+// per-genome code counts of a counting pass and the multi-allelic side cells. Per offset of a genome: every variant entry counts
+// (total_variants_, snp_count_: the matrix path holds SNPs only); one entry -> heterozygous_reference_minor_alleles_; otherwise
+// homozygous_minor_alleles_ += distinct alleles (UniqueUnphasedFilter) and heterozygous_minor_alleles_ += alleles that occur
+// once (HeterozygousFilter): a hom-alt pair gives {1, 0}, two different alternate alleles {2, 2}.
+// out[g] = {total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef}. other_entries: variant entries a code-3 cell of an
+// ordinary row stands for (1: one other allele, the flattener's usual case).
+__global__ void __launch_bounds__(128)
+k_hetero_homo(const uint32_t* __restrict__ gcounts, const uint32_t* __restrict__ n3s, const uint8_t* __restrict__ cells /* nullable */,
+              uint64_t n_multi, uint64_t n_genomes, uint32_t other_entries, uint64_t* __restrict__ out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_genomes) return;
+  uint64_t single = 0, same = 0, diff = 0, many = 0;
+  for (uint64_t m = 0; m < n_multi; ++m) {
+    const uint32_t cell = cells[m * n_genomes + g];
+    if (cell == 0) continue;
+    if (cell == 0xFFu) ++many;
+    else if ((cell >> 4) == 0) ++single;
+    else if ((cell >> 4) == (cell & 15u)) ++same;
+    else ++diff;
+  }
+  const uint64_t n3_all = n3s[g], n1 = gcounts[g * 2] - n3_all, n2 = gcounts[g * 2 + 1] - n3_all;
+  const uint64_t n3 = (n3_all - (single + same + diff + many)) * other_entries;      // code-3 cells of ordinary rows
+  const uint64_t total = n1 + 2 * n2 + n3 + single + 2 * same + 2 * diff + 3 * many;
+  uint64_t* o = out + g * 7;
+  o[0] = total; o[1] = total; o[2] = 0;
+  o[3] = n2 + same + 2 * diff + 2 * many;
+  o[4] = 2 * diff + many;
+  o[5] = n1 + n3 + single;
+  o[6] = 0;
+}
+
 // The frequency-table entries of the multi-allelic rows are not used: they are set to "no value" so that the dense path never
 // selects such a row, whatever the caller left there.
 __global__ void __launch_bounds__(128)

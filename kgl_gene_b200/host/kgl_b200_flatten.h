@@ -53,6 +53,7 @@ struct FlatContig {
   std::vector<float> multi_af;
   std::vector<uint8_t> multi_cells;
   size_t too_many_alleles_skipped{0};                      // offsets with more than three distinct alt alleles (not a SNP locus)
+  size_t non_snp_entries{0};                               // flattenSelf: variant entries that are not SNPs (not in the matrix)
   size_t mixed_phase_cells{0};                             // cells whose phase pattern contradicts `unphased` (coded 3)
 
   [[nodiscard]] uint64_t nGenomes() const { return genome_ids.size(); }
@@ -74,6 +75,13 @@ public:
                                            const SuperPopLookup& super_population,
                                            bool unphased_population,
                                            size_t threads = 0);
+
+  // A population that is its own locus list (kga_PfEMP: CalcFWS, HeteroHomoZygous): one row per offset at which a genome of
+  // the contig carries a SNP, alleles = the distinct SNPs seen there, every frequency column = allele_frequency(allele)
+  // (nullopt -> no value). Every genome that has the contig is a column; super-population 0 for all.
+  static std::optional<FlatContig> flattenSelf(const PopulationDB& population, const ContigId_t& contig_id,
+                                               const std::function<std::optional<double>(const Variant&)>& allele_frequency,
+                                               bool unphased_population, size_t threads = 0);
 
 };
 

@@ -18,6 +18,8 @@
 #include "kgl_hsgenealogy_parser.h"
 #include "kga_analysis_inbreed.h"
 #include "kga_analysis_inbreed_b200.h"
+#include "kga_analysis_pfemp_b200.h"
+#include "kga_analysis_PfEMP_heterozygous.h"
 
 #include "flat_io.h"
 #include "ref_population.h"
@@ -26,6 +28,7 @@
 #include <cstdlib>
 #include <filesystem>
 #include <fstream>
+#include <set>
 
 namespace kel = kellerberrin;
 namespace kgl = kellerberrin::genome;
@@ -44,6 +47,7 @@ struct Options {
   std::string algorithm{"Simple"};
   std::string min_af{"0.0"}, max_af{"1.0"}, spacing{"0"}, count{"1000"}, lower{"0"}, upper{"1000000000"};
   bool run_reference{true}, run_b200{true};
+  bool pfemp{false};          // --pfemp: the kga_PfEMP consumer (HeteroHomoZygous) instead of the INBREED analysis
 };
 Options g_opt;
 
@@ -76,8 +80,80 @@ bool runAnalysis(const std::string& ident, const kgl::ActiveParameterList& param
 
 int g_exit_code = 0;
 
+// ---- kga_PfEMP: HeteroHomoZygous (reference) and HeteroHomoB200 (product) on the same Pf7-style population -----------------
+// The call order of kga::PfEMPAnalysis (kga_analysis_PfEMP.cpp:92-109 fileReadAnalysis, :129-150 finalizeAnalysis):
+// analyzeVariantPopulation, location_summary, UpdateSampleLocation, write_variant_results. The Pf7 sample / FWS resources are
+// built in memory (their file parsers and the physical-distance resource need Boost): genome g lives in city "City<g % 7>" of
+// country "Country<(g % 7) / 3>"; every fifth genome fails QC, so some cities fall below MINIMUM_LOCATION_SAMPLES_ and take
+// their country's aggregate. The reference's location_summary asks Pf7SampleLocation::sampleRadius (stubbed here, returns
+// nothing), so its LocationSummaryMap is assembled from the reference's own aggregateResults with the same arithmetic
+// (kga_analysis_PfEMP_heterozygous.cpp:301-352); UpdateSampleLocation and the CSV writer are the reference's.
+void runPfEMP(const kglflat::Flat& flat) {
+  const bool unphased = (flat.hdr.flags & kglflat::FLAG_UNPHASED) != 0;
+  const auto source = unphased ? kgl::DataSourceEnum::Falciparum : kgl::DataSourceEnum::Genome1000;
+  kglref::BuiltPopulations built = kglref::buildPopulations(flat, kgl::DataSourceEnum::Genome1000, source, true);
+  kgl::Pf7SampleVector samples;
+  kgl::Pf7FwsVector fws;
+  kga::LocationSamplesMap locations;
+  for (uint32_t g = 0; g < flat.N(); ++g) {
+    kgl::Pf7SampleRecord rec;
+    rec.Pf7Sample_id = built.genome_ids[g];
+    rec.study_ = "Study" + std::to_string(g % 3);
+    rec.location1_ = "City" + std::to_string(g % 7);
+    rec.country_ = "Country" + std::to_string((g % 7) / 3);
+    rec.year_ = std::to_string(2010 + g % 9);
+    rec.qc_pass_ = (g % 5 == 4) ? "False" : "True";
+    samples.push_back(rec);
+    fws.push_back(kgl::Pf7FwsRecord{built.genome_ids[g], 0.5 + 0.001 * double(g % 400)});
+    for (const std::string& loc : {rec.location1_, rec.country_}) {
+      auto& l = locations[loc];
+      l.location_type = loc[1] == 'i' ? kgl::LocationType::City : kgl::LocationType::Country;
+      l.city = rec.location1_; l.country = rec.country_; l.region = "Region" + rec.country_.substr(7);
+      l.samples.push_back(rec.Pf7Sample_id);
+    }
+  }
+  auto sample_ptr = std::make_shared<const kgl::Pf7SampleResource>("harnessPf7Samples", samples);
+  auto fws_ptr = std::make_shared<const kgl::Pf7FwsResource>("harnessPf7Fws", fws);
+  std::set<kgl::GenomeId_t> pass;
+  for (auto const& [id, rec] : sample_ptr->getMap()) if (rec.pass()) pass.insert(id);
+
+  if (g_opt.run_reference) {
+    kga::HeteroHomoZygous reference;
+    reference.analyzeVariantPopulation(built.diploid, fws_ptr, sample_ptr);
+    kga::LocationSummaryMap summary;
+    for (auto const& [location, record] : locations) {
+      auto aggregated = reference.aggregateResults(record.samples);
+      kga::LocationSummary s;
+      s.location_ = location; s.location_type_ = record.location_type; s.city_ = record.city; s.country_ = record.country; s.region_ = record.region;
+      s.radii_samples_ = record.samples.size();
+      for (auto const& id : record.samples) s.radii_samples_OK_ += pass.contains(id) ? 1 : 0;
+      s.total_variants_ = aggregated.total_variants_;
+      s.homozygous_reference_alleles_ = aggregated.homozygous_reference_alleles_;
+      s.heterozygous_reference_minor_alleles_ = aggregated.heterozygous_reference_minor_alleles_;
+      s.homozygous_minor_alleles_ = aggregated.homozygous_minor_alleles_;
+      s.heterozygous_minor_alleles_ = aggregated.heterozygous_minor_alleles_;
+      s.snp_count_ = aggregated.snp_count_; s.indel_count_ = aggregated.indel_count_;
+      summary[location] = s;
+    }
+    reference.UpdateSampleLocation(summary);
+    std::filesystem::create_directories(g_opt.work_dir + "/PFEMP");
+    reference.write_variant_results(g_opt.work_dir + "/PFEMP/hetero_homo.csv", summary);
+    std::fprintf(stderr, "[plugin] PFEMP reference: wrote %s/PFEMP/hetero_homo.csv\n", g_opt.work_dir.c_str());
+  }
+  if (g_opt.run_b200) {
+    kga::HeteroHomoB200 product;
+    if (!product.analyzeVariantPopulation(built.diploid, fws_ptr, sample_ptr)) { std::fprintf(stderr, "[plugin] PFEMP_B200: analyzeVariantPopulation failed\n"); g_exit_code = 6; return; }
+    auto summary = product.location_summary(sample_ptr, locations, 0.0, fws_ptr);
+    product.UpdateSampleLocation(summary, locations, sample_ptr);
+    std::filesystem::create_directories(g_opt.work_dir + "/PFEMP_B200");
+    product.write_variant_results(g_opt.work_dir + "/PFEMP_B200/hetero_homo.csv", summary);
+    std::fprintf(stderr, "[plugin] PFEMP_B200: wrote %s/PFEMP_B200/hetero_homo.csv\n", g_opt.work_dir.c_str());
+  }
+}
+
 void run() {
   const kglflat::Flat flat = kglflat::readFlat(g_opt.in_path);
+  if (g_opt.pfemp) { runPfEMP(flat); return; }
   const bool unphased = (flat.hdr.flags & kglflat::FLAG_UNPHASED) != 0;
   // AF data as a gnomAD 3.1 file (UnphasedMonoGenome), genotypes as 1000 Genomes (DiploidPhased) or Pf (DiploidUnphased).
   const auto diploid_source = unphased ? kgl::DataSourceEnum::Falciparum : kgl::DataSourceEnum::Genome1000;
@@ -174,6 +250,7 @@ class PluginHarnessEnv {
       else if (a == "--upper") g_opt.upper = next();
       else if (a == "--no-reference") g_opt.run_reference = false;
       else if (a == "--no-b200") g_opt.run_b200 = false;
+      else if (a == "--pfemp") g_opt.pfemp = true;
       else pos.push_back(a);
     }
     if (pos.size() != 2) { std::fprintf(stderr, "usage: kgl_plugin_harness IN.flat WORK_DIR [options]\n"); return false; }

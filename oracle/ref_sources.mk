@@ -28,6 +28,7 @@ PLUGIN_TUS := \
   kgl_genomics/kgl_parser/kgl_hsgenealogy_parser.cpp \
   kgl_genomics/kgl_parser/kgl_hsgenome_aux.cpp \
   kgl_genomics/kgl_parser/kgl_square_parser.cpp \
+  kgl_genomics/kgl_parser/kgl_pf7_sample_parser.cpp kgl_genomics/kgl_parser/kgl_pf7_fws_parser.cpp \
   kel_io/kel_mt_buffer.cpp kel_io/kel_basic_io.cpp
 
 REF_INCLUDES := contrib/edlib kel_utility kel_thread kel_io kgl_genomics kel_app kel_math kgl_app \

@@ -245,13 +245,8 @@ std::optional<std::shared_ptr<const kgl::ContigReference>> kgl::GenomeReference:
   return std::nullopt;
 }
 
-// CalcFWS::writeGenomeResults (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:147) looks the published FWS of a sample up in the Pf7
-// metadata resource, whose parser needs the Boost-based file IO. The harness only calls CalcFWS::calcFwsStatistics; the
-// writer is never reached.
-double kgl::Pf7FwsResource::getFWS(const GenomeId_t&) const { return 0.0; }
-
-// HeteroHomoZygous::location_summary (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp) walks the Pf7 sample metadata (city /
-// country radii, FWS thresholds), whose parsers need the Boost-based file IO. The harness calls only the static per-offset
-// rule HeteroHomoZygous::updateVariantAnalysisType (:61-105); these two are never reached.
-std::vector<kgl::GenomeId_t> kgl::Pf7FwsResource::filterFWS(FwsFilterType, double, const std::vector<GenomeId_t>& sample_vector) const { return sample_vector; }
+// HeteroHomoZygous::location_summary (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:266-358) asks the Pf7 physical-distance
+// resource for the samples around a location; its parser needs the Boost-based file IO. Never reached: the harnesses assemble
+// the location summaries themselves (plugin_harness.cpp, runPfEMP). The two Pf7FwsResource members that kgl_ref_harness does not
+// link for real are in ref_stubs_pf7.cpp.
 std::vector<std::string> kgl::Pf7SampleLocation::sampleRadius(const std::string&, double, bool) const { return {}; }

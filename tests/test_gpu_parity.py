@@ -675,3 +675,46 @@ def test_count_limited_selection_and_locus_filter(gpu, multi):
     gpu.set_locus_filter(None)
     gpu.select_loci(spacing=40)
     assert np.array_equal(gpu.get_locus_selection(), sel_bits(O.select_all_pops(pop, spacing=40)))
+
+
+def test_hetero_homo_records_and_location_fis(gpu):
+    """kgl_b200_run_hetero_homo against the per-offset rule of HeteroHomoZygous::updateVariantAnalysisType restated on the codes and
+    side cells (pinned to the reference's translation unit by tests/test_plugin_dropin.py::test_pfemp_hetero_homo_csv_equals_reference_writer
+    and the golden hetero_homo arrays), and kgl_b200_location_fis against the formula of UpdateSampleLocation."""
+    from kgl_gene_b200.capi import location_fis
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(333, 6000, seed=44, missing_rate=0.01)
+    add_multi_allelic(pop, 500, seed=45, three_rate=0.002)
+    gpu.upload_population(pop)
+    hh = gpu.hetero_homo()
+    codes = pop.codes().astype(np.int64)
+    plain = np.ones(pop.n_loci, dtype=bool); plain[pop.multi_rows] = False
+    n1, n2, n3 = ((codes[plain] == c).sum(0) for c in (1, 2, 3))
+    cells = pop.multi_cells.astype(np.int64)
+    many = (cells == 0xFF).sum(0)
+    single = ((cells != 0) & (cells != 0xFF) & (cells >> 4 == 0)).sum(0)
+    same = ((cells != 0xFF) & (cells >> 4 != 0) & (cells >> 4 == (cells & 15))).sum(0)
+    diff = ((cells != 0xFF) & (cells >> 4 != 0) & (cells >> 4 != (cells & 15))).sum(0)
+    total = n1 + 2 * n2 + n3 + single + 2 * same + 2 * diff + 3 * many
+    assert np.array_equal(hh[:, 0], total) and np.array_equal(hh[:, 1], total) and not hh[:, 2].any() and not hh[:, 6].any()
+    assert np.array_equal(hh[:, 3], n2 + same + 2 * diff + 2 * many)
+    assert np.array_equal(hh[:, 4], 2 * diff + many)
+    assert np.array_equal(hh[:, 5], n1 + n3 + single)
+    # locations: 9 cities in 3 countries; a city with fewer than 20 QC-pass samples takes its country's aggregate
+    n = pop.n_genomes
+    city = (np.arange(n) % 9).astype(np.uint32)
+    city[:300] = (np.arange(300) % 8).astype(np.uint32)                   # city 8 is small
+    country = (9 + city // 3).astype(np.uint32)
+    qc = (np.arange(n) % 6 != 5).astype(np.uint8)
+    members = [np.flatnonzero(city == c) for c in range(9)] + [np.flatnonzero(country == 9 + k) for k in range(3)]
+    fis = location_fis(hh, members, city, country, qc, 20)
+    het, tot = (hh[:, 4] + hh[:, 5]).astype(np.float64), hh[:, 0].astype(np.float64)
+    for g in range(n):
+        loc = city[g] if qc[members[city[g]]].sum() >= 20 else country[g]
+        m = members[loc]
+        want = 0.0
+        if tot[m].sum() > 0 and tot[g] > 0:
+            h_exp = het[m].sum() / tot[m].sum()
+            want = (h_exp - het[g] / tot[g]) / h_exp
+        assert fis[g] == want, g
+    assert qc[members[8]].sum() < 20

@@ -133,3 +133,24 @@ def test_plugin_unphased_population(tmp_path):
     assert c_ref == c_new and sorted(r_ref) == sorted(r_new)
     for g, (_, vals) in r_ref.items():
         assert np.allclose(vals, r_new[g][1], rtol=2e-6, atol=2e-8)
+
+
+@needs_harness
+@pytest.mark.gpu
+@pytest.mark.parametrize("unphased", [True, False], ids=["pf7-unphased", "phased"])
+def test_pfemp_hetero_homo_csv_equals_reference_writer(tmp_path, unphased):
+    """kga_PfEMP's second consumer of the counting kernels (rows a17/a18): HeteroHomoB200 (host/kga_analysis_pfemp_b200.cpp) over
+    kgl_b200_run_hetero_homo + kgl_b200_location_fis against the reference's own HeteroHomoZygous -- analyzeVariantPopulation,
+    location aggregates, UpdateSampleLocation (Wright's F_IS incl. the city -> country fallback) and write_variant_results -- on a
+    Pf7-style population with multi-allelic sites: the two CSV files must be identical, F_IS column included."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(170, 2500, seed=41, spectrum="sfs", missing_rate=0.01, unphased=unphased, grouped=False)
+    add_multi_allelic(pop, 250, seed=42, three_rate=0.0)
+    work = run_harness(str(tmp_path), pop, "--pfemp")
+    ref = open(os.path.join(work, "PFEMP", "hetero_homo.csv")).read().splitlines()
+    new = open(os.path.join(work, "PFEMP_B200", "hetero_homo.csv")).read().splitlines()
+    assert len(ref) > 150 and ref[0] == new[0]
+    assert ref == new
+    fis = np.array([float(ln.split(",")[2]) for ln in ref[1:]])
+    het_diff = np.array([int(ln.split(",")[14]) for ln in ref[1:]])
+    assert np.count_nonzero(fis) > 100 and het_diff.sum() > 0          # F_IS is exercised; so is "Het Diff Minor (a;b)"
