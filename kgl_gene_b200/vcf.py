@@ -18,7 +18,8 @@ _AF_KEYS = ("AFR_AF", "AMR_AF", "EAS_AF", "EUR_AF", "SAS_AF", "AF")      # kgl_v
 
 
 class VcfStats(C.Structure):
-    _fields_ = [("records", C.c_uint64), ("kept", C.c_uint64), ("skipped_multi_allelic", C.c_uint64), ("skipped_non_snp", C.c_uint64),
+    _fields_ = [("records", C.c_uint64), ("kept", C.c_uint64), ("multi_allelic", C.c_uint64), ("skipped_too_many_alleles", C.c_uint64),
+                ("skipped_non_snp", C.c_uint64),
                 ("not_pass", C.c_uint64), ("malformed_genotypes", C.c_uint64), ("bytes", C.c_uint64), ("seconds", C.c_double)]
 
 
@@ -32,7 +33,8 @@ def _load():
             raise RuntimeError(f"{HOST_LIB_PATH} is missing: build it with `python kgl_gene_b200/build.py`")
         lib = C.CDLL(HOST_LIB_PATH)
         for name, res in (("n_genomes", C.c_uint64), ("n_loci", C.c_uint64), ("row_bytes", C.c_uint64), ("packed", C.c_void_p),
-                          ("af", C.c_void_p), ("offsets", C.c_void_p), ("contig", C.c_char_p)):
+                          ("af", C.c_void_p), ("offsets", C.c_void_p), ("contig", C.c_char_p), ("n_multi", C.c_uint64),
+                          ("multi_rows", C.c_void_p), ("multi_af", C.c_void_p), ("multi_cells", C.c_void_p)):
             fn = getattr(lib, "kgl_b200_vcf_" + name)
             fn.restype, fn.argtypes = res, [C.c_void_p]
         lib.kgl_b200_vcf_genome_name.restype, lib.kgl_b200_vcf_genome_name.argtypes = C.c_char_p, [C.c_void_p, C.c_uint64]
@@ -56,6 +58,12 @@ def ingest_vcf(path: str, unphased: bool = False, n_threads: int = 0, superpop=N
         packed = np.ctypeslib.as_array(C.cast(lib.kgl_b200_vcf_packed(h), C.POINTER(C.c_uint8)), shape=(l, rb)).copy() if l else np.zeros((0, rb), np.uint8)
         af = np.ctypeslib.as_array(C.cast(lib.kgl_b200_vcf_af(h), C.POINTER(C.c_float)), shape=(6, l)).copy() if l else np.zeros((6, 0), np.float32)
         offsets = np.ctypeslib.as_array(C.cast(lib.kgl_b200_vcf_offsets(h), C.POINTER(C.c_uint32)), shape=(l,)).copy() if l else np.zeros(0, np.uint32)
+        m = lib.kgl_b200_vcf_n_multi(h)
+        multi = None
+        if m:
+            multi = (np.ctypeslib.as_array(C.cast(lib.kgl_b200_vcf_multi_rows(h), C.POINTER(C.c_uint32)), shape=(m,)).copy(),
+                     np.ctypeslib.as_array(C.cast(lib.kgl_b200_vcf_multi_af(h), C.POINTER(C.c_float)), shape=(6, m, 3)).copy(),
+                     np.ctypeslib.as_array(C.cast(lib.kgl_b200_vcf_multi_cells(h), C.POINTER(C.c_uint8)), shape=(m, n)).copy())
         names = [lib.kgl_b200_vcf_genome_name(h, i).decode() for i in range(n)]
         contig = lib.kgl_b200_vcf_contig(h).decode()
         st = VcfStats()
@@ -64,7 +72,10 @@ def ingest_vcf(path: str, unphased: bool = False, n_threads: int = 0, superpop=N
     finally:
         lib.kgl_b200_vcf_free(h)
     sp = np.full(n, SUPER_POPULATIONS.index("ALL"), dtype=np.uint8) if superpop is None else np.ascontiguousarray(superpop, dtype=np.uint8)
-    return FlatPopulation(offsets, af, sp, packed, int(n), bool(unphased)), names, contig, stats
+    pop = FlatPopulation(offsets, af, sp, packed, int(n), bool(unphased))
+    if multi is not None:
+        pop.multi_rows, pop.multi_af, pop.multi_cells = multi
+    return pop, names, contig, stats
 
 
 def write_vcf(pop: FlatPopulation, path: str, contig: str = "22", names=None, missing_as: str = ".", extra_lines=()):
@@ -88,7 +99,27 @@ def write_vcf(pop: FlatPopulation, path: str, contig: str = "22", names=None, mi
         f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
         for text in extra.get(-1, []):
             f.write(text + "\n")
+        multi_of = {int(r): m for m, r in enumerate(pop.multi_rows)} if pop.n_multi else {}
+        alt_bases = "GCT"
         for l in range(pop.n_loci):
+            if l in multi_of:
+                # a multi-allelic locus: ALT = its allele slots, Number=A frequencies per slot ("." = none), genotypes from the
+                # side cells (phase A = first variant, phase B = second; slot 4 and 0xFF cannot be written: not generated here)
+                m = multi_of[l]
+                n_slots = max(a + 1 for a in range(3) if not np.all(np.isnan(pop.multi_af[:, m, a])))
+                info = ";".join(f"{k}=" + ",".join("." if np.isnan(pop.multi_af[i, m, a]) else repr(float(pop.multi_af[i, m, a])) for a in range(n_slots))
+                                for i, k in enumerate(_AF_KEYS) if not np.all(np.isnan(pop.multi_af[i, m, :n_slots]))) or "."
+                cells = []
+                for g, c in enumerate(pop.multi_cells[m]):
+                    a, b = int(c) & 15, int(c) >> 4
+                    if pop.unphased:
+                        cells.append(f"{a}/{b}" if b else f"0/{a}" if a else "0/0")
+                    else:
+                        cells.append(f"{a}|{b}" if b else ((f"{a}|0" if (g + l) % 2 else f"0|{a}") if a else "0|0"))
+                f.write(f"{contig}\t{int(pop.offsets[l]) + 1}\t.\tA\t{','.join(alt_bases[:n_slots])}\t100\tPASS\t{info}\tGT\t" + "\t".join(cells) + "\n")
+                for text in extra.get(l, []):
+                    f.write(text + "\n")
+                continue
             info = ";".join(f"{k}={float(pop.af[i, l])!r}" for i, k in enumerate(_AF_KEYS) if not np.isnan(pop.af[i, l])) or "."
             row = codes[l]
             cells = [(alt_het if (c == 1 and (g + l) % 2) else gts[int(c)]) for g, c in enumerate(row)]

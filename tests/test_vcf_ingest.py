@@ -45,23 +45,51 @@ def test_edge_rules(tmp_path):
     path = str(tmp_path / "e.vcf")
     base = int(pop.offsets[-1]) + 100
     extra = [
-        (5, f"22\t{base}\t.\tA\tG,T\t100\tPASS\tAF=0.1,0.2\tGT\t0|1\t1|2\t0|0\t2|2"),            # multi-allelic: left out
+        (5, f"22\t{base}\t.\tA\tG,T\t100\tPASS\tAF=0.1,0.2;EUR_AF=.,0.4\tGT\t0|1\t1|2\t0|0\t2|2"),   # two SNP alleles: a multi-allelic row
         (5, f"22\t{base + 10}\t.\tAT\tA\t100\tPASS\tAF=0.1\tGT\t0|1\t0|0\t0|0\t1|1"),              # indel: left out
         (5, f"22\t{base + 20}\t.\tA\tG\t100\tq10\tAF=0.25\tGT\t0|1\t1|1\t0|0\t.|1"),                # not PASS: kept, AF -> NaN
         (5, f"22\t{base + 30}\t.\tA\tG\t100\tPASS\tEUR_AF=0.5;AF=0.125;DP=7\tGT:DP\t1|0:3\t0|2:1\t1:9\t-|1:2"),
-        (5, f"22\t{base + 40}\t.\tC\tT\t100\tPASS\tAF=0.3\tGT\t0|1\t0|0\t0|0\t0|0"),                # repeated POS below: both dropped
-        (5, f"22\t{base + 40}\t.\tC\tA\t100\tPASS\tAF=0.1\tGT\t0|0\t0|1\t0|0\t0|0"),
+        (5, f"22\t{base + 40}\t.\tC\tT\t100\tPASS\tAF=0.3\tGT\t0|1\t0|0\t0|0\t1|1"),                # repeated POS: one offset, two alleles
+        (5, f"22\t{base + 40}\t.\tC\tA\t100\tPASS\tAF=0.1\tGT\t0|0\t0|1\t0|0\t1|0"),
+        (5, f"22\t{base + 50}\t.\tA\tG,AT\t100\tPASS\tAF=0.2,0.01\tGT\t0|1\t1|2\t2|2\t2|0"),          # SNP + indel: the indel vanishes
     ]
     write_vcf(pop, path, extra_lines=extra)
     got, _, _, st = ingest_vcf(path, n_threads=1)
-    assert st["records"] == 12 and st["kept"] == 8 and st["skipped_multi_allelic"] == 3 and st["skipped_non_snp"] == 1
+    assert st["records"] == 13 and st["kept"] == 11 and st["multi_allelic"] == 2 and st["skipped_non_snp"] == 1
     assert st["not_pass"] == 1
-    assert got.offsets.tolist()[6:] == [base + 20 - 1, base + 30 - 1]
-    assert np.all(np.isnan(got.af[:, 6]))                                               # not PASS
-    assert got.codes()[6].tolist() == [1, 2, 0, 1]                                      # ".|1": "." is the reference allele
+    assert got.offsets.tolist()[6:] == [base - 1, base + 20 - 1, base + 30 - 1, base + 40 - 1, base + 50 - 1]
+    # the multi-allelic rows: no value in the frequency table, 0 / 3 in the matrix, the alleles in the side structures
+    assert got.multi_rows.tolist() == [6, 9]
+    assert np.all(np.isnan(got.af[:, 6])) and got.codes()[6].tolist() == [3, 3, 0, 3]
+    assert got.multi_cells[0].tolist() == [1, 1 | (2 << 4), 0, 2 | (2 << 4)]            # 0|1, 1|2, 0|0, 2|2
+    assert got.multi_af[5, 0].tolist()[:2] == [np.float32(0.1), np.float32(0.2)] and np.isnan(got.multi_af[5, 0, 2])
+    assert np.isnan(got.multi_af[3, 0, 0]) and got.multi_af[3, 0, 1] == np.float32(0.4)     # EUR_AF=.,0.4
+    assert got.multi_cells[1].tolist() == [1, 2, 0, 0xFF]                               # T, T and A: three variants at the offset
+    assert np.all(np.isnan(got.af[:, 7]))                                               # not PASS
+    assert got.codes()[7].tolist() == [1, 2, 0, 1]                                      # ".|1": "." is the reference allele
     # 1|0 -> het; 0|2 -> index beyond the ALT list: whole genotype reference; "1" haploid on an autosome: reference; -|1 het
-    assert got.codes()[7].tolist() == [1, 0, 0, 1] and st["malformed_genotypes"] == 2
-    assert got.af[5, 7] == np.float32(0.125) and got.af[3, 7] == np.float32(0.5) and np.isnan(got.af[0, 7])
+    assert got.codes()[8].tolist() == [1, 0, 0, 1] and st["malformed_genotypes"] == 2
+    assert got.af[5, 8] == np.float32(0.125) and got.af[3, 8] == np.float32(0.5) and np.isnan(got.af[0, 8])
+    # G + an insertion: one SNP allele -> an ordinary row; the insertion is not a SNP and vanishes from the genome's offset array
+    assert got.codes()[10].tolist() == [1, 1, 0, 0] and got.af[5, 10] == np.float32(0.2)
+
+
+def test_round_trip_multi_allelic(tmp_path):
+    """A population with multi-allelic loci through VCF text and back: allele slots = ALT order, frequencies per slot from the
+    Number=A fields, side cells = (phase A allele, phase B allele)."""
+    from kgl_gene_b200.synth import add_multi_allelic
+    for unphased in (False, True):
+        pop, _ = make_population(70, 500, seed=8, missing_rate=0.0, unphased=unphased)
+        add_multi_allelic(pop, 60, seed=9, unknown_rate=0.0, three_rate=0.0)
+        path = str(tmp_path / f"m{int(unphased)}.vcf.gz")
+        write_vcf(pop, path)
+        got, _, _, st = ingest_vcf(path, unphased=unphased, n_threads=2)
+        assert st["kept"] == 500 and st["multi_allelic"] == 60
+        assert np.array_equal(got.offsets, pop.offsets) and np.array_equal(got.codes(), pop.codes())
+        assert np.array_equal(got.af.view(np.uint32), pop.af.view(np.uint32))
+        assert np.array_equal(got.multi_rows, pop.multi_rows) and np.array_equal(got.multi_cells, pop.multi_cells)
+        both = ~(np.isnan(got.multi_af) | np.isnan(pop.multi_af))
+        assert np.array_equal(np.isnan(got.multi_af), np.isnan(pop.multi_af)) and np.array_equal(got.multi_af[both], pop.multi_af[both])
 
 
 def test_ingested_population_feeds_the_oracle(tmp_path):
