@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -95,10 +96,17 @@ void parse_info(const char* b, const char* e, std::vector<Alt>& alts) {
           for (size_t a = 0; a < alts.size() && v <= fe; ++a) {
             const char* comma = static_cast<const char*>(std::memchr(v, ',', (size_t)(fe - v)));
             const char* ve = comma ? comma : fe;
+            // VCFInfoParser::convertToFloat (vcf_parse_info.cpp:208-270): std::stof; "." / "NaN" / anything that is not a
+            // number -> MISSING_VALUE_FLOAT_ = the lowest float, which IS a value (the allele is in the frequency list, its
+            // frequency clamps to 0, freq.cpp:47); out of range -> the smallest / largest float
             const std::string val(v, (size_t)(ve - v));
             char* endp = nullptr;
-            const float f = std::strtof(val.c_str(), &endp);        // std::stof of the reference (vcf_parse_info.cpp:232)
-            if (endp != val.c_str()) alts[a].af[k] = f;
+            errno = 0;
+            float f = std::strtof(val.c_str(), &endp);
+            const bool is_nan_text = val.size() == 3 && (val[0] | 0x20) == 'n' && (val[1] | 0x20) == 'a' && (val[2] | 0x20) == 'n';
+            if (endp == val.c_str() || is_nan_text) f = std::numeric_limits<float>::lowest();
+            else if (errno == ERANGE) f = (std::fabs(f) < 1.0f) ? std::numeric_limits<float>::min() : std::numeric_limits<float>::max();
+            alts[a].af[k] = f;
             if (!comma) break;
             v = comma + 1;
           }

@@ -20,6 +20,8 @@
 #include "kga_analysis_inbreed_b200.h"
 #include "kga_analysis_pfemp_b200.h"
 #include "kga_analysis_PfEMP_heterozygous.h"
+#include "kgl_variant_factory_1000_impl.h"
+#include "kgl_variant_factory_vcf_evidence_analysis.h"
 
 #include "flat_io.h"
 #include "ref_population.h"
@@ -48,6 +50,7 @@ struct Options {
   std::string min_af{"0.0"}, max_af{"1.0"}, spacing{"0"}, count{"1000"}, lower{"0"}, upper{"1000000000"};
   bool run_reference{true}, run_b200{true};
   bool pfemp{false};          // --pfemp: the kga_PfEMP consumer (HeteroHomoZygous) instead of the INBREED analysis
+  bool vcf{false};            // --vcf: IN is a plain-text VCF, parsed by the reference's own 1000 Genomes parser
 };
 Options g_opt;
 
@@ -151,7 +154,43 @@ void runPfEMP(const kglflat::Flat& flat) {
   }
 }
 
+// ---- N2 pin: the reference's own VCF parser (Genome1000VCFImpl over VCFReaderMT / ParseVCF, kgl_parser/kgl_variant_factory_1000_impl.cpp,
+// kgl_variant_factory_readvcf_impl.cpp, kgl_variant_vcf_impl.cpp) reads a plain-text VCF into a PopulationDB; the product's
+// flattener (flattenSelf: the population as its own locus list, frequency = the variant's INFO AF) turns it into the flat form,
+// which tests/test_plugin_dropin.py compares cell by cell with what kgl_b200_vcf_ingest makes of the same file.
+void runVcf() {
+  auto population = std::make_shared<kgl::PopulationDB>("VCF_POPULATION", kgl::DataSourceEnum::Genome1000);
+  kgl::ContigAliasMap alias_map;
+  alias_map.setAlias("22", "22", "autosome");
+  kgl::EvidenceInfoSet info_set;
+  for (int k = 0; k < 6; ++k) info_set.insert(kglref::afFields(kgl::DataSourceEnum::Genome1000)[k]);
+  kgl::Genome1000VCFImpl parser(population, nullptr, alias_map, info_set);
+  parser.readParseVCFImpl(g_opt.in_path);
+  auto allele_frequency = [](const kgl::Variant& variant) -> std::optional<double> {
+    auto info_opt = kgl::InfoEvidenceAnalysis::getTypedInfoData<std::vector<double>>(variant, "AF");
+    if (!info_opt) return std::nullopt;
+    const size_t alt_index = variant.evidence().altVariantIndex();
+    if (info_opt.value().size() <= alt_index) return std::nullopt;
+    return info_opt.value()[alt_index];
+  };
+  auto flat_opt = kgl::b200::PopulationFlattener::flattenSelf(*population, "22", allele_frequency, false);
+  if (!flat_opt) { std::fprintf(stderr, "[plugin] vcf: flatten failed\n"); g_exit_code = 7; return; }
+  auto const& f = flat_opt.value();
+  kglflat::Flat out;
+  std::memset(&out.hdr, 0, sizeof out.hdr);
+  out.hdr.n_genomes = uint32_t(f.nGenomes()); out.hdr.n_loci = uint32_t(f.nLoci()); out.hdr.n_superpop = 6;
+  out.hdr.row_bytes = uint32_t(f.row_bytes); out.hdr.reserved[0] = uint32_t(f.nMulti());
+  out.offsets = f.offsets; out.af = f.af; out.superpop = f.superpop; out.packed = f.packed;
+  out.multi_rows = f.multi_rows; out.multi_af = f.multi_af; out.multi_cells = f.multi_cells;
+  kglflat::writeFlat(g_opt.work_dir + "/flattened.flat", out);
+  std::ofstream ids(g_opt.work_dir + "/flattened_genomes.txt");
+  for (auto const& id : f.genome_ids) ids << id << '\n';
+  std::fprintf(stderr, "[plugin] vcf: reference parser -> %zu genomes, %zu variant entries; flattened %zu loci (%zu multi-allelic)\n",
+               population->getMap().size(), population->variantCount(), size_t(f.nLoci()), size_t(f.nMulti()));
+}
+
 void run() {
+  if (g_opt.vcf) { runVcf(); return; }
   const kglflat::Flat flat = kglflat::readFlat(g_opt.in_path);
   if (g_opt.pfemp) { runPfEMP(flat); return; }
   const bool unphased = (flat.hdr.flags & kglflat::FLAG_UNPHASED) != 0;
@@ -251,6 +290,7 @@ class PluginHarnessEnv {
       else if (a == "--no-reference") g_opt.run_reference = false;
       else if (a == "--no-b200") g_opt.run_b200 = false;
       else if (a == "--pfemp") g_opt.pfemp = true;
+      else if (a == "--vcf") g_opt.vcf = true;
       else pos.push_back(a);
     }
     if (pos.size() != 2) { std::fprintf(stderr, "usage: kgl_plugin_harness IN.flat WORK_DIR [options]\n"); return false; }

@@ -29,6 +29,8 @@ PLUGIN_TUS := \
   kgl_genomics/kgl_parser/kgl_hsgenome_aux.cpp \
   kgl_genomics/kgl_parser/kgl_square_parser.cpp \
   kgl_genomics/kgl_parser/kgl_pf7_sample_parser.cpp kgl_genomics/kgl_parser/kgl_pf7_fws_parser.cpp \
+  kgl_genomics/kgl_parser/kgl_variant_vcf_impl.cpp kgl_genomics/kgl_parser/kgl_variant_factory_readvcf_impl.cpp \
+  kgl_genomics/kgl_parser/kgl_variant_factory_1000_impl.cpp \
   kel_io/kel_mt_buffer.cpp kel_io/kel_basic_io.cpp
 
 REF_INCLUDES := contrib/edlib kel_utility kel_thread kel_io kgl_genomics kel_app kel_math kgl_app \

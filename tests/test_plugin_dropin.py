@@ -154,3 +154,69 @@ def test_pfemp_hetero_homo_csv_equals_reference_writer(tmp_path, unphased):
     fis = np.array([float(ln.split(",")[2]) for ln in ref[1:]])
     het_diff = np.array([int(ln.split(",")[14]) for ln in ref[1:]])
     assert np.count_nonzero(fis) > 100 and het_diff.sum() > 0          # F_IS is exercised; so is "Het Diff Minor (a;b)"
+
+
+def _carried_alleles(pop, col):
+    """{offset: list per genome of the sorted frequency values (column `col`) of the alleles the genome carries there}."""
+    out = {}
+    codes = pop.codes()
+    multi_of = {int(r): m for m, r in enumerate(pop.multi_rows)} if pop.n_multi else {}
+    for l in range(pop.n_loci):
+        if l in multi_of:
+            m = multi_of[l]
+            rows = []
+            for c in pop.multi_cells[m]:
+                c = int(c)
+                assert c != 0xFF and (c & 15) != 4 and (c >> 4) != 4
+                slots = [s - 1 for s in (c & 15, c >> 4) if s]
+                rows.append(sorted(float(pop.multi_af[col, m, s]) for s in slots))
+        else:
+            a = float(pop.af[col, l])
+            rows = [[a] * int(c) if c < 3 else None for c in codes[l]]
+        out[int(pop.offsets[l])] = rows
+    return out
+
+
+@needs_harness
+def test_vcf_ingest_equals_the_reference_vcf_parser(tmp_path):
+    """N2 pinned against the reference's own parser: the same plain-text VCF (bi- and multi-allelic sites, a repeated POS, "."
+    alleles, a GT with extra FORMAT fields) goes (a) through Genome1000VCFImpl / VCFReaderMT / ParseVCF
+    (kgl_variant_factory_1000_impl.cpp:63-272, compiled into the harness) into a PopulationDB, flattened by the product's
+    flattener, and (b) through kgl_b200_vcf_ingest. Every genome must carry the same alleles at every offset."""
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    from kgl_gene_b200.vcf import ingest_vcf, write_vcf
+    pop, _ = make_population(60, 600, seed=12, missing_rate=0.01)
+    add_multi_allelic(pop, 70, seed=13, unknown_rate=0.0, three_rate=0.0)
+    rng = np.random.default_rng(3)
+    nan = np.isnan(pop.multi_af[5]) & (np.arange(3)[None, :] < 2)          # every listed allele gets an "AF" value (the comparison key)
+    pop.multi_af[5][nan] = rng.uniform(0.01, 0.3, size=int(nan.sum())).astype(np.float32)
+    base = int(pop.offsets[-1]) + 100
+    extra = [
+        (5, f"22\t{base}\t.\tC\tT\t100\tPASS\tAF=0.31\tGT\t" + "\t".join(["0|1", "1|1", "0|0"] * 20)),          # repeated POS:
+        (5, f"22\t{base}\t.\tC\tA\t100\tPASS\tAF=0.11\tGT\t" + "\t".join(["0|0", "0|0", "1|0"] * 20)),          #   one offset, two alleles
+        (5, f"22\t{base + 10}\t.\tA\tG\t100\tPASS\tAF=0.125;DP=7\tGT:DP\t" + "\t".join(["1|0:3", ".|1:1", "0|0:9"] * 20)),
+    ]
+    path = str(tmp_path / "pin.vcf")
+    write_vcf(pop, path, extra_lines=extra)
+    ours, names, _, st = ingest_vcf(path, n_threads=2)
+    assert st["multi_allelic"] == 71
+    work = os.path.join(str(tmp_path), "work")
+    env = dict(os.environ, KGL_REF_LOG=os.path.join(str(tmp_path), "harness.log"))
+    r = subprocess.run([HARNESS, path, work, "--vcf"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = FlatPopulation.read(os.path.join(work, "flattened.flat"))
+    ids = [ln.strip() for ln in open(os.path.join(work, "flattened_genomes.txt"))]
+    cols = [names.index(i) for i in ids]
+    want = _carried_alleles(ref, 5)
+    got = _carried_alleles(ours, 5)
+    assert set(want) <= set(got) and len(want) > 500
+    for offset, rows in got.items():
+        if offset in want:
+            assert [rows[c] for c in cols] == want[offset], offset
+        else:                                  # an offset no genome carries a SNP at: absent from the variant DB
+            assert all(r == [] for r in rows), offset
+    # genomes that are absent from the variant DB carry nothing anywhere
+    absent = [g for g in range(len(names)) if g not in cols]
+    for rows in got.values():
+        assert all(rows[g] == [] for g in absent)

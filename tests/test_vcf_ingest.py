@@ -63,7 +63,8 @@ def test_edge_rules(tmp_path):
     assert np.all(np.isnan(got.af[:, 6])) and got.codes()[6].tolist() == [3, 3, 0, 3]
     assert got.multi_cells[0].tolist() == [1, 1 | (2 << 4), 0, 2 | (2 << 4)]            # 0|1, 1|2, 0|0, 2|2
     assert got.multi_af[5, 0].tolist()[:2] == [np.float32(0.1), np.float32(0.2)] and np.isnan(got.multi_af[5, 0, 2])
-    assert np.isnan(got.multi_af[3, 0, 0]) and got.multi_af[3, 0, 1] == np.float32(0.4)     # EUR_AF=.,0.4
+    # EUR_AF=.,0.4: "." inside a list is the parser's MISSING_VALUE_FLOAT_ (the lowest float), a value -- not an absent field
+    assert got.multi_af[3, 0, 0] == np.finfo(np.float32).min and got.multi_af[3, 0, 1] == np.float32(0.4)
     assert got.multi_cells[1].tolist() == [1, 2, 0, 0xFF]                               # T, T and A: three variants at the offset
     assert np.all(np.isnan(got.af[:, 7]))                                               # not PASS
     assert got.codes()[7].tolist() == [1, 2, 0, 1]                                      # ".|1": "." is the reference allele
@@ -88,8 +89,17 @@ def test_round_trip_multi_allelic(tmp_path):
         assert np.array_equal(got.offsets, pop.offsets) and np.array_equal(got.codes(), pop.codes())
         assert np.array_equal(got.af.view(np.uint32), pop.af.view(np.uint32))
         assert np.array_equal(got.multi_rows, pop.multi_rows) and np.array_equal(got.multi_cells, pop.multi_cells)
-        both = ~(np.isnan(got.multi_af) | np.isnan(pop.multi_af))
-        assert np.array_equal(np.isnan(got.multi_af), np.isnan(pop.multi_af)) and np.array_equal(got.multi_af[both], pop.multi_af[both])
+        # a "." inside a Number=A list comes back as the reference parser's missing-value float (the lowest float), an absent
+        # field as NaN: a slot that is NaN for a population that has values for other slots is written as "."
+        lowest = np.finfo(np.float32).min
+        want = pop.multi_af.copy()
+        n_slots = (~np.isnan(pop.multi_af)).any(axis=0).cumsum(axis=1).argmax(axis=1) + 1          # slots the locus lists
+        for k in range(6):
+            for m in range(pop.n_multi):
+                if not np.all(np.isnan(want[k, m, :n_slots[m]])):
+                    want[k, m, :n_slots[m]] = np.where(np.isnan(want[k, m, :n_slots[m]]), lowest, want[k, m, :n_slots[m]])
+        both = ~(np.isnan(got.multi_af) | np.isnan(want))
+        assert np.array_equal(np.isnan(got.multi_af), np.isnan(want)) and np.array_equal(got.multi_af[both], want[both])
 
 
 def test_ingested_population_feeds_the_oracle(tmp_path):
