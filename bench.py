@@ -32,9 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries exactly one JSON line. Libraries write there too (NCCL prints "NCCL version ..." to stdout from C), so
 # file descriptor 1 is pointed at stderr for the life of the process and the JSON line goes to a private copy of the
-# original stdout.
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# original stdout. (NCCL_DEBUG is left as the caller set it.)
 _JSON_FD = None
 
 
@@ -58,7 +56,13 @@ N_LOCI = 1_100_000
 SEED = 20261018
 METRIC = "inbreeding genotype-loci/s"
 UNIT = "genotype-loci/s"
-CPU_SAMPLE = (512, 20_000)      # genomes x loci of the bounded CPU sample (same generator, same law)
+# Bounded samples of the reference CPU path (BASELINE.md section 4 / SURVEY 8d: 2,504 genomes x 50,000 loci; the reference
+# cannot materialise config 2 as a PopulationDB). --impl reference times the BASELINE sample (~25 s per repeat on 15 threads,
+# so at most REFERENCE_MAX_REPEATS repeats: the run stays within a few minutes); the cpu_baseline object of the GPU arm
+# uses a 20,000-locus prefix of the same population (~10 s per repeat).
+REFERENCE_SAMPLE = (2504, 50_000)
+CPU_SAMPLE = (2504, 20_000)
+REFERENCE_MAX_REPEATS = 6
 
 
 def parse_args():
@@ -76,8 +80,10 @@ def parse_args():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-genome partial sums of the locus shards meet -- 'peer': inside the step's own kernel over "
                          "NVLink peer memory (CUDA IPC); 'nccl': an NCCL all-reduce between the step's kernels")
-    ap.add_argument("--kinship-loci", type=int, default=0, help="loci of the pairwise run (0 = the resident chr22-shape matrix)")
+    ap.add_argument("--kinship-loci", type=int, default=20_000_000,
+                    help="loci of the pairwise run (default: BASELINE config 4, 20 M SNPs; 0 = the resident chr22-shape matrix)")
     ap.add_argument("--kinship-steps", type=int, default=3)
+    ap.add_argument("--reference-sample", default="", help="--impl reference: GENOMESxLOCI of the CPU sample (default 2504x50000, BASELINE.md section 4)")
     return ap.parse_args()
 
 
@@ -99,13 +105,16 @@ def workload_name(n, l, world):
 
 
 # --------------------------------------------------------------------------------------------- CPU baseline ---------
-def cpu_reference_run(repeat: int):
+def cpu_reference_run(repeat: int, sample=None):
     """Times the reference CPU path on the bounded sample. Returns dict(value, cores, kind, sample, seconds list)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    from kgl_gene_b200.synth import make_population
-    n, l = CPU_SAMPLE
-    pop, _ = make_population(n, l, seed=SEED, spectrum="sfs")
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import make_genomes, make_loci
+    n, l = sample or CPU_SAMPLE
+    offsets, af = make_loci(l, SEED)                      # the bench generator: the first l loci of the population the GPU arm times
+    superpop, inbreeding = make_genomes(n, SEED)
+    pop = FlatPopulation(offsets, af, superpop, O.synth_genotypes(SEED, n, l, af, superpop, inbreeding), n, False)
     cells = float(n) * float(l)
     if O.have_reference_harness():
         out = O.run_reference(pop, algos=("Simple",), variantdb=False, repeat=repeat, timeout=3000)
@@ -156,16 +165,22 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps + args.warmup)
-    secs = r["seconds"][args.warmup:] if len(r["seconds"]) > args.warmup else r["seconds"]
+    repeats = max(1, min(args.steps + args.warmup, REFERENCE_MAX_REPEATS))
+    warm = min(args.warmup, repeats - 1, 1)               # at most one untimed repeat: the reference has no caches to warm
+    sample = REFERENCE_SAMPLE
+    if args.reference_sample:
+        sample = tuple(int(x) for x in args.reference_sample.lower().split("x"))
+    r = cpu_reference_run(repeats, sample)
+    secs = r["seconds"][warm:]
     mean = float(np.mean(secs))
     value = r["cells"] / mean
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
-        "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.genomes, args.loci, 1),
-                   "note": "reference CPU path timed on a bounded sample of this workload; value is per-unit throughput"},
+                   "note": "reference CPU path timed on a bounded sample of this workload (BASELINE.md section 4: 2,504 genomes x 50,000 loci); "
+                           "value is per-unit throughput; repeats capped so that the run ends within a few minutes"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -386,6 +401,37 @@ def run_ours(args):
                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps}
         lc2 = h_lc.numpy().view(np.uint32)
         assert np.array_equal(lc2, lc), "e2e per-locus counts differ from the resident run"
+        # What the host can deliver: the matrix alone, one cudaMemcpyAsync from the same pinned buffer, every rank at once (the
+        # ranks of one box share its memory controllers and PCIe switches: the e2e step is this copy plus ~1 ms)
+        d_tmp = torch.empty((l, rb), dtype=torch.uint8, device=dev)
+        bare_ms = timed(lambda: d_tmp.copy_(h_packed, non_blocking=True), 3, 1) / 3
+        e2e["bare_matrix_h2d_ms"] = bare_ms
+        e2e["bare_matrix_h2d_gbs_per_gpu"] = l * rb / (bare_ms * 1e-3) / 1e9
+        e2e["bare_matrix_h2d_gbs_all_gpus"] = world * l * rb / (bare_ms * 1e-3) / 1e9
+        del d_tmp
+        if world == 1:
+            # The plugin's real shape (kga_analysis_inbreed_b200.cpp): ONE upload per iteration, then the window loop for every
+            # parameter block -- here 20 windows of 55,000 loci x the four algorithms, results fetched to the host per window.
+            n_windows, per = 20, l // 20
+            t0 = time.perf_counter()
+            ctx.upload_genotypes_ptr(h_packed.data_ptr(), n, l, rb)
+            ctx.upload_loci(af_np, off_np)
+            ctx.set_genome_superpop(superpop)
+            ctx.synchronize()
+            t_upload = time.perf_counter() - t0
+            per_algo = {}
+            for algorithm in ("Simple", "RitlandLocus", "HallME", "Loglikelihood"):
+                t1 = time.perf_counter()
+                for w in range(n_windows):
+                    ctx.select_loci(lower=int(off_np[w * per]), upper=int(off_np[min(l, (w + 1) * per) - 1]))
+                    ctx.inbreed(algorithm)
+                per_algo[algorithm] = (time.perf_counter() - t1) * 1e3
+            total = time.perf_counter() - t0
+            e2e["plugin_shape"] = {"windows": n_windows, "loci_per_window": per, "algorithms": 4, "upload_ms": t_upload * 1e3,
+                                   "ms_per_algorithm": per_algo, "ms_total": total * 1e3,
+                                   "genotype_loci_per_s": 4.0 * n * per * n_windows / total,
+                                   "note": "one upload (matrix, AF, super-populations), then select_loci + run_inbreed with host results "
+                                           "for every window and algorithm; host wall clock"}
 
     est = None
     if not args.no_estimators:
@@ -560,7 +606,7 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
     value = pair_loci * steps / (ms * 1e-3)
     # end to end: host matrix in, host tiles out
     e2e = None
-    if not args.no_e2e and world == 1 and mine <= SLAB:
+    if not args.no_e2e and world == 1 and mine <= SLAB and kl <= 2_000_000:     # (12.5 GB of pinned host memory at 20 M loci: skipped)
         import ctypes as C
         h_packed = torch.empty((kl, rb), dtype=torch.uint8, pin_memory=True)
         ctx._check(ctx.lib.kgl_b200_download_genotypes(ctx.h, C.c_uint64(kl * rb), C.c_void_p(h_packed.data_ptr())), "download_genotypes")
@@ -628,6 +674,8 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
             "roofline": {"bound": "int-pipe (ALU/LOP3)", "kernel": "k_ibs_tiles<false,2> (+ k_ibs_missing_fix, k_ibs_finalize)",
                          "achieved": achieved, "peak": peak, "unit": "executed pair-loci/s",
                          "frac": (achieved / peak) if achieved else None,
+                         # on USEFUL pair-loci (N (N + 1) / 2 pairs: no padding genomes, diagonal tiles counted once), whole step
+                         "frac_useful": value / world / peak,
                          "peak_source": "62.45 LOP3/clk/SM (measured, kbench) x 148 SMs x 1.965 GHz / 5 LOP3 per 32 pair-loci",
                          "survey_8d_peak_popc_bound": POPC_PER_CLK_SM * sms * clk / 3.0 * 32.0,
                          "kernel_ms": k_s * 1e3 if k_s else None}}

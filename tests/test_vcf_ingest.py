@@ -1,7 +1,8 @@
 """N2: VCF genotype columns -> packed 2-bit matrix without a PopulationDB (kgl_gene_b200/host/kgl_b200_vcf_ingest.cpp).
 Round trips through VCF text, plus the reference parsers' edge rules (kgl_variant_factory_1000_impl.cpp:148-272,
-kgl_variant_factory_pf_impl.cpp:139-152). The reference's own VCF reader does not link here (Boost iostreams), so these
-rules are pinned by citation, not by its binary."""
+kgl_variant_factory_pf_impl.cpp:139-152). The 1000 Genomes rules are pinned against the reference's own parser in
+tests/test_plugin_dropin.py::test_vcf_ingest_equals_the_reference_vcf_parser (Genome1000VCFImpl / VCFReaderMT / ParseVCF compiled
+into the harness); the Pf7 parser needs a GenomeReference (FASTA / GFF readers: Boost) and stays pinned by citation."""
 import os
 
 import numpy as np
