@@ -432,6 +432,7 @@ def run_ours(args):
                                    "genotype_loci_per_s": 4.0 * n * per * n_windows / total,
                                    "note": "one upload (matrix, AF, super-populations), then select_loci + run_inbreed with host results "
                                            "for every window and algorithm; host wall clock"}
+            ctx.select_loci()                  # back to one window = all loci for what follows
 
     est = None
     if not args.no_estimators:

@@ -542,6 +542,7 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   P.locus_counts = want_locus_counts ? c->d_locus_counts.p : nullptr;
   P.cta_counts = want_genome ? c->d_cta_counts[c->cbuf].p : nullptr;
   P.n_genomes_padded = (uint32_t)c->Npad;
+  stream_make_tensor_map(P, pl, c->padded_rows);          // wide populations: one 2-D TMA box per stage
   cudaEvent_t e0 = c->ev0, e1 = c->ev1;
   if (c->timer_used < kgl_b200_ctx::kTimerSlots) {
     if ((int)c->timer_ev.size() < 2 * (c->timer_used + 1)) {

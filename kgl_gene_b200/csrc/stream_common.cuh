@@ -4,6 +4,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cuda.h>       // CUtensorMap (the type only: cuTensorMapEncodeTiled is looked up through the runtime, no libcuda link)
+
 namespace kgl {
 
 constexpr int kScConsumerWarps = 10;
@@ -16,6 +18,10 @@ constexpr int kScMaxStages = 8;
 constexpr int kScMaxSliceUnits = 56;           // 64 rows * 56 units * 16 B = 56 KB per stage
 
 struct StreamParams {
+  // Wide populations (row pitch of several 40-unit slices): 2-D tensor map over the matrix as uint32[padded_rows][units * 4], box
+  // = one stage of one slice (64 rows x 160 words): ONE cp.async.bulk.tensor per stage instead of 64 row copies of 640 bytes.
+  alignas(64) CUtensorMap tmap;
+  uint32_t use_tmap;
   const uint4* packed;        // [padded_rows][units]; rows >= n_loci are zero
   uint32_t units;             // 128-bit units per row
   uint32_t n_loci;
@@ -58,6 +64,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
+}
+__device__ __forceinline__ void tma_tensor2d_g2s(uint32_t dst, const CUtensorMap* tmap, uint32_t c0, uint32_t c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

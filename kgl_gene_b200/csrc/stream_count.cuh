@@ -90,7 +90,7 @@ __host__ __device__ constexpr int ct_threads(int su, int r) { return (kCtHWarps 
 // P.slice_units == SU, P.rows_per_stage == R, P.units a multiple of SU (the device row pitch is padded by the upload).
 template <int SU, int R, bool WANT_LOCUS, bool WANT_GENOME>
 __global__ void __maxnreg__(64)
-k_stream_count_ct(const StreamParams P) {
+k_stream_count_ct(const __grid_constant__ StreamParams P) {
   constexpr int PARTS = kScHThreads / R;        // lanes that share a row in the H role
   constexpr int HU = SU / PARTS;                // units per H thread
   static_assert(SU % PARTS == 0 && R % 64 == 0 && (SU * R) % 256 == 0, "shape");
@@ -140,9 +140,10 @@ k_stream_count_ct(const StreamParams P) {
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES + fbytes);
         if (fbytes) tma_bulk_g2s(smem_u32(s_flags + (size_t)s * R), P.flags16 + r0, fbytes, bar_full + 8 * s);
         if (contiguous) tma_bulk_g2s(dst, P.packed + r0 * P.units, STAGE_BYTES, bar_full + 8 * s);
+        else if (P.use_tmap) tma_tensor2d_g2s(dst, &P.tmap, unit0 * 4, (uint32_t)r0, bar_full + 8 * s);
       }
       __syncwarp();
-      if (!contiguous) {
+      if (!contiguous && !P.use_tmap) {
         for (uint32_t r = lane; r < (uint32_t)R; r += 32)
           tma_bulk_g2s(dst + r * SU * 16, P.packed + (r0 + r) * P.units + unit0, SU * 16, bar_full + 8 * s);
       }

@@ -16,6 +16,36 @@ inline cudaError_t stream_kernel_attributes(K kernel, size_t smem) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// 2-D tensor map of the matrix for the sliced <40,64> shape (box = 64 rows x 40 units). False: the driver entry point is not
+// available or the encode failed -- the kernel then falls back to one bulk copy per row.
+inline bool stream_make_tensor_map(StreamParams& P, const StreamPlan& pl, uint64_t padded_rows) {
+  P.use_tmap = 0;
+  if (pl.shape != 1 || pl.slices <= 1) return false;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    else cudaGetLastError();
+  }
+  if (!encode) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)P.units * 4, (cuuint64_t)padded_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)P.units * 16};                       // bytes between rows
+  const cuuint32_t box[2] = {pl.slice_units * 4, pl.rows_per_stage};
+  const cuuint32_t elem[2] = {1, 1};
+  const CUresult r = encode(&P.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint4*>(P.packed), dims, strides, box, elem,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  P.use_tmap = 1;
+  return true;
+}
+
 template <bool WL, bool WG>
 inline cudaError_t launch_stream_variant(const StreamParams& P, const StreamPlan& pl, cudaStream_t st) {
   dim3 grid(pl.n_ctas, pl.slices);

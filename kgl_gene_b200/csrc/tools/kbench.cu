@@ -301,6 +301,7 @@ int main(int argc, char** argv) {
     P.sum64 = flags_mode < 0 ? nullptr : d_sum64[flags_mode];
     P.need32 = d_need; P.popmask32 = d_popmask; P.n_pop = 6; P.locus_counts = wl ? d_lc : nullptr;
     P.cta_counts = wg ? planes : nullptr; P.n_genomes_padded = (uint32_t)(units * 64);
+    if (!getenv("KBENCH_NO_TMAP")) stream_make_tensor_map(P, pl, pad_rows);
     return P;
   };
 
