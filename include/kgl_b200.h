@@ -78,6 +78,16 @@ typedef struct kgl_b200_inbreed_options {
   /* != 0: the moments pass of kgl_b200_inbreed_accumulate also produces the per-locus allele counts of this rank's
    * locus shard (the fused pass of kgl_b200_run_count_and_inbreed, split around the all-reduce). */
   int32_t count_loci;
+  /* HallME / Loglikelihood sweeps: 0 = from the per-genome moment tables built once per selection (terms_moments.cuh; a sweep
+   * then reads no genotype), != 0 = every sweep evaluates every cell (the exact kernels, which the tables fall back to for
+   * genomes outside their domain). Both follow calc.cpp:94-129,257-285; they agree to < 1e-10. */
+  int32_t exact_sweeps;
+  /* != 0: the sparse half of the moment tables is built by the CUDA-core kernel (k_mom_build) instead of the tensor-core one
+   * (k_mom_mma). Same integers either way; the tensor-core builder is several times faster. */
+  int32_t moments_on_cuda_cores;
+  /* kgl_b200_run_inbreed only: != 0 = go through kgl_b200_inbreed_accumulate / kgl_b200_inbreed_update sweep by sweep (what a
+   * locus-sharded caller does around its all-reduce) instead of running all sweeps of all genomes in one launch over the tables. */
+  int32_t sweep_by_sweep;
 } kgl_b200_inbreed_options;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------------- */
@@ -151,6 +161,10 @@ int kgl_b200_run_allele_count(kgl_b200_ctx* ctx, uint32_t* locus_counts, uint64_
  * out[n_genomes]. options may be NULL. */
 int kgl_b200_run_inbreed(kgl_b200_ctx* ctx, int algorithm, const kgl_b200_inbreed_options* options,
                          kgl_b200_locus_results* out);
+
+/* The sweeps of the last HallME / Loglikelihood run on this context: 0 the exact kernels, 1 moment tables built on the CUDA cores,
+ * 2 moment tables built on the tensor cores. */
+int kgl_b200_inbreed_used_moment_tables(const kgl_b200_ctx* ctx);
 
 /* The fused streaming pass the benchmark times: one read of the genotype matrix yields the per-locus allele counts
  * AND the per-genome Simple moments (class counts, expected class-frequency sums, F). Either output may be NULL. */

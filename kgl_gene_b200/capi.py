@@ -27,7 +27,7 @@ EXPORTS = [
     "kgl_b200_set_stream", "kgl_b200_synchronize", "kgl_b200_upload_genotypes", "kgl_b200_upload_loci",
     "kgl_b200_set_genome_superpop", "kgl_b200_upload_multi_allelic", "kgl_b200_run_multi_allele_count", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_count_loci", "kgl_b200_set_locus_filter", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
-    "kgl_b200_run_inbreed", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
+    "kgl_b200_run_inbreed", "kgl_b200_inbreed_used_moment_tables", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
     "kgl_b200_run_binned_genome_counts", "kgl_b200_run_hetero_homo", "kgl_b200_location_fis", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_flush", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
@@ -39,7 +39,7 @@ EXPORTS = [
 
 class InbreedOptions(C.Structure):
     _fields_ = [("hall_start", C.POINTER(C.c_double)), ("hall_sweeps", C.c_int32), ("ll_tolerance", C.c_double),
-                ("ll_max_iterations", C.c_int32), ("count_loci", C.c_int32)]
+                ("ll_max_iterations", C.c_int32), ("count_loci", C.c_int32), ("exact_sweeps", C.c_int32), ("moments_on_cuda_cores", C.c_int32), ("sweep_by_sweep", C.c_int32)]
 
 
 class KglError(RuntimeError):
@@ -233,9 +233,13 @@ class KglB200:
         self._check(self.lib.kgl_b200_run_allele_count(self.h, _ptr(lc), _ptr(gc)), "run_allele_count")
         return lc, gc
 
-    def inbreed(self, algorithm: str, hall_start=None, hall_sweeps: int = 0, ll_tolerance: float = 0.0, ll_max_iterations: int = 0):
+    def inbreed(self, algorithm: str, hall_start=None, hall_sweeps: int = 0, ll_tolerance: float = 0.0, ll_max_iterations: int = 0,
+                exact_sweeps: bool = False, moments_on_cuda_cores: bool = False, sweep_by_sweep: bool = False):
         out = np.zeros(self.n_genomes, dtype=RESULT_DTYPE)
         opt = InbreedOptions()
+        opt.sweep_by_sweep = int(bool(sweep_by_sweep))
+        opt.exact_sweeps = int(bool(exact_sweeps))
+        opt.moments_on_cuda_cores = int(bool(moments_on_cuda_cores))
         start = None
         if hall_start is not None:
             start = np.ascontiguousarray(hall_start, dtype=np.float64)
@@ -243,6 +247,10 @@ class KglB200:
         opt.hall_sweeps, opt.ll_tolerance, opt.ll_max_iterations = int(hall_sweeps), float(ll_tolerance), int(ll_max_iterations)
         self._check(self.lib.kgl_b200_run_inbreed(self.h, C.c_int(ALGORITHMS[algorithm]), C.byref(opt), _ptr(out)), f"run_inbreed({algorithm})")
         return out
+
+    def used_moment_tables(self) -> int:
+        """Sweeps of the last HallME / Loglikelihood run: 0 exact kernels, 1 moment tables built on the CUDA cores, 2 on the tensor cores."""
+        return int(self.lib.kgl_b200_inbreed_used_moment_tables(self.h))
 
     def count_and_inbreed(self, want_loci=True):
         lc = np.zeros((self.n_loci, 4), dtype=np.uint32) if want_loci else None
@@ -388,9 +396,11 @@ class KglB200:
     def enqueue_count_and_inbreed_peer(self):
         self._check(self.lib.kgl_b200_enqueue_count_and_inbreed_peer(self.h), "enqueue_count_and_inbreed_peer")
 
-    def inbreed_begin(self, algorithm: str, hall_start=None, hall_sweeps=0, ll_tolerance=0.0, ll_max_iterations=0, count_loci=False):
+    def inbreed_begin(self, algorithm: str, hall_start=None, hall_sweeps=0, ll_tolerance=0.0, ll_max_iterations=0, count_loci=False,
+                      exact_sweeps=False):
         opt = InbreedOptions()
         opt.count_loci = int(bool(count_loci))
+        opt.exact_sweeps = int(bool(exact_sweeps))
         self._hall_keep = None
         if hall_start is not None:
             self._hall_keep = np.ascontiguousarray(hall_start, dtype=np.float64)

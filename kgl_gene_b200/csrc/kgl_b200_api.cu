@@ -7,6 +7,8 @@
 #include "sparse_events.cuh"
 #include "sample_major.cuh"
 #include "terms_fast.cuh"
+#include "terms_moments.cuh"
+#include "terms_moments_mma.cuh"
 #include "misc_kernels.cuh"
 #include "ibs_launch.cuh"
 #include "tail_kernels.cuh"
@@ -177,6 +179,23 @@ struct kgl_b200_ctx {
   DevBuf<uint32_t> d_n_slow, d_list;    // d_list: genomes whose root search is still running (late Newton sweeps)
   uint64_t list_len = 0;
   bool limits_valid = false;
+  // moment tables of the iterative estimators (terms_moments.cuh), built once per selection
+  DevBuf<uint64_t> d_mom_keys, d_mom_keys2, d_mom_base;
+  DevBuf<uint32_t> d_mom_rows, d_mom_rows2, d_mom_pop_begin, d_mom_cnt, d_mom_totals;
+  DevBuf<int> d_mom_stats;
+  DevBuf<long long> d_mom_pm, d_mom_mi;
+  DevBuf<double2> d_mom_lim;
+  DevBuf<uint2> d_mom_offs;
+  DevBuf<uint32_t> d_mom_bounds, d_mom_bounds2, d_mom_unit_out, d_mom_unit_cnt, d_mom_unit_offs;
+  DevBuf<MomUnit> d_mom_units;
+  DevBuf<uint2> d_mom_unit_range;
+  DevBuf<unsigned long long> d_mom_pop_cmin;
+  DevBuf<unsigned char> d_mom_btiles;
+  bool mom_used_mma = false;
+  DevBuf<double> d_mom_list, d_mom_limits, d_mom_rr;
+  DevBuf<uint8_t> d_mom_tmp;
+  bool mom_valid = false, mom_lists = false, mom_supported = false, used_moments = false;
+  int mom_b_lo = 0, mom_nbt = 0;
   DevBuf<uint64_t> d_genome_counts;
   DevBuf<kgl_b200_locus_results> d_results;
   DevBuf<uint32_t> d_ibs;
@@ -378,6 +397,7 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false, bool want_selw = fals
   KGL_CUDA(c, cudaEventRecord(c->prep_done, ps));
   KGL_CUDA(c, cudaStreamWaitEvent(c->stream, c->prep_done, 0));
   c->prep_valid = true; c->prep_has_w0 = want_w0; c->prep_has_selw = want_selw;
+  c->mom_valid = false;             // the moment tables belong to the selection that was prepared before
   return KGL_B200_OK;
 }
 
@@ -765,19 +785,10 @@ int launch_fast(kgl_b200_ctx* c, FastLaunch& fl, uint64_t list_len = 0) {
   return KGL_B200_OK;
 }
 
-// One Newton sweep of the log-likelihood root search: the table-driven kernel, its reduction, and the exact cell-by-cell
-// evaluation for the genomes the reduction marks (none in the normal case: the fallback kernels then return at once).
-template <int MODE>
-int newton_sweep(kgl_b200_ctx* c) {
-  FastLaunch fl;
-  int rc = launch_fast<MODE>(c, fl, c->list_len); if (rc) return rc;
+// The exact cell-by-cell evaluation for the genomes a Newton reduction marked (none in the normal case: the kernels then
+// return at once).
+int newton_exact_tail(kgl_b200_ctx* c) {
   const unsigned nb = blocks_for(c->N, 256);
-  KGL_CUDA(c, cudaMemsetAsync(c->d_n_slow.p, 0, 4, c->stream));
-  k_newton_reduce<<<blocks_for((c->list_len ? c->list_len : c->N) * 8, 256), 256, 0, c->stream>>>(
-      c->d_chunk_out.p, FastAcc<MODE>::N, fl.n_chunks, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len,
-      c->list_len ? c->d_list_count.p : nullptr, c->d_f.p,
-      c->d_limits.p, c->d_done.p, c->d_iter.p, c->d_lane_state.p, c->d_n_slow.p);
-  KGL_LAUNCH_CHECK(c);
   TermLaunch tl = plan_terms(c);
   KGL_CUDA(c, c->d_slow_out.ensure((size_t)tl.n_chunks * c->Npad * 4));
   TermParams P{};
@@ -792,6 +803,195 @@ int newton_sweep(kgl_b200_ctx* c) {
   k_newton_add_slow<<<nb, 256, 0, c->stream>>>(c->d_slow_out.p, tl.n_chunks, c->Npad, c->N, c->d_lane_state.p, c->d_n_slow.p, c->d_iter.p);
   KGL_LAUNCH_CHECK(c);
   return KGL_B200_OK;
+}
+
+// One Newton sweep of the log-likelihood root search: the table-driven kernel, its reduction, and the exact evaluation for
+// the genomes the reduction marks.
+template <int MODE>
+int newton_sweep(kgl_b200_ctx* c) {
+  FastLaunch fl;
+  int rc = launch_fast<MODE>(c, fl, c->list_len); if (rc) return rc;
+  KGL_CUDA(c, cudaMemsetAsync(c->d_n_slow.p, 0, 4, c->stream));
+  k_newton_reduce<<<blocks_for((c->list_len ? c->list_len : c->N) * 8, 256), 256, 0, c->stream>>>(
+      c->d_chunk_out.p, FastAcc<MODE>::N, fl.n_chunks, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len,
+      c->list_len ? c->d_list_count.p : nullptr, c->d_f.p,
+      c->d_limits.p, c->d_done.p, -kHuge, c->d_iter.p, c->d_lane_state.p, c->d_n_slow.p);
+  KGL_LAUNCH_CHECK(c);
+  return newton_exact_tail(c);
+}
+
+// ---- moment tables (terms_moments.cuh) ------------------------------------------------------------------------------------
+__global__ void k_mom_stats_init(int* stats) { stats[0] = kMomBinsMax; stats[1] = -1; stats[2] = 0; stats[3] = 0; }
+__global__ void k_mom_copy_limits(const double* __restrict__ src, uint64_t n, double* __restrict__ limits) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) { limits[g * 3 + 0] = src[g * 3 + 0]; limits[g * 3 + 1] = src[g * 3 + 1]; }
+}
+
+bool moments_enabled(const kgl_b200_ctx* c) {
+  static const bool on = std::getenv("KGL_B200_EXACT_SWEEPS") == nullptr;
+  return on && !c->opt.exact_sweeps;
+}
+
+// Builds the per-genome moment tables of the current selection (and, for the root search, the lists of rare homozygous cells
+// and the limits of the feasible region). mom_supported = false afterwards: the selection has a frequency outside the bins, or
+// the tables would not fit -- the caller then sweeps with the exact kernels.
+int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
+  if (c->mom_valid && (!c->mom_supported || c->mom_lists || !want_lists)) return KGL_B200_OK;
+  c->mom_valid = true; c->mom_lists = false; c->mom_supported = false; c->mom_used_mma = false;
+  int rc = ensure_sample_major(c); if (rc) return rc;       // the exact fallback reads the sample-major planes
+  const uint64_t L = c->L, N = c->N, npad = c->Npad;
+  const uint64_t row_lo = std::min<uint64_t>(L, c->sel_row_lo), row_hi = c->sel_row_hi == ~0ull ? L : std::min<uint64_t>(L, c->sel_row_hi);
+  const uint64_t W = row_hi > row_lo ? row_hi - row_lo : 0, n_items = W * c->n_pop;
+  if (W == 0 || n_items >= 0xFFFFFFFFull || !c->prep[c->par].selw.p) return KGL_B200_OK;
+  cudaStream_t st = c->stream;
+  const int unph = c->unphased ? 1 : 0;
+  KGL_CUDA(c, c->d_mom_keys.ensure(n_items)); KGL_CUDA(c, c->d_mom_keys2.ensure(n_items));
+  KGL_CUDA(c, c->d_mom_rows.ensure(n_items)); KGL_CUDA(c, c->d_mom_rows2.ensure(n_items));
+  KGL_CUDA(c, c->d_mom_stats.ensure(4)); KGL_CUDA(c, c->d_mom_pop_begin.ensure(kMaxPop + 2));
+  KGL_CUDA(c, c->d_mom_pop_cmin.ensure(kMaxPop));
+  KGL_CUDA(c, c->d_mom_bounds.ensure(kMomMaxUnits)); KGL_CUDA(c, c->d_mom_bounds2.ensure(kMomMaxUnits));
+  KGL_CUDA(c, c->d_mom_units.ensure(kMomMaxUnits)); KGL_CUDA(c, c->d_mom_unit_range.ensure(kMaxPop));
+  KGL_CUDA(c, c->d_mom_unit_out.ensure(4));
+  k_mom_stats_init<<<1, 1, 0, st>>>(c->d_mom_stats.p);
+  KGL_CUDA(c, cudaMemsetAsync(c->d_mom_pop_cmin.p, 0xFF, kMaxPop * 8, st));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_mom_bounds.p, 0xFF, kMomMaxUnits * 4, st));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_mom_unit_out.p, 0, 16, st));
+  k_mom_keys<<<dim3(blocks_for(W, 256), (unsigned)c->n_pop), 256, 0, st>>>(c->prep[c->par].selw.p, c->d_af.p, L, c->n_words, row_lo, W, unph,
+                                                                           c->d_mom_keys.p, c->d_mom_rows.p, c->d_mom_stats.p, c->d_mom_pop_cmin.p);
+  KGL_LAUNCH_CHECK(c);
+  size_t temp_bytes = 0, temp2 = 0;
+  KGL_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, c->d_mom_keys.p, c->d_mom_keys2.p, c->d_mom_rows.p, c->d_mom_rows2.p,
+                                              n_items, 0, 35, st));
+  KGL_CUDA(c, cub::DeviceRadixSort::SortKeys(nullptr, temp2, c->d_mom_bounds.p, c->d_mom_bounds2.p, (uint64_t)kMomMaxUnits, 0, 32, st));
+  KGL_CUDA(c, c->d_mom_tmp.ensure(std::max(temp_bytes, temp2)));
+  KGL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->d_mom_tmp.p, temp_bytes, c->d_mom_keys.p, c->d_mom_keys2.p, c->d_mom_rows.p, c->d_mom_rows2.p,
+                                              n_items, 0, 35, st));
+  k_mom_ranges<<<1, 32, 0, st>>>(c->d_mom_keys2.p, n_items, (int)c->n_pop, c->d_mom_pop_begin.p);
+  KGL_LAUNCH_CHECK(c);
+  // units of the tensor-core builder: boundaries, sorted, then the unit table
+  uint32_t* d_n_bounds = c->d_mom_unit_out.p + 3;
+  k_mom_bounds<<<blocks_for(n_items, 256), 256, 0, st>>>(c->d_mom_keys2.p, c->d_mom_rows2.p, c->d_mom_pop_begin.p, (int)c->n_pop, c->d_af.p, L,
+                                                         unph, c->d_mom_bounds.p, d_n_bounds);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cub::DeviceRadixSort::SortKeys(c->d_mom_tmp.p, temp2, c->d_mom_bounds.p, c->d_mom_bounds2.p, (uint64_t)kMomMaxUnits, 0, 32, st));
+  k_mom_units<<<1, 1024, 0, st>>>(c->d_mom_bounds2.p, d_n_bounds, c->d_mom_keys2.p, c->d_mom_rows2.p, c->d_mom_pop_begin.p, (int)c->n_pop,
+                                  c->d_af.p, L, unph, c->d_mom_units.p, c->d_mom_unit_range.p, c->d_mom_unit_out.p);
+  KGL_LAUNCH_CHECK(c);
+  int stats[4]; uint32_t pop_begin[kMaxPop + 2]; uint32_t unit_out[4];
+  KGL_CUDA(c, cudaMemcpyAsync(stats, c->d_mom_stats.p, sizeof stats, cudaMemcpyDeviceToHost, st));
+  KGL_CUDA(c, cudaMemcpyAsync(pop_begin, c->d_mom_pop_begin.p, (c->n_pop + 1) * 4, cudaMemcpyDeviceToHost, st));
+  KGL_CUDA(c, cudaMemcpyAsync(unit_out, c->d_mom_unit_out.p, sizeof unit_out, cudaMemcpyDeviceToHost, st));
+  KGL_CUDA(c, cudaStreamSynchronize(st));
+  if (stats[2] > 0 || stats[1] < stats[0]) return KGL_B200_OK;      // a frequency outside the bins / nothing selected: exact kernels
+  const int b_lo = stats[0], nbt = stats[1] - stats[0] + 2;           // + the a == 1 class
+  static const uint64_t limit_bytes = [] { const char* e = std::getenv("KGL_B200_MOMENT_BYTES"); return e ? std::strtoull(e, nullptr, 10) : (16ull << 30); }();
+  if ((uint64_t)npad * nbt * kMomJ * 8 > limit_bytes) return KGL_B200_OK;
+  uint32_t longest = 0;
+  for (uint32_t k = 0; k < c->n_pop; ++k) longest = std::max(longest, pop_begin[k + 1] - pop_begin[k]);
+  int sbits = 61; for (uint64_t v = longest; v; v >>= 1) --sbits;
+  const double scale = std::ldexp(1.0, std::min(sbits, 46));          // the tensor-core payload has six 8-bit limbs for U + 2^s
+  const uint32_t n_units = unit_out[0], n_btiles = unit_out[1];
+  static const bool mma_off = std::getenv("KGL_B200_MOMENTS_NO_MMA") != nullptr;
+  const bool use_mma = !mma_off && !c->opt.moments_on_cuda_cores && unit_out[2] <= kMomMaxUnits && n_units > 0 &&
+                       (uint64_t)n_btiles * 2 * kMmaBTile <= (4ull << 30) &&
+                       (!want_lists || (uint64_t)n_units * npad * 8 <= (4ull << 30));
+  KGL_CUDA(c, c->d_mom_pm.ensure((size_t)c->n_pop * nbt * kMomJ));
+  KGL_CUDA(c, c->d_mom_mi.ensure((size_t)npad * nbt * kMomJ));
+  KGL_CUDA(c, c->d_mom_totals.ensure((size_t)npad * 2));
+  KGL_CUDA(c, c->d_mom_limits.ensure((size_t)npad * 3));
+  KGL_CUDA(c, c->d_mom_base.ensure(N + 1));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_mom_pm.p, 0, (size_t)c->n_pop * nbt * kMomJ * 8, st));
+  KGL_CUDA(c, cudaMemsetAsync(c->d_mom_mi.p, 0, (size_t)npad * nbt * kMomJ * 8, st));
+  k_mom_dense<<<blocks_for(pop_begin[c->n_pop], 256), 256, 0, st>>>(c->d_mom_keys2.p, c->d_mom_rows2.p, c->d_mom_pop_begin.p, (int)c->n_pop,
+                                                                    c->d_af.p, L, unph, b_lo, nbt, scale, c->d_mom_pm.p);
+  KGL_LAUNCH_CHECK(c);
+  uint64_t list_len = 0;
+  if (use_mma) {
+    KGL_CUDA(c, c->d_mom_btiles.ensure((size_t)std::max<uint32_t>(1, n_btiles) * 2 * kMmaBTile));
+    KGL_CUDA(c, c->d_mom_rr.ensure(n_items));
+    k_mom_btiles<<<n_units, kMmaK, 0, st>>>(c->d_mom_units.p, c->d_mom_rows2.p, c->d_af.p, L, unph, scale, c->d_mom_btiles.p, c->d_mom_rr.p);
+    KGL_LAUNCH_CHECK(c);
+    if (want_lists) { KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad)); KGL_CUDA(c, c->d_mom_unit_offs.ensure((size_t)n_units * npad)); }
+    MomMmaParams M{};
+    M.packed = reinterpret_cast<const uint4*>(c->d_packed.p); M.units = c->units;
+    M.superpop = c->d_superpop.p; M.n_genomes = N; M.n_genomes_padded = npad;
+    M.rows = c->d_mom_rows2.p; M.unit_table = c->d_mom_units.p; M.btiles = c->d_mom_btiles.p;
+    M.b_lo = b_lo; M.nbt = nbt; M.scale = scale; M.mi = c->d_mom_mi.p; M.cnt = want_lists ? c->d_mom_unit_cnt.p : nullptr;
+    k_mom_mma<<<dim3(n_units, (unsigned)((N + kMmaM - 1) / kMmaM)), kMmaM, 0, st>>>(M);
+    KGL_LAUNCH_CHECK(c);
+    if (want_lists) {
+      k_mom_unit_scan<<<blocks_for(N, 32), 256, 0, st>>>(c->d_mom_unit_cnt.p, c->d_mom_units.p, c->d_mom_unit_range.p, c->d_superpop.p, N, npad,
+                                                          c->d_mom_unit_offs.p, c->d_mom_totals.p);
+      KGL_LAUNCH_CHECK(c);
+      k_mom_base<<<1, 1024, 0, st>>>(c->d_mom_totals.p, N, c->d_mom_base.p);
+      KGL_LAUNCH_CHECK(c);
+      KGL_CUDA(c, cudaMemcpyAsync(&list_len, c->d_mom_base.p + N, 8, cudaMemcpyDeviceToHost, st));
+      KGL_CUDA(c, cudaStreamSynchronize(st));
+      KGL_CUDA(c, c->d_mom_list.ensure(std::max<uint64_t>(1, list_len)));
+      MomFillParams F{};
+      F.packed = M.packed; F.units = c->units; F.rr = c->d_mom_rr.p;
+      F.superpop = c->d_superpop.p; F.n_genomes = N; F.n_genomes_padded = npad; F.rows = c->d_mom_rows2.p; F.unit_table = c->d_mom_units.p;
+      F.cnt = c->d_mom_unit_cnt.p; F.offs = c->d_mom_unit_offs.p; F.totals = c->d_mom_totals.p; F.base = c->d_mom_base.p; F.list = c->d_mom_list.p;
+      k_mom_unit_fill<<<dim3(n_units, (unsigned)((N + kMomTile - 1) / kMomTile)), kMomTile, 0, st>>>(F);
+      KGL_LAUNCH_CHECK(c);
+    }
+    c->mom_used_mma = true;
+  } else {
+    const uint32_t chunks_per_pop = (longest + kMomChunk - 1) / kMomChunk;
+    KGL_CUDA(c, c->d_mom_cnt.ensure((size_t)chunks_per_pop * npad));
+    if (want_lists) KGL_CUDA(c, c->d_mom_offs.ensure((size_t)chunks_per_pop * npad));
+    MomParams P{};
+    P.packed = reinterpret_cast<const uint4*>(c->d_packed.p); P.units = c->units;
+    P.af = c->d_af.p; P.n_loci = L; P.n_pop = (int)c->n_pop; P.unphased = unph;
+    P.superpop = c->d_superpop.p; P.n_genomes = N; P.n_genomes_padded = npad;
+    P.rows = c->d_mom_rows2.p; P.pop_begin = c->d_mom_pop_begin.p; P.chunks_per_pop = chunks_per_pop;
+    P.b_lo = b_lo; P.nbt = nbt; P.scale = scale;
+    P.mi = c->d_mom_mi.p; P.cnt = c->d_mom_cnt.p; P.lim = nullptr;
+    const dim3 grid((unsigned)(c->n_pop * chunks_per_pop), (unsigned)((N + kMomTile - 1) / kMomTile));
+    k_mom_build<false><<<grid, kMomTile, 0, st>>>(P);          // the limits of the root search come from the lists (k_mom_list_limits)
+    KGL_LAUNCH_CHECK(c);
+    k_mom_scan<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_cnt.p, nullptr, c->d_mom_pop_begin.p, c->d_superpop.p,
+                                                   N, npad, c->d_mom_totals.p, nullptr, want_lists ? c->d_mom_offs.p : nullptr);
+    KGL_LAUNCH_CHECK(c);
+    if (want_lists) {
+      k_mom_base<<<1, 1024, 0, st>>>(c->d_mom_totals.p, N, c->d_mom_base.p);
+      KGL_LAUNCH_CHECK(c);
+      KGL_CUDA(c, cudaMemcpyAsync(&list_len, c->d_mom_base.p + N, 8, cudaMemcpyDeviceToHost, st));
+      KGL_CUDA(c, cudaStreamSynchronize(st));
+      KGL_CUDA(c, c->d_mom_list.ensure(std::max<uint64_t>(1, list_len)));
+      P.base = c->d_mom_base.p; P.offs = c->d_mom_offs.p; P.list = c->d_mom_list.p;
+      k_mom_fill<<<grid, kMomTile, 0, st>>>(P, c->d_mom_totals.p);
+      KGL_LAUNCH_CHECK(c);
+    }
+  }
+  if (want_lists) {
+    k_mom_list_limits<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_list.p, c->d_mom_base.p, c->d_mom_totals.p, c->d_superpop.p,
+                                                              c->d_mom_pop_cmin.p, N, c->d_mom_limits.p);
+    KGL_LAUNCH_CHECK(c);
+    c->mom_lists = true;
+  }
+  k_mom_finalize<<<blocks_for(N * (uint64_t)nbt, 256), 256, 0, st>>>(c->d_mom_mi.p, c->d_mom_pm.p, c->d_superpop.p, N, nbt, 1.0 / scale);
+  KGL_LAUNCH_CHECK(c);
+  c->launches += 12;
+  c->mom_b_lo = b_lo; c->mom_nbt = nbt; c->mom_supported = true;
+  return KGL_B200_OK;
+}
+
+// One Newton sweep from the moment tables; same reduction and exact fallback as newton_sweep.
+int newton_sweep_moments(kgl_b200_ctx* c) {
+  const uint64_t n_pos = c->list_len ? c->list_len : c->N;
+  KGL_CUDA(c, c->d_chunk_out.ensure((size_t)c->Npad * 2));
+  k_mom_eval<FAST_NEWTON><<<(unsigned)n_pos, 128, 0, c->stream>>>(
+      reinterpret_cast<const double*>(c->d_mom_mi.p), c->mom_b_lo, c->mom_nbt, c->d_f.p, c->list_len ? c->d_list.p : nullptr, c->list_len,
+      c->list_len ? c->d_list_count.p : nullptr, c->N, c->d_mom_list.p, c->d_mom_base.p, c->d_mom_totals.p, c->d_chunk_out.p, nullptr);
+  KGL_LAUNCH_CHECK(c);
+  KGL_CUDA(c, cudaMemsetAsync(c->d_n_slow.p, 0, 4, c->stream));
+  k_newton_reduce<<<blocks_for(n_pos * 8, 256), 256, 0, c->stream>>>(
+      c->d_chunk_out.p, 2, 1, c->Npad, c->N, c->list_len ? c->d_list.p : nullptr, c->list_len,
+      c->list_len ? c->d_list_count.p : nullptr, c->d_f.p,
+      c->d_limits.p, c->d_done.p, kMomValidMin, c->d_iter.p, c->d_lane_state.p, c->d_n_slow.p);
+  KGL_LAUNCH_CHECK(c);
+  return newton_exact_tail(c);
 }
 
 // ---- pairwise IBS ----------------------------------------------------------------------------------------------------
@@ -1232,6 +1432,7 @@ int kgl_b200_run_multi_allele_count(kgl_b200_ctx* c, uint32_t* counts) {
 
 int kgl_b200_set_unphased(kgl_b200_ctx* c, int unphased) {
   if (!c) return KGL_B200_ERR_INVALID;
+  if (c->unphased != (unphased != 0)) c->mom_valid = false;
   c->unphased = unphased != 0;
   return KGL_B200_OK;
 }
@@ -1691,7 +1892,7 @@ int kgl_b200_inbreed_begin(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbree
   KGL_CUDA(c, c->d_n_slow.ensure(1));
   KGL_CUDA(c, c->d_list.ensure(c->Npad));
   KGL_CUDA(c, c->d_list_count.ensure(1));
-  c->limits_valid = false; c->list_len = 0; c->table_mode = -1;
+  c->limits_valid = false; c->list_len = 0; c->table_mode = -1; c->used_moments = false;
   return KGL_B200_OK;
 }
 
@@ -1716,10 +1917,33 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   }
   const unsigned nb = blocks_for(c->N, 256);
   if (c->algo == KGL_B200_ALGO_HALLME) {
+    bool start_ok = moments_enabled(c);         // the tables cover f >= 0 without the lists: a start in [0,1] stays there (calc.cpp:285)
+    for (double v : c->hall_start) start_ok = start_ok && v >= 0.0 && v <= 1.0;
+    if (start_ok) { rc = ensure_moments(c, false); if (rc) return rc; }
+    if (start_ok && c->mom_supported) {
+      c->used_moments = true;
+      k_mom_eval<FAST_HALL><<<(unsigned)c->N, 128, 0, c->stream>>>(reinterpret_cast<const double*>(c->d_mom_mi.p), c->mom_b_lo, c->mom_nbt, c->d_f.p,
+                                                                  nullptr, 0, nullptr, c->N, nullptr, nullptr, nullptr, nullptr, c->d_iter.p);
+      KGL_LAUNCH_CHECK(c);
+      return multi_add<MULTI_HALL>(c, c->d_iter.p);
+    }
     rc = launch_fast<FAST_HALL>(c, fl); if (rc) return rc;
     k_hall_reduce<<<blocks_for(c->N * 8, 256), 256, 0, c->stream>>>(c->d_chunk_out.p, fl.n_chunks, c->Npad, c->N, c->d_iter.p);
     KGL_LAUNCH_CHECK(c);
     return multi_add<MULTI_HALL>(c, c->d_iter.p);
+  }
+  if (!c->unphased && moments_enabled(c)) {
+    rc = ensure_moments(c, true); if (rc) return rc;
+    if (c->mom_supported) {
+      if (!c->limits_valid) {
+        k_mom_copy_limits<<<nb, 256, 0, c->stream>>>(c->d_mom_limits.p, c->N, c->d_limits.p);
+        KGL_LAUNCH_CHECK(c);
+        c->limits_valid = true;
+      }
+      c->used_moments = true;
+      rc = newton_sweep_moments(c); if (rc) return rc;
+      return multi_add<MULTI_NEWTON>(c, c->d_iter.p);
+    }
   }
   if (!c->limits_valid) {      // once per root search: the selection is fixed between inbreed_begin and inbreed_fetch
     rc = launch_fast<FAST_LIMITS>(c, fl); if (rc) return rc;
@@ -1731,6 +1955,8 @@ int kgl_b200_inbreed_accumulate(kgl_b200_ctx* c) {
   if (rc) return rc;
   return multi_add<MULTI_NEWTON>(c, c->d_iter.p);     // evaluated cell by cell, clamps included (a clamped homozygous term moves the search right)
 }
+
+int kgl_b200_inbreed_used_moment_tables(const kgl_b200_ctx* c) { return c && c->used_moments ? (c->mom_used_mma ? 2 : 1) : 0; }
 
 int kgl_b200_inbreed_partials_buffer(kgl_b200_ctx* c, void** device_ptr, uint64_t* n_doubles) {
   if (!c || !device_ptr || !n_doubles || c->algo < 0) return fail(c, KGL_B200_ERR_STATE, "inbreed_begin first");
@@ -1819,10 +2045,54 @@ int kgl_b200_inbreed_fetch(kgl_b200_ctx* c, kgl_b200_locus_results* out) {
   return peer_verdict(c, peer_word);
 }
 
+// HallME / the root search as ONE launch over the moment tables (k_mom_run): this context holds every locus, so nothing has to
+// be all-reduced between sweeps. Leaves *finished at 0 when the tables are not available (or a genome needs the exact
+// kernel): the caller then continues with the sweep-by-sweep protocol from the state the launch left behind.
+static int run_whole_from_tables(kgl_b200_ctx* c, int* finished) {
+  const bool hall = c->algo == KGL_B200_ALGO_HALLME;
+  if (!moments_enabled(c) || c->n_multi != 0 || c->opt.sweep_by_sweep) return KGL_B200_OK;
+  if (!hall && c->unphased) return KGL_B200_OK;
+  if (hall) for (double v : c->hall_start) if (!(v >= 0.0 && v <= 1.0)) return KGL_B200_OK;
+  int rc = ensure_moments(c, !hall); if (rc) return rc;
+  if (!c->mom_supported) return KGL_B200_OK;
+  const size_t smem = (size_t)c->mom_nbt * (kMomJ * 8 + 16);
+  if (smem > 200 * 1024) return KGL_B200_OK;
+  MomRunParams P{};
+  P.mom = reinterpret_cast<const double*>(c->d_mom_mi.p); P.b_lo = c->mom_b_lo; P.nbt = c->mom_nbt; P.n_genomes = c->N;
+  P.partials = c->d_partials.p; P.f = c->d_f.p; P.hall_sweeps = c->opt.hall_sweeps;
+  c->used_moments = true;
+  if (hall) {
+    KGL_CUDA(c, cudaFuncSetAttribute(k_mom_run<FAST_HALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mom_run<FAST_HALL><<<(unsigned)c->N, 128, smem, c->stream>>>(P);
+    KGL_LAUNCH_CHECK(c);
+    c->iteration = c->opt.hall_sweeps > 0 ? c->opt.hall_sweeps : 0;
+    *finished = 1;
+    return KGL_B200_OK;
+  }
+  k_mom_copy_limits<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_mom_limits.p, c->N, c->d_limits.p);
+  KGL_LAUNCH_CHECK(c);
+  c->limits_valid = true;
+  P.rare = c->d_mom_list.p; P.base = c->d_mom_base.p; P.totals = c->d_mom_totals.p; P.limits = c->d_limits.p;
+  P.bracket = c->d_bracket.p; P.done = c->d_done.p; P.tol = c->opt.ll_tolerance; P.max_iterations = c->opt.ll_max_iterations;
+  P.remaining = c->d_flag.p;
+  KGL_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, 8, c->stream));
+  KGL_CUDA(c, cudaFuncSetAttribute(k_mom_run<FAST_NEWTON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mom_run<FAST_NEWTON><<<(unsigned)c->N, 128, smem, c->stream>>>(P);
+  KGL_LAUNCH_CHECK(c);
+  unsigned long long remaining = 0;
+  KGL_CUDA(c, cudaMemcpyAsync(&remaining, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  *finished = remaining == 0 ? 1 : 0;
+  return KGL_B200_OK;
+}
+
 int kgl_b200_run_inbreed(kgl_b200_ctx* c, int algorithm, const kgl_b200_inbreed_options* options, kgl_b200_locus_results* out) {
   if (!c || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
   int rc = kgl_b200_inbreed_begin(c, algorithm, options); if (rc) return rc;
   int finished = 0;
+  rc = kgl_b200_inbreed_accumulate(c); if (rc) return rc;           // the counting pass
+  rc = kgl_b200_inbreed_update(c, &finished); if (rc) return rc;
+  if (!finished) { rc = run_whole_from_tables(c, &finished); if (rc) return rc; }
   while (!finished) {
     rc = kgl_b200_inbreed_accumulate(c); if (rc) return rc;
     rc = kgl_b200_inbreed_update(c, &finished); if (rc) return rc;

@@ -249,7 +249,9 @@ k_hall_update(const double* __restrict__ partials, const double* __restrict__ it
   if (g >= n_genomes) return;
   const double* P = partials + g * PART_COUNT;
   const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
-  const double nf = __ddiv_rn(iter[g * ITER_COUNT], n);
+  // f == 0 is a fixed point (every term is 0/(0 + a), calc.cpp:268-272) and an unstable one: the sweeps must not leave it through
+  // the 1e-60 the table kernel's neutral entries leave behind
+  const double nf = (f[g] == 0.0 && n > 0.0) ? 0.0 : __ddiv_rn(iter[g * ITER_COUNT], n);
   const double delta = fabs(nf - f[g]);
   f[g] = nf;
   if (delta == delta) atomicMax(flag, (unsigned long long)__double_as_longlong(delta));   // non-negative doubles order like ints

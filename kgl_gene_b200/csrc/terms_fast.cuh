@@ -302,7 +302,10 @@ k_terms_fast(const FastParams P) {
         const int k = (g < P.n_genomes) ? P.superpop[g] : 0;
         double f = ((MODE == FAST_HALL || MODE == FAST_NEWTON || MODE == FAST_NEWTON_U) && g != kNoGenome) ? P.f[g] : 0.0;
         const double upper = (MODE == FAST_NEWTON_U) ? __ddiv_rn(1.0, __dsub_rn(1.0, f)) : 0.0;   // 2 p p (1-f) > 1  <=>  2 p p > 1/(1-f)
-        if (MODE == FAST_HALL) f = fmin(fmax(__ddiv_rn(__dsub_rn(1.0, f), f), -kHallHuge), kHallHuge);   // f = 0: every term vanishes
+        if (MODE == FAST_HALL) {                 // k = (1-f)/f. f = 0: every term vanishes; f = 1: k = 0 would turn the neutral entries (a = 1e60)
+          f = fmin(fmax(__ddiv_rn(__dsub_rn(1.0, f), f), -kHallHuge), kHallHuge);   // into terms, so k stays >= 1e-30 (a real term moves by < 1e-30)
+          if (f >= 0.0 && f < 1e-30) f = 1e-30;
+        }
         const uint32_t base = (uint32_t)__cvta_generic_to_shared(tab + k * STRIDE + body * kFastBodyWords * 32 * 4 * E);
         uint2 z[kFastBodyWords];
 #pragma unroll
@@ -399,6 +402,7 @@ __global__ void __launch_bounds__(256)
 k_newton_reduce(const double* __restrict__ chunk_out, int n_out /* 2, or 3 with the upper-clamped count */, uint64_t n_chunks,
                 uint64_t n_genomes_padded, uint64_t n_genomes, const uint32_t* __restrict__ list, uint64_t n_list,
                 const uint32_t* __restrict__ n_list_dev, const double* __restrict__ f, const double* __restrict__ limits, const uint32_t* __restrict__ done,
+                double valid_min /* sums from the moment tables hold for f >= valid_min (terms_moments.cuh); -kHuge otherwise */,
                 double* __restrict__ iter, uint8_t* __restrict__ state, uint32_t* __restrict__ n_slow) {
   const uint64_t pos = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;       // position in chunk_out, eight lanes each
   if (list && n_list_dev) n_list = min(n_list, (uint64_t)*n_list_dev);
@@ -414,7 +418,7 @@ k_newton_reduce(const double* __restrict__ chunk_out, int n_out /* 2, or 3 with 
   uint8_t st = 0;
   if (done && done[g]) st = 1;                                  // converged genomes: values are not read any more
   else if (x < fmin_ - band) st = 1;
-  else if (x < fmin_ + band) st = 2;
+  else if (x < fmin_ + band || x < valid_min) st = 2;
   else if (nhet > 0.0 && !((1.0 - x) * cmin > kSmallProb * (1.0 + kLimitMargin))) st = 2;
   state[g] = st;
   if (st == 1) { I[0] = 0.0; I[1] = 0.0; I[2] = 1.0; I[3] = 0.0; return; }

@@ -287,6 +287,97 @@ def test_hallme_fixed_point(gpu):
     assert np.max(np.abs(got["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-9
 
 
+@pytest.mark.parametrize("case", [
+    dict(n_genomes=300, n_loci=20000, seed=41, spectrum="sfs", grouped=True),
+    dict(n_genomes=257, n_loci=9000, seed=42, spectrum="dense", grouped=False),                 # every tile holds every population
+    dict(n_genomes=500, n_loci=30000, seed=43, spectrum="sfs", missing_rate=0.01, missing_af_rate=0.01),
+    dict(n_genomes=96, n_loci=12000, seed=44, spectrum="sfs", unphased=True),
+], ids=lambda c: f"N{c['n_genomes']}xL{c['n_loci']}")
+def test_moment_tables_agree_with_exact_sweeps(gpu, case):
+    """HallME and the likelihood root search from the per-genome moment tables (terms_moments.cuh) against the kernels that
+    evaluate every cell in every sweep (terms_fast.cuh) and against the oracle -- with the frequencies that bend the tables:
+    a == 1 in one population (t = 0 cells), exactly 1/2, the ends of the bin range, rare homozygous cells far left."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(**case)
+    pop.af[1, ::61] = np.float32(1.0)
+    pop.af[:, 7::53] = np.float32(0.5)
+    pop.af[:, 11::211] = np.float32(1e-11)
+    pop.af[:, 13::199] = np.float32(0.9999)
+    pop.af[2, 17::97] = np.float32(0.75)
+    unphased = bool(case.get("unphased"))
+    for sel_kw in (dict(spacing=0), dict(spacing=15, lower=int(pop.offsets[pop.n_loci // 5]), upper=int(pop.offsets[pop.n_loci // 2]))):
+        sel = O.select_all_pops(pop, **sel_kw)
+        gpu.upload_population(pop)
+        gpu.select_loci(**sel_kw)
+        start = np.linspace(0.0, 1.0, pop.n_genomes)
+        want = O.inbreed(pop, sel, "HallME", start=start, sweeps=50)
+        ok = results_matrix(want)[0][:, 4] > 0
+        fast = gpu.inbreed("HallME", hall_start=start, hall_sweeps=50)
+        assert gpu.used_moment_tables() == 2                      # tables built on the tensor cores (k_mom_mma)
+        gpu.select_loci(**sel_kw)                                 # a new selection: the tables are rebuilt, now on the CUDA cores
+        cores = gpu.inbreed("HallME", hall_start=start, hall_sweeps=50, moments_on_cuda_cores=True)
+        assert gpu.used_moment_tables() == 1
+        assert np.array_equal(fast["inbred_allele_sum"], cores["inbred_allele_sum"], equal_nan=True)     # the same integers
+        steps = gpu.inbreed("HallME", hall_start=start, hall_sweeps=50, sweep_by_sweep=True)     # the protocol of a locus-sharded caller
+        assert gpu.used_moment_tables() and np.max(np.abs(fast["inbred_allele_sum"][ok] - steps["inbred_allele_sum"][ok])) < 1e-13
+        exact = gpu.inbreed("HallME", hall_start=start, hall_sweeps=50, exact_sweeps=True)
+        assert not gpu.used_moment_tables()
+        assert np.max(np.abs(fast["inbred_allele_sum"][ok] - exact["inbred_allele_sum"][ok])) < 1e-10
+        assert rel_err(fast["inbred_allele_sum"][ok], want["inbred_allele_sum"][ok]) < 1e-9
+        fast = gpu.inbreed("Loglikelihood")
+        if not unphased:
+            gpu.select_loci(**sel_kw)
+            cores = gpu.inbreed("Loglikelihood", moments_on_cuda_cores=True)
+            assert gpu.used_moment_tables() == 1
+            assert np.max(np.abs(fast["inbred_allele_sum"][ok] - cores["inbred_allele_sum"][ok])) < 1e-12
+            gpu.select_loci(**sel_kw)
+            fast = gpu.inbreed("Loglikelihood")
+        assert bool(gpu.used_moment_tables()) == (not unphased)       # Q6: the upper clamp of 2 (1-f) p p needs the cells
+        steps = gpu.inbreed("Loglikelihood", sweep_by_sweep=True)
+        assert np.max(np.abs(fast["inbred_allele_sum"][ok] - steps["inbred_allele_sum"][ok])) < 1e-12
+        exact = gpu.inbreed("Loglikelihood", exact_sweeps=True)
+        assert not gpu.used_moment_tables()
+        want = O.inbreed(pop, sel, "Loglikelihood")
+        assert np.max(np.abs(fast["inbred_allele_sum"][ok] - exact["inbred_allele_sum"][ok])) < 1e-10
+        assert np.max(np.abs(fast["inbred_allele_sum"][ok] - want["inbred_allele_sum"][ok])) < 1e-9
+        assert np.array_equal(results_matrix(fast)[0], results_matrix(want)[0])
+    # a HallME start outside [0,1], and a frequency below the bins (1e-13): the exact kernels take over, same results
+    start = np.linspace(-0.3, 1.2, pop.n_genomes)
+    got = gpu.inbreed("HallME", hall_start=start, hall_sweeps=10)
+    assert not gpu.used_moment_tables()
+    pop.af[0, 19::301] = np.float32(1e-13)
+    gpu.upload_population(pop)
+    gpu.select_loci()
+    sel = O.select_all_pops(pop)
+    got = gpu.inbreed("HallME", hall_sweeps=50)
+    assert not gpu.used_moment_tables()
+    want = O.inbreed(pop, sel, "HallME", sweeps=50)
+    ok = results_matrix(want)[0][:, 4] > 0
+    assert rel_err(got["inbred_allele_sum"][ok], want["inbred_allele_sum"][ok]) < 1e-9
+
+
+def test_moment_tables_left_of_zero(gpu):
+    """Outbred and negatively inbred genomes: the root search runs at f < 0, where the bins of the octaves below 4|f| give way
+    to the list of the genome's rare homozygous cells; genomes left of the tables' domain (f < -0.2) take the exact kernel."""
+    from kgl_gene_b200.flatfile import pack_codes
+    from kgl_gene_b200.synth import make_loci, make_genomes, synth_codes
+    from kgl_gene_b200.flatfile import FlatPopulation, row_bytes_for
+    n, l = 200, 16000
+    offsets, af = make_loci(l, 51, spectrum="dense")
+    superpop, _ = make_genomes(n, 51)
+    inbreeding = np.linspace(-0.45, 0.05, n)                # excess heterozygosity
+    codes = synth_codes(51, af, superpop, inbreeding, missing_rate=0.002)
+    pop = FlatPopulation(offsets, af, superpop, pack_codes(codes), n, False)
+    sel = O.select_all_pops(pop)
+    gpu.upload_population(pop)
+    gpu.select_loci()
+    want = O.inbreed(pop, sel, "Loglikelihood")
+    fast = gpu.inbreed("Loglikelihood")
+    assert gpu.used_moment_tables()
+    assert want["inbred_allele_sum"].min() < -0.25 and (want["inbred_allele_sum"] > -0.15).sum() > 20
+    assert np.max(np.abs(fast["inbred_allele_sum"] - want["inbred_allele_sum"])) < 1e-9
+
+
 @pytest.mark.parametrize("n,l,miss", [(130, 40_000, 0.012), (70, 2_400_000, 0.014)], ids=["segments", "counter-flush"])
 def test_ibs_sparse_repair_at_scale(gpu, n, l, miss):
     """The sparse repair of code-3 cells (k_ibs_missing_fix) where it splits a genome's dropped rows into segments (few tiles,

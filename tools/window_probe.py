@@ -27,10 +27,17 @@ def wall(fn, reps=5):
 w = 7
 lo, hi = int(offsets[w * per]), int(offsets[(w + 1) * per - 1])
 out = {"select_window_ms": wall(lambda: ctx.select_loci(lower=lo, upper=hi))}
+def cold(algorithm, **kw):        # a fresh selection: preparation and moment tables are rebuilt
+    ctx.select_loci(**kw)
+    ctx.inbreed(algorithm)
 for algorithm in ("Simple", "RitlandLocus", "HallME", "Loglikelihood"):
     out[algorithm + "_window_ms"] = wall(lambda: ctx.inbreed(algorithm))
+    out[algorithm + "_window_with_select_ms"] = wall(lambda: cold(algorithm, lower=lo, upper=hi))
 out["select_all_ms"] = wall(lambda: ctx.select_loci())
 for algorithm in ("Simple", "RitlandLocus", "HallME", "Loglikelihood"):
     out[algorithm + "_all_ms"] = wall(lambda: ctx.inbreed(algorithm), 3)
+    out[algorithm + "_all_with_select_ms"] = wall(lambda: cold(algorithm), 3)
+    if algorithm in ("HallME", "Loglikelihood"):
+        out[algorithm + "_all_exact_sweeps_ms"] = wall(lambda: ctx.inbreed(algorithm, exact_sweeps=True), 2)
 print(json.dumps(out), flush=True)
 ctx.close()
