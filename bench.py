@@ -434,9 +434,14 @@ def run_ours(args):
                                            "for every window and algorithm; host wall clock"}
             ctx.select_loci()                  # back to one window = all loci for what follows
 
+    hbm_peak = 6650.0
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        pass
     est = None
     if not args.no_estimators:
-        est = run_estimators(ctx, torch, dist, dev, stream, world, n, l, allreduce_partials)
+        est = run_estimators(ctx, torch, dist, dev, stream, world, n, l, rb, allreduce_partials, hbm_peak)
 
     kin = None
     if not args.no_kinship:
@@ -502,55 +507,60 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# FP64 instructions per cell of the table-driven sweeps (kgl_gene_b200/csrc/terms_fast.cuh) and the measured DFMA issue rate
-# of one B200 (profiles/r01_pipe_rates_f64_kbench.log: 56.35 lanes per clk per SM x 148 SMs x 1.965 GHz).
-FP64_OPS_PER_CELL = {"HallME": 3.5, "Loglikelihood": 5}
-FP64_PEAK_OPS = 56.35 * 148 * 1.965e9
-
-
-def run_estimators(ctx, torch, dist, dev, stream, world, n, l, allreduce_partials):
-    """The other three estimators of kga_inbreed on the resident shard: whole-estimator time (all sweeps, the all-reduce of
-    every sweep at N > 1) and the time of one full sweep against the FP64 pipe."""
+def run_estimators(ctx, torch, dist, dev, stream, world, n, l, rb, allreduce_partials, hbm_peak):
+    """The other three estimators of kga_inbreed on the resident shard. `ms` is the whole estimator on a FRESH selection: the
+    counting pass, the per-selection tables of the iterative estimators (terms_moments.cuh: sort, payload tiles, the tensor-core
+    pass over the matrix, lists) and all sweeps. One GPU: kgl_b200_run_inbreed (all sweeps in one launch); N > 1: the
+    accumulate / all-reduce / update protocol, sweep by sweep."""
     out = {}
+
+    def timed_call(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        r = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), r
+
+    def protocol(algorithm, **kw):
+        ctx.inbreed_begin(algorithm, **kw)
+        finished, sweeps = False, 0
+        while not finished:
+            ctx.inbreed_accumulate()
+            if world > 1:
+                allreduce_partials()
+            finished = ctx.inbreed_update()
+            sweeps += 1
+        return sweeps
+
     for algorithm in ("RitlandLocus", "HallME", "Loglikelihood"):
-        def run():
-            ev = []
-            ctx.inbreed_begin(algorithm)
-            finished = False
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record(stream)
-            while not finished:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                ctx.inbreed_accumulate()
-                e1.record(stream)
-                if world > 1:
-                    allreduce_partials()
-                finished = ctx.inbreed_update()
-                ev.append((e0, e1))
-            a1.record(stream)
-            torch.cuda.synchronize()
-            return [a.elapsed_time(b) for a, b in ev], a0.elapsed_time(a1)
-        run()                                   # warm-up: derived copies, buffers
+        iterative = algorithm != "RitlandLocus"
+        run = (lambda **kw: ctx.inbreed(algorithm, **kw)) if world == 1 else (lambda **kw: protocol(algorithm, **kw))
+        run()                                   # warm-up: buffers, derived copies
+        ctx.select_loci()                       # a fresh selection (untimed): nothing of the run before is reused
         if world > 1:
             dist.barrier()
-        ms, total = run()
-        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        cold, _ = timed_call(run)
+        cached, _ = timed_call(run)             # same selection again: the tables are reused
+        t = torch.tensor([cold, cached], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total = float(t.item())
+        cold, cached = float(t[0].item()), float(t[1].item())
         cells = float(n) * float(l) * world
-        o = {"passes": len(ms), "ms": total, "genotype_loci_per_s": cells / (total * 1e-3)}
-        if algorithm in FP64_OPS_PER_CELL:
-            full = sorted(ms[1:])[-3:] if algorithm == "Loglikelihood" else ms[1:]     # full sweeps (late Newton sweeps gather few genomes)
-            sweep = float(np.median(full))
-            cells_rank = float(n) * float(l)
-            achieved = cells_rank * FP64_OPS_PER_CELL[algorithm] / (sweep * 1e-3)
-            o["sweep_ms"] = sweep
-            o["roofline"] = {"bound": "fp64 pipe", "kernel": "k_terms_fast<%s>" % ("HALL" if algorithm == "HallME" else "NEWTON"),
-                             "achieved": achieved, "peak": FP64_PEAK_OPS, "unit": "FP64 lane-ops/s", "frac": achieved / FP64_PEAK_OPS,
-                             "fp64_ops_per_cell": FP64_OPS_PER_CELL[algorithm],
-                             "peak_source": "measured DFMA issue rate (kbench, profiles/r01_pipe_rates_f64_kbench.log)"}
+        o = {"ms": cold, "genotype_loci_per_s": cells / (cold * 1e-3), "ms_same_selection_again": cached}
+        if iterative:
+            path = ctx.used_moment_tables()
+            o["sweeps_from"] = {0: "exact kernels (every cell in every sweep)", 1: "moment tables, built on the CUDA cores",
+                                2: "moment tables, built on the tensor cores (k_mom_mma)"}[path]
+            exact, _ = timed_call(lambda: run(exact_sweeps=True))
+            o["ms_exact_sweeps"] = exact          # round-1 path: k_terms_fast, N x L reciprocals per sweep
+            build = max(cold - cached, 1e-6)
+            matrix_bytes = float(l) * rb
+            o["roofline"] = {"bound": "hbm", "kernel": "table build (k_mom_keys, radix sort, k_mom_btiles, k_mom_mma, lists): one pass over the matrix",
+                             "achieved": matrix_bytes / (build * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": matrix_bytes / (build * 1e-3) / 1e9 / hbm_peak, "build_ms": build,
+                             "note": "algorithmic bytes = one read of the 2-bit matrix; the sweeps read the tables only"}
         out[algorithm] = o
     return out
 

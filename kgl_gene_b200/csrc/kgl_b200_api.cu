@@ -191,7 +191,8 @@ struct kgl_b200_ctx {
   DevBuf<uint2> d_mom_unit_range;
   DevBuf<unsigned long long> d_mom_pop_cmin;
   DevBuf<unsigned char> d_mom_btiles;
-  bool mom_used_mma = false;
+  bool mom_used_mma = false, mom_cnt_valid = false;
+  uint32_t mom_n_units = 0;
   DevBuf<double> d_mom_list, d_mom_limits, d_mom_rr;
   DevBuf<uint8_t> d_mom_tmp;
   bool mom_valid = false, mom_lists = false, mom_supported = false, used_moments = false;
@@ -832,12 +833,56 @@ bool moments_enabled(const kgl_b200_ctx* c) {
   return on && !c->opt.exact_sweeps;
 }
 
+// Tiles (of tile_genomes genomes) that hold a genome of each population, from the host copy of the assignment; returns the widest range.
+uint32_t moment_tile_ranges(const kgl_b200_ctx* c, uint32_t tile_genomes, uint32_t (&lo)[kMaxPop], uint32_t (&hi)[kMaxPop]) {
+  uint32_t widest = 1;
+  for (int k = 0; k < kMaxPop; ++k) { lo[k] = 0xFFFFFFFFu; hi[k] = 0; }
+  for (uint64_t g = 0; g < c->N; ++g) {
+    const int k = g < c->h_superpop.size() ? c->h_superpop[g] : 0;
+    if (k >= kMaxPop) continue;
+    const uint32_t t = (uint32_t)(g / tile_genomes);
+    lo[k] = std::min(lo[k], t); hi[k] = std::max(hi[k], t + 1);
+  }
+  for (int k = 0; k < kMaxPop; ++k) { if (hi[k] == 0) lo[k] = 0; widest = std::max(widest, hi[k] - lo[k]); }
+  return widest;
+}
+
+// The lists of rare homozygous cells and the limits of the feasible region, from the per-unit counts the tensor-core builder left.
+int moments_build_lists(kgl_b200_ctx* c) {
+  cudaStream_t st = c->stream;
+  const uint64_t N = c->N, npad = c->Npad;
+  KGL_CUDA(c, c->d_mom_unit_offs.ensure((size_t)c->mom_n_units * npad));
+  k_mom_unit_scan<<<blocks_for(N, 32), 256, 0, st>>>(c->d_mom_unit_cnt.p, c->d_mom_units.p, c->d_mom_unit_range.p, c->d_superpop.p, N, npad,
+                                                     c->d_mom_unit_offs.p, c->d_mom_totals.p);
+  KGL_LAUNCH_CHECK(c);
+  k_mom_base<<<1, 1024, 0, st>>>(c->d_mom_totals.p, N, c->d_mom_base.p);
+  KGL_LAUNCH_CHECK(c);
+  uint64_t list_len = 0;
+  KGL_CUDA(c, cudaMemcpyAsync(&list_len, c->d_mom_base.p + N, 8, cudaMemcpyDeviceToHost, st));
+  KGL_CUDA(c, cudaStreamSynchronize(st));
+  KGL_CUDA(c, c->d_mom_list.ensure(std::max<uint64_t>(1, list_len)));
+  MomFillParams F{};
+  F.packed = reinterpret_cast<const uint4*>(c->d_packed.p); F.units = c->units; F.rr = c->d_mom_rr.p;
+  F.superpop = c->d_superpop.p; F.n_genomes = N; F.n_genomes_padded = npad; F.rows = c->d_mom_rows2.p; F.unit_table = c->d_mom_units.p;
+  F.cnt = c->d_mom_unit_cnt.p; F.offs = c->d_mom_unit_offs.p; F.totals = c->d_mom_totals.p; F.base = c->d_mom_base.p; F.list = c->d_mom_list.p;
+  const uint32_t fill_tiles = moment_tile_ranges(c, kMomTile, F.tile_lo, F.tile_hi);
+  k_mom_unit_fill<<<dim3(fill_tiles, c->mom_n_units), kMomTile, 0, st>>>(F);
+  KGL_LAUNCH_CHECK(c);
+  k_mom_list_limits<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_list.p, c->d_mom_base.p, c->d_mom_totals.p, c->d_superpop.p,
+                                                        c->d_mom_pop_cmin.p, N, c->d_mom_limits.p);
+  KGL_LAUNCH_CHECK(c);
+  c->mom_lists = true;
+  c->launches += 4;
+  return KGL_B200_OK;
+}
+
 // Builds the per-genome moment tables of the current selection (and, for the root search, the lists of rare homozygous cells
 // and the limits of the feasible region). mom_supported = false afterwards: the selection has a frequency outside the bins, or
 // the tables would not fit -- the caller then sweeps with the exact kernels.
 int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   if (c->mom_valid && (!c->mom_supported || c->mom_lists || !want_lists)) return KGL_B200_OK;
-  c->mom_valid = true; c->mom_lists = false; c->mom_supported = false; c->mom_used_mma = false;
+  if (c->mom_valid && c->mom_supported && c->mom_used_mma && c->mom_cnt_valid) return moments_build_lists(c);   // tables of an earlier HallME run: only the lists are missing
+  c->mom_valid = true; c->mom_lists = false; c->mom_supported = false; c->mom_used_mma = false; c->mom_cnt_valid = false;
   int rc = ensure_sample_major(c); if (rc) return rc;       // the exact fallback reads the sample-major planes
   const uint64_t L = c->L, N = c->N, npad = c->Npad;
   const uint64_t row_lo = std::min<uint64_t>(L, c->sel_row_lo), row_hi = c->sel_row_hi == ~0ull ? L : std::min<uint64_t>(L, c->sel_row_hi);
@@ -902,39 +947,30 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   KGL_CUDA(c, c->d_mom_base.ensure(N + 1));
   KGL_CUDA(c, cudaMemsetAsync(c->d_mom_pm.p, 0, (size_t)c->n_pop * nbt * kMomJ * 8, st));
   KGL_CUDA(c, cudaMemsetAsync(c->d_mom_mi.p, 0, (size_t)npad * nbt * kMomJ * 8, st));
-  k_mom_dense<<<blocks_for(pop_begin[c->n_pop], 256), 256, 0, st>>>(c->d_mom_keys2.p, c->d_mom_rows2.p, c->d_mom_pop_begin.p, (int)c->n_pop,
-                                                                    c->d_af.p, L, unph, b_lo, nbt, scale, c->d_mom_pm.p);
-  KGL_LAUNCH_CHECK(c);
+  if (!use_mma) {              // the tensor-core path sums the population's moments while it writes the payload tiles (k_mom_btiles)
+    k_mom_dense<<<blocks_for(pop_begin[c->n_pop], 256), 256, 0, st>>>(c->d_mom_keys2.p, c->d_mom_rows2.p, c->d_mom_pop_begin.p, (int)c->n_pop,
+                                                                      c->d_af.p, L, unph, b_lo, nbt, scale, c->d_mom_pm.p);
+    KGL_LAUNCH_CHECK(c);
+  }
   uint64_t list_len = 0;
   if (use_mma) {
     KGL_CUDA(c, c->d_mom_btiles.ensure((size_t)std::max<uint32_t>(1, n_btiles) * 2 * kMmaBTile));
     KGL_CUDA(c, c->d_mom_rr.ensure(n_items));
-    k_mom_btiles<<<n_units, kMmaK, 0, st>>>(c->d_mom_units.p, c->d_mom_rows2.p, c->d_af.p, L, unph, scale, c->d_mom_btiles.p, c->d_mom_rr.p);
+    k_mom_btiles<<<n_units, kMmaK, 0, st>>>(c->d_mom_units.p, c->d_mom_rows2.p, c->d_af.p, L, unph, scale, c->d_mom_btiles.p, c->d_mom_rr.p, b_lo, nbt, c->d_mom_pm.p);
     KGL_LAUNCH_CHECK(c);
     if (want_lists) { KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad)); KGL_CUDA(c, c->d_mom_unit_offs.ensure((size_t)n_units * npad)); }
+    const bool keep_counts = (uint64_t)n_units * npad * 8 <= (4ull << 30);     // lets a later root search add its lists to these tables
+    if (keep_counts) KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad));
     MomMmaParams M{};
+    const uint32_t mma_tiles = moment_tile_ranges(c, kMmaM, M.tile_lo, M.tile_hi);
     M.packed = reinterpret_cast<const uint4*>(c->d_packed.p); M.units = c->units;
     M.superpop = c->d_superpop.p; M.n_genomes = N; M.n_genomes_padded = npad;
     M.rows = c->d_mom_rows2.p; M.unit_table = c->d_mom_units.p; M.btiles = c->d_mom_btiles.p;
-    M.b_lo = b_lo; M.nbt = nbt; M.scale = scale; M.mi = c->d_mom_mi.p; M.cnt = want_lists ? c->d_mom_unit_cnt.p : nullptr;
-    k_mom_mma<<<dim3(n_units, (unsigned)((N + kMmaM - 1) / kMmaM)), kMmaM, 0, st>>>(M);
+    M.b_lo = b_lo; M.nbt = nbt; M.scale = scale; M.mi = c->d_mom_mi.p; M.cnt = keep_counts ? c->d_mom_unit_cnt.p : nullptr;
+    k_mom_mma<<<dim3(mma_tiles, n_units), kMmaM, 0, st>>>(M);
     KGL_LAUNCH_CHECK(c);
-    if (want_lists) {
-      k_mom_unit_scan<<<blocks_for(N, 32), 256, 0, st>>>(c->d_mom_unit_cnt.p, c->d_mom_units.p, c->d_mom_unit_range.p, c->d_superpop.p, N, npad,
-                                                          c->d_mom_unit_offs.p, c->d_mom_totals.p);
-      KGL_LAUNCH_CHECK(c);
-      k_mom_base<<<1, 1024, 0, st>>>(c->d_mom_totals.p, N, c->d_mom_base.p);
-      KGL_LAUNCH_CHECK(c);
-      KGL_CUDA(c, cudaMemcpyAsync(&list_len, c->d_mom_base.p + N, 8, cudaMemcpyDeviceToHost, st));
-      KGL_CUDA(c, cudaStreamSynchronize(st));
-      KGL_CUDA(c, c->d_mom_list.ensure(std::max<uint64_t>(1, list_len)));
-      MomFillParams F{};
-      F.packed = M.packed; F.units = c->units; F.rr = c->d_mom_rr.p;
-      F.superpop = c->d_superpop.p; F.n_genomes = N; F.n_genomes_padded = npad; F.rows = c->d_mom_rows2.p; F.unit_table = c->d_mom_units.p;
-      F.cnt = c->d_mom_unit_cnt.p; F.offs = c->d_mom_unit_offs.p; F.totals = c->d_mom_totals.p; F.base = c->d_mom_base.p; F.list = c->d_mom_list.p;
-      k_mom_unit_fill<<<dim3(n_units, (unsigned)((N + kMomTile - 1) / kMomTile)), kMomTile, 0, st>>>(F);
-      KGL_LAUNCH_CHECK(c);
-    }
+    c->mom_n_units = n_units; c->mom_cnt_valid = keep_counts;
+    if (want_lists) { rc = moments_build_lists(c); if (rc) return rc; }
     c->mom_used_mma = true;
   } else {
     const uint32_t chunks_per_pop = (longest + kMomChunk - 1) / kMomChunk;
@@ -964,9 +1000,9 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
       KGL_LAUNCH_CHECK(c);
     }
   }
-  if (want_lists) {
+  if (want_lists && !use_mma) {
     k_mom_list_limits<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_list.p, c->d_mom_base.p, c->d_mom_totals.p, c->d_superpop.p,
-                                                              c->d_mom_pop_cmin.p, N, c->d_mom_limits.p);
+                                                          c->d_mom_pop_cmin.p, N, c->d_mom_limits.p);
     KGL_LAUNCH_CHECK(c);
     c->mom_lists = true;
   }

@@ -645,7 +645,7 @@ k_mom_run(const MomRunParams P) {
   if (MODE == FAST_HALL) {
     const int limit = P.hall_sweeps > 0 ? P.hall_sweeps : 100000;
     for (int it = 0; it < limit; ++it) {
-      double s1, s2, n0;
+      double s1, s2, n0;                               // n0 (the homozygous cells) is the same in every sweep; recomputing it costs one add per bin
       mom_block_sums<FAST_HALL>(s_m, s_geo, P.b_lo, P.nbt, x, nullptr, 0, 0, s_red, s1, s2, n0);
       const double sum = x * (n0 + (1.0 - x) * s1);
       const double nx = (x == 0.0 && n_terms > 0.0) ? 0.0 : __ddiv_rn(sum, n_terms);       // as k_hall_update

@@ -106,10 +106,15 @@ __device__ __forceinline__ uint32_t mma_tile_offset(uint32_t n, uint32_t k) {
 // Payload tiles of a unit, stage by stage: [common 4 KB | rare 4 KB], column t of a tile = the limbs of item begin + 128 stage + t.
 __global__ void __launch_bounds__(kMmaK)
 k_mom_btiles(const MomUnit* __restrict__ units, const uint32_t* __restrict__ rows, const float* __restrict__ af, uint64_t n_loci,
-             int unphased, double scale, unsigned char* __restrict__ btiles, double* __restrict__ rr /* r of the rare class per sorted item */) {
+             int unphased, double scale, unsigned char* __restrict__ btiles, double* __restrict__ rr /* r of the rare class per sorted item */,
+             int b_lo, int nbt, long long* __restrict__ pm /* [n_pop][nbt][kMomJ]: the population's moments (what k_mom_dense computes) */) {
+  __shared__ long long s_pm[kMmaK / 32][kMomJ];
   const MomUnit U = units[blockIdx.x];
   const uint32_t n_stages = (U.end - U.begin + kMmaK - 1) / kMmaK;
   const long long offset = (long long)scale;
+  long long dense[kMomJ];
+#pragma unroll
+  for (int j = 0; j < kMomJ; ++j) dense[j] = 0;
   for (uint32_t s = 0; s < n_stages; ++s) {
     const uint32_t i = U.begin + s * kMmaK + threadIdx.x;
     unsigned char* tile = btiles + (size_t)(U.tile_base + s) * (2 * kMmaBTile);
@@ -128,6 +133,11 @@ k_mom_btiles(const MomUnit* __restrict__ units, const uint32_t* __restrict__ row
         const double r = x == 0 ? m.r_common : m.r_rare;
         long long u[kMomJ - 1];
         mom_powers(r, mom_bin(r), scale, u);
+        if (x == 0) {
+          dense[0] += 1;
+#pragma unroll
+          for (int j = 0; j < kMomJ - 1; ++j) dense[j + 1] += u[j];
+        }
         col[x][0] = 1;
 #pragma unroll
         for (int j = 0; j < kMomJ - 1; ++j) {
@@ -142,6 +152,22 @@ k_mom_btiles(const MomUnit* __restrict__ units, const uint32_t* __restrict__ row
 #pragma unroll
       for (int n = 0; n < kMmaN; ++n) tile[x * kMmaBTile + mma_tile_offset(n, threadIdx.x)] = col[x][n];
   }
+  // the unit's share of the population's moments: every item of a unit has the unit's common bin
+  if (U.cb < 0) return;
+#pragma unroll
+  for (int j = 0; j < kMomJ; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dense[j] += __shfl_xor_sync(kFull, dense[j], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < kMomJ; ++j) s_pm[threadIdx.x >> 5][j] = dense[j];
+  __syncthreads();
+  if (threadIdx.x < kMomJ) {
+    long long t = 0;
+    for (int w = 0; w < kMmaK / 32; ++w) t += s_pm[w][threadIdx.x];
+    const int bin = U.cb >= kMomBinsMax ? nbt - 1 : U.cb - b_lo;
+    atomicAdd(reinterpret_cast<unsigned long long*>(pm) + ((size_t)U.pop * nbt + bin) * kMomJ + threadIdx.x, (unsigned long long)t);
+  }
 }
 
 struct MomMmaParams {
@@ -153,6 +179,7 @@ struct MomMmaParams {
   int b_lo, nbt; double scale;
   long long* mi;                                     // [n_genomes_padded][nbt][kMomJ]
   uint32_t* cnt;                                     // [n_units][n_genomes_padded] rare homozygous cells (null: not wanted)
+  uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // 128-genome tiles that hold a genome of the population (grid.x spans the widest range)
 };
 
 __device__ __forceinline__ void mma_i8_n32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -203,9 +230,12 @@ k_mom_mma(const MomMmaParams P) {
   __shared__ __align__(16) uint32_t s_mask[2][4][kMmaK];           // [class][warp slice][locus]
   __shared__ uint64_t s_bar[2];
   __shared__ uint32_t s_tmem, s_mine[4];
-  const MomUnit U = P.unit_table[blockIdx.x];
+  // grid = (tiles of a population, units): the tiles of one unit run together, so its rows and payload tiles come from L2
+  const MomUnit U = P.unit_table[blockIdx.y];
+  const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x;
+  if (tile >= P.tile_hi[U.pop]) return;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t g = (uint64_t)blockIdx.y * kMmaM + tid;
+  const uint64_t g = (uint64_t)tile * kMmaM + tid;
   const bool mine = g < P.n_genomes && P.superpop[g] == U.pop;
   if (!__syncthreads_or(mine)) return;
   const uint32_t mine_mask = __ballot_sync(kFull, mine);
@@ -225,9 +255,21 @@ k_mom_mma(const MomMmaParams P) {
   const uint32_t tmem_base = s_tmem;
   const uint32_t mm0 = s_mine[0], mm1 = s_mine[1], mm2 = s_mine[2], mm3 = s_mine[3];
   const uint32_t n_stages = (U.end - U.begin + kMmaK - 1) / kMmaK;
-  const uint64_t unit0 = (uint64_t)blockIdx.y * (kMmaM / 64);
+  const uint64_t unit0 = (uint64_t)tile * (kMmaM / 64);
   uint32_t b_phase = 0, mma_phase = 0;
   bool pending = false, acc[2] = {false, false};
+  // the two units of this thread's locus, requested one stage ahead
+  auto fetch = [&](uint32_t s, uint4 (&v)[2]) {
+    v[0] = make_uint4(0u, 0u, 0u, 0u); v[1] = v[0];
+    const uint32_t i = U.begin + s * kMmaK + tid;
+    if (s < n_stages && i < U.end) {
+      const uint4* row = P.packed + (uint64_t)P.rows[i] * P.units + unit0;
+      if (unit0 < P.units) v[0] = __ldg(row);
+      if (unit0 + 1 < P.units) v[1] = __ldg(row + 1);
+    }
+  };
+  uint4 nxt[2];
+  fetch(0, nxt);
 
   for (uint32_t s = 0; s < n_stages; ++s) {
     if (pending) { mbar_wait(bar_mma, mma_phase); mma_phase ^= 1; pending = false; }      // the MMAs of the stage before have read s_a / s_b
@@ -237,17 +279,16 @@ k_mom_mma(const MomMmaParams P) {
     }
     // masks of this thread's locus over the tile's four warp slices
     uint32_t nc[4] = {0u, 0u, 0u, 0u}, ra[4] = {0u, 0u, 0u, 0u};
-    const uint32_t i = U.begin + s * kMmaK + tid;
-    if (i < U.end) {
-      const uint4* row = P.packed + (uint64_t)P.rows[i] * P.units + unit0;
+    if (U.begin + s * kMmaK + tid < U.end) {
 #pragma unroll
       for (int k = 0; k < 2; ++k)
         if (unit0 + k < P.units) {
-          const uint4 v = __ldg(row + k);                       // {lo.lo32, lo.hi32, hi.lo32, hi.hi32}
+          const uint4 v = nxt[k];                               // {lo.lo32, lo.hi32, hi.lo32, hi.hi32}
           const MomMasks a = mom_masks(v.x, v.z, U.common_code, U.rare_code), b = mom_masks(v.y, v.w, U.common_code, U.rare_code);
           nc[2 * k] = a.nc; nc[2 * k + 1] = b.nc; ra[2 * k] = a.rare; ra[2 * k + 1] = b.rare;
         }
     }
+    fetch(s + 1, nxt);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { s_mask[0][k][tid] = nc[k]; s_mask[1][k][tid] = ra[k]; }
     const bool has_c = __syncthreads_or(((nc[0] & mm0) | (nc[1] & mm1) | (nc[2] & mm2) | (nc[3] & mm3)) != 0u);
@@ -315,7 +356,7 @@ k_mom_mma(const MomMmaParams P) {
     }
     if (x == 1) n_rare = v[0];
   }
-  if (P.cnt && mine) P.cnt[(uint64_t)blockIdx.x * P.n_genomes_padded + g] = n_rare;
+  if (P.cnt && mine) P.cnt[(uint64_t)blockIdx.y * P.n_genomes_padded + g] = n_rare;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(64) : "memory");
@@ -361,6 +402,7 @@ struct MomFillParams {
   const uint32_t* rows; const MomUnit* unit_table;
   const uint32_t* cnt; const uint32_t* offs; const uint32_t* totals; const uint64_t* base;
   double* list;
+  uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // kMomTile-genome tiles of the population
 };
 
 // list[base[g] + ...] = r of the genome's rare homozygous cells: hom-alt part (r ascending), then hom-ref part (r descending).
@@ -369,16 +411,17 @@ k_mom_unit_fill(const MomFillParams P) {
   constexpr int kWarps = kMomTile / 32;
   __shared__ uint32_t s_rare[kMomStep][kWarps];
   __shared__ double s_r[kMomStep];
-  const MomUnit U = P.unit_table[blockIdx.x];
-  if (U.rare_code < 0) return;
+  const MomUnit U = P.unit_table[blockIdx.y];
+  const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x;
+  if (U.rare_code < 0 || tile >= P.tile_hi[U.pop]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t g = (uint64_t)blockIdx.y * kMomTile + threadIdx.x;
-  const bool mine = g < P.n_genomes && P.superpop[g] == U.pop && P.cnt[(uint64_t)blockIdx.x * P.n_genomes_padded + g] != 0u;
+  const uint64_t g = (uint64_t)tile * kMomTile + threadIdx.x;
+  const bool mine = g < P.n_genomes && P.superpop[g] == U.pop && P.cnt[(uint64_t)blockIdx.y * P.n_genomes_padded + g] != 0u;
   if (!__syncthreads_or(mine)) return;                      // no genome of the tile has a rare homozygous cell in this unit
   const uint32_t mine_mask = __ballot_sync(kFull, mine);
   const uint32_t bit = mine ? (1u << lane) : 0u;
   uint64_t pos = 0;
-  if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)blockIdx.x * P.n_genomes_padded + g];
+  if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)blockIdx.y * P.n_genomes_padded + g];
   const int tj = threadIdx.x >> 1, th = threadIdx.x & 1;
   for (uint32_t s = U.begin; s < U.end; s += kMomStep) {
     __syncthreads();
@@ -388,7 +431,7 @@ k_mom_unit_fill(const MomFillParams P) {
       if (i < U.end) {
         const uint32_t l = P.rows[i];
         if (th == 0) s_r[tj] = P.rr[i];
-        const uint64_t unit0 = (uint64_t)blockIdx.y * (kMomTile / 64) + 2 * th;
+        const uint64_t unit0 = (uint64_t)tile * (kMomTile / 64) + 2 * th;
         const uint4* row = P.packed + (uint64_t)l * P.units + unit0;
 #pragma unroll
         for (int k = 0; k < 2; ++k)

@@ -37,7 +37,7 @@ def test_python_binding_lists_the_same_symbols():
 def test_struct_layout_matches_header():
     from kgl_gene_b200 import capi
     assert capi.RESULT_DTYPE.itemsize == 80          # 5 x (uint64 + double)
-    assert C.sizeof(capi.InbreedOptions) == 32
+    assert C.sizeof(capi.InbreedOptions) == 48         # pointer, int32 (+4), double, 5 x int32 (+4)
 
 
 def test_no_cpu_fallback_without_gpu(lib_path):
