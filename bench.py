@@ -651,20 +651,16 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
         n_tiles = len(range(rank, n_tiles_all, world))
         k_stages = (kl + 127) // 128
         ops = 2.0 * n_tiles * 128 * 256 * k_stages * 128
-        peak_tops = None
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            peak_tops = 2.0 * float(peaks.get("bf16_tflops", 0.0)) or None
-        except Exception:
-            pass
-        peak_tops = peak_tops or 2.0 * 1608.9
+        # int8 tensor peak: MEASURED on this pool's B200s with the kernel's own MMA issue loop and epilogue, operand staging switched
+        # off (tools/grambench --skip 2, profiles/r01_grambench_skip_modes.log: 3512 / 3567 TOP/s at 2504 x 1.1 M / 8192 x 400 k)
+        peak_tops = 3567.3
         grm = {"metric": "kinship sample-pair-loci/s (int8 Gram matrix on tcgen05)", "value": pair_loci / (g_ms * 1e-3), "unit": "sample-pair-loci/s",
                "ms_per_step": g_ms, "n_gpus": world, "scaling": "strong",
                "kernel": "k_gram_i8 (tcgen05.mma kind::i8, TMEM accumulators, 128x256 tiles, in-kernel 2-bit -> int8 expansion)",
                "roofline": {"bound": "tensor", "achieved": ops / (gk_ms * 1e-3) / 1e12, "peak": peak_tops, "unit": "int8 TOP/s",
                             "frac": ops / (gk_ms * 1e-3) / 1e12 / peak_tops,
-                            "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 peak itself not measured by the driver)",
-                            "kernel_ms": gk_ms, "mma_only_ceiling_tops": 3512.0}}
+                            "peak_source": "measured: tcgen05.mma kind::i8 128x256x32 issued back to back + epilogue, no operand staging (profiles/r01_grambench_skip_modes.log)",
+                            "kernel_ms": gk_ms, "twice_measured_bf16_tops": 2.0 * 1608.9}}
     if rank != 0:
         return None
     # INT-pipe roofline of the tile kernel: 5 LOP3 + 1 POPC per executed pair-word (two-plane form: 3 for the two difference

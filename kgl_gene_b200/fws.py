@@ -6,6 +6,10 @@
   HeteroHomoZygous     kga_analytic/kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105 (updateVariantAnalysisType),
                        :362-412 (UpdateSampleLocation: Wright's FIS against the location aggregate)
 
+The product form of the HeteroHomoZygous half is the C++ class `HeteroHomoB200` (kgl_gene_b200/host/kga_analysis_pfemp_b200.{h,cpp})
+over `kgl_b200_run_hetero_homo` and `kgl_b200_location_fis` (include/kgl_b200.h); this module is the ctypes-side mirror the
+tests use to check the same bookkeeping from Python.
+
 The reference rebuilds a VariantDBVariant twelve times and copies the population eleven times for this; here it is one raw
 pass plus one masked pass of the streaming kernel per bin. Everything in this module is integer bookkeeping on the kernels'
 outputs; nothing here touches the CPU oracle.
