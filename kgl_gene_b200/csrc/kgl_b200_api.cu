@@ -937,9 +937,12 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   const double scale = std::ldexp(1.0, std::min(sbits, 46));          // the tensor-core payload has six 8-bit limbs for U + 2^s
   const uint32_t n_units = unit_out[0], n_btiles = unit_out[1];
   static const bool mma_off = std::getenv("KGL_B200_MOMENTS_NO_MMA") != nullptr;
+  // scratch of the tensor-core builder (payload tiles, per-unit counts and offsets): at most a third of what is free now
+  size_t free_bytes = 0, total_bytes = 0;
+  KGL_CUDA(c, cudaMemGetInfo(&free_bytes, &total_bytes));
+  const uint64_t scratch_limit = std::max<uint64_t>(4ull << 30, free_bytes / 3);
   const bool use_mma = !mma_off && !c->opt.moments_on_cuda_cores && unit_out[2] <= kMomMaxUnits && n_units > 0 &&
-                       (uint64_t)n_btiles * 2 * kMmaBTile <= (4ull << 30) &&
-                       (!want_lists || (uint64_t)n_units * npad * 8 <= (4ull << 30));
+                       (uint64_t)n_btiles * 2 * kMmaBTile + (want_lists ? (uint64_t)n_units * npad * 8 : 0) <= scratch_limit;
   KGL_CUDA(c, c->d_mom_pm.ensure((size_t)c->n_pop * nbt * kMomJ));
   KGL_CUDA(c, c->d_mom_mi.ensure((size_t)npad * nbt * kMomJ));
   KGL_CUDA(c, c->d_mom_totals.ensure((size_t)npad * 2));
@@ -959,7 +962,7 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
     k_mom_btiles<<<n_units, kMmaK, 0, st>>>(c->d_mom_units.p, c->d_mom_rows2.p, c->d_af.p, L, unph, scale, c->d_mom_btiles.p, c->d_mom_rr.p, b_lo, nbt, c->d_mom_pm.p);
     KGL_LAUNCH_CHECK(c);
     if (want_lists) { KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad)); KGL_CUDA(c, c->d_mom_unit_offs.ensure((size_t)n_units * npad)); }
-    const bool keep_counts = (uint64_t)n_units * npad * 8 <= (4ull << 30);     // lets a later root search add its lists to these tables
+    const bool keep_counts = want_lists || (uint64_t)n_units * npad * 8 <= (2ull << 30);     // lets a later root search add its lists to these tables
     if (keep_counts) KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad));
     MomMmaParams M{};
     const uint32_t mma_tiles = moment_tile_ranges(c, kMmaM, M.tile_lo, M.tile_hi);
@@ -2099,7 +2102,7 @@ static int run_whole_from_tables(kgl_b200_ctx* c, int* finished) {
   c->used_moments = true;
   if (hall) {
     KGL_CUDA(c, cudaFuncSetAttribute(k_mom_run<FAST_HALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_mom_run<FAST_HALL><<<(unsigned)c->N, 128, smem, c->stream>>>(P);
+    k_mom_run<FAST_HALL><<<(unsigned)c->N, kMomRunThreads, smem, c->stream>>>(P);
     KGL_LAUNCH_CHECK(c);
     c->iteration = c->opt.hall_sweeps > 0 ? c->opt.hall_sweeps : 0;
     *finished = 1;
@@ -2113,7 +2116,7 @@ static int run_whole_from_tables(kgl_b200_ctx* c, int* finished) {
   P.remaining = c->d_flag.p;
   KGL_CUDA(c, cudaMemsetAsync(c->d_flag.p, 0, 8, c->stream));
   KGL_CUDA(c, cudaFuncSetAttribute(k_mom_run<FAST_NEWTON>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_mom_run<FAST_NEWTON><<<(unsigned)c->N, 128, smem, c->stream>>>(P);
+  k_mom_run<FAST_NEWTON><<<(unsigned)c->N, kMomRunThreads, smem, c->stream>>>(P);
   KGL_LAUNCH_CHECK(c);
   unsigned long long remaining = 0;
   KGL_CUDA(c, cudaMemcpyAsync(&remaining, c->d_flag.p, 8, cudaMemcpyDeviceToHost, c->stream));

@@ -489,6 +489,15 @@ k_mom_finalize(long long* __restrict__ mi, const long long* __restrict__ pm, con
   }
 }
 
+// 1/d for the sweeps: MUFU.RCP64H and the second-order correction x0 (1 + e + e^2), e = 1 - d x0: 2.2e-16 relative (measured over
+// 2^26 arguments, tools/kbench), four instructions instead of the IEEE divide's dependent chain.
+__device__ __forceinline__ double mom_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  const double e = fma(-d, x, 1.0);
+  return fma(x, fma(e, e, e), x);
+}
+
 // ---- one sweep -----------------------------------------------------------------------------------------------------------------
 // Block = genome. NEWTON: out[pos] = {S1, S2} in the layout of one chunk of k_terms_fast<FAST_NEWTON> (k_newton_reduce follows);
 // HALL: iter[g][0] = f (n_hom + (1 - f) S1).
@@ -520,7 +529,7 @@ k_mom_eval(const double* __restrict__ mom, int b_lo, int nbt, const double* __re
     if (m0 == 0.0) continue;
     double rc, w;
     mom_geometry(gb, rc, w);
-    const double t = 1.0 / (x + rc), z = -w * t;
+    const double t = mom_rcp(x + rc), z = -w * t;
     const double m1 = M[b * kMomJ + 1], m2 = M[b * kMomJ + 2], m3 = M[b * kMomJ + 3], m4 = M[b * kMomJ + 4], m5 = M[b * kMomJ + 5];
     const double p1 = fma(z, fma(z, fma(z, fma(z, fma(z, m5, m4), m3), m2), m1), m0);
     s1 = fma(t, p1, s1);
@@ -537,13 +546,13 @@ k_mom_eval(const double* __restrict__ mom, int b_lo, int nbt, const double* __re
     for (uint64_t i = threadIdx.x; i < n_alt; i += blockDim.x) {           // hom-alt part: r ascending
       const double r = L[i];
       if (!(r < edge)) break;
-      const double t = 1.0 / (x + r);
+      const double t = mom_rcp(x + r);
       s1 += t; s2 = fma(t, t, s2); n0 += 1.0;
     }
     for (uint64_t i = threadIdx.x; i < n - n_alt; i += blockDim.x) {       // hom-ref part: r descending, from its end
       const double r = L[n - 1 - i];
       if (!(r < edge)) break;
-      const double t = 1.0 / (x + r);
+      const double t = mom_rcp(x + r);
       s1 += t; s2 = fma(t, t, s2); n0 += 1.0;
     }
   }
@@ -590,7 +599,7 @@ __device__ __forceinline__ void mom_block_sums(const double* s_m, const double2*
     const double m0 = s_m[b * kMomJ];
     if (m0 == 0.0) continue;
     const double2 geo = s_geo[b];
-    const double t = 1.0 / (x + geo.x), z = -geo.y * t;
+    const double t = mom_rcp(x + geo.x), z = -geo.y * t;
     const double m1 = s_m[b * kMomJ + 1], m2 = s_m[b * kMomJ + 2], m3 = s_m[b * kMomJ + 3], m4 = s_m[b * kMomJ + 4], m5 = s_m[b * kMomJ + 5];
     s1 = fma(t, fma(z, fma(z, fma(z, fma(z, fma(z, m5, m4), m3), m2), m1), m0), s1);
     if (MODE == FAST_NEWTON) s2 = fma(t * t, fma(z, fma(z, fma(z, fma(z, fma(z, 6.0 * m5, 5.0 * m4), 4.0 * m3), 3.0 * m2), 2.0 * m1), m0), s2);
@@ -601,35 +610,34 @@ __device__ __forceinline__ void mom_block_sums(const double* s_m, const double2*
     for (uint64_t i = threadIdx.x; i < n_alt; i += blockDim.x) {
       const double r = L[i];
       if (!(r < edge)) break;
-      const double t = 1.0 / (x + r);
+      const double t = mom_rcp(x + r);
       s1 += t; s2 = fma(t, t, s2); n0 += 1.0;
     }
     for (uint64_t i = threadIdx.x; i < n - n_alt; i += blockDim.x) {
       const double r = L[n - 1 - i];
       if (!(r < edge)) break;
-      const double t = 1.0 / (x + r);
+      const double t = mom_rcp(x + r);
       s1 += t; s2 = fma(t, t, s2); n0 += 1.0;
     }
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2); n0 = warp_sum(n0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();                                   // the sums of the sweep before have been read
-  if (lane == 0) { s_red[warp] = s1; s_red[4 + warp] = s2; s_red[8 + warp] = n0; }
+  if (lane == 0) { s_red[warp] = s1; s_red[8 + warp] = s2; s_red[16 + warp] = n0; }
   __syncthreads();
-  s1 = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-  s2 = (s_red[4] + s_red[5]) + (s_red[6] + s_red[7]);
-  n0 = (s_red[8] + s_red[9]) + (s_red[10] + s_red[11]);
+  s1 = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
+  s2 = ((s_red[8] + s_red[9]) + (s_red[10] + s_red[11])) + ((s_red[12] + s_red[13]) + (s_red[14] + s_red[15]));
+  n0 = ((s_red[16] + s_red[17]) + (s_red[18] + s_red[19])) + ((s_red[20] + s_red[21]) + (s_red[22] + s_red[23]));
 }
 
+constexpr int kMomRunThreads = 256;                    // eight warps per genome: mom_block_sums adds eight partial sums
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMomRunThreads)
 k_mom_run(const MomRunParams P) {
   extern __shared__ __align__(16) unsigned char mom_run_smem[];
   double* s_m = reinterpret_cast<double*>(mom_run_smem);                       // [nbt][kMomJ]
   double2* s_geo = reinterpret_cast<double2*>(s_m + (size_t)P.nbt * kMomJ);    // [nbt] {rc, w}
-  __shared__ double s_red[12];
-  __shared__ double s_x;
-  __shared__ int s_stop;
+  __shared__ double s_red[24];
   const uint64_t g = blockIdx.x;
   const double* M = P.mom + g * (uint64_t)P.nbt * kMomJ;
   for (int i = threadIdx.x; i < P.nbt * kMomJ; i += blockDim.x) s_m[i] = M[i];

@@ -272,12 +272,7 @@ k_mom_mma(const MomMmaParams P) {
   fetch(0, nxt);
 
   for (uint32_t s = 0; s < n_stages; ++s) {
-    if (pending) { mbar_wait(bar_mma, mma_phase); mma_phase ^= 1; pending = false; }      // the MMAs of the stage before have read s_a / s_b
-    if (tid == 0) {
-      mbar_expect_tx(bar_b, 2 * kMmaBTile);
-      tma_bulk_g2s(smem_u32(s_b), P.btiles + (size_t)(U.tile_base + s) * (2 * kMmaBTile), 2 * kMmaBTile, bar_b);
-    }
-    // masks of this thread's locus over the tile's four warp slices
+    // masks of this thread's locus over the tile's four warp slices (the MMAs of the stage before may still be running)
     uint32_t nc[4] = {0u, 0u, 0u, 0u}, ra[4] = {0u, 0u, 0u, 0u};
     if (U.begin + s * kMmaK + tid < U.end) {
 #pragma unroll
@@ -293,18 +288,25 @@ k_mom_mma(const MomMmaParams P) {
     for (int k = 0; k < 4; ++k) { s_mask[0][k][tid] = nc[k]; s_mask[1][k][tid] = ra[k]; }
     const bool has_c = __syncthreads_or(((nc[0] & mm0) | (nc[1] & mm1) | (nc[2] & mm2) | (nc[3] & mm3)) != 0u);
     const bool has_r = __syncthreads_or(((ra[0] & mm0) | (ra[1] & mm1) | (ra[2] & mm2) | (ra[3] & mm3)) != 0u);
-    const uint32_t keep = mine ? ~0u : 0u;
-    if (has_c) mma_build_row(s_a[0], s_mask[0][warp], tid, lane, keep);
-    if (has_r) {            // rare homozygous cells are few: most warps have none in a stage
-      const uint32_t* mr = s_mask[1][warp];
-      if (__any_sync(kFull, ((mr[lane] | mr[lane + 32] | mr[lane + 64] | mr[lane + 96]) & mine_mask) != 0u)) mma_build_row(s_a[1], mr, tid, lane, keep);
-      else mma_zero_row(s_a[1], tid);
+    if (pending) { mbar_wait(bar_mma, mma_phase); mma_phase ^= 1; pending = false; }      // the MMAs of the stage before have read s_a / s_b
+    if (has_c || has_r) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_b, 2 * kMmaBTile);
+        tma_bulk_g2s(smem_u32(s_b), P.btiles + (size_t)(U.tile_base + s) * (2 * kMmaBTile), 2 * kMmaBTile, bar_b);
+      }
+      const uint32_t keep = mine ? ~0u : 0u;
+      if (has_c) mma_build_row(s_a[0], s_mask[0][warp], tid, lane, keep);
+      if (has_r) {            // rare homozygous cells are few: most warps have none in a stage
+        const uint32_t* mr = s_mask[1][warp];
+        if (__any_sync(kFull, ((mr[lane] | mr[lane + 32] | mr[lane + 64] | mr[lane + 96]) & mine_mask) != 0u)) mma_build_row(s_a[1], mr, tid, lane, keep);
+        else mma_zero_row(s_a[1], tid);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar_b, b_phase);
-      if (has_c || has_r) {
+    __syncthreads();                                   // s_a complete; s_mask free for the next stage
+    if (has_c || has_r) {
+      if (tid == 0) {
+        mbar_wait(bar_b, b_phase);
         tc_fence_after();
 #pragma unroll
         for (uint32_t x = 0; x < 2; ++x) {
@@ -316,10 +318,10 @@ k_mom_mma(const MomMmaParams P) {
         }
         tc_commit(bar_mma);
       }
+      b_phase ^= 1;
+      pending = true;
+      acc[0] = acc[0] || has_c; acc[1] = acc[1] || has_r;
     }
-    b_phase ^= 1;
-    if (has_c || has_r) pending = true;
-    acc[0] = acc[0] || has_c; acc[1] = acc[1] || has_r;
   }
   if (pending) mbar_wait(bar_mma, mma_phase);
   tc_fence_after();
@@ -423,27 +425,34 @@ k_mom_unit_fill(const MomFillParams P) {
   uint64_t pos = 0;
   if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)blockIdx.y * P.n_genomes_padded + g];
   const int tj = threadIdx.x >> 1, th = threadIdx.x & 1;
+  const uint64_t unit0 = (uint64_t)tile * (kMomTile / 64) + 2 * th;
+  // this thread's half row of the step after the current one, requested a step ahead
+  auto fetch = [&](uint32_t s, uint4 (&v)[2], double& r) {
+    v[0] = make_uint4(0u, 0u, 0u, 0u); v[1] = v[0]; r = 0.0;
+    const uint32_t i = s + tj;
+    if (s < U.end && i < U.end) {
+      const uint4* row = P.packed + (uint64_t)P.rows[i] * P.units + unit0;
+      if (unit0 < P.units) v[0] = __ldg(row);
+      if (unit0 + 1 < P.units) v[1] = __ldg(row + 1);
+      if (th == 0) r = P.rr[i];
+    }
+  };
+  uint4 nxt[2]; double nxt_r;
+  fetch(U.begin, nxt, nxt_r);
   for (uint32_t s = U.begin; s < U.end; s += kMomStep) {
     __syncthreads();
     {
-      const uint32_t i = s + tj;
-      uint32_t mk[4] = {0u, 0u, 0u, 0u};
-      if (i < U.end) {
-        const uint32_t l = P.rows[i];
-        if (th == 0) s_r[tj] = P.rr[i];
-        const uint64_t unit0 = (uint64_t)tile * (kMomTile / 64) + 2 * th;
-        const uint4* row = P.packed + (uint64_t)l * P.units + unit0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (unit0 + k < P.units) {
-            const uint4 v = __ldg(row + k);
-            mk[2 * k] = mom_code_mask(make_uint2(v.x, v.z), U.rare_code);
-            mk[2 * k + 1] = mom_code_mask(make_uint2(v.y, v.w), U.rare_code);
-          }
-      }
+      uint32_t mk[4];
+      mk[0] = mom_code_mask(make_uint2(nxt[0].x, nxt[0].z), U.rare_code); mk[1] = mom_code_mask(make_uint2(nxt[0].y, nxt[0].w), U.rare_code);
+      mk[2] = mom_code_mask(make_uint2(nxt[1].x, nxt[1].z), U.rare_code); mk[3] = mom_code_mask(make_uint2(nxt[1].y, nxt[1].w), U.rare_code);
+      if (s + tj >= U.end) { mk[0] = 0u; mk[1] = 0u; mk[2] = 0u; mk[3] = 0u; }      // rare_code 0: zero padding would read as hom-ref
+      if (unit0 >= P.units) { mk[0] = 0u; mk[1] = 0u; }
+      if (unit0 + 1 >= P.units) { mk[2] = 0u; mk[3] = 0u; }
+      if (th == 0) s_r[tj] = nxt_r;
 #pragma unroll
       for (int k = 0; k < 4; ++k) s_rare[tj][4 * th + k] = mk[k];
     }
+    fetch(s + kMomStep, nxt, nxt_r);
     __syncthreads();
     const int n_here = (int)min((uint32_t)kMomStep, U.end - s);
 #pragma unroll
