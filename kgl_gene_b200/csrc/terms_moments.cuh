@@ -583,7 +583,8 @@ struct MomRunParams {
   unsigned long long* remaining;     // genomes the kernel left unfinished (they need the exact cell-by-cell kernel)
 };
 
-template <int MODE>
+// COUNT: also the number of homozygous cells n0 (the same in every sweep: HallME asks once).
+template <int MODE, bool COUNT>
 __device__ __forceinline__ void mom_block_sums(const double* s_m, const double2* s_geo, int b_lo, int nbt, double x, const double* L,
                                                uint64_t n, uint64_t n_alt, double* s_red, double& s1, double& s2, double& n0) {
   double edge = 0.0; int b_edge = 0;
@@ -603,31 +604,33 @@ __device__ __forceinline__ void mom_block_sums(const double* s_m, const double2*
     const double m1 = s_m[b * kMomJ + 1], m2 = s_m[b * kMomJ + 2], m3 = s_m[b * kMomJ + 3], m4 = s_m[b * kMomJ + 4], m5 = s_m[b * kMomJ + 5];
     s1 = fma(t, fma(z, fma(z, fma(z, fma(z, fma(z, m5, m4), m3), m2), m1), m0), s1);
     if (MODE == FAST_NEWTON) s2 = fma(t * t, fma(z, fma(z, fma(z, fma(z, fma(z, 6.0 * m5, 5.0 * m4), 4.0 * m3), 3.0 * m2), 2.0 * m1), m0), s2);
-    n0 += m0;
+    if (COUNT) n0 += m0;
   }
-  if (threadIdx.x == 0) n0 += s_m[(nbt - 1) * kMomJ];
+  if (COUNT && threadIdx.x == 0) n0 += s_m[(nbt - 1) * kMomJ];
   if (MODE == FAST_NEWTON && x < 0.0 && L) {
     for (uint64_t i = threadIdx.x; i < n_alt; i += blockDim.x) {
       const double r = L[i];
       if (!(r < edge)) break;
       const double t = mom_rcp(x + r);
-      s1 += t; s2 = fma(t, t, s2); n0 += 1.0;
+      s1 += t; s2 = fma(t, t, s2); if (COUNT) n0 += 1.0;
     }
     for (uint64_t i = threadIdx.x; i < n - n_alt; i += blockDim.x) {
       const double r = L[n - 1 - i];
       if (!(r < edge)) break;
       const double t = mom_rcp(x + r);
-      s1 += t; s2 = fma(t, t, s2); n0 += 1.0;
+      s1 += t; s2 = fma(t, t, s2); if (COUNT) n0 += 1.0;
     }
   }
-  s1 = warp_sum(s1); s2 = warp_sum(s2); n0 = warp_sum(n0);
+  s1 = warp_sum(s1);
+  if (MODE == FAST_NEWTON) s2 = warp_sum(s2);
+  if (COUNT) n0 = warp_sum(n0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();                                   // the sums of the sweep before have been read
-  if (lane == 0) { s_red[warp] = s1; s_red[8 + warp] = s2; s_red[16 + warp] = n0; }
+  if (lane == 0) { s_red[warp] = s1; if (MODE == FAST_NEWTON) s_red[8 + warp] = s2; if (COUNT) s_red[16 + warp] = n0; }
   __syncthreads();
   s1 = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
-  s2 = ((s_red[8] + s_red[9]) + (s_red[10] + s_red[11])) + ((s_red[12] + s_red[13]) + (s_red[14] + s_red[15]));
-  n0 = ((s_red[16] + s_red[17]) + (s_red[18] + s_red[19])) + ((s_red[20] + s_red[21]) + (s_red[22] + s_red[23]));
+  if (MODE == FAST_NEWTON) s2 = ((s_red[8] + s_red[9]) + (s_red[10] + s_red[11])) + ((s_red[12] + s_red[13]) + (s_red[14] + s_red[15]));
+  if (COUNT) n0 = ((s_red[16] + s_red[17]) + (s_red[18] + s_red[19])) + ((s_red[20] + s_red[21]) + (s_red[22] + s_red[23]));
 }
 
 constexpr int kMomRunThreads = 256;                    // eight warps per genome: mom_block_sums adds eight partial sums
@@ -652,9 +655,11 @@ k_mom_run(const MomRunParams P) {
   __syncthreads();
   if (MODE == FAST_HALL) {
     const int limit = P.hall_sweeps > 0 ? P.hall_sweeps : 100000;
+    double n0 = 0.0;                                   // the homozygous cells: the same in every sweep
     for (int it = 0; it < limit; ++it) {
-      double s1, s2, n0;                               // n0 (the homozygous cells) is the same in every sweep; recomputing it costs one add per bin
-      mom_block_sums<FAST_HALL>(s_m, s_geo, P.b_lo, P.nbt, x, nullptr, 0, 0, s_red, s1, s2, n0);
+      double s1, s2, unused;
+      if (it == 0) mom_block_sums<FAST_HALL, true>(s_m, s_geo, P.b_lo, P.nbt, x, nullptr, 0, 0, s_red, s1, s2, n0);
+      else mom_block_sums<FAST_HALL, false>(s_m, s_geo, P.b_lo, P.nbt, x, nullptr, 0, 0, s_red, s1, s2, unused);
       const double sum = x * (n0 + (1.0 - x) * s1);
       const double nx = (x == 0.0 && n_terms > 0.0) ? 0.0 : __ddiv_rn(sum, n_terms);       // as k_hall_update
       const bool stop = P.hall_sweeps < 0 && fabs(nx - x) < 1e-15;
@@ -682,7 +687,7 @@ k_mom_run(const MomRunParams P) {
     bool hom_clamped = st == 1;
     if (st == 0) {
       double s1, s2, n0;
-      mom_block_sums<FAST_NEWTON>(s_m, s_geo, P.b_lo, P.nbt, x, L, n, n_alt, s_red, s1, s2, n0);
+      mom_block_sums<FAST_NEWTON, false>(s_m, s_geo, P.b_lo, P.nbt, x, L, n, n_alt, s_red, s1, s2, n0);
       const double t = 1.0 / (1.0 - x);
       g1 = s1 - nhet * t;
       g2 = -s2 - nhet * t * t;

@@ -1,0 +1,33 @@
+"""Cuts the numbers DESIGN.md quotes out of an .ncu-rep (read here with `ncu -i ... --page raw --csv`): duration, DRAM bytes,
+throughputs, occupancy limits, issue utilisation, top stall reasons, tensor / FP64 / ALU pipe use. Usage: ncu_summary.py <rep> > out.txt"""
+import csv, subprocess, sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "launch__waves_per_multiprocessor",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "lts__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    head, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(head, r))
+        print("kernel:", d.get("Kernel Name", "?"))
+        for k in WANT:
+            if k in d:
+                print(f"  {k} = {d[k]} {units[head.index(k)]}")
+        stalls = sorted(((float(v.replace(',', '')), k) for k, v in d.items() if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and v),
+                        reverse=True)[:6]
+        for v, k in stalls:
+            print(f"  stall {k.split('issue_stalled_')[1].split('_per_issue')[0]} = {v:.2f} per issue")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
