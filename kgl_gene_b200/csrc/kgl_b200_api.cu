@@ -51,6 +51,9 @@ struct DevBuf {
     if (e == cudaSuccess) cap = n;
     return e;
   }
+  // For buffers whose size follows the selection window (the moment tables): a quarter of head room, so that a run of windows of
+  // similar sizes reallocates once, not every time a window is a little larger than all before it.
+  cudaError_t ensure_roomy(size_t n) { return n <= cap ? cudaSuccess : ensure(n + n / 4); }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
@@ -59,6 +62,7 @@ struct DevBuf {
 struct kgl_b200_ctx {
   int device = 0;
   int sm_count = 148;
+  uint64_t total_memory = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
@@ -851,7 +855,7 @@ uint32_t moment_tile_ranges(const kgl_b200_ctx* c, uint32_t tile_genomes, uint32
 int moments_build_lists(kgl_b200_ctx* c) {
   cudaStream_t st = c->stream;
   const uint64_t N = c->N, npad = c->Npad;
-  KGL_CUDA(c, c->d_mom_unit_offs.ensure((size_t)c->mom_n_units * npad));
+  KGL_CUDA(c, c->d_mom_unit_offs.ensure_roomy((size_t)c->mom_n_units * npad));
   k_mom_unit_scan<<<blocks_for(N, 32), 256, 0, st>>>(c->d_mom_unit_cnt.p, c->d_mom_units.p, c->d_mom_unit_range.p, c->d_superpop.p, N, npad,
                                                      c->d_mom_unit_offs.p, c->d_mom_totals.p);
   KGL_LAUNCH_CHECK(c);
@@ -860,7 +864,7 @@ int moments_build_lists(kgl_b200_ctx* c) {
   uint64_t list_len = 0;
   KGL_CUDA(c, cudaMemcpyAsync(&list_len, c->d_mom_base.p + N, 8, cudaMemcpyDeviceToHost, st));
   KGL_CUDA(c, cudaStreamSynchronize(st));
-  KGL_CUDA(c, c->d_mom_list.ensure(std::max<uint64_t>(1, list_len)));
+  KGL_CUDA(c, c->d_mom_list.ensure_roomy(std::max<uint64_t>(1, list_len)));
   MomFillParams F{};
   F.packed = reinterpret_cast<const uint4*>(c->d_packed.p); F.units = c->units; F.rr = c->d_mom_rr.p;
   F.superpop = c->d_superpop.p; F.n_genomes = N; F.n_genomes_padded = npad; F.rows = c->d_mom_rows2.p; F.unit_table = c->d_mom_units.p;
@@ -890,13 +894,13 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   if (W == 0 || n_items >= 0xFFFFFFFFull || !c->prep[c->par].selw.p) return KGL_B200_OK;
   cudaStream_t st = c->stream;
   const int unph = c->unphased ? 1 : 0;
-  KGL_CUDA(c, c->d_mom_keys.ensure(n_items)); KGL_CUDA(c, c->d_mom_keys2.ensure(n_items));
-  KGL_CUDA(c, c->d_mom_rows.ensure(n_items)); KGL_CUDA(c, c->d_mom_rows2.ensure(n_items));
-  KGL_CUDA(c, c->d_mom_stats.ensure(4)); KGL_CUDA(c, c->d_mom_pop_begin.ensure(kMaxPop + 2));
-  KGL_CUDA(c, c->d_mom_pop_cmin.ensure(kMaxPop));
-  KGL_CUDA(c, c->d_mom_bounds.ensure(kMomMaxUnits)); KGL_CUDA(c, c->d_mom_bounds2.ensure(kMomMaxUnits));
-  KGL_CUDA(c, c->d_mom_units.ensure(kMomMaxUnits)); KGL_CUDA(c, c->d_mom_unit_range.ensure(kMaxPop));
-  KGL_CUDA(c, c->d_mom_unit_out.ensure(4));
+  KGL_CUDA(c, c->d_mom_keys.ensure_roomy(n_items)); KGL_CUDA(c, c->d_mom_keys2.ensure_roomy(n_items));
+  KGL_CUDA(c, c->d_mom_rows.ensure_roomy(n_items)); KGL_CUDA(c, c->d_mom_rows2.ensure_roomy(n_items));
+  KGL_CUDA(c, c->d_mom_stats.ensure_roomy(4)); KGL_CUDA(c, c->d_mom_pop_begin.ensure_roomy(kMaxPop + 2));
+  KGL_CUDA(c, c->d_mom_pop_cmin.ensure_roomy(kMaxPop));
+  KGL_CUDA(c, c->d_mom_bounds.ensure_roomy(kMomMaxUnits)); KGL_CUDA(c, c->d_mom_bounds2.ensure_roomy(kMomMaxUnits));
+  KGL_CUDA(c, c->d_mom_units.ensure_roomy(kMomMaxUnits)); KGL_CUDA(c, c->d_mom_unit_range.ensure_roomy(kMaxPop));
+  KGL_CUDA(c, c->d_mom_unit_out.ensure_roomy(4));
   k_mom_stats_init<<<1, 1, 0, st>>>(c->d_mom_stats.p);
   KGL_CUDA(c, cudaMemsetAsync(c->d_mom_pop_cmin.p, 0xFF, kMaxPop * 8, st));
   KGL_CUDA(c, cudaMemsetAsync(c->d_mom_bounds.p, 0xFF, kMomMaxUnits * 4, st));
@@ -908,7 +912,7 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   KGL_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, c->d_mom_keys.p, c->d_mom_keys2.p, c->d_mom_rows.p, c->d_mom_rows2.p,
                                               n_items, 0, 35, st));
   KGL_CUDA(c, cub::DeviceRadixSort::SortKeys(nullptr, temp2, c->d_mom_bounds.p, c->d_mom_bounds2.p, (uint64_t)kMomMaxUnits, 0, 32, st));
-  KGL_CUDA(c, c->d_mom_tmp.ensure(std::max(temp_bytes, temp2)));
+  KGL_CUDA(c, c->d_mom_tmp.ensure_roomy(std::max(temp_bytes, temp2)));
   KGL_CUDA(c, cub::DeviceRadixSort::SortPairs(c->d_mom_tmp.p, temp_bytes, c->d_mom_keys.p, c->d_mom_keys2.p, c->d_mom_rows.p, c->d_mom_rows2.p,
                                               n_items, 0, 35, st));
   k_mom_ranges<<<1, 32, 0, st>>>(c->d_mom_keys2.p, n_items, (int)c->n_pop, c->d_mom_pop_begin.p);
@@ -937,17 +941,16 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   const double scale = std::ldexp(1.0, std::min(sbits, 46));          // the tensor-core payload has six 8-bit limbs for U + 2^s
   const uint32_t n_units = unit_out[0], n_btiles = unit_out[1];
   static const bool mma_off = std::getenv("KGL_B200_MOMENTS_NO_MMA") != nullptr;
-  // scratch of the tensor-core builder (payload tiles, per-unit counts and offsets): at most a third of what is free now
-  size_t free_bytes = 0, total_bytes = 0;
-  KGL_CUDA(c, cudaMemGetInfo(&free_bytes, &total_bytes));
-  const uint64_t scratch_limit = std::max<uint64_t>(4ull << 30, free_bytes / 3);
+  // scratch of the tensor-core builder (payload tiles, per-unit counts and offsets)
+  // (a quarter of the device's memory, from the properties read at kgl_b200_create: cudaMemGetInfo stalls the host for milliseconds)
+  const uint64_t scratch_limit = std::max<uint64_t>(4ull << 30, c->total_memory / 4);
   const bool use_mma = !mma_off && !c->opt.moments_on_cuda_cores && unit_out[2] <= kMomMaxUnits && n_units > 0 &&
                        (uint64_t)n_btiles * 2 * kMmaBTile + (want_lists ? (uint64_t)n_units * npad * 8 : 0) <= scratch_limit;
-  KGL_CUDA(c, c->d_mom_pm.ensure((size_t)c->n_pop * nbt * kMomJ));
-  KGL_CUDA(c, c->d_mom_mi.ensure((size_t)npad * nbt * kMomJ));
-  KGL_CUDA(c, c->d_mom_totals.ensure((size_t)npad * 2));
-  KGL_CUDA(c, c->d_mom_limits.ensure((size_t)npad * 3));
-  KGL_CUDA(c, c->d_mom_base.ensure(N + 1));
+  KGL_CUDA(c, c->d_mom_pm.ensure_roomy((size_t)c->n_pop * nbt * kMomJ));
+  KGL_CUDA(c, c->d_mom_mi.ensure_roomy((size_t)npad * nbt * kMomJ));
+  KGL_CUDA(c, c->d_mom_totals.ensure_roomy((size_t)npad * 2));
+  KGL_CUDA(c, c->d_mom_limits.ensure_roomy((size_t)npad * 3));
+  KGL_CUDA(c, c->d_mom_base.ensure_roomy(N + 1));
   KGL_CUDA(c, cudaMemsetAsync(c->d_mom_pm.p, 0, (size_t)c->n_pop * nbt * kMomJ * 8, st));
   KGL_CUDA(c, cudaMemsetAsync(c->d_mom_mi.p, 0, (size_t)npad * nbt * kMomJ * 8, st));
   if (!use_mma) {              // the tensor-core path sums the population's moments while it writes the payload tiles (k_mom_btiles)
@@ -957,13 +960,13 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
   }
   uint64_t list_len = 0;
   if (use_mma) {
-    KGL_CUDA(c, c->d_mom_btiles.ensure((size_t)std::max<uint32_t>(1, n_btiles) * 2 * kMmaBTile));
-    KGL_CUDA(c, c->d_mom_rr.ensure(n_items));
+    KGL_CUDA(c, c->d_mom_btiles.ensure_roomy((size_t)std::max<uint32_t>(1, n_btiles) * 2 * kMmaBTile));
+    KGL_CUDA(c, c->d_mom_rr.ensure_roomy(n_items));
     k_mom_btiles<<<n_units, kMmaK, 0, st>>>(c->d_mom_units.p, c->d_mom_rows2.p, c->d_af.p, L, unph, scale, c->d_mom_btiles.p, c->d_mom_rr.p, b_lo, nbt, c->d_mom_pm.p);
     KGL_LAUNCH_CHECK(c);
-    if (want_lists) { KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad)); KGL_CUDA(c, c->d_mom_unit_offs.ensure((size_t)n_units * npad)); }
+    if (want_lists) { KGL_CUDA(c, c->d_mom_unit_cnt.ensure_roomy((size_t)n_units * npad)); KGL_CUDA(c, c->d_mom_unit_offs.ensure_roomy((size_t)n_units * npad)); }
     const bool keep_counts = want_lists || (uint64_t)n_units * npad * 8 <= (2ull << 30);     // lets a later root search add its lists to these tables
-    if (keep_counts) KGL_CUDA(c, c->d_mom_unit_cnt.ensure((size_t)n_units * npad));
+    if (keep_counts) KGL_CUDA(c, c->d_mom_unit_cnt.ensure_roomy((size_t)n_units * npad));
     MomMmaParams M{};
     const uint32_t mma_tiles = moment_tile_ranges(c, kMmaM, M.tile_lo, M.tile_hi);
     M.packed = reinterpret_cast<const uint4*>(c->d_packed.p); M.units = c->units;
@@ -977,8 +980,8 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
     c->mom_used_mma = true;
   } else {
     const uint32_t chunks_per_pop = (longest + kMomChunk - 1) / kMomChunk;
-    KGL_CUDA(c, c->d_mom_cnt.ensure((size_t)chunks_per_pop * npad));
-    if (want_lists) KGL_CUDA(c, c->d_mom_offs.ensure((size_t)chunks_per_pop * npad));
+    KGL_CUDA(c, c->d_mom_cnt.ensure_roomy((size_t)chunks_per_pop * npad));
+    if (want_lists) KGL_CUDA(c, c->d_mom_offs.ensure_roomy((size_t)chunks_per_pop * npad));
     MomParams P{};
     P.packed = reinterpret_cast<const uint4*>(c->d_packed.p); P.units = c->units;
     P.af = c->d_af.p; P.n_loci = L; P.n_pop = (int)c->n_pop; P.unphased = unph;
@@ -997,7 +1000,7 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
       KGL_LAUNCH_CHECK(c);
       KGL_CUDA(c, cudaMemcpyAsync(&list_len, c->d_mom_base.p + N, 8, cudaMemcpyDeviceToHost, st));
       KGL_CUDA(c, cudaStreamSynchronize(st));
-      KGL_CUDA(c, c->d_mom_list.ensure(std::max<uint64_t>(1, list_len)));
+      KGL_CUDA(c, c->d_mom_list.ensure_roomy(std::max<uint64_t>(1, list_len)));
       P.base = c->d_mom_base.p; P.offs = c->d_mom_offs.p; P.list = c->d_mom_list.p;
       k_mom_fill<<<grid, kMomTile, 0, st>>>(P, c->d_mom_totals.p);
       KGL_LAUNCH_CHECK(c);
@@ -1218,6 +1221,7 @@ int kgl_b200_create(int device, kgl_b200_ctx** out) {
   auto* c = new kgl_b200_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  c->total_memory = prop.totalGlobalMem;
   // the context stream carries the streaming kernel: highest priority, so that its CTAs are placed before the blocks of the
   // side streams (preparation, tail) when both are ready
   int pr_least = 0, pr_greatest = 0;

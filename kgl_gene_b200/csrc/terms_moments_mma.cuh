@@ -421,7 +421,6 @@ k_mom_unit_fill(const MomFillParams P) {
   const bool mine = g < P.n_genomes && P.superpop[g] == U.pop && P.cnt[(uint64_t)blockIdx.y * P.n_genomes_padded + g] != 0u;
   if (!__syncthreads_or(mine)) return;                      // no genome of the tile has a rare homozygous cell in this unit
   const uint32_t mine_mask = __ballot_sync(kFull, mine);
-  const uint32_t bit = mine ? (1u << lane) : 0u;
   uint64_t pos = 0;
   if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)blockIdx.y * P.n_genomes_padded + g];
   const int tj = threadIdx.x >> 1, th = threadIdx.x & 1;
@@ -455,14 +454,18 @@ k_mom_unit_fill(const MomFillParams P) {
     fetch(s + kMomStep, nxt, nxt_r);
     __syncthreads();
     const int n_here = (int)min((uint32_t)kMomStep, U.end - s);
+    // 32 loci at a time: lane = locus holds the mask of its 32 genomes; after the transpose lane = genome holds the loci at which
+    // it has a cell, in order -- every lane then walks only its own cells
 #pragma unroll
     for (int k = 0; k < kMomStep / 32; ++k) {
       const int jj = k * 32 + lane;
-      uint32_t aw = __ballot_sync(kFull, jj < n_here && (s_rare[jj][warp] & mine_mask) != 0);
-      while (aw) {
-        const int j = k * 32 + __ffs(aw) - 1;
-        aw &= aw - 1;
-        if (s_rare[j][warp] & bit) P.list[pos++] = s_r[j];
+      const uint32_t w = jj < n_here ? (s_rare[jj][warp] & mine_mask) : 0u;
+      if (!__any_sync(kFull, w != 0u)) continue;
+      uint32_t cells = warp_transpose32(w, lane);
+      while (cells) {
+        const int j = __ffs(cells) - 1;
+        cells &= cells - 1;
+        P.list[pos++] = s_r[k * 32 + j];
       }
     }
   }
