@@ -188,7 +188,6 @@ struct kgl_b200_ctx {
   DevBuf<uint32_t> d_mom_rows, d_mom_rows2, d_mom_pop_begin, d_mom_cnt, d_mom_totals;
   DevBuf<int> d_mom_stats;
   DevBuf<long long> d_mom_pm, d_mom_mi;
-  DevBuf<double2> d_mom_lim;
   DevBuf<uint2> d_mom_offs;
   DevBuf<uint32_t> d_mom_bounds, d_mom_bounds2, d_mom_unit_out, d_mom_unit_cnt, d_mom_unit_offs;
   DevBuf<MomUnit> d_mom_units;
@@ -988,12 +987,12 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
     P.superpop = c->d_superpop.p; P.n_genomes = N; P.n_genomes_padded = npad;
     P.rows = c->d_mom_rows2.p; P.pop_begin = c->d_mom_pop_begin.p; P.chunks_per_pop = chunks_per_pop;
     P.b_lo = b_lo; P.nbt = nbt; P.scale = scale;
-    P.mi = c->d_mom_mi.p; P.cnt = c->d_mom_cnt.p; P.lim = nullptr;
+    P.mi = c->d_mom_mi.p; P.cnt = c->d_mom_cnt.p;
     const dim3 grid((unsigned)(c->n_pop * chunks_per_pop), (unsigned)((N + kMomTile - 1) / kMomTile));
-    k_mom_build<false><<<grid, kMomTile, 0, st>>>(P);          // the limits of the root search come from the lists (k_mom_list_limits)
+    k_mom_build<<<grid, kMomTile, 0, st>>>(P);          // the limits of the root search come from the lists (k_mom_list_limits)
     KGL_LAUNCH_CHECK(c);
-    k_mom_scan<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_cnt.p, nullptr, c->d_mom_pop_begin.p, c->d_superpop.p,
-                                                   N, npad, c->d_mom_totals.p, nullptr, want_lists ? c->d_mom_offs.p : nullptr);
+    k_mom_scan<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_cnt.p, c->d_mom_pop_begin.p, c->d_superpop.p, N, npad, c->d_mom_totals.p,
+                                                   want_lists ? c->d_mom_offs.p : nullptr);
     KGL_LAUNCH_CHECK(c);
     if (want_lists) {
       k_mom_base<<<1, 1024, 0, st>>>(c->d_mom_totals.p, N, c->d_mom_base.p);

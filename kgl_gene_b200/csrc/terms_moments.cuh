@@ -13,16 +13,17 @@
 //
 // Building the moments is dense-minus-sparse, as the rest of the path: at every locus one homozygous class is COMMON (the
 // allele with frequency >= 1/2) and one RARE. The population's moments over all selected loci (k_mom_dense) stand for "every
-// genome is common-homozygous everywhere"; one pass over the matrix (k_mom_build) subtracts, per genome, the cells that are not,
-// and adds the rare homozygous cells to their own bins. Loci are walked in the order of the population's frequency (a radix
+// genome is common-homozygous everywhere"; one pass over the matrix subtracts, per genome, the cells that are not, and adds the
+// rare homozygous cells to their own bins -- on the tensor cores (k_mom_mma, terms_moments_mma.cuh) or, as the fallback and the
+// cross-check, on the CUDA cores (k_mom_build below: lane = genome, predicated 64-bit adds). Loci are walked in the order of the population's frequency (a radix
 // sort of the float bits), so both bins change monotonically and the accumulators live in registers between bin changes. All
 // moments are 64-bit FIXED-POINT integers (normalised powers in [-1,1] x 2^s), added with integer atomics: dense minus sparse
 // cancels exactly, a bin the genome has no cell in is exactly zero, and the result does not depend on the schedule.
 //
 // Left of zero the poles of the rare cells come close (the feasible region of the likelihood ends at f = -r of the genome's
 // rarest homozygous allele), so for f < 0 the bins of the octaves below 4|f| are not used: the rare cells themselves are kept as
-// a per-genome list of r (k_mom_fill; ascending hom-alt part, descending hom-ref part) and the few below the threshold are
-// evaluated exactly. The domain of the tables is f >= kMomValidMin; a genome left of it takes the exact cell-by-cell kernel
+// a per-genome list of r (k_mom_unit_fill / k_mom_fill; ascending hom-alt part, descending hom-ref part) and the few below the
+// threshold are evaluated exactly. The domain of the tables is f >= kMomValidMin; a genome left of it takes the exact cell-by-cell kernel
 // (k_genome_terms), as do genomes within rounding of their feasible end (k_newton_reduce, unchanged).
 #pragma once
 #include "common.cuh"
@@ -58,7 +59,6 @@ __device__ __forceinline__ void mom_geometry(int b, double& rc, double& w) {
 struct MomClass {
   double r_common, r_rare;     // a/(1-a); +inf when a == 1 (t = 0: the cell only counts in n_hom)
   int common_code, rare_code;  // genotype code of the class (0 hom-ref, 2 hom-alt); -1: its cells are not terms
-  double e_rare;               // left end of the feasible region of a rare homozygous cell (calc.cpp:108-110)
   double c_het;                // 2 p q of a heterozygous cell (calc.cpp:117)
 };
 __device__ __forceinline__ MomClass mom_classify(float af, bool unphased) {
@@ -75,9 +75,6 @@ __device__ __forceinline__ MomClass mom_classify(float af, bool unphased) {
   m.rare_code = ref_common ? (alt_in ? 2 : -1) : (ref_in ? 0 : -1);
   m.r_common = ref_common ? r0 : r2;
   m.r_rare = ref_common ? r2 : r0;
-  const double a = ref_common ? p : q, ua = ref_common ? up : uq;
-  const double d = __dmul_rn(a, ua);
-  m.e_rare = d > 0.0 ? __ddiv_rn(__dsub_rn(kSmallProb, __dmul_rn(a, a)), d) : (a == 0.0 ? kHuge : -kHuge);
   m.c_het = __dmul_rn(__dmul_rn(2.0, p), q);
   return m;
 }
@@ -201,7 +198,6 @@ struct MomParams {
   int b_lo, nbt; double scale;
   long long* mi;                                     // [n_genomes_padded][nbt][kMomJ] (zeroed): - not-common cells + rare cells
   uint32_t* cnt;                                     // [chunks_per_pop][n_genomes_padded]: rare hom-alt cells | rare hom-ref cells << 16
-  double2* lim;                                      // [chunks_per_pop][n_genomes_padded]: {max e_rare, min 2pq over heterozygous cells}
   // k_mom_fill
   const uint64_t* base; const uint2* offs; double* list;   // list[base[g] + ...] = r of the genome's rare homozygous cells
 };
@@ -232,15 +228,12 @@ __device__ __forceinline__ MomMasks mom_masks(uint32_t lo, uint32_t hi, int comm
   return m;
 }
 
-template <bool LIMITS>
 __global__ void __launch_bounds__(kMomTile)
 k_mom_build(const MomParams P) {
   constexpr int kWarps = kMomTile / 32;
   __shared__ int2 s_hdr[kMomStep];                                  // {common bin, rare bin} (-1: the class has no terms)
   __shared__ uint2 s_m[kMomStep][kWarps];                           // per locus and warp: {not-common mask, rare mask}
-  __shared__ uint32_t s_het[LIMITS ? kMomStep : 1][kWarps];
   __shared__ __align__(16) long long s_cu[kMomStep][kMomJ], s_ru[kMomStep][kMomJ];   // {-1, -u1..-u5} and {+1, +u1..+u5}
-  __shared__ double2 s_lim[LIMITS ? kMomStep : 1];                  // {e_rare, 2pq}
   const int pop = blockIdx.x / P.chunks_per_pop, chunk = blockIdx.x % P.chunks_per_pop;
   const uint32_t begin = P.pop_begin[pop] + chunk * kMomChunk, end = min(P.pop_begin[pop + 1], begin + kMomChunk);
   if (begin >= end) return;
@@ -254,7 +247,6 @@ k_mom_build(const MomParams P) {
 #pragma unroll
   for (int j = 0; j < kMomJ; ++j) { ca[j] = 0; ra[j] = 0; }
   int cur_cb = -1, cur_rb = -1;
-  double fmin_ = -kHuge, cmin = kHuge;
   uint32_t n_alt = 0, n_ref = 0;
   long long* mi_g = P.mi + g * (uint64_t)P.nbt * kMomJ;
   // table phase: two threads per locus, each with two of the tile's four units (four warp slices)
@@ -293,7 +285,6 @@ k_mom_build(const MomParams P) {
             for (int j = 0; j < kMomJ - 1; ++j) s_ru[tj][j + 1] = u[j];
           }
         }
-        if (LIMITS && th == 0) s_lim[tj] = make_double2(m.e_rare, m.c_het);
         const uint64_t unit0 = (uint64_t)blockIdx.y * (kMomTile / 64) + 2 * th;
         const uint4* row = P.packed + (uint64_t)l * P.units + unit0;
 #pragma unroll
@@ -308,7 +299,6 @@ k_mom_build(const MomParams P) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         s_m[tj][4 * th + k] = make_uint2(mk[k].nc, mk[k].rare);
-        if (LIMITS) s_het[tj][4 * th + k] = mk[k].het;
       }
     }
     __syncthreads();
@@ -320,7 +310,6 @@ k_mom_build(const MomParams P) {
       const int j = k * 32 + lane;
       const uint2 m = s_m[j][warp];
       uint32_t act = m.x | m.y;
-      if (LIMITS) act |= s_het[j][warp];
       actw[k] = __ballot_sync(kFull, j < n_here && (act & mine_mask) != 0);
     }
 #pragma unroll
@@ -346,10 +335,8 @@ k_mom_build(const MomParams P) {
             const longlong2 a = u[0], b = u[1], c = u[2];
             ra[0] += a.x; ra[1] += a.y; ra[2] += b.x; ra[3] += b.y; ra[4] += c.x; ra[5] += c.y;
             if (hdr.y >> 20) ++n_ref; else ++n_alt;
-            if (LIMITS) fmin_ = fmax(fmin_, s_lim[j].x);
           }
         }
-        if (LIMITS) { if (s_het[j][warp] & bit) cmin = fmin(cmin, s_lim[j].y); }
       }
     }
   }
@@ -357,29 +344,25 @@ k_mom_build(const MomParams P) {
   mom_flush(ca, mi_g, cur_cb);
   mom_flush(ra, mi_g, cur_rb < 0 ? -1 : (cur_rb & 0xFFFFF));
   P.cnt[(uint64_t)chunk * P.n_genomes_padded + g] = n_alt | (n_ref << 16);
-  if (LIMITS) P.lim[(uint64_t)chunk * P.n_genomes_padded + g] = make_double2(fmin_, cmin);
 }
 
 // Per genome: prefix of the chunk counts (offs: cells of the chunks before, hom-alt and hom-ref part; the hom-ref part of the list
-// follows the whole hom-alt part), totals = {rare cells, rare hom-alt cells}, limits = {fmin, cmin}.
+// follows the whole hom-alt part), totals = {rare cells, rare hom-alt cells}.
 __global__ void __launch_bounds__(256)
-k_mom_scan(const uint32_t* __restrict__ cnt, const double2* __restrict__ lim, const uint32_t* __restrict__ pop_begin,
-           const uint8_t* __restrict__ superpop, uint64_t n_genomes, uint64_t n_genomes_padded, uint32_t* __restrict__ totals /* [Npad][2] */,
-           double* __restrict__ limits /* [N][3], may be null */, uint2* __restrict__ offs /* [chunks][Npad] {hom-alt, hom-ref} before the chunk; may be null */) {
+k_mom_scan(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pop_begin, const uint8_t* __restrict__ superpop,
+           uint64_t n_genomes, uint64_t n_genomes_padded, uint32_t* __restrict__ totals /* [Npad][2] */,
+           uint2* __restrict__ offs /* [chunks][Npad] {hom-alt, hom-ref} before the chunk; may be null */) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_genomes) return;
   const int pop = superpop[g];
   const uint32_t n = pop_begin[pop + 1] - pop_begin[pop], n_chunks = (n + kMomChunk - 1) / kMomChunk;
   uint32_t n_alt = 0, n_ref = 0;
-  double fmin_ = -kHuge, cmin = kHuge;
   for (uint32_t ch = 0; ch < n_chunks; ++ch) {
     const uint32_t c = cnt[(uint64_t)ch * n_genomes_padded + g];
     if (offs) offs[(uint64_t)ch * n_genomes_padded + g] = make_uint2(n_alt, n_ref);
     n_alt += c & 0xFFFFu; n_ref += c >> 16;
-    if (lim) { const double2 v = lim[(uint64_t)ch * n_genomes_padded + g]; fmin_ = fmax(fmin_, v.x); cmin = fmin(cmin, v.y); }
   }
   totals[g * 2 + 0] = n_alt + n_ref; totals[g * 2 + 1] = n_alt;
-  if (limits) { limits[g * 3 + 0] = fmin_; limits[g * 3 + 1] = cmin; }
 }
 
 // base[g] = sum of the totals of the genomes before g; base[n_genomes] = the length of the list (one block).
