@@ -640,7 +640,7 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
         t = h_tiles.numpy().view(np.uint32)
         assert np.array_equal(t[..., :3].sum(-1), t[..., 3]), "IBS0 + IBS1 + IBS2 != valid"
     # tensor-core variant (K5): the dosage Gram matrix of the same population, int8 x int8 -> int32 on tcgen05. At N > 1 the
-    # 128 x 256 tiles are dealt to the ranks and the int32 matrix is assembled with one NCCL all-reduce (26 MB at 2,504 genomes).
+    # 256 x 256 tiles are dealt to the ranks and the int32 matrix is assembled with one NCCL all-reduce (26 MB at 2,504 genomes).
     from kgl_gene_b200.shards import allreduce_gram
 
     def gram_step():
@@ -654,16 +654,16 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
     if rank == 0:
         gk_ms = ctx.last_gram_kernel_ms()
         ld = (n + 255) // 256 * 256
-        n_tiles_all = sum(1 for ti in range(ld // 128) for tj in range(ti // 2, ld // 256))
+        n_tiles_all = sum(1 for ti in range(ld // 256) for tj in range(ti, ld // 256))
         n_tiles = len(range(rank, n_tiles_all, world))
         k_stages = (kl + 127) // 128
-        ops = 2.0 * n_tiles * 128 * 256 * k_stages * 128
+        ops = 2.0 * n_tiles * 256 * 256 * k_stages * 128
         # int8 tensor peak: MEASURED on this pool's B200s with the kernel's own MMA issue loop and epilogue, operand staging switched
         # off (tools/grambench --skip 2, profiles/r01_grambench_skip_modes.log: 3512 / 3567 TOP/s at 2504 x 1.1 M / 8192 x 400 k)
         peak_tops = 3567.3
         grm = {"metric": "kinship sample-pair-loci/s (int8 Gram matrix on tcgen05)", "value": pair_loci / (g_ms * 1e-3), "unit": "sample-pair-loci/s",
                "ms_per_step": g_ms, "n_gpus": world, "scaling": "strong",
-               "kernel": "k_gram_i8 (tcgen05.mma kind::i8, TMEM accumulators, 128x256 tiles, in-kernel 2-bit -> int8 expansion)",
+               "kernel": "k_gram_i8 (tcgen05.mma kind::i8, TMEM accumulators, 256x256 tiles = two M128 MMAs per B operand, in-kernel 2-bit -> int8 expansion)",
                "roofline": {"bound": "tensor", "achieved": ops / (gk_ms * 1e-3) / 1e12, "peak": peak_tops, "unit": "int8 TOP/s",
                             "frac": ops / (gk_ms * 1e-3) / 1e12 / peak_tops,
                             "peak_source": "measured: tcgen05.mma kind::i8 128x256x32 issued back to back + epilogue, no operand staging (profiles/r01_grambench_skip_modes.log)",

@@ -25,12 +25,13 @@
 
 namespace kgl {
 
-constexpr int kGramM = 128, kGramN = 256, kGramK = 128;         // tile; K-stage = 128 loci = 128 B per operand row
-constexpr int kGramStages = 4;
-constexpr int kGramExpWarps = 12;                                // expander warps: one thread per operand row of a stage (128 + 256)
+constexpr int kGramM = 256, kGramN = 256, kGramK = 128;         // tile (two M = 128 MMAs share the B operand); K-stage = 128 loci = 128 B per operand row
+constexpr int kGramMmaM = 128;                                   // rows per tcgen05.mma (cta_group::1)
+constexpr int kGramStages = 3;
+constexpr int kGramExpWarps = 16;                                // expander warps: one thread per operand row of a stage (256 + 256)
 constexpr int kGramThreads = (5 + kGramExpWarps) * 32;
 constexpr uint32_t kGramABytes = kGramM * kGramK, kGramBBytes = kGramN * kGramK;
-constexpr uint32_t kGramStageBytes = kGramABytes + kGramBBytes;  // 48 KB
+constexpr uint32_t kGramStageBytes = kGramABytes + kGramBBytes;  // 64 KB
 constexpr size_t kGramSmem = (size_t)kGramStages * kGramStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 
 // Code matrix layout ("row-block major"): uint32 [ld / 128][k_stages][128 rows][8 words]; a word holds 16 loci, 2 bits each,
@@ -61,7 +62,7 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // UMMA::InstrDescriptor for kind::i8: c_format S32 (2) at [4,6), a/b format unsigned 8-bit (0), K-major both, N >> 3 at [17,23), M >> 4 at [24,29).
-constexpr uint32_t kGramIdesc = (2u << 4) | ((uint32_t)(kGramN >> 3) << 17) | ((uint32_t)(kGramM >> 4) << 24);
+constexpr uint32_t kGramIdesc = (2u << 4) | ((uint32_t)(kGramN >> 3) << 17) | ((uint32_t)(kGramMmaM >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -95,7 +96,7 @@ k_gram_i8(const GramParams P) {
 
   if (tid == 0) {
     for (int s = 0; s < kGramStages; ++s) { mbar_init(bar_full + 8 * s, kGramExpWarps * 32); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+    mbar_init(bar_tfull, 1); mbar_init(bar_tempty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -131,7 +132,7 @@ k_gram_i8(const GramParams P) {
       const uint32_t chunk = c.u / P.n_tiles, tile = c.u - chunk * P.n_tiles;
       const uint2 tc = P.tiles[tile];
       const uint64_t ks = (uint64_t)chunk * P.stages_per_chunk + c.ks;
-      const uint64_t block = is_b ? (uint64_t)2 * tc.y + (r >> 7) : (uint64_t)tc.x;
+      const uint64_t block = (uint64_t)2 * (is_b ? tc.y : tc.x) + (r >> 7);
       const uint4* src = reinterpret_cast<const uint4*>(P.codes + (block * P.k_stages + ks) * 1024 + (uint64_t)(r & 127) * 8);
       dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
     };
@@ -163,20 +164,23 @@ k_gram_i8(const GramParams P) {
     for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
       const uint32_t chunk = u / P.n_tiles;
       const uint32_t ns = min(P.stages_per_chunk, P.k_stages - chunk * P.stages_per_chunk);
-      const uint32_t a = ui & 1, aph = (ui >> 1) & 1;
-      if (ui >= 2) mbar_wait(bar_tempty + 8 * a, aph ^ 1);
+      // one accumulator set (2 x 256 columns = all of TMEM): the MMAs of a unit start when the epilogue of the unit before has
+      // drained it -- a unit is thousands of stages long, the epilogue a few microseconds
+      if (ui >= 1) mbar_wait(bar_tempty, (ui - 1) & 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + a * kGramN;
       for (uint32_t k = 0; k < ns; ++k) {
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = base + s * kGramStageBytes, sb = sa + kGramABytes;
 #pragma unroll
-          for (uint32_t kk = 0; kk < kGramK / 32; ++kk)
-            tc_mma_i8(tmem_d, tc_smem_desc(sa + kk * 32), tc_smem_desc(sb + kk * 32), (k | kk) ? 1u : 0u);
+          for (uint32_t kk = 0; kk < kGramK / 32; ++kk) {
+            const uint64_t bdesc = tc_smem_desc(sb + kk * 32);
+            tc_mma_i8(tmem_base, tc_smem_desc(sa + kk * 32), bdesc, (k | kk) ? 1u : 0u);                                        // rows 0..127
+            tc_mma_i8(tmem_base + kGramN, tc_smem_desc(sa + kGramMmaM * kGramK + kk * 32), bdesc, (k | kk) ? 1u : 0u);          // rows 128..255
+          }
           tc_commit(bar_empty + 8 * s);
-          if (k + 1 == ns) tc_commit(bar_tfull + 8 * a);
+          if (k + 1 == ns) tc_commit(bar_tfull);
         }
         __syncwarp();
         if (++s == kGramStages) { s = 0; ph ^= 1; }
@@ -188,33 +192,35 @@ k_gram_i8(const GramParams P) {
     for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
       const uint32_t chunk = u / P.n_tiles, tile = u - chunk * P.n_tiles;
       const uint2 tc = P.tiles[tile];
-      const uint32_t a = ui & 1, aph = (ui >> 1) & 1;
-      mbar_wait(bar_tfull + 8 * a, aph);
+      mbar_wait(bar_tfull, ui & 1);
       tc_fence_after();
-      const uint64_t row = (uint64_t)tc.x * kGramM + warp * 32 + lane;
-      int32_t* orow = P.out + row * P.ld + (uint64_t)tc.y * kGramN;
-      const uint32_t taddr = tmem_base + a * kGramN + ((warp * 32) << 16);
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < (uint32_t)kGramN; c0 += 32) {
-        uint32_t v[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr + c0));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (P.n_chunks > 1) {
+      for (uint32_t half = 0; half < 2; ++half) {
+        const uint64_t row = (uint64_t)tc.x * kGramM + half * kGramMmaM + warp * 32 + lane;
+        int32_t* orow = P.out + row * P.ld + (uint64_t)tc.y * kGramN;
+        const uint32_t taddr = tmem_base + half * kGramN + ((warp * 32) << 16);
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < (uint32_t)kGramN; c0 += 32) {
+          uint32_t v[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (P.n_chunks > 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (v[j]) atomicAdd(orow + c0 + j, (int32_t)v[j]);
-        } else {
+            for (int j = 0; j < 32; ++j) if (v[j]) atomicAdd(orow + c0 + j, (int32_t)v[j]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(orow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * a);
+      mbar_arrive(bar_tempty);
     }
   }
 

@@ -6,11 +6,12 @@
 
 namespace kgl {
 
-// 128 x 256 tiles (ti, tj) that touch the upper triangle of an ld x ld matrix (ld a multiple of 256): 256 tj + 255 >= 128 ti.
+// 256 x 256 tiles (ti, tj), ti <= tj: the upper triangle of an ld x ld matrix (ld a multiple of 256).
 inline std::vector<uint2> gram_upper_tiles(uint64_t ld) {
+  static_assert(kGramM == kGramN, "square tiles");
   std::vector<uint2> t;
   for (uint32_t ti = 0; ti < ld / kGramM; ++ti)
-    for (uint32_t tj = ti / 2; tj < ld / kGramN; ++tj) t.push_back(make_uint2(ti, tj));
+    for (uint32_t tj = ti; tj < ld / kGramN; ++tj) t.push_back(make_uint2(ti, tj));
   return t;
 }
 

@@ -40,8 +40,8 @@ g = torch.as_tensor(_RawCudaArray(ptr, count, "<i4"), device=dev).view(ld, ld)
 diag = torch.diagonal(g)[:n].cpu().numpy().astype(np.int64)
 _, gc = ctx.allele_count(want_loci=False, want_genomes=True)
 ok_diag = bool(np.array_equal(diag, (gc[:, 1] + 4 * gc[:, 2]).astype(np.int64)))
-n_tiles = sum(1 for ti in range(ld // 128) for tj in range(ti // 2, ld // 256))
-ops = 2.0 * n_tiles * 128 * 256 * ((l + 127) // 128) * 128
+n_tiles = sum(1 for ti in range(ld // 256) for tj in range(ti, ld // 256))
+ops = 2.0 * n_tiles * 256 * 256 * ((l + 127) // 128) * 128
 pair_loci = n * (n + 1) / 2 * l
 print(json.dumps({"workload": f"{n} genomes x {l} SNPs, dosage Gram matrix, 1 GPU", "ms": ms, "kernel_ms": k_ms,
                   "pair_loci_per_s": pair_loci / (ms * 1e-3), "int8_tops": ops / (k_ms * 1e-3) / 1e12, "diag_matches_allele_counts": ok_diag}))
