@@ -10,16 +10,18 @@
 // upload by k_codes16 from the sample-major planes); expander warps turn every 32-bit word into 16 int8 with the byte
 // permuter (expand16: 9 integer ops per 16 bytes) and write them straight into the 128-byte-swizzled K-major layout
 // tcgen05 reads. HBM/L2 traffic is therefore 1/4 byte per genotype, and the expansion costs 0.56 integer ops per operand
-// byte = 0.0066 per MAC at a 128 x 256 tile.
+// byte = 0.0044 per MAC at a 256 x 256 tile.
 //
-// CTA = 17 warps: 0-3 epilogue (TMEM lane quadrants 0-3), 4 MMA issuer (one elected thread) + TMEM allocator, 5-16 expanders
-// (384 threads = one per operand row of a stage).
-// Work unit = (128 x 256 output tile, chunk of K); per K-stage of 128 loci: A 128 x 128 B, B 256 x 128 B (48 KB), 4 stages.
+// CTA = 21 warps: 0-3 epilogue (TMEM lane quadrants 0-3), 4 MMA issuer (one elected thread) + TMEM allocator, 5-20 expanders
+// (512 threads = one per operand row of a stage).
+// Work unit = (256 x 256 output tile, chunk of K); per K-stage of 128 loci: A 256 x 128 B, B 256 x 128 B (64 KB), 3 stages. The
+// tile is two M = 128 MMAs on one B operand: a third less shared-memory traffic per MAC than 128 x 256 (the round-1 shape, bound
+// by exactly that traffic: 2.0 -> 3.0 PetaOP/s).
 //   expanders : wait empty[s] -> LDG (prefetched a stage ahead) -> expand -> st.shared (swizzled) -> fence.proxy.async -> arrive full[s]
-//   MMA       : wait full[s] -> 4 x tcgen05.mma (K = 32 each, descriptors advanced by 32 B inside the swizzle atom)
+//   MMA       : wait full[s] -> 2 x 4 x tcgen05.mma (K = 32 each, descriptors advanced by 32 B inside the swizzle atom)
 //               -> tcgen05.commit empty[s]; after the unit's last stage tcgen05.commit tmem_full[a]
 //   epilogue  : wait tmem_full[a] -> tcgen05.ld 32x32b.x32 -> st / red.add to S (int32 adds commute: split-K is exact)
-//               -> arrive tmem_empty[a]. Two 256-column accumulators: the MMA of unit u+1 overlaps the epilogue of unit u.
+//               -> arrive tmem_empty. The two 256-column accumulators of a tile fill TMEM: unit u+1 starts after unit u's epilogue.
 #pragma once
 #include "stream_common.cuh"
 
