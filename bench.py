@@ -592,7 +592,7 @@ POPC_PER_CLK_SM = 15.90
 def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, rb, seed, superpop, inbreeding):
     """BASELINE.json's second metric: pairwise IBS over all sample pairs; 64 x 64 tiles of the upper triangle dealt round-robin
     to the ranks, every rank holds the whole matrix, no collective in the data path."""
-    from kgl_gene_b200.shards import tiles_of_rank
+    from kgl_gene_b200.shards import block_tile_coords, tiles_of_rank
     from kgl_gene_b200.synth import make_loci
     kl = args.kinship_loci or l
     if world > 1 or kl != l:
@@ -602,14 +602,19 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
         ctx.set_genome_superpop(superpop)
         ctx.synth_genotypes(seed, n, kl, inbreeding, missing_rate=0.001, locus_base=0)
     side, n_up = ctx.ibs_tile_grid()
-    mine = tiles_of_rank(n_up, rank, world)
     SLAB = 8192
+    # N > 1: whole 256 x 256 blocks of tiles are dealt to the ranks (shards.block_tile_coords), the unit of the tensor-core form
+    coords = block_tile_coords(n, rank, world) if world > 1 else None
+    mine = tiles_of_rank(n_up, rank, world) if coords is None else int(coords.shape[0])
 
     def step():
         done = 0
         while done < mine:
             k = min(SLAB, mine - done)
-            ctx.enqueue_ibs_tiles(rank + done * world, world, k)
+            if coords is None:
+                ctx.enqueue_ibs_tiles(done, 1, k)
+            else:
+                ctx.enqueue_ibs_tile_list(coords[done:done + k])
             done += k
 
     step()                                   # builds the sample-major planes once (part of the upload, not of a pass)
@@ -632,7 +637,7 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
 
         def step_e2e():
             ctx.upload_genotypes_ptr(h_packed.data_ptr(), n, kl, rb)
-            ctx._check(ctx.lib.kgl_b200_run_ibs_tiles(ctx.h, C.c_uint64(rank), C.c_uint64(world), C.c_uint64(mine), C.c_void_p(h_tiles.data_ptr())), "run_ibs_tiles")
+            ctx._check(ctx.lib.kgl_b200_run_ibs_tiles(ctx.h, C.c_uint64(0), C.c_uint64(1), C.c_uint64(mine), C.c_void_p(h_tiles.data_ptr())), "run_ibs_tiles")
 
         e_ms = timed(step_e2e, 2, 1)
         e2e = {"value": pair_loci * 2 / (e_ms * 1e-3), "unit": "sample-pair-loci/s", "h2d_bytes_per_step": int(kl * rb),
@@ -670,29 +675,45 @@ def run_kinship(args, ctx, torch, dist, dev, stream, rank, world, timed, n, l, r
                             "kernel_ms": gk_ms, "twice_measured_bf16_tops": 2.0 * 1608.9}}
     if rank != 0:
         return None
-    # INT-pipe roofline of the tile kernel: 5 LOP3 + 1 POPC per executed pair-word (two-plane form: 3 for the two difference
-    # vectors, 2 for the carry-save step); the ALU pipe issues 62.45 LOP3 per clk per SM (measured), POPC 15.9.
     clk = 1.965e9
     sms = 148
-    exec_pair_loci = float(mine) * 4096 * kl                   # this rank's launches, incl. padding genomes and diagonal halves
     launches_per_step = (mine + SLAB - 1) // SLAB
     k_s = float(np.mean(k_ms)) * launches_per_step * 1e-3 if len(k_ms) else None   # the timer ring also holds the warm-up step
-    peak = LOP3_PER_CLK_SM * sms * clk / 5.0 * 32.0
-    achieved = exec_pair_loci / k_s if k_s else None
+    lop3_peak = LOP3_PER_CLK_SM * sms * clk / 5.0 * 32.0
+    if ctx.ibs_used_tensor_cores():
+        # dense part = three exact int8 Gram matrices (dosage, heterozygous, hom-alt indicators) over this rank's 256 x 256 blocks
+        bs = ((n + 63) // 64 + 3) // 4
+        n_blocks = len(range(rank, bs * (bs + 1) // 2, world))
+        ops = 3 * 2.0 * n_blocks * 256 * 256 * ((kl + 127) // 128) * 128
+        achieved = ops / k_s / 1e12 if k_s else None
+        roof = {"bound": "tensor", "kernel": "3 x k_gram_i8 (tcgen05.mma kind::i8; dosage, heterozygous and hom-alt indicator Gram matrices) + k_ibs_from_grams "
+                                             "(+ k_ibs_missing_fix, k_ibs_finalize outside the timed kernels)",
+                "achieved": achieved, "peak": 3567.3, "unit": "int8 TOP/s", "frac": (achieved / 3567.3) if achieved else None,
+                "peak_source": "measured: tcgen05.mma kind::i8 issued back to back + epilogue, no operand staging (profiles/r01_grambench_skip_modes.log)",
+                "kernel_ms": k_s * 1e3 if k_s else None,
+                "popcount_kernel_bound_pair_loci_per_s": lop3_peak,
+                "note": "IBS0 / IBS1 follow exactly from the three matrices and the per-genome class counts (ibs_gram.cuh): 1.5 N^2 L int8 MACs "
+                        "instead of 5 LOP3 + 1 POPC per pair-word; round 1's popcount tile kernel (8.5e13 pair-loci/s, 0.73 of its LOP3 bound on "
+                        "useful pair-loci) remains for populations whose matrices do not fit or whose code-3 cells are not indexed"}
+    else:
+        # INT-pipe roofline of the tile kernel: 5 LOP3 + 1 POPC per executed pair-word (two-plane form: 3 for the two difference
+        # vectors, 2 for the carry-save step); the ALU pipe issues 62.45 LOP3 per clk per SM (measured), POPC 15.9.
+        exec_pair_loci = float(mine) * 4096 * kl                   # this rank's launches, incl. padding genomes and diagonal halves
+        achieved = exec_pair_loci / k_s if k_s else None
+        roof = {"bound": "int-pipe (ALU/LOP3)", "kernel": "k_ibs_tiles<false,2> (+ k_ibs_missing_fix, k_ibs_finalize)",
+                "achieved": achieved, "peak": lop3_peak, "unit": "executed pair-loci/s",
+                "frac": (achieved / lop3_peak) if achieved else None,
+                # on USEFUL pair-loci (N (N + 1) / 2 pairs: no padding genomes, diagonal tiles counted once), whole step
+                "frac_useful": value / world / lop3_peak,
+                "peak_source": "62.45 LOP3/clk/SM (measured, kbench) x 148 SMs x 1.965 GHz / 5 LOP3 per 32 pair-loci",
+                "survey_8d_peak_popc_bound": POPC_PER_CLK_SM * sms * clk / 3.0 * 32.0,
+                "kernel_ms": k_s * 1e3 if k_s else None}
     return {"metric": KINSHIP_METRIC, "value": value, "unit": "sample-pair-loci/s", "ms_per_step": ms / steps, "steps": steps,
             "n_gpus": world, "scaling": "strong",
-            "config": {"workload": f"pairwise IBS0/IBS1/IBS2/valid, {n} x {n} genomes over {kl} SNPs (BASELINE config 4 shape is 20M SNPs: "
-                                   f"the same tile kernel, 18x more words per tile), upper-triangle 64x64 tiles dealt to {world} GPU(s)",
+            "config": {"workload": f"pairwise IBS0/IBS1/IBS2/valid, {n} x {n} genomes over {kl} SNPs (BASELINE config 4 shape: 20 M SNPs), "
+                                   f"upper-triangle 64x64 tiles, whole 256x256 blocks of them dealt to {world} GPU(s)",
                        "tiles": int(n_up), "tiles_this_rank": int(mine), "missing_rate": 0.001},
-            "e2e": e2e, "gpu_launches": int(launches), "grm_i8": grm,
-            "roofline": {"bound": "int-pipe (ALU/LOP3)", "kernel": "k_ibs_tiles<false,2> (+ k_ibs_missing_fix, k_ibs_finalize)",
-                         "achieved": achieved, "peak": peak, "unit": "executed pair-loci/s",
-                         "frac": (achieved / peak) if achieved else None,
-                         # on USEFUL pair-loci (N (N + 1) / 2 pairs: no padding genomes, diagonal tiles counted once), whole step
-                         "frac_useful": value / world / peak,
-                         "peak_source": "62.45 LOP3/clk/SM (measured, kbench) x 148 SMs x 1.965 GHz / 5 LOP3 per 32 pair-loci",
-                         "survey_8d_peak_popc_bound": POPC_PER_CLK_SM * sms * clk / 3.0 * 32.0,
-                         "kernel_ms": k_s * 1e3 if k_s else None}}
+            "e2e": e2e, "gpu_launches": int(launches), "grm_i8": grm, "roofline": roof}
 
 
 def main():

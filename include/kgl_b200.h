@@ -185,6 +185,12 @@ int kgl_b200_run_ibs(kgl_b200_ctx* ctx, uint64_t row_begin, uint64_t row_end, ui
  * stride = R) into out uint32[count][64][64][4] = {IBS0, IBS1, IBS2, valid}; cell [i][j] of tile (ti,tj) is the pair
  * (64 ti + i, 64 tj + j); cells of padding genomes are 0. */
 int kgl_b200_ibs_tile_grid(kgl_b200_ctx* ctx, uint64_t* tiles_per_side, uint64_t* n_upper_tiles);
+/* The dense part of every IBS entry point runs on the tensor cores when it can (default): IBS0 / IBS1 follow exactly from three
+ * int8 Gram matrices -- heterozygous indicator, hom-alt indicator, dosage (ibs_gram.cuh) -- at ~3 PetaOP/s instead of 5 LOP3 + 1
+ * POPC per pair-word. It needs n_loci < 2^29, the three n x n int32 matrices in memory (n <= ~26,000), and code-3 cells that are
+ * indexed or absent; otherwise, or with enable = 0, the popcount tile kernel runs. Same integers either way. */
+int kgl_b200_set_ibs_tensor_cores(kgl_b200_ctx* ctx, int enable);
+int kgl_b200_ibs_used_tensor_cores(const kgl_b200_ctx* ctx);     /* the last IBS call: 1 tensor cores, 0 popcount kernel */
 int kgl_b200_run_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count, uint32_t* out);
 
 /* CalcFWS::updateGenomeFWSMap (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:15-101): for each of n_bins allele-frequency bins
@@ -241,6 +247,11 @@ int kgl_b200_kernel_timer_read(kgl_b200_ctx* ctx, float* ms, uint32_t capacity, 
  * kgl_b200_ibs_tiles_buffer exposes (uint32[count][64][64][4]) for a device-side gather. The ibs timer is the kernel timer
  * of the pairwise tile kernel (k_ibs_tiles). */
 int kgl_b200_enqueue_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count);
+/* The same for an explicit list of tiles, coords uint32[count][2] = (tile row, tile column) of 64-genome tiles (any cell of the
+ * grid, count <= 8192): what a caller uses to deal the tiles of whole 256 x 256 blocks to a rank, the unit the tensor-core form
+ * computes (kgl_gene_b200/shards.py: block_tile_coords). */
+int kgl_b200_enqueue_ibs_tile_list(kgl_b200_ctx* ctx, uint64_t count, const uint32_t* coords);
+int kgl_b200_run_ibs_tile_list(kgl_b200_ctx* ctx, uint64_t count, const uint32_t* coords, uint32_t* out);   /* any count; host result */
 int kgl_b200_ibs_tiles_buffer(kgl_b200_ctx* ctx, void** device_ptr, uint64_t* n_u32);
 /* Resident Gram contraction (the matrix stays on the device) and the milliseconds its tcgen05 kernel took. */
 int kgl_b200_enqueue_gram(kgl_b200_ctx* ctx);

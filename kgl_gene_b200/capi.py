@@ -27,7 +27,7 @@ EXPORTS = [
     "kgl_b200_set_stream", "kgl_b200_synchronize", "kgl_b200_upload_genotypes", "kgl_b200_upload_loci",
     "kgl_b200_set_genome_superpop", "kgl_b200_upload_multi_allelic", "kgl_b200_run_multi_allele_count", "kgl_b200_set_unphased", "kgl_b200_select_loci", "kgl_b200_set_locus_selection",
     "kgl_b200_get_locus_selection", "kgl_b200_count_loci", "kgl_b200_set_locus_filter", "kgl_b200_synth_genotypes", "kgl_b200_download_genotypes", "kgl_b200_run_allele_count",
-    "kgl_b200_run_inbreed", "kgl_b200_inbreed_used_moment_tables", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_run_ibs_tiles",
+    "kgl_b200_run_inbreed", "kgl_b200_inbreed_used_moment_tables", "kgl_b200_run_count_and_inbreed", "kgl_b200_run_loglik_grid", "kgl_b200_run_ibs", "kgl_b200_ibs_tile_grid", "kgl_b200_enqueue_ibs_tile_list", "kgl_b200_run_ibs_tile_list", "kgl_b200_set_ibs_tensor_cores", "kgl_b200_ibs_used_tensor_cores", "kgl_b200_run_ibs_tiles",
     "kgl_b200_run_binned_genome_counts", "kgl_b200_run_hetero_homo", "kgl_b200_location_fis", "kgl_b200_run_gram", "kgl_b200_run_grm", "kgl_b200_enqueue_gram", "kgl_b200_last_gram_kernel_ms", "kgl_b200_enqueue_gram_tiles", "kgl_b200_gram_buffer", "kgl_b200_fetch_gram",
     "kgl_b200_enqueue_ibs_tiles", "kgl_b200_ibs_tiles_buffer", "kgl_b200_ibs_timer_reset", "kgl_b200_ibs_timer_read",
     "kgl_b200_enqueue_count_and_inbreed", "kgl_b200_flush", "kgl_b200_launch_count", "kgl_b200_last_stream_kernel_ms",
@@ -326,6 +326,26 @@ class KglB200:
 
     def last_gram_kernel_ms(self) -> float:
         return float(self.lib.kgl_b200_last_gram_kernel_ms(self.h))
+
+    def set_ibs_tensor_cores(self, enable: bool):
+        """Dense part of the IBS calls on the tensor cores (default) or on the popcount tile kernel."""
+        self._check(self.lib.kgl_b200_set_ibs_tensor_cores(self.h, C.c_int(int(bool(enable)))), "set_ibs_tensor_cores")
+
+    def ibs_used_tensor_cores(self) -> bool:
+        return bool(self.lib.kgl_b200_ibs_used_tensor_cores(self.h))
+
+    def enqueue_ibs_tile_list(self, coords: np.ndarray):
+        """Resident tiles of an explicit list, coords uint32[count][2]; results in ibs_tiles_buffer()."""
+        coords = np.ascontiguousarray(coords, dtype=np.uint32).reshape(-1, 2)
+        self._check(self.lib.kgl_b200_enqueue_ibs_tile_list(self.h, C.c_uint64(coords.shape[0]), _ptr(coords)), "enqueue_ibs_tile_list")
+
+    def ibs_tile_list(self, coords: np.ndarray) -> np.ndarray:
+        """uint32[count][64][64][4] for an explicit list of tiles."""
+        coords = np.ascontiguousarray(coords, dtype=np.uint32).reshape(-1, 2)
+        out = np.zeros((coords.shape[0], 64, 64, 4), dtype=np.uint32)
+        if coords.shape[0]:
+            self._check(self.lib.kgl_b200_run_ibs_tile_list(self.h, C.c_uint64(coords.shape[0]), _ptr(coords), _ptr(out)), "run_ibs_tile_list")
+        return out
 
     def ibs_tile_grid(self):
         side, n = C.c_uint64(), C.c_uint64()

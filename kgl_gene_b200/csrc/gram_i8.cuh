@@ -51,6 +51,9 @@ struct GramParams {
   uint32_t stages_per_chunk, n_chunks;
   int32_t* out;               // [ld][ld]
   uint64_t ld;
+  // value of a 2-bit code as an operand byte: byte c of the table is the value of code c (code 3 is stored as 0). 0x00020100 is the
+  // dosage {0,1,2}; 0x00000100 / 0x00010000 are the indicators "heterozygous" / "homozygous alternate" (pairwise IBS, ibs_gram.cuh)
+  uint32_t table_a, table_b;
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -77,10 +80,9 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
 // {c0, c2, c4, c6} of the table {0,1,2,3} and (x >> 2) & 0x3333 the bytes {c1, c3, c5, c7}. The loci of a word come out
 // de-interleaved (even, odd, even, odd); A and B are expanded by the same function and a dot product does not care about
 // the order of its terms. 2 LOP3 + 3 SHF + 4 PRMT per 16 bytes.
-__device__ __forceinline__ uint4 expand16(uint32_t x) {
+__device__ __forceinline__ uint4 expand16(uint32_t x, uint32_t table) {
   const uint32_t m0 = x & 0x33333333u, m1 = (x >> 2) & 0x33333333u;
-  return make_uint4(__byte_perm(0x03020100u, 0u, m0), __byte_perm(0x03020100u, 0u, m1), __byte_perm(0x03020100u, 0u, m0 >> 16),
-                    __byte_perm(0x03020100u, 0u, m1 >> 16));
+  return make_uint4(__byte_perm(table, 0u, m0), __byte_perm(table, 0u, m1), __byte_perm(table, 0u, m0 >> 16), __byte_perm(table, 0u, m1 >> 16));
 }
 
 __global__ void __launch_bounds__(kGramThreads, 1)
@@ -117,6 +119,7 @@ k_gram_i8(const GramParams P) {
     const uint32_t is_b = t >= (uint32_t)kGramM ? 1u : 0u;
     const uint32_t r = is_b ? t - kGramM : t;                    // row inside the A tile / the B tile
     const uint32_t sw = r & 7;                                   // swizzle phase of the row
+    const uint32_t table = is_b ? P.table_b : P.table_a;
     const uint32_t row_off = (is_b ? kGramABytes : 0u) + (r >> 3) * 1024 + sw * 128;
     uint32_t s = 0, ph = 0, it = 0;
     constexpr int D = 3;                                          // register prefetch depth in stages (L2/HBM latency ~ one stage time)
@@ -152,7 +155,7 @@ k_gram_i8(const GramParams P) {
         if (it >= (uint32_t)kGramStages) mbar_wait(bar_empty + 8 * s, ph ^ 1);
         unsigned char* row = smem + (size_t)s * kGramStageBytes + row_off;
 #pragma unroll
-        for (uint32_t c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = expand16(wds[c]);
+        for (uint32_t c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) * 16)) = expand16(wds[c], table);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(bar_full + 8 * s);
         ++it;

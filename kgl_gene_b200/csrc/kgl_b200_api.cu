@@ -14,6 +14,7 @@
 #include "tail_kernels.cuh"
 #include "multi_allelic.cuh"
 #include "gram_launch.cuh"
+#include "ibs_gram.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -219,7 +220,12 @@ struct kgl_b200_ctx {
   uint64_t bin_tables_n = 0, bin_tables_units = 0;
   // K5 (gram_i8.cuh): 2-bit code matrix in row-block-major layout, tile list, int32 Gram matrix, rank-one terms
   DevBuf<uint32_t> d_codes16;
-  DevBuf<int32_t> d_gram;
+  DevBuf<int32_t> d_gram, d_gram_hh, d_gram_aa;
+  DevBuf<uint2> d_ibs_blocks;          // 256 x 256 Gram blocks the current IBS tile list needs (ibs_gram.cuh)
+  uint32_t ibs_n_blocks = 0;
+  DevBuf<int32_t> d_ibs_class;         // {heterozygous, hom-alt} cells per genome on the IBS planes
+  bool ibs_class_valid = false;
+  bool ibs_tensor_enabled = true, ibs_used_tensor = false;
   DevBuf<uint2> d_gram_tiles;
   DevBuf<double> d_gp_chunks, d_gp;
   DevBuf<uint8_t> d_gram_out;
@@ -1078,6 +1084,8 @@ uint2 ibs_upper_tile(uint64_t t, uint64_t side) {
   return make_uint2((uint32_t)lo, (uint32_t)(lo + (t - start)));
 }
 
+int ensure_codes16(kgl_b200_ctx* c);
+
 constexpr uint64_t kIbsMaxTilesPerLaunch = 8192;     // 384 MB of accumulators
 
 // Dense kernel (+ sparse repair) over a host tile list; leaves acc[n][3][4096] in d_ibs_acc. n <= kIbsMaxTilesPerLaunch.
@@ -1086,9 +1094,45 @@ int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const ui
   const uint32_t n = tiles.empty() ? n_cached : (uint32_t)tiles.size();
   KGL_CUDA(c, c->d_ibs_tiles.ensure(n));
   KGL_CUDA(c, c->d_ibs_acc.ensure((size_t)n * 3 * kIbsTileCells));
-  if (std::memcmp(key, c->ibs_tiles_key, sizeof key) != 0) {
-    KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_tiles.p, tiles.data(), (size_t)n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
-    KGL_CUDA(c, cudaStreamSynchronize(c->stream));     // `tiles` is pageable host memory owned by the caller
+  // Tensor-core form of the dense part: populations whose code-3 cells are indexed (or absent), matrices that fit, n_loci < 2^29
+  static const bool tensor_off = std::getenv("KGL_B200_IBS_POPCOUNT") != nullptr;
+  c->gram_ld = (c->N + kGramN - 1) / kGramN * kGramN;
+  const bool tensor = !tensor_off && c->ibs_tensor_enabled && c->ibs_mode != 1 && c->L < (1ull << 29) &&
+                      (uint64_t)c->gram_ld * c->gram_ld * 12 <= (8ull << 30);
+  if (tensor) {
+    int rc = ensure_codes16(c); if (rc) return rc;
+    KGL_CUDA(c, c->d_gram.ensure((size_t)c->gram_ld * c->gram_ld));
+    KGL_CUDA(c, c->d_gram_hh.ensure((size_t)c->gram_ld * c->gram_ld));
+    KGL_CUDA(c, c->d_gram_aa.ensure((size_t)c->gram_ld * c->gram_ld));
+    if (!c->ibs_class_valid) {          // the genomes' heterozygous / hom-alt cells, once per upload
+      const size_t n_rows = (size_t)std::max<uint64_t>(c->n_gblocks * 32, c->gram_ld);
+      KGL_CUDA(c, c->d_ibs_class.ensure(n_rows * 2));
+      KGL_CUDA(c, cudaMemsetAsync(c->d_ibs_class.p, 0, n_rows * 2 * 4, c->stream));
+      const uint32_t wpc = 4096;
+      k_ibs_class_counts<<<dim3((unsigned)c->n_gblocks, (unsigned)((c->n_words + wpc - 1) / wpc)), 256, 0, c->stream>>>(
+          c->ibs_mode == 2 ? c->d_ibs_lo.p : c->d_sm_lo.p, c->ibs_mode == 2 ? c->d_ibs_hi.p : c->d_sm_hi.p, c->n_words, wpc, c->d_ibs_class.p);
+      KGL_LAUNCH_CHECK(c);
+      c->ibs_class_valid = true;
+    }
+  }
+  if (std::memcmp(key, c->ibs_tiles_key, sizeof key) != 0 || (tensor && c->ibs_n_blocks == 0)) {
+    std::vector<uint2> list = tiles;
+    if (list.empty()) return fail(c, KGL_B200_ERR_STATE, "tile list not available");
+    KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_tiles.p, list.data(), (size_t)n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint2> blocks;
+    if (tensor) {
+      // the 256 x 256 Gram blocks under the tiles (upper triangle)
+      std::vector<uint8_t> seen((size_t)(c->gram_ld / kGramM) * (c->gram_ld / kGramM), 0);
+      const uint32_t bs = (uint32_t)(c->gram_ld / kGramM);
+      auto mark = [&](uint32_t bi, uint32_t bj) { if (bi > bj) std::swap(bi, bj); if (!seen[(size_t)bi * bs + bj]) { seen[(size_t)bi * bs + bj] = 1; blocks.push_back(make_uint2(bi, bj)); } };
+      for (const uint2& t : list) {
+        mark(t.x / kIbsTilesPerBlock, t.y / kIbsTilesPerBlock);
+      }
+      KGL_CUDA(c, c->d_ibs_blocks.ensure(blocks.size()));
+      KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_blocks.p, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+      c->ibs_n_blocks = (uint32_t)blocks.size();
+    }
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));     // the lists are pageable host memory
     std::memcpy(c->ibs_tiles_key, key, sizeof key);
   }
   const uint32_t words_used = (uint32_t)(((c->L + 31) / 32 + 1) / 2 * 2);
@@ -1112,8 +1156,31 @@ int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const ui
     ++c->ibs_timer_used;
   }
   if (e0) KGL_CUDA(c, cudaEventRecord(e0, c->stream));
-  KGL_CUDA(c, launch_ibs(P, pl, c->ibs_mode == 1, c->stream));
-  ++c->launches;
+  if (tensor) {
+    // dense part on the tensor cores: three Gram matrices over the blocks the tile list touches, then the tile cells (ibs_gram.cuh)
+    const uint64_t ld = c->gram_ld;
+    const uint32_t k_stages = (uint32_t)((c->L + kGramK - 1) / kGramK);
+    const GramPlan gp = plan_gram(std::max<uint32_t>(c->ibs_n_blocks, 1), k_stages, c->sm_count);
+    GramParams G{};
+    G.codes = c->d_codes16.p; G.k_stages = k_stages; G.tiles = c->d_ibs_blocks.p; G.n_tiles = c->ibs_n_blocks;
+    G.stages_per_chunk = gp.stages_per_chunk; G.n_chunks = gp.n_chunks; G.ld = ld;
+    int32_t* outs[3] = {c->d_gram.p, c->d_gram_hh.p, c->d_gram_aa.p};
+    const uint32_t tables[3] = {kGramTableDosage, kGramTableHet, kGramTableHomAlt};
+    for (int m = 0; m < 3; ++m) {
+      G.out = outs[m]; G.table_a = G.table_b = tables[m];
+      if (gp.n_chunks > 1) KGL_CUDA(c, cudaMemsetAsync(outs[m], 0, (size_t)ld * ld * 4, c->stream));
+      KGL_CUDA(c, launch_gram(G, gp, c->stream));
+      ++c->launches;
+    }
+    k_ibs_from_grams<<<blocks_for((uint64_t)n * kIbsTileCells, 256), 256, 0, c->stream>>>(c->d_gram.p, c->d_gram_hh.p, c->d_gram_aa.p, ld,
+                                                                                         c->d_ibs_class.p, c->d_ibs_tiles.p, n, c->d_ibs_acc.p);
+    KGL_LAUNCH_CHECK(c);
+    ++c->launches;
+  } else {
+    KGL_CUDA(c, launch_ibs(P, pl, c->ibs_mode == 1, c->stream));
+    ++c->launches;
+  }
+  c->ibs_used_tensor = tensor;
   if (e1) KGL_CUDA(c, cudaEventRecord(e1, c->stream));
   if (c->ibs_mode == 2) {
     // every genome's dropped rows are cut into segments so that the repair fills the GPU also when few tiles are dealt to it
@@ -1177,6 +1244,7 @@ int gram_compute(kgl_b200_ctx* c, uint64_t first = 0, uint64_t stride = 1) {
   GramParams P{};
   P.codes = c->d_codes16.p; P.k_stages = k_stages; P.tiles = c->d_gram_tiles.p; P.n_tiles = (uint32_t)c->gram_n_tiles;
   P.stages_per_chunk = pl.stages_per_chunk; P.n_chunks = pl.n_chunks; P.out = c->d_gram.p; P.ld = ld;
+  P.table_a = P.table_b = kGramTableDosage;
   if (pl.n_chunks > 1 || stride > 1) KGL_CUDA(c, cudaMemsetAsync(c->d_gram.p, 0, (size_t)ld * ld * 4, c->stream));
   if (!c->gram_e0) { KGL_CUDA(c, cudaEventCreate(&c->gram_e0)); KGL_CUDA(c, cudaEventCreate(&c->gram_e1)); }
   KGL_CUDA(c, cudaEventRecord(c->gram_e0, c->stream));
@@ -1333,7 +1401,7 @@ static int set_shape(kgl_b200_ctx* c, uint64_t n_genomes, uint64_t n_loci, uint6
   c->N = n_genomes; c->L = n_loci; c->row_bytes = row_bytes; c->host_units = row_bytes / 16;
   c->n_multi = 0;                    // the side cells belong to the matrix: kgl_b200_upload_multi_allelic comes after it
   c->units = stream_units_padded(c->host_units); c->Npad = c->units * 64;
-  c->sm_valid = false; c->codes_valid = false; c->units_valid = false; c->dropped_valid = false; c->dropped_cells_state = 0; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull;
+  c->sm_valid = false; c->codes_valid = false; c->units_valid = false; c->dropped_valid = false; c->dropped_cells_state = 0; c->prep_valid = false; c->ibs_mode = -1; c->ibs_tiles_key[0] = ~0ull; c->ibs_n_blocks = 0; c->ibs_class_valid = false;
   c->codes16_valid = false;
   return KGL_B200_OK;
 }
@@ -2224,6 +2292,15 @@ int kgl_b200_run_ibs(kgl_b200_ctx* c, uint64_t row_begin, uint64_t row_end, uint
   return KGL_B200_OK;
 }
 
+int kgl_b200_set_ibs_tensor_cores(kgl_b200_ctx* c, int enable) {
+  if (!c) return KGL_B200_ERR_INVALID;
+  c->ibs_tensor_enabled = enable != 0;
+  c->ibs_tiles_key[0] = ~0ull; c->ibs_n_blocks = 0;          // the cached tile list carries no block list for the other form
+  return KGL_B200_OK;
+}
+
+int kgl_b200_ibs_used_tensor_cores(const kgl_b200_ctx* c) { return c && c->ibs_used_tensor ? 1 : 0; }
+
 int kgl_b200_ibs_tile_grid(kgl_b200_ctx* c, uint64_t* tiles_per_side, uint64_t* n_upper_tiles) {
   if (!c) return KGL_B200_ERR_INVALID;
   if (!c->have_geno) return fail(c, KGL_B200_ERR_STATE, "no genotype matrix uploaded");
@@ -2251,6 +2328,39 @@ int kgl_b200_enqueue_ibs_tiles(kgl_b200_ctx* c, uint64_t first, uint64_t stride,
   KGL_CUDA(c, c->d_ibs_tiles_out.ensure((size_t)count * kIbsTileCells * 4));
   rc = ibs_finalize(c, (uint32_t)count, 0, 0, 0, 0, c->d_ibs_tiles_out.p); if (rc) return rc;
   c->ibs_last_count = count;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_enqueue_ibs_tile_list(kgl_b200_ctx* c, uint64_t count, const uint32_t* coords) {
+  if (!c || !coords) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  int rc = use_device(c); if (rc) return rc;
+  rc = require_population(c, false); if (rc) return rc;
+  const uint64_t side = ibs_side(c);
+  if (count == 0 || count > kIbsMaxTilesPerLaunch) return fail(c, KGL_B200_ERR_INVALID, "bad tile count (1..8192 per call)");
+  uint64_t hash = 1469598103934665603ull;                       // FNV-1a of the list: a repeated request skips the upload
+  std::vector<uint2> tiles(count);
+  for (uint64_t i = 0; i < count; ++i) {
+    if (coords[2 * i] >= side || coords[2 * i + 1] >= side) return fail(c, KGL_B200_ERR_INVALID, "tile coordinate outside the grid");
+    tiles[i] = make_uint2(coords[2 * i], coords[2 * i + 1]);
+    hash = (hash ^ coords[2 * i]) * 1099511628211ull; hash = (hash ^ coords[2 * i + 1]) * 1099511628211ull;
+  }
+  rc = ensure_ibs_planes(c); if (rc) return rc;
+  const uint64_t key[4] = {3, hash, count, side};
+  rc = ibs_compute_tiles(c, tiles, key, (uint32_t)count); if (rc) return rc;
+  KGL_CUDA(c, c->d_ibs_tiles_out.ensure((size_t)count * kIbsTileCells * 4));
+  rc = ibs_finalize(c, (uint32_t)count, 0, 0, 0, 0, c->d_ibs_tiles_out.p); if (rc) return rc;
+  c->ibs_last_count = count;
+  return KGL_B200_OK;
+}
+
+int kgl_b200_run_ibs_tile_list(kgl_b200_ctx* c, uint64_t count, const uint32_t* coords, uint32_t* out) {
+  if (!c || !coords || !out) return fail(c, KGL_B200_ERR_INVALID, "null argument");
+  for (uint64_t done = 0; done < count; done += kIbsMaxTilesPerLaunch) {
+    const uint64_t n = std::min<uint64_t>(kIbsMaxTilesPerLaunch, count - done);
+    int rc = kgl_b200_enqueue_ibs_tile_list(c, n, coords + 2 * done); if (rc) return rc;
+    KGL_CUDA(c, cudaMemcpyAsync(out + (size_t)done * kIbsTileCells * 4, c->d_ibs_tiles_out.p, (size_t)n * kIbsTileCells * 16, cudaMemcpyDeviceToHost, c->stream));
+    KGL_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   return KGL_B200_OK;
 }
 

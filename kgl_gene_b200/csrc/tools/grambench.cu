@@ -68,6 +68,7 @@ int main(int argc, char** argv) {
   GramParams P{};
   P.codes = d_codes; P.k_stages = k_stages; P.tiles = d_tiles; P.n_tiles = (uint32_t)tiles.size();
   P.stages_per_chunk = pl.stages_per_chunk; P.n_chunks = pl.n_chunks; P.out = d_out; P.ld = ld; (void)skip;
+  P.table_a = P.table_b = 0x03020100u;
   std::printf("tiles %zu, chunks %u x %u stages, grid %u, smem %zu\n", tiles.size(), pl.n_chunks, pl.stages_per_chunk, pl.grid, kGramSmem);
   auto go = [&]() {
     if (pl.n_chunks > 1) CK(cudaMemsetAsync(d_out, 0, ld * ld * 4));

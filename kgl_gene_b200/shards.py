@@ -110,6 +110,41 @@ def upper_tile_coords(n_genomes: int) -> np.ndarray:
     return np.stack([ti, tj], axis=1).astype(np.int64)
 
 
+BLOCK_TILES = 4     # 64-genome tiles per side of a 256 x 256 block: the unit the tensor-core form of the dense part computes
+
+
+def block_tile_coords(n_genomes: int, rank: int, world: int) -> np.ndarray:
+    """(ti, tj) of the upper-triangle 64x64 tiles inside the 256 x 256 blocks rank owns when upper-triangle block b goes to rank
+    b mod world (blocks row-major, bi <= bj): uint32[n][2], for kgl_b200_enqueue_ibs_tile_list. Dealing whole blocks keeps the
+    tensor-core Gram work of a rank proportional to its tiles (a strided deal of single tiles touches every block on every rank)."""
+    side = tile_side(n_genomes)
+    bside = (side + BLOCK_TILES - 1) // BLOCK_TILES
+    out = []
+    b = 0
+    for bi in range(bside):
+        for bj in range(bi, bside):
+            if b % world == rank:
+                for ti in range(bi * BLOCK_TILES, min(side, (bi + 1) * BLOCK_TILES)):
+                    for tj in range(bj * BLOCK_TILES, min(side, (bj + 1) * BLOCK_TILES)):
+                        if ti <= tj:
+                            out.append((ti, tj))
+            b += 1
+    return np.asarray(out, dtype=np.uint32).reshape(-1, 2)
+
+
+def assemble_ibs_coords(n_genomes: int, coords_by_rank: list[np.ndarray], tiles_by_rank: list[np.ndarray]) -> np.ndarray:
+    """Tiles with explicit coordinates (block_tile_coords) -> uint32[N][N][4], symmetric."""
+    n = n_genomes
+    out = np.zeros((n, n, 4), dtype=np.uint32)
+    for coords, tiles in zip(coords_by_rank, tiles_by_rank):
+        for (ti, tj), t in zip(coords.tolist(), tiles):
+            a0, b0 = ti * TILE, tj * TILE
+            a1, b1 = min(n, a0 + TILE), min(n, b0 + TILE)
+            out[a0:a1, b0:b1] = t[: a1 - a0, : b1 - b0]
+            out[b0:b1, a0:a1] = t[: a1 - a0, : b1 - b0].transpose(1, 0, 2)
+    return out
+
+
 def assemble_ibs(n_genomes: int, blocks_by_rank: list[np.ndarray]) -> np.ndarray:
     """blocks_by_rank[r] = uint32[tiles_of_rank(r)][64][64][4], the tiles r, r + world, ... -> uint32[N][N][4], symmetric."""
     world = len(blocks_by_rank)

@@ -399,9 +399,13 @@ def test_ibs_matches_oracle(gpu):
     pop, _ = make_population(150, 3001, seed=21, missing_rate=0.03)
     gpu.upload_population(pop)
     want = O.ibs(pop)
-    assert np.array_equal(gpu.ibs(), want)
-    assert np.array_equal(gpu.ibs(64, 130), want[64:130])
-    assert np.array_equal(gpu.ibs(149, 150), want[149:150])
+    for tensor in (True, False):                       # dense part on the tensor cores (ibs_gram.cuh) and on the popcount kernel
+        gpu.set_ibs_tensor_cores(tensor)
+        assert np.array_equal(gpu.ibs(), want)
+        assert gpu.ibs_used_tensor_cores() == tensor
+        assert np.array_equal(gpu.ibs(64, 130), want[64:130])
+        assert np.array_equal(gpu.ibs(149, 150), want[149:150])
+    gpu.set_ibs_tensor_cores(True)
 
 
 @pytest.mark.parametrize("n,l,miss", [(70, 999, 0.0),        # no code-3 cell: the sample-major planes as they are
@@ -414,10 +418,14 @@ def test_ibs_modes_and_edges(gpu, n, l, miss):
     pop, _ = make_population(n, l, seed=3 + n, missing_rate=miss)
     gpu.upload_population(pop)
     want = O.ibs(pop)
-    got = gpu.ibs()
-    assert np.array_equal(got, want)
-    assert np.array_equal(got, got.transpose(1, 0, 2))
-    assert np.array_equal(got[..., :3].sum(-1), got[..., 3])
+    for tensor in (True, False):
+        gpu.set_ibs_tensor_cores(tensor)
+        got = gpu.ibs()
+        assert gpu.ibs_used_tensor_cores() == (tensor and n != 300)       # 300 x 20000 at 3 %: too many code-3 cells to index -> popcount kernel with a validity plane
+        assert np.array_equal(got, want)
+        assert np.array_equal(got, got.transpose(1, 0, 2))
+        assert np.array_equal(got[..., :3].sum(-1), got[..., 3])
+    gpu.set_ibs_tensor_cores(True)
 
 
 def test_ibs_tiles_dealt_to_ranks(gpu):
@@ -435,6 +443,21 @@ def test_ibs_tiles_dealt_to_ranks(gpu):
     # cells of padding genomes (200..255) read zero
     last = gpu.ibs_tiles(first=n_up - 1, stride=1, count=1)[0]
     assert np.all(last[200 - 192:, :, :] == 0) and np.all(last[:, 200 - 192:, :] == 0)
+
+
+def test_ibs_blocks_dealt_to_ranks(gpu):
+    """Whole 256 x 256 blocks of tiles per 'rank' (shards.block_tile_coords -> kgl_b200_run_ibs_tile_list): the unit of the
+    tensor-core form; three ranks' tiles assemble into the oracle's matrix."""
+    from kgl_gene_b200.shards import assemble_ibs_coords, block_tile_coords, n_upper_tiles
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(700, 2500, seed=23, missing_rate=0.01)
+    gpu.upload_population(pop)
+    want = O.ibs(pop)
+    coords = [block_tile_coords(pop.n_genomes, r, 3) for r in range(3)]
+    assert sum(c.shape[0] for c in coords) == n_upper_tiles(pop.n_genomes)
+    tiles = [gpu.ibs_tile_list(c) for c in coords]
+    assert gpu.ibs_used_tensor_cores()
+    assert np.array_equal(assemble_ibs_coords(pop.n_genomes, coords, tiles), want)
 
 
 def test_ibs_full_width_properties(gpu):

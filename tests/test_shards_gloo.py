@@ -96,3 +96,27 @@ def test_tile_dealing_is_a_partition(n_genomes, world):
     sym = sym + np.triu(sym.transpose(2, 0, 1), 1).transpose(2, 1, 0)
     blocks = [_cut_tiles(sym, n_genomes, r, world) for r in range(world)]
     assert np.array_equal(shards.assemble_ibs(n_genomes, blocks), sym)
+
+
+@pytest.mark.parametrize("n_genomes,world", [(1, 1), (64, 2), (257, 2), (700, 3), (2504, 8), (500, 8)])
+def test_block_dealing_is_a_partition(n_genomes, world):
+    """Whole 256 x 256 blocks of 64 x 64 tiles per rank (the unit of the tensor-core IBS form): every upper-triangle tile exactly
+    once, and assemble_ibs_coords inverts the dealing."""
+    n_up = shards.n_upper_tiles(n_genomes)
+    coords = [shards.block_tile_coords(n_genomes, r, world) for r in range(world)]
+    allc = np.concatenate([c for c in coords if c.size]) if n_up else np.zeros((0, 2), np.uint32)
+    assert allc.shape[0] == n_up and np.all(allc[:, 0] <= allc[:, 1])
+    assert len({(int(a), int(b)) for a, b in allc}) == n_up
+    rng = np.random.default_rng(2)
+    sym = rng.integers(0, 1000, size=(n_genomes, n_genomes, 4), dtype=np.uint32)
+    sym = np.triu(sym.transpose(2, 0, 1)).transpose(1, 2, 0)
+    sym = sym + np.triu(sym.transpose(2, 0, 1), 1).transpose(2, 1, 0)
+    tiles = []
+    for c in coords:
+        t = np.zeros((c.shape[0], 64, 64, 4), dtype=np.uint32)
+        for i, (ti, tj) in enumerate(c.tolist()):
+            a0, b0 = ti * 64, tj * 64
+            a1, b1 = min(n_genomes, a0 + 64), min(n_genomes, b0 + 64)
+            t[i, : a1 - a0, : b1 - b0] = sym[a0:a1, b0:b1]
+        tiles.append(t)
+    assert np.array_equal(shards.assemble_ibs_coords(n_genomes, coords, tiles), sym)
