@@ -267,10 +267,21 @@ k_ibs_missing_fix(const uint4* __restrict__ packed, uint32_t units, const unsign
       for (int lv = 0; lv < kIbsFixLevels; ++lv) cnt[q][lv] = 0;
     const uint64_t k_stop = min(k_end, k + (uint64_t)((1u << (kIbsFixLevels - 1)) - 8));
     while (k < k_stop) {
-      const uint64_t k_low = min(k_stop, k + 8);
-      for (; k < k_low; ++k) {
-        const uint32_t row = (uint32_t)keys[k];
-        const uint4 v = __ldg(packed + (size_t)row * units + partner);
+      // eight rows at a time: the eight keys, then the eight partner units, are requested together (the walk is bound by the
+      // latency of these two dependent loads, not by the counters)
+      const uint32_t n8 = (uint32_t)min((uint64_t)8, k_stop - k);
+      uint4 v8[8];
+      {
+        uint32_t row8[8];
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) row8[i] = i < n8 ? (uint32_t)keys[k + i] : 0u;
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) v8[i] = i < n8 ? __ldg(packed + (size_t)row8[i] * units + partner) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      k += n8;
+#pragma unroll
+      for (uint32_t i = 0; i < 8; ++i) {
+        const uint4 v = v8[i];                               // rows past n8 are all-zero units: they add nothing
         const uint64_t lo = (uint64_t)v.x | ((uint64_t)v.y << 32), hi = (uint64_t)v.z | ((uint64_t)v.w << 32);
         uint64_t x[3] = {hi & ~lo, lo & ~hi, lo & hi};
 #pragma unroll
