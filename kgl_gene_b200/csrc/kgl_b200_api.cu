@@ -875,7 +875,8 @@ int moments_build_lists(kgl_b200_ctx* c) {
   F.superpop = c->d_superpop.p; F.n_genomes = N; F.n_genomes_padded = npad; F.rows = c->d_mom_rows2.p; F.unit_table = c->d_mom_units.p;
   F.cnt = c->d_mom_unit_cnt.p; F.offs = c->d_mom_unit_offs.p; F.totals = c->d_mom_totals.p; F.base = c->d_mom_base.p; F.list = c->d_mom_list.p;
   const uint32_t fill_tiles = moment_tile_ranges(c, kMomTile, F.tile_lo, F.tile_hi);
-  k_mom_unit_fill<<<dim3(fill_tiles, c->mom_n_units), kMomTile, 0, st>>>(F);
+  F.tiles_per_unit = fill_tiles;
+  k_mom_unit_fill<<<(unsigned)((uint64_t)fill_tiles * c->mom_n_units), kMomTile, 0, st>>>(F);
   KGL_LAUNCH_CHECK(c);
   k_mom_list_limits<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_list.p, c->d_mom_base.p, c->d_mom_totals.p, c->d_superpop.p,
                                                         c->d_mom_pop_cmin.p, N, c->d_mom_limits.p);
@@ -978,7 +979,8 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
     M.superpop = c->d_superpop.p; M.n_genomes = N; M.n_genomes_padded = npad;
     M.rows = c->d_mom_rows2.p; M.unit_table = c->d_mom_units.p; M.btiles = c->d_mom_btiles.p;
     M.b_lo = b_lo; M.nbt = nbt; M.scale = scale; M.mi = c->d_mom_mi.p; M.cnt = keep_counts ? c->d_mom_unit_cnt.p : nullptr;
-    k_mom_mma<<<dim3(mma_tiles, n_units), kMmaM, 0, st>>>(M);
+    M.tiles_per_unit = mma_tiles;
+    k_mom_mma<<<(unsigned)((uint64_t)mma_tiles * n_units), kMmaM, 0, st>>>(M);
     KGL_LAUNCH_CHECK(c);
     c->mom_n_units = n_units; c->mom_cnt_valid = keep_counts;
     if (want_lists) { rc = moments_build_lists(c); if (rc) return rc; }

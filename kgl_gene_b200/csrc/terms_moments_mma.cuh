@@ -179,7 +179,8 @@ struct MomMmaParams {
   int b_lo, nbt; double scale;
   long long* mi;                                     // [n_genomes_padded][nbt][kMomJ]
   uint32_t* cnt;                                     // [n_units][n_genomes_padded] rare homozygous cells (null: not wanted)
-  uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // 128-genome tiles that hold a genome of the population (grid.x spans the widest range)
+  uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // 128-genome tiles that hold a genome of the population
+  uint32_t tiles_per_unit;                           // the widest of those ranges: grid = n_units * tiles_per_unit blocks
 };
 
 __device__ __forceinline__ void mma_i8_n32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -230,9 +231,11 @@ k_mom_mma(const MomMmaParams P) {
   __shared__ __align__(16) uint32_t s_mask[2][4][kMmaK];           // [class][warp slice][locus]
   __shared__ uint64_t s_bar[2];
   __shared__ uint32_t s_tmem, s_mine[4];
-  // grid = (tiles of a population, units): the tiles of one unit run together, so its rows and payload tiles come from L2
-  const MomUnit U = P.unit_table[blockIdx.y];
-  const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x;
+  // 1-D grid, block = unit * tiles_per_unit + tile: the tiles of one unit run together, so its rows and payload tiles come from L2
+  // (a 2-D grid would cap the units at 65,535)
+  const uint32_t unit_index = blockIdx.x / P.tiles_per_unit;
+  const MomUnit U = P.unit_table[unit_index];
+  const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x % P.tiles_per_unit;
   if (tile >= P.tile_hi[U.pop]) return;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t g = (uint64_t)tile * kMmaM + tid;
@@ -358,7 +361,7 @@ k_mom_mma(const MomMmaParams P) {
     }
     if (x == 1) n_rare = v[0];
   }
-  if (P.cnt && mine) P.cnt[(uint64_t)blockIdx.y * P.n_genomes_padded + g] = n_rare;
+  if (P.cnt && mine) P.cnt[(uint64_t)unit_index * P.n_genomes_padded + g] = n_rare;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(64) : "memory");
@@ -405,6 +408,7 @@ struct MomFillParams {
   const uint32_t* cnt; const uint32_t* offs; const uint32_t* totals; const uint64_t* base;
   double* list;
   uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // kMomTile-genome tiles of the population
+  uint32_t tiles_per_unit;
 };
 
 // list[base[g] + ...] = r of the genome's rare homozygous cells: hom-alt part (r ascending), then hom-ref part (r descending).
@@ -413,16 +417,17 @@ k_mom_unit_fill(const MomFillParams P) {
   constexpr int kWarps = kMomTile / 32;
   __shared__ uint32_t s_rare[kMomStep][kWarps];
   __shared__ double s_r[kMomStep];
-  const MomUnit U = P.unit_table[blockIdx.y];
-  const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x;
+  const uint32_t unit_index = blockIdx.x / P.tiles_per_unit;
+  const MomUnit U = P.unit_table[unit_index];
+  const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x % P.tiles_per_unit;
   if (U.rare_code < 0 || tile >= P.tile_hi[U.pop]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t g = (uint64_t)tile * kMomTile + threadIdx.x;
-  const bool mine = g < P.n_genomes && P.superpop[g] == U.pop && P.cnt[(uint64_t)blockIdx.y * P.n_genomes_padded + g] != 0u;
+  const bool mine = g < P.n_genomes && P.superpop[g] == U.pop && P.cnt[(uint64_t)unit_index * P.n_genomes_padded + g] != 0u;
   if (!__syncthreads_or(mine)) return;                      // no genome of the tile has a rare homozygous cell in this unit
   const uint32_t mine_mask = __ballot_sync(kFull, mine);
   uint64_t pos = 0;
-  if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)blockIdx.y * P.n_genomes_padded + g];
+  if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)unit_index * P.n_genomes_padded + g];
   const int tj = threadIdx.x >> 1, th = threadIdx.x & 1;
   const uint64_t unit0 = (uint64_t)tile * (kMomTile / 64) + 2 * th;
   // this thread's half row of the step after the current one, requested a step ahead
