@@ -195,6 +195,8 @@ struct kgl_b200_ctx {
   DevBuf<uint2> d_mom_unit_range;
   DevBuf<unsigned long long> d_mom_pop_cmin;
   DevBuf<unsigned char> d_mom_btiles;
+  DevBuf<uint32_t> d_mom_rare_bits;
+  uint32_t mom_mma_tile_lo[kMaxPop] = {}, mom_mma_tile_hi[kMaxPop] = {}, mom_mma_tiles = 1;
   bool mom_used_mma = false, mom_cnt_valid = false;
   uint32_t mom_n_units = 0;
   DevBuf<double> d_mom_list, d_mom_limits, d_mom_rr;
@@ -876,6 +878,8 @@ int moments_build_lists(kgl_b200_ctx* c) {
   F.cnt = c->d_mom_unit_cnt.p; F.offs = c->d_mom_unit_offs.p; F.totals = c->d_mom_totals.p; F.base = c->d_mom_base.p; F.list = c->d_mom_list.p;
   const uint32_t fill_tiles = moment_tile_ranges(c, kMomTile, F.tile_lo, F.tile_hi);
   F.tiles_per_unit = fill_tiles;
+  F.rare_bits = c->d_mom_rare_bits.p; F.mma_tiles_per_unit = c->mom_mma_tiles;
+  for (int k = 0; k < kMaxPop; ++k) { F.mma_tile_lo[k] = c->mom_mma_tile_lo[k]; F.mma_tile_hi[k] = c->mom_mma_tile_hi[k]; }
   k_mom_unit_fill<<<(unsigned)((uint64_t)fill_tiles * c->mom_n_units), kMomTile, 0, st>>>(F);
   KGL_LAUNCH_CHECK(c);
   k_mom_list_limits<<<blocks_for(N, 256), 256, 0, st>>>(c->d_mom_list.p, c->d_mom_base.p, c->d_mom_totals.p, c->d_superpop.p,
@@ -980,6 +984,14 @@ int ensure_moments(kgl_b200_ctx* c, bool want_lists) {
     M.rows = c->d_mom_rows2.p; M.unit_table = c->d_mom_units.p; M.btiles = c->d_mom_btiles.p;
     M.b_lo = b_lo; M.nbt = nbt; M.scale = scale; M.mi = c->d_mom_mi.p; M.cnt = keep_counts ? c->d_mom_unit_cnt.p : nullptr;
     M.tiles_per_unit = mma_tiles;
+    M.rare_bits = nullptr;
+    if (keep_counts) {          // the bitmap of the rows the list pass has to load
+      KGL_CUDA(c, c->d_mom_rare_bits.ensure_roomy((size_t)std::max<uint32_t>(1, n_btiles) * mma_tiles * 4));
+      KGL_CUDA(c, cudaMemsetAsync(c->d_mom_rare_bits.p, 0, (size_t)std::max<uint32_t>(1, n_btiles) * mma_tiles * 16, st));
+      M.rare_bits = c->d_mom_rare_bits.p;
+    }
+    for (int k = 0; k < kMaxPop; ++k) { c->mom_mma_tile_lo[k] = M.tile_lo[k]; c->mom_mma_tile_hi[k] = M.tile_hi[k]; }
+    c->mom_mma_tiles = mma_tiles;
     k_mom_mma<<<(unsigned)((uint64_t)mma_tiles * n_units), kMmaM, 0, st>>>(M);
     KGL_LAUNCH_CHECK(c);
     c->mom_n_units = n_units; c->mom_cnt_valid = keep_counts;

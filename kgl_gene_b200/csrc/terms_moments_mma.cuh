@@ -181,6 +181,8 @@ struct MomMmaParams {
   uint32_t* cnt;                                     // [n_units][n_genomes_padded] rare homozygous cells (null: not wanted)
   uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // 128-genome tiles that hold a genome of the population
   uint32_t tiles_per_unit;                           // the widest of those ranges: grid = n_units * tiles_per_unit blocks
+  uint32_t* rare_bits;                               // [payload tile pairs][tiles_per_unit][4]: loci of the stage at which a genome of the
+                                                     // tile has a rare homozygous cell (k_mom_unit_fill loads only those rows); may be null
 };
 
 __device__ __forceinline__ void mma_i8_n32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -290,7 +292,12 @@ k_mom_mma(const MomMmaParams P) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) { s_mask[0][k][tid] = nc[k]; s_mask[1][k][tid] = ra[k]; }
     const bool has_c = __syncthreads_or(((nc[0] & mm0) | (nc[1] & mm1) | (nc[2] & mm2) | (nc[3] & mm3)) != 0u);
-    const bool has_r = __syncthreads_or(((ra[0] & mm0) | (ra[1] & mm1) | (ra[2] & mm2) | (ra[3] & mm3)) != 0u);
+    const bool rare_here = ((ra[0] & mm0) | (ra[1] & mm1) | (ra[2] & mm2) | (ra[3] & mm3)) != 0u;
+    if (P.rare_bits) {
+      const uint32_t bal = __ballot_sync(kFull, rare_here);
+      if (lane == 0) P.rare_bits[((size_t)(U.tile_base + s) * P.tiles_per_unit + (tile - P.tile_lo[U.pop])) * 4 + warp] = bal;
+    }
+    const bool has_r = __syncthreads_or(rare_here);
     if (pending) { mbar_wait(bar_mma, mma_phase); mma_phase ^= 1; pending = false; }      // the MMAs of the stage before have read s_a / s_b
     if (has_c || has_r) {
       if (tid == 0) {
@@ -409,14 +416,16 @@ struct MomFillParams {
   double* list;
   uint32_t tile_lo[kMaxPop], tile_hi[kMaxPop];       // kMomTile-genome tiles of the population
   uint32_t tiles_per_unit;
+  const uint32_t* rare_bits;                         // k_mom_mma's bitmap and the tile ranges it is indexed with
+  uint32_t mma_tile_lo[kMaxPop], mma_tile_hi[kMaxPop], mma_tiles_per_unit;
 };
 
 // list[base[g] + ...] = r of the genome's rare homozygous cells: hom-alt part (r ascending), then hom-ref part (r descending).
 __global__ void __launch_bounds__(kMomTile)
 k_mom_unit_fill(const MomFillParams P) {
   constexpr int kWarps = kMomTile / 32;
-  __shared__ uint32_t s_rare[kMomStep][kWarps];
-  __shared__ double s_r[kMomStep];
+  __shared__ uint32_t s_rare[2][kMomStep][kWarps];          // two steps: one barrier per step (a warp may write step i + 1 while
+  __shared__ double s_r[2][kMomStep];                       // another still walks step i)
   const uint32_t unit_index = blockIdx.x / P.tiles_per_unit;
   const MomUnit U = P.unit_table[unit_index];
   const uint32_t tile = P.tile_lo[U.pop] + blockIdx.x % P.tiles_per_unit;
@@ -430,47 +439,56 @@ k_mom_unit_fill(const MomFillParams P) {
   if (mine) pos = P.base[g] + (U.rare_code == 0 ? P.totals[g * 2 + 1] : 0u) + P.offs[(uint64_t)unit_index * P.n_genomes_padded + g];
   const int tj = threadIdx.x >> 1, th = threadIdx.x & 1;
   const uint64_t unit0 = (uint64_t)tile * (kMomTile / 64) + 2 * th;
+  static_assert(kMomStep == kMmaK && kMomTile == 2 * kMmaM, "a step is a stage of k_mom_mma, a tile two of its tiles");
+  // this thread's half of the tile is one 128-genome tile of k_mom_mma: its bitmap says which loci of a stage have a rare
+  // homozygous cell there -- only those rows are loaded (rare cells are a few per cent of the cells)
+  const uint32_t t128 = tile * 2 + (uint32_t)th;
+  const bool half_live = t128 >= P.mma_tile_lo[U.pop] && t128 < P.mma_tile_hi[U.pop];
+  const uint32_t* bits = P.rare_bits + ((size_t)U.tile_base * P.mma_tiles_per_unit + (half_live ? t128 - P.mma_tile_lo[U.pop] : 0u)) * 4 + (tj >> 5);
   // this thread's half row of the step after the current one, requested a step ahead
-  auto fetch = [&](uint32_t s, uint4 (&v)[2], double& r) {
-    v[0] = make_uint4(0u, 0u, 0u, 0u); v[1] = v[0]; r = 0.0;
+  auto fetch = [&](uint32_t s, uint4 (&v)[2], double& r, bool& flag) {
+    v[0] = make_uint4(0u, 0u, 0u, 0u); v[1] = v[0]; r = 0.0; flag = false;
     const uint32_t i = s + tj;
-    if (s < U.end && i < U.end) {
-      const uint4* row = P.packed + (uint64_t)P.rows[i] * P.units + unit0;
-      if (unit0 < P.units) v[0] = __ldg(row);
-      if (unit0 + 1 < P.units) v[1] = __ldg(row + 1);
-      if (th == 0) r = P.rr[i];
+    if (s < U.end && i < U.end && half_live) {
+      flag = (bits[(size_t)((s - U.begin) / kMomStep) * P.mma_tiles_per_unit * 4] >> (tj & 31)) & 1u;
+      if (flag) {
+        const uint4* row = P.packed + (uint64_t)P.rows[i] * P.units + unit0;
+        if (unit0 < P.units) v[0] = __ldg(row);
+        if (unit0 + 1 < P.units) v[1] = __ldg(row + 1);
+        r = P.rr[i];
+      }
     }
   };
-  uint4 nxt[2]; double nxt_r;
-  fetch(U.begin, nxt, nxt_r);
-  for (uint32_t s = U.begin; s < U.end; s += kMomStep) {
-    __syncthreads();
+  uint4 nxt[2]; double nxt_r; bool nxt_flag;
+  fetch(U.begin, nxt, nxt_r, nxt_flag);
+  uint32_t buf = 0;
+  for (uint32_t s = U.begin; s < U.end; s += kMomStep, buf ^= 1u) {
     {
-      uint32_t mk[4];
-      mk[0] = mom_code_mask(make_uint2(nxt[0].x, nxt[0].z), U.rare_code); mk[1] = mom_code_mask(make_uint2(nxt[0].y, nxt[0].w), U.rare_code);
-      mk[2] = mom_code_mask(make_uint2(nxt[1].x, nxt[1].z), U.rare_code); mk[3] = mom_code_mask(make_uint2(nxt[1].y, nxt[1].w), U.rare_code);
-      if (s + tj >= U.end) { mk[0] = 0u; mk[1] = 0u; mk[2] = 0u; mk[3] = 0u; }      // rare_code 0: zero padding would read as hom-ref
-      if (unit0 >= P.units) { mk[0] = 0u; mk[1] = 0u; }
-      if (unit0 + 1 >= P.units) { mk[2] = 0u; mk[3] = 0u; }
-      if (th == 0) s_r[tj] = nxt_r;
+      uint32_t mk[4] = {0u, 0u, 0u, 0u};
+      if (nxt_flag) {
+        if (unit0 < P.units) { mk[0] = mom_code_mask(make_uint2(nxt[0].x, nxt[0].z), U.rare_code); mk[1] = mom_code_mask(make_uint2(nxt[0].y, nxt[0].w), U.rare_code); }
+        if (unit0 + 1 < P.units) { mk[2] = mom_code_mask(make_uint2(nxt[1].x, nxt[1].z), U.rare_code); mk[3] = mom_code_mask(make_uint2(nxt[1].y, nxt[1].w), U.rare_code); }
+        s_r[buf][tj] = nxt_r;                                   // both halves may write it: the same value
+      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s_rare[tj][4 * th + k] = mk[k];
+      for (int k = 0; k < 4; ++k) s_rare[buf][tj][4 * th + k] = mk[k];
     }
-    fetch(s + kMomStep, nxt, nxt_r);
-    __syncthreads();
+    const bool step_live = __syncthreads_or(nxt_flag);
+    fetch(s + kMomStep, nxt, nxt_r, nxt_flag);
+    if (!step_live) continue;
     const int n_here = (int)min((uint32_t)kMomStep, U.end - s);
     // 32 loci at a time: lane = locus holds the mask of its 32 genomes; after the transpose lane = genome holds the loci at which
     // it has a cell, in order -- every lane then walks only its own cells
 #pragma unroll
     for (int k = 0; k < kMomStep / 32; ++k) {
       const int jj = k * 32 + lane;
-      const uint32_t w = jj < n_here ? (s_rare[jj][warp] & mine_mask) : 0u;
+      const uint32_t w = jj < n_here ? (s_rare[buf][jj][warp] & mine_mask) : 0u;
       if (!__any_sync(kFull, w != 0u)) continue;
       uint32_t cells = warp_transpose32(w, lane);
       while (cells) {
         const int j = __ffs(cells) - 1;
         cells &= cells - 1;
-        P.list[pos++] = s_r[k * 32 + j];
+        P.list[pos++] = s_r[buf][k * 32 + j];
       }
     }
   }
