@@ -187,8 +187,9 @@ int kgl_b200_run_ibs(kgl_b200_ctx* ctx, uint64_t row_begin, uint64_t row_end, ui
 int kgl_b200_ibs_tile_grid(kgl_b200_ctx* ctx, uint64_t* tiles_per_side, uint64_t* n_upper_tiles);
 /* The dense part of every IBS entry point runs on the tensor cores when it can (default): IBS0 / IBS1 follow exactly from three
  * int8 Gram matrices -- heterozygous indicator, hom-alt indicator, dosage (ibs_gram.cuh) -- at ~3 PetaOP/s instead of 5 LOP3 + 1
- * POPC per pair-word. It needs n_loci < 2^29, the three n x n int32 matrices in memory (n <= ~26,000), and code-3 cells that are
- * indexed or absent; otherwise, or with enable = 0, the popcount tile kernel runs. Same integers either way. */
+ * POPC per pair-word. The matrices exist only as the 256 x 256 blocks under the tiles of a call, so any width works; it needs
+ * n_loci < 2^29 and code-3 cells that are indexed or absent; otherwise, or with enable = 0, the popcount tile kernel runs. Same
+ * integers either way. */
 int kgl_b200_set_ibs_tensor_cores(kgl_b200_ctx* ctx, int enable);
 int kgl_b200_ibs_used_tensor_cores(const kgl_b200_ctx* ctx);     /* the last IBS call: 1 tensor cores, 0 popcount kernel */
 int kgl_b200_run_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, uint64_t count, uint32_t* out);

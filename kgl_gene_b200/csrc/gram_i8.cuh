@@ -54,6 +54,9 @@ struct GramParams {
   // value of a 2-bit code as an operand byte: byte c of the table is the value of code c (code 3 is stored as 0). 0x00020100 is the
   // dosage {0,1,2}; 0x00000100 / 0x00010000 are the indicators "heterozygous" / "homozygous alternate" (pairwise IBS, ibs_gram.cuh)
   uint32_t table_a, table_b;
+  // != 0: tile t of the list is written as its own 256 x 256 block at out + t * 65536 (row stride 256) instead of into the ld x ld
+  // matrix -- populations whose N x N matrix would not fit (pairwise IBS, ibs_gram.cuh)
+  uint32_t compact;
 };
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -202,7 +205,8 @@ k_gram_i8(const GramParams P) {
 #pragma unroll 1
       for (uint32_t half = 0; half < 2; ++half) {
         const uint64_t row = (uint64_t)tc.x * kGramM + half * kGramMmaM + warp * 32 + lane;
-        int32_t* orow = P.out + row * P.ld + (uint64_t)tc.y * kGramN;
+        int32_t* orow = P.compact ? P.out + ((size_t)tile * kGramM + half * kGramMmaM + warp * 32 + lane) * kGramN
+                                  : P.out + row * P.ld + (uint64_t)tc.y * kGramN;
         const uint32_t taddr = tmem_base + half * kGramN + ((warp * 32) << 16);
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < (uint32_t)kGramN; c0 += 32) {

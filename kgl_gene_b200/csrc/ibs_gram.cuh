@@ -7,7 +7,8 @@
 //     IBS0[a][b] = #(one hom-ref, the other hom-alt)              = a_a + a_b - X[a][b] - 2 AA[a][b]
 // h_a, a_a = the genome's heterozygous / hom-alt cells (k_ibs_class_counts, once per upload).
 // Three runs of k_gram_i8 (gram_i8.cuh) with the expansion tables below instead of 5 LOP3 + 1 POPC per pair-word: 1.5 N^2 L MACs at
-// ~3 PetaOP/s against the INT pipe's 1.2e14 pair-loci/s. Exact in int32 for n_loci < 2^29.
+// ~3 PetaOP/s against the INT pipe's 1.2e14 pair-loci/s. Exact in int32 for n_loci < 2^29. The matrices exist only as the 256 x 256
+// blocks under the tiles of a call (GramParams::compact), so the width of the population does not matter.
 #pragma once
 #include "gram_i8.cuh"
 #include "ibs_tile.cuh"
@@ -40,17 +41,23 @@ k_ibs_class_counts(const uint32_t* __restrict__ lo, const uint32_t* __restrict__
   }
 }
 
-// acc[tile][0] = IBS0, acc[tile][1] = IBS1 (the layout k_ibs_tiles leaves) of 64 x 64 tiles from the upper triangles of the three matrices.
+// acc[tile][0] = IBS0, acc[tile][1] = IBS1 (the layout k_ibs_tiles leaves) of 64 x 64 tiles from the three matrices, stored block by
+// block (256 x 256, GramParams::compact). tile_block[t] = index of the block that holds tile t | 1u << 31 when the tile lies below
+// the diagonal (the block list holds its mirror image: rows and columns swap).
 __global__ void __launch_bounds__(256)
-k_ibs_from_grams(const int32_t* __restrict__ s, const int32_t* __restrict__ hh, const int32_t* __restrict__ aa, uint64_t ld,
-                 const int32_t* __restrict__ counts, const uint2* __restrict__ tiles, uint32_t n_tiles, uint32_t* __restrict__ acc) {
+k_ibs_from_grams(const int32_t* __restrict__ s, const int32_t* __restrict__ hh, const int32_t* __restrict__ aa,
+                 const int32_t* __restrict__ counts, const uint2* __restrict__ tiles, const uint32_t* __restrict__ tile_block,
+                 uint32_t n_tiles, uint32_t* __restrict__ acc) {
   const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (uint64_t)n_tiles * kIbsTileCells) return;
   const uint32_t tile = (uint32_t)(idx / kIbsTileCells), cell = (uint32_t)(idx % kIbsTileCells);
   const uint2 tc = tiles[tile];
+  const uint32_t tb = tile_block[tile];
+  const bool mirrored = (tb >> 31) != 0u;
   const uint64_t a = (uint64_t)tc.x * kIbsT + cell / kIbsT, b = (uint64_t)tc.y * kIbsT + cell % kIbsT;
-  const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
-  const int32_t v_hh = hh[lo * ld + hi], v_aa = aa[lo * ld + hi], v_s = s[lo * ld + hi];
+  const uint32_t ra = (uint32_t)(a % kGramM), rb = (uint32_t)(b % kGramN);          // position inside the block
+  const size_t at = (size_t)(tb & 0x7FFFFFFFu) * kGramM * kGramN + (mirrored ? (size_t)rb * kGramN + ra : (size_t)ra * kGramN + rb);
+  const int32_t v_hh = hh[at], v_aa = aa[at], v_s = s[at];
   const int32_t h_a = counts[a * 2], a_a = counts[a * 2 + 1], h_b = counts[b * 2], a_b = counts[b * 2 + 1];
   const int32_t x = (v_s - v_hh - 4 * v_aa) / 2;
   uint32_t* out = acc + (size_t)tile * 3 * kIbsTileCells + cell;

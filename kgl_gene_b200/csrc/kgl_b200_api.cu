@@ -26,6 +26,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 using namespace kgl;
@@ -224,6 +225,7 @@ struct kgl_b200_ctx {
   DevBuf<uint32_t> d_codes16;
   DevBuf<int32_t> d_gram, d_gram_hh, d_gram_aa;
   DevBuf<uint2> d_ibs_blocks;          // 256 x 256 Gram blocks the current IBS tile list needs (ibs_gram.cuh)
+  DevBuf<uint32_t> d_ibs_tile_block;   // per tile: index of its block | 1 << 31 when mirrored
   uint32_t ibs_n_blocks = 0;
   DevBuf<int32_t> d_ibs_class;         // {heterozygous, hom-alt} cells per genome on the IBS planes
   bool ibs_class_valid = false;
@@ -1108,16 +1110,12 @@ int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const ui
   const uint32_t n = tiles.empty() ? n_cached : (uint32_t)tiles.size();
   KGL_CUDA(c, c->d_ibs_tiles.ensure(n));
   KGL_CUDA(c, c->d_ibs_acc.ensure((size_t)n * 3 * kIbsTileCells));
-  // Tensor-core form of the dense part: populations whose code-3 cells are indexed (or absent), matrices that fit, n_loci < 2^29
+  // Tensor-core form of the dense part: populations whose code-3 cells are indexed (or absent), n_loci < 2^29
   static const bool tensor_off = std::getenv("KGL_B200_IBS_POPCOUNT") != nullptr;
   c->gram_ld = (c->N + kGramN - 1) / kGramN * kGramN;
-  const bool tensor = !tensor_off && c->ibs_tensor_enabled && c->ibs_mode != 1 && c->L < (1ull << 29) &&
-                      (uint64_t)c->gram_ld * c->gram_ld * 12 <= (8ull << 30);
+  const bool tensor = !tensor_off && c->ibs_tensor_enabled && c->ibs_mode != 1 && c->L < (1ull << 29);
   if (tensor) {
     int rc = ensure_codes16(c); if (rc) return rc;
-    KGL_CUDA(c, c->d_gram.ensure((size_t)c->gram_ld * c->gram_ld));
-    KGL_CUDA(c, c->d_gram_hh.ensure((size_t)c->gram_ld * c->gram_ld));
-    KGL_CUDA(c, c->d_gram_aa.ensure((size_t)c->gram_ld * c->gram_ld));
     if (!c->ibs_class_valid) {          // the genomes' heterozygous / hom-alt cells, once per upload
       const size_t n_rows = (size_t)std::max<uint64_t>(c->n_gblocks * 32, c->gram_ld);
       KGL_CUDA(c, c->d_ibs_class.ensure(n_rows * 2));
@@ -1134,20 +1132,34 @@ int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const ui
     if (list.empty()) return fail(c, KGL_B200_ERR_STATE, "tile list not available");
     KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_tiles.p, list.data(), (size_t)n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
     std::vector<uint2> blocks;
+    std::vector<uint32_t> tile_block;
     if (tensor) {
-      // the 256 x 256 Gram blocks under the tiles (upper triangle)
-      std::vector<uint8_t> seen((size_t)(c->gram_ld / kGramM) * (c->gram_ld / kGramM), 0);
-      const uint32_t bs = (uint32_t)(c->gram_ld / kGramM);
-      auto mark = [&](uint32_t bi, uint32_t bj) { if (bi > bj) std::swap(bi, bj); if (!seen[(size_t)bi * bs + bj]) { seen[(size_t)bi * bs + bj] = 1; blocks.push_back(make_uint2(bi, bj)); } };
-      for (const uint2& t : list) {
-        mark(t.x / kIbsTilesPerBlock, t.y / kIbsTilesPerBlock);
+      // the 256 x 256 Gram blocks under the tiles (upper triangle of the block grid; a tile below the diagonal uses the mirror block)
+      std::unordered_map<uint64_t, uint32_t> index;
+      tile_block.resize(list.size());
+      for (size_t t = 0; t < list.size(); ++t) {
+        uint32_t bi = list[t].x / kIbsTilesPerBlock, bj = list[t].y / kIbsTilesPerBlock;
+        const bool mirrored = bi > bj;
+        if (mirrored) std::swap(bi, bj);
+        const uint64_t k2 = ((uint64_t)bi << 32) | bj;
+        auto it = index.find(k2);
+        if (it == index.end()) { it = index.emplace(k2, (uint32_t)blocks.size()).first; blocks.push_back(make_uint2(bi, bj)); }
+        tile_block[t] = it->second | (mirrored ? 0x80000000u : 0u);
       }
       KGL_CUDA(c, c->d_ibs_blocks.ensure(blocks.size()));
+      KGL_CUDA(c, c->d_ibs_tile_block.ensure(tile_block.size()));
       KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_blocks.p, blocks.data(), blocks.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+      KGL_CUDA(c, cudaMemcpyAsync(c->d_ibs_tile_block.p, tile_block.data(), tile_block.size() * 4, cudaMemcpyHostToDevice, c->stream));
       c->ibs_n_blocks = (uint32_t)blocks.size();
     }
     KGL_CUDA(c, cudaStreamSynchronize(c->stream));     // the lists are pageable host memory
     std::memcpy(c->ibs_tiles_key, key, sizeof key);
+  }
+  if (tensor) {
+    const size_t block_cells = (size_t)c->ibs_n_blocks * kGramM * kGramN;
+    KGL_CUDA(c, c->d_gram.ensure(block_cells));             // (also kgl_b200_run_gram's matrix: that call sizes it for itself)
+    KGL_CUDA(c, c->d_gram_hh.ensure(block_cells));
+    KGL_CUDA(c, c->d_gram_aa.ensure(block_cells));
   }
   const uint32_t words_used = (uint32_t)(((c->L + 31) / 32 + 1) / 2 * 2);
   const IbsPlan pl = plan_ibs(n, words_used, c->sm_count);
@@ -1177,17 +1189,18 @@ int ibs_compute_tiles(kgl_b200_ctx* c, const std::vector<uint2>& tiles, const ui
     const GramPlan gp = plan_gram(std::max<uint32_t>(c->ibs_n_blocks, 1), k_stages, c->sm_count);
     GramParams G{};
     G.codes = c->d_codes16.p; G.k_stages = k_stages; G.tiles = c->d_ibs_blocks.p; G.n_tiles = c->ibs_n_blocks;
-    G.stages_per_chunk = gp.stages_per_chunk; G.n_chunks = gp.n_chunks; G.ld = ld;
+    G.stages_per_chunk = gp.stages_per_chunk; G.n_chunks = gp.n_chunks; G.ld = ld; G.compact = 1;
+    const size_t block_cells = (size_t)c->ibs_n_blocks * kGramM * kGramN;
     int32_t* outs[3] = {c->d_gram.p, c->d_gram_hh.p, c->d_gram_aa.p};
     const uint32_t tables[3] = {kGramTableDosage, kGramTableHet, kGramTableHomAlt};
     for (int m = 0; m < 3; ++m) {
       G.out = outs[m]; G.table_a = G.table_b = tables[m];
-      if (gp.n_chunks > 1) KGL_CUDA(c, cudaMemsetAsync(outs[m], 0, (size_t)ld * ld * 4, c->stream));
+      if (gp.n_chunks > 1) KGL_CUDA(c, cudaMemsetAsync(outs[m], 0, block_cells * 4, c->stream));
       KGL_CUDA(c, launch_gram(G, gp, c->stream));
       ++c->launches;
     }
-    k_ibs_from_grams<<<blocks_for((uint64_t)n * kIbsTileCells, 256), 256, 0, c->stream>>>(c->d_gram.p, c->d_gram_hh.p, c->d_gram_aa.p, ld,
-                                                                                         c->d_ibs_class.p, c->d_ibs_tiles.p, n, c->d_ibs_acc.p);
+    k_ibs_from_grams<<<blocks_for((uint64_t)n * kIbsTileCells, 256), 256, 0, c->stream>>>(c->d_gram.p, c->d_gram_hh.p, c->d_gram_aa.p,
+                                                                                         c->d_ibs_class.p, c->d_ibs_tiles.p, c->d_ibs_tile_block.p, n, c->d_ibs_acc.p);
     KGL_LAUNCH_CHECK(c);
     ++c->launches;
   } else {

@@ -460,6 +460,19 @@ def test_ibs_blocks_dealt_to_ranks(gpu):
     assert np.array_equal(assemble_ibs_coords(pop.n_genomes, coords, tiles), want)
 
 
+def test_ibs_wide_population_on_tensor_cores(gpu):
+    """More genomes than one launch's tile list (3,000 -> 1,128 tiles of 141 blocks): the Gram blocks are stored block by block, no
+    N x N matrix; rows of a band use mirrored blocks below the diagonal."""
+    from kgl_gene_b200.synth import make_population
+    pop, _ = make_population(3000, 400, seed=29, missing_rate=0.004)
+    gpu.upload_population(pop)
+    want = O.ibs(pop)
+    got = gpu.ibs()
+    assert gpu.ibs_used_tensor_cores()
+    assert np.array_equal(got, want)
+    assert np.array_equal(gpu.ibs(2100, 2400), want[2100:2400])
+
+
 def test_ibs_full_width_properties(gpu):
     """chr22-shaped width on device-generated data: symmetry through independent tiles, diagonal, row sums vs allele counts."""
     from kgl_gene_b200.synth import make_genomes, make_loci

@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from kgl_gene_b200.capi import KglB200
-from kgl_gene_b200.shards import _RawCudaArray, tiles_of_rank
+from kgl_gene_b200.shards import _RawCudaArray, block_tile_coords, tiles_of_rank
 from kgl_gene_b200.synth import make_genomes, make_loci
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
@@ -74,32 +74,43 @@ if mode in ("both", "gram"):
     ctx.close()
     torch.cuda.empty_cache()
 
-if mode in ("both", "ibs"):
+if mode in ("both", "ibs", "ibs_popcount"):
     ctx, stream = fresh()
     side, n_up = ctx.ibs_tile_grid()
-    mine = tiles_of_rank(n_up, rank, world)
     SLAB = 8192
+    tensor = mode != "ibs_popcount"
+    ctx.set_ibs_tensor_cores(tensor)
+    # tensor-core form: whole 256 x 256 blocks of tiles per rank (explicit tile lists); popcount form: single tiles, strided
+    coords = block_tile_coords(n, rank, world) if tensor else None
+    mine = int(coords.shape[0]) if tensor else tiles_of_rank(n_up, rank, world)
 
     def sweep():
         done = 0
         while done < mine:
             k = min(SLAB, mine - done)
-            ctx.enqueue_ibs_tiles(rank + done * world, world, k)
+            if tensor:
+                ctx.enqueue_ibs_tile_list(coords[done:done + k])
+            else:
+                ctx.enqueue_ibs_tiles(rank + done * world, world, k)
             done += k
         return k
 
-    ctx.enqueue_ibs_tiles(rank, world, min(SLAB, mine))      # warm-up: sample-major planes, masked planes
+    if tensor:
+        ctx.enqueue_ibs_tile_list(coords[: min(SLAB, mine)])   # warm-up: sample-major planes, masked planes, code matrix, class counts
+    else:
+        ctx.enqueue_ibs_tiles(rank, world, min(SLAB, mine))
     torch.cuda.synchronize()
     last = [0]
     ms = timed(stream, lambda: last.__setitem__(0, sweep()))
     ptr, cnt = ctx.ibs_tiles_buffer()
     t = torch.as_tensor(_RawCudaArray(ptr, cnt, "<u4"), device=dev).view(-1, 64, 64, 4)[: last[0]].to(torch.int64)
-    ok = bool(torch.equal(t[..., :3].sum(-1), t[..., 3]))
+    ok = bool(torch.equal(t[..., :3].sum(-1), t[..., 3])) and bool((t >= 0).all()) and bool((t[..., 3] <= l).all())
     okt = torch.tensor([int(ok)], device=dev)
     if world > 1:
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-    out["ibs_popcount"] = {"ms": ms, "pair_loci_per_s": pair_loci / (ms * 1e-3), "tiles": int(n_up), "tiles_this_rank": int(mine),
-                           "ibs_classes_sum_to_valid": bool(okt.item()), "free_hbm_gb": torch.cuda.mem_get_info()[0] / 1e9}
+    out["ibs_tensor" if ctx.ibs_used_tensor_cores() else "ibs_popcount"] = {
+        "ms": ms, "pair_loci_per_s": pair_loci / (ms * 1e-3), "tiles": int(n_up), "tiles_this_rank": int(mine),
+        "ibs_classes_sum_to_valid": bool(okt.item()), "free_hbm_gb": torch.cuda.mem_get_info()[0] / 1e9}
     assert ok
     ctx.close()
 
