@@ -251,7 +251,8 @@ k_hall_update(const double* __restrict__ partials, const double* __restrict__ it
   const double n = P[PART_NMAJHOM] + P[PART_NMAJHET] + P[PART_NMINHOM] + P[PART_NMINHET];
   // f == 0 is a fixed point (every term is 0/(0 + a), calc.cpp:268-272) and an unstable one: the sweeps must not leave it through
   // the 1e-60 the table kernel's neutral entries leave behind
-  const double nf = (f[g] == 0.0 && n > 0.0) ? 0.0 : __ddiv_rn(iter[g * ITER_COUNT], n);
+  // A genome without any term is 0/0 in the reference (calc.cpp:285), not the 1e-60 / 0 the neutral entries would make of it.
+  const double nf = n > 0.0 ? (f[g] == 0.0 ? 0.0 : __ddiv_rn(iter[g * ITER_COUNT], n)) : __ddiv_rn(0.0, n);
   const double delta = fabs(nf - f[g]);
   f[g] = nf;
   if (delta == delta) atomicMax(flag, (unsigned long long)__double_as_longlong(delta));   // non-negative doubles order like ints

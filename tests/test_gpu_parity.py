@@ -845,3 +845,13 @@ def test_hetero_homo_records_and_location_fis(gpu):
             want = (h_exp - het[g] / tot[g]) / h_exp
         assert fis[g] == want, g
     assert qc[members[8]].sum() < 20
+
+
+def test_equivalent_implementations_on_random_shapes():
+    """tools/fuzz_paths.py: moment tables (tensor-core and CUDA-core builders) against the every-cell sweeps, tensor-core IBS against
+    the popcount kernel, on 25 random shapes / selections / frequency edge values (1 .. 1,500 genomes, 1 .. 60,000 loci)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_paths.py"), "25", "11"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "all equal" in r.stdout
