@@ -257,7 +257,7 @@ int kgl_b200_ibs_tiles_buffer(kgl_b200_ctx* ctx, void** device_ptr, uint64_t* n_
 /* Resident Gram contraction (the matrix stays on the device) and the milliseconds its tcgen05 kernel took. */
 int kgl_b200_enqueue_gram(kgl_b200_ctx* ctx);
 float kgl_b200_last_gram_kernel_ms(kgl_b200_ctx* ctx);
-/* Multi-GPU form: rank r of R computes the 128 x 256 tiles r, r + R, ... of the upper triangle (first = r, stride = R) and
+/* Multi-GPU form: rank r of R computes the 256 x 256 tiles r, r + R, ... of the upper triangle (first = r, stride = R) and
  * leaves the rest of its device matrix zero; a SUM all-reduce of kgl_b200_gram_buffer (int32[ld][ld], ld = n_genomes rounded
  * up to 256; 26 MB at 2,504 genomes -- SURVEY 8e) over the ranks assembles the matrix, kgl_b200_fetch_gram copies the
  * symmetric [n_genomes][n_genomes] result to the host. */
