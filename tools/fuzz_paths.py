@@ -10,11 +10,12 @@ from kgl_gene_b200.synth import make_population
 
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+WIDE = os.environ.get("FUZZ_WIDE") == "1"      # also draws populations of thousands of genomes and hundreds of thousands of loci
 ctx = KglB200(0)
 worst = {"HallME": 0.0, "Loglikelihood": 0.0}
 for case in range(n_cases):
-    n = int(rng.choice([1, 2, 33, 64, 65, 127, 130, 256, 300, 511, 700, 1500]))
-    l = int(rng.choice([1, 31, 32, 100, 1000, 4097, 20000, 60000]))
+    n = int(rng.choice([1, 2, 33, 64, 65, 127, 130, 256, 300, 511, 700, 1500] + ([2504, 4100] if WIDE else [])))
+    l = int(rng.choice([1, 31, 32, 100, 1000, 4097, 20000, 60000] + ([8191, 150000, 400000] if WIDE else [])))
     kw = dict(n_genomes=n, n_loci=l, seed=int(rng.integers(1, 10**6)), spectrum=str(rng.choice(["sfs", "dense"])),
               grouped=bool(rng.integers(0, 2)), unphased=bool(rng.integers(0, 4) == 0),
               missing_rate=float(rng.choice([0.0, 0.001, 0.02])), missing_af_rate=float(rng.choice([0.0, 0.02])))
