@@ -200,7 +200,11 @@ int kgl_b200_run_ibs_tiles(kgl_b200_ctx* ctx, uint64_t first, uint64_t stride, u
  * genome_counts uint64[n_bins][n_genomes][4] = {referenceHomozygous_, minorHeterozygous_, minorHomozygous_, code 3},
  * bin_rows (nullable) uint64[n_bins] = loci in the bin. present_only != 0 restricts a bin to loci carried by at least one
  * genome -- the variants a filtered PopulationDB / VariantDBVariant holds (kgl_variant_db_variant.cpp:11-123).
- * The per-variant half of CalcFWS (updateVariantFWSMap, :41-70) is kgl_b200_run_allele_count's locus_counts. */
+ * Multi-allelic loci (kgl_b200_upload_multi_allelic): every listed allele is a variant of its own with its own AF (its element
+ * of the record's Number=A list, kgl_variant_filter_Pf7.cpp:22-48) and is added to the bin it falls in; a genome has 0, 1 or 2
+ * copies of it. Side cells with more than two variants (0xFF) do not record which alleles: no copy.
+ * The per-variant half of CalcFWS (updateVariantFWSMap, :41-70) is kgl_b200_run_allele_count's locus_counts and, for those
+ * loci, kgl_b200_run_multi_allele_count. */
 int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* ctx, uint32_t pop, uint32_t n_bins, const double* lower, const double* upper,
                                       int present_only, uint64_t* genome_counts, uint64_t* bin_rows);
 

@@ -2507,6 +2507,11 @@ int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* c, uint32_t pop, uint32_t n_
   if (pop >= c->n_pop) return fail(c, KGL_B200_ERR_INVALID, "population index out of range");
   // "variants of the population" = rows carried by at least one genome: needs the per-locus counts of a raw pass
   if (present_only) { rc = launch_count(c, true, true, false); if (rc) return rc; }
+  if (c->n_multi && present_only) {      // which alleles of the multi-allelic loci occur
+    KGL_CUDA(c, c->d_multi_counts.ensure(c->n_multi * kMultiSlots * 3));
+    k_multi_allele_count<<<(unsigned)c->n_multi, 256, 0, c->stream>>>(c->d_multi_cells.p, c->N, c->d_multi_counts.p);
+    KGL_LAUNCH_CHECK(c);
+  }
   if (c->bin_tables_n != c->N || c->bin_tables_units != c->units) {
     std::vector<uint32_t> pm(c->units * 2, 0);
     for (uint64_t g = 0; g < c->N; ++g) pm[g >> 5] |= 1u << (g & 31);
@@ -2535,6 +2540,13 @@ int kgl_b200_run_binned_genome_counts(kgl_b200_ctx* c, uint32_t pop, uint32_t n_
     k_genome_counts_masked<<<blocks_for(c->N, 256), 256, 0, c->stream>>>(c->d_gcounts, c->d_n3, c->N, c->d_bin_state.p + 1,
                                                                          c->d_bin_out.p + (size_t)b * c->N * 4, c->d_bin_out.p + (size_t)n_bins * c->N * 4 + b);
     KGL_LAUNCH_CHECK(c);
+    if (c->n_multi) {
+      k_multi_bin_counts<<<blocks_for(c->N, 128), 128, 0, c->stream>>>(c->d_multi_cells.p, c->d_multi_af.p + (size_t)pop * c->n_multi * kMultiSlots,
+                                                                       present_only ? c->d_multi_counts.p : nullptr, c->d_multi_rows.p,
+                                                                       c->keep_valid ? c->d_locus_keep.p : nullptr, c->n_multi, c->N, lower[b], upper[b],
+                                                                       c->d_bin_out.p + (size_t)b * c->N * 4, c->d_bin_out.p + (size_t)n_bins * c->N * 4 + b);
+      KGL_LAUNCH_CHECK(c);
+    }
   }
   KGL_CUDA(c, cudaMemcpyAsync(genome_counts, c->d_bin_out.p, (size_t)n_bins * c->N * 32, cudaMemcpyDeviceToHost, c->stream));
   if (bin_rows) KGL_CUDA(c, cudaMemcpyAsync(bin_rows, c->d_bin_out.p + (size_t)n_bins * c->N * 4, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, c->stream));

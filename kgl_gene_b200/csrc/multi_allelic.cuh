@@ -256,6 +256,41 @@ k_multi_allele_count(const uint8_t* __restrict__ cells, uint64_t n_genomes, uint
   if (threadIdx.x < kMultiSlots * 3) counts[m * kMultiSlots * 3 + threadIdx.x] = (&s_c[0][0])[threadIdx.x];
 }
 
+// CalcFWS::updateGenomeFWSMap (kga_PfEMP/kga_analysis_PfEMP_FWS.cpp:72-101) over the alleles of the multi-allelic loci, one AF bin
+// per launch, added to what the masked pass over the ordinary rows left in out[g] = {refHom, het, minorHom, code 3}: every listed
+// allele is a variant of its own with its own AF (P7FrequencyFilter reads the variant's element of the Number=A vector,
+// kgl_variant_filter_Pf7.cpp:22-48); it is in the bin when lower <= AF < upper and, with allele_counts, when some genome carries
+// it. A genome has 0, 1 or 2 copies of the allele (kgl_variant_db_variant.cpp:73-103). Cells with more than two variants (0xFF)
+// do not record which: they count as no copy, as in k_multi_allele_count. One thread per genome; the membership test is
+// recomputed by every thread (3 M float reads from L1).
+__global__ void __launch_bounds__(128)
+k_multi_bin_counts(const uint8_t* __restrict__ cells, const float* __restrict__ af_pop /* [M][3] of the population */,
+                   const uint32_t* __restrict__ allele_counts /* nullable [M][3][3] */, const uint32_t* __restrict__ rows,
+                   const uint8_t* __restrict__ keep /* nullable, per row */, uint64_t n_multi, uint64_t n_genomes, double lower, double upper,
+                   uint64_t* __restrict__ out, uint64_t* __restrict__ rows_out) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t members = 0, het = 0, hom = 0;
+  for (uint64_t m = 0; m < n_multi; ++m) {
+    if (keep && keep[rows[m]] == 0) continue;
+    const uint32_t cell = g < n_genomes ? cells[m * n_genomes + g] : 0u;
+#pragma unroll
+    for (int a = 0; a < kMultiSlots; ++a) {
+      const float af = af_pop[m * kMultiSlots + a];
+      if (!(af == af)) continue;
+      const double v = (double)af;
+      if (!(v >= lower && !(v >= upper))) continue;
+      if (allele_counts && allele_counts[(m * kMultiSlots + a) * 3 + 1] + allele_counts[(m * kMultiSlots + a) * 3 + 2] == 0) continue;
+      ++members;
+      if (cell == 0u || cell == 0xFFu) continue;
+      const uint32_t copies = ((cell & 15u) == (uint32_t)(a + 1)) + ((cell >> 4) == (uint32_t)(a + 1));
+      het += copies == 1u; hom += copies == 2u;
+    }
+  }
+  if (g == 0) *rows_out += members;
+  if (g >= n_genomes) return;
+  out[g * 4 + 0] += members - het - hom; out[g * 4 + 1] += het; out[g * 4 + 2] += hom;
+}
+
 // HeteroHomoZygous::updateVariantAnalysisType (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105) for every genome, from the raw
 // per-genome code counts of a counting pass and the multi-allelic side cells. Per offset of a genome: every variant entry counts
 // (total_variants_, snp_count_: the matrix path holds SNPs only); one entry -> heterozygous_reference_minor_alleles_; otherwise

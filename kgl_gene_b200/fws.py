@@ -23,8 +23,10 @@ FWS_BINS = [(0.0, 0.05), (0.05, 0.10), (0.10, 0.15), (0.15, 0.20), (0.20, 0.25),
             (0.40, 0.45), (0.45, 0.5), (0.5, 1.0)]
 
 
-def calc_fws(ctx, pop: int = 0, bins=FWS_BINS):
-    """Returns dict(variant_summary uint32[L][3], present bool[L], genome_bins uint64[n_bins][N][3], bin_variants uint64[n_bins]).
+def calc_fws(ctx, pop: int = 0, bins=FWS_BINS, n_multi: int = 0):
+    """Returns dict(variant_summary uint32[L][3], present bool[L], genome_bins uint64[n_bins][N][3], bin_variants uint64[n_bins]) and,
+    with n_multi multi-allelic loci uploaded, multi_variant_summary uint32[M][3][3] / multi_present bool[M][3] -- one variant per
+    listed allele there (the rows of those loci in variant_summary are not variants).
 
     variant_summary[l] = {referenceHomozygous_, minorHeterozygous_, minorHomozygous_} of locus l over all genomes; `present`
     marks the loci that are variants of the population (carried by some genome) -- only those have an entry in the
@@ -41,8 +43,13 @@ def calc_fws(ctx, pop: int = 0, bins=FWS_BINS):
     variant_summary[:, 0] += lc[:, 3]
     genome_bins = counts[:, :, :3].copy()
     genome_bins[:, :, 0] += counts[:, :, 3]
-    return {"variant_summary": variant_summary, "present": (lc[:, 1] + lc[:, 2]) > 0,
-            "genome_bins": genome_bins, "bin_variants": rows}
+    out = {"variant_summary": variant_summary, "present": (lc[:, 1] + lc[:, 2]) > 0,
+           "genome_bins": genome_bins, "bin_variants": rows}
+    if n_multi:
+        mc = ctx.multi_allele_count(n_multi)               # genomes with 0 / 1 / 2 copies per allele slot
+        out["multi_variant_summary"] = mc
+        out["multi_present"] = (mc[:, :, 1] + mc[:, :, 2]) > 0
+    return out
 
 
 def hetero_homo_summary(genome_counts: np.ndarray, other_allele_entries: int = 1) -> dict:

@@ -161,7 +161,66 @@ def fws_bins(pop, af_col: int, bins, present_only=True):
         sub = codes[m]
         for c in range(4):
             out[b, :, c] = (sub == c).sum(axis=0)
+    if getattr(pop, "n_multi", 0):
+        # every listed allele of a multi-allelic locus is a variant with its own AF (its element of the Number=A list,
+        # kgl_variant_filter_Pf7.cpp:22-48); a genome has 0, 1 or 2 copies of it (kgl_variant_db_variant.cpp:73-103). Cells with
+        # more than two variants (0xFF) do not record which alleles: no copy (flattener contract).
+        copies = multi_allele_copies(pop)                  # [M][3][N]
+        for b, (lo, hi) in enumerate(bins):
+            for m_i in range(pop.n_multi):
+                for a in range(3):
+                    v = float(pop.multi_af[af_col, m_i, a])
+                    if np.isnan(v) or not (v >= lo and not v >= hi):
+                        continue
+                    if present_only and not (copies[m_i, a] > 0).any():
+                        continue
+                    rows[b] += np.uint64(1)
+                    for c in range(3):
+                        out[b, :, c] += (copies[m_i, a] == c).astype(np.uint64)
     return out, rows
+
+
+def hetero_homo(pop, other_allele_entries: int = 1) -> np.ndarray:
+    """HeteroHomoZygous::updateVariantAnalysisType (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105) per genome over every
+    offset: uint64[N][7] = total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef. One entry at an offset ->
+    heterozygous_reference_minor_alleles_; otherwise homozygous_minor_alleles_ += distinct alleles, heterozygous_minor_alleles_ +=
+    alleles that occur once. A 0xFF side cell stands for three entries, two of one allele and one of another (what the reference
+    harness builds for it)."""
+    codes = pop.codes()
+    out = np.zeros((pop.n_genomes, 7), dtype=np.uint64)
+    is_multi = np.zeros(pop.n_loci, dtype=bool)
+    if getattr(pop, "n_multi", 0):
+        is_multi[pop.multi_rows] = True
+    for g in range(pop.n_genomes):
+        col = codes[~is_multi, g]
+        n1, n2, n3 = int((col == 1).sum()), int((col == 2).sum()), int((col == 3).sum()) * (1 if other_allele_entries else 0)
+        single = same = diff = many = 0
+        for m in range(getattr(pop, "n_multi", 0)):
+            cell = int(pop.multi_cells[m, g])
+            if cell == 0:
+                continue
+            if cell == 0xFF:
+                many += 1
+            elif cell >> 4 == 0:
+                single += 1
+            elif cell >> 4 == cell & 15:
+                same += 1
+            else:
+                diff += 1
+        total = n1 + 2 * n2 + n3 + single + 2 * same + 2 * diff + 3 * many
+        out[g] = (total, total, 0, n2 + same + 2 * diff + 2 * many, 2 * diff + many, n1 + n3 + single, 0)
+    return out
+
+
+def multi_allele_copies(pop) -> np.ndarray:
+    """int64[M][3][N]: copies of allele slot a genome g carries at multi-allelic locus m (side cells: low nibble = first variant's
+    slot + 1, high nibble = the second's, 0xFF = more than two variants, counted as none)."""
+    cells = pop.multi_cells.astype(np.int64)
+    out = np.zeros((pop.n_multi, 3, pop.n_genomes), dtype=np.int64)
+    for a in range(3):
+        out[:, a, :] = ((cells & 15) == a + 1).astype(np.int64) + ((cells >> 4) == a + 1).astype(np.int64)
+    out[:, :, :] *= (cells != 0xFF)[:, None, :]
+    return out
 
 
 def gram(pop, af_pop=None):

@@ -270,6 +270,25 @@ void run() {
     out.addU32("fws_genome_present", {N}, fws_genome_present);
     out.addU64("fws_variant", {L, 3}, fws_variant);             // per "A>G" variant over all genomes
     out.addU32("fws_variant_present", {L}, fws_variant_present);
+    if (flat.M() > 0) {                                         // one map entry per allele of a multi-allelic locus
+      static const char* const kAlt[3] = {"G", "C", "T"};
+      const size_t M = flat.M();
+      std::vector<uint64_t> multi_variant(M * 3 * 3, 0);
+      std::vector<uint32_t> multi_present(M * 3, 0);
+      for (size_t m = 0; m < M; ++m)
+        for (size_t a = 0; a < 3; ++a) {
+          const kgl::Variant probe(kglref::kContig, flat.offsets[flat.multi_rows[m]], kgl::VariantPhase::UNPHASED, "",
+                                   kgl::DNA5SequenceLinear(kgl::StringDNA5("A")), kgl::DNA5SequenceLinear(kgl::StringDNA5(kAlt[a])),
+                                   pf.locus_variant[flat.multi_rows[m]]->evidence());
+          auto it = calc_fws.getVariantMap().find(probe.HGVS());
+          if (it == calc_fws.getVariantMap().end()) continue;
+          multi_present[m * 3 + a] = 1;
+          multi_variant[(m * 3 + a) * 3 + 0] = it->second.referenceHomozygous_; multi_variant[(m * 3 + a) * 3 + 1] = it->second.minorHeterozygous_;
+          multi_variant[(m * 3 + a) * 3 + 2] = it->second.minorHomozygous_;
+        }
+      out.addU64("fws_multi_variant", {M, 3, 3}, multi_variant);      // refHom, het, minorHom per allele slot
+      out.addU32("fws_multi_variant_present", {M, 3}, multi_present);
+    }
     // HeteroHomoZygous::updateVariantAnalysisType (kga_PfEMP/kga_analysis_PfEMP_heterozygous.cpp:61-105), applied to every
     // offset of every genome exactly as analyzeVariantPopulation does (:14-58); the harness population has one contig.
     std::vector<uint64_t> hh(size_t(N) * 7, 0);

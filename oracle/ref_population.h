@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <memory>
 #include <string>
+#include <map>
 #include <vector>
 
 namespace kglref {
@@ -74,6 +75,7 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
   const std::vector<kgl::GenomeId_t> af_genome{"AF_GENOME"};
   std::vector<kgl::VariantEvidence> locus_evidence;
   if (diploid_evidence) locus_evidence.reserve(L);
+  std::map<std::pair<uint32_t, uint32_t>, kgl::VariantEvidence> multi_evidence;   // (locus, allele slot) -> the allele's INFO, diploid side
   std::vector<int> multi_of(L, -1);
   for (uint32_t m = 0; m < flat.M(); ++m) multi_of[flat.multi_rows[m]] = int(m);
   static const char* const kAltBases[3] = {"G", "C", "T"};
@@ -101,6 +103,8 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
                                                             kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
                                                             kgl::DNA5SequenceLinear(kgl::StringDNA5(kAltBases[a])), evidence);
         if (!out.af_population->addVariant(variant, af_genome)) kel::ExecEnv::log().error("harness: AF addVariant failed at multi locus {}", l);
+        // Pf7 style: every allele of the record is a variant of its own carrying its own frequency (its element of the Number=A list)
+        if (diploid_evidence) multi_evidence.emplace(std::make_pair(l, a), kgl::VariantEvidence(l, diploid_source, true, block, nullptr, 0, 1));
       }
       if (diploid_evidence) locus_evidence.emplace_back(l, diploid_source, true, nullptr, nullptr, 0, 1);
       continue;
@@ -130,9 +134,15 @@ inline BuiltPopulations buildPopulations(const kglflat::Flat& flat, kgl::DataSou
   const kgl::VariantEvidence no_evidence(0, diploid_source, true, nullptr, nullptr, 0, 1);
   auto make = [&](uint32_t l, kgl::VariantPhase phase, const char* alt) {
     const bool with_info = diploid_evidence && alt[0] == 'G';
+    const kgl::VariantEvidence* evidence = with_info ? &locus_evidence[l] : &no_evidence;
+    if (diploid_evidence && multi_of[l] >= 0) {
+      evidence = &no_evidence;
+      for (uint32_t a = 0; a < 3; ++a)
+        if (alt[0] == kAltBases[a][0]) { auto it = multi_evidence.find({l, a}); if (it != multi_evidence.end()) evidence = &it->second; }
+    }
     return std::make_shared<const kgl::Variant>(kContig, flat.offsets[l], phase, "",
                                                 kgl::DNA5SequenceLinear(kgl::StringDNA5("A")),
-                                                kgl::DNA5SequenceLinear(kgl::StringDNA5(alt)), with_info ? locus_evidence[l] : no_evidence);
+                                                kgl::DNA5SequenceLinear(kgl::StringDNA5(alt)), *evidence);
   };
   std::vector<kgl::GenomeId_t> first, second, other;
   for (uint32_t l = 0; l < L; ++l) {

@@ -50,7 +50,7 @@ def main():
             pop.af[:, 5::13] = np.float32(1.0)
         if name in MULTI:
             add_multi_allelic(pop, *MULTI[name])
-        ref = O.run_reference(pop, grid=21, fws=name not in MULTI, **ref_kw)
+        ref = O.run_reference(pop, grid=21, fws=True, **ref_kw)
         stderr = ref.pop("_stderr")
         arrays = {"in_offsets": pop.offsets, "in_af": pop.af, "in_superpop": pop.superpop, "in_packed": pop.packed,
                   "in_n_genomes": np.array([pop.n_genomes]), "in_unphased": np.array([int(pop.unphased)]),

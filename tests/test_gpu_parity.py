@@ -545,24 +545,50 @@ def test_gram_full_width_identity(gpu):
 
 def test_golden_calc_fws(gpu, golden):
     """CalcFWS against the reference's own kga_analysis_PfEMP_FWS.cpp (compiled into oracle/_ref, golden ref_fws_*): per-genome
-    AlleleSummmary in the eleven AF bins and the per-variant summaries, bit-exact."""
+    AlleleSummmary in the eleven AF bins and the per-variant summaries, bit-exact; the alleles of multi-allelic loci are variants
+    with their own AF (k_multi_bin_counts). Side cells with more than two variants (0xFF) do not say which alleles the genome
+    carries: those genomes are compared with the oracle instead, those loci left out of the per-variant comparison."""
     from kgl_gene_b200 import fws
     name, pop, ref, _ = golden
-    if "fws_genome" not in ref:
-        pytest.skip("fixture without the CalcFWS run (multi-allelic loci)")
     gpu.upload_population(pop)
-    got = fws.calc_fws(gpu, pop=5)
-    assert np.array_equal(np.transpose(got["genome_bins"], (1, 0, 2)), ref["fws_genome"])
-    m = ref["fws_variant_present"] == 1
-    assert np.array_equal(got["present"], m)
+    got = fws.calc_fws(gpu, pop=5, n_multi=pop.n_multi)
+    known = np.ones(pop.n_genomes, dtype=bool)
+    ordinary = np.ones(pop.n_loci, dtype=bool)
+    if pop.n_multi:
+        known = ~(pop.multi_cells == 0xFF).any(axis=0)
+        ordinary[pop.multi_rows] = False
+    bins = np.transpose(got["genome_bins"], (1, 0, 2))
+    assert np.array_equal(bins[known], ref["fws_genome"][known])
+    assert np.array_equal(got["bin_variants"], ref["fws_genome"].sum(axis=2)[0])
+    want, want_rows = O.fws_bins(pop, 5, fws.FWS_BINS)
+    assert np.array_equal(got["bin_variants"], want_rows)
+    assert np.array_equal(got["genome_bins"][:, :, 1:], want[:, :, 1:3])
+    assert np.array_equal(got["genome_bins"][:, :, 0], want[:, :, 0] + want[:, :, 3])
+    m = (ref["fws_variant_present"] == 1) & ordinary
+    assert np.array_equal(got["present"][ordinary], (ref["fws_variant_present"] == 1)[ordinary])
     assert np.array_equal(got["variant_summary"][m].astype(np.uint64), ref["fws_variant"][m])
+    if pop.n_multi:
+        has = ~np.isnan(pop.multi_af).all(axis=0)
+        n_slots = np.where(has.any(axis=1), 3 - np.argmax(has[:, ::-1], axis=1), 0)
+        sel = (np.arange(3)[None, :] < n_slots[:, None]) & ~(pop.multi_cells == 0xFF).any(axis=1)[:, None]
+        present = ref["fws_multi_variant_present"] == 1
+        assert np.array_equal(got["multi_present"][sel], present[sel])
+        sel &= present
+        assert np.array_equal(got["multi_variant_summary"][sel].astype(np.uint64), ref["fws_multi_variant"][sel])
+        # all alleles, no presence filter: one bin over everything = every ordinary row and every listed allele that has an AF
+        allc, rows = gpu.binned_genome_counts([0.0], [2.0], pop=5, present_only=False)
+        assert int(rows[0]) == int((~np.isnan(pop.af[5][ordinary])).sum()) + int((~np.isnan(pop.multi_af[5])).sum())
+        w2, _ = O.fws_bins(pop, 5, [(0.0, 2.0)], present_only=False)
+        assert np.array_equal(allc, w2)
     # HeteroHomoZygous::updateVariantAnalysisType run by the harness over every offset of every genome
-    _, gc = gpu.allele_count()
-    hh = fws.hetero_homo_summary(gc)
-    want = ref["hetero_homo"]       # total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef
-    for j, key in enumerate(["total_variants", "snp_count", "indel_count", "homozygous_minor_alleles", "heterozygous_minor_alleles",
-                             "heterozygous_reference_minor_alleles", "homozygous_reference_alleles"]):
-        assert np.array_equal(hh[key], want[:, j]), key
+    want_hh = ref["hetero_homo"]       # total, snp, indel, homMinor, hetMinor, hetRefMinor, homRef
+    assert np.array_equal(gpu.hetero_homo(), want_hh)
+    if not pop.n_multi:
+        _, gc = gpu.allele_count()
+        hh = fws.hetero_homo_summary(gc)
+        for j, key in enumerate(["total_variants", "snp_count", "indel_count", "homozygous_minor_alleles", "heterozygous_minor_alleles",
+                                 "heterozygous_reference_minor_alleles", "homozygous_reference_alleles"]):
+            assert np.array_equal(hh[key], want_hh[:, j]), key
 
 
 @pytest.mark.parametrize("n,l,miss,spectrum", [(131, 5000, 0.01, "sfs"), (500, 3000, 0.0, "dense"), (2504, 20000, 0.001, "sfs")])
