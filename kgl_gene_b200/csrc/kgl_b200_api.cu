@@ -124,6 +124,7 @@ struct kgl_b200_ctx {
     unsigned long long* totals_fx() const { return reinterpret_cast<unsigned long long*>(acc.p + kTotalsOff); }
     unsigned long long* ecorr_fx() const { return reinterpret_cast<unsigned long long*>(acc.p + kEcorrOff); }
     uint32_t* nz_rare(uint64_t npad) const { return reinterpret_cast<uint32_t*>(acc.p + kEcorrOff + npad * 16); }
+    double fx = 0.0;        // fixed-point scale of this set's sums (fx_scale_for the rows of the selection window it was prepared for)
     void release() { flags16.release(); sum64.release(); selw.release(); acc.release(); }
   } prep[2];
   int par = 0;                                  // the set the current selection was prepared into
@@ -397,7 +398,10 @@ int ensure_prepared(kgl_b200_ctx* c, bool want_w0 = false, bool want_selw = fals
   }
   KGL_CUDA(c, cudaMemsetAsync(S.acc.p, 0, acc_bytes, ps));
   const uint4* packed = reinterpret_cast<const uint4*>(c->d_packed.p);
-  const double fx = fx_scale_for(L);
+  // at most one term per row of the selection window: a narrow window of a long contig keeps its low-order bits
+  const uint64_t window_rows = c->sel_row_hi == ~0ull ? L : std::min<uint64_t>(L, c->sel_row_hi) - std::min<uint64_t>(L, c->sel_row_lo);
+  const double fx = fx_scale_for(std::max<uint64_t>(window_rows, 1));
+  S.fx = fx;
 #define KGL_PREP(W0, SELW)                                                                                                          \
   k_locus_prepare<W0, SELW><<<nb, kPrepThreads, 0, ps>>>(c->d_af.p, c->d_sel.p, L, c->padded_rows, n_tiles, (int)c->n_pop,         \
       S.flags16.p, S.sum64.p, SELW ? S.selw.p : nullptr, c->n_words, packed, (uint32_t)c->units, c->d_popmask.p,                   \
@@ -520,7 +524,7 @@ int mark_tail(kgl_b200_ctx* c, bool join) {
 }
 
 DenseTotals dense_totals(const kgl_b200_ctx* c, const kgl_b200_ctx::PrepSet& S) {
-  const double fx = fx_scale_for(c->L);
+  const double fx = S.fx > 0.0 ? S.fx : fx_scale_for(c->L);      // a set that was never prepared: the totals are not read
   return DenseTotals{S.totals_fx(), 1.0 / fx, 128.0 / fx};
 }
 
@@ -602,7 +606,7 @@ int launch_count(kgl_b200_ctx* c, bool raw, bool want_locus_counts, bool want_ge
   const uint16_t* fl = mo ? mo->flags16 : (raw ? nullptr : c->prep[c->par].flags16.p);
   const kgl_b200_ctx::PrepSet& S = c->prep[c->par];
   const bool prepared = !raw && !mo;
-  const double fx = fx_scale_for(c->L);
+  const double fx = prepared ? S.fx : fx_scale_for(c->L);
   if (indexed) {
     // the tail runs on its own stream, behind this pass's streaming kernel
     KGL_CUDA(c, cudaEventRecord(c->stream_done[c->cbuf], c->stream));
