@@ -3,6 +3,8 @@ cells, missing frequencies, multi-allelic loci, frequency pokes (p = 1, p = 0.5,
 spacing, AF range) are all drawn at random from a fixed seed. Everything the hot path returns is compared: selection bits,
 allele counts, class counts (bit-exact), expected sums, the four estimators, logLikelihood on a grid, the CalcFWS bins, the
 hetero/homo records, pairwise IBS and the dosage Gram matrix. Sizes keep the oracle at a fraction of a second per case."""
+import os
+
 import numpy as np
 import pytest
 
@@ -55,7 +57,10 @@ def draw_case(rng):
     return kw, pop, sel_kw
 
 
-@pytest.mark.parametrize("seed", [11, 23, 37, 41])
+SEEDS = [int(x) for x in os.environ.get("KGL_FUZZ_SEEDS", "11,23,37,41").split(",")]      # a longer campaign: KGL_FUZZ_SEEDS=1,2,3,...
+
+
+@pytest.mark.parametrize("seed", SEEDS)
 def test_random_populations_match_oracle(gpu, seed):
     from kgl_gene_b200 import fws
     rng = np.random.default_rng(seed)
@@ -85,13 +90,23 @@ def test_random_populations_match_oracle(gpu, seed):
             assert np.array_equal(c_got, c_want), (tag, algo)
             # the expected sums are 64-bit fixed-point sums (quantum 2^-(62 - log2 of the window's rows)): a sum that is
             # itself below 1e-6 is compared on that scale
-            assert rel_err(f_got, f_want, floor=1e-6) < TIGHT, (tag, algo)
+            assert rel_err(f_got, f_want, floor=1e-6) < 1e-10, (tag, algo)
             a, b = got["inbred_allele_sum"][has_terms], want["inbred_allele_sum"][has_terms]
             assert np.array_equal(np.isnan(a), np.isnan(b)), (tag, algo)
             fin = np.isfinite(b)
             assert np.array_equal(np.isfinite(a), fin), (tag, algo)
             if fin.any():
-                assert np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-3)) < 1e-8, (tag, algo)
+                bad = np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-3) >= 1e-8
+                if algo == "Loglikelihood" and bad.any():
+                    # a handful of loci: the objective can be flat where its terms are clamped, or monotone, and then has many
+                    # maximisers -- the answer must be as good as the oracle's, not the same point
+                    idx = np.flatnonzero(has_terms)[fin][bad]
+                    for g in idx:
+                        ll = O.loglik_grid(pop, sel, np.array([got["inbred_allele_sum"][g], want["inbred_allele_sum"][g]]))[g]
+                        assert ll[0] >= ll[1] - 1e-9 * max(1.0, abs(ll[1])), (tag, algo, int(g), ll)
+                    assert int(sel.sum(axis=1).max()) <= 64, (tag, "several maximisers on a selection of this size")
+                else:
+                    assert not bad.any(), (tag, algo)
         grid = np.array([-0.3, 0.0, 0.11, 0.6])
         g_got, g_want = gpu.loglik_grid(grid)[has_terms], O.loglik_grid(pop, sel, grid)[has_terms]
         fin = np.isfinite(g_want)
