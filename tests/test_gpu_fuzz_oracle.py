@@ -35,8 +35,12 @@ def sel_bits(sel):
 
 def draw_case(rng):
     from kgl_gene_b200.synth import add_multi_allelic, make_population
-    n = int(rng.choice([1, 2, 31, 64, 65, 100, 129, 200, 449, 513]))
-    l = int(rng.choice([1, 5, 63, 64, 257, 1000, 3000, 8000, 20000]))
+    if WIDE:
+        n = int(rng.choice([700, 1500, 2504, 2561, 4100]))
+        l = int(rng.choice([4097, 30000, 120000]))
+    else:
+        n = int(rng.choice([1, 2, 31, 64, 65, 100, 129, 200, 449, 513]))
+        l = int(rng.choice([1, 5, 63, 64, 257, 1000, 3000, 8000, 20000]))
     kw = dict(n_genomes=n, n_loci=l, seed=int(rng.integers(1, 10**6)), spectrum=str(rng.choice(["sfs", "dense"])),
               grouped=bool(rng.integers(0, 2)), unphased=bool(rng.integers(0, 3) == 0),
               missing_rate=float(rng.choice([0.0, 0.002, 0.03])), missing_af_rate=float(rng.choice([0.0, 0.03])))
@@ -57,6 +61,8 @@ def draw_case(rng):
     return kw, pop, sel_kw
 
 
+WIDE = os.environ.get("KGL_FUZZ_WIDE") == "1"        # thousands of genomes (the sliced streaming kernel, many CTAs): seconds of oracle per case
+CASES_PER_SEED = 4 if WIDE else 25
 SEEDS = [int(x) for x in os.environ.get("KGL_FUZZ_SEEDS", "11,23,37,41").split(",")]      # a longer campaign: KGL_FUZZ_SEEDS=1,2,3,...
 
 
@@ -64,7 +70,7 @@ SEEDS = [int(x) for x in os.environ.get("KGL_FUZZ_SEEDS", "11,23,37,41").split("
 def test_random_populations_match_oracle(gpu, seed):
     from kgl_gene_b200 import fws
     rng = np.random.default_rng(seed)
-    for case in range(25):
+    for case in range(CASES_PER_SEED):
         kw, pop, sel_kw = draw_case(rng)
         tag = (seed, case, kw, pop.n_multi, sel_kw)
         sel = O.select_all_pops(pop, **sel_kw)
