@@ -220,3 +220,51 @@ def test_vcf_ingest_equals_the_reference_vcf_parser(tmp_path):
     absent = [g for g in range(len(names)) if g not in cols]
     for rows in got.values():
         assert all(rows[g] == [] for g in absent)
+
+
+@needs_harness
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("KGL_FUZZ_SEEDS", "5,6,7").split(",")])
+def test_plugin_csv_on_random_populations_and_parameters(tmp_path, seed):
+    """The INBREED_B200 analysis against the unmodified INBREED analysis on populations and parameter blocks drawn at random
+    (phase, missing cells and frequencies, multi-allelic sites, sampling distance, window size, frequency range, offsets range):
+    same header, same window columns, same genomes, same class counts, coefficients to the digits the reference prints."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    rng = np.random.default_rng(seed)
+    n, l = int(rng.choice([40, 96, 130])), int(rng.choice([1500, 4000, 9000]))
+    pop, _ = make_population(n, l, seed=int(rng.integers(1, 10**6)), spectrum=str(rng.choice(["sfs", "dense"])),
+                             missing_rate=float(rng.choice([0.0, 0.01])), missing_af_rate=float(rng.choice([0.0, 0.03])),
+                             grouped=bool(rng.integers(0, 2)), unphased=bool(rng.integers(0, 3) == 0))
+    if rng.integers(0, 2):
+        add_multi_allelic(pop, int(rng.choice([20, 200])), seed=int(rng.integers(1, 10**6)))
+    args = ["--algo", "Simple,RitlandLocus,Loglikelihood", "--spacing", str(int(rng.choice([0, 20, 300]))),
+            "--count", str(int(rng.choice([150, 600, 5000]))), "--min-af", str(float(rng.choice([0.0, 0.01, 0.1]))),
+            "--max-af", str(float(rng.choice([1.0, 0.5])))]
+    if rng.integers(0, 2):
+        lo, hi = sorted(rng.integers(0, l, size=2).tolist())
+        args += ["--lower", str(int(pop.offsets[lo])), "--upper", str(int(pop.offsets[hi]))]
+    work = run_harness(str(tmp_path), pop, *args)
+    n_values = n_far = 0
+    for algo, atol in (("Simple", 1e-9), ("RitlandLocus", 1e-9), ("Loglikelihood", 5e-6)):
+        ref_csv = os.path.join(work, "INBREED", f"harness_out_{algo}.csv")
+        new_csv = os.path.join(work, "INBREED_B200", f"harness_out_{algo}.csv")
+        if not os.path.exists(ref_csv):
+            # no window: the first count-limited window already ends at or beyond UpperOffset (kga_analysis_inbreed_diploid.cpp:53),
+            # writePedResults has nothing to write (kga_analysis_inbreed_output.cpp:189) -- the drop-in must not write either
+            assert not os.path.exists(new_csv), (seed, args, algo)
+            continue
+        h_ref, c_ref, r_ref = read_csv(ref_csv)
+        h_new, c_new, r_new = read_csv(new_csv)
+        assert h_ref == h_new and c_ref == c_new, (seed, args, algo)
+        assert sorted(r_ref) == sorted(r_new), (seed, args, algo)
+        for g, (meta, vals) in r_ref.items():
+            meta2, vals2 = r_new[g]
+            assert meta == meta2 and len(vals) == len(vals2), (seed, args, algo, g)
+            close = np.isclose(vals2, vals, rtol=2e-6, atol=atol, equal_nan=True)
+            if algo == "Loglikelihood" and pop.unphased:
+                # parity unpinned (DESIGN 8): on unphased populations the reference's Nelder-Mead run regularly stops at the bound
+                # or at a lower likelihood than the maximiser (checked against the oracle's objective); counted, not compared
+                n_values += close.size; n_far += int((~close).sum())
+            else:
+                assert close.all(), (seed, args, algo, g, vals, vals2)
+    assert n_far <= 0.1 * n_values, (seed, args, n_far, n_values)
