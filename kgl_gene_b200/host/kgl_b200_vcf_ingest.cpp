@@ -49,7 +49,7 @@ namespace {
 
 // One ALT allele of a record.
 struct Alt {
-  char base = 0;                        // the alternate base of a SNP, 0 otherwise (indel, abstract "<...>", "*", ".")
+  char base = 0;                        // the alternate base of a SNP as DNA5 reads it (A C G T N), 0 otherwise (indel, abstract "<...>", ".")
   float af[kPops];
 };
 
@@ -66,6 +66,17 @@ struct Line {
 };
 
 // One allele token -> alt index (0 = reference); returns false when the token is not a number.
+// DNA5::convertChar (kgl_alphabet_dna5.cpp:55-90): case folded, U read as T, anything that is not a nucleotide becomes N.
+inline char dna5_base(char ch) {
+  switch (ch & ~0x20) {
+    case 'A': return 'A';
+    case 'C': return 'C';
+    case 'G': return 'G';
+    case 'T': case 'U': return 'T';
+    default: return ch == 0 ? 0 : 'N';
+  }
+}
+
 inline bool allele_index(const char* b, const char* e, uint32_t& out) {
   if (b == e) return false;
   if (e - b == 1 && (*b == '.' || *b == '-')) { out = 0; return true; }
@@ -154,8 +165,11 @@ void parse_line(const char* b, const char* e, uint64_t n_genomes, uint64_t row_b
       const char* comma = static_cast<const char*>(std::memchr(a, ',', (size_t)(alt_end - a)));
       const char* ae = comma ? comma : alt_end;
       Alt alt;
-      const bool snp = ln.ref != 0 && ae - a == 1 && *a != '.' && *a != '<' && *a != '*' && *a != ln.ref;
-      alt.base = snp ? *a : 0;
+      // a one-character ALT is a SNP of the variant DB whatever the character: StringDNA5 folds case, reads U as T and turns
+      // everything else -- IUPAC codes, the spanning-deletion "*" -- into N (DNA5::convertChar, kgl_alphabet_dna5.cpp:55-90)
+      const char alt_base = ae - a == 1 ? dna5_base(*a) : 0;
+      const bool snp = ln.ref != 0 && alt_base != 0 && *a != '.' && alt_base != dna5_base(ln.ref);
+      alt.base = snp ? alt_base : 0;
       ln.alts.push_back(alt);
       if (!comma) break;
       a = comma + 1;
@@ -412,7 +426,17 @@ int kgl_b200_vcf_ingest(const char* path, int unphased, int n_threads, kgl_b200_
     for (size_t i = 0; i < n_lines; ++i) {
       Line& ln = parsed[i];
       if (!ln.usable) { ++v->stats.skipped_non_snp; continue; }
-      if (!open.lines.empty() && open.lines.front()->offset != ln.offset) { emit_group(*v, open, unphased != 0); open.lines.clear(); held.clear(); }
+      if (!open.lines.empty() && open.lines.front()->offset != ln.offset) {
+        if (ln.offset < open.lines.front()->offset) {
+          // the locus table must be sorted and unique (kgl_b200_select_loci searches it); the variant DB sorts by itself, a
+          // streamed ingest cannot -- refuse instead of handing over a table that selects the wrong loci
+          const std::string msg = "VCF is not sorted by POS: record at POS " + std::to_string((unsigned long long)ln.offset + 1) +
+                                  " follows POS " + std::to_string((unsigned long long)open.lines.front()->offset + 1);
+          gzclose(gz); delete v;
+          return fail(msg);
+        }
+        emit_group(*v, open, unphased != 0); open.lines.clear(); held.clear();
+      }
       open.lines.push_back(&ln);
     }
     // the open group may continue in the next block: its lines move out of `parsed`, which the next block overwrites

@@ -21,7 +21,10 @@
  *     fields (indexed by the ALT's position, kgl_variant_db_freq.cpp:89-92) and one byte per genome naming the allele of
  *     phase A, then phase B (the order of addVariants, 1000_impl.cpp:118-139). Non-SNP alleles vanish from the genome's
  *     offset array (SNPFilter, kga_analysis_inbreed_freq.cpp:436); a POS without any SNP allele is left out.
- *   - offset = POS - 1 (kgl offsets are 0-based).
+ *   - A one-character ALT is a SNP allele whatever the character: the variant DB stores it as DNA5 (case folded, U = T, IUPAC
+ *     codes and the spanning deletion "*" = N, kgl_alphabet_dna5.cpp:55-90), so "*" next to a base is a second allele slot.
+ *   - offset = POS - 1 (kgl offsets are 0-based). The records must be sorted by POS (the variant DB sorts by itself; the locus
+ *     table of a streamed ingest is searched by kgl_b200_select_loci): a POS below its predecessor's is an error.
  *   - AF columns: INFO AFR_AF, AMR_AF, EAS_AF, EUR_AF, SAS_AF, AF (DataSourceEnum::Genome1000, kgl_variant_db_freq.h:87-92),
  *     parsed with strtof like the reference's std::stof (kgl_variant_factory_vcf_parse_info.cpp:232); absent -> NaN.
  * Plain text or gzip (zlib), streamed in blocks: memory = the outputs + one block of parsed lines. Lines are parsed by a

@@ -193,9 +193,9 @@ def test_vcf_ingest_equals_the_reference_vcf_parser(tmp_path):
     pop.multi_af[5][nan] = rng.uniform(0.01, 0.3, size=int(nan.sum())).astype(np.float32)
     base = int(pop.offsets[-1]) + 100
     extra = [
-        (5, f"22\t{base}\t.\tC\tT\t100\tPASS\tAF=0.31\tGT\t" + "\t".join(["0|1", "1|1", "0|0"] * 20)),          # repeated POS:
-        (5, f"22\t{base}\t.\tC\tA\t100\tPASS\tAF=0.11\tGT\t" + "\t".join(["0|0", "0|0", "1|0"] * 20)),          #   one offset, two alleles
-        (5, f"22\t{base + 10}\t.\tA\tG\t100\tPASS\tAF=0.125;DP=7\tGT:DP\t" + "\t".join(["1|0:3", ".|1:1", "0|0:9"] * 20)),
+        (599, f"22\t{base}\t.\tC\tT\t100\tPASS\tAF=0.31\tGT\t" + "\t".join(["0|1", "1|1", "0|0"] * 20)),          # repeated POS:
+        (599, f"22\t{base}\t.\tC\tA\t100\tPASS\tAF=0.11\tGT\t" + "\t".join(["0|0", "0|0", "1|0"] * 20)),          #   one offset, two alleles
+        (599, f"22\t{base + 10}\t.\tA\tG\t100\tPASS\tAF=0.125;DP=7\tGT:DP\t" + "\t".join(["1|0:3", ".|1:1", "0|0:9"] * 20)),
     ]
     path = str(tmp_path / "pin.vcf")
     write_vcf(pop, path, extra_lines=extra)
@@ -220,6 +220,101 @@ def test_vcf_ingest_equals_the_reference_vcf_parser(tmp_path):
     absent = [g for g in range(len(names)) if g not in cols]
     for rows in got.values():
         assert all(rows[g] == [] for g in absent)
+
+
+def test_vcf_ingest_refuses_an_unsorted_file(tmp_path):
+    """The locus table must be sorted and unique (select_loci searches it): a record whose POS lies before the previous one is an
+    error, not a silently unsorted table (the reference's variant DB sorts by itself, a streamed ingest cannot)."""
+    from kgl_gene_b200.synth import make_population
+    from kgl_gene_b200.vcf import ingest_vcf, write_vcf
+    pop, _ = make_population(5, 40, seed=3)
+    late = f"22\t{int(pop.offsets[3]) + 2}\t.\tA\tG\t100\tPASS\tAF=0.2\tGT\t" + "\t".join(["0|1"] * 5)
+    path = str(tmp_path / "unsorted.vcf")
+    write_vcf(pop, path, extra_lines=[(20, late)])
+    with pytest.raises(RuntimeError, match="not sorted by POS"):
+        ingest_vcf(path, n_threads=1)
+
+
+KINDS = os.environ.get("KGL_VCF_FUZZ_KINDS", "indel,symbolic,format,noaf,mnp,mixed_alt,star,lower,three,unphased_gt,haploid").split(",")
+
+
+@needs_harness
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("KGL_VCF_FUZZ_SEEDS", "1,2,3,4,5,6").split(",")])
+def test_vcf_ingest_on_random_files(tmp_path, seed):
+    """N2 on VCF files drawn at random: population shape, missing calls, multi-allelic sites, and spliced-in records of the kinds
+    a 1000 Genomes file holds -- two SNP records at one POS (one genome may carry both alleles), an indel record between them,
+    indels, MNPs, symbolic and spanning-deletion ("*") alleles, lower-case bases, three alternate alleles, an ALT list that mixes a SNP
+    with an indel, '/'-separated and haploid calls, extra FORMAT fields with half-missing calls, a record without AF.
+    kgl_b200_vcf_ingest against the reference's own parser (compiled into the harness), allele by allele for every genome."""
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    from kgl_gene_b200.vcf import ingest_vcf, write_vcf
+    rng = np.random.default_rng(seed)
+    n, l = int(rng.choice([3, 20, 60])), int(rng.choice([50, 300, 600]))
+    pop, _ = make_population(n, l, seed=int(rng.integers(1, 10**6)), missing_rate=float(rng.choice([0.0, 0.01])))
+    n_multi = int(rng.choice([0, 5, 40]))
+    if n_multi:
+        add_multi_allelic(pop, min(n_multi, l // 4), seed=int(rng.integers(1, 10**6)), unknown_rate=0.0, three_rate=0.0)
+        nan = np.isnan(pop.multi_af[5]) & (np.arange(3)[None, :] < 2)
+        pop.multi_af[5][nan] = rng.uniform(0.01, 0.3, size=int(nan.sum())).astype(np.float32)
+
+    def gts(choices):
+        return "\t".join(rng.choice(choices, size=n))
+
+    def pair():        # two records at one POS: per genome a combination with at most two alternate alleles in total
+        combos = rng.choice(5, size=n)
+        first = ["0|1", "1|1", "0|0", "0|0", "0|1"]
+        second = ["0|0", "0|0", "1|0", "0|0", "1|0"]
+        return "\t".join(first[c] for c in combos), "\t".join(second[c] for c in combos)
+
+    extra = []
+    base = int(pop.offsets[-1]) + 100
+    for i in range(int(rng.integers(1, 4))):
+        a, b = pair()
+        pos = base + 40 * i
+        extra.append((l - 1, f"22\t{pos}\t.\tC\tT\t100\tPASS\tAF=0.31\tGT\t{a}"))
+        if rng.integers(0, 2):
+            extra.append((l - 1, f"22\t{pos}\t.\tCA\tC\t100\tPASS\tAF=0.21\tGT\t" + gts(["0|1", "0|0"])))
+        extra.append((l - 1, f"22\t{pos}\t.\tC\tA\t100\tPASS\tAF=0.11\tGT\t{b}"))
+    for kind in rng.choice(KINDS, size=int(rng.integers(2, 6))):
+        row = int(rng.integers(0, l))
+        pos = int(pop.offsets[row]) + 1 + int(rng.integers(1, 9))         # between two loci of the generated population
+        line = {"indel": f"22\t{pos}\t.\tAT\tA\t100\tPASS\tAF=0.2\tGT\t" + gts(["0|1", "1|1", "0|0"]),
+                "symbolic": f"22\t{pos}\t.\tA\t<CN0>\t100\tPASS\tAF=0.2\tGT\t" + gts(["0|1", "1|1", "0|0"]),
+                "format": f"22\t{pos}\t.\tA\tG\t100\tPASS\tAF=0.125;DP=7\tGT:DP\t" + gts(["1|0:3", ".|1:1", "0|0:9"]),
+                "noaf": f"22\t{pos}\t.\tA\tG\t100\tPASS\tDP=7\tGT\t" + gts(["1|0", "0|1", "0|0"]),
+                "mnp": f"22\t{pos}\t.\tAC\tGT\t100\tPASS\tAF=0.3\tGT\t" + gts(["1|0", "0|1", "0|0"]),
+                "mixed_alt": f"22\t{pos}\t.\tA\tG,AT\t100\tPASS\tAF=0.3,0.1\tGT\t" + gts(["1|0", "0|2", "0|0", "1|1", "2|0"]),
+                "star": f"22\t{pos}\t.\tA\tG,*\t100\tPASS\tAF=0.3,0.1\tGT\t" + gts(["1|0", "0|2", "0|0", "1|1"]),
+                "lower": f"22\t{pos}\t.\ta\tg\t100\tPASS\tAF=0.3\tGT\t" + gts(["1|0", "0|1", "0|0"]),
+                "three": f"22\t{pos}\t.\tA\tG,C,T\t100\tPASS\tAF=0.3,0.1,0.05\tGT\t" + gts(["1|0", "0|2", "0|0", "3|0", "0|3"]),
+                "unphased_gt": f"22\t{pos}\t.\tA\tG\t100\tPASS\tAF=0.3\tGT\t" + gts(["1/0", "0/1", "0/0", "1/1"]),
+                "haploid": f"22\t{pos}\t.\tA\tG\t100\tPASS\tAF=0.3\tGT\t" + gts(["1", "0", "0|1"])}[str(kind)]
+        if row < l - 1 and not any(e[1].split("\t")[1] == str(pos) for e in extra):      # after the last row come the pairs above
+            extra.append((row, line))
+    extra.sort(key=lambda e: (e[0], int(e[1].split("\t")[1])))                              # a VCF is sorted by POS
+    path = str(tmp_path / "random.vcf")
+    write_vcf(pop, path, extra_lines=extra)
+    ours, names, _, st = ingest_vcf(path, n_threads=int(rng.choice([1, 3])))
+    work = os.path.join(str(tmp_path), "work")
+    env = dict(os.environ, KGL_REF_LOG=os.path.join(str(tmp_path), "harness.log"))
+    r = subprocess.run([HARNESS, path, work, "--vcf"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = FlatPopulation.read(os.path.join(work, "flattened.flat"))
+    ids = [ln.strip() for ln in open(os.path.join(work, "flattened_genomes.txt"))]
+    cols = [names.index(i) for i in ids]
+
+    def key(rows):      # NaN ("no AF") compares equal to itself
+        return [None if r is None else [-1.0 if x != x else x for x in r] for r in rows]
+
+    want, got = _carried_alleles(ref, 5), _carried_alleles(ours, 5)
+    assert set(want) <= set(got), (seed, sorted(set(want) - set(got))[:5])
+    assert np.all(np.diff(ours.offsets.astype(np.int64)) > 0)                    # the locus table stays sorted and unique
+    for offset, rows in got.items():
+        if offset in want:
+            assert key([rows[c] for c in cols]) == key(want[offset]), (seed, offset)
+        else:
+            assert all(r == [] for r in rows), (seed, offset)
 
 
 @needs_harness
