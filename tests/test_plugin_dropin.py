@@ -62,6 +62,39 @@ def test_flattener_reproduces_the_flat_population(tmp_path, unphased):
 
 
 @needs_harness
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("KGL_FLATTEN_FUZZ_SEEDS", "1,2,3,4,5,6,7,8").split(",")])
+def test_flattener_on_random_populations(tmp_path, seed):
+    """The flattener against the reference containers on populations drawn at random: shape, spectrum, phase, missing cells and
+    frequencies, super-population order, multi-allelic sites (with alleles outside the list and cells of more than two variants).
+    Everything it emits -- offsets, frequency bits, codes, side structures -- bit for bit what the containers were built from."""
+    from kgl_gene_b200.flatfile import FlatPopulation
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    rng = np.random.default_rng(seed)
+    n, l = int(rng.choice([1, 7, 64, 65, 150])), int(rng.choice([1, 40, 700, 2000]))
+    pop, _ = make_population(n, l, seed=int(rng.integers(1, 10**6)), spectrum=str(rng.choice(["sfs", "dense"])),
+                             missing_rate=float(rng.choice([0.0, 0.02])), missing_af_rate=float(rng.choice([0.0, 0.05])),
+                             grouped=bool(rng.integers(0, 2)), unphased=bool(rng.integers(0, 2)))
+    if l >= 40 and rng.integers(0, 2):
+        add_multi_allelic(pop, int(rng.choice([1, l // 10])), seed=int(rng.integers(1, 10**6)))
+    work = run_harness(str(tmp_path), pop, "--no-reference", "--no-b200")
+    got = FlatPopulation.read(os.path.join(work, "flattened.flat"))
+    ids = [ln.strip() for ln in open(os.path.join(work, "flattened_genomes.txt"))]
+    cols = np.array([int(i[1:]) for i in ids], dtype=np.int64)
+    carries = (pop.codes() != 0).any(axis=0)
+    assert np.array_equal(cols, np.flatnonzero(carries))          # genomes without any non-reference allele never enter a PopulationDB
+    assert np.array_equal(got.offsets, pop.offsets)
+    assert np.array_equal(got.af.view(np.uint32), pop.af.view(np.uint32))
+    assert np.array_equal(got.superpop, pop.superpop[cols])
+    assert got.unphased == pop.unphased or not carries.any()
+    assert np.array_equal(got.codes(), pop.codes()[:, cols])
+    assert got.n_multi == pop.n_multi
+    if pop.n_multi:
+        assert np.array_equal(got.multi_rows, pop.multi_rows)
+        assert np.array_equal(got.multi_af.view(np.uint32), pop.multi_af.view(np.uint32))
+        assert np.array_equal(got.multi_cells, pop.multi_cells[:, cols])
+
+
+@needs_harness
 @pytest.mark.gpu
 @pytest.mark.parametrize("algo,rtol,atol", [("Simple", 2e-6, 1e-9), ("RitlandLocus", 2e-6, 1e-9),
                                             # the reference's optimiser stops at xtol_abs = 1e-6 (kga_analysis_inbreed_calc.cpp:131-143)
