@@ -189,6 +189,24 @@ def test_pfemp_hetero_homo_csv_equals_reference_writer(tmp_path, unphased):
     assert np.count_nonzero(fis) > 100 and het_diff.sum() > 0          # F_IS is exercised; so is "Het Diff Minor (a;b)"
 
 
+@needs_harness
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [int(x) for x in os.environ.get("KGL_FUZZ_SEEDS", "5,6,7").split(",")])
+def test_pfemp_hetero_homo_csv_on_random_populations(tmp_path, seed):
+    """HeteroHomoB200 against the reference's HeteroHomoZygous writer on populations drawn at random: the two CSV files are identical."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    rng = np.random.default_rng(seed)
+    n, l = int(rng.choice([9, 64, 170, 300])), int(rng.choice([50, 800, 2500]))
+    pop, _ = make_population(n, l, seed=int(rng.integers(1, 10**6)), spectrum=str(rng.choice(["sfs", "dense"])),
+                             missing_rate=float(rng.choice([0.0, 0.01, 0.05])), unphased=bool(rng.integers(0, 2)), grouped=bool(rng.integers(0, 2)))
+    if l >= 800 and rng.integers(0, 3):
+        add_multi_allelic(pop, int(rng.choice([3, l // 10])), seed=int(rng.integers(1, 10**6)), three_rate=0.0)
+    work = run_harness(str(tmp_path), pop, "--pfemp")
+    ref = open(os.path.join(work, "PFEMP", "hetero_homo.csv")).read().splitlines()
+    new = open(os.path.join(work, "PFEMP_B200", "hetero_homo.csv")).read().splitlines()
+    assert len(ref) > 1 and ref == new, (seed, n, l, pop.n_multi, [i for i, (a, b) in enumerate(zip(ref, new)) if a != b][:3])
+
+
 def _carried_alleles(pop, col):
     """{offset: list per genome of the sorted frequency values (column `col`) of the alleles the genome carries there}."""
     out = {}
