@@ -340,9 +340,13 @@ int kgl_b200_vcf_ingest(const char* path, int unphased, int n_threads, kgl_b200_
   auto v = new kgl_b200_vcf();
   int nt = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
 
-  constexpr size_t kBlock = 32u << 20;                         // text per block
+  size_t kBlock = 32u << 20;                                   // text per block
+  if (const char* e = std::getenv("KGL_B200_VCF_BLOCK_BYTES")) {   // test hook: small blocks put the block boundaries everywhere
+    const unsigned long long b = std::strtoull(e, nullptr, 10);
+    if (b >= 64) kBlock = (size_t)b;
+  }
   std::string block, carry;
-  std::vector<char> buf(8u << 20);
+  std::vector<char> buf(std::min<size_t>(8u << 20, kBlock));
   bool have_header = false, eof = false;
   std::vector<Line> parsed;
   std::vector<std::unique_ptr<Line>> held;                     // lines of a POS group that a block boundary cuts
@@ -352,13 +356,13 @@ int kgl_b200_vcf_ingest(const char* path, int unphased, int n_threads, kgl_b200_
     // ---- next block: the carried-over partial line + fresh text, cut at the last line end ----
     block.swap(carry);
     carry.clear();
-    while (block.size() < kBlock) {
+    do {                                                       // at least one read: a line longer than a block keeps growing
       const int n = gzread(gz, buf.data(), (unsigned)buf.size());
       if (n < 0) { int e = 0; const std::string m = std::string("read error: ") + gzerror(gz, &e); gzclose(gz); delete v; return fail(m); }
       if (n == 0) { eof = true; break; }
       block.append(buf.data(), (size_t)n);
       total_bytes += (size_t)n;
-    }
+    } while (block.size() < kBlock);
     if (!eof) {
       const size_t last_nl = block.rfind('\n');
       if (last_nl == std::string::npos) { carry.swap(block); continue; }
