@@ -164,3 +164,73 @@ def test_narrow_window_of_a_long_contig_keeps_small_sums(gpu):
     c_got, f_got = results_matrix(res)
     c_want, f_want = results_matrix(O.inbreed(pop, sel, "Simple"))
     assert np.array_equal(c_got, c_want) and rel_err(f_got, f_want, floor=1e-6) < TIGHT
+
+
+def test_misuse_is_an_error_code_and_the_context_survives():
+    """Calls out of order or with arguments that do not fit: every one returns an error code with a message (KglError through the
+    binding), none crashes or hangs, and the same context then runs a correct sequence to the oracle's results."""
+    import ctypes as C
+    from kgl_gene_b200.capi import KglB200, KglError
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    ctx = KglB200(0)
+    try:
+        pop, _ = make_population(70, 900, seed=5, missing_rate=0.01)
+        # nothing uploaded yet
+        for call in (lambda: ctx.select_loci(), lambda: ctx.allele_count(), lambda: ctx.inbreed("Simple"), lambda: ctx.count_and_inbreed(),
+                     lambda: ctx.ibs(0, 1), lambda: ctx.gram(), lambda: ctx.hetero_homo(), lambda: ctx.multi_allele_count(3),
+                     lambda: ctx.binned_genome_counts([0.0], [1.0]), lambda: ctx.loglik_grid([0.0]), lambda: ctx.count_loci()):
+            with pytest.raises(KglError):
+                call()
+        # the matrix alone: no frequencies, no super-populations
+        ctx.upload_genotypes(pop.packed, pop.n_genomes)
+        for call in (lambda: ctx.select_loci(), lambda: ctx.inbreed("Simple"), lambda: ctx.binned_genome_counts([0.0], [1.0])):
+            with pytest.raises(KglError):
+                call()
+        # tables that do not fit the matrix
+        with pytest.raises(KglError):
+            ctx.upload_loci(pop.af[:, :-1], pop.offsets[:-1]); ctx.set_genome_superpop(pop.superpop); ctx.select_loci(); ctx.inbreed("Simple")
+        ctx.upload_genotypes(pop.packed, pop.n_genomes)
+        ctx.upload_loci(pop.af, pop.offsets)
+        with pytest.raises(KglError):
+            ctx.set_genome_superpop(np.full(pop.n_genomes, 6, dtype=np.uint8))                  # index out of range
+        with pytest.raises(KglError):
+            ctx.set_genome_superpop(pop.superpop[:-1]); ctx.select_loci(); ctx.count_and_inbreed()   # wrong length: a new population without a matrix
+        ctx.upload_population(pop)
+        with pytest.raises(KglError):
+            ctx.set_locus_selection(np.ones(pop.n_loci - 1, dtype=np.uint8))
+        with pytest.raises(KglError):
+            ctx.set_locus_filter(np.ones(pop.n_loci + 1, dtype=np.uint8))
+        with pytest.raises(KglError):
+            ctx.upload_multi_allelic(np.array([5, 5], dtype=np.uint32), np.zeros((6, 2, 3), np.float32), np.zeros((2, 70), np.uint8))   # not ascending
+        with pytest.raises(KglError):
+            ctx.upload_multi_allelic(np.array([pop.n_loci], dtype=np.uint32), np.zeros((6, 1, 3), np.float32), np.zeros((1, 70), np.uint8))   # beyond the table
+        scratch = np.zeros((pop.n_genomes, pop.n_genomes, 4), dtype=np.uint32)
+        raw_ibs = lambda a, b: ctx._check(ctx.lib.kgl_b200_run_ibs(ctx.h, C.c_uint64(a), C.c_uint64(b), scratch.ctypes.data_as(C.c_void_p)), "run_ibs")
+        for call in (lambda: raw_ibs(5, 3), lambda: ctx.ibs(0, pop.n_genomes + 1), lambda: ctx.binned_genome_counts([0.0], [1.0], pop=6),
+                     lambda: ctx.count_loci(pop=9), lambda: ctx.multi_allele_count(1)):
+            with pytest.raises(KglError):
+                call()
+        with pytest.raises((KglError, KeyError, ValueError)):
+            ctx.inbreed("NoSuchAlgorithm")
+        with pytest.raises(KglError):                                                            # an algorithm id the ABI does not know
+            ctx._check(ctx.lib.kgl_b200_inbreed_begin(ctx.h, C.c_int(99), None), "inbreed_begin")
+        # an empty selection is not an error: no terms, zero counts
+        ctx.select_loci(lower=10**8, upper=10**8 + 5)
+        _, res = ctx.count_and_inbreed()
+        assert int(res["total_allele_count"].sum()) == 0
+        for algo in ("RitlandLocus", "HallME", "Loglikelihood"):
+            assert int(ctx.inbreed(algo)["total_allele_count"].sum()) == 0
+        # ... and the context still computes
+        add_multi_allelic(pop, 40, seed=6)
+        ctx.upload_population(pop)
+        sel = O.select_all_pops(pop, spacing=15)
+        ctx.select_loci(spacing=15)
+        _, res = ctx.count_and_inbreed()
+        want = O.inbreed(pop, sel, "Simple")
+        assert np.array_equal(results_matrix(res)[0], results_matrix(want)[0])
+        assert rel_err(results_matrix(res)[1], results_matrix(want)[1], floor=1e-6) < 1e-10
+        got = ctx.inbreed("Loglikelihood")["inbred_allele_sum"]
+        assert np.max(np.abs(got - O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"])) < 1e-9
+        assert np.array_equal(ctx.ibs(), O.ibs(pop))
+    finally:
+        ctx.close()
