@@ -285,3 +285,174 @@ void kga::HeteroHomoB200::write_variant_results(const std::string& file_name, co
   }
 
 }
+
+
+// ---- CalcFwsB200 -----------------------------------------------------------------------------------------------------------
+
+kga::CalcFwsB200::~CalcFwsB200() {
+  if (context_ != nullptr) kgl_b200_destroy(context_);
+}
+
+std::pair<double, double> kga::CalcFwsB200::binRange(size_t bin) {
+  // 5 % steps up to one half, then everything above (CalcFWS::getFrequency, kga_analysis_PfEMP_FWS.cpp:104-145)
+  static constexpr double kEdges[FWS_FREQUENCY_ARRAY_SIZE + 1] = {0.0, 0.05, 0.10, 0.15, 0.20, 0.25, 0.30, 0.35, 0.40, 0.45, 0.5, 1.0};
+  return bin < FWS_FREQUENCY_ARRAY_SIZE ? std::pair<double, double>{kEdges[bin], kEdges[bin + 1]} : std::pair<double, double>{0.0, 0.0};
+}
+
+bool kga::CalcFwsB200::calcFwsStatistics(const std::shared_ptr<const PopulationDB>& population) {
+
+  if (context_ == nullptr) {
+    int device = 0;
+    if (const char* env = std::getenv("KGL_B200_DEVICE")) device = std::atoi(env);
+    if (kgl_b200_create(device, &context_) != KGL_B200_OK) {
+      ExecEnv::log().error("CalcFwsB200; cannot create a device context on GPU {}: {}", device, kgl_b200_last_error(nullptr));
+      context_ = nullptr;
+      return false;
+    }
+  }
+  auto check = [this](int rc, const char* what) {
+    if (rc != KGL_B200_OK) ExecEnv::log().error("CalcFwsB200; {} failed [{}]: {}", what, rc, kgl_b200_last_error(context_));
+    return rc == KGL_B200_OK;
+  };
+  auto allele_frequency = [](const Variant& variant) -> std::optional<double> {        // P7FrequencyFilter's value (kgl_variant_filter_Pf7.cpp:22-48)
+    auto info_opt = InfoEvidenceAnalysis::getTypedInfoData<std::vector<double>>(variant, "AF");
+    if (not info_opt) return std::nullopt;
+    const size_t alt_index = variant.evidence().altVariantIndex();
+    if (info_opt.value().size() != variant.evidence().altVariantCount() or info_opt.value().size() <= alt_index) return std::nullopt;
+    return info_opt.value()[alt_index];
+  };
+
+  std::set<ContigId_t> contigs;
+  for (auto const& [genome_id, genome_ptr] : population->getMap())
+    for (auto const& [contig_id, contig_ptr] : genome_ptr->getMap()) contigs.insert(contig_id);
+  const size_t population_genomes = population->getMap().size();
+  const bool unphased = population->dataSource() == DataSourceEnum::Falciparum;
+
+  // Everything is collected first: a population the matrix cannot hold leaves the maps untouched.
+  GenomeFWSMap genome_update;
+  VariantFWSMap variant_update;
+  for (auto const& [genome_id, genome_ptr] : population->getMap()) genome_update.try_emplace(genome_id, FwsFrequencyArray());
+  double lower[FWS_FREQUENCY_ARRAY_SIZE], upper[FWS_FREQUENCY_ARRAY_SIZE];
+  for (size_t b = 0; b < FWS_FREQUENCY_ARRAY_SIZE; ++b) std::tie(lower[b], upper[b]) = binRange(b);
+
+  for (auto const& contig_id : contigs) {
+
+    auto flat_opt = b200::PopulationFlattener::flattenSelf(*population, contig_id, allele_frequency, unphased);
+    if (not flat_opt) return false;
+    const b200::FlatContig& flat = flat_opt.value();
+    if (flat.non_snp_entries > 0 or flat.too_many_alleles_skipped > 0) {
+      ExecEnv::log().error("CalcFwsB200::calcFwsStatistics; contig: {} holds {} variant entries that are not SNPs and {} offsets with more than three alleles: filter the population first",
+                           contig_id, flat.non_snp_entries, flat.too_many_alleles_skipped);
+      return false;
+    }
+    const size_t N = flat.nGenomes(), L = flat.nLoci(), M = flat.nMulti();
+    if (N == 0 or L == 0) continue;
+    for (size_t i = 0; i < flat.multi_cells.size(); ++i)
+      if (flat.multi_cells[i] == 0xFF) {
+        ExecEnv::log().error("CalcFwsB200::calcFwsStatistics; contig: {}, a genome carries more than two variants at one offset", contig_id);
+        return false;
+      }
+    if (not check(kgl_b200_upload_genotypes(context_, N, L, flat.row_bytes, flat.packed.data()), "upload_genotypes")) return false;
+    if (not check(kgl_b200_upload_loci(context_, L, b200::kSuperPopCount, flat.af.data(), flat.offsets.data()), "upload_loci")) return false;
+    if (not check(kgl_b200_set_genome_superpop(context_, N, flat.superpop.data()), "set_genome_superpop")) return false;
+    if (not check(kgl_b200_upload_multi_allelic(context_, M, flat.multi_rows.data(), flat.multi_af.data(), flat.multi_cells.data()), "upload_multi_allelic")) return false;
+
+    // updateGenomeFWSMap (:72-101) for the eleven bins at once
+    std::vector<uint64_t> bins(FWS_FREQUENCY_ARRAY_SIZE * N * 4), bin_variants(FWS_FREQUENCY_ARRAY_SIZE);
+    if (not check(kgl_b200_run_binned_genome_counts(context_, 0, FWS_FREQUENCY_ARRAY_SIZE, lower, upper, 1, bins.data(), bin_variants.data()), "run_binned_genome_counts")) return false;
+    std::set<GenomeId_t> in_matrix(flat.genome_ids.begin(), flat.genome_ids.end());
+    for (size_t b = 0; b < FWS_FREQUENCY_ARRAY_SIZE; ++b) {
+      for (size_t g = 0; g < N; ++g) {
+        const uint64_t* c = bins.data() + (b * N + g) * 4;
+        AlleleSummmary& record = genome_update[flat.genome_ids[g]][b];
+        record.referenceHomozygous_ += c[0] + c[3];          // a cell with some other allele has no copy of the column's variant
+        record.minorHeterozygous_ += c[1];
+        record.minorHomozygous_ += c[2];
+      }
+      for (auto& [genome_id, freq_array] : genome_update)   // a genome without this contig: every column of the bin is hom-ref
+        if (not in_matrix.contains(genome_id)) freq_array[b].referenceHomozygous_ += bin_variants[b];
+    }
+
+    // updateVariantFWSMap (:41-70): one record per variant of the population
+    std::vector<uint32_t> locus_counts(L * 4), multi_counts(M * 3 * 3);
+    if (not check(kgl_b200_run_allele_count(context_, locus_counts.data(), nullptr), "run_allele_count")) return false;
+    if (M > 0 and not check(kgl_b200_run_multi_allele_count(context_, multi_counts.data()), "run_multi_allele_count")) return false;
+    std::vector<uint8_t> is_multi(L, 0);
+    for (uint32_t row : flat.multi_rows) is_multi[row] = 1;
+    const size_t absent = population_genomes - N;
+    auto add_variant = [&variant_update, absent](const std::shared_ptr<const Variant>& variant, uint64_t none, uint64_t one, uint64_t two) {
+      if (variant == nullptr or one + two == 0) return;      // only variants some genome carries have a column (kgl_variant_db_variant.cpp:14-30)
+      AlleleSummmary& summary = variant_update[variant->HGVS()];
+      summary.referenceHomozygous_ += none + absent;
+      summary.minorHeterozygous_ += one;
+      summary.minorHomozygous_ += two;
+    };
+    for (size_t l = 0; l < L; ++l)
+      if (not is_multi[l]) add_variant(flat.locus_variant[l], uint64_t(locus_counts[l * 4]) + locus_counts[l * 4 + 3], locus_counts[l * 4 + 1], locus_counts[l * 4 + 2]);
+    for (size_t m = 0; m < M; ++m)
+      for (size_t a = 0; a < 3; ++a)
+        add_variant(flat.multi_variant[m * 3 + a], multi_counts[(m * 3 + a) * 3], multi_counts[(m * 3 + a) * 3 + 1], multi_counts[(m * 3 + a) * 3 + 2]);
+
+  }
+
+  for (auto const& [genome_id, freq_array] : genome_update) {
+    auto& target = genome_fws_map_[genome_id];
+    for (size_t b = 0; b < FWS_FREQUENCY_ARRAY_SIZE; ++b) target[b] += freq_array[b];
+  }
+  for (auto const& [hgvs, summary] : variant_update) variant_fws_map_[hgvs] += summary;
+  return true;
+
+}
+
+namespace {
+
+// "hom / het" of the two CSV files: 0 when there is no heterozygous entry
+double ratioOrZero(size_t numerator, size_t denominator) {
+  return denominator > 0 ? static_cast<double>(numerator) / static_cast<double>(denominator) : 0.0;
+}
+
+}  // namespace
+
+void kga::CalcFwsB200::writeGenomeResults(const std::shared_ptr<const Pf7FwsResource>& Pf7_fws_ptr, const std::string& file_name) const {
+
+  std::ofstream out(file_name);
+  if (not out.good()) {
+    ExecEnv::log().error("CalcFwsB200::writeGenomeResults; Unable to open results file: {}", file_name);
+    return;
+  }
+  static const char* const kBinColumns[] = {"LowerFreq", "UpperFreq", "Hom/Het", "Minor Hom/Het", "Variant Count", "Hom Ref (A;A)",
+                                            "Het Ref Minor (A;a)", "Hom Minor (a;a)"};
+  out << "Genome,FWS";
+  for (size_t b = 0; b < FWS_FREQUENCY_ARRAY_SIZE; ++b) for (const char* column : kBinColumns) out << ',' << column;
+  out << '\n';
+  for (auto const& [genome_id, freq_array] : genome_fws_map_) {
+    out << genome_id << ',' << Pf7_fws_ptr->getFWS(genome_id);
+    for (size_t b = 0; b < FWS_FREQUENCY_ARRAY_SIZE; ++b) {
+      const AlleleSummmary& s = freq_array[b];
+      auto const [lower, upper] = binRange(b);
+      out << ',' << lower << ',' << upper
+          << ',' << ratioOrZero(s.minorHomozygous_ + s.referenceHomozygous_, s.minorHeterozygous_)
+          << ',' << ratioOrZero(s.minorHomozygous_, s.minorHeterozygous_)
+          << ',' << (s.minorHeterozygous_ + s.minorHomozygous_)
+          << ',' << s.referenceHomozygous_ << ',' << s.minorHeterozygous_ << ',' << s.minorHomozygous_;
+    }
+    out << '\n';
+  }
+
+}
+
+void kga::CalcFwsB200::writeVariantResults(const std::string& file_name) const {
+
+  std::ofstream out(file_name);
+  if (not out.good()) {
+    ExecEnv::log().error("CalcFwsB200::writeVariantResults; Unable to open results file: {}", file_name);
+    return;
+  }
+  out << "Variant,Hom/Het,Minor Hom/Het,Genome Count,Hom Ref (A;A),Het Ref Minor (A;a),Hom Minor (a;a)\n";
+  for (auto const& [hgvs, s] : variant_fws_map_)
+    out << hgvs << ',' << ratioOrZero(s.minorHomozygous_ + s.referenceHomozygous_, s.minorHeterozygous_)
+        << ',' << ratioOrZero(s.minorHomozygous_, s.minorHeterozygous_)
+        << ',' << (s.minorHeterozygous_ + s.minorHomozygous_)
+        << ',' << s.referenceHomozygous_ << ',' << s.minorHeterozygous_ << ',' << s.minorHomozygous_ << '\n';
+
+}

@@ -12,6 +12,7 @@
 #ifndef KGA_ANALYSIS_PFEMP_B200_H
 #define KGA_ANALYSIS_PFEMP_B200_H
 
+#include "kga_analysis_PfEMP_FWS.h"
 #include "kga_analysis_PfEMP_heterozygous.h"
 #include "kgl_pf7_fws_parser.h"
 #include "kgl_pf7_sample_parser.h"
@@ -67,6 +68,42 @@ private:
   constexpr static const size_t MINIMUM_LOCATION_SAMPLES_ = 20;
 
   [[nodiscard]] bool ensureContext();
+
+};
+
+// Mirrors kga::CalcFWS (kga_analytic/kga_PfEMP/kga_analysis_PfEMP_FWS.h:32-56): same method names, the reference's own map types
+// (GenomeFWSMap: genome -> eleven AlleleSummmary records, one per allele-frequency bin; VariantFWSMap: HGVS -> AlleleSummmary) and
+// CSV layouts. Underneath: one flatten per contig (PopulationFlattener::flattenSelf: the population is its own locus list, every
+// allele carries its INFO AF), then kgl_b200_run_binned_genome_counts (all eleven P7FrequencyFilter bins, the alleles of
+// multi-allelic offsets included), kgl_b200_run_allele_count and kgl_b200_run_multi_allele_count for the per-variant map.
+// The matrix holds SNPs, up to three alleles per offset and up to two variants per genome and offset: calcFwsStatistics refuses
+// (returns false, nothing recorded) a population with anything else -- FilterPf7::qualityFilter's SNP filter
+// (kga_analysis_lib_PfFilter.cpp:83-86) yields populations it accepts.
+class CalcFwsB200 {
+
+public:
+
+  CalcFwsB200() = default;
+  ~CalcFwsB200();
+  CalcFwsB200(const CalcFwsB200&) = delete;
+  CalcFwsB200& operator=(const CalcFwsB200&) = delete;
+
+  // CalcFWS::calcFwsStatistics (kga_analysis_PfEMP_FWS.cpp:15-39), accumulating over calls as the reference does.
+  [[nodiscard]] bool calcFwsStatistics(const std::shared_ptr<const PopulationDB>& population);
+  [[nodiscard]] const GenomeFWSMap& getGenomeMap() const { return genome_fws_map_; }
+  [[nodiscard]] const VariantFWSMap& getVariantMap() const { return variant_fws_map_; }
+  // CalcFWS::writeGenomeResults (:147-240) and writeVariantResults (:243-310): same columns, same formatting.
+  void writeGenomeResults(const std::shared_ptr<const Pf7FwsResource>& Pf7_fws_ptr, const std::string& file_name) const;
+  void writeVariantResults(const std::string& file_name) const;
+
+  // The eleven bins of CalcFWS::getFrequency (:104-145).
+  static std::pair<double, double> binRange(size_t bin);
+
+private:
+
+  GenomeFWSMap genome_fws_map_;
+  VariantFWSMap variant_fws_map_;
+  kgl_b200_ctx* context_{nullptr};
 
 };
 

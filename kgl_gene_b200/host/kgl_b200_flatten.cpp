@@ -97,6 +97,10 @@ void finishLocusTable(b200::FlatContig& flat, const LocusTable& table) {
   for (size_t m = 0; m < M; ++m)
     for (size_t k = 0; k < b200::kSuperPopCount; ++k)
       for (size_t a = 0; a < kSlots; ++a) flat.multi_af[(k * M + m) * kSlots + a] = table.multi_af_rows[m][k * kSlots + a];
+  flat.locus_variant = table.locus_allele;
+  flat.multi_variant.assign(M * kSlots, nullptr);
+  for (size_t m = 0; m < M; ++m)
+    for (size_t a = 0; a < table.multi_alleles[m].size() && a < kSlots; ++a) flat.multi_variant[m * kSlots + a] = table.multi_alleles[m][a];
   if (flat.too_many_alleles_skipped > 0)
     ExecEnv::log().warn("PopulationFlattener; contig: {}, {} offsets with more than three alt alleles left out of the locus table",
                         flat.contig_id, flat.too_many_alleles_skipped);

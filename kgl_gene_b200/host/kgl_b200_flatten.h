@@ -26,6 +26,7 @@
 
 #include <cstdint>
 #include <functional>
+#include <memory>
 #include <optional>
 #include <string>
 #include <vector>
@@ -52,6 +53,10 @@ struct FlatContig {
   std::vector<uint32_t> multi_rows;
   std::vector<float> multi_af;
   std::vector<uint8_t> multi_cells;
+  // the variants behind the rows (for consumers that report per variant, e.g. CalcFWS' HGVS-keyed map): the allele of an ordinary
+  // row, [n_multi][3] alleles of a multi-allelic one (nullptr = slot not used)
+  std::vector<std::shared_ptr<const Variant>> locus_variant;
+  std::vector<std::shared_ptr<const Variant>> multi_variant;
   size_t too_many_alleles_skipped{0};                      // offsets with more than three distinct alt alleles (not a SNP locus)
   size_t non_snp_entries{0};                               // flattenSelf: variant entries that are not SNPs (not in the matrix)
   size_t mixed_phase_cells{0};                             // cells whose phase pattern contradicts `unphased` (coded 3)

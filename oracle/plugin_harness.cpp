@@ -19,6 +19,7 @@
 #include "kga_analysis_inbreed.h"
 #include "kga_analysis_inbreed_b200.h"
 #include "kga_analysis_pfemp_b200.h"
+#include "kga_analysis_PfEMP_FWS.h"
 #include "kga_analysis_PfEMP_heterozygous.h"
 #include "kgl_variant_factory_1000_impl.h"
 #include "kgl_variant_factory_vcf_evidence_analysis.h"
@@ -142,6 +143,11 @@ void runPfEMP(const kglflat::Flat& flat) {
     std::filesystem::create_directories(g_opt.work_dir + "/PFEMP");
     reference.write_variant_results(g_opt.work_dir + "/PFEMP/hetero_homo.csv", summary);
     std::fprintf(stderr, "[plugin] PFEMP reference: wrote %s/PFEMP/hetero_homo.csv\n", g_opt.work_dir.c_str());
+    // CalcFWS as kga::PfEMPAnalysis drives it (kga_analysis_PfEMP.cpp:104 calcFwsStatistics; the two writers in finalizeAnalysis)
+    kga::CalcFWS calc_fws;
+    calc_fws.calcFwsStatistics(built.diploid);
+    calc_fws.writeGenomeResults(fws_ptr, g_opt.work_dir + "/PFEMP/fws_genome.csv");
+    calc_fws.writeVariantResults(g_opt.work_dir + "/PFEMP/fws_variant.csv");
   }
   if (g_opt.run_b200) {
     kga::HeteroHomoB200 product;
@@ -151,6 +157,13 @@ void runPfEMP(const kglflat::Flat& flat) {
     std::filesystem::create_directories(g_opt.work_dir + "/PFEMP_B200");
     product.write_variant_results(g_opt.work_dir + "/PFEMP_B200/hetero_homo.csv", summary);
     std::fprintf(stderr, "[plugin] PFEMP_B200: wrote %s/PFEMP_B200/hetero_homo.csv\n", g_opt.work_dir.c_str());
+    kga::CalcFwsB200 calc_fws;
+    if (calc_fws.calcFwsStatistics(built.diploid)) {
+      calc_fws.writeGenomeResults(fws_ptr, g_opt.work_dir + "/PFEMP_B200/fws_genome.csv");
+      calc_fws.writeVariantResults(g_opt.work_dir + "/PFEMP_B200/fws_variant.csv");
+    } else {
+      std::fprintf(stderr, "[plugin] PFEMP_B200: CalcFwsB200 refused the population\n");
+    }
   }
 }
 

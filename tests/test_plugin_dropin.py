@@ -168,6 +168,17 @@ def test_plugin_unphased_population(tmp_path):
         assert np.allclose(vals, r_new[g][1], rtol=2e-6, atol=2e-8)
 
 
+def _compare_fws_csv(work, tag):
+    """CalcFwsB200 (host/kga_analysis_pfemp_b200.cpp over kgl_b200_run_binned_genome_counts, ..._allele_count, ..._multi_allele_count)
+    against the reference's CalcFWS (kga_analysis_PfEMP_FWS.cpp, calcFwsStatistics + the two writers): per-genome records in the
+    eleven allele-frequency bins and the HGVS-keyed per-variant records, both CSV files byte for byte."""
+    for name in ("fws_genome.csv", "fws_variant.csv"):
+        ref = open(os.path.join(work, "PFEMP", name)).read().splitlines()
+        new = open(os.path.join(work, "PFEMP_B200", name)).read().splitlines()
+        assert len(ref) > 1 and ref[0] == new[0], (tag, name)
+        assert ref == new, (tag, name, len(ref), len(new), [(a, b) for a, b in zip(ref, new) if a != b][:2])
+
+
 @needs_harness
 @pytest.mark.gpu
 @pytest.mark.parametrize("unphased", [True, False], ids=["pf7-unphased", "phased"])
@@ -187,6 +198,8 @@ def test_pfemp_hetero_homo_csv_equals_reference_writer(tmp_path, unphased):
     fis = np.array([float(ln.split(",")[2]) for ln in ref[1:]])
     het_diff = np.array([int(ln.split(",")[14]) for ln in ref[1:]])
     assert np.count_nonzero(fis) > 100 and het_diff.sum() > 0          # F_IS is exercised; so is "Het Diff Minor (a;b)"
+    _compare_fws_csv(work, unphased)
+    assert len(open(os.path.join(work, "PFEMP", "fws_variant.csv")).read().splitlines()) > 2500      # one line per variant: more than the offsets
 
 
 @needs_harness
@@ -205,6 +218,7 @@ def test_pfemp_hetero_homo_csv_on_random_populations(tmp_path, seed):
     ref = open(os.path.join(work, "PFEMP", "hetero_homo.csv")).read().splitlines()
     new = open(os.path.join(work, "PFEMP_B200", "hetero_homo.csv")).read().splitlines()
     assert len(ref) > 1 and ref == new, (seed, n, l, pop.n_multi, [i for i, (a, b) in enumerate(zip(ref, new)) if a != b][:3])
+    _compare_fws_csv(work, (seed, n, l, pop.n_multi))
 
 
 def _carried_alleles(pop, col):
