@@ -221,6 +221,25 @@ def test_pfemp_hetero_homo_csv_on_random_populations(tmp_path, seed):
     _compare_fws_csv(work, (seed, n, l, pop.n_multi))
 
 
+@needs_harness
+@pytest.mark.gpu
+def test_calc_fws_b200_refuses_what_the_matrix_cannot_hold(tmp_path):
+    """A genome with three variants at one offset (side cell 0xFF: the flat form does not say which): CalcFwsB200 refuses the
+    population instead of writing records that differ from the reference's; HeteroHomoB200, which only needs the number of entries
+    there, still equals the reference file."""
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    pop, _ = make_population(60, 800, seed=51, spectrum="sfs", unphased=True)
+    add_multi_allelic(pop, 120, seed=52, three_rate=0.02)
+    assert (pop.multi_cells == 0xFF).any()
+    work = run_harness(str(tmp_path), pop, "--pfemp")
+    assert os.path.exists(os.path.join(work, "PFEMP", "fws_genome.csv"))
+    assert not os.path.exists(os.path.join(work, "PFEMP_B200", "fws_genome.csv")) and not os.path.exists(os.path.join(work, "PFEMP_B200", "fws_variant.csv"))
+    assert "more than two variants at one offset" in open(os.path.join(str(tmp_path), "harness.log")).read()
+    ref = open(os.path.join(work, "PFEMP", "hetero_homo.csv")).read().splitlines()
+    new = open(os.path.join(work, "PFEMP_B200", "hetero_homo.csv")).read().splitlines()
+    assert ref == new
+
+
 def _carried_alleles(pop, col):
     """{offset: list per genome of the sorted frequency values (column `col`) of the alleles the genome carries there}."""
     out = {}
