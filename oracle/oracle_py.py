@@ -257,7 +257,7 @@ def have_reference_harness() -> bool:
 
 
 def run_reference(pop, algos=("Simple", "RitlandLocus", "HallME", "Loglikelihood"), spacing=0, min_af=0.0, max_af=1.0,
-                  lower=0, upper=10**9, grid=0, threads=0, variantdb=True, seed=None, repeat=1, timeout=3600, fws=False):
+                  lower=0, upper=10**9, grid=0, threads=0, variantdb=True, seed=None, repeat=1, timeout=3600, fws=False, count=None):
     """Runs the reference's own code (oracle/_ref/kgl_ref_harness) on `pop`; returns the dumped arrays."""
     from kgl_gene_b200.flatfile import read_tensors
     with tempfile.TemporaryDirectory() as d:
@@ -269,6 +269,8 @@ def run_reference(pop, algos=("Simple", "RitlandLocus", "HallME", "Loglikelihood
             cmd.append("--no-variantdb")
         if fws:
             cmd.append("--fws")
+        if count is not None:
+            cmd += ["--count", str(int(count))]
         if seed is not None:
             cmd += ["--seed", str(int(seed))]
         if repeat > 1:

@@ -114,6 +114,18 @@ void run() {
     out.addU32(std::string("selected_offsets_") + kSuperPops[k], {selected.size()}, selected);
   }
 
+  // ---- count-limited windows: RetrieveLociiVector::getLociiCount (kga_analysis_inbreed_locus.cpp:159-183), the walk the window
+  // loop of InbreedingAnalysis::populationInbreeding makes (kga_analysis_inbreed_diploid.cpp:47-73) -- only with --count
+  if (g_opt.count < 1000000000) {
+    auto const& [af_genome_id, af_genome_ptr] = *af_population->getMap().begin();
+    auto const& [af_contig_id, af_contig_ptr] = *af_genome_ptr->getMap().begin();
+    for (int k = 0; k < 6; ++k) {
+      std::vector<kgl::ContigOffset_t> counted = kga::RetrieveLociiVector::getLociiCount(af_contig_ptr, kSuperPops[k], args);
+      std::vector<uint32_t> offsets32(counted.begin(), counted.end());
+      out.addU32(std::string("counted_offsets_") + kSuperPops[k], {offsets32.size()}, offsets32);
+    }
+  }
+
   // ---- estimators: one task per genome on the reference thread pool -----------------------------------
   if (g_opt.grid > 1) {
     for (size_t i = 0; i < g_opt.grid; ++i) kglref::g_grid.push_back(-0.5 + double(i) / double(g_opt.grid - 1));

@@ -265,9 +265,14 @@ def test_oracle_pinned_on_random_populations(seed):
     if rng.integers(0, 2):
         lo, hi = sorted(rng.integers(0, l, size=2).tolist())
         sel_kw.update(lower=int(pop.offsets[lo]), upper=int(pop.offsets[hi]))
-    ref = O.run_reference(pop, grid=9, fws=True, seed=int(rng.integers(1, 100)), **sel_kw)
+    count = int(rng.choice([1, 7, 100, 5000]))
+    ref = O.run_reference(pop, grid=9, fws=True, seed=int(rng.integers(1, 100)), count=count, **sel_kw)
     ref.pop("_stderr", None)
     sel_kw.setdefault("lower", 0); sel_kw.setdefault("upper", 10**9)
+    # the count-limited walk of the window loop (RetrieveLociiVector::getLociiCount, kga_analysis_inbreed_locus.cpp:159-183)
+    counted = O.select_all_pops(pop, count=count, mode=1, **sel_kw)
+    for k, sp in enumerate(SUPER_POPS):
+        assert np.array_equal(pop.offsets[counted[k] == 1], ref["counted_offsets_" + sp]), (seed, sp, count)
     case = (f"random-{seed}", pop, ref, sel_kw)
     test_locus_selection_matches_reference(case)
     for algo in ("Simple", "RitlandLocus"):
