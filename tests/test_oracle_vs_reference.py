@@ -282,3 +282,44 @@ def test_oracle_pinned_on_random_populations(seed):
     test_allele_summaries_match_variantdb(case)
     test_calc_fws_restatement_matches_reference(case)
     test_hetero_homo_rule_matches_reference(case)
+
+
+@pytest.mark.skipif(not O.have_reference_harness(), reason="oracle/_ref/kgl_ref_harness not built (make -C oracle ref)")
+def test_loglikelihood_maximiser_against_the_reference_optimiser_on_random_populations():
+    """Loglikelihood is parity-unpinned (nlopt's Nelder-Mead from random starts). What can be pinned: on random
+    populations the coefficient the reference returns lies within its own tolerance (xtol_abs 1e-6) of the oracle's maximiser for
+    almost every genome; where it does not, the oracle's point has the higher likelihood -- except for a few genomes of UNPHASED
+    populations, where the reference's simplex leaves the feasible region and finds a higher value of the clamped objective
+    (calc.cpp:108; the waiver of DESIGN 8). A campaign of 60 populations (KGL_ORACLE_FUZZ_SEEDS=1..60): 2,825 genomes, 2,790
+    within 2e-6, 29 with the oracle strictly better, 6 (all unphased) with the clamped objective higher at the reference's point."""
+    import os
+    from kgl_gene_b200.synth import add_multi_allelic, make_population
+    total = close = better = outside = 0
+    for seed in [int(x) for x in os.environ.get("KGL_ORACLE_FUZZ_SEEDS", "1,2,3,4,5,6,7,8").split(",")]:
+        rng = np.random.default_rng(1000 + seed)
+        n, l = int(rng.choice([20, 45, 70])), int(rng.choice([400, 1500]))
+        unphased = bool(rng.integers(0, 3) == 0)
+        pop, _ = make_population(n, l, seed=int(rng.integers(1, 10**6)), spectrum=str(rng.choice(["sfs", "dense"])),
+                                 missing_rate=float(rng.choice([0.0, 0.02])), missing_af_rate=float(rng.choice([0.0, 0.05])),
+                                 grouped=bool(rng.integers(0, 2)), unphased=unphased)
+        if rng.integers(0, 2):
+            add_multi_allelic(pop, int(rng.choice([10, l // 8])), seed=int(rng.integers(1, 10**6)))
+        sel_kw = dict(spacing=int(rng.choice([0, 15])), min_af=float(rng.choice([0.0, 0.01])))
+        ref = O.run_reference(pop, algos=("Loglikelihood",), seed=int(rng.integers(1, 100)), variantdb=False, **sel_kw)
+        sel = O.select_all_pops(pop, **sel_kw)
+        opt = O.inbreed(pop, sel, "Loglikelihood")["inbred_allele_sum"]
+        got = ref["Loglikelihood_coeff"]
+        for g in np.flatnonzero(ref["genome_present"] == 1):
+            if not (np.isfinite(got[g]) and np.isfinite(opt[g])):
+                continue
+            total += 1
+            if abs(got[g] - opt[g]) < 2e-6:
+                close += 1
+                continue
+            ll = O.loglik_grid(pop, sel, np.array([opt[g], got[g]]))[g]
+            if ll[0] >= ll[1] - 1e-9 * max(1.0, abs(ll[1])):
+                better += 1
+            else:
+                outside += 1
+                assert unphased, (seed, int(g), opt[g], got[g], ll)
+    assert total > 200 and close >= 0.97 * total and outside <= 0.01 * total, (total, close, better, outside)
